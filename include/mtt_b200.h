@@ -1,0 +1,214 @@
+/*
+ * mtt_b200.h -- plain-C ABI of the B200-native MultiTypeTree likelihood hot path.
+ *
+ * This is the drop-in boundary: what a BEAST 2 plugin binds through Panama FFM / JNI (see
+ * INTEGRATION.md and java/) in place of the reference's Java + jblas code.  Plain pointers
+ * and sizes only; no torch / CUDA / JNI types.  Each entry point cites the reference
+ * interface (file:line, relative to tgvaughan/MultiTypeTree v8.1.0 src/multitypetree/) it
+ * replaces.
+ *
+ * Conventions
+ *   - return 0 (MTT_OK) on success, < 0 on API / CUDA failure (text via mtt_last_error);
+ *     never aborts, never throws, no callbacks.
+ *   - numerical failure is a VALUE, as in the reference: logP may be -inf, and per-item
+ *     status codes MTT_ST_* report what the Java code signals with -Infinity / exceptions.
+ *   - caller owns every host buffer for the duration of the call only; the library owns all
+ *     device memory, tied to the ctx.  One ctx per chain/thread (a ctx is not re-entrant);
+ *     separate ctxs are independent.  Calls block until results are on the host unless the
+ *     name ends in _dev (device pointers, asynchronous on the ctx stream).
+ *   - there is NO CPU fallback: without a CUDA device mtt_ctx_create fails.
+ *
+ * Flattened MultiTypeTree ("tree SoA"; replaces the object graph of
+ * evolution/tree/MultiTypeNode.java:33-36 + MultiTypeTree.java:256-264).  A batch of B trees
+ * is stored back to back:
+ *   nodeOff [B+1]  int64   node offsets; tree b owns nodes [nodeOff[b], nodeOff[b+1]),
+ *                          nNodes = 2*nLeaves-1, nodes [0,nLeaves) are the leaves (BEAST Nr
+ *                          numbering, relied on by operators/NodeRetype.java:36-37)
+ *   height  [nodes] f64    Node.getHeight()
+ *   parent  [nodes] int32  tree-local parent Nr, -1 for the root (may be NULL when neither
+ *                          validity checking nor peeling is requested)
+ *   nodeType[nodes] uint8  MultiTypeNode.getNodeType()           (MultiTypeNode.java:100-102)
+ *   chgCount[nodes] uint16 MultiTypeNode.getChangeCount()        (:43-45); the root entry
+ *                          must be 0 unless parent[] is given (root-branch changes are
+ *                          ignored, distributions/StructuredCoalescentTreeDensity.java:161-162)
+ *   chgBase [B+1]  int64   offsets into chgTime/chgType; a tree's changes are stored node by
+ *                          node in Nr order, each branch youngest -> oldest
+ *   chgTime [changes] f64  MultiTypeNode.getChangeTime(idx)      (:65-67)
+ *   chgType [changes] uint8 MultiTypeNode.getChangeType(idx)     (:54-56)
+ * Compact integer widths are part of the contract: the density path is HBM/PCIe bound and
+ * these arrays ARE its traffic (12 bytes per event algorithmic).
+ */
+#ifndef MTT_B200_H
+#define MTT_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MTT_ABI_VERSION 1
+
+#define MTT_OK                0
+#define MTT_ERR_INVALID_ARG  -1
+#define MTT_ERR_CUDA         -2
+#define MTT_ERR_NO_DEVICE    -3
+#define MTT_ERR_TOO_LARGE    -4   /* a tree / model exceeds a documented kernel limit */
+#define MTT_ERR_STATE        -5   /* call order violated (e.g. logl before set_*) */
+
+#define MTT_MAX_DEMES        16   /* register/smem-resident d x d kernels */
+#define MTT_MAX_TREE_EVENTS  16384 /* nodes + changes per tree (density kernel, smem sort) */
+
+/* per-item status codes (values, not errors) */
+#define MTT_ST_OK                 0
+#define MTT_ST_NO_VALID_PATH      1  /* Pba == 0: NoValidPathException,
+                                        operators/UniformizationRetypeOperator.java:137-138 */
+#define MTT_ST_PBA_RUBBISH        2  /* Pba > 1 || Pba < 0 (:141-144, :267-270) -> -inf */
+#define MTT_ST_FB_FELL_THROUGH    3  /* forward-backward failure (:179-190) -> -inf */
+#define MTT_ST_NEEDS_POISSON_TAIL 4  /* steady-state tail (:96-102): the host Randomizer must
+                                        draw nVirt >= nVirt_out and resubmit with nVirtForced */
+#define MTT_ST_NEED_MORE_UNIFORMS 5  /* uniform window exhausted: resubmit with a longer one */
+#define MTT_ST_NEED_MORE_POWERS   6  /* internal (handled inside the library) */
+#define MTT_ST_SKIPPED            7  /* an earlier branch of the same job aborted */
+
+typedef struct mtt_ctx mtt_ctx;
+
+/* ------------------------------------------------------------------ context */
+
+/* device: CUDA ordinal, or -1 for the current device. */
+int mtt_ctx_create(int device, mtt_ctx **out);
+int mtt_ctx_destroy(mtt_ctx *ctx);
+/* last error text of this ctx (or of the failed mtt_ctx_create when ctx == NULL) */
+const char *mtt_last_error(const mtt_ctx *ctx);
+int mtt_abi_version(void);
+/* Run this ctx's work on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * the caller's torch stream, instead of the ctx's own stream.  NULL restores the own stream. */
+int mtt_ctx_set_stream(mtt_ctx *ctx, void *cuda_stream);
+int mtt_ctx_synchronize(mtt_ctx *ctx);
+/* number of kernels this ctx has launched so far (bench.py's gpu_launches) */
+int64_t mtt_ctx_launch_count(const mtt_ctx *ctx);
+/* page-lock / unlock a caller buffer so that host<->device copies run at full PCIe rate */
+int mtt_host_register(void *ptr, int64_t bytes);
+int mtt_host_unregister(void *ptr);
+
+/* ------------------------------------------------------------------ piece 1: density
+ * Replaces distributions/StructuredCoalescentTreeDensity.java:86-147 (calculateLogP),
+ * :153-248 (updateEventSequence) and evolution/tree/MultiTypeTree.java:396-429 (isValid),
+ * batched over B trees.  The migration model arrives already resolved to dense form (what
+ * evolution/tree/SCMigrationModel.java:252-268 getBackwardRate and :373-375 getPopSize
+ * return): m[nModels][d*d] row-major backward rates (diagonal ignored), N[nModels][d];
+ * nModels is 1 (shared by all trees) or B (one per tree).
+ *   logP [B]  out: log density; -inf when checkValidity != 0 and the tree is invalid (:90-91)
+ *   valid[B]  out (may be NULL): isValid() result, computed whenever parent != NULL
+ * Event extraction, time ordering and the interval scan all happen on the device. */
+int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                      const double *N, const int64_t *nodeOff, const double *height,
+                      const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
+                      const int64_t *chgBase, const double *chgTime, const uint8_t *chgType,
+                      int checkValidity, double *logP, uint8_t *valid);
+
+/* Same with every pointer a DEVICE pointer; asynchronous on the ctx stream.  Each array must
+ * be readable 16 bytes past its logical end (bulk-copy granularity). */
+int mtt_sc_logp_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                          const double *N, const int64_t *nodeOff, const double *height,
+                          const int32_t *parent, const uint8_t *nodeType,
+                          const uint16_t *chgCount, const int64_t *chgBase,
+                          const double *chgTime, const uint8_t *chgType, int checkValidity,
+                          double *logP, uint8_t *valid);
+/* Optional hint for the _dev entry: an upper bound on nodes + changes of any tree in later
+ * batches (0 = unknown).  With a bound <= 256 the large-tree kernel launch is skipped. */
+int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents);
+
+/* ------------------------------------------------------------------ piece 3: uniformization
+ * Replaces evolution/tree/SCMigrationModel.java:150-201 (updateMatrices), :404-473 (getRpowN /
+ * RpowSteadyN: the jblas mmul chain) and operators/UniformizationRetypeOperator.java:74-275
+ * (drawEventCount, retypeBranch, getBranchTypeProb: jblas expm + forward-backward sampling).
+ *
+ * A ctx holds nModels uniformization models (one per chain).  m is the dense backward-rate
+ * matrix as above; sym selects the symmetrised variant (useSymmetrizedRates,
+ * UniformizationRetypeOperator.java:41-43,118).  Setting a model drops its cached powers,
+ * like SCMigrationModel.java:187-198. */
+int mtt_unif_set_models(mtt_ctx *ctx, int nModels, int d, const double *m, int sym);
+
+/* Q, R (row-major d*d) and mu of one model, as getQ/getR/getMu(sym) return them. */
+int mtt_unif_get_matrices(mtt_ctx *ctx, int model, double *Q, double *R, double *mu);
+
+/* R^0 .. R^kmax of one model (out: (kmax+1)*d*d doubles, row-major), computed on the device
+ * with the reference's chain R^i = R^(i-1) * R and steady-state rule (every 10th power,
+ * SCMigrationModel.java:435-447).  *steadyN receives RpowSteadyN() (-1 if not steady within
+ * kmax); powers beyond the steady index repeat the last matrix (:422-426). */
+int mtt_unif_rpow(mtt_ctx *ctx, int model, int kmax, double *out, int *steadyN);
+
+/* expm(Q*L) for a batch of branch lengths (out: n*d*d doubles): the jblas
+ * MatrixFunctions.expm call of UniformizationRetypeOperator.java:132-134. */
+int mtt_unif_expm_batch(mtt_ctx *ctx, int64_t n, const int32_t *model, const double *L,
+                        double *out);
+
+/* getBranchTypeProb (:233-275) for nBranches branches.  Branch i runs from (tBottom,
+ * typeBottom) up to (tTop, typeTop) with the existing changes
+ * chgTime/chgType[chgOff[i] .. chgOff[i+1]).  status: MTT_ST_OK | MTT_ST_PBA_RUBBISH. */
+int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t nBranches, const int32_t *model,
+                               const double *tBottom, const double *tTop,
+                               const uint8_t *typeBottom, const uint8_t *typeTop,
+                               const int64_t *chgOff, const double *chgTime,
+                               const uint8_t *chgType, double *logProb, int32_t *status);
+
+/* retypeBranch (:116-225) for nJobs jobs.  A job is the sequence of branches
+ * [brOff[j], brOff[j+1]) retyped in order from ONE uniform stream
+ * uniforms[uOff[j] .. uOff[j+1]) -- e.g. the <= 3 branches of one NodeRetype proposal
+ * (operators/NodeRetype.java:52-56).  Uniforms are consumed in the reference's order
+ * (per branch: 1 for the event count, nVirt times, nVirt forward-backward draws).
+ * nVirtForced (may be NULL): >= 0 skips the event-count draw of that branch.
+ * Outputs per branch: nChg, changes written at outCap*branch (at most outCap of them),
+ * logProb, status, nVirt; per job: uUsed.  A branch with status NO_VALID_PATH /
+ * PBA_RUBBISH / FB_FELL_THROUGH / NEEDS_POISSON_TAIL / NEED_MORE_UNIFORMS stops its job;
+ * the job's later branches get MTT_ST_SKIPPED. */
+int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
+                          const int32_t *model, const double *tBottom, const double *tTop,
+                          const uint8_t *typeBottom, const uint8_t *typeTop,
+                          const int32_t *nVirtForced, const double *uniforms,
+                          const int64_t *uOff, int outCap, int32_t *nChg, double *outChgTime,
+                          uint8_t *outChgType, double *logProb, int32_t *status,
+                          int32_t *nVirt, int64_t *uUsed);
+
+/* ------------------------------------------------------------------ piece 2: peeling
+ * Replaces BEAST 2 core beast.base.evolution.likelihood.TreeLikelihood.calculateLogP +
+ * BeerLikelihoodCore as wired by the reference at examples/structuredCoalescent.xml:568-572
+ * and fxtemplates/MultiTypeTree.xml:184-197 (Inputs data, tree, siteModel, branchRateModel).
+ * 4-state (nucleotide) data. */
+typedef struct mtt_peel mtt_peel;
+
+/* nTips taxa, nPatterns site patterns owned by THIS handle (a pattern shard when sharded
+ * across GPUs), nCat site-rate categories. */
+int mtt_peel_create(mtt_ctx *ctx, int nTips, int64_t nPatterns, int nCat, mtt_peel **out);
+int mtt_peel_destroy(mtt_peel *h);
+/* states[nTips][nPatterns] (Alignment.getPattern; state >= 4 = gap / ambiguity code, treated
+ * as missing) and integer pattern weights (Alignment.getPatternWeight). */
+int mtt_peel_set_tip_states(mtt_peel *h, const int32_t *states);
+int mtt_peel_set_pattern_weights(mtt_peel *h, const int32_t *weights);
+/* SiteModel: category rates and proportions (already adjusted for pInv as BEAST's SiteModel
+ * does), root frequencies, proportion invariant; strict-clock branchRate. */
+int mtt_peel_set_site_model(mtt_peel *h, const double *catRates, const double *catProps,
+                            const double *freqs, double pInv, double branchRate);
+/* HKY substitution model (examples/structuredCoalescent.xml:534-539): transition matrices are
+ * evaluated on the device from node heights. */
+int mtt_peel_set_hky(mtt_peel *h, double kappa);
+/* log-likelihoods of B trees over this handle's patterns:
+ * parent/height [B][2*nTips-1] (tree SoA above).  logL[B] = sum_p weight_p * logL_p. */
+int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                        double *logL);
+/* same with explicit transition matrices mats[B][2*nTips-1][nCat][16] (row = parent state),
+ * for substitution models other than HKY (root entry unused). */
+int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,
+                             double *logL);
+/* device-pointer variant of mtt_peel_logl_batch (async on the ctx stream) */
+int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                            double *logL);
+/* per-pattern log-likelihoods of ONE tree (TreeLikelihood.getPatternLogLikelihoods) */
+int mtt_peel_pattern_logl(mtt_peel *h, const int32_t *parent, const double *height,
+                          double *patternLogL);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

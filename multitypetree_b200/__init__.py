@@ -1,0 +1,18 @@
+"""multitypetree_b200 -- B200-native likelihood hot path of the BEAST 2 MultiTypeTree package.
+
+The product is the CUDA library ``libmtt_b200.so`` behind the C-ABI of ``include/mtt_b200.h``;
+this package is the thin host-side mirror of the reference's plugin interface used by the
+tests, the benchmark and as a model for the Java shims in ``java/``.
+"""
+from ._lib import Context, MttError, default_context, lib  # noqa: F401
+from .tree import (MultiTypeTree, MultiTypeTreeFromNewick, TreeBatch,  # noqa: F401
+                   read_nexus_tree, simulate_trees, synthetic_model)
+from .migration_model import SCMigrationModel, TypeSet  # noqa: F401
+from .density import StructuredCoalescentTreeDensity, sc_logp_batch, tree_validity  # noqa: F401
+
+__all__ = [
+    "Context", "MttError", "default_context", "lib", "MultiTypeTree",
+    "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "simulate_trees",
+    "synthetic_model", "SCMigrationModel", "TypeSet", "StructuredCoalescentTreeDensity",
+    "sc_logp_batch", "tree_validity",
+]

@@ -1,0 +1,966 @@
+// k1_density.cu -- piece 1: batched structured-coalescent tree density on sm_100a.
+//
+// Replaces distributions/StructuredCoalescentTreeDensity.java:86-147 (calculateLogP),
+// :153-248 (updateEventSequence) and evolution/tree/MultiTypeTree.java:396-429 (isValid).
+//
+// The reference rebuilds a time-ordered event list with an O(E x active lineages) scan and
+// then walks it.  Here the flattened tree (height / nodeType / chgCount / chgTime / chgType,
+// include/mtt_b200.h) is turned into events, ordered and scanned inside one kernel:
+//
+//   k1_density_warp   one WARP per tree (E = nodes + changes <= 256).  Persistent warps; each
+//                     stages the NEXT tree's five array slices into shared memory with 1-D
+//                     bulk async copies (TMA engine, mbarrier completion) while it works on
+//                     the current one.  Events are ordered by a register-resident bitonic
+//                     network over packed 32-bit keys (24-bit quantised time | 8-bit event
+//                     index; shuffles across lanes), then repaired against the exact fp64
+//                     times (rare), then the per-deme lineage counts are obtained by a warp
+//                     prefix sum of packed 16-bit count fields and every lane integrates its
+//                     8 consecutive intervals.  fp64 throughout; no atomics on the result.
+//   k1_density_block  one CTA per tree for larger trees (E <= 16384), fed from the queue the
+//                     warp kernel fills: shared-memory bitonic sort of 64-bit keys
+//                     (38-bit quantised time | index | descriptor), same scan.
+//
+// HBM traffic per tree is the input arrays once (<= 12 B per event) + 8 B out: the kernel is
+// bound by HBM bandwidth and, at 2-deme/100-tip size, by the issue rate of the sort.
+#include "mtt_common.cuh"
+
+#include <math.h>
+
+namespace {
+
+constexpr int KIND_SAMPLE = 0, KIND_COALESCE = 1, KIND_MIGRATE = 2, KIND_NONE = 3;
+
+struct K1Params {
+    long long B;
+    int d;
+    long long nModels;
+    const double *m, *N;
+    const long long *nodeOff;
+    const double *height;
+    const int *parent;
+    const uint8_t *nodeType;
+    const uint16_t *chgCount;
+    const long long *chgBase;
+    const double *chgTime;
+    const uint8_t *chgType;
+    int checkValidity;
+    double *logP;
+    uint8_t *valid;
+    int *queue;        // [0] = count, [1..] = tree indices for the block kernel
+};
+
+// ---- per-model tables (shared memory) ------------------------------------------------
+struct ModelTab {
+    double inv2N[MTT_MAX_DEMES];     // 1 / (2 N_c)
+    double mu[MTT_MAX_DEMES];        // sum_{c' != c} m(c,c')
+    double logInvN[MTT_MAX_DEMES];   // log(1.0 / N_c)      (StructuredCoalescentTreeDensity.java:130)
+    double logM[MTT_MAX_DEMES * MTT_MAX_DEMES];   // log(m(c,c'))   (:136)
+};
+
+// cooperative fill by `nthr` threads with index `tid`
+__device__ __forceinline__ void fill_model_tab(ModelTab *t, const double *m, const double *N,
+                                               int d, int tid, int nthr)
+{
+    for (int c = tid; c < d; c += nthr) {
+        double Nc = N[c];
+        t->inv2N[c] = 1.0 / (2.0 * Nc);
+        t->logInvN[c] = log(1.0 / Nc);
+        double s = 0.0;
+        for (int cp = 0; cp < d; cp++)
+            if (cp != c)
+                s += m[c * d + cp];
+        t->mu[c] = s;
+    }
+    for (int e = tid; e < d * d; e += nthr)
+        t->logM[e] = (e / d == e % d) ? 0.0 : log(m[e]);
+}
+
+// lineage counts packed as 16-bit fields, 4 demes per 64-bit word
+template <int NW>
+struct Counts {
+    unsigned long long w[NW];
+};
+
+template <int NW>
+__device__ __forceinline__ void cnt_add(Counts<NW> &c, int deme, long long sgn)
+{
+    unsigned long long inc = (unsigned long long)sgn << (16 * (deme & 3));
+    if (NW == 1) {
+        c.w[0] += inc;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            if ((deme >> 2) == i)
+                c.w[i] += inc;
+    }
+}
+
+template <int NW>
+__device__ __forceinline__ void cnt_apply(Counts<NW> &c, uint32_t desc)
+{
+    int kind = (desc >> 10) & 3, from = (desc >> 5) & 31, to = desc & 31;
+    if (kind == KIND_SAMPLE)
+        cnt_add<NW>(c, from, 1);
+    else if (kind == KIND_COALESCE)
+        cnt_add<NW>(c, from, -1);
+    else if (kind == KIND_MIGRATE) {
+        cnt_add<NW>(c, from, -1);
+        cnt_add<NW>(c, to, 1);
+    }
+}
+
+// lambda = sum_c k_c (k_c - 1) / (2 N_c) + sum_c k_c sum_{c'!=c} m(c,c')     (:109-123)
+template <int NW>
+__device__ __forceinline__ double cnt_lambda(const Counts<NW> &c, const ModelTab *t, int d)
+{
+    double lambda = 0.0;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+#pragma unroll
+        for (int f = 0; f < 4; f++) {
+            int deme = i * 4 + f;
+            if (deme < d) {
+                int k = (int)((c.w[i] >> (16 * f)) & 0xffffu);
+                double kd = (double)k;
+                lambda += (kd * (kd - 1.0)) * t->inv2N[deme] + kd * t->mu[deme];
+            }
+        }
+    }
+    return lambda;
+}
+
+__device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, int d)
+{
+    int kind = (desc >> 10) & 3, from = (desc >> 5) & 31, to = desc & 31;
+    if (kind == KIND_COALESCE)
+        return t->logInvN[from];
+    if (kind == KIND_MIGRATE)
+        return t->logM[from * d + to];
+    return 0.0;
+}
+
+// =====================================================================================
+// warp-per-tree kernel
+// =====================================================================================
+constexpr int W_EMAX = 512;               // largest tree (nodes + changes) on the warp path
+constexpr int W_WARPS = 8;                // warps per CTA
+constexpr int W_TIME_BYTES = 8 * W_EMAX + 64;
+constexpr int W_TYPE_BYTES = W_EMAX + 64;
+constexpr int W_CNT_BYTES = 2 * W_EMAX + 32;
+constexpr int W_PAR_BYTES = 4 * W_EMAX + 32;
+
+template <bool HAS_PARENT>
+struct WarpStage {
+    alignas(16) unsigned char time[W_TIME_BYTES];   // heights | change times
+    alignas(16) unsigned char type[W_TYPE_BYTES];   // node types | change types
+    alignas(16) unsigned char cnt[W_CNT_BYTES];     // change counts
+    alignas(16) unsigned char par[HAS_PARENT ? W_PAR_BYTES : 16];
+};
+
+template <bool HAS_PARENT>
+struct WarpSmem {
+    WarpStage<HAS_PARENT> st[2];
+    alignas(8) unsigned long long bar[2];
+    alignas(8) uint16_t desc[W_EMAX];
+};
+
+struct TreeSpan {
+    long long n0, c0;
+    int n, M;
+};
+
+__device__ __forceinline__ TreeSpan load_span(const K1Params &p, long long t)
+{
+    TreeSpan s;
+    if (t < p.B) {
+        s.n0 = p.nodeOff[t];
+        s.n = (int)(p.nodeOff[t + 1] - s.n0);
+        s.c0 = p.chgBase[t];
+        s.M = (int)(p.chgBase[t + 1] - s.c0);
+    } else {
+        s.n0 = s.c0 = 0;
+        s.n = s.M = 0;
+    }
+    return s;
+}
+
+// A slice [src, src+bytes) is staged as its 16 B-aligned superset: `a` leading pad bytes,
+// `sz` total bytes (a multiple of 16; 0 for an empty slice).
+__device__ __forceinline__ void slice_of(const void *src, uint32_t bytes, uint32_t &a,
+                                         uint32_t &sz)
+{
+    a = (uint32_t)((uintptr_t)src & 15);
+    sz = bytes ? ((a + bytes + 15u) & ~15u) : 0u;
+}
+
+// byte layout of a staged tree inside a WarpStage
+struct StageLayout {
+    uint32_t hOff, cOff, tOff, ctOff, kOff, pOff;     // where the data starts
+    uint32_t szH, szC, szT, szCT, szK, szP;           // bulk-copy sizes
+};
+
+template <bool HAS_PARENT>
+__device__ __forceinline__ StageLayout make_layout(const K1Params &p, const TreeSpan &s)
+{
+    StageLayout L;
+    uint32_t a;
+    slice_of(p.height + s.n0, 8u * s.n, a, L.szH);
+    L.hOff = a;
+    slice_of(p.chgTime + s.c0, 8u * s.M, a, L.szC);
+    L.cOff = L.szH + a;
+    slice_of(p.nodeType + s.n0, (uint32_t)s.n, a, L.szT);
+    L.tOff = a;
+    slice_of(p.chgType + s.c0, (uint32_t)s.M, a, L.szCT);
+    L.ctOff = L.szT + a;
+    slice_of(p.chgCount + s.n0, 2u * s.n, a, L.szK);
+    L.kOff = a;
+    L.pOff = 0;
+    L.szP = 0;
+    if (HAS_PARENT) {
+        slice_of(p.parent + s.n0, 4u * s.n, a, L.szP);
+        L.pOff = a;
+    }
+    return L;
+}
+
+// one elected lane: arm the stage's mbarrier and launch the bulk copies
+template <bool HAS_PARENT>
+__device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
+                                           WarpStage<HAS_PARENT> *st, uint64_t *bar)
+{
+    const StageLayout L = make_layout<HAS_PARENT>(p, s);
+    mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szT + L.szCT + L.szK + L.szP);
+    bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
+    if (L.szC) {
+        bulk_g2s(st->time + L.szH, (const unsigned char *)(p.chgTime + s.c0) - (L.cOff - L.szH),
+                 L.szC, bar);
+        bulk_g2s(st->type + L.szT, (const unsigned char *)(p.chgType + s.c0) - (L.ctOff - L.szT),
+                 L.szCT, bar);
+    }
+    bulk_g2s(st->type, (const unsigned char *)(p.nodeType + s.n0) - L.tOff, L.szT, bar);
+    bulk_g2s(st->cnt, (const unsigned char *)(p.chgCount + s.n0) - L.kOff, L.szK, bar);
+    if (HAS_PARENT)
+        bulk_g2s(st->par, (const unsigned char *)(p.parent + s.n0) - L.pOff, L.szP, bar);
+}
+
+__device__ __forceinline__ void ce_u32(uint32_t &a, uint32_t &b)
+{
+    const uint32_t lo = min(a, b), hi = max(a, b);
+    a = lo;
+    b = hi;
+}
+
+// Bitonic sort of 32*EPL keys held EPL per lane; position = EPL * lane + r.  Every
+// compare-exchange is "lower position keeps the minimum": each merge starts with the
+// reflected partner, followed by ordinary half cleaners (no direction flags).
+template <int EPL>
+__device__ __forceinline__ void warp_sort(uint32_t (&v)[EPL], int lane)
+{
+    // blocks of 2 .. EPL positions: inside the lane
+#pragma unroll
+    for (int size = 2; size <= EPL; size <<= 1) {
+#pragma unroll
+        for (int r = 0; r < EPL; r++) {
+            const int q = r ^ (size - 1);
+            if (q > r)
+                ce_u32(v[r], v[q]);
+        }
+#pragma unroll
+        for (int s = size >> 2; s >= 1; s >>= 1) {
+#pragma unroll
+            for (int r = 0; r < EPL; r++)
+                if ((r & s) == 0)
+                    ce_u32(v[r], v[r | s]);
+        }
+    }
+    // blocks of 2 .. 32 lanes
+#pragma unroll
+    for (int lanes = 2; lanes <= 32; lanes <<= 1) {
+        {   // reflected partner: lane ^ (lanes - 1), register EPL-1-r
+            const bool lower = (lane & (lanes >> 1)) == 0;
+            uint32_t t[EPL];
+#pragma unroll
+            for (int r = 0; r < EPL; r++)
+                t[r] = __shfl_xor_sync(FULL_MASK, v[EPL - 1 - r], lanes - 1);
+#pragma unroll
+            for (int r = 0; r < EPL; r++)
+                v[r] = lower ? min(v[r], t[r]) : max(v[r], t[r]);
+        }
+#pragma unroll
+        for (int s = lanes >> 2; s >= 1; s >>= 1) {      // half cleaners across lanes
+            const bool lower = (lane & s) == 0;
+#pragma unroll
+            for (int r = 0; r < EPL; r++) {
+                const uint32_t t = __shfl_xor_sync(FULL_MASK, v[r], s);
+                v[r] = lower ? min(v[r], t) : max(v[r], t);
+            }
+        }
+#pragma unroll
+        for (int s = EPL >> 1; s >= 1; s >>= 1) {        // half cleaners inside the lane
+#pragma unroll
+            for (int r = 0; r < EPL; r++)
+                if ((r & s) == 0)
+                    ce_u32(v[r], v[r | s]);
+        }
+    }
+}
+
+__device__ __forceinline__ bool ce_td(double &ta, uint32_t &da, double &tb, uint32_t &db)
+{
+    if (ta > tb) {
+        const double t = ta; ta = tb; tb = t;
+        const uint32_t d = da; da = db; db = d;
+        return true;
+    }
+    return false;
+}
+
+// One staged tree, EPL events per lane (E <= 32 * EPL).  Returns the warp-reduced logP in
+// lane 0; `ok` is the validity verdict (all lanes).
+template <int NW, bool HAS_PARENT, int EPL>
+__device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
+                                               const StageLayout &L, uint16_t *desc, int n, int M,
+                                               const ModelTab *tab, int d, int lane, bool &okOut)
+{
+    constexpr int IDX_BITS = (EPL == 8) ? 8 : 9;
+    constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;   // all-ones is the padding key
+    const int E = n + M;
+    const int nLeaves = (n + 1) >> 1;
+    const double *sH = reinterpret_cast<const double *>(st->time + L.hOff);
+    const double *sC = reinterpret_cast<const double *>(st->time + L.cOff);
+    const uint8_t *sT = st->type + L.tOff;
+    const uint8_t *sCT = st->type + L.ctOff;
+    const uint16_t *sK = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);
+    const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
+
+    // ---- phase A: descriptors (node-centric), validity
+    bool ok = true;
+    int carry = 0;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+        const int e = lane + 32 * k;
+        if (32 * k < n) {                                    // warp-uniform
+            int c = (e < n) ? (int)sK[e] : 0;
+            int incl = c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o)
+                    incl += v;
+            }
+            const int off = carry + incl - c;
+            carry += __shfl_sync(FULL_MASK, incl, 31);
+            if (off + c > M) {                               // inconsistent chgCount / chgBase
+                c = max(0, M - off);
+                ok = false;
+            }
+            if (e < n) {
+                int type = sT[e];
+                desc[e] = (uint16_t)(((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 |
+                                     type << 5);
+                const int par = HAS_PARENT ? sP[e] : 0;
+                const bool isRoot = HAS_PARENT && par < 0;
+                double lastT = sH[e];
+                for (int j = 0; j < c; j++) {
+                    const int to = sCT[off + j];
+                    desc[n + off + j] =
+                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
+                    if (HAS_PARENT) {
+                        const double tj = sC[off + j];
+                        ok = ok && !(lastT > tj);            // MultiTypeTree.java:404-405
+                        lastT = tj;
+                    }
+                    type = to;
+                }
+                if (HAS_PARENT && !isRoot) {
+                    ok = ok && !(lastT > sH[par]);           // :401, :408-409
+                    ok = ok && (type == (int)sT[par]);       // :421-422
+                }
+            }
+        }
+    }
+    if (HAS_PARENT)
+        ok = __all_sync(FULL_MASK, ok);
+    okOut = ok;
+    __syncwarp();
+
+    // ---- keys: quantised time | event index
+    double tm[EPL];
+    uint32_t ds[EPL];
+    double lo = INFINITY, hi = -INFINITY;
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+        const int e = lane + 32 * k;
+        double x = INFINITY;
+        if (e < E) {
+            x = (e < n) ? sH[e] : sC[e - n];
+            if (HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)
+                x = INFINITY;                                // root-branch change: ignored (:161-162)
+        }
+        tm[k] = x;
+        if (x < INFINITY) {
+            lo = fmin(lo, x);
+            hi = fmax(hi, x);
+        }
+    }
+    lo = warp_min(lo);
+    hi = warp_max(hi);
+    const double range = hi - lo;
+    const double scale = (range > 0.0) ? (double)QMAX / range : 0.0;
+    uint32_t key[EPL];
+#pragma unroll
+    for (int k = 0; k < EPL; k++) {
+        const int e = lane + 32 * k;
+        if (tm[k] < INFINITY) {
+            uint32_t q = (uint32_t)((tm[k] - lo) * scale);
+            q = min(q, QMAX);
+            key[k] = (q << IDX_BITS) | (uint32_t)e;
+        } else {
+            key[k] = 0xffffffffu;
+        }
+    }
+
+    // ---- phase B: order
+    warp_sort<EPL>(key, lane);
+
+    // ---- phase C: exact times + descriptors in sorted order, then repair quantisation ties
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        const int idx = key[r] & ((1 << IDX_BITS) - 1);
+        if (key[r] == 0xffffffffu) {
+            tm[r] = INFINITY;
+            ds[r] = KIND_NONE << 10;
+        } else {
+            tm[r] = (idx < n) ? sH[idx] : sC[idx - n];
+            ds[r] = desc[idx];
+        }
+    }
+    {
+        bool swapped;
+        do {
+            swapped = false;
+#pragma unroll
+            for (int i = 0; i + 1 < EPL; i += 2)
+                swapped |= ce_td(tm[i], ds[i], tm[i + 1], ds[i + 1]);
+#pragma unroll
+            for (int i = 1; i + 1 < EPL; i += 2)
+                swapped |= ce_td(tm[i], ds[i], tm[i + 1], ds[i + 1]);
+            // lane boundary: my last against the next lane's first
+            const double nt = __shfl_down_sync(FULL_MASK, tm[0], 1);
+            const uint32_t nd = __shfl_down_sync(FULL_MASK, ds[0], 1);
+            const bool sw = (lane < 31) && (tm[EPL - 1] > nt);
+            const double pt = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
+            const uint32_t pd = __shfl_up_sync(FULL_MASK, ds[EPL - 1], 1);
+            const bool swPrev = (__shfl_up_sync(FULL_MASK, (int)sw, 1) != 0) && lane > 0;
+            if (sw) {
+                tm[EPL - 1] = nt;
+                ds[EPL - 1] = nd;
+            }
+            if (swPrev) {
+                tm[0] = pt;
+                ds[0] = pd;
+            }
+            swapped = __any_sync(FULL_MASK, swapped || sw);
+        } while (swapped);
+    }
+
+    // ---- phase D: lineage counts by prefix sum, interval integration
+    Counts<NW> local;
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        local.w[i] = 0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++)
+        cnt_apply<NW>(local, ds[r]);
+    Counts<NW> base;
+#pragma unroll
+    for (int i = 0; i < NW; i++) {
+        unsigned long long incl = local.w[i];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long v = shfl_up_u64(incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        base.w[i] = incl - local.w[i];
+    }
+    double prevT = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
+    if (lane == 0)
+        prevT = tm[0];
+    double acc = 0.0;
+#pragma unroll
+    for (int r = 0; r < EPL; r++) {
+        if (tm[r] < INFINITY) {
+            const double dt = tm[r] - prevT;
+            if (dt > 0.0)                                    // StructuredCoalescentTreeDensity.java:108
+                acc -= dt * cnt_lambda<NW>(base, tab, d);
+            if (lane != 0 || r != 0)                         // event 0 is skipped (:101)
+                acc += event_term(ds[r], tab, d);
+            prevT = tm[r];
+        }
+        cnt_apply<NW>(base, ds[r]);
+    }
+    return warp_sum_down(acc);
+}
+
+template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL>
+__global__ void __launch_bounds__(W_WARPS * 32, 2)
+k1_density_warp(const K1Params p)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ModelTab *tabs = reinterpret_cast<ModelTab *>(smem_raw);
+    constexpr int nTabs = PER_TREE_MODEL ? W_WARPS : 1;
+    WarpSmem<HAS_PARENT> *wsAll =
+        reinterpret_cast<WarpSmem<HAS_PARENT> *>(smem_raw + sizeof(ModelTab) * nTabs);
+
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    WarpSmem<HAS_PARENT> *ws = wsAll + warp;
+    ModelTab *tab = tabs + (PER_TREE_MODEL ? warp : 0);
+    const int d = p.d;
+
+    if (!PER_TREE_MODEL)
+        fill_model_tab(tab, p.m, p.N, d, threadIdx.x, blockDim.x);
+    if (lane == 0) {
+        mbar_init((uint64_t *)&ws->bar[0], 1);
+        mbar_init((uint64_t *)&ws->bar[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const long long nWarpsTotal = (long long)gridDim.x * W_WARPS;
+    long long t = (long long)blockIdx.x * W_WARPS + warp;
+    uint32_t phase0 = 0, phase1 = 0;
+
+    TreeSpan cur = load_span(p, t);
+    TreeSpan nxt = load_span(p, t + nWarpsTotal);
+    bool curBig = cur.n + cur.M > W_EMAX;
+    if (t < p.B && !curBig && lane == 0)
+        issue_tree<HAS_PARENT>(p, cur, &ws->st[0], (uint64_t *)&ws->bar[0]);
+
+    for (int it = 0; t < p.B; it++, t += nWarpsTotal) {
+        const int sidx = it & 1;
+        // ---- prefetch this warp's next tree into the other stage
+        const long long tn = t + nWarpsTotal;
+        const bool nxtBig = nxt.n + nxt.M > W_EMAX;
+        if (tn < p.B && !nxtBig && lane == 0)
+            issue_tree<HAS_PARENT>(p, nxt, &ws->st[sidx ^ 1], (uint64_t *)&ws->bar[sidx ^ 1]);
+        const TreeSpan nxt2 = load_span(p, tn + nWarpsTotal);
+
+        if (curBig) {
+            // too large for the warp path: queue for k1_density_block
+            if (lane == 0) {
+                const int slot = atomicAdd(&p.queue[0], 1);
+                p.queue[1 + slot] = (int)t;
+            }
+        } else {
+            const WarpStage<HAS_PARENT> *st = &ws->st[sidx];
+            const StageLayout L = make_layout<HAS_PARENT>(p, cur);
+            if (PER_TREE_MODEL) {
+                fill_model_tab(tab, p.m + t * d * d, p.N + t * d, d, lane, 32);
+                __syncwarp();
+            }
+            if (sidx == 0) {
+                mbar_wait((uint64_t *)&ws->bar[0], phase0);
+                phase0 ^= 1;
+            } else {
+                mbar_wait((uint64_t *)&ws->bar[1], phase1);
+                phase1 ^= 1;
+            }
+            bool ok = true;
+            double acc;
+            if (cur.n + cur.M <= 256)
+                acc = process_tree<NW, HAS_PARENT, 8>(st, L, ws->desc, cur.n, cur.M, tab, d, lane,
+                                                      ok);
+            else
+                acc = process_tree<NW, HAS_PARENT, 16>(st, L, ws->desc, cur.n, cur.M, tab, d,
+                                                       lane, ok);
+            if (lane == 0) {
+                if (HAS_PARENT && p.valid)
+                    p.valid[t] = ok ? 1 : 0;
+                p.logP[t] = (HAS_PARENT && p.checkValidity && !ok) ? -INFINITY : acc;   // :90-91
+            }
+            __syncwarp();
+        }
+        cur = nxt;
+        nxt = nxt2;
+        curBig = nxtBig;
+    }
+}
+
+// =====================================================================================
+// CTA-per-tree kernel (queue consumer; also the direct path when every tree is large)
+// =====================================================================================
+constexpr int BLK_THREADS = 512;
+
+__device__ __forceinline__ unsigned long long block_key(double x, double lo, double scale,
+                                                        int idx, uint32_t desc)
+{
+    // 38-bit quantised time | 14-bit index | 12-bit descriptor
+    unsigned long long q = (unsigned long long)((x - lo) * scale);
+    if (q > 0x3fffffffffull)
+        q = 0x3fffffffffull;
+    return (q << 26) | ((unsigned long long)idx << 12) | (desc & 0xfffu);
+}
+
+template <int NW>
+__global__ void __launch_bounds__(BLK_THREADS)
+k1_density_block(const K1Params p, int Ecap, int useQueue)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    ModelTab *tab = reinterpret_cast<ModelTab *>(smem_raw);
+    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(ModelTab));
+    uint32_t *offs = reinterpret_cast<uint32_t *>(keys + Ecap);      // Ecap entries
+    __shared__ double redD[BLK_THREADS / 32 * 2];
+    __shared__ unsigned long long redC[BLK_THREADS / 32][NW];
+    __shared__ uint32_t redU[BLK_THREADS / 32];
+    __shared__ int sFlag;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nWarps = BLK_THREADS / 32;
+    const int d = p.d;
+    const long long nWork = useQueue ? (long long)p.queue[0] : p.B;
+
+    for (long long wi = blockIdx.x; wi < nWork; wi += gridDim.x) {
+        const long long t = useQueue ? (long long)p.queue[1 + wi] : wi;
+        const long long n0 = p.nodeOff[t], c0 = p.chgBase[t];
+        const int n = (int)(p.nodeOff[t + 1] - n0), M = (int)(p.chgBase[t + 1] - c0);
+        const int E = n + M;
+        const int nLeaves = (n + 1) >> 1;
+        const double *H = p.height + n0;
+        const double *CT = p.chgTime + c0;
+        const uint8_t *T = p.nodeType + n0, *CTy = p.chgType + c0;
+        const uint16_t *K = p.chgCount + n0;
+        const int *P = p.parent ? p.parent + n0 : nullptr;
+
+        __syncthreads();
+        if (E > Ecap) {   // beyond the smem sort capacity: report NaN (host maps it to an error)
+            if (tid == 0) {
+                p.logP[t] = NAN;
+                if (p.valid)
+                    p.valid[t] = 0;
+            }
+            continue;
+        }
+        const bool perTree = p.nModels > 1;
+        fill_model_tab(tab, p.m + (perTree ? t * d * d : 0), p.N + (perTree ? t * d : 0), d, tid,
+                       BLK_THREADS);
+
+        // ---- time range over node heights and change times
+        double lo = INFINITY, hi = -INFINITY;
+        for (int e = tid; e < E; e += BLK_THREADS) {
+            double x = (e < n) ? H[e] : CT[e - n];
+            lo = fmin(lo, x);
+            hi = fmax(hi, x);
+        }
+        lo = warp_min(lo);
+        hi = warp_max(hi);
+        if (lane == 0) {
+            redD[warp] = lo;
+            redD[nWarps + warp] = hi;
+        }
+        // ---- exclusive scan of change counts -> offs[]
+        const int per = (n + BLK_THREADS - 1) / BLK_THREADS;
+        const int b0 = min(tid * per, n), b1 = min(b0 + per, n);
+        uint32_t s = 0;
+        for (int e = b0; e < b1; e++)
+            s += K[e];
+        uint32_t incl = s;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        if (lane == 31)
+            redU[warp] = incl;
+        __syncthreads();
+        lo = redD[0];
+        hi = redD[nWarps];
+        for (int w = 1; w < nWarps; w++) {
+            lo = fmin(lo, redD[w]);
+            hi = fmax(hi, redD[nWarps + w]);
+        }
+        uint32_t wbase = 0;
+        for (int w = 0; w < warp; w++)
+            wbase += redU[w];
+        uint32_t run = wbase + incl - s;
+        for (int e = b0; e < b1; e++) {
+            offs[e] = run;
+            run += K[e];
+        }
+        const double range = hi - lo;
+        const double scale = (range > 0.0) ? 274877906943.0 / range : 0.0;   // 2^38 - 1
+        __syncthreads();
+
+        // ---- keys (node-centric) + validity
+        int Epad = 1;
+        while (Epad < E)
+            Epad <<= 1;
+        bool ok = true;
+        for (int e = tid; e < n; e += BLK_THREADS) {
+            int type = T[e];
+            keys[e] = block_key(H[e], lo, scale, e,
+                                ((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | type << 5);
+            const int c = K[e];
+            const uint32_t off = offs[e];
+            const int par = P ? P[e] : 0;
+            const bool isRoot = P && par < 0;
+            double lastT = H[e];
+            for (int j = 0; j < c; j++) {
+                int to = CTy[off + j];
+                double tj = CT[off + j];
+                if (isRoot)
+                    keys[n + off + j] = ~0ull;       // ignored (:161-162): sorts with the padding
+                else
+                    keys[n + off + j] = block_key(tj, lo, scale, n + off + j,
+                                                  KIND_MIGRATE << 10 | type << 5 | to);
+                if (P) {
+                    ok = ok && !(lastT > tj);
+                    lastT = tj;
+                }
+                type = to;
+            }
+            if (P && !isRoot) {
+                ok = ok && !(lastT > H[par]);
+                ok = ok && (type == (int)T[par]);
+            }
+        }
+        for (int e = E + tid; e < Epad; e += BLK_THREADS)
+            keys[e] = ~0ull;
+        if (tid == 0)
+            sFlag = 1;
+        __syncthreads();
+        if (!ok)
+            sFlag = 0;
+
+        // ---- bitonic sort in shared memory (ascending)
+        for (int size = 2; size <= Epad; size <<= 1) {
+            for (int stride = size >> 1; stride > 0; stride >>= 1) {
+                __syncthreads();
+                for (int i = tid; i < (Epad >> 1); i += BLK_THREADS) {
+                    const int a = 2 * i - (i & (stride - 1));
+                    int b = a + stride;                       // half cleaner
+                    if (stride == (size >> 1))                // merge start: reflected partner
+                        b = (a & ~(size - 1)) + (size - 1 - (a & (size - 1)));
+                    unsigned long long ka = keys[a], kb = keys[b];
+                    if (ka > kb) {
+                        keys[a] = kb;
+                        keys[b] = ka;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const bool treeOk = sFlag != 0;
+
+        // ---- chunked scan: thread owns sorted positions [q0, q1)
+        const int chunk = (Epad + BLK_THREADS - 1) / BLK_THREADS;
+        const int q0 = min(tid * chunk, Epad), q1 = min(q0 + chunk, Epad);
+        auto evTime = [&](unsigned long long k) -> double {
+            if (k == ~0ull)
+                return INFINITY;
+            int idx = (int)((k >> 12) & 0x3fff);
+            return (idx < n) ? H[idx] : CT[idx - n];
+        };
+        // repair pass: quantisation ties may be out of exact order (rare; 38-bit quanta)
+        {
+            bool again = true;
+            while (again) {
+                __syncthreads();
+                if (tid == 0)
+                    sFlag = 0;
+                __syncthreads();
+                bool bad = false;
+                for (int par2 = 0; par2 < 2; par2++) {
+                    for (int i = tid; 2 * i + par2 + 1 < Epad; i += BLK_THREADS) {
+                        int a = 2 * i + par2;
+                        unsigned long long ka = keys[a], kb = keys[a + 1];
+                        if ((ka >> 26) == (kb >> 26) && ka != ~0ull && kb != ~0ull) {
+                            if (evTime(ka) > evTime(kb)) {
+                                keys[a] = kb;
+                                keys[a + 1] = ka;
+                                bad = true;
+                            }
+                        }
+                    }
+                    __syncthreads();
+                }
+                if (bad)
+                    sFlag = 1;
+                __syncthreads();
+                again = sFlag != 0;
+            }
+        }
+
+        Counts<NW> local;
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            local.w[i] = 0;
+        for (int q = q0; q < q1; q++) {
+            unsigned long long k = keys[q];
+            if (k != ~0ull)
+                cnt_apply<NW>(local, (uint32_t)(k & 0xfff));
+        }
+        Counts<NW> base;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            unsigned long long incl2 = local.w[i];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                unsigned long long v = shfl_up_u64(incl2, o);
+                if (lane >= o)
+                    incl2 += v;
+            }
+            if (lane == 31)
+                redC[warp][i] = incl2;
+            base.w[i] = incl2 - local.w[i];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            for (int w = 0; w < warp; w++)
+                base.w[i] += redC[w][i];
+
+        double prevT = (q0 > 0 && q0 < Epad) ? evTime(keys[q0 - 1]) : 0.0;
+        double acc = 0.0;
+        for (int q = q0; q < q1; q++) {
+            unsigned long long k = keys[q];
+            if (k == ~0ull)
+                break;
+            double x = evTime(k);
+            uint32_t desc = (uint32_t)(k & 0xfff);
+            if (q > 0) {
+                double dt = x - prevT;
+                if (dt > 0.0)
+                    acc -= dt * cnt_lambda<NW>(base, tab, d);
+                acc += event_term(desc, tab, d);
+            }
+            cnt_apply<NW>(base, desc);
+            prevT = x;
+        }
+        acc = warp_sum_down(acc);
+        __syncthreads();
+        if (lane == 0)
+            redD[warp] = acc;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int w = 0; w < nWarps; w++)
+                tot += redD[w];
+            if (P && p.valid)
+                p.valid[t] = treeOk ? 1 : 0;
+            p.logP[t] = (P && p.checkValidity && !treeOk) ? -INFINITY : tot;
+        }
+    }
+}
+
+__global__ void k1_reset_queue(int *queue)
+{
+    queue[0] = 0;
+}
+
+template <int NW, bool HP, bool PT>
+int launch_warp(mtt_ctx *ctx, const K1Params &p)
+{
+    size_t smem = sizeof(ModelTab) * (PT ? W_WARPS : 1) + sizeof(WarpSmem<HP>) * W_WARPS;
+    auto kern = k1_density_warp<NW, HP, PT>;
+    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    int perSM = 1;
+    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, W_WARPS * 32, smem));
+    if (perSM < 1)
+        perSM = 1;
+    long long want = (p.B + W_WARPS - 1) / W_WARPS;
+    long long grid = (long long)ctx->numSMs * perSM;
+    if (want < grid)
+        grid = want;
+    kern<<<(unsigned)grid, W_WARPS * 32, smem, ctx->stream>>>(p);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
+}
+
+template <int NW>
+int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long long nWorkHint)
+{
+    size_t smem = sizeof(ModelTab) + (size_t)Ecap * 12;
+    auto kern = k1_density_block<NW>;
+    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    int perSM = 1;
+    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, BLK_THREADS, smem));
+    if (perSM < 1)
+        perSM = 1;
+    long long grid = (long long)ctx->numSMs * perSM;
+    if (nWorkHint > 0 && nWorkHint < grid)
+        grid = nWorkHint;
+    kern<<<(unsigned)grid, BLK_THREADS, smem, ctx->stream>>>(p, Ecap, useQueue);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
+}
+
+template <int NW>
+int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
+{
+    const bool hp = p.parent != nullptr, pt = p.nModels > 1;
+    int Ecap = MTT_MAX_TREE_EVENTS;
+    if (maxEvents > 0) {
+        Ecap = 512;
+        while (Ecap < maxEvents)
+            Ecap <<= 1;
+        if (Ecap > MTT_MAX_TREE_EVENTS)
+            Ecap = MTT_MAX_TREE_EVENTS;
+    }
+    // every tree certainly large -> block kernel directly
+    if (maxEvents < 0)
+        return launch_block<NW>(ctx, p, Ecap, 0, p.B);
+    k1_reset_queue<<<1, 1, 0, ctx->stream>>>(p.queue);
+    MTT_CHECK_LAUNCH(ctx);
+    int rc;
+    if (hp)
+        rc = pt ? launch_warp<NW, true, true>(ctx, p) : launch_warp<NW, true, false>(ctx, p);
+    else
+        rc = pt ? launch_warp<NW, false, true>(ctx, p) : launch_warp<NW, false, false>(ctx, p);
+    if (rc != MTT_OK)
+        return rc;
+    if (maxEvents == 0 || maxEvents > W_EMAX)
+        return launch_block<NW>(ctx, p, Ecap, 1, 0);
+    return MTT_OK;
+}
+
+}  // namespace
+
+// maxEvents: > 0 upper bound on nodes+changes of any tree (known to the caller), 0 unknown,
+// < 0 "all trees exceed the warp path" (|maxEvents| is the bound).
+int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                  const double *N, const int64_t *nodeOff, const double *height,
+                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
+                  const int64_t *chgBase, const double *chgTime, const uint8_t *chgType,
+                  int checkValidity, double *logP, uint8_t *valid, long long maxEvents)
+{
+    if (B <= 0)
+        return MTT_OK;
+    if (d < 1 || d > MTT_MAX_DEMES)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "density: d=%d outside [1,%d]", d, MTT_MAX_DEMES);
+    if (nModels != 1 && nModels != B)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "density: nModels must be 1 or B");
+    if (B > 0x7fffffffLL)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "density: B exceeds 2^31-1 trees per call");
+    K1Params p;
+    p.B = B; p.d = d; p.nModels = nModels; p.m = m; p.N = N;
+    p.nodeOff = (const long long *)nodeOff; p.height = height; p.parent = parent;
+    p.nodeType = nodeType; p.chgCount = chgCount; p.chgBase = (const long long *)chgBase;
+    p.chgTime = chgTime; p.chgType = chgType; p.checkValidity = checkValidity;
+    p.logP = logP; p.valid = valid;
+    p.queue = (int *)mtt_buf(ctx, BUF_D_QUEUE, sizeof(int) * (size_t)(B + 1));
+    if (!p.queue)
+        return MTT_ERR_CUDA;
+    long long me = maxEvents;
+    if (me > 0 && me <= W_EMAX)
+        me = W_EMAX;
+    // all-large shortcut only when the caller says so
+    if (d <= 4)
+        return launch_all<1>(ctx, p, me);
+    if (d <= 8)
+        return launch_all<2>(ctx, p, me);
+    return launch_all<4>(ctx, p, me);
+}

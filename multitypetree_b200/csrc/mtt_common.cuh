@@ -1,0 +1,162 @@
+// mtt_common.cuh -- shared host/device plumbing for the sm_100a kernels behind include/mtt_b200.h
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/mtt_b200.h"
+
+// ------------------------------------------------------------------ context
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+};
+
+struct mtt_ctx {
+    int device = 0;
+    int numSMs = 148;
+    cudaStream_t ownStream = nullptr;
+    cudaStream_t stream = nullptr;   // stream in use (own or caller's)
+    std::string err;
+    int64_t launches = 0;
+    // grow-only device scratch, indexed by purpose
+    std::vector<DevBuf> bufs;
+    // piece 1: caller's bound on nodes+changes per tree for the _dev entry (0 = unknown)
+    long long k1MaxEvents = 0;
+    // piece 3 state
+    int unifModels = 0, unifD = 0, unifSym = 0;
+    int unifPowCap = 0;                 // powers allocated per model (entries 0..cap-1)
+    std::vector<int> unifPowSize;       // powers valid per model
+    std::vector<int> unifSteady;        // steady flag per model
+    std::vector<double> unifMu;         // host copy of mu per model
+};
+
+enum BufId {
+    BUF_D_MODEL = 0, BUF_D_N, BUF_D_NODEOFF, BUF_D_HEIGHT, BUF_D_PARENT, BUF_D_NODETYPE,
+    BUF_D_CHGCOUNT, BUF_D_CHGBASE, BUF_D_CHGTIME, BUF_D_CHGTYPE, BUF_D_LOGP, BUF_D_VALID,
+    BUF_D_QUEUE,
+    BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
+    BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
+    BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6,
+    BUF_COUNT
+};
+
+int mtt_fail(mtt_ctx *ctx, int code, const char *fmt, ...);
+// grow-only device buffer with 256 B of slack past `bytes` (bulk copies over-read <= 15 B)
+void *mtt_buf(mtt_ctx *ctx, int id, size_t bytes);
+
+#define MTT_CUDA(ctx, expr)                                                              \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess)                                                           \
+            return mtt_fail((ctx), MTT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,         \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+#define MTT_CHECK_LAUNCH(ctx)                                                            \
+    do {                                                                                 \
+        (ctx)->launches++;                                                               \
+        cudaError_t _e = cudaGetLastError();                                             \
+        if (_e != cudaSuccess)                                                           \
+            return mtt_fail((ctx), MTT_ERR_CUDA, "kernel launch failed: %s (%s:%d)",     \
+                            cudaGetErrorString(_e), __FILE__, __LINE__);                 \
+    } while (0)
+
+// ------------------------------------------------------------------ device helpers
+#ifdef __CUDACC__
+
+#define FULL_MASK 0xffffffffu
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+
+// ---- mbarrier + 1-D bulk async copy (TMA engine; SASS UBLKCP)
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy; src/dst 16 B aligned, bytes a multiple of 16
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, uint32_t bytes,
+                                         uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+        ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// order-preserving map double -> uint64 (total order on non-NaN values)
+__device__ __forceinline__ uint64_t f64_key(double x)
+{
+    uint64_t b = (uint64_t)__double_as_longlong(x);
+    return (b & 0x8000000000000000ull) ? ~b : (b | 0x8000000000000000ull);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_xor_sync(FULL_MASK, v, o);
+    return v;
+}
+// fixed-order (lane 0 .. 31) reduction tree: deterministic run to run
+__device__ __forceinline__ double warp_sum_down(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v += __shfl_down_sync(FULL_MASK, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_min(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmin(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_max(double v)
+{
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1)
+        v = fmax(v, __shfl_xor_sync(FULL_MASK, v, o));
+    return v;
+}
+__device__ __forceinline__ uint64_t shfl_up_u64(uint64_t v, int o)
+{
+    return (uint64_t)__shfl_up_sync(FULL_MASK, (unsigned long long)v, o);
+}
+
+#endif  // __CUDACC__

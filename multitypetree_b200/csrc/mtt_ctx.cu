@@ -1,0 +1,279 @@
+// mtt_ctx.cu -- context, error handling, device scratch, and the piece-1 C-ABI entry points.
+#include "mtt_common.cuh"
+
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+static thread_local std::string g_create_err;
+
+int mtt_fail(mtt_ctx *ctx, int code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (ctx)
+        ctx->err = buf;
+    else
+        g_create_err = buf;
+    return code;
+}
+
+void *mtt_buf(mtt_ctx *ctx, int id, size_t bytes)
+{
+    DevBuf &b = ctx->bufs[id];
+    if (bytes + 256 > b.cap) {
+        if (b.p) {
+            cudaStreamSynchronize(ctx->stream);
+            cudaFree(b.p);
+            b.p = nullptr;
+            b.cap = 0;
+        }
+        size_t cap = bytes + bytes / 4 + 4096;
+        cudaError_t e = cudaMalloc(&b.p, cap);
+        if (e != cudaSuccess) {
+            mtt_fail(ctx, MTT_ERR_CUDA, "cudaMalloc(%zu) failed: %s", cap, cudaGetErrorString(e));
+            b.p = nullptr;
+            return nullptr;
+        }
+        b.cap = cap;
+    }
+    return b.p;
+}
+
+extern "C" {
+
+int mtt_abi_version(void)
+{
+    return MTT_ABI_VERSION;
+}
+
+int mtt_ctx_create(int device, mtt_ctx **out)
+{
+    if (!out)
+        return mtt_fail(nullptr, MTT_ERR_INVALID_ARG, "mtt_ctx_create: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return mtt_fail(nullptr, MTT_ERR_NO_DEVICE,
+                        "no CUDA device available (%s); this library has no CPU fallback",
+                        e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0");
+    if (device < 0) {
+        e = cudaGetDevice(&device);
+        if (e != cudaSuccess)
+            return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaGetDevice: %s", cudaGetErrorString(e));
+    }
+    if (device >= count)
+        return mtt_fail(nullptr, MTT_ERR_INVALID_ARG, "device %d out of range (%d devices)",
+                        device, count);
+    e = cudaSetDevice(device);
+    if (e != cudaSuccess)
+        return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaSetDevice(%d): %s", device,
+                        cudaGetErrorString(e));
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess)
+        return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaGetDeviceProperties: %s",
+                        cudaGetErrorString(e));
+    if (prop.major != 10)
+        return mtt_fail(nullptr, MTT_ERR_NO_DEVICE,
+                        "device %d is sm_%d%d; this library is built for sm_100a (B200) only",
+                        device, prop.major, prop.minor);
+    mtt_ctx *ctx = new mtt_ctx();
+    ctx->device = device;
+    ctx->numSMs = prop.multiProcessorCount;
+    ctx->bufs.resize(BUF_COUNT);
+    e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        delete ctx;
+        return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+    }
+    ctx->stream = ctx->ownStream;
+    *out = ctx;
+    return MTT_OK;
+}
+
+int mtt_ctx_destroy(mtt_ctx *ctx)
+{
+    if (!ctx)
+        return MTT_OK;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    for (auto &b : ctx->bufs)
+        if (b.p)
+            cudaFree(b.p);
+    if (ctx->ownStream)
+        cudaStreamDestroy(ctx->ownStream);
+    delete ctx;
+    return MTT_OK;
+}
+
+const char *mtt_last_error(const mtt_ctx *ctx)
+{
+    return ctx ? ctx->err.c_str() : g_create_err.c_str();
+}
+
+int mtt_ctx_set_stream(mtt_ctx *ctx, void *cuda_stream)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->ownStream;
+    return MTT_OK;
+}
+
+int mtt_ctx_synchronize(mtt_ctx *ctx)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    return MTT_OK;
+}
+
+int64_t mtt_ctx_launch_count(const mtt_ctx *ctx)
+{
+    return ctx ? ctx->launches : 0;
+}
+
+int mtt_host_register(void *ptr, int64_t bytes)
+{
+    cudaError_t e = cudaHostRegister(ptr, (size_t)bytes, cudaHostRegisterDefault);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaHostRegister: %s", cudaGetErrorString(e));
+    }
+    return MTT_OK;
+}
+
+int mtt_host_unregister(void *ptr)
+{
+    cudaError_t e = cudaHostUnregister(ptr);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        return mtt_fail(nullptr, MTT_ERR_CUDA, "cudaHostUnregister: %s", cudaGetErrorString(e));
+    }
+    return MTT_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------ piece 1 entry points
+
+int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                  const double *N, const int64_t *nodeOff, const double *height,
+                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
+                  const int64_t *chgBase, const double *chgTime, const uint8_t *chgType,
+                  int checkValidity, double *logP, uint8_t *valid, long long maxEvents);
+
+extern "C" int mtt_sc_logp_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                     const double *m, const double *N, const int64_t *nodeOff,
+                                     const double *height, const int32_t *parent,
+                                     const uint8_t *nodeType, const uint16_t *chgCount,
+                                     const int64_t *chgBase, const double *chgTime,
+                                     const uint8_t *chgType, int checkValidity, double *logP,
+                                     uint8_t *valid)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgCount || !chgBase || !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch_dev: NULL argument");
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    return mtt_k1_launch(ctx, B, d, nModels, m, N, nodeOff, height, parent, nodeType, chgCount,
+                         chgBase, chgTime, chgType, checkValidity, logP, valid, ctx->k1MaxEvents);
+}
+
+extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                 const double *m, const double *N, const int64_t *nodeOff,
+                                 const double *height, const int32_t *parent,
+                                 const uint8_t *nodeType, const uint16_t *chgCount,
+                                 const int64_t *chgBase, const double *chgTime,
+                                 const uint8_t *chgType, int checkValidity, double *logP,
+                                 uint8_t *valid)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgCount || !chgBase || !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch: NULL argument");
+    if (B == 0)
+        return MTT_OK;
+    if (nModels != 1 && nModels != B)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch: nModels must be 1 or B");
+    if (checkValidity && !parent)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG,
+                        "mtt_sc_logp_batch: checkValidity requires parent[]");
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+
+    const int64_t nodes = nodeOff[B] - nodeOff[0], changes = chgBase[B] - chgBase[0];
+    if (nodeOff[0] != 0 || chgBase[0] != 0)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "nodeOff[0] and chgBase[0] must be 0");
+    if (changes > 0 && (!chgTime || !chgType))
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "chgTime/chgType NULL with changes present");
+    long long maxEv = 0;
+    for (int64_t b = 0; b < B; b++) {
+        long long e = (nodeOff[b + 1] - nodeOff[b]) + (chgBase[b + 1] - chgBase[b]);
+        if (nodeOff[b + 1] < nodeOff[b] || chgBase[b + 1] < chgBase[b])
+            return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "offsets of tree %lld not monotone",
+                            (long long)b);
+        if (e > maxEv)
+            maxEv = e;
+    }
+    if (maxEv > MTT_MAX_TREE_EVENTS)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE,
+                        "a tree has %lld events (nodes + changes); limit is %d", maxEv,
+                        MTT_MAX_TREE_EVENTS);
+
+    cudaStream_t s = ctx->stream;
+    const size_t md = (size_t)nModels * d * d * 8, nd = (size_t)nModels * d * 8;
+    double *dM = (double *)mtt_buf(ctx, BUF_D_MODEL, md);
+    double *dN = (double *)mtt_buf(ctx, BUF_D_N, nd);
+    int64_t *dNodeOff = (int64_t *)mtt_buf(ctx, BUF_D_NODEOFF, (B + 1) * 8);
+    int64_t *dChgBase = (int64_t *)mtt_buf(ctx, BUF_D_CHGBASE, (B + 1) * 8);
+    double *dH = (double *)mtt_buf(ctx, BUF_D_HEIGHT, nodes * 8);
+    uint8_t *dT = (uint8_t *)mtt_buf(ctx, BUF_D_NODETYPE, nodes);
+    uint16_t *dK = (uint16_t *)mtt_buf(ctx, BUF_D_CHGCOUNT, nodes * 2);
+    double *dCT = (double *)mtt_buf(ctx, BUF_D_CHGTIME, changes * 8);
+    uint8_t *dCTy = (uint8_t *)mtt_buf(ctx, BUF_D_CHGTYPE, changes);
+    int32_t *dP = parent ? (int32_t *)mtt_buf(ctx, BUF_D_PARENT, nodes * 4) : nullptr;
+    double *dLogP = (double *)mtt_buf(ctx, BUF_D_LOGP, B * 8);
+    uint8_t *dValid = (valid && parent) ? (uint8_t *)mtt_buf(ctx, BUF_D_VALID, B) : nullptr;
+    if (!dM || !dN || !dNodeOff || !dChgBase || !dH || !dT || !dK || !dCT || !dCTy || !dLogP ||
+        (parent && !dP) || (valid && parent && !dValid))
+        return MTT_ERR_CUDA;
+
+    MTT_CUDA(ctx, cudaMemcpyAsync(dM, m, md, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dN, N, nd, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dNodeOff, nodeOff, (B + 1) * 8, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dChgBase, chgBase, (B + 1) * 8, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dH, height, nodes * 8, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dT, nodeType, nodes, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dK, chgCount, nodes * 2, cudaMemcpyHostToDevice, s));
+    if (changes > 0) {
+        MTT_CUDA(ctx, cudaMemcpyAsync(dCT, chgTime, changes * 8, cudaMemcpyHostToDevice, s));
+        MTT_CUDA(ctx, cudaMemcpyAsync(dCTy, chgType, changes, cudaMemcpyHostToDevice, s));
+    }
+    if (parent)
+        MTT_CUDA(ctx, cudaMemcpyAsync(dP, parent, nodes * 4, cudaMemcpyHostToDevice, s));
+
+    int rc = mtt_k1_launch(ctx, B, d, nModels, dM, dN, dNodeOff, dH, dP, dT, dK, dChgBase, dCT,
+                           dCTy, checkValidity, dLogP, dValid, maxEv > 0 ? maxEv : 1);
+    if (rc != MTT_OK)
+        return rc;
+    MTT_CUDA(ctx, cudaMemcpyAsync(logP, dLogP, B * 8, cudaMemcpyDeviceToHost, s));
+    if (dValid)
+        MTT_CUDA(ctx, cudaMemcpyAsync(valid, dValid, B, cudaMemcpyDeviceToHost, s));
+    MTT_CUDA(ctx, cudaStreamSynchronize(s));
+    if (valid && !parent)
+        memset(valid, 1, (size_t)B);
+    return MTT_OK;
+}
+
+// hint for the device-pointer entry point (upper bound on nodes+changes per tree; 0 unknown)
+extern "C" int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    ctx->k1MaxEvents = maxEvents;
+    return MTT_OK;
+}

@@ -1,0 +1,372 @@
+"""Host-side mirror of the reference's typed-tree state, flattened to the tree-SoA layout.
+
+Mirrors (names and meaning, not code) evolution/tree/MultiTypeNode.java:33-102,
+evolution/tree/MultiTypeTree.java:396-429 (isValid), :538-665 (initFromFlatTree: single-child
+Newick nodes are type changes) and evolution/tree/MultiTypeTreeFromNewick.java:30-43.
+All arithmetic on these trees happens in the CUDA library; this module only moves data.
+"""
+from __future__ import annotations
+
+import re
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import _lib
+
+
+@dataclass
+class MultiTypeTree:
+    """One flattened multi-type tree.  Node Nr in [0, nLeaves) are leaves (BEAST numbering)."""
+
+    height: np.ndarray            # f64 [nNodes]
+    parent: np.ndarray            # i32 [nNodes], -1 = root
+    nodeType: np.ndarray          # u8  [nNodes]
+    changeTimes: List[List[float]] = field(default_factory=list)   # per node, youngest first
+    changeTypes: List[List[int]] = field(default_factory=list)
+    taxa: Optional[List[str]] = None
+
+    # ---- MultiTypeNode / Tree accessors (same names as the reference) ----
+    def getNodeCount(self) -> int:
+        return len(self.height)
+
+    def getLeafNodeCount(self) -> int:
+        return (len(self.height) + 1) // 2
+
+    def getInternalNodeCount(self) -> int:
+        return len(self.height) - self.getLeafNodeCount()
+
+    def getRoot(self) -> int:
+        return int(np.nonzero(self.parent < 0)[0][0])
+
+    def getChangeCount(self, node: int) -> int:
+        return len(self.changeTimes[node])
+
+    def getChangeTime(self, node: int, idx: int) -> float:
+        return self.changeTimes[node][idx]
+
+    def getChangeType(self, node: int, idx: int) -> int:
+        return self.changeTypes[node][idx]
+
+    def getNodeType(self, node: int) -> int:
+        return int(self.nodeType[node])
+
+    def getFinalType(self, node: int) -> int:
+        return self.changeTypes[node][-1] if self.changeTypes[node] else int(self.nodeType[node])
+
+    def setNodeType(self, node: int, t: int) -> None:
+        self.nodeType[node] = t
+
+    def clearChanges(self, node: int) -> None:
+        self.changeTimes[node] = []
+        self.changeTypes[node] = []
+
+    def addChange(self, node: int, newType: int, time: float) -> None:
+        self.changeTimes[node].append(float(time))
+        self.changeTypes[node].append(int(newType))
+
+    def getChildren(self, node: int) -> List[int]:
+        return [int(c) for c in np.nonzero(self.parent == node)[0]]
+
+    def getTotalNumberOfChanges(self) -> int:
+        return sum(len(c) for c in self.changeTimes)
+
+    def copy(self) -> "MultiTypeTree":
+        return MultiTypeTree(self.height.copy(), self.parent.copy(), self.nodeType.copy(),
+                             [list(c) for c in self.changeTimes],
+                             [list(c) for c in self.changeTypes],
+                             list(self.taxa) if self.taxa else None)
+
+    def isValid(self, ctx=None) -> bool:
+        """MultiTypeTree.isValid (MultiTypeTree.java:396-429), evaluated on the device."""
+        from .density import tree_validity
+        return bool(tree_validity(TreeBatch.from_trees([self]), ctx)[0])
+
+
+@dataclass
+class TreeBatch:
+    """B trees back to back in the C-ABI layout (include/mtt_b200.h)."""
+
+    nodeOff: np.ndarray    # i64 [B+1]
+    height: np.ndarray     # f64 [nodes]
+    parent: np.ndarray     # i32 [nodes]
+    nodeType: np.ndarray   # u8  [nodes]
+    chgCount: np.ndarray   # u16 [nodes]
+    chgBase: np.ndarray    # i64 [B+1]
+    chgTime: np.ndarray    # f64 [changes]
+    chgType: np.ndarray    # u8  [changes]
+
+    @property
+    def B(self) -> int:
+        return len(self.nodeOff) - 1
+
+    def n_events(self) -> np.ndarray:
+        """E = nodes + changes per tree (the unit of algorithmic traffic)."""
+        return np.diff(self.nodeOff) + np.diff(self.chgBase)
+
+    @staticmethod
+    def from_trees(trees: Sequence[MultiTypeTree]) -> "TreeBatch":
+        nodeOff = np.zeros(len(trees) + 1, np.int64)
+        chgBase = np.zeros(len(trees) + 1, np.int64)
+        hs, ps, ts, ks, cts, ctys = [], [], [], [], [], []
+        for b, t in enumerate(trees):
+            n = t.getNodeCount()
+            nodeOff[b + 1] = nodeOff[b] + n
+            hs.append(np.asarray(t.height, np.float64))
+            ps.append(np.asarray(t.parent, np.int32))
+            ts.append(np.asarray(t.nodeType, np.uint8))
+            root = t.getRoot()
+            cnt = np.zeros(n, np.uint16)
+            m = 0
+            for i in range(n):
+                if i == root:
+                    continue      # root-branch changes are never exported
+                c = len(t.changeTimes[i])
+                cnt[i] = c
+                m += c
+                cts.extend(t.changeTimes[i])
+                ctys.extend(t.changeTypes[i])
+            ks.append(cnt)
+            chgBase[b + 1] = chgBase[b] + m
+        cat = lambda xs, dt: (np.concatenate(xs).astype(dt) if xs else np.zeros(0, dt))
+        return TreeBatch(nodeOff, cat(hs, np.float64), cat(ps, np.int32), cat(ts, np.uint8),
+                         cat(ks, np.uint16), chgBase, np.asarray(cts, np.float64),
+                         np.asarray(ctys, np.uint8))
+
+    def tree(self, b: int) -> MultiTypeTree:
+        n0, n1 = int(self.nodeOff[b]), int(self.nodeOff[b + 1])
+        c = int(self.chgBase[b])
+        times, types = [], []
+        for i in range(n0, n1):
+            k = int(self.chgCount[i])
+            times.append([float(x) for x in self.chgTime[c:c + k]])
+            types.append([int(x) for x in self.chgType[c:c + k]])
+            c += k
+        return MultiTypeTree(self.height[n0:n1].copy(), self.parent[n0:n1].copy(),
+                             self.nodeType[n0:n1].copy(), times, types)
+
+    def slice(self, b0: int, b1: int) -> "TreeBatch":
+        n0, n1 = int(self.nodeOff[b0]), int(self.nodeOff[b1])
+        c0, c1 = int(self.chgBase[b0]), int(self.chgBase[b1])
+        return TreeBatch(self.nodeOff[b0:b1 + 1] - n0, self.height[n0:n1], self.parent[n0:n1],
+                         self.nodeType[n0:n1], self.chgCount[n0:n1],
+                         self.chgBase[b0:b1 + 1] - c0, self.chgTime[c0:c1], self.chgType[c0:c1])
+
+    def nbytes(self) -> int:
+        return sum(a.nbytes for a in (self.nodeOff, self.height, self.nodeType, self.chgCount,
+                                      self.chgBase, self.chgTime, self.chgType))
+
+
+# ---------------------------------------------------------------------------- Newick
+
+class _FlatNode:
+    __slots__ = ("children", "label", "meta", "length", "height")
+
+    def __init__(self):
+        self.children = []
+        self.label = None
+        self.meta = {}
+        self.length = 0.0
+        self.height = 0.0
+
+
+_META_ITEM = re.compile(r'\s*([^=,\s]+)\s*=\s*("([^"]*)"|\'([^\']*)\'|\{[^}]*\}|[^,\]]*)')
+
+
+def _parse_meta(s: str) -> dict:
+    out = {}
+    for mm in _META_ITEM.finditer(s):
+        key = mm.group(1)
+        val = mm.group(3) if mm.group(3) is not None else (
+            mm.group(4) if mm.group(4) is not None else mm.group(2).strip())
+        out[key] = val
+    return out
+
+
+def parse_flat_newick(s: str) -> _FlatNode:
+    """Newick with BEAST metadata comments ``[&k=v,...]`` and single-child nodes allowed
+    (TreeParser with singlechild=true, MultiTypeTreeFromNewick.java:35-40)."""
+    s = s.strip()
+    pos = 0
+
+    def parse_node() -> _FlatNode:
+        nonlocal pos
+        node = _FlatNode()
+        if s[pos] == "(":
+            pos += 1
+            while True:
+                node.children.append(parse_node())
+                if s[pos] == ",":
+                    pos += 1
+                    continue
+                if s[pos] == ")":
+                    pos += 1
+                    break
+                raise ValueError("bad Newick at %d: %r" % (pos, s[pos:pos + 20]))
+        # label
+        start = pos
+        if pos < len(s) and s[pos] in "'\"":
+            q = s[pos]
+            pos = s.index(q, pos + 1) + 1
+            node.label = s[start + 1:pos - 1]
+        else:
+            while pos < len(s) and s[pos] not in ":,()[;":
+                pos += 1
+            node.label = s[start:pos].strip() or None
+        # metadata and branch length (metadata may come before or after the colon)
+        while pos < len(s) and s[pos] in "[:":
+            if s[pos] == "[":
+                end = s.index("]", pos)
+                body = s[pos + 1:end]
+                if body.startswith("&"):
+                    node.meta.update(_parse_meta(body[1:]))
+                pos = end + 1
+            else:
+                pos += 1
+                start = pos
+                while pos < len(s) and s[pos] not in ",()[;":
+                    pos += 1
+                txt = s[start:pos].strip()
+                if txt:
+                    node.length = float(txt)
+        return node
+
+    root = parse_node()
+    # heights: distance from the youngest tip (TreeParser without adjustTipHeights keeps the
+    # lengths; heights are measured back from the most recent tip)
+    def depth(node, d0):
+        node.height = d0
+        for c in node.children:
+            depth(c, d0 + c.length)
+    depth(root, 0.0)
+    stack, maxd = [root], 0.0
+    while stack:
+        nd = stack.pop()
+        maxd = max(maxd, nd.height)
+        stack.extend(nd.children)
+    stack = [root]
+    while stack:
+        nd = stack.pop()
+        nd.height = maxd - nd.height
+        stack.extend(nd.children)
+    return root
+
+
+def _type_index(val, typeSet) -> int:
+    """MultiTypeTree.java:568-582: Integer, rounded Double, or type-set name."""
+    try:
+        return int(val)
+    except (TypeError, ValueError):
+        pass
+    try:
+        return int(round(float(val)))
+    except (TypeError, ValueError):
+        pass
+    if typeSet is None:
+        raise ValueError("non-numeric type %r needs a typeSet" % (val,))
+    return typeSet.getTypeIndex(str(val))
+
+
+def MultiTypeTreeFromNewick(value: str, typeLabel: str = "type", typeSet=None) -> MultiTypeTree:
+    """Build a MultiTypeTree from a 'flat' Newick string whose single-child nodes mark type
+    changes: a single-child node's ``[&typeLabel=k]`` is the type ABOVE it and its height the
+    change time; changes are ordered youngest -> oldest (MultiTypeTree.java:538-665).
+    Leaves are numbered in order of appearance, internal nodes in post-order (root last)."""
+    flat = parse_flat_newick(value)
+    # strip trailing tiny negative zeros
+    leaves, internals = [], []
+    heights, parents, types, ctimes, ctypes, names = {}, {}, {}, {}, {}, {}
+    counter = [0]
+
+    def build(fnode, parent_id):
+        col, tim = [], []
+        while len(fnode.children) == 1:
+            col.append(_type_index(fnode.meta.get(typeLabel), typeSet))
+            tim.append(fnode.height)
+            fnode = fnode.children[0]
+        col.reverse()
+        tim.reverse()
+        my = counter[0]
+        counter[0] += 1
+        heights[my] = fnode.height
+        parents[my] = parent_id
+        types[my] = _type_index(fnode.meta.get(typeLabel), typeSet)
+        ctimes[my], ctypes[my] = tim, col
+        names[my] = fnode.label
+        if len(fnode.children) == 0:
+            leaves.append(my)
+        elif len(fnode.children) == 2:
+            kids = [build(c, my) for c in fnode.children]
+            internals.append(my)       # post-order: children first
+        else:
+            raise ValueError("multifurcations are not supported")
+        return my
+
+    root = build(flat, -1)
+    order = leaves + internals          # new Nr -> temp id
+    newnr = {tmp: i for i, tmp in enumerate(order)}
+    n = len(order)
+    height = np.array([heights[t] for t in order], np.float64)
+    parent = np.array([newnr[parents[t]] if parents[t] >= 0 else -1 for t in order], np.int32)
+    nodeType = np.array([types[t] for t in order], np.uint8)
+    assert newnr[root] == n - 1
+    return MultiTypeTree(height, parent, nodeType, [list(ctimes[t]) for t in order],
+                         [list(ctypes[t]) for t in order],
+                         [names[t] for t in order[:len(leaves)]])
+
+
+def read_nexus_tree(path: str) -> str:
+    """First ``tree NAME = ...;`` Newick string of a NEXUS file."""
+    txt = open(path).read()
+    m = re.search(r"tree\s+\S+\s*=\s*(?:\[&R\]\s*)?(.*?;)", txt, re.S | re.I)
+    if not m:
+        raise ValueError("no tree statement in %s" % path)
+    return m.group(1).strip()
+
+
+# ---------------------------------------------------------------------------- simulation
+
+def simulate_trees(B: int, nLeaves: int, d: int, m: np.ndarray, N: np.ndarray,
+                   leafTypes=None, leafTimes=None, seed: int = 1, nThreads: int = 8) -> TreeBatch:
+    """Synthetic structured-coalescent trees (host-side input generator; the semantics of
+    evolution/tree/StructuredCoalescentMultiTypeTree.java:191-442, see csrc/host/simulator.cpp).
+    Defaults follow SURVEY 8d: leaf type i mod d, leaf height 0.5 * (i mod 4)."""
+    L = _lib.lib()
+    m = _lib.as_c(m, np.float64).reshape(d, d)
+    N = _lib.as_c(N, np.float64)
+    if leafTypes is None:
+        leafTypes = np.arange(nLeaves) % d
+    if leafTimes is None:
+        leafTimes = 0.5 * (np.arange(nLeaves) % 4)
+    lt = _lib.as_c(leafTypes, np.uint8)
+    ltm = _lib.as_c(leafTimes, np.float64)
+    h = L.mtt_sim_run(B, nLeaves, d, _lib.ptr(m), _lib.ptr(N), _lib.ptr(lt), _lib.ptr(ltm),
+                      seed, nThreads)
+    if not h:
+        raise ValueError("mtt_sim_run: bad arguments")
+    try:
+        nNodes = 2 * nLeaves - 1
+        tot = L.mtt_sim_total_changes(h)
+        tb = TreeBatch(np.zeros(B + 1, np.int64), np.zeros(B * nNodes, np.float64),
+                       np.zeros(B * nNodes, np.int32), np.zeros(B * nNodes, np.uint8),
+                       np.zeros(B * nNodes, np.uint16), np.zeros(B + 1, np.int64),
+                       np.zeros(tot, np.float64), np.zeros(tot, np.uint8))
+        L.mtt_sim_export(h, _lib.ptr(tb.nodeOff), _lib.ptr(tb.height), _lib.ptr(tb.parent),
+                         _lib.ptr(tb.nodeType), _lib.ptr(tb.chgCount), _lib.ptr(tb.chgBase),
+                         _lib.ptr(tb.chgTime), _lib.ptr(tb.chgType))
+    finally:
+        L.mtt_sim_free(h)
+    return tb
+
+
+def synthetic_model(d: int):
+    """Migration model of the synthetic workloads: N_c = 1 + 0.25 c,
+    m(c,c') = (1 + 0.1 ((c d + c') mod 3)) / (d - 1)."""
+    N = 1.0 + 0.25 * np.arange(d)
+    m = np.zeros((d, d))
+    for c in range(d):
+        for cp in range(d):
+            if c != cp:
+                m[c, cp] = (1.0 + 0.1 * ((c * d + cp) % 3)) / (d - 1)
+    return m, N

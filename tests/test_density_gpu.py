@@ -1,0 +1,188 @@
+"""GPU parity tests for piece 1 (csrc/k1_density.cu) through the C-ABI, against the oracle.
+Tolerance: |logP_gpu - logP_oracle| <= 1e-9 * |logP_oracle| (north_star: 1e-9 relative, fp64)."""
+import numpy as np
+import pytest
+
+import multitypetree_b200 as mtt
+from oracle import oracle as orc
+from tests.util import concat_batches, load_density_fixture
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _check(tb, m, N, ctx, **kw):
+    want = orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL)
+    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx, **kw)
+    assert got.shape == want.shape
+    np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    return got
+
+
+def test_reference_kat(ctx):
+    """SCLikelihoodTest.java:43-73 through the plugin mirror: -16.52831 within 1e-5."""
+    kat = ("(((A[&state=1]:0.25)[&state=0]:0.25,B[&state=0]:0.5)[&state=0]:1.5,"
+           "(C[&state=0]:1.0,D[&state=0]:1.0)[&state=0]:1.0)[&state=0]:0.0;")
+    mtTree = mtt.MultiTypeTreeFromNewick(kat, "state")
+    migrationModel = mtt.SCMigrationModel([2.0, 1.0], [5.0, 10.0], mtt.TypeSet("A", "B"))
+    likelihood = mtt.StructuredCoalescentTreeDensity(migrationModel=migrationModel,
+                                                    multiTypeTree=mtTree, ctx=ctx)
+    result = likelihood.calculateLogP()
+    assert abs(result - (-16.52831)) < 1e-5
+    assert abs(result - (-11.7 - 3 * np.log(5))) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["kat", "true128", "true64", "ewing3"])
+def test_golden_fixtures(ctx, name):
+    tb, m, N, expected = load_density_fixture(name)
+    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    tol = 1e-5 if name == "kat" else RTOL * abs(expected)
+    assert abs(got[0] - expected) <= tol
+    got_v, valid = mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+    assert valid[0] and got_v[0] == got[0]
+
+
+@pytest.mark.parametrize("n,d,B", [(2, 2, 64), (3, 2, 64), (5, 3, 256), (50, 2, 512),
+                                   (100, 2, 4096), (128, 2, 512), (200, 4, 256),
+                                   (250, 3, 128), (100, 10, 256), (60, 16, 128)])
+def test_simulated_small_trees(ctx, n, d, B):
+    """warp-per-tree path (E <= 512), incl. config 2 (100 tips, 2 demes, 4096 trees)."""
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=1000 * 2 + n)
+    _check(tb, m, N, ctx)
+    _check(tb, m, N, ctx, checkValidity=True)
+
+
+@pytest.mark.parametrize("n,d,B", [(300, 2, 64), (1000, 4, 32), (5000, 8, 8), (7000, 2, 2)])
+def test_simulated_large_trees(ctx, n, d, B):
+    """CTA-per-tree path (512 < E <= 16384): configs 3 and 4 tree sizes."""
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=3000 + n)
+    _check(tb, m, N, ctx)
+    _check(tb, m, N, ctx, checkValidity=True)
+
+
+def test_mixed_sizes_and_ragged_batch(ctx):
+    """Small and large trees interleaved in one batch (warp kernel + queue + block kernel)."""
+    m, N = mtt.synthetic_model(3)
+    parts = [mtt.simulate_trees(b, n, 3, m, N, seed=77 + n)
+             for n, b in ((4, 5), (400, 3), (90, 40), (1500, 2), (127, 9), (2, 3), (170, 20))]
+    tb = concat_batches(parts)
+    assert tb.n_events().min() < 16 and tb.n_events().max() > 3000
+    _check(tb, m, N, ctx)
+    _check(tb, m, N, ctx, checkValidity=True)
+
+
+def test_per_tree_models(ctx):
+    """nModels == B: one migration model per tree (batched proposals / chains)."""
+    rng = np.random.default_rng(5)
+    d, B = 4, 300
+    m0, N0 = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, 80, d, m0, N0, seed=9)
+    m = m0[None] * rng.uniform(0.5, 2.0, size=(B, d, d))
+    N = N0[None] * rng.uniform(0.5, 2.0, size=(B, d))
+    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    want = orc.sc_logp_batch(tb, m, N)
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    big = mtt.simulate_trees(6, 700, d, m0, N0, seed=10)
+    got = mtt.sc_logp_batch(big, m[:6], N[:6], ctx=ctx)
+    np.testing.assert_allclose(got, orc.sc_logp_batch(big, m[:6], N[:6]), rtol=RTOL)
+
+
+def test_zero_rate_gives_minus_inf(ctx):
+    """BSSVS: a switched-off rate on an observed migration gives log(0) = -inf."""
+    tb, m, N, _ = load_density_fixture("kat")
+    m = m.copy()
+    m[1, 0] = 0.0
+    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    assert got[0] == -np.inf and orc.sc_logp_batch(tb, m, N)[0] == -np.inf
+
+
+def test_invalid_trees(ctx):
+    """MultiTypeTree.isValid (MultiTypeTree.java:396-429) + checkValidity (:90-91)."""
+    tb, m, N, _ = load_density_fixture("true128")
+    good = tb.tree(0)
+    rng = np.random.default_rng(3)
+    trees, expect = [], []
+    for k in range(40):
+        t = good.copy()
+        kind = k % 4
+        if kind == 0:
+            expect.append(True)
+        elif kind == 1:      # node type differs from what its children's branches end in
+            node = int(rng.integers(t.getLeafNodeCount(), t.getNodeCount()))
+            t.nodeType[node] = 1 - t.nodeType[node]
+            expect.append(False)
+        elif kind == 2:      # a change above its parent's height
+            node = next(i for i in range(t.getNodeCount())
+                        if t.getChangeCount(i) > 0 and t.parent[i] >= 0)
+            t.changeTimes[node][-1] = float(t.height[t.parent[node]]) + 1.0
+            expect.append(False)
+        else:                # child older than parent
+            node = int(rng.integers(0, t.getLeafNodeCount()))
+            t.height[node] = float(t.height[t.parent[node]]) + 0.5
+            expect.append(False)
+        trees.append(t)
+    b = mtt.TreeBatch.from_trees(trees)
+    lp, valid = mtt.sc_logp_batch(b, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+    want = orc.sc_logp_batch(b, m, N, checkValidity=True)
+    assert list(valid) == expect
+    assert np.array_equal(np.isneginf(lp), np.isneginf(want))
+    ok = np.array(expect)
+    np.testing.assert_allclose(lp[ok], want[ok], rtol=RTOL)
+    assert good.isValid(ctx)
+    assert not trees[1].isValid(ctx)
+
+
+def test_quantisation_ties_are_repaired(ctx):
+    """Events closer than the 24-bit time quantum of the packed sort key must still be ordered
+    exactly: a huge root height squeezes all other events into a few quanta."""
+    m, N = mtt.synthetic_model(2)
+    tb = mtt.simulate_trees(64, 100, 2, m, N, seed=4242)
+    tb.height = tb.height.copy()
+    nN = 199
+    roots = np.arange(64) * nN + nN - 1
+    tb.height[roots] += 1e7          # quantum becomes ~0.6 time units
+    _check(tb, m, N, ctx)
+    # same for the CTA path (38-bit quantum): root at 1e13
+    big = mtt.simulate_trees(4, 600, 2, m, N, seed=4243)
+    big.height = big.height.copy()
+    big.height[np.arange(4) * 1199 + 1198] += 1e13
+    _check(big, m, N, ctx)
+
+
+def test_root_branch_changes_ignored(ctx):
+    """StructuredCoalescentTreeDensity.java:161-162: changes above the root do not count."""
+    tb, m, N, expected = load_density_fixture("kat")
+    t = tb.tree(0)
+    root = t.getRoot()
+    b = mtt.TreeBatch.from_trees([t])
+    # hand-build a batch that DOES carry root changes (from_trees never exports them)
+    cnt = b.chgCount.copy()
+    cnt[root] = 2
+    b2 = mtt.TreeBatch(b.nodeOff, b.height, b.parent, b.nodeType, cnt,
+                       np.array([0, 3], np.int64), np.append(b.chgTime, [2.5, 3.0]),
+                       np.append(b.chgType, [1, 0]).astype(np.uint8))
+    got = mtt.sc_logp_batch(b2, m, N, ctx=ctx, with_parent=True)
+    assert abs(got[0] - expected) < 1e-5
+
+
+def test_batch_size_independence_and_determinism(ctx):
+    m, N = mtt.synthetic_model(2)
+    tb = mtt.simulate_trees(20000, 100, 2, m, N, seed=31337)
+    a = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    b = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    assert np.array_equal(a, b)                       # bit-reproducible run to run
+    part = mtt.sc_logp_batch(tb.slice(777, 1500), m, N, ctx=ctx)
+    assert np.array_equal(part, a[777:1500])          # independent of batch composition
+    want = orc.sc_logp_batch(tb, m, N, variant=orc.SORTED, nThreads=8)
+    np.testing.assert_allclose(a, want, rtol=RTOL)
+
+
+def test_api_errors(ctx):
+    tb, m, N, _ = load_density_fixture("kat")
+    with pytest.raises(mtt.MttError):
+        mtt.sc_logp_batch(tb, np.zeros((17, 17)), np.ones(17), ctx=ctx)      # d > MTT_MAX_DEMES
+    with pytest.raises(mtt.MttError):
+        mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx, with_parent=False)
+    assert mtt.sc_logp_batch(tb.slice(0, 0), m, N, ctx=ctx).shape == (0,)   # empty batch

@@ -1,0 +1,511 @@
+#!/usr/bin/env python
+"""bench.py -- throughput of the B200-native MultiTypeTree likelihood hot path.
+
+Headline workload (BASELINE.json configs[1], "cfg2"): batched structured-coalescent logP of
+simulated 2-deme 100-tip multi-type trees, density only.  One step = one pass of the density
+kernel over one batch of B trees per GPU (B = 2^20 by default = 256 x the 4096-tree batch the
+config names, so that the ~2.6 GB of inputs exceed the 126 MB L2; the literal 4096-tree batch
+is timed as well, with an L2 flush before every launch, and reported under "cfg2_b4096").
+
+  value         trees/s, inputs resident in HBM, CUDA-event timed, max over ranks
+  e2e           same metric through the reference-facing C-ABI call mtt_sc_logp_batch with
+                pinned HOST buffers: host->device copies and the device->host read of logP are
+                inside the timed region
+  roofline      algorithmic bytes (12 B per event + 8 B per tree) / kernel time vs
+                the measured HBM copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline  the oracle's faithful restatement of the reference algorithm on the host cores
+
+  --impl reference   times the reference's CPU algorithm (oracle port; no JVM exists here) on
+                     the same config with all host threads.
+  --workload peel|retype   the other pieces (configs 3 and 5) as separate bench lines.
+
+Multi-GPU: one process per GPU (torchrun); trees are sharded across ranks, no collective on
+the data path (weak scaling).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "structured-coalescent+tree logP evals/sec (batched trees) at 1/2/4/8 B200"
+FALLBACK_HBM_GBS = 6650.0
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None,
+                "sm_max_mhz": float(max(mx)) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def dist_setup(n_gpus):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def to_dev(a):
+    """device copy with 64 elements of slack (bulk copies over-read <= 15 B)."""
+    import torch
+    t = torch.from_numpy(np.ascontiguousarray(a).ravel())
+    out = torch.zeros(t.numel() + 64, dtype=t.dtype, device="cuda")
+    out[:t.numel()] = t.cuda()
+    return out
+
+
+# ------------------------------------------------------------------ cfg2: density
+
+def make_cfg2(B, rank, n=100, d=2, threads=8):
+    import multitypetree_b200 as mtt
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=2000 + rank * B, nThreads=threads)
+    return tb, m, N
+
+
+def cpu_density(tb, m, N, sample, threads):
+    """oracle faithful path (the reference's O(E x active) algorithm) on `sample` trees."""
+    from oracle import oracle as orc
+    sub = tb.slice(0, sample)
+    orc.sc_logp_batch(tb.slice(0, min(sample, 256)), m, N, variant=orc.FAITHFUL, nThreads=threads)
+    t0 = time.perf_counter()
+    orc.sc_logp_batch(sub, m, N, variant=orc.FAITHFUL, nThreads=threads)
+    dt = time.perf_counter() - t0
+    return sample / dt, dt
+
+
+def bench_density(args):
+    import torch
+    import multitypetree_b200 as mtt
+    from multitypetree_b200 import _lib
+    world, rank, local = dist_setup(args.gpus)
+    cores = os.cpu_count() or 1
+    threads = max(1, cores // world)
+    B = args.batch
+    tb, m, N = make_cfg2(B, rank, threads=threads)
+    ev = tb.n_events()
+    alg_bytes = float(12 * ev.sum() + 8 * B)
+
+    L = _lib.lib()
+    ctx = mtt.Context(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    L.mtt_sc_set_max_tree_events(ctx.handle, int(ev.max()))
+
+    dm, dN = to_dev(m), to_dev(N)
+    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgCount, tb.chgBase,
+                               tb.chgTime, tb.chgType)]
+    logP = torch.zeros(B, dtype=torch.float64, device="cuda")
+
+    def step(Bs=B, out=logP):
+        ctx.check(L.mtt_sc_logp_batch_dev(
+            ctx.handle, Bs, 2, 1, dm.data_ptr(), dN.data_ptr(), dev[0].data_ptr(),
+            dev[1].data_ptr(), None, dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
+            dev[5].data_ptr(), dev[6].data_ptr(), 0, out.data_ptr(), None))
+
+    for _ in range(args.warmup):
+        step()
+    barrier(world)
+    launches0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    launches = ctx.launch_count() - launches0
+    ms_per_step = ms / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    kernel_ms = e0.elapsed_time(e1) / args.steps          # one kernel launch per step
+    hbm, hbm_src = peaks()
+    achieved = alg_bytes / (kernel_ms * 1e-3) / 1e9
+
+    # ---- the literal 4096-tree batch of the config, L2 flushed before every launch
+    small = None
+    if rank == 0:
+        flush = torch.empty(192 << 20, dtype=torch.uint8, device="cuda")
+        out4k = torch.zeros(4096, dtype=torch.float64, device="cuda")
+        ts = []
+        for i in range(args.warmup + 10):
+            flush.fill_(i & 255)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            step(4096, out4k)
+            b.record(stream)
+            torch.cuda.synchronize()
+            if i >= args.warmup:
+                ts.append(a.elapsed_time(b))
+        small = {"batch": 4096, "ms": float(np.median(ts)),
+                 "value": 4096 / (float(np.median(ts)) * 1e-3), "l2": "flushed before each launch"}
+        del flush
+
+    # ---- end to end through the C-ABI with pinned host buffers
+    host = [np.ascontiguousarray(x) for x in (m, N, tb.nodeOff, tb.height, tb.nodeType,
+                                              tb.chgCount, tb.chgBase, tb.chgTime, tb.chgType)]
+    out_h = np.empty(B, np.float64)
+    pinned = []
+    for a in host + [out_h]:
+        if L.mtt_host_register(a.ctypes.data, a.nbytes) == 0:
+            pinned.append(a)
+    h2d = int(sum(a.nbytes for a in host))
+    d2h = int(out_h.nbytes)
+
+    def e2e_step():
+        ctx.check(L.mtt_sc_logp_batch(
+            ctx.handle, B, 2, 1, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(host[2]),
+            _lib.ptr(host[3]), None, _lib.ptr(host[4]), _lib.ptr(host[5]), _lib.ptr(host[6]),
+            _lib.ptr(host[7]), _lib.ptr(host[8]), 0, _lib.ptr(out_h), None))
+
+    e2e_steps = max(3, min(args.steps, 10))
+    for _ in range(2):
+        e2e_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        e2e_step()
+    barrier(world)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    e2e_value = B * world * e2e_steps / e2e_s
+    for a in pinned:
+        L.mtt_host_unregister(a.ctypes.data)
+    # device-resident and end-to-end paths must agree bit for bit
+    assert np.array_equal(out_h, logP.cpu().numpy()), "e2e and device-resident results differ"
+
+    if rank != 0:
+        return
+    sample = min(B, 1 << 19)
+    cpu_v, cpu_dt = cpu_density(tb, m, N, sample, cores)
+    # parity spot-check of the timed results against the oracle (checker only)
+    from oracle import oracle as orc
+    want = orc.sc_logp_batch(tb.slice(0, 4096), m, N, variant=orc.SORTED, nThreads=cores)
+    rel = float(np.max(np.abs(out_h[:4096] - want) / np.abs(want)))
+    assert rel < 1e-9, "parity check failed: %g" % rel
+
+    line = {
+        "metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (structured-coalescent Gillespie simulator, SURVEY 8d; seeds 2000+)",
+        "config": {
+            "workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
+                        "density only (extraction + time ordering + interval scan on device)",
+            "batch_per_gpu": B, "tips": 100, "demes": 2,
+            "events_per_tree_mean": float(ev.mean()), "events_per_tree_max": int(ev.max()),
+            "input_bytes_per_gpu": int(tb.nbytes()),
+            "l2": "inputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (tb.nbytes() / 1e9),
+            "parallelism": "trees sharded across %d GPU(s), no data-path collective" % world,
+        },
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
+                     "frac": achieved / hbm, "traffic": None, "peak_source": hbm_src,
+                     "kernel": "k1_density_warp", "algorithmic_bytes_per_launch": alg_bytes,
+                     "kernel_ms": kernel_ms},
+        "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d trees of the same batch, oracle faithful restatement of "
+                                   "the reference algorithm (not a JVM), %.1f s" % (sample, cpu_dt)},
+        "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                "pinned": len(pinned) == len(host) + 1},
+        "gpu_launches": int(launches),
+        "clocks": clk.summary(),
+        "cfg2_b4096": small,
+        "parity_max_rel_err_vs_oracle": rel,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------ reference arm
+
+def bench_reference(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    sample = 1 << 17
+    tb, m, N = make_cfg2(sample, 0, threads=cores)
+    from oracle import oracle as orc
+    for _ in range(max(1, min(args.warmup, 3))):
+        orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL, nThreads=cores)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL, nThreads=cores)
+    dt = time.perf_counter() - t0
+    v = sample * args.steps / dt
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (same generator and seeds as the GPU arm)",
+        "config": {"workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
+                               "density only", "batch_per_step": sample, "tips": 100, "demes": 2},
+        "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
+                         "sample": "%d trees per step; C restatement of "
+                                   "StructuredCoalescentTreeDensity (the reference is Java and no "
+                                   "JVM exists on this box)" % sample},
+        "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------ other pieces
+
+def bench_peel(args):
+    """cfg3: 4-deme 1000-tip trees, 10k-site alignment, density + peeling per evaluation."""
+    import torch
+    import multitypetree_b200 as mtt
+    from multitypetree_b200 import _lib
+    from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, TreeLikelihood,
+                                               simulate_alignment)
+    world, rank, local = dist_setup(args.gpus)
+    cores = os.cpu_count() or 1
+    n, d, sites, B = 1000, 4, 10000, args.batch if args.batch != (1 << 20) else 64
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=3000 + rank * B, nThreads=max(1, cores // world))
+    nN = 2 * n - 1
+    par, hgt = tb.parent.reshape(B, nN), tb.height.reshape(B, nN)
+    f = np.array([.25] * 4)
+    clock = 0.2 / float(hgt[0].max())
+    ref = mtt.simulate_trees(1, n, d, m, N, seed=3000)
+    al = Alignment(states=simulate_alignment(ref.parent, ref.height, sites, 2.0, f, clock, seed=3000))
+    P = al.getPatternCount()
+    ctx = mtt.Context(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    L = _lib.lib()
+    tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f), mutationRate=clock), ctx=ctx)
+    dpar, dhgt = to_dev(par), to_dev(hgt)
+    out = torch.zeros(B, dtype=torch.float64, device="cuda")
+    dm, dN = to_dev(m), to_dev(N)
+    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgCount, tb.chgBase,
+                               tb.chgTime, tb.chgType)]
+    dens = torch.zeros(B, dtype=torch.float64, device="cuda")
+    L.mtt_sc_set_max_tree_events(ctx.handle, int(tb.n_events().max()))
+
+    def step():
+        ctx.check(L.mtt_peel_logl_batch_dev(tl.handle, B, dpar.data_ptr(), dhgt.data_ptr(),
+                                            out.data_ptr()))
+        ctx.check(L.mtt_sc_logp_batch_dev(
+            ctx.handle, B, d, 1, dm.data_ptr(), dN.data_ptr(), dev[0].data_ptr(),
+            dev[1].data_ptr(), None, dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
+            dev[5].data_ptr(), dev[6].data_ptr(), 0, dens.data_ptr(), None))
+
+    for _ in range(args.warmup):
+        step()
+    barrier(world)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(stream)
+        for _ in range(args.steps):
+            step()
+        e1.record(stream)
+        barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    launches = ctx.launch_count() - l0
+    # e2e: host buffers through the C-ABI
+    t0 = time.perf_counter()
+    for _ in range(3):
+        lp = tl.calculateLogPBatch(par, hgt)
+        ld = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    barrier(world)
+    e2e = B * world * 3 / max_over_ranks(time.perf_counter() - t0, world)
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    k = min(B, 8)
+    t0 = time.perf_counter()
+    want = orc.tree_likelihood_batch(al.patterns, al.patternWeight, par[:k], hgt[:k], [clock], [1.0],
+                                     f, 2.0, nThreads=min(cores, k))
+    cpu_dt = time.perf_counter() - t0
+    rel = float(np.max(np.abs(lp[:k] - want) / np.abs(want)))
+    S, C = 4, 1
+    alg = 8.0 * S * C * P * (2 * n - 3) + 4.0 * n * P + 8.0 * P + 8.0 * S * S * C * (2 * n - 2)
+    flop = (n - 1) * P * C * (4 * S * S + S)
+    hbm, src = peaks()
+    print(json.dumps({
+        "metric": "cfg3 (density + peeling) evaluations/s", "value": B * world / (ms * 1e-3),
+        "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg3: 4-deme 1000-tip trees x 10k-site alignment "
+                               "(%d patterns), density + peeling" % P, "batch_per_gpu": B},
+        "roofline": {"bound": "hbm", "achieved": alg * B / (ms * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": alg * B / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "peak_source": src, "kernel": "k2_peel",
+                     "note": "algorithmic bytes of the materialised-partials model (SURVEY 8d); "
+                             "the kernel keeps partials on chip, so frac may exceed 1",
+                     "fp64_tflops": flop * B / (ms * 1e-3) / 1e12},
+        "cpu_baseline": {"value": k / cpu_dt, "unit": "evals/s", "cores": min(cores, k),
+                         "kind": "port", "sample": "%d trees, peeling only" % k},
+        "e2e": {"value": e2e, "unit": "evals/s",
+                "h2d_bytes_per_step": int(par.nbytes + hgt.nbytes + tb.nbytes()),
+                "d2h_bytes_per_step": int(16 * B)},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "parity_max_rel_err_vs_oracle": rel}))
+
+
+def bench_retype(args):
+    """cfg5: NodeRetype-style uniformization sweep, chains x 10-deme models."""
+    import multitypetree_b200 as mtt
+    from multitypetree_b200.uniformization import UniformizationModels
+    world, rank, local = dist_setup(args.gpus)
+    d, chains = 10, 64 // world if world <= 64 else 1
+    jobs_per_chain = args.batch if args.batch != (1 << 20) else 4096
+    rng = np.random.default_rng(5000 + rank)
+    ms_ = np.stack([mtt.synthetic_model(d)[0] * rng.uniform(0.5, 2.0) for _ in range(chains)])
+    ctx = mtt.Context(local)
+    um = UniformizationModels(ms_, ctx=ctx)
+    nJobs = chains * jobs_per_chain
+    brOff = np.arange(nJobs + 1) * 3
+    nBr = 3 * nJobs
+    t0_ = rng.uniform(0, 5, nBr)
+    t1_ = t0_ + rng.exponential(1.5, nBr)
+    a = rng.integers(0, d, nBr)
+    b = rng.integers(0, d, nBr)
+    model = np.repeat(np.arange(chains), 3 * jobs_per_chain)
+    W = 256
+    u = rng.random(nJobs * W)
+    uOff = np.arange(nJobs + 1) * W
+    for _ in range(args.warmup):
+        r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=32, model=model)
+    barrier(world)
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=32, model=model)
+    barrier(world)
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    if rank != 0:
+        return
+    print(json.dumps({
+        "metric": "cfg5 uniformization branch retypes/s (end to end, host buffers)",
+        "value": nBr * world * args.steps / dt, "unit": "branches/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg5: %d chains x %d NodeRetype-shaped jobs (3 branches), d=10"
+                               % (chains * world, jobs_per_chain)},
+        "ok_fraction": float((r["status"] == 0).mean()),
+        "gpu_launches": int(ctx.launch_count() - l0)}))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="density", choices=["density", "peel", "retype"])
+    ap.add_argument("--batch", type=int, default=1 << 20, help="trees per GPU per step")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    if args.impl == "reference":
+        return bench_reference(args)
+    if args.workload == "peel":
+        return bench_peel(args)
+    if args.workload == "retype":
+        return bench_retype(args)
+    return bench_density(args)
+
+
+if __name__ == "__main__":
+    main()
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass

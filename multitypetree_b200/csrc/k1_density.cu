@@ -25,6 +25,7 @@
 #include "mtt_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 namespace {
 
@@ -315,8 +316,23 @@ __device__ __forceinline__ bool ce_td(double &ta, uint32_t &da, double &tb, uint
     return false;
 }
 
+template <int NW>
+__device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
+{
+    unsigned long long w = c.w[0];
+    if (NW > 1) {
+#pragma unroll
+        for (int i = 1; i < NW; i++)
+            if ((deme >> 2) == i)
+                w = c.w[i];
+    }
+    return (int)((w >> (16 * (deme & 3))) & 0xffffu);
+}
+
 // One staged tree, EPL events per lane (E <= 32 * EPL).  Returns the warp-reduced logP in
-// lane 0; `ok` is the validity verdict (all lanes).
+// lane 0; `okOut` is the validity verdict (all lanes).  Code size matters here (the body
+// must stay instruction-cache resident): only the phases that index register arrays are
+// unrolled.
 template <int NW, bool HAS_PARENT, int EPL>
 __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
                                                const StageLayout &L, uint16_t *desc, int n, int M,
@@ -333,58 +349,62 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     const uint16_t *sK = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);
     const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
 
-    // ---- phase A: descriptors (node-centric), validity
+    // ---- phase A: descriptors (lane owns nodes [EPL*lane, EPL*lane+EPL)), validity
     bool ok = true;
-    int carry = 0;
+    {
+        const int e0 = EPL * lane;
+        int mine = 0;
+#pragma unroll 1
+        for (int j = 0; j < EPL; j++)
+            if (e0 + j < n)
+                mine += sK[e0 + j];
+        int incl = mine;
 #pragma unroll
-    for (int k = 0; k < EPL; k++) {
-        const int e = lane + 32 * k;
-        if (32 * k < n) {                                    // warp-uniform
-            int c = (e < n) ? (int)sK[e] : 0;
-            int incl = c;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int v = __shfl_up_sync(FULL_MASK, incl, o);
-                if (lane >= o)
-                    incl += v;
-            }
-            const int off = carry + incl - c;
-            carry += __shfl_sync(FULL_MASK, incl, 31);
-            if (off + c > M) {                               // inconsistent chgCount / chgBase
-                c = max(0, M - off);
-                ok = false;
-            }
-            if (e < n) {
-                int type = sT[e];
-                desc[e] = (uint16_t)(((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 |
-                                     type << 5);
-                const int par = HAS_PARENT ? sP[e] : 0;
-                const bool isRoot = HAS_PARENT && par < 0;
-                double lastT = sH[e];
-                for (int j = 0; j < c; j++) {
-                    const int to = sCT[off + j];
-                    desc[n + off + j] =
-                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
-                    if (HAS_PARENT) {
-                        const double tj = sC[off + j];
-                        ok = ok && !(lastT > tj);            // MultiTypeTree.java:404-405
-                        lastT = tj;
-                    }
-                    type = to;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        int off = incl - mine;
+        if (incl > M) {                                      // inconsistent chgCount / chgBase
+            ok = false;
+            off = 0;
+            mine = 0;
+        }
+#pragma unroll 1
+        for (int j = 0; j < EPL; j++) {
+            const int e = e0 + j;
+            if (e >= n)
+                break;
+            const int c = (mine > 0) ? (int)sK[e] : 0;
+            int type = sT[e];
+            desc[e] = (uint16_t)(((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | type << 5);
+            const int par = HAS_PARENT ? sP[e] : 0;
+            const bool isRoot = HAS_PARENT && par < 0;
+            double lastT = HAS_PARENT ? sH[e] : 0.0;
+            for (int q = 0; q < c; q++) {
+                const int to = sCT[off + q];
+                desc[n + off + q] =
+                    (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
+                if (HAS_PARENT) {
+                    const double tq = sC[off + q];
+                    ok = ok && !(lastT > tq);                // MultiTypeTree.java:404-405
+                    lastT = tq;
                 }
-                if (HAS_PARENT && !isRoot) {
-                    ok = ok && !(lastT > sH[par]);           // :401, :408-409
-                    ok = ok && (type == (int)sT[par]);       // :421-422
-                }
+                type = to;
+            }
+            off += c;
+            if (HAS_PARENT && !isRoot) {
+                ok = ok && !(lastT > sH[par]);               // :401, :408-409
+                ok = ok && (type == (int)sT[par]);           // :421-422
             }
         }
     }
-    if (HAS_PARENT)
-        ok = __all_sync(FULL_MASK, ok);
+    ok = __all_sync(FULL_MASK, ok);
     okOut = ok;
     __syncwarp();
 
-    // ---- keys: quantised time | event index
+    // ---- keys: quantised time | event index (interleaved, conflict-free reads)
     double tm[EPL];
     uint32_t ds[EPL];
     double lo = INFINITY, hi = -INFINITY;
@@ -410,14 +430,9 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     uint32_t key[EPL];
 #pragma unroll
     for (int k = 0; k < EPL; k++) {
-        const int e = lane + 32 * k;
-        if (tm[k] < INFINITY) {
-            uint32_t q = (uint32_t)((tm[k] - lo) * scale);
-            q = min(q, QMAX);
-            key[k] = (q << IDX_BITS) | (uint32_t)e;
-        } else {
-            key[k] = 0xffffffffu;
-        }
+        uint32_t q = (uint32_t)((tm[k] - lo) * scale);
+        q = min(q, QMAX);
+        key[k] = (tm[k] < INFINITY) ? ((q << IDX_BITS) | (uint32_t)(lane + 32 * k)) : 0xffffffffu;
     }
 
     // ---- phase B: order
@@ -426,14 +441,11 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     // ---- phase C: exact times + descriptors in sorted order, then repair quantisation ties
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        const int idx = key[r] & ((1 << IDX_BITS) - 1);
-        if (key[r] == 0xffffffffu) {
-            tm[r] = INFINITY;
-            ds[r] = KIND_NONE << 10;
-        } else {
-            tm[r] = (idx < n) ? sH[idx] : sC[idx - n];
-            ds[r] = desc[idx];
-        }
+        const bool pad = key[r] == 0xffffffffu;
+        const int idx = pad ? 0 : (int)(key[r] & ((1u << IDX_BITS) - 1));
+        const double x = (idx < n) ? sH[idx] : sC[idx - n];
+        tm[r] = pad ? INFINITY : x;
+        ds[r] = pad ? (uint32_t)(KIND_NONE << 10) : (uint32_t)desc[idx];
     }
     {
         bool swapped;
@@ -449,22 +461,24 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
             const double nt = __shfl_down_sync(FULL_MASK, tm[0], 1);
             const uint32_t nd = __shfl_down_sync(FULL_MASK, ds[0], 1);
             const bool sw = (lane < 31) && (tm[EPL - 1] > nt);
-            const double pt = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
-            const uint32_t pd = __shfl_up_sync(FULL_MASK, ds[EPL - 1], 1);
-            const bool swPrev = (__shfl_up_sync(FULL_MASK, (int)sw, 1) != 0) && lane > 0;
-            if (sw) {
-                tm[EPL - 1] = nt;
-                ds[EPL - 1] = nd;
+            const unsigned swMask = __ballot_sync(FULL_MASK, sw);
+            if (swMask) {                                    // rare
+                const double pt = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
+                const uint32_t pd = __shfl_up_sync(FULL_MASK, ds[EPL - 1], 1);
+                if (sw) {
+                    tm[EPL - 1] = nt;
+                    ds[EPL - 1] = nd;
+                }
+                if (lane > 0 && ((swMask >> (lane - 1)) & 1)) {
+                    tm[0] = pt;
+                    ds[0] = pd;
+                }
             }
-            if (swPrev) {
-                tm[0] = pt;
-                ds[0] = pd;
-            }
-            swapped = __any_sync(FULL_MASK, swapped || sw);
+            swapped = __any_sync(FULL_MASK, swapped) || swMask != 0;
         } while (swapped);
     }
 
-    // ---- phase D: lineage counts by prefix sum, interval integration
+    // ---- phase D: lineage counts by prefix sum, interval integration with a running lambda
     Counts<NW> local;
 #pragma unroll
     for (int i = 0; i < NW; i++)
@@ -487,26 +501,48 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     double prevT = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
     if (lane == 0)
         prevT = tm[0];
+    // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
+    double lambda = 0.0;
+#pragma unroll 1
+    for (int c = 0; c < d; c++) {
+        const double kd = (double)cnt_get<NW>(base, c);
+        lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+    }
     double acc = 0.0;
 #pragma unroll
     for (int r = 0; r < EPL; r++) {
-        if (tm[r] < INFINITY) {
+        const int kind = (ds[r] >> 10) & 3, from = (ds[r] >> 5) & 31, to = ds[r] & 31;
+        if (kind != KIND_NONE) {
             const double dt = tm[r] - prevT;
             if (dt > 0.0)                                    // StructuredCoalescentTreeDensity.java:108
-                acc -= dt * cnt_lambda<NW>(base, tab, d);
-            if (lane != 0 || r != 0)                         // event 0 is skipped (:101)
-                acc += event_term(ds[r], tab, d);
+                acc -= dt * lambda;
             prevT = tm[r];
+            const bool first = (lane == 0 && r == 0);        // event 0 is skipped (:101)
+            if (kind != KIND_SAMPLE) {                       // a lineage leaves deme `from`
+                if (!first)
+                    acc += (kind == KIND_COALESCE) ? tab->logInvN[from] : tab->logM[from * d + to];
+                const double kd = (double)cnt_get<NW>(base, from);
+                lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
+                cnt_add<NW>(base, from, -1);
+            }
+            if (kind != KIND_COALESCE) {                     // a lineage enters a deme
+                const int a = (kind == KIND_MIGRATE) ? to : from;
+                const double kd = (double)cnt_get<NW>(base, a);
+                lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
+                cnt_add<NW>(base, a, 1);
+            }
         }
-        cnt_apply<NW>(base, ds[r]);
     }
     return warp_sum_down(acc);
 }
 
-template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL>
+// MODE 0: EPL 8 only (E <= 256; larger trees are queued)   MODE 1: EPL 16 only (E <= 512)
+// MODE 2: per tree, EPL 8 when E <= 256 else EPL 16
+template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int MODE>
 __global__ void __launch_bounds__(W_WARPS * 32, 2)
 k1_density_warp(const K1Params p)
 {
+    constexpr int EMAX = (MODE == 0) ? 256 : 512;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tabs = reinterpret_cast<ModelTab *>(smem_raw);
     constexpr int nTabs = PER_TREE_MODEL ? W_WARPS : 1;
@@ -533,15 +569,16 @@ k1_density_warp(const K1Params p)
 
     TreeSpan cur = load_span(p, t);
     TreeSpan nxt = load_span(p, t + nWarpsTotal);
-    bool curBig = cur.n + cur.M > W_EMAX;
+    bool curBig = cur.n + cur.M > EMAX;
     if (t < p.B && !curBig && lane == 0)
         issue_tree<HAS_PARENT>(p, cur, &ws->st[0], (uint64_t *)&ws->bar[0]);
 
+#pragma unroll 1
     for (int it = 0; t < p.B; it++, t += nWarpsTotal) {
         const int sidx = it & 1;
         // ---- prefetch this warp's next tree into the other stage
         const long long tn = t + nWarpsTotal;
-        const bool nxtBig = nxt.n + nxt.M > W_EMAX;
+        const bool nxtBig = nxt.n + nxt.M > EMAX;
         if (tn < p.B && !nxtBig && lane == 0)
             issue_tree<HAS_PARENT>(p, nxt, &ws->st[sidx ^ 1], (uint64_t *)&ws->bar[sidx ^ 1]);
         const TreeSpan nxt2 = load_span(p, tn + nWarpsTotal);
@@ -568,7 +605,7 @@ k1_density_warp(const K1Params p)
             }
             bool ok = true;
             double acc;
-            if (cur.n + cur.M <= 256)
+            if (MODE == 0 || (MODE == 2 && cur.n + cur.M <= 256))
                 acc = process_tree<NW, HAS_PARENT, 8>(st, L, ws->desc, cur.n, cur.M, tab, d, lane,
                                                       ok);
             else
@@ -854,16 +891,11 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
     }
 }
 
-__global__ void k1_reset_queue(int *queue)
-{
-    queue[0] = 0;
-}
-
-template <int NW, bool HP, bool PT>
+template <int NW, bool HP, bool PT, int MODE>
 int launch_warp(mtt_ctx *ctx, const K1Params &p)
 {
     size_t smem = sizeof(ModelTab) * (PT ? W_WARPS : 1) + sizeof(WarpSmem<HP>) * W_WARPS;
-    auto kern = k1_density_warp<NW, HP, PT>;
+    auto kern = k1_density_warp<NW, HP, PT, MODE>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     int perSM = 1;
@@ -877,6 +909,17 @@ int launch_warp(mtt_ctx *ctx, const K1Params &p)
     kern<<<(unsigned)grid, W_WARPS * 32, smem, ctx->stream>>>(p);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
+}
+
+template <int NW, int MODE>
+int launch_warp_mode(mtt_ctx *ctx, const K1Params &p)
+{
+    const bool hp = p.parent != nullptr, pt = p.nModels > 1;
+    if (hp)
+        return pt ? launch_warp<NW, true, true, MODE>(ctx, p)
+                  : launch_warp<NW, true, false, MODE>(ctx, p);
+    return pt ? launch_warp<NW, false, true, MODE>(ctx, p)
+              : launch_warp<NW, false, false, MODE>(ctx, p);
 }
 
 template <int NW>
@@ -898,39 +941,47 @@ int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long l
     return MTT_OK;
 }
 
+// maxEvents: > 0 upper bound on nodes + changes of any tree, 0 unknown
 template <int NW>
 int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
 {
-    const bool hp = p.parent != nullptr, pt = p.nModels > 1;
     int Ecap = MTT_MAX_TREE_EVENTS;
     if (maxEvents > 0) {
-        Ecap = 512;
+        Ecap = 1024;
         while (Ecap < maxEvents)
             Ecap <<= 1;
         if (Ecap > MTT_MAX_TREE_EVENTS)
             Ecap = MTT_MAX_TREE_EVENTS;
     }
-    // every tree certainly large -> block kernel directly
-    if (maxEvents < 0)
-        return launch_block<NW>(ctx, p, Ecap, 0, p.B);
-    k1_reset_queue<<<1, 1, 0, ctx->stream>>>(p.queue);
-    MTT_CHECK_LAUNCH(ctx);
-    int rc;
-    if (hp)
-        rc = pt ? launch_warp<NW, true, true>(ctx, p) : launch_warp<NW, true, false>(ctx, p);
-    else
-        rc = pt ? launch_warp<NW, false, true>(ctx, p) : launch_warp<NW, false, false>(ctx, p);
+    static const char *force = getenv("MTT_K1_FORCE_MODE");      // development knob
+    if (force && force[0] == '0') {                 // EPL-8 warp path + block kernel for the rest
+        int rc0 = launch_warp_mode<NW, 0>(ctx, p);
+        if (rc0 != MTT_OK || (maxEvents > 0 && maxEvents <= 256))
+            return rc0;
+        rc0 = launch_block<NW>(ctx, p, Ecap, 1, 0);
+        if (rc0 != MTT_OK)
+            return rc0;
+        MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
+        return MTT_OK;
+    }
+    if (maxEvents > 0 && maxEvents <= 256 && !(force && force[0] == '2'))
+        return launch_warp_mode<NW, 0>(ctx, p);     // one launch, nothing can be queued
+    if (maxEvents > 0 && maxEvents <= W_EMAX)
+        return launch_warp_mode<NW, 2>(ctx, p);
+    // some trees may exceed the warp path: they are queued and consumed by the block kernel,
+    // which leaves the queue counter at zero again for the next call
+    int rc = launch_warp_mode<NW, 2>(ctx, p);
     if (rc != MTT_OK)
         return rc;
-    if (maxEvents == 0 || maxEvents > W_EMAX)
-        return launch_block<NW>(ctx, p, Ecap, 1, 0);
+    rc = launch_block<NW>(ctx, p, Ecap, 1, 0);
+    if (rc != MTT_OK)
+        return rc;
+    MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
     return MTT_OK;
 }
 
 }  // namespace
 
-// maxEvents: > 0 upper bound on nodes+changes of any tree (known to the caller), 0 unknown,
-// < 0 "all trees exceed the warp path" (|maxEvents| is the bound).
 int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
                   const double *N, const int64_t *nodeOff, const double *height,
                   const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
@@ -951,16 +1002,17 @@ int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double 
     p.nodeType = nodeType; p.chgCount = chgCount; p.chgBase = (const long long *)chgBase;
     p.chgTime = chgTime; p.chgType = chgType; p.checkValidity = checkValidity;
     p.logP = logP; p.valid = valid;
-    p.queue = (int *)mtt_buf(ctx, BUF_D_QUEUE, sizeof(int) * (size_t)(B + 1));
+    // work queue for the block kernel: [0] = count (zero between calls), [1..] = tree indices
+    const size_t need = sizeof(int) * (size_t)(B + 1);
+    const bool fresh = need + 256 > ctx->bufs[BUF_D_QUEUE].cap;
+    p.queue = (int *)mtt_buf(ctx, BUF_D_QUEUE, need);
     if (!p.queue)
         return MTT_ERR_CUDA;
-    long long me = maxEvents;
-    if (me > 0 && me <= W_EMAX)
-        me = W_EMAX;
-    // all-large shortcut only when the caller says so
+    if (fresh)
+        MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
     if (d <= 4)
-        return launch_all<1>(ctx, p, me);
+        return launch_all<1>(ctx, p, maxEvents);
     if (d <= 8)
-        return launch_all<2>(ctx, p, me);
-    return launch_all<4>(ctx, p, me);
+        return launch_all<2>(ctx, p, maxEvents);
+    return launch_all<4>(ctx, p, maxEvents);
 }

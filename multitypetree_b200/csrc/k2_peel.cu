@@ -1,0 +1,844 @@
+// k2_peel.cu -- piece 2: batched Felsenstein peeling over site patterns on sm_100a.
+//
+// Replaces BEAST 2 core's TreeLikelihood.calculateLogP + BeerLikelihoodCore (wired by the
+// reference at examples/structuredCoalescent.xml:568-572, fxtemplates/MultiTypeTree.xml:184-197)
+// for 4-state data: per-branch transition matrices, the three pruning cases (states x states,
+// states x partials, partials x partials), per-node rescaling, root integration over rate
+// categories and frequencies, and the weighted sum of pattern log-likelihoods.
+//
+// Design (full re-evaluation of B candidate trees that share one alignment):
+//   k2_prepare  one CTA per tree.  Builds child lists from parent[], orders the post-order
+//               traversal Sethi-Ullman style (the child needing more live partials first) so
+//               that at most ~log2(n)+1 partial vectors are ever live, assigns each internal
+//               node a slot, and writes the traversal as a list of ops together with the two
+//               child transition matrices of every op IN OP ORDER (HKY closed form evaluated
+//               here from the node heights, or copied from caller matrices).
+//   k2_peel     grid = (pattern tiles, trees).  A CTA owns a tile of patterns of one tree and
+//               runs the WHOLE traversal for it: the live partial vectors stay in shared
+//               memory (thread-private columns: no synchronisation between ops), op lists and
+//               transition matrices stream through shared memory in stages with 1-D bulk async
+//               copies (TMA engine, mbarrier completion), tips are read as 1-byte states.
+//               Partials never touch HBM: traffic is tip states + the op/matrix stream, and the
+//               kernel is bound by the FP64 pipe and shared-memory bandwidth instead of HBM.
+//   k2_finalize fixed-order sum of the per-tile partial sums -> logL[tree].
+// fp64 throughout; rescaling follows BeerLikelihoodCore.scalePartials (threshold 1e-100,
+// always on -- results agree with the unscaled path to rounding whenever that path is finite).
+#include "mtt_common.cuh"
+
+#include <math.h>
+
+#include <algorithm>
+#include <vector>
+
+struct mtt_peel {
+    mtt_ctx *ctx = nullptr;
+    int nTips = 0, nCat = 0;
+    long long nPatterns = 0, pStride = 0;      // pStride: padded row length of tipStates
+    uint8_t *dStates = nullptr;                // [nTips][pStride]
+    double *dWeights = nullptr;                // [pStride] (0 beyond nPatterns)
+    uint8_t *dConst = nullptr;                 // [pStride] bit k: pattern constant for state k
+    double *dSite = nullptr;                   // catRates[C] | catProps[C] | freqs[4]
+    double pInv = 0.0, branchRate = 1.0, kappa = 1.0;
+    bool haveStates = false, haveWeights = false, haveSite = false, haveHky = false;
+    // per-call scratch (grow only)
+    void *dOps = nullptr; size_t opsCap = 0;
+    double *dMats = nullptr; size_t matsCap = 0;
+    double *dPart = nullptr; size_t partCap = 0;
+    int *dParent = nullptr; size_t parentCap = 0;
+    double *dHeight = nullptr; size_t heightCap = 0;
+    double *dMatsIn = nullptr; size_t matsInCap = 0;
+    double *dLogL = nullptr; size_t logLCap = 0;
+    int *dInfo = nullptr; size_t infoCap = 0;   // per tree: max slots used (or -1 = bad tree)
+};
+
+namespace {
+
+constexpr int TP = 128;                 // pattern padding granule (largest tile)
+constexpr int PREP_THREADS = 128;
+constexpr int MAX_SLOTS = 24;
+
+struct PeelOp {
+    int c1, c2;     // child refs: >= 0 slot of an internal child, < 0 tip index as -(tip+1)
+    int dst;        // slot receiving this node's partials
+    int node;
+};
+
+// ---- HKY.getTransitionProbabilities [EXT] (closed form) ---------------
+__device__ __forceinline__ void hky_matrix(double kappa, const double *f, double distance,
+                                           double *matrix)
+{
+    const double freqA = f[0], freqC = f[1], freqG = f[2], freqT = f[3];
+    const double freqR = freqA + freqG, freqY = freqC + freqT;
+    const double tab1A = freqA * ((1 / freqR) - 1), tab3A = freqA / freqR, tab2A = 1 - tab3A;
+    const double tab1C = freqC * ((1 / freqY) - 1), tab3C = freqC / freqY, tab2C = 1 - tab3C;
+    const double tab1G = freqG * ((1 / freqR) - 1), tab3G = tab2A, tab2G = tab3A;
+    const double tab1T = freqT * ((1 / freqY) - 1), tab3T = tab2C, tab2T = tab3C;
+    const double beta = -1.0 / (2.0 * (freqR * freqY + kappa * (freqA * freqG + freqC * freqT)));
+    const double A_R = 1.0 + freqR * (kappa - 1), A_Y = 1.0 + freqY * (kappa - 1);
+    const double xx = beta * distance;
+    const double bbR = exp(xx * A_R), bbY = exp(xx * A_Y), aa = exp(xx);
+    const double oneminusa = 1 - aa;
+    const double t1Aaa = tab1A * aa, t1Gaa = tab1G * aa, t1Caa = tab1C * aa, t1Taa = tab1T * aa;
+    matrix[0] = freqA + t1Aaa + (tab2A * bbR);
+    matrix[1] = freqC * oneminusa;
+    matrix[2] = freqG + t1Gaa - (tab3G * bbR);
+    matrix[3] = freqT * oneminusa;
+    matrix[4] = freqA * oneminusa;
+    matrix[5] = freqC + t1Caa + (tab2C * bbY);
+    matrix[6] = freqG * oneminusa;
+    matrix[7] = freqT + t1Taa - (tab3T * bbY);
+    matrix[8] = freqA + t1Aaa - (tab3A * bbR);
+    matrix[9] = matrix[1];
+    matrix[10] = freqG + t1Gaa + (tab2G * bbR);
+    matrix[11] = matrix[3];
+    matrix[12] = matrix[4];
+    matrix[13] = freqC + t1Caa - (tab3C * bbY);
+    matrix[14] = matrix[6];
+    matrix[15] = freqT + t1Taa + (tab2T * bbY);
+}
+
+// ---- k2_prepare ------------------------------------------------------------------------
+// shared: int left[N], right[N], order[N], stack[N]; uint8 need[N]      (N = 2n-1)
+__global__ void __launch_bounds__(PREP_THREADS)
+k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
+           const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
+           int *info)
+{
+    extern __shared__ int smi[];
+    const int N = 2 * n - 1, nOps = n - 1;
+    int *left = smi, *right = smi + N, *order = smi + 2 * N, *stack = smi + 3 * N;
+    uint8_t *need = reinterpret_cast<uint8_t *>(smi + 4 * N);
+    __shared__ int sRoot, sBad, sMaxSlots;
+
+    const int b = blockIdx.x, tid = threadIdx.x;
+    const int *parent = parentAll + (size_t)b * N;
+    PeelOp *ops = opsAll + (size_t)b * nOps;
+    double *mats = matsAll + (size_t)b * nOps * 2 * C * 16;
+
+    if (tid == 0) {
+        sRoot = -1;
+        sBad = 0;
+        sMaxSlots = 0;
+    }
+    for (int i = tid; i < N; i += PREP_THREADS) {
+        left[i] = 0x7fffffff;
+        right[i] = -1;
+    }
+    __syncthreads();
+    for (int i = tid; i < N; i += PREP_THREADS) {
+        const int p = parent[i];
+        if (p < 0) {
+            atomicMax(&sRoot, i);
+        } else if (p >= N || p < n) {
+            sBad = 1;                      // parent out of range or a tip used as a parent
+        } else {
+            atomicMin(&left[p], i);        // left = lower Nr, right = higher Nr
+            atomicMax(&right[p], i);
+        }
+    }
+    __syncthreads();
+    for (int i = n + tid; i < N; i += PREP_THREADS)
+        if (left[i] == 0x7fffffff || right[i] < 0 || left[i] == right[i])
+            sBad = 1;                      // an internal node without exactly two children
+    __syncthreads();
+    if (sBad || sRoot < n) {
+        if (tid == 0)
+            info[b] = -1;
+        return;
+    }
+
+    if (tid == 0) {
+        const int root = sRoot;
+        // pass 1: any pre-order (parents before children)
+        int sp = 0, cnt = 0;
+        stack[sp++] = root;
+        while (sp > 0 && cnt < N) {
+            const int v = stack[--sp];
+            order[cnt++] = v;
+            if (v >= n) {
+                stack[sp++] = left[v];
+                stack[sp++] = right[v];
+            }
+        }
+        if (cnt != N) {
+            sBad = 1;                      // not a single connected binary tree
+        } else {
+            // pass 2: Sethi-Ullman need (live partial vectors), children before parents
+            for (int i = N - 1; i >= 0; i--) {
+                const int v = order[i];
+                if (v < n) {
+                    need[v] = 0;
+                    continue;
+                }
+                const int a = need[left[v]] & 0x7f, c = need[right[v]] & 0x7f;
+                const int holdL = left[v] >= n, holdR = right[v] >= n;
+                const int lf = max(max(a, holdL + c), 1);   // left first
+                const int rf = max(max(c, holdR + a), 1);   // right first
+                need[v] = (uint8_t)((rf < lf) ? (rf | 0x80) : lf);
+            }
+            // pass 3a: pre-order of internal nodes, second-evaluated child popped first;
+            // its reverse is the post-order "first child, second child, node"
+            sp = 0;
+            cnt = 0;
+            stack[sp++] = root;
+            while (sp > 0) {
+                const int v = stack[--sp];
+                if (v < n)
+                    continue;
+                order[cnt++] = v;
+                const bool rightFirst = need[v] & 0x80;
+                stack[sp++] = rightFirst ? right[v] : left[v];    // first: popped last
+                stack[sp++] = rightFirst ? left[v] : right[v];    // second: popped first
+            }
+            // pass 3b: slots, in execution order
+            unsigned long long freeMask = ~0ull;
+            int maxSlots = 0;
+            for (int k = 0; k < nOps; k++) {
+                const int v = order[nOps - 1 - k];
+                const bool rightFirst = need[v] & 0x80;
+                const int c1 = rightFirst ? right[v] : left[v];
+                const int c2 = rightFirst ? left[v] : right[v];
+                PeelOp op;
+                op.c1 = (c1 < n) ? -(c1 + 1) : (need[c1] & 0x7f);
+                op.c2 = (c2 < n) ? -(c2 + 1) : (need[c2] & 0x7f);
+                if (c1 >= n)
+                    freeMask |= 1ull << (need[c1] & 0x7f);
+                if (c2 >= n)
+                    freeMask |= 1ull << (need[c2] & 0x7f);
+                const int dst = __ffsll((long long)freeMask) - 1;
+                freeMask &= ~(1ull << dst);
+                need[v] = (uint8_t)((need[v] & 0x80) | dst);
+                maxSlots = max(maxSlots, dst + 1);
+                op.dst = dst;
+                op.node = v;
+                ops[k] = op;
+                stack[k] = v;              // op -> node, for the matrix pass below
+            }
+            sMaxSlots = maxSlots;
+        }
+    }
+    __syncthreads();
+    if (sBad) {
+        if (tid == 0)
+            info[b] = -1;
+        return;
+    }
+    if (tid == 0)
+        info[b] = sMaxSlots;
+
+    // transition matrices of both children of every op, in op order:
+    // mats[op][child j][category c][16]
+    const double *catRates = site, *freqs = site + 2 * C;
+    const double *height = heightAll ? heightAll + (size_t)b * N : nullptr;
+    const double *matsIn = matsInAll ? matsInAll + (size_t)b * N * C * 16 : nullptr;
+    for (int idx = tid; idx < nOps * 2 * C; idx += PREP_THREADS) {
+        const int k = idx / (2 * C), j = (idx / C) & 1, c = idx % C;
+        const int v = stack[k];
+        const bool rightFirst = need[v] & 0x80;
+        const int child = (j == 0) == rightFirst ? right[v] : left[v];
+        double *M = mats + (size_t)idx * 16;
+        if (matsIn) {
+            const double *src = matsIn + ((size_t)child * C + c) * 16;
+            for (int e = 0; e < 16; e++)
+                M[e] = src[e];
+        } else {
+            // TreeLikelihood.traverse [EXT]: jointBranchRate = categoryRate * branchRate
+            const double jointBranchRate = catRates[c] * branchRate;
+            const double distance = (height[v] - height[child]) * jointBranchRate;
+            hky_matrix(kappa, freqs, distance, M);
+        }
+    }
+}
+
+// ---- k2_peel ---------------------------------------------------------------------------
+constexpr double SCALING_THRESHOLD = 1.0E-100;     // BeerLikelihoodCore.scalingThreshold
+
+template <int C>
+struct PeelCfg {
+    static constexpr int OPS_PER_STAGE = (C == 1) ? 32 : (C == 2 ? 16 : (C <= 4 ? 8 : 4));
+    static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
+    static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
+};
+
+// partials of one child for category c -> a[i] = sum_j M[i][j] x[j]  (or the tip column)
+template <int C, int TPT>
+__device__ __forceinline__ void child_term(int ref, const double *M, const double *stackBase,
+                                           int c, int tid, const uint8_t *tipRow, long long p,
+                                           double (&a)[4], int &tipState, bool &tipLoaded)
+{
+    if (ref < 0) {
+        if (!tipLoaded) {
+            tipState = tipRow[p];
+            tipLoaded = true;
+        }
+        if (tipState < 4) {
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                a[i] = M[i * 4 + tipState];
+        } else {                                    // gap / ambiguity: treated as unknown
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                a[i] = 1.0;
+        }
+    } else {
+        const double *x = stackBase + ((size_t)(ref * C + c) * 4) * TPT + tid;
+        const double x0 = x[0], x1 = x[TPT], x2 = x[2 * TPT], x3 = x[3 * TPT];
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            double s = M[i * 4 + 0] * x0;
+            s += M[i * 4 + 1] * x1;
+            s += M[i * 4 + 2] * x2;
+            s += M[i * 4 + 3] * x3;
+            a[i] = s;
+        }
+    }
+}
+
+// TPT = patterns per tile = threads per CTA (128, 64 or 32: smaller tiles when many rate
+// categories make the live partial vectors large)
+template <int C, int TPT>
+__global__ void __launch_bounds__(TPT)
+k2_peel(int n, long long P, long long pStride, const uint8_t *states, const double *weights,
+        const uint8_t *constMask, const double *site, double pInv, const PeelOp *opsAll,
+        const double *matsAll, const int *info, int nSlots, double *partial, int nTiles,
+        double *patternLogL)
+{
+    using Cfg = PeelCfg<C>;
+    extern __shared__ __align__(16) unsigned char smem[];
+    // layout: [2 stages: ops | mats][barriers][stack nSlots*C*4*TP doubles]
+    unsigned char *stageBase = smem;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::STAGE_BYTES);
+    double *stackBase = reinterpret_cast<double *>(smem + 2 * Cfg::STAGE_BYTES + 16);
+    __shared__ double red[TPT / 32];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tile = blockIdx.x, b = blockIdx.y;
+    const int nOps = n - 1;
+    const long long p = (long long)tile * TPT + tid;         // < pStride by construction
+    const PeelOp *ops = opsAll + (size_t)b * nOps;
+    const double *mats = matsAll + (size_t)b * nOps * Cfg::MAT_DOUBLES_PER_OP;
+    const int treeInfo = info[b];
+
+    if (treeInfo < 0 || treeInfo > nSlots) {                 // malformed tree: NaN, loudly
+        if (tid == 0)
+            partial[(size_t)b * nTiles + tile] = NAN;
+        if (patternLogL && p < P)
+            patternLogL[p] = NAN;
+        return;
+    }
+    if (tid == 0) {
+        mbar_init(&bars[0], 1);
+        mbar_init(&bars[1], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    const int nStages = (nOps + Cfg::OPS_PER_STAGE - 1) / Cfg::OPS_PER_STAGE;
+    auto issue = [&](int s) {
+        const int k0 = s * Cfg::OPS_PER_STAGE;
+        const int cnt = min(Cfg::OPS_PER_STAGE, nOps - k0);
+        unsigned char *dst = stageBase + (s & 1) * Cfg::STAGE_BYTES;
+        const uint32_t opBytes = cnt * 16, matBytes = cnt * Cfg::MAT_DOUBLES_PER_OP * 8;
+        mbar_arrive_expect_tx(&bars[s & 1], opBytes + matBytes);
+        bulk_g2s(dst, ops + k0, opBytes, &bars[s & 1]);
+        bulk_g2s(dst + Cfg::OPS_PER_STAGE * 16, mats + (size_t)k0 * Cfg::MAT_DOUBLES_PER_OP,
+                 matBytes, &bars[s & 1]);
+    };
+    if (tid == 0)
+        issue(0);
+
+    double out[C][4];
+    double logScale = 0.0;
+    uint32_t ph0 = 0, ph1 = 0;
+    for (int s = 0; s < nStages; s++) {
+        if (tid == 0 && s + 1 < nStages)
+            issue(s + 1);      // the other stage was released by the __syncthreads below
+        if (s & 1) {
+            mbar_wait(&bars[1], ph1);
+            ph1 ^= 1;
+        } else {
+            mbar_wait(&bars[0], ph0);
+            ph0 ^= 1;
+        }
+        const unsigned char *st = stageBase + (s & 1) * Cfg::STAGE_BYTES;
+        const PeelOp *sOps = reinterpret_cast<const PeelOp *>(st);
+        const double *sMats = reinterpret_cast<const double *>(st + Cfg::OPS_PER_STAGE * 16);
+        const int cnt = min(Cfg::OPS_PER_STAGE, nOps - s * Cfg::OPS_PER_STAGE);
+        for (int k = 0; k < cnt; k++) {
+            const PeelOp op = sOps[k];
+            int ts1 = 0, ts2 = 0;
+            bool l1 = false, l2 = false;
+            const uint8_t *row1 = op.c1 < 0 ? states + (size_t)(-op.c1 - 1) * pStride : nullptr;
+            const uint8_t *row2 = op.c2 < 0 ? states + (size_t)(-op.c2 - 1) * pStride : nullptr;
+            double mx = 0.0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                const double *M1 = sMats + (size_t)k * Cfg::MAT_DOUBLES_PER_OP + c * 16;
+                const double *M2 = M1 + C * 16;
+                double a[4], bb[4];
+                child_term<C, TPT>(op.c1, M1, stackBase, c, tid, row1, p, a, ts1, l1);
+                child_term<C, TPT>(op.c2, M2, stackBase, c, tid, row2, p, bb, ts2, l2);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    out[c][i] = a[i] * bb[i];
+                    mx = fmax(mx, out[c][i]);
+                }
+            }
+            // BeerLikelihoodCore.scalePartials [EXT]
+            if (mx < SCALING_THRESHOLD) {
+#pragma unroll
+                for (int c = 0; c < C; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+                        out[c][i] /= mx;
+                logScale += log(mx);
+            }
+            double *dst = stackBase + ((size_t)(op.dst * C) * 4) * TPT + tid;
+#pragma unroll
+            for (int c = 0; c < C; c++)
+#pragma unroll
+                for (int i = 0; i < 4; i++)
+                    dst[(c * 4 + i) * TPT] = out[c][i];
+        }
+        __syncthreads();       // every thread is done with this stage's ops and matrices
+    }
+
+    // root: integratePartials, proportion invariant, frequencies, log  [EXT]
+    const double *catProps = site + C, *freqs = site + 2 * C;
+    double root[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        double r = out[0][i] * catProps[0];
+#pragma unroll
+        for (int c = 1; c < C; c++)
+            r += out[c][i] * catProps[c];
+        root[i] = r;
+    }
+    if (pInv > 0.0) {
+        const int cm = constMask[p];
+#pragma unroll
+        for (int i = 0; i < 4; i++)
+            if (cm & (1 << i))
+                root[i] += pInv;
+    }
+    double sum = 0.0;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        sum += freqs[i] * root[i];
+    const double ll = log(sum) + logScale;
+    if (patternLogL && p < P)
+        patternLogL[p] = ll;
+    double contrib = (p < P) ? ll * weights[p] : 0.0;
+    contrib = warp_sum_down(contrib);
+    if (lane == 0)
+        red[warp] = contrib;
+    __syncthreads();
+    if (tid == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < TPT / 32; w++)
+            t += red[w];
+        partial[(size_t)b * nTiles + tile] = t;
+    }
+}
+
+__global__ void k2_finalize(long long B, int nTiles, const double *partial, double *logL)
+{
+    const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= B)
+        return;
+    double s = 0.0;
+    for (int t = 0; t < nTiles; t++)
+        s += partial[(size_t)b * nTiles + t];
+    logL[b] = s;
+}
+
+// constant-site masks (TreeLikelihood.calcConstantPatternIndices [EXT]): pattern p is constant
+// for state k when every unambiguous tip shows k
+__global__ void k2_const_mask(int n, long long P, long long pStride, const uint8_t *states,
+                              uint8_t *mask)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= pStride)
+        return;
+    int m = 0xf;
+    if (p < P)
+        for (int t = 0; t < n; t++) {
+            const int s = states[(size_t)t * pStride + p];
+            if (s < 4)
+                m &= (1 << s);
+        }
+    mask[p] = (uint8_t)m;
+}
+
+template <typename T>
+int grow(mtt_ctx *ctx, T *&ptr, size_t &cap, size_t bytes)
+{
+    if (bytes + 256 <= cap)
+        return MTT_OK;
+    if (ptr) {
+        MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        cudaFree(ptr);
+        ptr = nullptr;
+        cap = 0;
+    }
+    size_t want = bytes + bytes / 8 + 4096;
+    MTT_CUDA(ctx, cudaMalloc((void **)&ptr, want));
+    cap = want;
+    return MTT_OK;
+}
+
+template <int C, int TPT>
+int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
+{
+    mtt_ctx *ctx = h->ctx;
+    using Cfg = PeelCfg<C>;
+    const int nTiles = (int)(h->pStride / TPT);
+    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * TPT * 8;
+    auto kern = k2_peel<C, TPT>;
+    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    dim3 grid((unsigned)nTiles, (unsigned)B);
+    kern<<<grid, TPT, smem, ctx->stream>>>(h->nTips, h->nPatterns, h->pStride, h->dStates,
+                                           h->dWeights, h->dConst, h->dSite, h->pInv,
+                                           (const PeelOp *)h->dOps, h->dMats, h->dInfo, nSlots,
+                                           h->dPart, nTiles, patternLogL);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
+}
+
+// tile size: the largest of 128 / 64 / 32 patterns whose live partial vectors leave room for
+// at least two CTAs per SM
+inline int pick_tile(int C, int nSlots, size_t stageBytes)
+{
+    for (int t = 128; t >= 32; t >>= 1)
+        if (2 * stageBytes + 16 + (size_t)nSlots * C * 4 * t * 8 <= 110 * 1024 || t == 32)
+            return t;
+    return 32;
+}
+
+template <int C>
+int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *patternLogL)
+{
+    using Cfg = PeelCfg<C>;
+    const int t = pick_tile(C, nSlots, Cfg::STAGE_BYTES);
+    if (2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * t * 8 > 227 * 1024)
+        return mtt_fail(h->ctx, MTT_ERR_TOO_LARGE,
+                        "peeling: %d live partial vectors x %d categories exceed shared memory",
+                        nSlots, C);
+    *nTilesOut = (int)(h->pStride / t);
+    if (t == 128)
+        return launch_peel_t<C, 128>(h, B, nSlots, patternLogL);
+    if (t == 64)
+        return launch_peel_t<C, 64>(h, B, nSlots, patternLogL);
+    return launch_peel_t<C, 32>(h, B, nSlots, patternLogL);
+}
+
+// run the pipeline on device-resident parent/height (or matsIn) for a chunk of trees
+int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeight,
+               const double *dMatsIn, double *dLogL, double *patternLogL)
+{
+    mtt_ctx *ctx = h->ctx;
+    const int n = h->nTips, C = h->nCat, N = 2 * n - 1, nOps = n - 1;
+    const int maxTiles = (int)(h->pStride / 32);
+    int nTiles = 0;
+    int rc;
+    if ((rc = grow(ctx, h->dOps, h->opsCap, (size_t)B * nOps * sizeof(PeelOp))) != MTT_OK)
+        return rc;
+    if ((rc = grow(ctx, h->dMats, h->matsCap, (size_t)B * nOps * 2 * C * 16 * 8)) != MTT_OK)
+        return rc;
+    if ((rc = grow(ctx, h->dPart, h->partCap, (size_t)B * maxTiles * 8)) != MTT_OK)
+        return rc;
+    if ((rc = grow(ctx, h->dInfo, h->infoCap, (size_t)B * 4)) != MTT_OK)
+        return rc;
+    const size_t prepSmem = (size_t)N * 17 + 64;
+    if (prepSmem > 227 * 1024)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: %d tips exceed the traversal planner's "
+                        "shared memory (limit ~6800 tips)", n);
+    MTT_CUDA(ctx, cudaFuncSetAttribute(k2_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)prepSmem));
+    k2_prepare<<<(unsigned)B, PREP_THREADS, prepSmem, ctx->stream>>>(
+        n, C, dParent, dHeight, dMatsIn, h->dSite, h->branchRate, h->kappa, (PeelOp *)h->dOps,
+        h->dMats, h->dInfo);
+    MTT_CHECK_LAUNCH(ctx);
+    // Sethi-Ullman bound on live partial vectors: floor(log2(n)) + 1
+    int nSlots = 1;
+    while ((1 << nSlots) <= n)
+        nSlots++;
+    nSlots = std::min(nSlots + 1, MAX_SLOTS);
+    switch (C) {
+    case 1: rc = launch_peel<1>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 2: rc = launch_peel<2>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 3: rc = launch_peel<3>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 4: rc = launch_peel<4>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 5: rc = launch_peel<5>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 6: rc = launch_peel<6>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 7: rc = launch_peel<7>(h, B, nSlots, &nTiles, patternLogL); break;
+    case 8: rc = launch_peel<8>(h, B, nSlots, &nTiles, patternLogL); break;
+    default:
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: nCat=%d outside [1,8]", C);
+    }
+    if (rc != MTT_OK)
+        return rc;
+    k2_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(B, nTiles, h->dPart, dLogL);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
+}
+
+long long chunk_trees(const mtt_peel *h)
+{
+    // bound the op/matrix stream scratch to ~512 MB per chunk
+    const size_t perTree = (size_t)(h->nTips - 1) * (sizeof(PeelOp) + 2 * h->nCat * 16 * 8);
+    long long c = (long long)((512ull << 20) / perTree);
+    return std::max(1LL, std::min(c, 65535LL));
+}
+
+int check_ready(mtt_peel *h, bool needHky)
+{
+    if (!h)
+        return MTT_ERR_INVALID_ARG;
+    if (!h->haveStates || !h->haveWeights || !h->haveSite || (needHky && !h->haveHky))
+        return mtt_fail(h->ctx, MTT_ERR_STATE,
+                        "peeling: set_tip_states, set_pattern_weights, set_site_model%s must be "
+                        "called first", needHky ? " and set_hky" : "");
+    return MTT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtt_peel_create(mtt_ctx *ctx, int nTips, int64_t nPatterns, int nCat, mtt_peel **out)
+{
+    if (!ctx || !out)
+        return MTT_ERR_INVALID_ARG;
+    *out = nullptr;
+    if (nTips < 2 || nPatterns < 1)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_peel_create: need >= 2 tips, >= 1 pattern");
+    if (nCat < 1 || nCat > 8)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "mtt_peel_create: nCat=%d outside [1,8]", nCat);
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    mtt_peel *h = new mtt_peel();
+    h->ctx = ctx;
+    h->nTips = nTips;
+    h->nCat = nCat;
+    h->nPatterns = nPatterns;
+    h->pStride = (nPatterns + TP - 1) / TP * TP;
+    cudaError_t e = cudaMalloc((void **)&h->dStates, (size_t)nTips * h->pStride + 256);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&h->dWeights, h->pStride * 8 + 256);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&h->dConst, h->pStride + 256);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&h->dSite, (2 * nCat + 4) * 8 + 256);
+    if (e != cudaSuccess) {
+        mtt_peel_destroy(h);
+        return mtt_fail(ctx, MTT_ERR_CUDA, "mtt_peel_create: cudaMalloc failed: %s",
+                        cudaGetErrorString(e));
+    }
+    *out = h;
+    return MTT_OK;
+}
+
+int mtt_peel_destroy(mtt_peel *h)
+{
+    if (!h)
+        return MTT_OK;
+    cudaSetDevice(h->ctx->device);
+    cudaStreamSynchronize(h->ctx->stream);
+    void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart,
+                    h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo};
+    for (void *p : ptrs)
+        if (p)
+            cudaFree(p);
+    delete h;
+    return MTT_OK;
+}
+
+int mtt_peel_set_tip_states(mtt_peel *h, const int32_t *states)
+{
+    if (!h || !states)
+        return MTT_ERR_INVALID_ARG;
+    mtt_ctx *ctx = h->ctx;
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    // int32 [nTips][nPatterns] -> uint8 [nTips][pStride]; padding patterns are "unknown"
+    std::vector<uint8_t> packed((size_t)h->nTips * h->pStride, 4);
+    for (int t = 0; t < h->nTips; t++)
+        for (long long p = 0; p < h->nPatterns; p++) {
+            const int32_t s = states[(size_t)t * h->nPatterns + p];
+            packed[(size_t)t * h->pStride + p] = (uint8_t)((s >= 0 && s < 4) ? s : 4);
+        }
+    MTT_CUDA(ctx, cudaMemcpyAsync(h->dStates, packed.data(), packed.size(),
+                                  cudaMemcpyHostToDevice, ctx->stream));
+    k2_const_mask<<<(unsigned)((h->pStride + 255) / 256), 256, 0, ctx->stream>>>(
+        h->nTips, h->nPatterns, h->pStride, h->dStates, h->dConst);
+    MTT_CHECK_LAUNCH(ctx);
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h->haveStates = true;
+    return MTT_OK;
+}
+
+int mtt_peel_set_pattern_weights(mtt_peel *h, const int32_t *weights)
+{
+    if (!h || !weights)
+        return MTT_ERR_INVALID_ARG;
+    mtt_ctx *ctx = h->ctx;
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> w((size_t)h->pStride, 0.0);
+    for (long long p = 0; p < h->nPatterns; p++)
+        w[p] = (double)weights[p];
+    MTT_CUDA(ctx, cudaMemcpyAsync(h->dWeights, w.data(), w.size() * 8, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h->haveWeights = true;
+    return MTT_OK;
+}
+
+int mtt_peel_set_site_model(mtt_peel *h, const double *catRates, const double *catProps,
+                            const double *freqs, double pInv, double branchRate)
+{
+    if (!h || !catRates || !catProps || !freqs)
+        return MTT_ERR_INVALID_ARG;
+    mtt_ctx *ctx = h->ctx;
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    std::vector<double> s(2 * h->nCat + 4);
+    for (int c = 0; c < h->nCat; c++) {
+        s[c] = catRates[c];
+        s[h->nCat + c] = catProps[c];
+    }
+    for (int i = 0; i < 4; i++)
+        s[2 * h->nCat + i] = freqs[i];
+    MTT_CUDA(ctx, cudaMemcpyAsync(h->dSite, s.data(), s.size() * 8, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    h->pInv = pInv;
+    h->branchRate = branchRate;
+    h->haveSite = true;
+    return MTT_OK;
+}
+
+int mtt_peel_set_hky(mtt_peel *h, double kappa)
+{
+    if (!h)
+        return MTT_ERR_INVALID_ARG;
+    h->kappa = kappa;
+    h->haveHky = true;
+    return MTT_OK;
+}
+
+int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                            double *logL)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    mtt_ctx *ctx = h->ctx;
+    if (B < 0 || !parent || !height || !logL)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_batch_dev: bad arguments");
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int N = 2 * h->nTips - 1;
+    const long long chunk = chunk_trees(h);
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min(chunk, (long long)B - b0);
+        rc = peel_chunk(h, nb, parent + b0 * N, height + b0 * N, nullptr, logL + b0, nullptr);
+        if (rc != MTT_OK)
+            return rc;
+    }
+    return MTT_OK;
+}
+
+static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                     const double *mats, double *logL, double *patternLogL)
+{
+    mtt_ctx *ctx = h->ctx;
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    const int N = 2 * h->nTips - 1, C = h->nCat;
+    const long long chunk = chunk_trees(h);
+    int rc;
+    if ((rc = grow(ctx, h->dLogL, h->logLCap, (size_t)std::max<int64_t>(B, 1) * 8)) != MTT_OK)
+        return rc;
+    double *dPat = nullptr;
+    if (patternLogL) {
+        // reuse the weights-sized scratch behind dPart for the per-pattern output
+        if ((rc = grow(ctx, h->dHeight, h->heightCap,
+                       std::max((size_t)N * 8, (size_t)h->pStride * 8))) != MTT_OK)
+            return rc;
+    }
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min(chunk, (long long)B - b0);
+        if ((rc = grow(ctx, h->dParent, h->parentCap, (size_t)nb * N * 4)) != MTT_OK)
+            return rc;
+        MTT_CUDA(ctx, cudaMemcpyAsync(h->dParent, parent + b0 * N, (size_t)nb * N * 4,
+                                      cudaMemcpyHostToDevice, s));
+        const double *dH = nullptr, *dM = nullptr;
+        if (mats) {
+            if ((rc = grow(ctx, h->dMatsIn, h->matsInCap, (size_t)nb * N * C * 16 * 8)) != MTT_OK)
+                return rc;
+            MTT_CUDA(ctx, cudaMemcpyAsync(h->dMatsIn, mats + (size_t)b0 * N * C * 16,
+                                          (size_t)nb * N * C * 16 * 8, cudaMemcpyHostToDevice, s));
+            dM = h->dMatsIn;
+        } else {
+            double *&hbuf = patternLogL ? h->dMatsIn : h->dHeight;
+            size_t &hcap = patternLogL ? h->matsInCap : h->heightCap;
+            if ((rc = grow(ctx, hbuf, hcap, (size_t)nb * N * 8)) != MTT_OK)
+                return rc;
+            MTT_CUDA(ctx, cudaMemcpyAsync(hbuf, height + b0 * N, (size_t)nb * N * 8,
+                                          cudaMemcpyHostToDevice, s));
+            dH = hbuf;
+        }
+        if (patternLogL)
+            dPat = h->dHeight;
+        rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat);
+        if (rc != MTT_OK)
+            return rc;
+        // the upload buffers are reused by the next chunk
+        MTT_CUDA(ctx, cudaStreamSynchronize(s));
+    }
+    if (logL)
+        MTT_CUDA(ctx, cudaMemcpyAsync(logL, h->dLogL, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+    if (patternLogL)
+        MTT_CUDA(ctx, cudaMemcpyAsync(patternLogL, dPat, (size_t)h->nPatterns * 8,
+                                      cudaMemcpyDeviceToHost, s));
+    MTT_CUDA(ctx, cudaStreamSynchronize(s));
+    return MTT_OK;
+}
+
+int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                        double *logL)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    if (B < 0 || !parent || !height || !logL)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_batch: bad arguments");
+    if (B == 0)
+        return MTT_OK;
+    return peel_host(h, B, parent, height, nullptr, logL, nullptr);
+}
+
+int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,
+                             double *logL)
+{
+    int rc = check_ready(h, false);
+    if (rc != MTT_OK)
+        return rc;
+    if (B < 0 || !parent || !mats || !logL)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_batch_mats: bad arguments");
+    if (B == 0)
+        return MTT_OK;
+    return peel_host(h, B, parent, nullptr, mats, logL, nullptr);
+}
+
+int mtt_peel_pattern_logl(mtt_peel *h, const int32_t *parent, const double *height,
+                          double *patternLogL)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    if (!parent || !height || !patternLogL)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_pattern_logl: bad arguments");
+    return peel_host(h, 1, parent, height, nullptr, nullptr, patternLogL);
+}
+
+}  // extern "C"

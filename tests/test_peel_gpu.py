@@ -1,0 +1,206 @@
+"""GPU parity tests for piece 2 (csrc/k2_peel.cu) through the C-ABI, against the oracle
+(BeerLikelihoodCore semantics).  Tolerance: 1e-9 relative on logL (north_star)."""
+import numpy as np
+import pytest
+
+import multitypetree_b200 as mtt
+from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, StrictClockModel,
+                                           TreeLikelihood, simulate_alignment)
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+def _trees(B, n, d=2, seed=1):
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=seed)
+    nN = 2 * n - 1
+    return tb.parent.reshape(B, nN), tb.height.reshape(B, nN), tb
+
+
+def _oracle(al, par, hgt, sm, clock=1.0, nThreads=8):
+    rates, props = sm.category_rates_and_proportions()
+    return orc.tree_likelihood_batch(al.patterns, al.patternWeight, par, hgt, rates, props,
+                                     sm.substModel.frequencies, sm.substModel.kappa,
+                                     branchRate=clock, pInv=sm.proportionInvariant,
+                                     useScaling=2, nThreads=nThreads)
+
+
+@pytest.mark.parametrize("n,sites,gamma,pInv,missing,B", [
+    (2, 50, 0, 0.0, 0.0, 4), (3, 200, 0, 0.0, 0.0, 8), (5, 300, 4, 0.0, 0.1, 16),
+    (17, 1000, 0, 0.2, 0.0, 16), (64, 2000, 4, 0.1, 0.05, 8), (128, 2000, 0, 0.0, 0.0, 8),
+    (100, 700, 2, 0.0, 0.0, 8), (33, 400, 8, 0.3, 0.2, 4), (200, 513, 3, 0.0, 0.0, 5)])
+def test_logl_matches_oracle(ctx, n, sites, gamma, pInv, missing, B):
+    par, hgt, _ = _trees(B, n, seed=10 + n)
+    f = np.array([.1, .2, .3, .4])
+    tips = simulate_alignment(par[0], hgt[0], sites, 2.5, f, 0.05, seed=n, missing=missing)
+    al = Alignment(states=tips)
+    sm = SiteModel(HKY(2.5, f), mutationRate=0.05, gammaCategoryCount=gamma, shape=0.6,
+                   proportionInvariant=pInv)
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    got = tl.calculateLogPBatch(par, hgt)
+    want = _oracle(al, par, hgt, sm)
+    assert np.all(np.isfinite(want))
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    tl.close()
+
+
+def test_config1_shape_tree_likelihood_object(ctx):
+    """config 1 shape (128 taxa, 2000 sites, HKY, 1 category, strict clock rate 1) through
+    the TreeLikelihood mirror with a MultiTypeTree as its `tree` Input."""
+    par, hgt, tb = _trees(1, 128, seed=128)
+    tree = tb.tree(0)
+    f = np.array([.25] * 4)
+    tips = simulate_alignment(par[0], hgt[0], 2000, 3.0, f, 0.01, seed=3)
+    al = Alignment(states=tips)
+    assert al.getPatternCount() < 2000
+    sm = SiteModel(HKY(3.0, f), mutationRate=0.01)
+    tl = TreeLikelihood(data=al, tree=tree, siteModel=sm, ctx=ctx)
+    lp = tl.calculateLogP()
+    want = _oracle(al, par, hgt, sm)[0]
+    assert lp == pytest.approx(want, rel=RTOL)
+    pl = tl.getPatternLogLikelihoods()
+    rates, props = sm.category_rates_and_proportions()
+    _, pl_want = orc.tree_likelihood(al.patterns, al.patternWeight, par[0], hgt[0], rates, props,
+                                     f, 3.0, want_patterns=True)
+    np.testing.assert_allclose(pl, pl_want, rtol=RTOL)
+    assert (pl * al.patternWeight).sum() == pytest.approx(lp, rel=1e-12)
+    # a parameter move: kappa and clock rate change, same handle
+    sm.substModel.kappa = 5.0
+    tl.branchRateModel = StrictClockModel(1.7)
+    tl.update_models()
+    assert tl.calculateLogP() == pytest.approx(_oracle(al, par, hgt, sm, clock=1.7)[0], rel=RTOL)
+    tl.close()
+
+
+@pytest.mark.parametrize("n,P,rate", [(1000, 1500, 0.02), (1000, 300, 50.0), (3000, 256, 0.01),
+                                      (5000, 130, 0.005)])
+def test_large_trees_need_rescaling(ctx, n, P, rate):
+    """configs 3/4 tree sizes: underflow is certain without per-node rescaling."""
+    par, hgt, _ = _trees(2, n, d=4, seed=n)
+    f = np.array([.3, .2, .2, .3])
+    tips = simulate_alignment(par[0], hgt[0], P, 2.0, f, rate, seed=5)
+    al = Alignment(states=tips, compress=False)
+    sm = SiteModel(HKY(2.0, f), mutationRate=rate)
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    got = tl.calculateLogPBatch(par, hgt)
+    want = _oracle(al, par, hgt, sm)
+    assert np.all(np.isfinite(want))
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    tl.close()
+
+
+def test_unbalanced_and_balanced_topologies(ctx):
+    """Caterpillar (depth n) and perfectly balanced trees: the traversal planner must keep the
+    number of live partial vectors within its log2(n)+1 bound for both."""
+    f = np.array([.25] * 4)
+    for n, kind in ((257, "cat"), (256, "bal"), (1000, "cat")):
+        N = 2 * n - 1
+        parent = np.full(N, -1, np.int32)
+        height = np.zeros(N)
+        if kind == "cat":
+            prev = 0
+            for i in range(1, n):
+                node = n + i - 1
+                parent[prev] = node
+                parent[i] = node
+                height[node] = 0.01 * i
+                prev = node
+        else:
+            level = list(range(n))
+            nxt, hh = n, 0.02
+            while len(level) > 1:
+                new = []
+                for a, b in zip(level[::2], level[1::2]):
+                    parent[a] = parent[b] = nxt
+                    height[nxt] = hh
+                    new.append(nxt)
+                    nxt += 1
+                level, hh = new, hh + 0.02
+        tips = simulate_alignment(parent, height, 300, 2.0, f, 1.0, seed=n)
+        al = Alignment(states=tips)
+        sm = SiteModel(HKY(2.0, f))
+        tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+        got = tl.calculateLogPBatch(parent[None], height[None])
+        want = _oracle(al, parent[None], height[None], sm)
+        np.testing.assert_allclose(got, want, rtol=RTOL)
+        tl.close()
+
+
+def test_explicit_matrices_mode(ctx):
+    """mtt_peel_logl_batch_mats: caller-provided per-node transition matrices (any model)."""
+    n, B = 40, 6
+    par, hgt, _ = _trees(B, n, seed=77)
+    f = np.array([.1, .2, .3, .4])
+    tips = simulate_alignment(par[0], hgt[0], 500, 2.0, f, 0.1, seed=1)
+    al = Alignment(states=tips)
+    sm = SiteModel(HKY(2.0, f), mutationRate=0.1, gammaCategoryCount=4, shape=0.8)
+    rates, props = sm.category_rates_and_proportions()
+    N = 2 * n - 1
+    mats = np.zeros((B, N, 4, 16))
+    for b in range(B):
+        for v in range(N):
+            if par[b, v] >= 0:
+                for c in range(4):
+                    mats[b, v, c] = orc.hky_matrix(2.0, f, (hgt[b, par[b, v]] - hgt[b, v])
+                                                   * rates[c]).ravel()
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    got = tl.calculateLogPBatchMats(par, mats)
+    want = np.array([orc.tree_likelihood_mats(al.patterns, al.patternWeight, par[b], mats[b],
+                                              props, f) for b in range(B)])
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    np.testing.assert_allclose(got, tl.calculateLogPBatch(par, hgt), rtol=1e-12)
+    tl.close()
+
+
+def test_pattern_shards_sum_to_whole(ctx):
+    """config 4 decomposition: logL over pattern shards adds up to the unsharded logL (the
+    all-reduce of SURVEY 8e, emulated on one GPU as a sum over shard handles)."""
+    n, B = 50, 4
+    par, hgt, _ = _trees(B, n, seed=5)
+    f = np.array([.25] * 4)
+    al = Alignment(states=simulate_alignment(par[0], hgt[0], 3000, 2.0, f, 0.1, seed=9))
+    sm = SiteModel(HKY(2.0, f), mutationRate=0.1, gammaCategoryCount=4, shape=0.5)
+    whole = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    full = whole.calculateLogPBatch(par, hgt)
+    acc = np.zeros(B)
+    for r in range(8):
+        sh = TreeLikelihood(data=al.shard(r, 8), siteModel=sm, ctx=ctx)
+        acc += sh.calculateLogPBatch(par, hgt)
+        sh.close()
+    np.testing.assert_allclose(acc, full, rtol=1e-12)
+    np.testing.assert_allclose(full, _oracle(al, par, hgt, sm), rtol=RTOL)
+    whole.close()
+
+
+def test_malformed_tree_is_reported_not_silently_wrong(ctx):
+    n = 10
+    par, hgt, _ = _trees(2, n, seed=3)
+    par = par.copy()
+    par[1, 0] = par[1, 1]            # a node with three children / another with one
+    f = np.array([.25] * 4)
+    al = Alignment(states=simulate_alignment(par[0], hgt[0], 100, 2.0, f, 0.1, seed=9))
+    tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f)), ctx=ctx)
+    got = tl.calculateLogPBatch(par, hgt)
+    assert np.isfinite(got[0]) and np.isnan(got[1])
+    with pytest.raises(mtt.MttError):
+        _ = mtt.lib().mtt_peel_logl_batch  # noqa
+        bad = TreeLikelihood.__new__(TreeLikelihood)
+        bad.ctx, bad._h = ctx, mtt._lib.VP()
+        import ctypes
+        ctx.check(mtt.lib().mtt_peel_create(ctx.handle, 4, 10, 9, ctypes.byref(bad._h)))
+    tl.close()
+
+
+def test_determinism_and_batch_independence(ctx):
+    n, B = 100, 12
+    par, hgt, _ = _trees(B, n, seed=1)
+    f = np.array([.25] * 4)
+    al = Alignment(states=simulate_alignment(par[0], hgt[0], 1200, 2.0, f, 0.05, seed=2))
+    tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f), 0.05), ctx=ctx)
+    a = tl.calculateLogPBatch(par, hgt)
+    b = tl.calculateLogPBatch(par, hgt)
+    c = tl.calculateLogPBatch(par[3:7], hgt[3:7])
+    assert np.array_equal(a, b) and np.array_equal(a[3:7], c)
+    tl.close()

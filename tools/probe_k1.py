@@ -11,7 +11,7 @@ from multitypetree_b200 import _lib
 
 
 def dev(a):
-    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    t = torch.from_numpy(np.ascontiguousarray(a).ravel()).cuda()
     pad = torch.zeros(t.numel() + 64, dtype=t.dtype, device="cuda")
     pad[:t.numel()] = t
     return pad
@@ -28,7 +28,9 @@ def main():
         B, time.time() - t0, tb.n_events().mean(), tb.n_events().max(), tb.nbytes() / 1e6))
     ctx = mtt.Context(0)
     L = _lib.lib()
-    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
     arrs = [dev(x) for x in (m, N, tb.nodeOff, tb.height, tb.parent, tb.nodeType, tb.chgCount,
                              tb.chgBase, tb.chgTime, tb.chgType)]
     logP = torch.zeros(B, dtype=torch.float64, device="cuda")

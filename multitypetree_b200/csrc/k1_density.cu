@@ -143,26 +143,30 @@ __device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, i
 // =====================================================================================
 // warp-per-tree kernel
 // =====================================================================================
-constexpr int W_EMAX = 512;               // largest tree (nodes + changes) on the warp path
+// The kernel body must stay resident in the 32 KB instruction cache: an earlier fully
+// unrolled version (13k SASS instructions) spent most of its cycles in instruction-fetch
+// stalls.  Only the 256-key sorting network is unrolled; everything else is a rolled loop
+// over shared memory.
 constexpr int W_WARPS = 8;                // warps per CTA
-constexpr int W_TIME_BYTES = 8 * W_EMAX + 64;
-constexpr int W_TYPE_BYTES = W_EMAX + 64;
-constexpr int W_CNT_BYTES = 2 * W_EMAX + 32;
-constexpr int W_PAR_BYTES = 4 * W_EMAX + 32;
+constexpr uint32_t KEY_PAD = 0xffffffffu;
+constexpr int IDX_BITS = 9;               // event index inside a tree (E <= 512)
+constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;
 
-template <bool HAS_PARENT>
+template <bool HAS_PARENT, int EMAX>
 struct WarpStage {
-    alignas(16) unsigned char time[W_TIME_BYTES];   // heights | change times
-    alignas(16) unsigned char type[W_TYPE_BYTES];   // node types | change types
-    alignas(16) unsigned char cnt[W_CNT_BYTES];     // change counts
-    alignas(16) unsigned char par[HAS_PARENT ? W_PAR_BYTES : 16];
+    alignas(16) unsigned char time[8 * EMAX + 64];   // heights | change times
+    alignas(16) unsigned char type[EMAX + 64];       // node types | change types
+    alignas(16) unsigned char cnt[2 * EMAX + 32];    // change counts
+    alignas(16) unsigned char par[HAS_PARENT ? 4 * EMAX + 32 : 16];
 };
 
-template <bool HAS_PARENT>
+template <bool HAS_PARENT, int EMAX>
 struct WarpSmem {
-    WarpStage<HAS_PARENT> st[2];
-    alignas(8) unsigned long long bar[2];
-    alignas(8) uint16_t desc[W_EMAX];
+    WarpStage<HAS_PARENT, EMAX> st;       // one staged tree; latency is hidden by the other
+                                          // resident warps (24 per SM), not by prefetching
+    alignas(16) uint32_t keys[EMAX];      // time-ordered (quantised time | event index)
+    alignas(8) unsigned long long bar;
+    alignas(8) uint16_t desc[EMAX];       // kind | from | to per event
 };
 
 struct TreeSpan {
@@ -225,9 +229,9 @@ __device__ __forceinline__ StageLayout make_layout(const K1Params &p, const Tree
 }
 
 // one elected lane: arm the stage's mbarrier and launch the bulk copies
-template <bool HAS_PARENT>
+template <bool HAS_PARENT, int EMAX>
 __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
-                                           WarpStage<HAS_PARENT> *st, uint64_t *bar)
+                                           WarpStage<HAS_PARENT, EMAX> *st, uint64_t *bar)
 {
     const StageLayout L = make_layout<HAS_PARENT>(p, s);
     mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szT + L.szCT + L.szK + L.szP);
@@ -251,13 +255,12 @@ __device__ __forceinline__ void ce_u32(uint32_t &a, uint32_t &b)
     b = hi;
 }
 
-// Bitonic sort of 32*EPL keys held EPL per lane; position = EPL * lane + r.  Every
-// compare-exchange is "lower position keeps the minimum": each merge starts with the
-// reflected partner, followed by ordinary half cleaners (no direction flags).
-template <int EPL>
-__device__ __forceinline__ void warp_sort(uint32_t (&v)[EPL], int lane)
+// Bitonic sort of 256 keys held 8 per lane; position = 8 * lane + r.  Every compare-exchange
+// is "lower position keeps the minimum": each merge starts with the reflected partner,
+// followed by ordinary half cleaners (no direction flags).
+__device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane)
 {
-    // blocks of 2 .. EPL positions: inside the lane
+    constexpr int EPL = 8;
 #pragma unroll
     for (int size = 2; size <= EPL; size <<= 1) {
 #pragma unroll
@@ -274,7 +277,6 @@ __device__ __forceinline__ void warp_sort(uint32_t (&v)[EPL], int lane)
                     ce_u32(v[r], v[r | s]);
         }
     }
-    // blocks of 2 .. 32 lanes
 #pragma unroll
     for (int lanes = 2; lanes <= 32; lanes <<= 1) {
         {   // reflected partner: lane ^ (lanes - 1), register EPL-1-r
@@ -306,16 +308,6 @@ __device__ __forceinline__ void warp_sort(uint32_t (&v)[EPL], int lane)
     }
 }
 
-__device__ __forceinline__ bool ce_td(double &ta, uint32_t &da, double &tb, uint32_t &db)
-{
-    if (ta > tb) {
-        const double t = ta; ta = tb; tb = t;
-        const uint32_t d = da; da = db; db = d;
-        return true;
-    }
-    return false;
-}
-
 template <int NW>
 __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
 {
@@ -329,17 +321,14 @@ __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
     return (int)((w >> (16 * (deme & 3))) & 0xffffu);
 }
 
-// One staged tree, EPL events per lane (E <= 32 * EPL).  Returns the warp-reduced logP in
-// lane 0; `okOut` is the validity verdict (all lanes).  Code size matters here (the body
-// must stay instruction-cache resident): only the phases that index register arrays are
-// unrolled.
-template <int NW, bool HAS_PARENT, int EPL>
-__device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
-                                               const StageLayout &L, uint16_t *desc, int n, int M,
-                                               const ModelTab *tab, int d, int lane, bool &okOut)
+// One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
+// the validity verdict (all lanes).
+template <int NW, bool HAS_PARENT, int EMAX>
+__device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *st,
+                                               const StageLayout &L, uint16_t *desc,
+                                               uint32_t *keys, int n, int M, const ModelTab *tab,
+                                               int d, int lane, bool &okOut)
 {
-    constexpr int IDX_BITS = (EPL == 8) ? 8 : 9;
-    constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;   // all-ones is the padding key
     const int E = n + M;
     const int nLeaves = (n + 1) >> 1;
     const double *sH = reinterpret_cast<const double *>(st->time + L.hOff);
@@ -348,16 +337,17 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     const uint8_t *sCT = st->type + L.ctOff;
     const uint16_t *sK = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);
     const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
+    auto ev_time = [&](int e) -> double { return (e < n) ? sH[e] : sC[e - n]; };
 
-    // ---- phase A: descriptors (lane owns nodes [EPL*lane, EPL*lane+EPL)), validity
+    // ---- phase A: event descriptors; lane owns nodes [per*lane, per*lane+per); validity
     bool ok = true;
     {
-        const int e0 = EPL * lane;
+        const int per = (n + 31) >> 5;
+        const int e0 = per * lane, e1 = min(e0 + per, n);
         int mine = 0;
 #pragma unroll 1
-        for (int j = 0; j < EPL; j++)
-            if (e0 + j < n)
-                mine += sK[e0 + j];
+        for (int e = e0; e < e1; e++)
+            mine += sK[e];
         int incl = mine;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -366,22 +356,17 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
                 incl += v;
         }
         int off = incl - mine;
-        if (incl > M) {                                      // inconsistent chgCount / chgBase
-            ok = false;
-            off = 0;
-            mine = 0;
-        }
+        const bool sane = incl <= M;                         // chgCount consistent with chgBase
+        ok = sane;
 #pragma unroll 1
-        for (int j = 0; j < EPL; j++) {
-            const int e = e0 + j;
-            if (e >= n)
-                break;
-            const int c = (mine > 0) ? (int)sK[e] : 0;
+        for (int e = e0; e < e1; e++) {
+            const int c = sane ? (int)sK[e] : 0;
             int type = sT[e];
             desc[e] = (uint16_t)(((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | type << 5);
             const int par = HAS_PARENT ? sP[e] : 0;
             const bool isRoot = HAS_PARENT && par < 0;
             double lastT = HAS_PARENT ? sH[e] : 0.0;
+#pragma unroll 1
             for (int q = 0; q < c; q++) {
                 const int to = sCT[off + q];
                 desc[n + off + q] =
@@ -404,88 +389,115 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
     okOut = ok;
     __syncwarp();
 
-    // ---- keys: quantised time | event index (interleaved, conflict-free reads)
-    double tm[EPL];
-    uint32_t ds[EPL];
+    // ---- time range (interleaved, conflict-free reads)
     double lo = INFINITY, hi = -INFINITY;
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-        const int e = lane + 32 * k;
-        double x = INFINITY;
-        if (e < E) {
-            x = (e < n) ? sH[e] : sC[e - n];
-            if (HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)
-                x = INFINITY;                                // root-branch change: ignored (:161-162)
-        }
-        tm[k] = x;
-        if (x < INFINITY) {
-            lo = fmin(lo, x);
-            hi = fmax(hi, x);
-        }
+#pragma unroll 1
+    for (int e = lane; e < E; e += 32) {
+        if (HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)
+            continue;                                        // root-branch change: ignored (:161-162)
+        const double x = ev_time(e);
+        lo = fmin(lo, x);
+        hi = fmax(hi, x);
     }
     lo = warp_min(lo);
     hi = warp_max(hi);
     const double range = hi - lo;
     const double scale = (range > 0.0) ? (double)QMAX / range : 0.0;
-    uint32_t key[EPL];
-#pragma unroll
-    for (int k = 0; k < EPL; k++) {
-        uint32_t q = (uint32_t)((tm[k] - lo) * scale);
-        q = min(q, QMAX);
-        key[k] = (tm[k] < INFINITY) ? ((q << IDX_BITS) | (uint32_t)(lane + 32 * k)) : 0xffffffffu;
-    }
 
-    // ---- phase B: order
-    warp_sort<EPL>(key, lane);
-
-    // ---- phase C: exact times + descriptors in sorted order, then repair quantisation ties
+    // ---- phase B: order.  256 events at a time through the register network, sorted runs
+    //      land in keys[]; a second run is merged in shared memory.
+    int Epad = (E > 256) ? 512 : 256;
+    asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
+#pragma unroll 1
+    for (int base = 0; base < Epad; base += 256) {
+        uint32_t key[8];
 #pragma unroll
-    for (int r = 0; r < EPL; r++) {
-        const bool pad = key[r] == 0xffffffffu;
-        const int idx = pad ? 0 : (int)(key[r] & ((1u << IDX_BITS) - 1));
-        const double x = (idx < n) ? sH[idx] : sC[idx - n];
-        tm[r] = pad ? INFINITY : x;
-        ds[r] = pad ? (uint32_t)(KIND_NONE << 10) : (uint32_t)desc[idx];
+        for (int k = 0; k < 8; k++) {
+            const int e = base + lane + 32 * k;
+            uint32_t kk = KEY_PAD;
+            if (e < E && !(HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)) {
+                uint32_t q = (uint32_t)((ev_time(e) - lo) * scale);
+                q = min(q, QMAX);
+                kk = (q << IDX_BITS) | (uint32_t)e;
+            }
+            key[k] = kk;
+        }
+        warp_sort256(key, lane);
+        uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
+        dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
+        dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
     }
-    {
-        bool swapped;
-        do {
-            swapped = false;
-#pragma unroll
-            for (int i = 0; i + 1 < EPL; i += 2)
-                swapped |= ce_td(tm[i], ds[i], tm[i + 1], ds[i + 1]);
-#pragma unroll
-            for (int i = 1; i + 1 < EPL; i += 2)
-                swapped |= ce_td(tm[i], ds[i], tm[i + 1], ds[i + 1]);
-            // lane boundary: my last against the next lane's first
-            const double nt = __shfl_down_sync(FULL_MASK, tm[0], 1);
-            const uint32_t nd = __shfl_down_sync(FULL_MASK, ds[0], 1);
-            const bool sw = (lane < 31) && (tm[EPL - 1] > nt);
-            const unsigned swMask = __ballot_sync(FULL_MASK, sw);
-            if (swMask) {                                    // rare
-                const double pt = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
-                const uint32_t pd = __shfl_up_sync(FULL_MASK, ds[EPL - 1], 1);
-                if (sw) {
-                    tm[EPL - 1] = nt;
-                    ds[EPL - 1] = nd;
-                }
-                if (lane > 0 && ((swMask >> (lane - 1)) & 1)) {
-                    tm[0] = pt;
-                    ds[0] = pd;
+    __syncwarp();
+    if (EMAX > 256 && Epad == 512) {
+        // bitonic merge of the two ascending runs: reflected step, then half cleaners
+#pragma unroll 1
+        for (int stride = 256; stride >= 1; stride >>= 1) {
+#pragma unroll 1
+            for (int i = lane; i < 256; i += 32) {
+                const int a = 2 * i - (i & (stride - 1));
+                const int b = (stride == 256) ? (511 - a) : (a + stride);
+                const uint32_t ka = keys[a], kb = keys[b];
+                if (ka > kb) {
+                    keys[a] = kb;
+                    keys[b] = ka;
                 }
             }
-            swapped = __any_sync(FULL_MASK, swapped) || swMask != 0;
-        } while (swapped);
+            __syncwarp();
+        }
+    }
+
+    // ---- phase C: lane owns positions [per*lane, per*lane+per); local count deltas, and a
+    //      check that quantisation ties came out in exact time order (repaired if not)
+    const int per = Epad >> 5;
+    const int p0 = per * lane;
+    Counts<NW> local;
+    for (;;) {
+#pragma unroll
+        for (int i = 0; i < NW; i++)
+            local.w[i] = 0;
+        bool inv = false;
+        double prevT = -INFINITY;
+        if (lane > 0) {
+            const uint32_t kp = keys[p0 - 1];
+            if (kp != KEY_PAD)
+                prevT = ev_time((int)(kp & ((1u << IDX_BITS) - 1)));
+        }
+#pragma unroll 2
+        for (int q = 0; q < per; q++) {
+            const uint32_t k = keys[p0 + q];
+            if (k == KEY_PAD)
+                break;
+            const int idx = (int)(k & ((1u << IDX_BITS) - 1));
+            const double x = ev_time(idx);
+            inv |= x < prevT;
+            prevT = x;
+            cnt_apply<NW>(local, desc[idx]);
+        }
+        if (!__any_sync(FULL_MASK, inv))
+            break;
+        // rare: odd-even transposition on exact times until sorted
+        bool swapped = true;
+        while (swapped) {
+            swapped = false;
+#pragma unroll 1
+            for (int parity = 0; parity < 2; parity++) {
+#pragma unroll 1
+                for (int a = parity + 2 * lane; a + 1 < Epad; a += 64) {
+                    const uint32_t ka = keys[a], kb = keys[a + 1];
+                    if (ka != KEY_PAD && kb != KEY_PAD &&
+                        ev_time((int)(ka & 511)) > ev_time((int)(kb & 511))) {
+                        keys[a] = kb;
+                        keys[a + 1] = ka;
+                        swapped = true;
+                    }
+                }
+                __syncwarp();
+            }
+            swapped = __any_sync(FULL_MASK, swapped);
+        }
     }
 
     // ---- phase D: lineage counts by prefix sum, interval integration with a running lambda
-    Counts<NW> local;
-#pragma unroll
-    for (int i = 0; i < NW; i++)
-        local.w[i] = 0;
-#pragma unroll
-    for (int r = 0; r < EPL; r++)
-        cnt_apply<NW>(local, ds[r]);
     Counts<NW> base;
 #pragma unroll
     for (int i = 0; i < NW; i++) {
@@ -498,9 +510,6 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
         }
         base.w[i] = incl - local.w[i];
     }
-    double prevT = __shfl_up_sync(FULL_MASK, tm[EPL - 1], 1);
-    if (lane == 0)
-        prevT = tm[0];
     // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
     double lambda = 0.0;
 #pragma unroll 1
@@ -508,119 +517,109 @@ __device__ __forceinline__ double process_tree(const WarpStage<HAS_PARENT> *st,
         const double kd = (double)cnt_get<NW>(base, c);
         lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
     }
+    double prevT = 0.0;
+    bool first = (lane == 0);                                // event 0 is skipped (:101)
+    if (lane > 0) {
+        const uint32_t kp = keys[p0 - 1];
+        if (kp != KEY_PAD)
+            prevT = ev_time((int)(kp & 511));
+    }
     double acc = 0.0;
-#pragma unroll
-    for (int r = 0; r < EPL; r++) {
-        const int kind = (ds[r] >> 10) & 3, from = (ds[r] >> 5) & 31, to = ds[r] & 31;
-        if (kind != KIND_NONE) {
-            const double dt = tm[r] - prevT;
+#pragma unroll 1
+    for (int q = 0; q < per; q++) {
+        const uint32_t k = keys[p0 + q];
+        if (k == KEY_PAD)
+            break;
+        const int idx = (int)(k & 511);
+        const double x = ev_time(idx);
+        const uint32_t ds = desc[idx];
+        const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+        if (!first) {
+            const double dt = x - prevT;
             if (dt > 0.0)                                    // StructuredCoalescentTreeDensity.java:108
                 acc -= dt * lambda;
-            prevT = tm[r];
-            const bool first = (lane == 0 && r == 0);        // event 0 is skipped (:101)
-            if (kind != KIND_SAMPLE) {                       // a lineage leaves deme `from`
-                if (!first)
-                    acc += (kind == KIND_COALESCE) ? tab->logInvN[from] : tab->logM[from * d + to];
-                const double kd = (double)cnt_get<NW>(base, from);
-                lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
-                cnt_add<NW>(base, from, -1);
-            }
-            if (kind != KIND_COALESCE) {                     // a lineage enters a deme
-                const int a = (kind == KIND_MIGRATE) ? to : from;
-                const double kd = (double)cnt_get<NW>(base, a);
-                lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
-                cnt_add<NW>(base, a, 1);
-            }
         }
+        prevT = x;
+        if (kind != KIND_SAMPLE) {                           // a lineage leaves deme `from`
+            if (!first)
+                acc += (kind == KIND_COALESCE) ? tab->logInvN[from] : tab->logM[from * d + to];
+            const double kd = (double)cnt_get<NW>(base, from);
+            lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
+            cnt_add<NW>(base, from, -1);
+        }
+        if (kind != KIND_COALESCE) {                         // a lineage enters a deme
+            const int a = (kind == KIND_MIGRATE) ? to : from;
+            const double kd = (double)cnt_get<NW>(base, a);
+            lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
+            cnt_add<NW>(base, a, 1);
+        }
+        first = false;
     }
     return warp_sum_down(acc);
 }
 
-// MODE 0: EPL 8 only (E <= 256; larger trees are queued)   MODE 1: EPL 16 only (E <= 512)
-// MODE 2: per tree, EPL 8 when E <= 256 else EPL 16
-template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int MODE>
-__global__ void __launch_bounds__(W_WARPS * 32, 2)
+// EMAX = 256: every tree of the batch is known to have <= 256 events (smaller shared-memory
+// footprint).  EMAX = 512: trees up to 512 events; larger ones are queued for the CTA-per-tree
+// kernel.  Persistent warps, one tree at a time per warp: lane 0 launches the bulk copies of
+// the tree's array slices (TMA engine), the warp waits on its mbarrier, orders and scans.
+template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int EMAX>
+__global__ void __launch_bounds__(W_WARPS * 32, 3)
 k1_density_warp(const K1Params p)
 {
-    constexpr int EMAX = (MODE == 0) ? 256 : 512;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tabs = reinterpret_cast<ModelTab *>(smem_raw);
     constexpr int nTabs = PER_TREE_MODEL ? W_WARPS : 1;
-    WarpSmem<HAS_PARENT> *wsAll =
-        reinterpret_cast<WarpSmem<HAS_PARENT> *>(smem_raw + sizeof(ModelTab) * nTabs);
+    using WS = WarpSmem<HAS_PARENT, EMAX>;
+    WS *wsAll = reinterpret_cast<WS *>(smem_raw + sizeof(ModelTab) * nTabs);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    WarpSmem<HAS_PARENT> *ws = wsAll + warp;
+    WS *ws = wsAll + warp;
     ModelTab *tab = tabs + (PER_TREE_MODEL ? warp : 0);
     const int d = p.d;
 
     if (!PER_TREE_MODEL)
         fill_model_tab(tab, p.m, p.N, d, threadIdx.x, blockDim.x);
     if (lane == 0) {
-        mbar_init((uint64_t *)&ws->bar[0], 1);
-        mbar_init((uint64_t *)&ws->bar[1], 1);
+        mbar_init((uint64_t *)&ws->bar, 1);
         mbar_fence_init();
     }
     __syncthreads();
 
     const long long nWarpsTotal = (long long)gridDim.x * W_WARPS;
     long long t = (long long)blockIdx.x * W_WARPS + warp;
-    uint32_t phase0 = 0, phase1 = 0;
-
+    uint32_t phase = 0;
     TreeSpan cur = load_span(p, t);
-    TreeSpan nxt = load_span(p, t + nWarpsTotal);
-    bool curBig = cur.n + cur.M > EMAX;
-    if (t < p.B && !curBig && lane == 0)
-        issue_tree<HAS_PARENT>(p, cur, &ws->st[0], (uint64_t *)&ws->bar[0]);
 
 #pragma unroll 1
-    for (int it = 0; t < p.B; it++, t += nWarpsTotal) {
-        const int sidx = it & 1;
-        // ---- prefetch this warp's next tree into the other stage
-        const long long tn = t + nWarpsTotal;
-        const bool nxtBig = nxt.n + nxt.M > EMAX;
-        if (tn < p.B && !nxtBig && lane == 0)
-            issue_tree<HAS_PARENT>(p, nxt, &ws->st[sidx ^ 1], (uint64_t *)&ws->bar[sidx ^ 1]);
-        const TreeSpan nxt2 = load_span(p, tn + nWarpsTotal);
-
-        if (curBig) {
+    for (; t < p.B; t += nWarpsTotal) {
+        const TreeSpan nxt = load_span(p, t + nWarpsTotal);     // offsets of my next tree
+        if (cur.n + cur.M > EMAX) {
             // too large for the warp path: queue for k1_density_block
             if (lane == 0) {
                 const int slot = atomicAdd(&p.queue[0], 1);
                 p.queue[1 + slot] = (int)t;
             }
         } else {
-            const WarpStage<HAS_PARENT> *st = &ws->st[sidx];
+            if (lane == 0)
+                issue_tree<HAS_PARENT, EMAX>(p, cur, &ws->st, (uint64_t *)&ws->bar);
             const StageLayout L = make_layout<HAS_PARENT>(p, cur);
             if (PER_TREE_MODEL) {
                 fill_model_tab(tab, p.m + t * d * d, p.N + t * d, d, lane, 32);
                 __syncwarp();
             }
-            if (sidx == 0) {
-                mbar_wait((uint64_t *)&ws->bar[0], phase0);
-                phase0 ^= 1;
-            } else {
-                mbar_wait((uint64_t *)&ws->bar[1], phase1);
-                phase1 ^= 1;
-            }
+            mbar_wait((uint64_t *)&ws->bar, phase);
+            phase ^= 1u;
             bool ok = true;
-            double acc;
-            if (MODE == 0 || (MODE == 2 && cur.n + cur.M <= 256))
-                acc = process_tree<NW, HAS_PARENT, 8>(st, L, ws->desc, cur.n, cur.M, tab, d, lane,
-                                                      ok);
-            else
-                acc = process_tree<NW, HAS_PARENT, 16>(st, L, ws->desc, cur.n, cur.M, tab, d,
-                                                       lane, ok);
+            const double acc = process_tree<NW, HAS_PARENT, EMAX>(&ws->st, L, ws->desc, ws->keys,
+                                                                 cur.n, cur.M, tab, d, lane, ok);
             if (lane == 0) {
                 if (HAS_PARENT && p.valid)
                     p.valid[t] = ok ? 1 : 0;
                 p.logP[t] = (HAS_PARENT && p.checkValidity && !ok) ? -INFINITY : acc;   // :90-91
             }
-            __syncwarp();
+            __syncwarp();      // the stage is free again
         }
         cur = nxt;
-        nxt = nxt2;
-        curBig = nxtBig;
     }
 }
 
@@ -891,35 +890,36 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
     }
 }
 
-template <int NW, bool HP, bool PT, int MODE>
+template <int NW, bool HP, bool PT, int EMAX>
 int launch_warp(mtt_ctx *ctx, const K1Params &p)
 {
-    size_t smem = sizeof(ModelTab) * (PT ? W_WARPS : 1) + sizeof(WarpSmem<HP>) * W_WARPS;
-    auto kern = k1_density_warp<NW, HP, PT, MODE>;
+    constexpr int W = W_WARPS;
+    size_t smem = sizeof(ModelTab) * (PT ? W : 1) + sizeof(WarpSmem<HP, EMAX>) * W;
+    auto kern = k1_density_warp<NW, HP, PT, EMAX>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     int perSM = 1;
-    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, W_WARPS * 32, smem));
+    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, W * 32, smem));
     if (perSM < 1)
         perSM = 1;
-    long long want = (p.B + W_WARPS - 1) / W_WARPS;
+    long long want = (p.B + W - 1) / W;
     long long grid = (long long)ctx->numSMs * perSM;
     if (want < grid)
         grid = want;
-    kern<<<(unsigned)grid, W_WARPS * 32, smem, ctx->stream>>>(p);
+    kern<<<(unsigned)grid, W * 32, smem, ctx->stream>>>(p);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
 }
 
-template <int NW, int MODE>
-int launch_warp_mode(mtt_ctx *ctx, const K1Params &p)
+template <int NW, int EMAX>
+int launch_warp_any(mtt_ctx *ctx, const K1Params &p)
 {
     const bool hp = p.parent != nullptr, pt = p.nModels > 1;
     if (hp)
-        return pt ? launch_warp<NW, true, true, MODE>(ctx, p)
-                  : launch_warp<NW, true, false, MODE>(ctx, p);
-    return pt ? launch_warp<NW, false, true, MODE>(ctx, p)
-              : launch_warp<NW, false, false, MODE>(ctx, p);
+        return pt ? launch_warp<NW, true, true, EMAX>(ctx, p)
+                  : launch_warp<NW, true, false, EMAX>(ctx, p);
+    return pt ? launch_warp<NW, false, true, EMAX>(ctx, p)
+              : launch_warp<NW, false, false, EMAX>(ctx, p);
 }
 
 template <int NW>
@@ -953,24 +953,13 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
         if (Ecap > MTT_MAX_TREE_EVENTS)
             Ecap = MTT_MAX_TREE_EVENTS;
     }
-    static const char *force = getenv("MTT_K1_FORCE_MODE");      // development knob
-    if (force && force[0] == '0') {                 // EPL-8 warp path + block kernel for the rest
-        int rc0 = launch_warp_mode<NW, 0>(ctx, p);
-        if (rc0 != MTT_OK || (maxEvents > 0 && maxEvents <= 256))
-            return rc0;
-        rc0 = launch_block<NW>(ctx, p, Ecap, 1, 0);
-        if (rc0 != MTT_OK)
-            return rc0;
-        MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
-        return MTT_OK;
-    }
-    if (maxEvents > 0 && maxEvents <= 256 && !(force && force[0] == '2'))
-        return launch_warp_mode<NW, 0>(ctx, p);     // one launch, nothing can be queued
-    if (maxEvents > 0 && maxEvents <= W_EMAX)
-        return launch_warp_mode<NW, 2>(ctx, p);
-    // some trees may exceed the warp path: they are queued and consumed by the block kernel,
-    // which leaves the queue counter at zero again for the next call
-    int rc = launch_warp_mode<NW, 2>(ctx, p);
+    if (maxEvents > 0 && maxEvents <= 256)          // one launch, nothing can be queued
+        return launch_warp_any<NW, 256>(ctx, p);
+    if (maxEvents > 0 && maxEvents <= 512)
+        return launch_warp_any<NW, 512>(ctx, p);
+    // some trees may exceed the warp path: they are queued and consumed by the block kernel;
+    // the queue counter is zeroed again for the next call
+    int rc = launch_warp_any<NW, 512>(ctx, p);
     if (rc != MTT_OK)
         return rc;
     rc = launch_block<NW>(ctx, p, Ecap, 1, 0);

@@ -49,19 +49,23 @@ struct mtt_peel {
     double *dMatsIn = nullptr; size_t matsInCap = 0;
     double *dLogL = nullptr; size_t logLCap = 0;
     int *dInfo = nullptr; size_t infoCap = 0;   // per tree: max slots used (or -1 = bad tree)
+    int *dMaxSlots = nullptr;                   // max over the chunk of the above
+    int *hMaxSlots = nullptr;                   // pinned host copy
 };
 
 namespace {
 
-constexpr int TP = 128;                 // pattern padding granule (largest tile)
+constexpr int TP = 256;                 // pattern padding granule (largest tile: 128 threads x 2)
 constexpr int PREP_THREADS = 128;
 constexpr int MAX_SLOTS = 24;
 
 struct PeelOp {
     int c1, c2;     // child refs: >= 0 slot of an internal child, < 0 tip index as -(tip+1)
     int dst;        // slot receiving this node's partials
-    int node;
+    int flags;      // bit 0 / 1: child 1 / 2 is the result of the previous op (still in
+                    // registers); bit 2: this result must be parked in its slot
 };
+constexpr int OP_C1_PREV = 1, OP_C2_PREV = 2, OP_STORE = 4;
 
 // ---- HKY.getTransitionProbabilities [EXT] (closed form) ---------------
 __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double distance,
@@ -102,7 +106,7 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
-           int *info)
+           int *info, int *maxSlotsAll)
 {
     extern __shared__ int smi[];
     const int N = 2 * n - 1, nOps = n - 1;
@@ -190,7 +194,9 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
                 stack[sp++] = rightFirst ? right[v] : left[v];    // first: popped last
                 stack[sp++] = rightFirst ? left[v] : right[v];    // second: popped first
             }
-            // pass 3b: slots, in execution order
+            // pass 3b, in execution order.  An internal second child is always the previous op;
+            // an internal first child is the previous op when the second child is a tip.  Only
+            // a first child whose sibling is internal has to park its result in a slot.
             unsigned long long freeMask = ~0ull;
             int maxSlots = 0;
             for (int k = 0; k < nOps; k++) {
@@ -199,18 +205,26 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
                 const int c1 = rightFirst ? right[v] : left[v];
                 const int c2 = rightFirst ? left[v] : right[v];
                 PeelOp op;
-                op.c1 = (c1 < n) ? -(c1 + 1) : (need[c1] & 0x7f);
-                op.c2 = (c2 < n) ? -(c2 + 1) : (need[c2] & 0x7f);
-                if (c1 >= n)
+                op.flags = (c2 >= n) ? OP_C2_PREV : ((c1 >= n) ? OP_C1_PREV : 0);
+                op.c1 = (c1 < n) ? -(c1 + 1) : ((op.flags & OP_C1_PREV) ? 0 : (need[c1] & 0x7f));
+                op.c2 = (c2 < n) ? -(c2 + 1) : 0;
+                if (c1 >= n && !(op.flags & OP_C1_PREV))
                     freeMask |= 1ull << (need[c1] & 0x7f);
-                if (c2 >= n)
-                    freeMask |= 1ull << (need[c2] & 0x7f);
-                const int dst = __ffsll((long long)freeMask) - 1;
-                freeMask &= ~(1ull << dst);
-                need[v] = (uint8_t)((need[v] & 0x80) | dst);
-                maxSlots = max(maxSlots, dst + 1);
-                op.dst = dst;
-                op.node = v;
+                op.dst = 0;
+                if (v != root) {
+                    const int pp = parent[v];
+                    const bool pRightFirst = need[pp] & 0x80;
+                    const int pFirst = pRightFirst ? right[pp] : left[pp];
+                    const int pSecond = pRightFirst ? left[pp] : right[pp];
+                    if (pFirst == v && pSecond >= n) {
+                        const int dst = __ffsll((long long)freeMask) - 1;
+                        freeMask &= ~(1ull << dst);
+                        need[v] = (uint8_t)((need[v] & 0x80) | dst);
+                        maxSlots = max(maxSlots, dst + 1);
+                        op.dst = dst;
+                        op.flags |= OP_STORE;
+                    }
+                }
                 ops[k] = op;
                 stack[k] = v;              // op -> node, for the matrix pass below
             }
@@ -223,8 +237,10 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
             info[b] = -1;
         return;
     }
-    if (tid == 0)
+    if (tid == 0) {
         info[b] = sMaxSlots;
+        atomicMax(maxSlotsAll, sMaxSlots);
+    }
 
     // transition matrices of both children of every op, in op order:
     // mats[op][child j][category c][16]
@@ -258,44 +274,41 @@ struct PeelCfg {
     static constexpr int OPS_PER_STAGE = (C == 1) ? 32 : (C == 2 ? 16 : (C <= 4 ? 8 : 4));
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
+    static constexpr int PPT = (C <= 4) ? 2 : 1;       // patterns per thread
 };
 
-// partials of one child for category c -> a[i] = sum_j M[i][j] x[j]  (or the tip column)
-template <int C, int TPT>
-__device__ __forceinline__ void child_term(int ref, const double *M, const double *stackBase,
-                                           int c, int tid, const uint8_t *tipRow, long long p,
-                                           double (&a)[4], int &tipState, bool &tipLoaded)
+// one child's contribution for PPT patterns of one category:
+//   a[u][i] = sum_j M[i][j] x[u][j]      (internal child; x from registers or its slot)
+//   a[u][i] = M[i][state_u] or 1         (tip child)
+template <int PPT>
+__device__ __forceinline__ void child_term(bool isTip, const double *M, const double (&x)[PPT][4],
+                                           const int (&tip)[PPT], double (&a)[PPT][4])
 {
-    if (ref < 0) {
-        if (!tipLoaded) {
-            tipState = tipRow[p];
-            tipLoaded = true;
-        }
-        if (tipState < 4) {
+    if (isTip) {
+#pragma unroll
+        for (int u = 0; u < PPT; u++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                a[i] = M[i * 4 + tipState];
-        } else {                                    // gap / ambiguity: treated as unknown
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                a[i] = 1.0;
-        }
+                a[u][i] = (tip[u] < 4) ? M[i * 4 + tip[u]] : 1.0;   // gap / ambiguity: unknown
     } else {
-        const double *x = stackBase + ((size_t)(ref * C + c) * 4) * TPT + tid;
-        const double x0 = x[0], x1 = x[TPT], x2 = x[2 * TPT], x3 = x[3 * TPT];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            double s = M[i * 4 + 0] * x0;
-            s += M[i * 4 + 1] * x1;
-            s += M[i * 4 + 2] * x2;
-            s += M[i * 4 + 3] * x3;
-            a[i] = s;
+            const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 4);
+            const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 4 + 2);
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                double s = m01.x * x[u][0];
+                s += m01.y * x[u][1];
+                s += m23.x * x[u][2];
+                s += m23.y * x[u][3];
+                a[u][i] = s;
+            }
         }
     }
 }
 
-// TPT = patterns per tile = threads per CTA (128, 64 or 32: smaller tiles when many rate
-// categories make the live partial vectors large)
+// TPT threads per CTA, PPT patterns per thread: a tile is TPT * PPT patterns
+// (pattern of (thread, u) = tile * TPT * PPT + u * TPT + tid, so global reads stay coalesced)
 template <int C, int TPT>
 __global__ void __launch_bounds__(TPT)
 k2_peel(int n, long long P, long long pStride, const uint8_t *states, const double *weights,
@@ -304,17 +317,18 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
         double *patternLogL)
 {
     using Cfg = PeelCfg<C>;
+    constexpr int PPT = Cfg::PPT;
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: [2 stages: ops | mats][barriers][stack nSlots*C*4*TP doubles]
+    // layout: [2 stages: ops | mats][barriers][stack nSlots*C*4*PPT*TPT doubles]
     unsigned char *stageBase = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::STAGE_BYTES);
     double *stackBase = reinterpret_cast<double *>(smem + 2 * Cfg::STAGE_BYTES + 16);
-    __shared__ double red[TPT / 32];
+    __shared__ double red[(TPT + 31) / 32];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int tile = blockIdx.x, b = blockIdx.y;
     const int nOps = n - 1;
-    const long long p = (long long)tile * TPT + tid;         // < pStride by construction
+    const long long p0 = (long long)tile * TPT * PPT + tid;   // + u * TPT; < pStride
     const PeelOp *ops = opsAll + (size_t)b * nOps;
     const double *mats = matsAll + (size_t)b * nOps * Cfg::MAT_DOUBLES_PER_OP;
     const int treeInfo = info[b];
@@ -322,8 +336,10 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     if (treeInfo < 0 || treeInfo > nSlots) {                 // malformed tree: NaN, loudly
         if (tid == 0)
             partial[(size_t)b * nTiles + tile] = NAN;
-        if (patternLogL && p < P)
-            patternLogL[p] = NAN;
+        if (patternLogL)
+            for (int u = 0; u < PPT; u++)
+                if (p0 + u * TPT < P)
+                    patternLogL[p0 + u * TPT] = NAN;
         return;
     }
     if (tid == 0) {
@@ -347,88 +363,178 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     if (tid == 0)
         issue(0);
 
-    double out[C][4];
-    double logScale = 0.0;
-    uint32_t ph0 = 0, ph1 = 0;
+    // tip states of the op about to run are fetched one op ahead
+    auto load_tips = [&](const PeelOp &op, int (&t1)[PPT], int (&t2)[PPT]) {
+        if (op.c1 < 0) {
+            const uint8_t *row = states + (size_t)(-op.c1 - 1) * pStride + p0;
+#pragma unroll
+            for (int u = 0; u < PPT; u++)
+                t1[u] = __ldg(row + u * TPT);
+        }
+        if (op.c2 < 0) {
+            const uint8_t *row = states + (size_t)(-op.c2 - 1) * pStride + p0;
+#pragma unroll
+            for (int u = 0; u < PPT; u++)
+                t2[u] = __ldg(row + u * TPT);
+        }
+    };
+
+    double prev[PPT][C][4];          // result of the previous op (top of the stack, in registers)
+    double logScale[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+        logScale[u] = 0.0;
+#pragma unroll
+        for (int c = 0; c < C; c++)
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                prev[u][c][i] = 1.0;
+    }
+    uint32_t phaseBits = 0;
     for (int s = 0; s < nStages; s++) {
         if (tid == 0 && s + 1 < nStages)
             issue(s + 1);      // the other stage was released by the __syncthreads below
-        if (s & 1) {
-            mbar_wait(&bars[1], ph1);
-            ph1 ^= 1;
-        } else {
-            mbar_wait(&bars[0], ph0);
-            ph0 ^= 1;
-        }
+        mbar_wait(&bars[s & 1], (phaseBits >> (s & 1)) & 1u);
+        phaseBits ^= 1u << (s & 1);
         const unsigned char *st = stageBase + (s & 1) * Cfg::STAGE_BYTES;
         const PeelOp *sOps = reinterpret_cast<const PeelOp *>(st);
         const double *sMats = reinterpret_cast<const double *>(st + Cfg::OPS_PER_STAGE * 16);
         const int cnt = min(Cfg::OPS_PER_STAGE, nOps - s * Cfg::OPS_PER_STAGE);
+        int nt1[PPT], nt2[PPT];
+#pragma unroll
+        for (int u = 0; u < PPT; u++)
+            nt1[u] = nt2[u] = 4;
+        load_tips(sOps[0], nt1, nt2);
+#pragma unroll 1
         for (int k = 0; k < cnt; k++) {
             const PeelOp op = sOps[k];
-            int ts1 = 0, ts2 = 0;
-            bool l1 = false, l2 = false;
-            const uint8_t *row1 = op.c1 < 0 ? states + (size_t)(-op.c1 - 1) * pStride : nullptr;
-            const uint8_t *row2 = op.c2 < 0 ? states + (size_t)(-op.c2 - 1) * pStride : nullptr;
-            double mx = 0.0;
+            int t1[PPT], t2[PPT];
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                t1[u] = nt1[u];
+                t2[u] = nt2[u];
+            }
+            if (k + 1 < cnt)
+                load_tips(sOps[k + 1], nt1, nt2);
+            double nw[PPT][C][4];
+            double mx[PPT];
+#pragma unroll
+            for (int u = 0; u < PPT; u++)
+                mx[u] = 0.0;
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 const double *M1 = sMats + (size_t)k * Cfg::MAT_DOUBLES_PER_OP + c * 16;
                 const double *M2 = M1 + C * 16;
-                double a[4], bb[4];
-                child_term<C, TPT>(op.c1, M1, stackBase, c, tid, row1, p, a, ts1, l1);
-                child_term<C, TPT>(op.c2, M2, stackBase, c, tid, row2, p, bb, ts2, l2);
+                double x[PPT][4], a[PPT][4], bb[PPT][4];
+                // child 1
+                if (op.c1 >= 0) {
+                    if (op.flags & OP_C1_PREV) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    out[c][i] = a[i] * bb[i];
-                    mx = fmax(mx, out[c][i]);
+                        for (int u = 0; u < PPT; u++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                x[u][i] = prev[u][c][i];
+                    } else {
+                        const double *src = stackBase + ((size_t)(op.c1 * C + c) * 4) * PPT * TPT + tid;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int u = 0; u < PPT; u++)
+                                x[u][i] = src[(i * PPT + u) * TPT];
+                    }
                 }
+                child_term<PPT>(op.c1 < 0, M1, x, t1, a);
+                // child 2
+                if (op.c2 >= 0) {
+                    if (op.flags & OP_C2_PREV) {
+#pragma unroll
+                        for (int u = 0; u < PPT; u++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                x[u][i] = prev[u][c][i];
+                    } else {
+                        const double *src = stackBase + ((size_t)(op.c2 * C + c) * 4) * PPT * TPT + tid;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int u = 0; u < PPT; u++)
+                                x[u][i] = src[(i * PPT + u) * TPT];
+                    }
+                }
+                child_term<PPT>(op.c2 < 0, M2, x, t2, bb);
+#pragma unroll
+                for (int u = 0; u < PPT; u++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        nw[u][c][i] = a[u][i] * bb[u][i];
+                        mx[u] = fmax(mx[u], nw[u][c][i]);
+                    }
             }
             // BeerLikelihoodCore.scalePartials [EXT]
-            if (mx < SCALING_THRESHOLD) {
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                if (mx[u] < SCALING_THRESHOLD) {
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            nw[u][c][i] /= mx[u];
+                    logScale[u] += log(mx[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < PPT; u++)
 #pragma unroll
                 for (int c = 0; c < C; c++)
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        out[c][i] /= mx;
-                logScale += log(mx);
+                        prev[u][c][i] = nw[u][c][i];
+            if (op.flags & OP_STORE) {
+                double *dst = stackBase + ((size_t)(op.dst * C) * 4) * PPT * TPT + tid;
+#pragma unroll
+                for (int c = 0; c < C; c++)
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
+#pragma unroll
+                        for (int u = 0; u < PPT; u++)
+                            dst[((c * 4 + i) * PPT + u) * TPT] = nw[u][c][i];
             }
-            double *dst = stackBase + ((size_t)(op.dst * C) * 4) * TPT + tid;
-#pragma unroll
-            for (int c = 0; c < C; c++)
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    dst[(c * 4 + i) * TPT] = out[c][i];
         }
         __syncthreads();       // every thread is done with this stage's ops and matrices
     }
 
-    // root: integratePartials, proportion invariant, frequencies, log  [EXT]
+    // root (= result of the last op): integratePartials, proportion invariant, frequencies, log
     const double *catProps = site + C, *freqs = site + 2 * C;
-    double root[4];
+    double contrib = 0.0;
 #pragma unroll
-    for (int i = 0; i < 4; i++) {
-        double r = out[0][i] * catProps[0];
+    for (int u = 0; u < PPT; u++) {
+        const long long p = p0 + u * TPT;
+        double root[4];
 #pragma unroll
-        for (int c = 1; c < C; c++)
-            r += out[c][i] * catProps[c];
-        root[i] = r;
-    }
-    if (pInv > 0.0) {
-        const int cm = constMask[p];
+        for (int i = 0; i < 4; i++) {
+            double r = prev[u][0][i] * catProps[0];
+#pragma unroll
+            for (int c = 1; c < C; c++)
+                r += prev[u][c][i] * catProps[c];
+            root[i] = r;
+        }
+        if (pInv > 0.0) {
+            const int cm = constMask[p];
+#pragma unroll
+            for (int i = 0; i < 4; i++)
+                if (cm & (1 << i))
+                    root[i] += pInv;
+        }
+        double sum = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; i++)
-            if (cm & (1 << i))
-                root[i] += pInv;
+            sum += freqs[i] * root[i];
+        const double ll = log(sum) + logScale[u];
+        if (patternLogL && p < P)
+            patternLogL[p] = ll;
+        if (p < P)
+            contrib += ll * weights[p];
     }
-    double sum = 0.0;
-#pragma unroll
-    for (int i = 0; i < 4; i++)
-        sum += freqs[i] * root[i];
-    const double ll = log(sum) + logScale;
-    if (patternLogL && p < P)
-        patternLogL[p] = ll;
-    double contrib = (p < P) ? ll * weights[p] : 0.0;
     contrib = warp_sum_down(contrib);
     if (lane == 0)
         red[warp] = contrib;
@@ -436,7 +542,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     if (tid == 0) {
         double t = 0.0;
 #pragma unroll
-        for (int w = 0; w < TPT / 32; w++)
+        for (int w = 0; w < (TPT + 31) / 32; w++)
             t += red[w];
         partial[(size_t)b * nTiles + tile] = t;
     }
@@ -493,8 +599,8 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
 {
     mtt_ctx *ctx = h->ctx;
     using Cfg = PeelCfg<C>;
-    const int nTiles = (int)(h->pStride / TPT);
-    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * TPT * 8;
+    const int nTiles = (int)(h->pStride / (TPT * Cfg::PPT));
+    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * Cfg::PPT * TPT * 8;
     auto kern = k2_peel<C, TPT>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -507,12 +613,12 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
     return MTT_OK;
 }
 
-// tile size: the largest of 128 / 64 / 32 patterns whose live partial vectors leave room for
+// threads per CTA: the largest of 128 / 64 / 32 whose live partial vectors leave room for
 // at least two CTAs per SM
-inline int pick_tile(int C, int nSlots, size_t stageBytes)
+inline int pick_tile(int C, int ppt, int nSlots, size_t stageBytes)
 {
     for (int t = 128; t >= 32; t >>= 1)
-        if (2 * stageBytes + 16 + (size_t)nSlots * C * 4 * t * 8 <= 110 * 1024 || t == 32)
+        if (2 * stageBytes + 16 + (size_t)nSlots * C * 4 * ppt * t * 8 <= 110 * 1024 || t == 32)
             return t;
     return 32;
 }
@@ -521,12 +627,12 @@ template <int C>
 int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *patternLogL)
 {
     using Cfg = PeelCfg<C>;
-    const int t = pick_tile(C, nSlots, Cfg::STAGE_BYTES);
-    if (2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * t * 8 > 227 * 1024)
+    const int t = pick_tile(C, Cfg::PPT, nSlots, Cfg::STAGE_BYTES);
+    if (2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * Cfg::PPT * t * 8 > 227 * 1024)
         return mtt_fail(h->ctx, MTT_ERR_TOO_LARGE,
                         "peeling: %d live partial vectors x %d categories exceed shared memory",
                         nSlots, C);
-    *nTilesOut = (int)(h->pStride / t);
+    *nTilesOut = (int)(h->pStride / (t * Cfg::PPT));
     if (t == 128)
         return launch_peel_t<C, 128>(h, B, nSlots, patternLogL);
     if (t == 64)
@@ -557,15 +663,21 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
                         "shared memory (limit ~6800 tips)", n);
     MTT_CUDA(ctx, cudaFuncSetAttribute(k2_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)prepSmem));
+    if (!h->dMaxSlots) {
+        MTT_CUDA(ctx, cudaMalloc((void **)&h->dMaxSlots, 256));
+        MTT_CUDA(ctx, cudaMallocHost((void **)&h->hMaxSlots, sizeof(int)));
+    }
+    MTT_CUDA(ctx, cudaMemsetAsync(h->dMaxSlots, 0, sizeof(int), ctx->stream));
     k2_prepare<<<(unsigned)B, PREP_THREADS, prepSmem, ctx->stream>>>(
         n, C, dParent, dHeight, dMatsIn, h->dSite, h->branchRate, h->kappa, (PeelOp *)h->dOps,
-        h->dMats, h->dInfo);
+        h->dMats, h->dInfo, h->dMaxSlots);
     MTT_CHECK_LAUNCH(ctx);
-    // Sethi-Ullman bound on live partial vectors: floor(log2(n)) + 1
-    int nSlots = 1;
-    while ((1 << nSlots) <= n)
-        nSlots++;
-    nSlots = std::min(nSlots + 1, MAX_SLOTS);
+    // the number of parked partial vectors sizes the peel kernel's shared memory (a few for
+    // coalescent-shaped trees, up to floor(log2 n) for balanced ones): read it back
+    MTT_CUDA(ctx, cudaMemcpyAsync(h->hMaxSlots, h->dMaxSlots, sizeof(int), cudaMemcpyDeviceToHost,
+                                  ctx->stream));
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    int nSlots = std::max(1, std::min(*h->hMaxSlots, MAX_SLOTS));
     switch (C) {
     case 1: rc = launch_peel<1>(h, B, nSlots, &nTiles, patternLogL); break;
     case 2: rc = launch_peel<2>(h, B, nSlots, &nTiles, patternLogL); break;
@@ -647,7 +759,9 @@ int mtt_peel_destroy(mtt_peel *h)
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->stream);
     void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart,
-                    h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo};
+                    h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots};
+    if (h->hMaxSlots)
+        cudaFreeHost(h->hMaxSlots);
     for (void *p : ptrs)
         if (p)
             cudaFree(p);

@@ -389,13 +389,13 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
     okOut = ok;
     __syncwarp();
 
-    // ---- time range (interleaved, conflict-free reads)
+    // ---- time range over the node heights (interleaved, conflict-free reads).  Change times
+    //      of a valid tree lie inside it; anything outside just saturates the quantised key
+    //      and is put in exact order by the repair pass below.
     double lo = INFINITY, hi = -INFINITY;
-#pragma unroll 1
-    for (int e = lane; e < E; e += 32) {
-        if (HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)
-            continue;                                        // root-branch change: ignored (:161-162)
-        const double x = ev_time(e);
+#pragma unroll 2
+    for (int e = lane; e < n; e += 32) {
+        const double x = sH[e];
         lo = fmin(lo, x);
         hi = fmax(hi, x);
     }

@@ -253,16 +253,22 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         const bool rightFirst = need[v] & 0x80;
         const int child = (j == 0) == rightFirst ? right[v] : left[v];
         double *M = mats + (size_t)idx * 16;
+        double T[16];
         if (matsIn) {
             const double *src = matsIn + ((size_t)child * C + c) * 16;
             for (int e = 0; e < 16; e++)
-                M[e] = src[e];
+                T[e] = src[e];
         } else {
             // TreeLikelihood.traverse [EXT]: jointBranchRate = categoryRate * branchRate
             const double jointBranchRate = catRates[c] * branchRate;
             const double distance = (height[v] - height[child]) * jointBranchRate;
-            hky_matrix(kappa, freqs, distance, M);
+            hky_matrix(kappa, freqs, distance, T);
         }
+        // internal child: row-major P[i][j] (row = parent state) for the mat-vec; tip child:
+        // TRANSPOSED, so that the column of the observed state is 4 contiguous doubles
+        const bool tip = child < n;
+        for (int e = 0; e < 16; e++)
+            M[e] = tip ? T[(e & 3) * 4 + (e >> 2)] : T[e];
     }
 }
 
@@ -285,11 +291,18 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
                                            const int (&tip)[PPT], double (&a)[PPT][4])
 {
     if (isTip) {
+        // M is transposed for tip children: column of the observed state = M[4 s .. 4 s + 3]
 #pragma unroll
-        for (int u = 0; u < PPT; u++)
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                a[u][i] = (tip[u] < 4) ? M[i * 4 + tip[u]] : 1.0;   // gap / ambiguity: unknown
+        for (int u = 0; u < PPT; u++) {
+            const bool known = tip[u] < 4;                          // gap / ambiguity: unknown
+            const double *col = M + (known ? tip[u] * 4 : 0);
+            const double2 c01 = *reinterpret_cast<const double2 *>(col);
+            const double2 c23 = *reinterpret_cast<const double2 *>(col + 2);
+            a[u][0] = known ? c01.x : 1.0;
+            a[u][1] = known ? c01.y : 1.0;
+            a[u][2] = known ? c23.x : 1.0;
+            a[u][3] = known ? c23.y : 1.0;
+        }
     } else {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
@@ -417,10 +430,10 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             if (k + 1 < cnt)
                 load_tips(sOps[k + 1], nt1, nt2);
             double nw[PPT][C][4];
-            double mx[PPT];
+            int mxhi[PPT];       // partials are >= 0: their order is the order of the high words
 #pragma unroll
             for (int u = 0; u < PPT; u++)
-                mx[u] = 0.0;
+                mxhi[u] = 0;
 #pragma unroll
             for (int c = 0; c < C; c++) {
                 const double *M1 = sMats + (size_t)k * Cfg::MAT_DOUBLES_PER_OP + c * 16;
@@ -467,19 +480,29 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
                         nw[u][c][i] = a[u][i] * bb[u][i];
-                        mx[u] = fmax(mx[u], nw[u][c][i]);
+                        mxhi[u] = max(mxhi[u], __double2hiint(nw[u][c][i]));
                     }
             }
-            // BeerLikelihoodCore.scalePartials [EXT]
+            // BeerLikelihoodCore.scalePartials [EXT]: rescale when the largest partial of the
+            // pattern (over categories and states) drops below the threshold.  The cheap test
+            // on the high word is conservative; the exact maximum is formed only when needed.
 #pragma unroll
             for (int u = 0; u < PPT; u++) {
-                if (mx[u] < SCALING_THRESHOLD) {
+                if (mxhi[u] <= __double2hiint(SCALING_THRESHOLD)) {
+                    double mx = 0.0;
 #pragma unroll
                     for (int c = 0; c < C; c++)
 #pragma unroll
                         for (int i = 0; i < 4; i++)
-                            nw[u][c][i] /= mx[u];
-                    logScale[u] += log(mx[u]);
+                            mx = fmax(mx, nw[u][c][i]);
+                    if (mx < SCALING_THRESHOLD) {
+#pragma unroll
+                        for (int c = 0; c < C; c++)
+#pragma unroll
+                            for (int i = 0; i < 4; i++)
+                                nw[u][c][i] /= mx;
+                        logScale[u] += log(mx);
+                    }
                 }
             }
 #pragma unroll

@@ -73,7 +73,7 @@ __device__ __forceinline__ void fill_model_tab(ModelTab *t, const double *m, con
         t->mu[c] = s;
     }
     for (int e = tid; e < d * d; e += nthr)
-        t->logM[e] = (e / d == e % d) ? 0.0 : log(m[e]);
+        t->logM[e] = (e / d == e % d) ? log(1.0 / N[e / d]) : log(m[e]);   // diagonal: coalescence
 }
 
 // lineage counts packed as 16-bit fields, 4 demes per 64-bit word
@@ -322,12 +322,14 @@ __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
 }
 
 // One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
-// the validity verdict (all lanes).
+// the validity verdict (all lanes).  Scratch aliases: `keys` doubles as a byte array during
+// phase A (before the sort writes it); the stage's chgCount region, dead after phase A,
+// receives the time-ordered event index list.
 template <int NW, bool HAS_PARENT, int EMAX>
-__device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *st,
-                                               const StageLayout &L, uint16_t *desc,
-                                               uint32_t *keys, int n, int M, const ModelTab *tab,
-                                               int d, int lane, bool &okOut)
+__device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
+                                            const StageLayout &L, uint16_t *desc,
+                                            uint32_t *keys, int n, int M, const ModelTab *tab,
+                                            int d, int lane, bool &okOut)
 {
     const int E = n + M;
     const int nLeaves = (n + 1) >> 1;
@@ -337,11 +339,14 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
     const uint8_t *sCT = st->type + L.ctOff;
     const uint16_t *sK = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);
     const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
+    uint16_t *order = reinterpret_cast<uint16_t *>(st->cnt);      // written after phase A
     auto ev_time = [&](int e) -> double { return (e < n) ? sH[e] : sC[e - n]; };
 
-    // ---- phase A: event descriptors; lane owns nodes [per*lane, per*lane+per); validity
+    // ---- phase A: event descriptors  kind | from | to  (COALESCE carries to = from so that
+    //      the event term is always tab->logM[from * d + to])
     bool ok = true;
     {
+        // lane owns nodes [per*lane, per*lane+per): exclusive offset of its first change
         const int per = (n + 31) >> 5;
         const int e0 = per * lane, e1 = min(e0 + per, n);
         int mine = 0;
@@ -356,36 +361,75 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
                 incl += v;
         }
         int off = incl - mine;
-        const bool sane = incl <= M;                         // chgCount consistent with chgBase
+        const bool sane = __all_sync(FULL_MASK, incl <= M);  // chgCount consistent with chgBase
         ok = sane;
+        if (!HAS_PARENT) {
+            // first change of every branch takes its `from` type from the node: scatter it
+            uint8_t *firstFrom = reinterpret_cast<uint8_t *>(keys);
+            for (int i = lane * 16; i < M; i += 512)
+                *reinterpret_cast<uint4 *>(firstFrom + i) = make_uint4(~0u, ~0u, ~0u, ~0u);
+            __syncwarp();
+            if (sane && mine > 0) {
 #pragma unroll 1
-        for (int e = e0; e < e1; e++) {
-            const int c = sane ? (int)sK[e] : 0;
-            int type = sT[e];
-            desc[e] = (uint16_t)(((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | type << 5);
-            const int par = HAS_PARENT ? sP[e] : 0;
-            const bool isRoot = HAS_PARENT && par < 0;
-            double lastT = HAS_PARENT ? sH[e] : 0.0;
-#pragma unroll 1
-            for (int q = 0; q < c; q++) {
-                const int to = sCT[off + q];
-                desc[n + off + q] =
-                    (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
-                if (HAS_PARENT) {
-                    const double tq = sC[off + q];
-                    ok = ok && !(lastT > tq);                // MultiTypeTree.java:404-405
-                    lastT = tq;
+                for (int e = e0; e < e1; e++) {
+                    const int c = sK[e];
+                    if (c)
+                        firstFrom[off] = sT[e];
+                    off += c;
                 }
-                type = to;
             }
-            off += c;
-            if (HAS_PARENT && !isRoot) {
-                ok = ok && !(lastT > sH[par]);               // :401, :408-409
-                ok = ok && (type == (int)sT[par]);           // :421-422
+#pragma unroll 2
+            for (int e = lane; e < n; e += 32) {
+                const int type = sT[e];
+                desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
+                                                   : (KIND_COALESCE << 10 | type << 5 | type));
             }
+            __syncwarp();
+            if (sane) {
+#pragma unroll 1
+                for (int c = lane; c < M; c += 32) {
+                    const int f = firstFrom[c];
+                    const int from = (f != 0xff) ? f : (int)sCT[c - 1];
+                    desc[n + c] = (uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]);
+                }
+            } else {
+                for (int c = lane; c < M; c += 32)
+                    desc[n + c] = (uint16_t)(KIND_NONE << 10);
+            }
+        } else {
+            // node-centric walk with the validity chain of MultiTypeTree.java:396-429
+#pragma unroll 1
+            for (int e = e0; e < e1; e++) {
+                const int c = sane ? (int)sK[e] : 0;
+                int type = sT[e];
+                desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
+                                                   : (KIND_COALESCE << 10 | type << 5 | type));
+                const int par = sP[e];
+                const bool isRoot = par < 0;
+                double lastT = sH[e];
+#pragma unroll 1
+                for (int q = 0; q < c; q++) {
+                    const int to = sCT[off + q];
+                    // root-branch changes are ignored (StructuredCoalescentTreeDensity.java:161-162)
+                    desc[n + off + q] =
+                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
+                    const double tq = sC[off + q];
+                    ok = ok && !(lastT > tq);                // :404-405
+                    lastT = tq;
+                    type = to;
+                }
+                off += c;
+                if (!isRoot) {
+                    ok = ok && !(lastT > sH[par]);           // :401, :408-409
+                    ok = ok && (type == (int)sT[par]);       // :421-422
+                }
+            }
+            if (!sane)
+                for (int c = lane; c < M; c += 32)
+                    desc[n + c] = (uint16_t)(KIND_NONE << 10);
+            ok = __all_sync(FULL_MASK, ok);
         }
     }
-    ok = __all_sync(FULL_MASK, ok);
     okOut = ok;
     __syncwarp();
 
@@ -404,8 +448,8 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
     const double range = hi - lo;
     const double scale = (range > 0.0) ? (double)QMAX / range : 0.0;
 
-    // ---- phase B: order.  256 events at a time through the register network, sorted runs
-    //      land in keys[]; a second run is merged in shared memory.
+    // ---- phase B: order.  256 events at a time through the register network.  One run goes
+    //      straight to the order list; two runs are stored as keys and merged (merge path).
     int Epad = (E > 256) ? 512 : 256;
     asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
 #pragma unroll 1
@@ -423,59 +467,130 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
             key[k] = kk;
         }
         warp_sort256(key, lane);
-        uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
-        dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
-        dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
+        if (Epad == 256) {
+            // event indices, 0xffff for padding; 8 x u16 = one 16-byte store per lane
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & 511u);
+                const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & 511u);
+                w[k] = a | (b << 16);
+            }
+            *reinterpret_cast<uint4 *>(order + 8 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
+        } else {
+            uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
+            dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
+            dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
+        }
     }
     __syncwarp();
     if (EMAX > 256 && Epad == 512) {
-        // bitonic merge of the two ascending runs: reflected step, then half cleaners
-#pragma unroll 1
-        for (int stride = 256; stride >= 1; stride >>= 1) {
-#pragma unroll 1
-            for (int i = lane; i < 256; i += 32) {
-                const int a = 2 * i - (i & (stride - 1));
-                const int b = (stride == 256) ? (511 - a) : (a + stride);
-                const uint32_t ka = keys[a], kb = keys[b];
-                if (ka > kb) {
-                    keys[a] = kb;
-                    keys[b] = ka;
-                }
-            }
-            __syncwarp();
+        // merge path: lane produces outputs [16*lane, 16*lane+16) of the two ascending runs
+        const uint32_t *A = keys, *B = keys + 256;
+        const int diag = 16 * lane;
+        int a0 = max(0, diag - 256), a1 = min(diag, 256);
+        while (a0 < a1) {
+            const int mid = (a0 + a1) >> 1;
+            if (A[mid] <= B[diag - 1 - mid])
+                a0 = mid + 1;
+            else
+                a1 = mid;
         }
+        int i = a0, j = diag - a0;
+        uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < 256) ? B[j] : KEY_PAD;
+#pragma unroll 1
+        for (int q = 0; q < 16; q++) {
+            const bool takeA = ka <= kb;
+            const uint32_t out = takeA ? ka : kb;
+            order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & 511u);
+            if (takeA) {
+                i++;
+                ka = (i < 256) ? A[i] : KEY_PAD;
+            } else {
+                j++;
+                kb = (j < 256) ? B[j] : KEY_PAD;
+            }
+        }
+        __syncwarp();
     }
 
-    // ---- phase C: lane owns positions [per*lane, per*lane+per); local count deltas, and a
-    //      check that quantisation ties came out in exact time order (repaired if not)
+    // ---- phases C / D over the order list; lane owns positions [per*lane, per*lane+per)
     const int per = Epad >> 5;
     const int p0 = per * lane;
-    Counts<NW> local;
+    double acc;
     for (;;) {
+        // C: packed count deltas of my chunk, warp prefix sum -> counts before my chunk
+        Counts<NW> local;
 #pragma unroll
         for (int i = 0; i < NW; i++)
             local.w[i] = 0;
-        bool inv = false;
-        double prevT = -INFINITY;
-        if (lane > 0) {
-            const uint32_t kp = keys[p0 - 1];
-            if (kp != KEY_PAD)
-                prevT = ev_time((int)(kp & ((1u << IDX_BITS) - 1)));
-        }
 #pragma unroll 2
         for (int q = 0; q < per; q++) {
-            const uint32_t k = keys[p0 + q];
-            if (k == KEY_PAD)
+            const int idx = order[p0 + q];
+            if (idx == 0xffff)
                 break;
-            const int idx = (int)(k & ((1u << IDX_BITS) - 1));
-            const double x = ev_time(idx);
-            inv |= x < prevT;
-            prevT = x;
             cnt_apply<NW>(local, desc[idx]);
+        }
+        Counts<NW> base;
+#pragma unroll
+        for (int i = 0; i < NW; i++) {
+            unsigned long long incl = local.w[i];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long v = shfl_up_u64(incl, o);
+                if (lane >= o)
+                    incl += v;
+            }
+            base.w[i] = incl - local.w[i];
+        }
+        // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
+        double lambda = 0.0;
+#pragma unroll 1
+        for (int c = 0; c < d; c++) {
+            const double kd = (double)cnt_get<NW>(base, c);
+            lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+        }
+        // D: interval integration with a running lambda; also verifies the exact time order
+        double prevT = -INFINITY;
+        bool first = (lane == 0);                            // event 0 is skipped (:101)
+        if (lane > 0) {
+            const int ip = order[p0 - 1];
+            if (ip != 0xffff)
+                prevT = ev_time(ip);
+        }
+        bool inv = false;
+        acc = 0.0;
+#pragma unroll 2
+        for (int q = 0; q < per; q++) {
+            const int idx = order[p0 + q];
+            if (idx == 0xffff)
+                break;
+            const double x = ev_time(idx);
+            const uint32_t ds = desc[idx];
+            const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+            const double dt = x - prevT;
+            inv |= dt < 0.0;
+            if (!first && dt > 0.0)                          // StructuredCoalescentTreeDensity.java:108
+                acc -= dt * lambda;
+            prevT = x;
+            if (kind != KIND_SAMPLE) {                       // a lineage leaves deme `from`
+                if (!first)
+                    acc += tab->logM[from * d + to];         // log(1/N) or log(m)  (:127-137)
+                const double kd = (double)cnt_get<NW>(base, from);
+                lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
+                cnt_add<NW>(base, from, -1);
+            }
+            if (kind != KIND_COALESCE) {                     // a lineage enters a deme
+                const int a = (kind == KIND_MIGRATE) ? to : from;
+                const double kd = (double)cnt_get<NW>(base, a);
+                lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
+                cnt_add<NW>(base, a, 1);
+            }
+            first = false;
         }
         if (!__any_sync(FULL_MASK, inv))
             break;
-        // rare: odd-even transposition on exact times until sorted
+        // rare: quantisation ties out of exact order -> odd-even transposition on exact times
         bool swapped = true;
         while (swapped) {
             swapped = false;
@@ -483,11 +598,10 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
             for (int parity = 0; parity < 2; parity++) {
 #pragma unroll 1
                 for (int a = parity + 2 * lane; a + 1 < Epad; a += 64) {
-                    const uint32_t ka = keys[a], kb = keys[a + 1];
-                    if (ka != KEY_PAD && kb != KEY_PAD &&
-                        ev_time((int)(ka & 511)) > ev_time((int)(kb & 511))) {
-                        keys[a] = kb;
-                        keys[a + 1] = ka;
+                    const int ia = order[a], ib = order[a + 1];
+                    if (ia != 0xffff && ib != 0xffff && ev_time(ia) > ev_time(ib)) {
+                        order[a] = (uint16_t)ib;
+                        order[a + 1] = (uint16_t)ia;
                         swapped = true;
                     }
                 }
@@ -495,65 +609,6 @@ __device__ __noinline__ double process_tree(const WarpStage<HAS_PARENT, EMAX> *s
             }
             swapped = __any_sync(FULL_MASK, swapped);
         }
-    }
-
-    // ---- phase D: lineage counts by prefix sum, interval integration with a running lambda
-    Counts<NW> base;
-#pragma unroll
-    for (int i = 0; i < NW; i++) {
-        unsigned long long incl = local.w[i];
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const unsigned long long v = shfl_up_u64(incl, o);
-            if (lane >= o)
-                incl += v;
-        }
-        base.w[i] = incl - local.w[i];
-    }
-    // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
-    double lambda = 0.0;
-#pragma unroll 1
-    for (int c = 0; c < d; c++) {
-        const double kd = (double)cnt_get<NW>(base, c);
-        lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
-    }
-    double prevT = 0.0;
-    bool first = (lane == 0);                                // event 0 is skipped (:101)
-    if (lane > 0) {
-        const uint32_t kp = keys[p0 - 1];
-        if (kp != KEY_PAD)
-            prevT = ev_time((int)(kp & 511));
-    }
-    double acc = 0.0;
-#pragma unroll 1
-    for (int q = 0; q < per; q++) {
-        const uint32_t k = keys[p0 + q];
-        if (k == KEY_PAD)
-            break;
-        const int idx = (int)(k & 511);
-        const double x = ev_time(idx);
-        const uint32_t ds = desc[idx];
-        const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
-        if (!first) {
-            const double dt = x - prevT;
-            if (dt > 0.0)                                    // StructuredCoalescentTreeDensity.java:108
-                acc -= dt * lambda;
-        }
-        prevT = x;
-        if (kind != KIND_SAMPLE) {                           // a lineage leaves deme `from`
-            if (!first)
-                acc += (kind == KIND_COALESCE) ? tab->logInvN[from] : tab->logM[from * d + to];
-            const double kd = (double)cnt_get<NW>(base, from);
-            lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
-            cnt_add<NW>(base, from, -1);
-        }
-        if (kind != KIND_COALESCE) {                         // a lineage enters a deme
-            const int a = (kind == KIND_MIGRATE) ? to : from;
-            const double kd = (double)cnt_get<NW>(base, a);
-            lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
-            cnt_add<NW>(base, a, 1);
-        }
-        first = false;
     }
     return warp_sum_down(acc);
 }

@@ -437,6 +437,90 @@ def bench_peel(args):
         "parity_max_rel_err_vs_oracle": rel}))
 
 
+def bench_peel_sharded(args):
+    """cfg4 shape: 8-deme 5000-tip trees, site patterns sharded across ranks (125k patterns per
+    GPU = 1M over 8 GPUs), per-rank partial logL combined with one NCCL all-reduce."""
+    import torch
+    import torch.distributed as dist
+    import multitypetree_b200 as mtt
+    from multitypetree_b200 import _lib
+    from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, TreeLikelihood,
+                                               simulate_alignment)
+    world, rank, local = dist_setup(args.gpus)
+    n, d = args.tips or 5000, 8
+    sites = args.sites or 125000
+    B = args.batch if args.batch != (1 << 20) else 8
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=4000, nThreads=max(1, (os.cpu_count() or 1) // world))
+    nN = 2 * n - 1
+    par, hgt = tb.parent.reshape(B, nN), tb.height.reshape(B, nN)
+    f = np.array([.25] * 4)
+    clock = 0.2 / float(hgt[0].max())
+    # this rank's shard of the alignment: its own sites, evolved on the same reference tree
+    al = Alignment(states=simulate_alignment(par[0], hgt[0], sites, 2.0, f, clock, seed=4000 + rank),
+                   compress=False)
+    ctx = mtt.Context(local)
+    stream = torch.cuda.current_stream()
+    side = torch.cuda.Stream()
+    torch.cuda.set_stream(side)
+    ctx.set_stream(side.cuda_stream)
+    L = _lib.lib()
+    tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f), mutationRate=clock), ctx=ctx)
+    dpar, dhgt = to_dev(par), to_dev(hgt)
+    out = torch.zeros(B, dtype=torch.float64, device="cuda")
+
+    def step():
+        ctx.check(L.mtt_peel_logl_batch_dev(tl.handle, B, dpar.data_ptr(), dhgt.data_ptr(),
+                                            out.data_ptr()))
+        if world > 1:
+            dist.all_reduce(out, op=dist.ReduceOp.SUM)      # 8 B per tree over NVLink
+
+    for _ in range(args.warmup):
+        step()
+    barrier(world)
+    l0 = ctx.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clk:
+        e0.record(side)
+        for _ in range(args.steps):
+            step()
+        e1.record(side)
+        barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    total = out.cpu().numpy().copy()
+    # parity: this rank's partial against the oracle on a few patterns-worth of work
+    from oracle import oracle as orc
+    k = 1
+    sub = Alignment(states=al.patterns[:, :2000], compress=False)
+    tl2 = TreeLikelihood(data=sub, siteModel=SiteModel(HKY(2.0, f), mutationRate=clock), ctx=ctx)
+    got = tl2.calculateLogPBatch(par[:k], hgt[:k])
+    want = orc.tree_likelihood_batch(sub.patterns, sub.patternWeight, par[:k], hgt[:k], [clock],
+                                     [1.0], f, 2.0)
+    rel = float(np.max(np.abs(got - want) / np.abs(want)))
+    assert rel < 1e-9, rel
+    if rank != 0:
+        return
+    P, S, C = sites, 4, 1
+    alg = 8.0 * S * C * P * (2 * n - 3) + 4.0 * n * P + 8.0 * P + 8.0 * S * S * C * (2 * n - 2)
+    flop = (n - 1) * P * C * (4 * S * S + S)
+    hbm, src = peaks()
+    print(json.dumps({
+        "metric": "cfg4 pattern-sharded tree-likelihood evaluations/s (whole alignment)",
+        "value": B / (ms * 1e-3), "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "cfg4: 8-deme %d-tip trees, %d site patterns per GPU x %d GPUs, "
+                               "NCCL all-reduce of the per-shard logL" % (n, sites, world),
+                   "trees_per_step": B},
+        "roofline": {"bound": "hbm", "achieved": alg * B / (ms * 1e-3) / 1e9, "peak": hbm,
+                     "unit": "GB/s", "frac": alg * B / (ms * 1e-3) / 1e9 / hbm, "traffic": None,
+                     "peak_source": src, "kernel": "k2_peel",
+                     "note": "per-GPU algorithmic bytes of the materialised-partials model; "
+                             "partials stay on chip", "fp64_tflops_per_gpu": flop * B / (ms * 1e-3) / 1e12},
+        "logL_first_tree": float(total[0]), "gpu_launches": int(ctx.launch_count() - l0),
+        "clocks": clk.summary(), "parity_max_rel_err_vs_oracle": rel}))
+
+
 def bench_retype(args):
     """cfg5: NodeRetype-style uniformization sweep, chains x 10-deme models."""
     import multitypetree_b200 as mtt
@@ -488,7 +572,9 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="density", choices=["density", "peel", "retype"])
+    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_sharded", "retype"])
+    ap.add_argument("--tips", type=int, default=0)
+    ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--batch", type=int, default=1 << 20, help="trees per GPU per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -496,6 +582,8 @@ def main():
         return bench_reference(args)
     if args.workload == "peel":
         return bench_peel(args)
+    if args.workload == "peel_sharded":
+        return bench_peel_sharded(args)
     if args.workload == "retype":
         return bench_retype(args)
     return bench_density(args)

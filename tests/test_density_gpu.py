@@ -186,3 +186,66 @@ def test_api_errors(ctx):
     with pytest.raises(mtt.MttError):
         mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx, with_parent=False)
     assert mtt.sc_logp_batch(tb.slice(0, 0), m, N, ctx=ctx).shape == (0,)   # empty batch
+
+
+def _pad_changes(tree, target_M):
+    """Add back-and-forth migration pairs on the longest branches until the tree has exactly
+    target_M changes (parity permitting); keeps the tree valid."""
+    t = tree.copy()
+    d_other = lambda c: 1 - c if c < 2 else 0
+    M = t.getTotalNumberOfChanges()
+    order = np.argsort([-(t.height[t.parent[i]] - t.height[i]) if t.parent[i] >= 0 else 1
+                        for i in range(t.getNodeCount())])
+    k = 0
+    while M + 2 <= target_M:
+        b = int(order[k % 20])
+        k += 1
+        lo = t.changeTimes[b][-1] if t.changeTimes[b] else float(t.height[b])
+        hi = float(t.height[t.parent[b]])
+        cur = t.getFinalType(b)
+        t.addChange(b, d_other(cur), lo + (hi - lo) * 0.3)
+        t.addChange(b, cur, lo + (hi - lo) * 0.6)
+        M += 2
+    return t
+
+
+@pytest.mark.parametrize("n,targets", [(128, (255, 256, 257, 258)), (250, (510, 511, 512, 513, 514)),
+                                       (64, (127, 128, 129))])
+def test_event_count_boundaries(ctx, n, targets):
+    """E = nodes + changes right at the 256 / 512 limits of the warp path (one run, two runs
+    + merge, hand-over to the CTA kernel)."""
+    m, N = mtt.synthetic_model(2)
+    pool = mtt.simulate_trees(64, n, 2, m, N, seed=600 + n)
+    trees, want_E = [], []
+    for E in targets:
+        for parity in (0, 1):
+            for b in range(pool.B):
+                t = pool.tree(b)
+                M0 = t.getTotalNumberOfChanges()
+                need = E - (2 * n - 1)
+                if need >= M0 and (need - M0) % 2 == 0:
+                    trees.append(_pad_changes(t, need))
+                    want_E.append(E)
+                    break
+            break
+    assert trees
+    tb = mtt.TreeBatch.from_trees(trees)
+    assert list(tb.n_events()) == want_E
+    _check(tb, m, N, ctx)
+    _check(tb, m, N, ctx, checkValidity=True)
+
+
+def test_ties_and_zero_length_branches(ctx):
+    """Equal event times (contemporaneous tips, zero-length branches, a change exactly at a
+    node height): interval terms vanish (delta_t > 0 is false, :108) but every event term and
+    count change must still be applied."""
+    nw = ("((A[&s=0]:1.0,B[&s=0]:1.0)[&s=0]:0.0,((C[&s=1]:0.5)[&s=0]:0.5,D[&s=0]:1.0)[&s=0]:0.0)"
+          "[&s=0]:0.0;")
+    t = mtt.MultiTypeTreeFromNewick(nw, "s")
+    m = np.array([[0, 0.7], [0.4, 0]])
+    N = np.array([3.0, 2.0])
+    tb = mtt.TreeBatch.from_trees([t] * 5)
+    got = _check(tb, m, N, ctx, checkValidity=True)
+    assert np.all(got == got[0]) and np.isfinite(got[0])
+    want = orc.sc_logp_batch(tb, m, N, variant=orc.SUFFSTAT)
+    np.testing.assert_allclose(got, want, rtol=1e-12)

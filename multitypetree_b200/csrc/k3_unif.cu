@@ -27,12 +27,32 @@ constexpr int U_TCAP = 512;         // virtual events kept in shared memory per 
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+// one copy each of the long libm / division sequences (instruction-cache footprint)
+__device__ __noinline__ double log_ni(double x) { return log(x); }
+__device__ __noinline__ double exp_ni(double x) { return exp(x); }
+__device__ __noinline__ double div_ni(double a, double b) { return __ddiv_rn(a, b); }
 
-// C = A * B (d x d, row-major, shared memory); C must not alias A or B
-__device__ __forceinline__ void mm(int d, const double *A, const double *B, double *C, int lane)
+// (row << 8 | col) of every element index of a d x d matrix: filled once per warp so that the
+// hot loops need no integer division
+__device__ __forceinline__ void fill_rc(uint16_t *rc, int d, int lane)
 {
+    #pragma unroll 1
+    for (int e = lane; e < d * d; e += 32)
+        rc[e] = (uint16_t)(((e / d) << 8) | (e % d));
+    __syncwarp();
+}
+#define RC_ROW(v) ((int)(v) >> 8)
+#define RC_COL(v) ((int)(v) & 255)
+
+// C = A * B (d x d, row-major, shared memory); C must not alias A or B.  Deliberately NOT
+// inlined: expm calls it ~10 times and the kernels must stay instruction-cache resident
+// (the fully inlined expm was 4400 SASS instructions and stalled on instruction fetch).
+__device__ __noinline__ void mm(int d, const double *A, const double *B, double *C,
+                                const uint16_t *rc, int lane)
+{
+    #pragma unroll 1
     for (int e = lane; e < d * d; e += 32) {
-        const int i = e / d, j = e - i * d;
+        const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
         double s = 0.0;
         for (int k = 0; k < d; k++)
             s = add_rn(s, mul_rn(A[i * d + k], B[k * d + j]));
@@ -66,7 +86,8 @@ __global__ void k3_update_matrices(int nModels, int d, const double *m, int sym,
     }
     const double muV = warp_max(diagNeg);
     __syncwarp();
-    const double rm = __ddiv_rn(1.0, muV);
+    const double rm = div_ni(1.0, muV);
+    #pragma unroll 1
     for (int e = lane; e < d * d; e += 32) {
         const int i = e / d, j = e - i * d;
         r[e] = add_rn(mul_rn(q[e], rm), (i == j) ? 1.0 : 0.0);   // Q.mul(1.0/mu).add(eye) :183
@@ -86,24 +107,31 @@ __global__ void k3_rpow_extend(int nModels, int d, const double *R, double *pow,
     if (model >= nModels)
         return;
     const int dd = d * d;
+    __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
+    uint16_t *rc = rcAll[threadIdx.x >> 5];
+    fill_rc(rc, d, threadIdx.x & 31);
     double *sR = sm + (size_t)warp * 3 * dd, *sPrev = sR + dd, *sNew = sPrev + dd;
     double *tab = pow + (size_t)model * powCap * dd;
     int size = meta[2 * model], steady = meta[2 * model + 1];
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
         sR[e] = R[(size_t)model * dd + e];
     if (size == 0) {                                        // RpowN = [I]  (:193)
+        #pragma unroll 1
         for (int e = lane; e < dd; e += 32)
-            tab[e] = (e / d == e % d) ? 1.0 : 0.0;
+            tab[e] = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
         size = 1;
     }
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
         sPrev[e] = tab[(size_t)(size - 1) * dd + e];
     __syncwarp();
     if (target >= powCap)
         target = powCap - 1;
     for (int i = size; i <= target && !steady; i++) {       // :428-448
-        mm(d, sPrev, sR, sNew, lane);
+        mm(d, sPrev, sR, sNew, rc, lane);
         bool anyNaN = false, anyPos = false;
+        #pragma unroll 1
         for (int e = lane; e < dd; e += 32) {
             const double v = sNew[e];
             tab[(size_t)i * dd + e] = v;
@@ -145,7 +173,7 @@ __device__ __forceinline__ double pade_poly(double eye, double a2, double a4, do
 }
 
 // LU with partial pivoting, F = D^-1 N left in N (unblocked right-looking elimination)
-__device__ __forceinline__ void lu_solve(int d, double *D, double *N, int lane)
+__device__ __noinline__ void lu_solve(int d, double *D, double *N, const uint16_t *rc, int lane)
 {
     for (int k = 0; k < d; k++) {
         int p = k;
@@ -159,6 +187,7 @@ __device__ __forceinline__ void lu_solve(int d, double *D, double *N, int lane)
         }
         __syncwarp();
         if (p != k) {
+            #pragma unroll 1
             for (int j = lane; j < d; j += 32) {
                 double t = D[k * d + j]; D[k * d + j] = D[p * d + j]; D[p * d + j] = t;
                 t = N[k * d + j]; N[k * d + j] = N[p * d + j]; N[p * d + j] = t;
@@ -166,12 +195,14 @@ __device__ __forceinline__ void lu_solve(int d, double *D, double *N, int lane)
             __syncwarp();
         }
         const double pivot = D[k * d + k];
+        #pragma unroll 1
         for (int i = k + 1 + lane; i < d; i += 32)
-            D[i * d + k] = __ddiv_rn(D[i * d + k], pivot);
+            D[i * d + k] = div_ni(D[i * d + k], pivot);
         __syncwarp();
         const int rows = d - k - 1;
+        #pragma unroll 1
         for (int e = lane; e < rows * d; e += 32) {
-            const int i = k + 1 + e / d, j = e % d;
+            const int i = k + 1 + RC_ROW(rc[e]), j = RC_COL(rc[e]);
             const double l = D[i * d + k];
             if (j > k)
                 D[i * d + j] = sub_rn(D[i * d + j], mul_rn(l, D[k * d + j]));
@@ -182,11 +213,13 @@ __device__ __forceinline__ void lu_solve(int d, double *D, double *N, int lane)
     for (int k = d - 1; k >= 0; k--) {
         const double pivot = D[k * d + k];
         __syncwarp();
+        #pragma unroll 1
         for (int j = lane; j < d; j += 32)
-            N[k * d + j] = __ddiv_rn(N[k * d + j], pivot);
+            N[k * d + j] = div_ni(N[k * d + j], pivot);
         __syncwarp();
+        #pragma unroll 1
         for (int e = lane; e < k * d; e += 32) {
-            const int i = e / d, j = e % d;
+            const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
             N[i * d + j] = sub_rn(N[i * d + j], mul_rn(D[i * d + k], N[k * d + j]));
         }
         __syncwarp();
@@ -195,13 +228,14 @@ __device__ __forceinline__ void lu_solve(int d, double *D, double *N, int lane)
 
 // expm(Q * L) with Q in global/shared memory; `buf` = 8 d*d shared-memory matrices of this
 // warp.  Returns a pointer (inside buf) to the result.
-__device__ __forceinline__ const double *expm_QL(int d, const double *Q, double L, double *buf,
-                                                 int lane)
+__device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, double *buf,
+                                              const uint16_t *rc, int lane)
 {
     const int dd = d * d;
     double *As = buf, *A2 = buf + dd, *A4 = buf + 2 * dd, *A6 = buf + 3 * dd, *T = buf + 4 * dd,
            *U = buf + 5 * dd, *V = buf + 6 * dd, *W = buf + 7 * dd;
     double nm = 0.0;
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
         const double a = mul_rn(Q[e], L);                   // Q.mul(L)
         As[e] = a;
@@ -210,52 +244,58 @@ __device__ __forceinline__ const double *expm_QL(int d, const double *Q, double 
     nm = warp_max(nm);
     int j = 0;
     if (nm > 0.0) {
-        const double f = floor(log(nm) / log(2.0));
+        const double f = floor(log_ni(nm) / log_ni(2.0));
         if (f > -1.0)
             j = 1 + (int)f;
     }
     const double scale = scalbn(1.0, j);
     __syncwarp();
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
-        As[e] = __ddiv_rn(As[e], scale);
+        As[e] = div_ni(As[e], scale);
     __syncwarp();
-    mm(d, As, As, A2, lane);
-    mm(d, A2, A2, A4, lane);
-    mm(d, A4, A2, A6, lane);
+    mm(d, As, As, A2, rc, lane);
+    mm(d, A2, A2, A4, rc, lane);
+    mm(d, A4, A2, A6, rc, lane);
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
-        T[e] = pade_poly((e / d == e % d) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 6);
+        T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 6);
     __syncwarp();
-    mm(d, T, A6, U, lane);
+    mm(d, T, A6, U, rc, lane);
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
-        const double eye = (e / d == e % d) ? 1.0 : 0.0;
+        const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
         U[e] = add_rn(add_rn(add_rn(mul_rn(eye, PADE[0]), mul_rn(A2[e], PADE[2])),
                              mul_rn(A4[e], PADE[4])),
                       U[e]);
     }
     __syncwarp();
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
-        T[e] = pade_poly((e / d == e % d) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 7);
+        T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 7);
     __syncwarp();
-    mm(d, T, A6, V, lane);
+    mm(d, T, A6, V, rc, lane);
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
-        const double eye = (e / d == e % d) ? 1.0 : 0.0;
+        const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
         V[e] = add_rn(add_rn(add_rn(mul_rn(eye, PADE[1]), mul_rn(A2[e], PADE[3])),
                              mul_rn(A4[e], PADE[5])),
                       V[e]);
     }
     __syncwarp();
-    mm(d, As, V, W, lane);                                  // AV
+    mm(d, As, V, W, rc, lane);                                  // AV
     double *Nn = A2, *D = A4;                               // A2, A4 are dead from here
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
         const double u = U[e], av = W[e];
         Nn[e] = add_rn(u, av);
         D[e] = sub_rn(u, av);
     }
     __syncwarp();
-    lu_solve(d, D, Nn, lane);
+    lu_solve(d, D, Nn, rc, lane);
     double *F = Nn, *G = T;
     for (int k = 0; k < j; k++) {                           // F = F * F, j times
-        mm(d, F, F, G, lane);
+        mm(d, F, F, G, rc, lane);
         double *t = F;
         F = G;
         G = t;
@@ -272,8 +312,12 @@ __global__ void k3_expm_batch(long long n, int d, const double *Q, const int *mo
     if (item >= n)
         return;
     const int dd = d * d;
+    __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
+    uint16_t *rc = rcAll[threadIdx.x >> 5];
+    fill_rc(rc, d, threadIdx.x & 31);
     double *buf = sm + (size_t)warp * 8 * dd;
-    const double *F = expm_QL(d, Q + (size_t)model[item] * dd, L[item], buf, lane);
+    const double *F = expm_QL(d, Q + (size_t)model[item] * dd, L[item], buf, rc, lane);
+    #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
         out[item * dd + e] = F[e];
 }
@@ -291,6 +335,9 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
     if (br >= n)
         return;
     const int dd = d * d;
+    __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
+    uint16_t *rc = rcAll[threadIdx.x >> 5];
+    fill_rc(rc, d, threadIdx.x & 31);
     double *buf = sm + (size_t)warp * 8 * dd;
     const double *Q = Qall + (size_t)model[br] * dd;
     const double t0 = tBottom[br], t1 = tTop[br];
@@ -301,19 +348,19 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
         const double thisTime = chgTime[k];
         const int thisCol = chgType[k];
         lp = add_rn(lp, add_rn(mul_rn(sub_rn(thisTime, lastTime), Q[lastCol * d + lastCol]),
-                               log(Q[lastCol * d + thisCol])));
+                               log_ni(Q[lastCol * d + thisCol])));
         lastTime = thisTime;
         lastCol = thisCol;
     }
     lp = add_rn(lp, mul_rn(sub_rn(t1, lastTime), Q[lastCol * d + lastCol]));   // :259
-    const double *E = expm_QL(d, Q, sub_rn(t1, t0), buf, lane);          // :263-264
+    const double *E = expm_QL(d, Q, sub_rn(t1, t0), buf, rc, lane);          // :263-264
     const double Pba = E[a * d + b];
     if (lane == 0) {
         if (Pba > 1.0 || Pba < 0.0) {                                    // :267-270
             logProb[br] = -INFINITY;
             status[br] = MTT_ST_PBA_RUBBISH;
         } else {
-            logProb[br] = sub_rn(lp, log(Pba));                          // :272
+            logProb[br] = sub_rn(lp, log_ni(Pba));                          // :272
             status[br] = MTT_ST_OK;
         }
     }
@@ -372,6 +419,9 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
     if (job >= p.nJobs)
         return;
     const int d = p.d, dd = d * d;
+    __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
+    uint16_t *rc = rcAll[threadIdx.x >> 5];
+    fill_rc(rc, d, threadIdx.x & 31);
     const size_t perWarp = (size_t)8 * dd + U_TCAP + U_TCAP / 8;
     double *buf = sm + (size_t)warp * perWarp;
     double *sTimes = buf + 8 * dd;
@@ -401,7 +451,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
         const int a = p.typeBottom[br], b = p.typeTop[br];
         const double L = sub_rn(t1, t0);                                 // :124
         const double muL = mul_rn(p.mu[mdl], L);                         // :130
-        const double *E = expm_QL(d, Q, L, buf, lane);                   // :132-134
+        const double *E = expm_QL(d, Q, L, buf, rc, lane);                   // :132-134
         const double Pba = E[a * d + b];
         __syncwarp();
 
@@ -422,8 +472,8 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
             } else {
                 const double uu = u[pos++];                              // :79
                 double Plow = 0.0;
-                double acc = sub_rn(-muL, log(Pba));                     // :81
-                const double log_muL = log(muL);                         // :82
+                double acc = sub_rn(-muL, log_ni(Pba));                     // :81
+                const double log_muL = log_ni(muL);                         // :82
                 int n = 0;
                 while (true) {
                     if (n >= size && !steady) {
@@ -431,13 +481,13 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
                         break;
                     }
                     const double Rn = tab[(size_t)min(n, size - 1) * dd + a * d + b];
-                    Plow = add_rn(Plow, exp(add_rn(log(Rn), acc)));      // :86
+                    Plow = add_rn(Plow, exp_ni(add_rn(log_ni(Rn), acc)));      // :86
                     if (Plow > uu) {                                     // :88-89
                         nVirt = n;
                         break;
                     }
                     n += 1;
-                    acc = add_rn(acc, sub_rn(log_muL, log((double)n)));  // :92
+                    acc = add_rn(acc, sub_rn(log_muL, log_ni((double)n)));  // :92
                     if (!(steadyN < 0 || n < steadyN)) {                 // :94
                         st = MTT_ST_NEEDS_POISSON_TAIL;                  // :96-102 -> host
                         nVirt = n;                                       // thresh
@@ -520,13 +570,13 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
                     }
                     nChg++;
                     lp = add_rn(lp, add_rn(mul_rn(Q[prevType * d + prevType], sub_rn(ti, prevTime)),
-                                           log(Q[prevType * d + ty])));
+                                           log_ni(Q[prevType * d + ty])));
                     prevType = ty;
                     prevTime = ti;
                 }
             }
             lp = add_rn(lp, mul_rn(Q[prevType * d + prevType], sub_rn(t1, prevTime)));
-            lp = sub_rn(lp, log(Pba));
+            lp = sub_rn(lp, log_ni(Pba));
         }
         __syncwarp();
         if (lane == 0) {

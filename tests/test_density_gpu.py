@@ -215,7 +215,7 @@ def test_event_count_boundaries(ctx, n, targets):
     """E = nodes + changes right at the 256 / 512 limits of the warp path (one run, two runs
     + merge, hand-over to the CTA kernel)."""
     m, N = mtt.synthetic_model(2)
-    pool = mtt.simulate_trees(64, n, 2, m, N, seed=600 + n)
+    pool = mtt.simulate_trees(64, n, 2, m * 0.01, N, seed=600 + n)      # few migrations
     trees, want_E = [], []
     for E in targets:
         for parity in (0, 1):

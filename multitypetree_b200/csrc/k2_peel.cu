@@ -56,7 +56,7 @@ struct mtt_peel {
 namespace {
 
 constexpr int TP = 256;                 // pattern padding granule (largest tile: 128 threads x 2)
-constexpr int PREP_THREADS = 128;
+constexpr int PREP_THREADS = 256;
 constexpr int MAX_SLOTS = 24;
 
 struct PeelOp {
@@ -102,7 +102,16 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 }
 
 // ---- k2_prepare ------------------------------------------------------------------------
-// shared: int left[N], right[N], order[N], stack[N]; uint8 need[N]      (N = 2n-1)
+// One CTA per tree; every step is parallel over nodes (level-synchronous sweeps; the number of
+// rounds is the depth of the tree):
+//   bottom-up  isize(v) = internal nodes in the subtree, need(v) = Sethi-Ullman label + which
+//              child is evaluated first (the one needing more live partial vectors)
+//   top-down   istart(v) = index of the first op of the subtree, pd(v) = parked vectors live
+//              while the subtree is evaluated
+//   emission   op index of v = istart(v) + isize(v) - 1 (post-order: first subtree, second
+//              subtree, node); a first child whose sibling is internal parks its result in
+//              slot pd(parent); matrices of both children written in op order.
+// shared: int left[N], right[N]; u16 isize[N], istart[N]; u8 need[N], pd[N], state[N]
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
@@ -110,9 +119,10 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
 {
     extern __shared__ int smi[];
     const int N = 2 * n - 1, nOps = n - 1;
-    int *left = smi, *right = smi + N, *order = smi + 2 * N, *stack = smi + 3 * N;
-    uint8_t *need = reinterpret_cast<uint8_t *>(smi + 4 * N);
-    __shared__ int sRoot, sBad, sMaxSlots;
+    int *left = smi, *right = smi + N;
+    uint16_t *isize = reinterpret_cast<uint16_t *>(smi + 2 * N), *istart = isize + N;
+    uint8_t *need = reinterpret_cast<uint8_t *>(istart + N), *pd = need + N, *state = pd + N;
+    __shared__ int sRoot, sBad, sMaxSlots, sProgress;
 
     const int b = blockIdx.x, tid = threadIdx.x;
     const int *parent = parentAll + (size_t)b * N;
@@ -127,6 +137,9 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
     for (int i = tid; i < N; i += PREP_THREADS) {
         left[i] = 0x7fffffff;
         right[i] = -1;
+        isize[i] = 0;
+        need[i] = 0;
+        state[i] = (i < n) ? 1 : 0;        // bottom-up: tips are done
     }
     __syncthreads();
     for (int i = tid; i < N; i += PREP_THREADS) {
@@ -150,109 +163,128 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
             info[b] = -1;
         return;
     }
+    const int root = sRoot;
 
-    if (tid == 0) {
-        const int root = sRoot;
-        // pass 1: any pre-order (parents before children)
-        int sp = 0, cnt = 0;
-        stack[sp++] = root;
-        while (sp > 0 && cnt < N) {
-            const int v = stack[--sp];
-            order[cnt++] = v;
-            if (v >= n) {
-                stack[sp++] = left[v];
-                stack[sp++] = right[v];
-            }
+    // ---- bottom-up sweep
+    for (int round = 0; round < N; round++) {
+        __syncthreads();
+        if (tid == 0)
+            sProgress = 0;
+        __syncthreads();
+        if (state[root])
+            break;
+        bool progressed = false;
+        for (int v = n + tid; v < N; v += PREP_THREADS) {
+            if (state[v])
+                continue;
+            const int l = left[v], r = right[v];
+            if (state[l] != 1 || state[r] != 1)
+                continue;
+            const int a = need[l] & 0x7f, c = need[r] & 0x7f;
+            const int holdL = l >= n, holdR = r >= n;
+            const int lf = max(max(a, holdL + c), 1);   // left first
+            const int rf = max(max(c, holdR + a), 1);   // right first
+            need[v] = (uint8_t)((rf < lf) ? (rf | 0x80) : lf);
+            isize[v] = (uint16_t)(isize[l] + isize[r] + 1);
+            state[v] = 2;                  // done, visible to parents from the next round on
+            progressed = true;
         }
-        if (cnt != N) {
-            sBad = 1;                      // not a single connected binary tree
-        } else {
-            // pass 2: Sethi-Ullman need (live partial vectors), children before parents
-            for (int i = N - 1; i >= 0; i--) {
-                const int v = order[i];
-                if (v < n) {
-                    need[v] = 0;
-                    continue;
-                }
-                const int a = need[left[v]] & 0x7f, c = need[right[v]] & 0x7f;
-                const int holdL = left[v] >= n, holdR = right[v] >= n;
-                const int lf = max(max(a, holdL + c), 1);   // left first
-                const int rf = max(max(c, holdR + a), 1);   // right first
-                need[v] = (uint8_t)((rf < lf) ? (rf | 0x80) : lf);
-            }
-            // pass 3a: pre-order of internal nodes, second-evaluated child popped first;
-            // its reverse is the post-order "first child, second child, node"
-            sp = 0;
-            cnt = 0;
-            stack[sp++] = root;
-            while (sp > 0) {
-                const int v = stack[--sp];
-                if (v < n)
-                    continue;
-                order[cnt++] = v;
-                const bool rightFirst = need[v] & 0x80;
-                stack[sp++] = rightFirst ? right[v] : left[v];    // first: popped last
-                stack[sp++] = rightFirst ? left[v] : right[v];    // second: popped first
-            }
-            // pass 3b, in execution order.  An internal second child is always the previous op;
-            // an internal first child is the previous op when the second child is a tip.  Only
-            // a first child whose sibling is internal has to park its result in a slot.
-            unsigned long long freeMask = ~0ull;
-            int maxSlots = 0;
-            for (int k = 0; k < nOps; k++) {
-                const int v = order[nOps - 1 - k];
-                const bool rightFirst = need[v] & 0x80;
-                const int c1 = rightFirst ? right[v] : left[v];
-                const int c2 = rightFirst ? left[v] : right[v];
-                PeelOp op;
-                op.flags = (c2 >= n) ? OP_C2_PREV : ((c1 >= n) ? OP_C1_PREV : 0);
-                op.c1 = (c1 < n) ? -(c1 + 1) : ((op.flags & OP_C1_PREV) ? 0 : (need[c1] & 0x7f));
-                op.c2 = (c2 < n) ? -(c2 + 1) : 0;
-                if (c1 >= n && !(op.flags & OP_C1_PREV))
-                    freeMask |= 1ull << (need[c1] & 0x7f);
-                op.dst = 0;
-                if (v != root) {
-                    const int pp = parent[v];
-                    const bool pRightFirst = need[pp] & 0x80;
-                    const int pFirst = pRightFirst ? right[pp] : left[pp];
-                    const int pSecond = pRightFirst ? left[pp] : right[pp];
-                    if (pFirst == v && pSecond >= n) {
-                        const int dst = __ffsll((long long)freeMask) - 1;
-                        freeMask &= ~(1ull << dst);
-                        need[v] = (uint8_t)((need[v] & 0x80) | dst);
-                        maxSlots = max(maxSlots, dst + 1);
-                        op.dst = dst;
-                        op.flags |= OP_STORE;
-                    }
-                }
-                ops[k] = op;
-                stack[k] = v;              // op -> node, for the matrix pass below
-            }
-            sMaxSlots = maxSlots;
-        }
+        if (progressed)
+            sProgress = 1;
+        __syncthreads();
+        for (int v = n + tid; v < N; v += PREP_THREADS)
+            if (state[v] == 2)
+                state[v] = 1;
+        if (!sProgress)
+            break;                         // a cycle / disconnected piece: never completes
     }
     __syncthreads();
-    if (sBad) {
+    if (!state[root] || isize[root] != nOps) {
         if (tid == 0)
-            info[b] = -1;
+            info[b] = -1;                  // not a single connected binary tree
         return;
     }
-    if (tid == 0) {
-        info[b] = sMaxSlots;
-        atomicMax(maxSlotsAll, sMaxSlots);
-    }
 
-    // transition matrices of both children of every op, in op order:
+    // ---- top-down sweep (state: 1 = not yet placed, 3 = placed)
+    if (tid == 0) {
+        istart[root] = 0;
+        pd[root] = 0;
+        state[root] = 3;
+    }
+    for (int round = 0; round < N; round++) {
+        __syncthreads();
+        if (tid == 0)
+            sProgress = 0;
+        __syncthreads();
+        bool progressed = false;
+        for (int v = tid; v < N; v += PREP_THREADS) {
+            if (state[v] == 3 || v == root)
+                continue;
+            const int pp = parent[v];
+            if (state[pp] != 3)
+                continue;
+            const bool pRightFirst = need[pp] & 0x80;
+            const int first = pRightFirst ? right[pp] : left[pp];
+            const int second = pRightFirst ? left[pp] : right[pp];
+            if (v == first) {
+                istart[v] = istart[pp];
+                pd[v] = pd[pp];
+            } else {
+                istart[v] = (uint16_t)(istart[pp] + isize[first]);
+                pd[v] = (uint8_t)(pd[pp] + ((first >= n && second >= n) ? 1 : 0));
+            }
+            state[v] = 4;
+            progressed = true;
+        }
+        if (progressed)
+            sProgress = 1;
+        __syncthreads();
+        for (int v = tid; v < N; v += PREP_THREADS)
+            if (state[v] == 4)
+                state[v] = 3;
+        if (!sProgress)
+            break;
+    }
+    __syncthreads();
+
+    // ---- emission: ops and, in op order, the transition matrices of both children
     // mats[op][child j][category c][16]
     const double *catRates = site, *freqs = site + 2 * C;
     const double *height = heightAll ? heightAll + (size_t)b * N : nullptr;
     const double *matsIn = matsInAll ? matsInAll + (size_t)b * N * C * 16 : nullptr;
+    int myMax = 0;
+    for (int v = n + tid; v < N; v += PREP_THREADS) {
+        const bool rightFirst = need[v] & 0x80;
+        const int c1 = rightFirst ? right[v] : left[v];
+        const int c2 = rightFirst ? left[v] : right[v];
+        PeelOp op;
+        // post-order: an internal second child is always the previous op; an internal first
+        // child is the previous op when the second child is a tip; otherwise it was parked
+        op.flags = (c2 >= n) ? OP_C2_PREV : ((c1 >= n) ? OP_C1_PREV : 0);
+        op.c1 = (c1 < n) ? -(c1 + 1) : ((op.flags & OP_C1_PREV) ? 0 : (int)pd[v]);
+        op.c2 = (c2 < n) ? -(c2 + 1) : 0;
+        op.dst = 0;
+        if (v != root) {
+            const int pp = parent[v];
+            const bool pRightFirst = need[pp] & 0x80;
+            const int pFirst = pRightFirst ? right[pp] : left[pp];
+            const int pSecond = pRightFirst ? left[pp] : right[pp];
+            if (pFirst == v && pSecond >= n) {      // my result waits for the sibling subtree
+                op.dst = pd[pp];
+                op.flags |= OP_STORE;
+                myMax = max(myMax, (int)pd[pp] + 1);
+            }
+        }
+        ops[istart[v] + isize[v] - 1] = op;
+    }
+    if (myMax)
+        atomicMax(&sMaxSlots, myMax);
     for (int idx = tid; idx < nOps * 2 * C; idx += PREP_THREADS) {
-        const int k = idx / (2 * C), j = (idx / C) & 1, c = idx % C;
-        const int v = stack[k];
+        const int v = n + idx / (2 * C), j = (idx / C) & 1, c = idx % C;
+        const int k = istart[v] + isize[v] - 1;
         const bool rightFirst = need[v] & 0x80;
         const int child = (j == 0) == rightFirst ? right[v] : left[v];
-        double *M = mats + (size_t)idx * 16;
+        double *M = mats + ((size_t)(k * 2 + j) * C + c) * 16;
         double T[16];
         if (matsIn) {
             const double *src = matsIn + ((size_t)child * C + c) * 16;
@@ -269,6 +301,11 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         const bool tip = child < n;
         for (int e = 0; e < 16; e++)
             M[e] = tip ? T[(e & 3) * 4 + (e >> 2)] : T[e];
+    }
+    __syncthreads();
+    if (tid == 0) {
+        info[b] = sMaxSlots;
+        atomicMax(maxSlotsAll, sMaxSlots);
     }
 }
 
@@ -680,10 +717,10 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
         return rc;
     if ((rc = grow(ctx, h->dInfo, h->infoCap, (size_t)B * 4)) != MTT_OK)
         return rc;
-    const size_t prepSmem = (size_t)N * 17 + 64;
+    const size_t prepSmem = (size_t)N * 15 + 64;
     if (prepSmem > 227 * 1024)
         return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: %d tips exceed the traversal planner's "
-                        "shared memory (limit ~6800 tips)", n);
+                        "shared memory (limit ~7700 tips)", n);
     MTT_CUDA(ctx, cudaFuncSetAttribute(k2_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)prepSmem));
     if (!h->dMaxSlots) {

@@ -308,6 +308,15 @@ __device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane)
     }
 }
 
+// The warp path keeps its running counts BIASED by CNT_BIAS per 16-bit field.  Events with
+// exactly equal times are processed in index order, which need not be a valid lineage order
+// (a coalescence may be seen before the same-time migration that brings its child into the
+// deme), so a count can be -1 transiently; the bias keeps such a field from borrowing from
+// its neighbour, and lambda -- a polynomial in the counts -- is updated consistently through
+// the transient.  Intervals are only integrated at dt > 0, when the counts are true again.
+constexpr int CNT_BIAS = 0x4000;
+constexpr unsigned long long CNT_BIAS_WORD = 0x4000400040004000ull;
+
 template <int NW>
 __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
 {
@@ -318,7 +327,7 @@ __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
             if ((deme >> 2) == i)
                 w = c.w[i];
     }
-    return (int)((w >> (16 * (deme & 3))) & 0xffffu);
+    return (int)((w >> (16 * (deme & 3))) & 0xffffu) - CNT_BIAS;
 }
 
 // One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
@@ -541,7 +550,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 if (lane >= o)
                     incl += v;
             }
-            base.w[i] = incl - local.w[i];
+            base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
         }
         // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
         double lambda = 0.0;

@@ -317,7 +317,7 @@ struct PeelCfg {
     static constexpr int OPS_PER_STAGE = (C == 1) ? 32 : (C == 2 ? 16 : (C <= 4 ? 8 : 4));
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
-    static constexpr int PPT = (C <= 4) ? 2 : 1;       // patterns per thread
+    static constexpr int MAX_PPT = (C <= 4) ? 2 : 1;   // patterns per thread (register budget)
 };
 
 // one child's contribution for PPT patterns of one category:
@@ -359,7 +359,7 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
 
 // TPT threads per CTA, PPT patterns per thread: a tile is TPT * PPT patterns
 // (pattern of (thread, u) = tile * TPT * PPT + u * TPT + tid, so global reads stay coalesced)
-template <int C, int TPT>
+template <int C, int TPT, int PPT>
 __global__ void __launch_bounds__(TPT)
 k2_peel(int n, long long P, long long pStride, const uint8_t *states, const double *weights,
         const uint8_t *constMask, const double *site, double pInv, const PeelOp *opsAll,
@@ -367,7 +367,6 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
         double *patternLogL)
 {
     using Cfg = PeelCfg<C>;
-    constexpr int PPT = Cfg::PPT;
     extern __shared__ __align__(16) unsigned char smem[];
     // layout: [2 stages: ops | mats][barriers][stack nSlots*C*4*PPT*TPT doubles]
     unsigned char *stageBase = smem;
@@ -654,14 +653,14 @@ int grow(mtt_ctx *ctx, T *&ptr, size_t &cap, size_t bytes)
     return MTT_OK;
 }
 
-template <int C, int TPT>
+template <int C, int TPT, int PPT>
 int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
 {
     mtt_ctx *ctx = h->ctx;
     using Cfg = PeelCfg<C>;
-    const int nTiles = (int)(h->pStride / (TPT * Cfg::PPT));
-    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * Cfg::PPT * TPT * 8;
-    auto kern = k2_peel<C, TPT>;
+    const int nTiles = (int)(h->pStride / (TPT * PPT));
+    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * PPT * TPT * 8;
+    auto kern = k2_peel<C, TPT, PPT>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     dim3 grid((unsigned)nTiles, (unsigned)B);
@@ -673,31 +672,34 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
     return MTT_OK;
 }
 
-// threads per CTA: the largest of 128 / 64 / 32 whose live partial vectors leave room for
-// at least two CTAs per SM
-inline int pick_tile(int C, int ppt, int nSlots, size_t stageBytes)
-{
-    for (int t = 128; t >= 32; t >>= 1)
-        if (2 * stageBytes + 16 + (size_t)nSlots * C * 4 * ppt * t * 8 <= 110 * 1024 || t == 32)
-            return t;
-    return 32;
-}
-
+// Tile shape: 128 threads x 2 patterns when two such CTAs fit an SM (parked partial vectors
+// live in shared memory); otherwise 128 x 1, then 64 x 1, then 32 x 1.
 template <int C>
 int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *patternLogL)
 {
     using Cfg = PeelCfg<C>;
-    const int t = pick_tile(C, Cfg::PPT, nSlots, Cfg::STAGE_BYTES);
-    if (2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * Cfg::PPT * t * 8 > 227 * 1024)
+    auto need = [&](int t, int ppt) {
+        return 2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * ppt * t * 8;
+    };
+    const size_t budget = 110 * 1024;
+    if (Cfg::MAX_PPT == 2 && need(128, 2) <= budget) {
+        *nTilesOut = (int)(h->pStride / 256);
+        return launch_peel_t<C, 128, Cfg::MAX_PPT>(h, B, nSlots, patternLogL);
+    }
+    if (need(128, 1) <= budget) {
+        *nTilesOut = (int)(h->pStride / 128);
+        return launch_peel_t<C, 128, 1>(h, B, nSlots, patternLogL);
+    }
+    if (need(64, 1) <= budget) {
+        *nTilesOut = (int)(h->pStride / 64);
+        return launch_peel_t<C, 64, 1>(h, B, nSlots, patternLogL);
+    }
+    if (need(32, 1) > 227 * 1024)
         return mtt_fail(h->ctx, MTT_ERR_TOO_LARGE,
-                        "peeling: %d live partial vectors x %d categories exceed shared memory",
+                        "peeling: %d parked partial vectors x %d categories exceed shared memory",
                         nSlots, C);
-    *nTilesOut = (int)(h->pStride / (t * Cfg::PPT));
-    if (t == 128)
-        return launch_peel_t<C, 128>(h, B, nSlots, patternLogL);
-    if (t == 64)
-        return launch_peel_t<C, 64>(h, B, nSlots, patternLogL);
-    return launch_peel_t<C, 32>(h, B, nSlots, patternLogL);
+    *nTilesOut = (int)(h->pStride / 32);
+    return launch_peel_t<C, 32, 1>(h, B, nSlots, patternLogL);
 }
 
 // run the pipeline on device-resident parent/height (or matsIn) for a chunk of trees

@@ -3,8 +3,8 @@
 
 Headline workload (BASELINE.json configs[1], "cfg2"): batched structured-coalescent logP of
 simulated 2-deme 100-tip multi-type trees, density only.  One step = one pass of the density
-kernel over one batch of B trees per GPU (B = 2^20 by default = 256 x the 4096-tree batch the
-config names, so that the ~2.6 GB of inputs exceed the 126 MB L2; the literal 4096-tree batch
+kernel over one batch of B trees per GPU (B = 2^19 by default = 128 x the 4096-tree batch the
+config names, so that the ~1.35 GB of inputs exceed the 126 MB L2; the literal 4096-tree batch
 is timed as well, with an L2 flush before every launch, and reported under "cfg2_b4096").
 
   value         trees/s, inputs resident in HBM, CUDA-event timed, max over ranks
@@ -354,7 +354,7 @@ def bench_peel(args):
                                                simulate_alignment)
     world, rank, local = dist_setup(args.gpus)
     cores = os.cpu_count() or 1
-    n, d, sites, B = 1000, 4, 10000, args.batch if args.batch != (1 << 20) else 64
+    n, d, sites, B = 1000, 4, 10000, args.batch if args.batch != (1 << 19) else 64
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(B, n, d, m, N, seed=3000 + rank * B, nThreads=max(1, cores // world))
     nN = 2 * n - 1
@@ -453,7 +453,7 @@ def bench_peel_sharded(args):
     world, rank, local = dist_setup(args.gpus)
     n, d = args.tips or 5000, 8
     sites = args.sites or 125000
-    B = args.batch if args.batch != (1 << 20) else 8
+    B = args.batch if args.batch != (1 << 19) else 8
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(B, n, d, m, N, seed=4000, nThreads=max(1, (os.cpu_count() or 1) // world))
     nN = 2 * n - 1
@@ -531,7 +531,7 @@ def bench_retype(args):
     from multitypetree_b200.uniformization import UniformizationModels
     world, rank, local = dist_setup(args.gpus)
     d, chains = 10, 64 // world if world <= 64 else 1
-    jobs_per_chain = args.batch if args.batch != (1 << 20) else 4096
+    jobs_per_chain = args.batch if args.batch != (1 << 19) else 4096
     rng = np.random.default_rng(5000 + rank)
     ms_ = np.stack([mtt.synthetic_model(d)[0] * rng.uniform(0.5, 2.0) for _ in range(chains)])
     ctx = mtt.Context(local)
@@ -579,7 +579,7 @@ def main():
     ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_sharded", "retype"])
     ap.add_argument("--tips", type=int, default=0)
     ap.add_argument("--sites", type=int, default=0)
-    ap.add_argument("--batch", type=int, default=1 << 20, help="trees per GPU per step")
+    ap.add_argument("--batch", type=int, default=1 << 19, help="trees per GPU per step")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     if args.impl == "reference":

@@ -47,7 +47,10 @@ struct SimTree {
     std::vector<double> height;
     std::vector<int32_t> parent;
     std::vector<uint8_t> nodeType;
-    std::vector<std::vector<std::pair<double, uint8_t>>> changes;   // per node, youngest first
+    // type changes in simulation (= increasing time) order: (node, time, new type); a flat list
+    // keeps the per-tree footprint small (2^20-tree batches are simulated for the benchmark)
+    struct Change { int32_t node; double time; uint8_t type; };
+    std::vector<Change> changes;
 };
 
 struct SimBatch {
@@ -64,7 +67,7 @@ void simulate_one(SimTree &t, int n, int d, const double *m, const double *N,
     t.height.assign(nNodes, 0.0);
     t.parent.assign(nNodes, -1);
     t.nodeType.assign(nNodes, 0);
-    t.changes.assign(nNodes, {});
+    t.changes.clear();
 
     // current type of the lineage above each created node, per-deme active lists
     std::vector<std::vector<int>> active(d);
@@ -138,7 +141,7 @@ void simulate_one(SimTree &t, int n, int d, const double *m, const double *N,
                     auto &L = active[i];
                     int a = rng.below((int)L.size());
                     int node = L[a];
-                    t.changes[node].push_back({tEvent, (uint8_t)j});
+                    t.changes.push_back({node, tEvent, (uint8_t)j});
                     L.erase(L.begin() + a);
                     active[j].push_back(node);
                     done = true;
@@ -192,8 +195,7 @@ int64_t mtt_sim_total_changes(const void *h)
     const SimBatch *sb = (const SimBatch *)h;
     int64_t tot = 0;
     for (auto &t : sb->trees)
-        for (auto &c : t.changes)
-            tot += (int64_t)c.size();
+        tot += (int64_t)t.changes.size();
     return tot;
 }
 
@@ -206,22 +208,32 @@ void mtt_sim_export(const void *h, int64_t *nodeOff, double *height, int32_t *pa
     const SimBatch *sb = (const SimBatch *)h;
     const int nNodes = 2 * sb->nLeaves - 1;
     int64_t c = 0;
+    std::vector<int32_t> cnt(nNodes), pos(nNodes);
     for (int64_t b = 0; b < sb->B; b++) {
         const SimTree &t = sb->trees[(size_t)b];
         nodeOff[b] = b * nNodes;
         chgBase[b] = c;
+        // counting sort of the change list by node; within a node the simulation order is
+        // already youngest -> oldest
+        std::fill(cnt.begin(), cnt.end(), 0);
+        for (auto &ch : t.changes)
+            cnt[ch.node]++;
+        int32_t run = 0;
         for (int i = 0; i < nNodes; i++) {
             int64_t g = b * nNodes + i;
             height[g] = t.height[i];
             parent[g] = t.parent[i];
             nodeType[g] = t.nodeType[i];
-            chgCount[g] = (uint16_t)t.changes[i].size();
-            for (auto &ch : t.changes[i]) {
-                chgTime[c] = ch.first;
-                chgType[c] = ch.second;
-                c++;
-            }
+            chgCount[g] = (uint16_t)cnt[i];
+            pos[i] = run;
+            run += cnt[i];
         }
+        for (auto &ch : t.changes) {
+            const int64_t k = c + pos[ch.node]++;
+            chgTime[k] = ch.time;
+            chgType[k] = ch.type;
+        }
+        c += run;
     }
     nodeOff[sb->B] = sb->B * nNodes;
     chgBase[sb->B] = c;

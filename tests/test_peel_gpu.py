@@ -204,3 +204,25 @@ def test_determinism_and_batch_independence(ctx):
     c = tl.calculateLogPBatch(par[3:7], hgt[3:7])
     assert np.array_equal(a, b) and np.array_equal(a[3:7], c)
     tl.close()
+
+
+@pytest.mark.parametrize("gamma", [0, 4])
+def test_random_topologies(ctx, gamma):
+    """Arbitrary (non-coalescent) topologies with dated tips and random data incl. missing
+    states: every tree of a batch has its own traversal plan."""
+    from tests.test_property_density import random_typed_tree
+    rng = np.random.default_rng(17 + gamma)
+    n, B = 37, 60
+    trees = [random_typed_tree(rng, n, 2, 0.0) for _ in range(B)]
+    par = np.stack([t.parent for t in trees])
+    hgt = np.stack([t.height for t in trees])
+    f = np.array([.15, .35, .3, .2])
+    tips = rng.integers(0, 5, size=(n, 333)).astype(np.int32)      # 4 = missing
+    al = Alignment(states=tips)
+    sm = SiteModel(HKY(4.0, f), mutationRate=0.3, gammaCategoryCount=gamma, shape=0.4,
+                   proportionInvariant=0.1)
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    got = tl.calculateLogPBatch(par, hgt)
+    want = _oracle(al, par, hgt, sm)
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    tl.close()

@@ -78,6 +78,39 @@ class MultiTypeTree:
                              [list(c) for c in self.changeTypes],
                              list(self.taxa) if self.taxa else None)
 
+    def getFlattenedNewick(self, typeLabel: str = "type") -> str:
+        """The 'flat' Newick of evolution/tree/MultiTypeTree.java:444-526 (getFlattenedTree):
+        every type change becomes a single-child node whose ``[&typeLabel=k]`` is the type
+        above it and whose height is the change time -- the format
+        ``MultiTypeTreeFromNewick`` / ``initFromFlatTree`` reads back, and the one BEAST uses to
+        log and checkpoint multi-type trees."""
+        kids = {}
+        for v, p in enumerate(self.parent):
+            kids.setdefault(int(p), []).append(v)
+        root = self.getRoot()
+        pieces = {}
+        # iterative post-order so that 5000-tip caterpillars do not hit the recursion limit
+        stack, order = [root], []
+        while stack:
+            v = stack.pop()
+            order.append(v)
+            stack.extend(kids.get(v, []))
+        for v in reversed(order):
+            ch = kids.get(v, [])
+            name = (self.taxa[v] if self.taxa and v < len(self.taxa) and self.taxa[v] else str(v)) \
+                if not ch else ""
+            body = ("(" + ",".join(pieces.pop(c) for c in ch) + ")" if ch else "") + name
+            s = "%s[&%s=%d]" % (body, typeLabel, int(self.nodeType[v]))
+            if v == root:
+                pieces[v] = s + ":0.0;"
+                continue
+            t_prev = float(self.height[v])
+            for t, c in zip(self.changeTimes[v], self.changeTypes[v]):
+                s = "(%s:%r)[&%s=%d]" % (s, float(t) - t_prev, typeLabel, int(c))
+                t_prev = float(t)
+            pieces[v] = "%s:%r" % (s, float(self.height[int(self.parent[v])]) - t_prev)
+        return pieces[root]
+
     def isValid(self, ctx=None) -> bool:
         """MultiTypeTree.isValid (MultiTypeTree.java:396-429), evaluated on the device."""
         from .density import tree_validity

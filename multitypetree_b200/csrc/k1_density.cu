@@ -7,21 +7,24 @@
 // then walks it.  Here the flattened tree (height / nodeType / chgCount / chgTime / chgType,
 // include/mtt_b200.h) is turned into events, ordered and scanned inside one kernel:
 //
-//   k1_density_warp   one WARP per tree (E = nodes + changes <= 256).  Persistent warps; each
-//                     stages the NEXT tree's five array slices into shared memory with 1-D
-//                     bulk async copies (TMA engine, mbarrier completion) while it works on
-//                     the current one.  Events are ordered by a register-resident bitonic
-//                     network over packed 32-bit keys (24-bit quantised time | 8-bit event
-//                     index; shuffles across lanes), then repaired against the exact fp64
-//                     times (rare), then the per-deme lineage counts are obtained by a warp
-//                     prefix sum of packed 16-bit count fields and every lane integrates its
-//                     8 consecutive intervals.  fp64 throughout; no atomics on the result.
+//   k1_density_warp   one WARP per tree (E = nodes + changes <= 512).  Persistent warps, 24
+//                     resident per SM; lane 0 stages the tree's five array slices into the
+//                     warp's shared-memory stage with 1-D bulk async copies (TMA engine,
+//                     mbarrier completion).  Events are ordered by a register-resident bitonic
+//                     network over packed 32-bit keys (23-bit quantised time | 9-bit event
+//                     index; shuffles across lanes), 256 at a time; a second run is merged by
+//                     merge path.  The per-deme lineage counts come from a warp prefix sum of
+//                     packed (biased) 16-bit count fields; every lane then integrates its 8
+//                     (16) consecutive intervals with a running lambda and verifies the exact
+//                     fp64 time order (quantisation ties are repaired, rarely).  fp64
+//                     throughout; no atomics on the result.
 //   k1_density_block  one CTA per tree for larger trees (E <= 16384), fed from the queue the
 //                     warp kernel fills: shared-memory bitonic sort of 64-bit keys
 //                     (38-bit quantised time | index | descriptor), same scan.
 //
-// HBM traffic per tree is the input arrays once (<= 12 B per event) + 8 B out: the kernel is
-// bound by HBM bandwidth and, at 2-deme/100-tip size, by the issue rate of the sort.
+// HBM traffic per tree is the input arrays once (<= 12 B per event) + 8 B out.  At the
+// 2-deme / 100-tip size the kernel is bound by instruction issue (the ordering network), not by
+// HBM bandwidth: see DESIGN.md section 4.1 and profiles/.
 #include "mtt_common.cuh"
 
 #include <math.h>
@@ -94,6 +97,18 @@ __device__ __forceinline__ void cnt_add(Counts<NW> &c, int deme, long long sgn)
             if ((deme >> 2) == i)
                 c.w[i] += inc;
     }
+}
+
+// branch-free variant for converged code: SAMPLE enters `from`, COALESCE leaves `from`,
+// MIGRATE leaves `from` and enters `to`, NONE does nothing
+template <int NW>
+__device__ __forceinline__ void cnt_apply_bf(Counts<NW> &c, uint32_t desc)
+{
+    const int kind = (desc >> 10) & 3, from = (desc >> 5) & 31, to = desc & 31;
+    const bool leave = (kind == KIND_COALESCE) | (kind == KIND_MIGRATE);
+    const bool enter = (kind == KIND_SAMPLE) | (kind == KIND_MIGRATE);
+    cnt_add<NW>(c, from, -(long long)leave);
+    cnt_add<NW>(c, (kind == KIND_MIGRATE) ? to : from, (long long)enter);
 }
 
 template <int NW>
@@ -461,6 +476,12 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     //      straight to the order list; two runs are stored as keys and merged (merge path).
     int Epad = (E > 256) ? 512 : 256;
     asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
+    // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
+    // accumulated while the ordered events are still in registers
+    Counts<NW> local;
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        local.w[i] = 0;
 #pragma unroll 1
     for (int base = 0; base < Epad; base += 256) {
         uint32_t key[8];
@@ -484,6 +505,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & 511u);
                 const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & 511u);
                 w[k] = a | (b << 16);
+                cnt_apply_bf<NW>(local, (a == 0xffffu) ? (uint32_t)(KIND_NONE << 10) : desc[a]);
+                cnt_apply_bf<NW>(local, (b == 0xffffu) ? (uint32_t)(KIND_NONE << 10) : desc[b]);
             }
             *reinterpret_cast<uint4 *>(order + 8 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
         } else {
@@ -512,6 +535,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             const bool takeA = ka <= kb;
             const uint32_t out = takeA ? ka : kb;
             order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & 511u);
+            cnt_apply_bf<NW>(local, (out == KEY_PAD) ? (uint32_t)(KIND_NONE << 10)
+                                                    : desc[out & 511u]);
             if (takeA) {
                 i++;
                 ka = (i < 256) ? A[i] : KEY_PAD;
@@ -527,18 +552,20 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     const int per = Epad >> 5;
     const int p0 = per * lane;
     double acc;
+    bool recount = false;                // only after a repair pass changed the order list
     for (;;) {
-        // C: packed count deltas of my chunk, warp prefix sum -> counts before my chunk
-        Counts<NW> local;
+        // C: warp prefix sum of the per-lane count deltas -> counts before my chunk
+        if (recount) {
 #pragma unroll
-        for (int i = 0; i < NW; i++)
-            local.w[i] = 0;
-#pragma unroll 2
-        for (int q = 0; q < per; q++) {
-            const int idx = order[p0 + q];
-            if (idx == 0xffff)
-                break;
-            cnt_apply<NW>(local, desc[idx]);
+            for (int i = 0; i < NW; i++)
+                local.w[i] = 0;
+#pragma unroll 1
+            for (int q = 0; q < per; q++) {
+                const int idx = order[p0 + q];
+                if (idx == 0xffff)
+                    break;
+                cnt_apply<NW>(local, desc[idx]);
+            }
         }
         Counts<NW> base;
 #pragma unroll
@@ -582,19 +609,19 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             if (!first && dt > 0.0)                          // StructuredCoalescentTreeDensity.java:108
                 acc -= dt * lambda;
             prevT = x;
-            if (kind != KIND_SAMPLE) {                       // a lineage leaves deme `from`
-                if (!first)
-                    acc += tab->logM[from * d + to];         // log(1/N) or log(m)  (:127-137)
-                const double kd = (double)cnt_get<NW>(base, from);
-                lambda -= (2.0 * (kd - 1.0)) * tab->inv2N[from] + tab->mu[from];
-                cnt_add<NW>(base, from, -1);
-            }
-            if (kind != KIND_COALESCE) {                     // a lineage enters a deme
-                const int a = (kind == KIND_MIGRATE) ? to : from;
-                const double kd = (double)cnt_get<NW>(base, a);
-                lambda += (2.0 * kd) * tab->inv2N[a] + tab->mu[a];
-                cnt_add<NW>(base, a, 1);
-            }
+            // Branch-free (lanes hold different event kinds): a lineage leaves deme `from`
+            // (COALESCE, MIGRATE) and / or enters deme `a` (SAMPLE, MIGRATE).  MIGRATE has
+            // a != from, so both updates can use the counts before the event.
+            const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
+            const int a = (kind == KIND_MIGRATE) ? to : from;
+            const double term = tab->logM[from * d + to];    // log(1/N) or log(m)  (:127-137)
+            acc += (leave && !first) ? term : 0.0;
+            const double kl = (double)cnt_get<NW>(base, from), ke = (double)cnt_get<NW>(base, a);
+            const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
+            const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
+            lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
+            cnt_add<NW>(base, from, -(long long)leave);
+            cnt_add<NW>(base, a, (long long)enter);
             first = false;
         }
         if (!__any_sync(FULL_MASK, inv))
@@ -618,6 +645,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             }
             swapped = __any_sync(FULL_MASK, swapped);
         }
+        recount = true;
     }
     return warp_sum_down(acc);
 }

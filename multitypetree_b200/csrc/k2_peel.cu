@@ -314,7 +314,9 @@ constexpr double SCALING_THRESHOLD = 1.0E-100;     // BeerLikelihoodCore.scaling
 
 template <int C>
 struct PeelCfg {
-    static constexpr int OPS_PER_STAGE = (C == 1) ? 32 : (C == 2 ? 16 : (C <= 4 ? 8 : 4));
+    // small stages: shared memory decides how many CTAs (warps) an SM holds, and the kernel
+    // is latency-bound on dependent fp64 chains, so residency matters more than stage depth
+    static constexpr int OPS_PER_STAGE = (C == 1) ? 16 : (C == 2 ? 8 : 4);
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
     static constexpr int MAX_PPT = (C <= 4) ? 2 : 1;   // patterns per thread (register budget)

@@ -196,6 +196,36 @@ def test_retype_status_codes(ctx):
     assert o.retype_branch(0, 1, 2, 0, u)["status"] == ST_NO_VALID_PATH
 
 
+def test_retype_degenerate_branches(ctx):
+    """Zero-length and very short / very long branches: L = 0 gives expm = I (jblas: j = 0),
+    so equal end types yield an empty path and different end types NO_VALID_PATH."""
+    d = 4
+    m = _model(d, 31)
+    um = UniformizationModels(m, ctx=ctx)
+    o = orc.UnifModel(m)
+    t0 = np.array([1.0, 1.0, 0.0, 0.0, 2.0, 0.0])
+    t1 = np.array([1.0, 1.0, 1e-12, 1e-300, 2.0 + 1e-9, 60.0])
+    a = np.array([2, 2, 1, 3, 0, 1])
+    b = np.array([2, 0, 1, 3, 0, 2])
+    W = 4096
+    u = np.random.default_rng(4).random(len(t0) * W)
+    r = um.retype(np.arange(len(t0) + 1), t0, t1, a, b, u, np.arange(len(t0) + 1) * W, outCap=512)
+    for i in range(len(t0)):
+        w = o.retype_branch(t0[i], t1[i], int(a[i]), int(b[i]), u[i * W:(i + 1) * W], cap=512)
+        assert r["status"][i] == w["status"], i
+        if w["status"] == ST_OK:
+            n = w["nChg"]
+            assert r["nChg"][i] == n and r["nVirt"][i] == w["nVirt"]
+            assert np.array_equal(r["chgTime"][i, :n], w["chgTime"])
+            assert r["logProb"][i] == pytest.approx(w["logProb"], rel=1e-9, abs=1e-12)
+    assert r["status"][0] == ST_OK and r["nChg"][0] == 0
+    assert r["status"][1] == ST_NO_VALID_PATH
+    E = um.expm([0.0, 1e-300])
+    assert np.array_equal(E[0], np.eye(d)) and np.allclose(E[1], np.eye(d), atol=1e-290)
+    lp, st = um.branch_logp([1.0], [1.0], [2], [2], [0, 0], [], [])
+    assert st[0] == 0 and lp[0] == 0.0
+
+
 def test_retype_steady_state_tail_and_forced_count(ctx):
     """Huge mu*L: the count draw runs past the steady index -> NEEDS_POISSON_TAIL with the
     threshold in nVirt (:94-102); resubmitting with nVirtForced samples the path."""

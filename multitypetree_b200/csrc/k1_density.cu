@@ -99,6 +99,29 @@ __device__ __forceinline__ void cnt_add(Counts<NW> &c, int deme, long long sgn)
     }
 }
 
+// NW == 0: the two-deme specialisation of the warp path -- one 32-bit word, two 16-bit fields
+template <>
+struct Counts<0> {
+    uint32_t w32;
+};
+template <>
+__device__ __forceinline__ void cnt_add<0>(Counts<0> &c, int deme, long long sgn)
+{
+    c.w32 += (uint32_t)((int)sgn << (16 * deme));
+}
+template <int NW>
+__device__ __forceinline__ void cnt_zero(Counts<NW> &c)
+{
+#pragma unroll
+    for (int i = 0; i < NW; i++)
+        c.w[i] = 0;
+}
+template <>
+__device__ __forceinline__ void cnt_zero<0>(Counts<0> &c)
+{
+    c.w32 = 0;
+}
+
 // branch-free variant for converged code: SAMPLE enters `from`, COALESCE leaves `from`,
 // MIGRATE leaves `from` and enters `to`, NONE does nothing
 template <int NW>
@@ -479,9 +502,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
     // accumulated while the ordered events are still in registers
     Counts<NW> local;
-#pragma unroll
-    for (int i = 0; i < NW; i++)
-        local.w[i] = 0;
+    cnt_zero<NW>(local);
 #pragma unroll 1
     for (int base = 0; base < Epad; base += 256) {
         uint32_t key[8];
@@ -556,9 +577,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     for (;;) {
         // C: warp prefix sum of the per-lane count deltas -> counts before my chunk
         if (recount) {
-#pragma unroll
-            for (int i = 0; i < NW; i++)
-                local.w[i] = 0;
+            cnt_zero<NW>(local);
 #pragma unroll 1
             for (int q = 0; q < per; q++) {
                 const int idx = order[p0 + q];
@@ -566,25 +585,6 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                     break;
                 cnt_apply<NW>(local, desc[idx]);
             }
-        }
-        Counts<NW> base;
-#pragma unroll
-        for (int i = 0; i < NW; i++) {
-            unsigned long long incl = local.w[i];
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const unsigned long long v = shfl_up_u64(incl, o);
-                if (lane >= o)
-                    incl += v;
-            }
-            base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
-        }
-        // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123) at the start of my chunk
-        double lambda = 0.0;
-#pragma unroll 1
-        for (int c = 0; c < d; c++) {
-            const double kd = (double)cnt_get<NW>(base, c);
-            lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
         }
         // D: interval integration with a running lambda; also verifies the exact time order
         double prevT = -INFINITY;
@@ -596,33 +596,91 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
         }
         bool inv = false;
         acc = 0.0;
+        if constexpr (NW == 0) {
+            // ---- two demes: counts as two doubles, lambda evaluated directly
+            uint32_t incl = local.w32;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+                if (lane >= o)
+                    incl += v;
+            }
+            const uint32_t b32 = incl - local.w32 + 0x40004000u;      // biased, see CNT_BIAS
+            double k0 = (double)((int)(b32 & 0xffffu) - CNT_BIAS);
+            double k1 = (double)((int)(b32 >> 16) - CNT_BIAS);
+            const double i0 = tab->inv2N[0], i1 = tab->inv2N[1], m0 = tab->mu[0], m1 = tab->mu[1];
+            // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123)
+            double lambda = ((k0 * (k0 - 1.0)) * i0 + k0 * m0) + ((k1 * (k1 - 1.0)) * i1 + k1 * m1);
 #pragma unroll 2
-        for (int q = 0; q < per; q++) {
-            const int idx = order[p0 + q];
-            if (idx == 0xffff)
-                break;
-            const double x = ev_time(idx);
-            const uint32_t ds = desc[idx];
-            const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
-            const double dt = x - prevT;
-            inv |= dt < 0.0;
-            if (!first && dt > 0.0)                          // StructuredCoalescentTreeDensity.java:108
-                acc -= dt * lambda;
-            prevT = x;
-            // Branch-free (lanes hold different event kinds): a lineage leaves deme `from`
-            // (COALESCE, MIGRATE) and / or enters deme `a` (SAMPLE, MIGRATE).  MIGRATE has
-            // a != from, so both updates can use the counts before the event.
-            const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
-            const int a = (kind == KIND_MIGRATE) ? to : from;
-            const double term = tab->logM[from * d + to];    // log(1/N) or log(m)  (:127-137)
-            acc += (leave && !first) ? term : 0.0;
-            const double kl = (double)cnt_get<NW>(base, from), ke = (double)cnt_get<NW>(base, a);
-            const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
-            const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
-            lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
-            cnt_add<NW>(base, from, -(long long)leave);
-            cnt_add<NW>(base, a, (long long)enter);
-            first = false;
+            for (int q = 0; q < per; q++) {
+                const int idx = order[p0 + q];
+                if (idx == 0xffff)
+                    break;
+                const double x = ev_time(idx);
+                const uint32_t ds = desc[idx];
+                const int kind = (ds >> 10) & 3, from = (ds >> 5) & 1, to = ds & 1;
+                const double dt = x - prevT;
+                inv |= dt < 0.0;
+                if (!first && dt > 0.0)                      // StructuredCoalescentTreeDensity.java:108
+                    acc -= dt * lambda;
+                prevT = x;
+                const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
+                const int a = (kind == KIND_MIGRATE) ? to : from;
+                const double term = tab->logM[from * 2 + to];   // log(1/N) or log(m)  (:127-137)
+                acc += (leave && !first) ? term : 0.0;
+                k0 += ((enter && a == 0) ? 1.0 : 0.0) - ((leave && from == 0) ? 1.0 : 0.0);
+                k1 += ((enter && a == 1) ? 1.0 : 0.0) - ((leave && from == 1) ? 1.0 : 0.0);
+                lambda = ((k0 * (k0 - 1.0)) * i0 + k0 * m0) + ((k1 * (k1 - 1.0)) * i1 + k1 * m1);
+                first = false;
+            }
+        } else {
+            Counts<NW> base;
+#pragma unroll
+            for (int i = 0; i < NW; i++) {
+                unsigned long long incl = local.w[i];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const unsigned long long v = shfl_up_u64(incl, o);
+                    if (lane >= o)
+                        incl += v;
+                }
+                base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
+            }
+            // lambda at the start of my chunk
+            double lambda = 0.0;
+#pragma unroll 1
+            for (int c = 0; c < d; c++) {
+                const double kd = (double)cnt_get<NW>(base, c);
+                lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+            }
+#pragma unroll 2
+            for (int q = 0; q < per; q++) {
+                const int idx = order[p0 + q];
+                if (idx == 0xffff)
+                    break;
+                const double x = ev_time(idx);
+                const uint32_t ds = desc[idx];
+                const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+                const double dt = x - prevT;
+                inv |= dt < 0.0;
+                if (!first && dt > 0.0)                      // StructuredCoalescentTreeDensity.java:108
+                    acc -= dt * lambda;
+                prevT = x;
+                // Branch-free (lanes hold different event kinds): a lineage leaves deme `from`
+                // (COALESCE, MIGRATE) and / or enters deme `a` (SAMPLE, MIGRATE).  MIGRATE has
+                // a != from, so both updates can use the counts before the event.
+                const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
+                const int a = (kind == KIND_MIGRATE) ? to : from;
+                const double term = tab->logM[from * d + to];   // log(1/N) or log(m)  (:127-137)
+                acc += (leave && !first) ? term : 0.0;
+                const double kl = (double)cnt_get<NW>(base, from), ke = (double)cnt_get<NW>(base, a);
+                const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
+                const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
+                lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
+                cnt_add<NW>(base, from, -(long long)leave);
+                cnt_add<NW>(base, a, (long long)enter);
+                first = false;
+            }
         }
         if (!__any_sync(FULL_MASK, inv))
             break;
@@ -1018,7 +1076,7 @@ template <int NW>
 int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long long nWorkHint)
 {
     size_t smem = sizeof(ModelTab) + (size_t)Ecap * 12;
-    auto kern = k1_density_block<NW>;
+    auto kern = k1_density_block<(NW == 0) ? 1 : NW>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     int perSM = 1;
@@ -1091,6 +1149,8 @@ int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double 
         return MTT_ERR_CUDA;
     if (fresh)
         MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
+    if (d <= 2)
+        return launch_all<0>(ctx, p, maxEvents);     // two-deme specialisation of the warp path
     if (d <= 4)
         return launch_all<1>(ctx, p, maxEvents);
     if (d <= 8)

@@ -9,10 +9,17 @@ from .tree import (MultiTypeTree, MultiTypeTreeFromNewick, TreeBatch,  # noqa: F
                    read_nexus_tree, simulate_trees, synthetic_model)
 from .migration_model import SCMigrationModel, TypeSet  # noqa: F401
 from .density import StructuredCoalescentTreeDensity, sc_logp_batch, tree_validity  # noqa: F401
+from .uniformization import Randomizer, UniformizationModels  # noqa: F401
+from .operators import (MultiTypeTreeScale, MultiTypeUniform, NodeRetype,  # noqa: F401
+                        NodeShiftRetype, TypedSubtreeExchange, TypedWilsonBalding,
+                        run_proposals)
+from .mcmc import MCMC, Chain, MCMCEnsemble  # noqa: F401
 
 __all__ = [
     "Context", "MttError", "default_context", "lib", "MultiTypeTree",
     "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "simulate_trees",
     "synthetic_model", "SCMigrationModel", "TypeSet", "StructuredCoalescentTreeDensity",
-    "sc_logp_batch", "tree_validity",
+    "sc_logp_batch", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",
+    "NodeShiftRetype", "TypedSubtreeExchange", "TypedWilsonBalding", "MultiTypeTreeScale",
+    "MultiTypeUniform", "run_proposals", "MCMC", "Chain", "MCMCEnsemble",
 ]

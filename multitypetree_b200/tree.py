@@ -26,8 +26,74 @@ class MultiTypeTree:
     changeTimes: List[List[float]] = field(default_factory=list)   # per node, youngest first
     changeTypes: List[List[int]] = field(default_factory=list)
     taxa: Optional[List[str]] = None
+    # explicit child order (BEAST's getLeft / getRight); built from `parent` on first use and
+    # kept up to date by the topology-changing operators (operators.py)
+    left: Optional[np.ndarray] = None     # i32 [nNodes], -1 = none
+    right: Optional[np.ndarray] = None
 
     # ---- MultiTypeNode / Tree accessors (same names as the reference) ----
+    def _ensure_children(self) -> None:
+        if self.left is not None:
+            return
+        n = len(self.height)
+        self.left = np.full(n, -1, np.int32)
+        self.right = np.full(n, -1, np.int32)
+        for v in range(n):                       # lower node number = left child
+            p = int(self.parent[v])
+            if p >= 0:
+                if self.left[p] < 0:
+                    self.left[p] = v
+                else:
+                    self.right[p] = v
+
+    def getLeft(self, node: int) -> int:
+        self._ensure_children()
+        return int(self.left[node])
+
+    def getRight(self, node: int) -> int:
+        self._ensure_children()
+        return int(self.right[node])
+
+    def getParent(self, node: int) -> int:
+        return int(self.parent[node])
+
+    def isRoot(self, node: int) -> bool:
+        return self.parent[node] < 0
+
+    def isLeaf(self, node: int) -> bool:
+        return node < self.getLeafNodeCount()
+
+    def getHeight(self, node: int) -> float:
+        return float(self.height[node])
+
+    def setHeight(self, node: int, h: float) -> None:
+        self.height[node] = h
+
+    def removeChild(self, node: int, child: int) -> None:
+        """beast Node.removeChild: drop `child` from the ordered child list of `node`."""
+        self._ensure_children()
+        if self.left[node] == child:
+            self.left[node], self.right[node] = self.right[node], -1
+        elif self.right[node] == child:
+            self.right[node] = -1
+
+    def addChild(self, node: int, child: int) -> None:
+        """beast Node.addChild: append to the child list and set the child's parent."""
+        self._ensure_children()
+        if self.left[node] < 0:
+            self.left[node] = child
+        else:
+            self.right[node] = child
+        self.parent[child] = node
+
+    def truncateChanges(self, node: int, newNChanges: int) -> None:
+        """MultiTypeNode.truncateChanges (MultiTypeNode.java:164-173)."""
+        del self.changeTimes[node][newNChanges:]
+        del self.changeTypes[node][newNChanges:]
+
+    def setChangeTime(self, node: int, idx: int, time: float) -> None:
+        self.changeTimes[node][idx] = float(time)
+
     def getNodeCount(self) -> int:
         return len(self.height)
 
@@ -67,16 +133,32 @@ class MultiTypeTree:
         self.changeTypes[node].append(int(newType))
 
     def getChildren(self, node: int) -> List[int]:
-        return [int(c) for c in np.nonzero(self.parent == node)[0]]
+        self._ensure_children()
+        return [int(c) for c in (self.left[node], self.right[node]) if c >= 0]
 
     def getTotalNumberOfChanges(self) -> int:
-        return sum(len(c) for c in self.changeTimes)
+        """MultiTypeTree.java:694-705: changes on the root branch are not counted."""
+        root = self.getRoot()
+        return sum(len(c) for v, c in enumerate(self.changeTimes) if v != root)
 
     def copy(self) -> "MultiTypeTree":
         return MultiTypeTree(self.height.copy(), self.parent.copy(), self.nodeType.copy(),
                              [list(c) for c in self.changeTimes],
                              [list(c) for c in self.changeTypes],
-                             list(self.taxa) if self.taxa else None)
+                             list(self.taxa) if self.taxa else None,
+                             None if self.left is None else self.left.copy(),
+                             None if self.right is None else self.right.copy())
+
+    def assignFrom(self, other: "MultiTypeTree") -> None:
+        """Restore this tree in place from a copy (BEAST ``StateNode.restore``); operators keep
+        their reference to the same object."""
+        self.height[:] = other.height
+        self.parent[:] = other.parent
+        self.nodeType[:] = other.nodeType
+        self.changeTimes = [list(c) for c in other.changeTimes]
+        self.changeTypes = [list(c) for c in other.changeTypes]
+        self.left = None if other.left is None else other.left.copy()
+        self.right = None if other.right is None else other.right.copy()
 
     def getFlattenedNewick(self, typeLabel: str = "type") -> str:
         """The 'flat' Newick of evolution/tree/MultiTypeTree.java:444-526 (getFlattenedTree):
@@ -84,9 +166,8 @@ class MultiTypeTree:
         above it and whose height is the change time -- the format
         ``MultiTypeTreeFromNewick`` / ``initFromFlatTree`` reads back, and the one BEAST uses to
         log and checkpoint multi-type trees."""
-        kids = {}
-        for v, p in enumerate(self.parent):
-            kids.setdefault(int(p), []).append(v)
+        self._ensure_children()
+        kids = {v: self.getChildren(v) for v in range(len(self.parent)) if self.left[v] >= 0}
         root = self.getRoot()
         pieces = {}
         # iterative post-order so that 5000-tip caterpillars do not hit the recursion limit

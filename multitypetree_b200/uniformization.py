@@ -1,5 +1,5 @@
-"""Host-side wrappers of the uniformization entry points (csrc/k3_unif.cu) and the mirror of
-operators/NodeRetype.java + operators/UniformizationRetypeOperator.java.
+"""Host-side wrappers of the uniformization entry points (csrc/k3_unif.cu); the operators that
+call them (NodeRetype, NodeShiftRetype, ...) live in operators.py.
 
 The numerical work -- Q/R/mu (SCMigrationModel.java:150-201), the R^k chain (:404-473), expm,
 the virtual-event count, forward-backward path sampling and path probabilities
@@ -56,6 +56,10 @@ class Randomizer:
     def skipDoubles(self, n: int):
         _lib.lib().mtt_rng_skip_doubles(self._h, n)
 
+    def nextExponential(self, lam: float) -> float:
+        """BEAST ``Randomizer.nextExponential``: -log(1 - nextDouble()) / lambda  ([EXT])."""
+        return -1.0 * np.log(1 - self.nextDouble()) / lam
+
     def nextPoisson(self, lam: float) -> int:
         """Poisson draw for the steady-state tail (UniformizationRetypeOperator.java:100-102).
         BEAST's own algorithm for this call is [EXT] and not reproduced: for lam < 40 the
@@ -88,11 +92,23 @@ class UniformizationModels:
             m = m[None]
         self.nModels, self.d = m.shape[0], m.shape[1]
         self.sym = bool(sym)
+        self._m = m
+        self._upload()
+
+    def _upload(self):
         self.ctx.check(_lib.lib().mtt_unif_set_models(self.ctx.handle, self.nModels, self.d,
-                                                      _lib.ptr(m), int(self.sym)))
+                                                      _lib.ptr(self._m), int(self.sym)))
+        self.ctx._unif_owner = self
+
+    def _activate(self):
+        """A ctx holds ONE model set (mtt_unif_set_models); if another UniformizationModels has
+        been installed on this ctx since, install this one again (its R^k cache restarts)."""
+        if getattr(self.ctx, "_unif_owner", None) is not self:
+            self._upload()
 
     def matrices(self, model: int = 0):
         """(Q, R, mu) as getQ/getR/getMu(sym) return them."""
+        self._activate()
         Q = np.empty((self.d, self.d))
         R = np.empty((self.d, self.d))
         mu = C.c_double()
@@ -102,6 +118,7 @@ class UniformizationModels:
 
     def rpow(self, model: int, kmax: int):
         """(R^0..R^kmax [kmax+1,d,d], RpowSteadyN) -- SCMigrationModel.getRpowN / RpowSteadyN."""
+        self._activate()
         out = np.empty((kmax + 1, self.d, self.d))
         steady = C.c_int()
         self.ctx.check(_lib.lib().mtt_unif_rpow(self.ctx.handle, model, kmax, _lib.ptr(out),
@@ -110,6 +127,7 @@ class UniformizationModels:
 
     def expm(self, L: Sequence[float], model: Optional[Sequence[int]] = None) -> np.ndarray:
         """expm(Q * L) for every L (the jblas call of UniformizationRetypeOperator.java:132)."""
+        self._activate()
         L = _lib.as_c(L, np.float64).ravel()
         mdl = np.zeros(len(L), np.int32) if model is None else _lib.as_c(model, np.int32)
         out = np.empty((len(L), self.d, self.d))
@@ -120,6 +138,7 @@ class UniformizationModels:
     def branch_logp(self, tBottom, tTop, typeBottom, typeTop, chgOff, chgTime, chgType,
                     model=None):
         """getBranchTypeProb for a batch of branches -> (logProb, status)."""
+        self._activate()
         t0 = _lib.as_c(tBottom, np.float64)
         n = len(t0)
         t1 = _lib.as_c(tTop, np.float64)
@@ -141,6 +160,7 @@ class UniformizationModels:
         """retypeBranch for a batch of jobs (mtt_unif_retype_batch).  Returns a dict of
         per-branch arrays nChg, chgTime [nBr,outCap], chgType, logProb, status, nVirt and
         per-job uUsed."""
+        self._activate()
         brOff = _lib.as_c(brOff, np.int64)
         nJobs = len(brOff) - 1
         t0 = _lib.as_c(tBottom, np.float64)
@@ -166,101 +186,3 @@ class UniformizationModels:
             _lib.ptr(nv), _lib.ptr(used)))
         return dict(nChg=nChg, chgTime=oct_, chgType=octy, logProb=lp, status=st, nVirt=nv,
                     uUsed=used)
-
-
-class NodeRetype:
-    """operators/NodeRetype.java: retype a random internal node and its <= 3 attached
-    branches with the uniformization sampler.  Same Inputs: ``multiTypeTree``,
-    ``migrationModel``, ``useSymmetrizedRates``."""
-
-    def __init__(self, multiTypeTree: MultiTypeTree, migrationModel,
-                 useSymmetrizedRates: bool = False, randomizer: Randomizer = None, ctx=None,
-                 uniform_window: int = 256):
-        self.mtTree = multiTypeTree
-        self.migModel = migrationModel
-        self.sym = bool(useSymmetrizedRates)
-        self.rng = randomizer or Randomizer(127)
-        self.ctx = ctx
-        self.window = uniform_window
-
-    def _models(self) -> UniformizationModels:
-        return self.migModel._ensure_device(self.sym)
-
-    def _branches(self, node: int) -> List[int]:
-        """node (if not root), left, right -- the order of NodeRetype.java:40-44, 52-56."""
-        t = self.mtTree
-        kids = t.getChildren(node)
-        return ([node] if t.parent[node] >= 0 else []) + kids
-
-    def proposal(self) -> float:
-        """Returns the log Hastings ratio, or -inf (NodeRetype.java:31-63)."""
-        t = self.mtTree
-        um = self._models()
-        node = t.getLeafNodeCount() + self.rng.nextInt(t.getInternalNodeCount())   # :36-37
-        branches = self._branches(node)
-
-        def desc(bs):
-            t0 = [t.height[b] for b in bs]
-            t1 = [t.height[t.parent[b]] for b in bs]
-            a = [t.getNodeType(b) for b in bs]
-            bb = [t.getNodeType(int(t.parent[b])) for b in bs]
-            return t0, t1, a, bb
-
-        # probability of the current types along the attached branches (:40-44)
-        t0, t1, a, bb = desc(branches)
-        off = np.cumsum([0] + [t.getChangeCount(b) for b in branches])
-        ct = [x for b in branches for x in t.changeTimes[b]]
-        cty = [x for b in branches for x in t.changeTypes[b]]
-        lp_old, st_old = um.branch_logp(t0, t1, a, bb, off, ct, cty)
-        logHR = float(np.sum(lp_old))
-        # new node type (:47-48)
-        t.setNodeType(node, self.rng.nextInt(self.migModel.getNTypes()))
-        # retype the attached branches from one uniform stream (:52-56)
-        t0, t1, a, bb = desc(branches)
-        nb = len(branches)
-        new_lp = [0.0] * nb
-        forced = [-1] * nb
-        start, window = 0, self.window
-        while start < nb:
-            u = self.rng.peekDoubles(window)
-            sl = slice(start, nb)
-            r = um.retype([0, nb - start], t0[sl], t1[sl], a[sl], bb[sl], u, [0, window],
-                          outCap=window, nVirtForced=forced[sl])
-            st = r["status"]
-            if np.any(st == ST_NEED_MORE_UNIFORMS):
-                window *= 4
-                continue
-            bad = np.nonzero(st != ST_OK)[0]
-            k = int(bad[0]) if len(bad) else nb - start
-            for i in range(k):                      # branches retyped successfully
-                b = branches[start + i]
-                t.clearChanges(b)
-                for j in range(int(r["nChg"][i])):
-                    t.addChange(b, int(r["chgType"][i, j]), float(r["chgTime"][i, j]))
-                new_lp[start + i] = float(r["logProb"][i])
-            self.rng.skipDoubles(int(r["uUsed"][0]))
-            if k == nb - start:
-                break
-            if st[k] == ST_NO_VALID_PATH:
-                return float("-inf")                # NoValidPathException (:57-58)
-            if st[k] == ST_NEEDS_POISSON_TAIL:
-                # steady-state tail (UniformizationRetypeOperator.java:96-102): the host
-                # Randomizer draws nVirt >= thresh, the branch is resubmitted with it forced
-                thresh = int(r["nVirt"][k])
-                muL = um.matrices(0)[2] * (t1[start + k] - t0[start + k])
-                while True:
-                    nv = self.rng.nextPoisson(muL)
-                    if nv >= thresh:
-                        break
-                forced[start + k] = nv
-                start += k
-                continue
-            # Pba rubbish / forward-backward failure: retypeBranch returned -Infinity and the
-            # proposal carries on with the remaining branches (:141-144, :179-190)
-            new_lp[start + k] = float("-inf")
-            start += k + 1
-        first = new_lp[0] if t.parent[node] >= 0 else 0.0
-        rest = new_lp[1:] if t.parent[node] >= 0 else new_lp
-        logHR -= first                               # logHR -= retypeBranch(node)
-        logHR -= sum(rest)                           # logHR -= retype(left) + retype(right)
-        return logHR

@@ -7,7 +7,8 @@ import pytest
 import scipy.linalg
 
 import multitypetree_b200 as mtt
-from multitypetree_b200.uniformization import (NodeRetype, Randomizer, UniformizationModels,
+from multitypetree_b200.operators import NodeRetype
+from multitypetree_b200.uniformization import (Randomizer, UniformizationModels,
                                                ST_NEED_MORE_UNIFORMS, ST_NEEDS_POISSON_TAIL,
                                                ST_NO_VALID_PATH, ST_OK, ST_SKIPPED)
 from oracle import oracle as orc

@@ -59,6 +59,11 @@ struct ModelTab {
     double mu[MTT_MAX_DEMES];        // sum_{c' != c} m(c,c')
     double logInvN[MTT_MAX_DEMES];   // log(1.0 / N_c)      (StructuredCoalescentTreeDensity.java:130)
     double logM[MTT_MAX_DEMES * MTT_MAX_DEMES];   // log(m(c,c'))   (:136)
+    // two-deme path: everything an event does, looked up by its class = 2 * kind + from
+    // (SAMPLE 0/1, COALESCE 2/3, MIGRATE 4/5 with to = 1 - from, NONE 6/7)
+    double clsTerm[8];               // log(1/N) / log(m) event term
+    double clsDk[2][8];              // change of the lineage count of deme 0 / 1
+    uint32_t clsDelta[8];            // the same as a packed pair of 16-bit fields
 };
 
 // cooperative fill by `nthr` threads with index `tid`
@@ -77,6 +82,28 @@ __device__ __forceinline__ void fill_model_tab(ModelTab *t, const double *m, con
     }
     for (int e = tid; e < d * d; e += nthr)
         t->logM[e] = (e / d == e % d) ? log(1.0 / N[e / d]) : log(m[e]);   // diagonal: coalescence
+    if (d <= 2) {
+        for (int c = tid; c < 8; c += nthr) {
+            const int kind = c >> 1, from = c & 1, to = 1 - from;
+            double term = 0.0, dk[2] = {0.0, 0.0};
+            if (from < d) {
+                if (kind == KIND_SAMPLE) {
+                    dk[from] = 1.0;
+                } else if (kind == KIND_COALESCE) {
+                    dk[from] = -1.0;
+                    term = log(1.0 / N[from]);
+                } else if (kind == KIND_MIGRATE && to < d) {
+                    dk[from] = -1.0;
+                    dk[to] = 1.0;
+                    term = log(m[from * d + to]);
+                }
+            }
+            t->clsTerm[c] = term;
+            t->clsDk[0][c] = dk[0];
+            t->clsDk[1][c] = dk[1];
+            t->clsDelta[c] = (uint32_t)((int)dk[0] + (int)dk[1] * 65536);
+        }
+    }
 }
 
 // lineage counts packed as 16-bit fields, 4 demes per 64-bit word
@@ -104,11 +131,6 @@ template <>
 struct Counts<0> {
     uint32_t w32;
 };
-template <>
-__device__ __forceinline__ void cnt_add<0>(Counts<0> &c, int deme, long long sgn)
-{
-    c.w32 += (uint32_t)((int)sgn << (16 * deme));
-}
 template <int NW>
 __device__ __forceinline__ void cnt_zero(Counts<NW> &c)
 {
@@ -368,6 +390,23 @@ __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
     return (int)((w >> (16 * (deme & 3))) & 0xffffu) - CNT_BIAS;
 }
 
+// two-deme path: the event class 2 * kind + from rides in bits 12..14 of the descriptor
+template <int NW>
+__device__ __forceinline__ uint16_t cls_bits(int kind, int from)
+{
+    return (NW == 0) ? (uint16_t)((kind * 2 + (from & 1)) << 12) : (uint16_t)0;
+}
+
+// count deltas of one ordered event added to the lane's packed sum
+template <int NW>
+__device__ __forceinline__ void cnt_accumulate(Counts<NW> &c, uint32_t ds, const ModelTab *tab)
+{
+    if constexpr (NW == 0)
+        c.w32 += tab->clsDelta[ds >> 12];
+    else
+        cnt_apply_bf<NW>(c, ds);
+}
+
 // One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
 // the validity verdict (all lanes).  Scratch aliases: `keys` doubles as a byte array during
 // phase A (before the sort writes it); the stage's chgCount region, dead after phase A,
@@ -429,7 +468,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             for (int e = lane; e < n; e += 32) {
                 const int type = sT[e];
                 desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
-                                                   : (KIND_COALESCE << 10 | type << 5 | type));
+                                                   : (KIND_COALESCE << 10 | type << 5 | type)) |
+                          cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
             }
             __syncwarp();
             if (sane) {
@@ -437,11 +477,12 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 for (int c = lane; c < M; c += 32) {
                     const int f = firstFrom[c];
                     const int from = (f != 0xff) ? f : (int)sCT[c - 1];
-                    desc[n + c] = (uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]);
+                    desc[n + c] = (uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]) |
+                                  cls_bits<NW>(KIND_MIGRATE, from);
                 }
             } else {
                 for (int c = lane; c < M; c += 32)
-                    desc[n + c] = (uint16_t)(KIND_NONE << 10);
+                    desc[n + c] = (uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0);
             }
         } else {
             // node-centric walk with the validity chain of MultiTypeTree.java:396-429
@@ -450,7 +491,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 const int c = sane ? (int)sK[e] : 0;
                 int type = sT[e];
                 desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
-                                                   : (KIND_COALESCE << 10 | type << 5 | type));
+                                                   : (KIND_COALESCE << 10 | type << 5 | type)) |
+                          cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
                 const int par = sP[e];
                 const bool isRoot = par < 0;
                 double lastT = sH[e];
@@ -459,7 +501,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                     const int to = sCT[off + q];
                     // root-branch changes are ignored (StructuredCoalescentTreeDensity.java:161-162)
                     desc[n + off + q] =
-                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to);
+                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to) |
+                        cls_bits<NW>(isRoot ? KIND_NONE : KIND_MIGRATE, type);
                     const double tq = sC[off + q];
                     ok = ok && !(lastT > tq);                // :404-405
                     lastT = tq;
@@ -473,7 +516,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             }
             if (!sane)
                 for (int c = lane; c < M; c += 32)
-                    desc[n + c] = (uint16_t)(KIND_NONE << 10);
+                    desc[n + c] = (uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0);
             ok = __all_sync(FULL_MASK, ok);
         }
     }
@@ -483,21 +526,28 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     // ---- time range over the node heights (interleaved, conflict-free reads).  Change times
     //      of a valid tree lie inside it; anything outside just saturates the quantised key
     //      and is put in exact order by the repair pass below.
-    double lo = INFINITY, hi = -INFINITY;
+    // Only the high words are compared (as order-preserving integers): lo is rounded down and
+    // hi up by less than 2^-20 relative, which quantisation does not notice.
+    int kmin = 0x7fffffff, kmax = (int)0x80000000;
 #pragma unroll 2
     for (int e = lane; e < n; e += 32) {
-        const double x = sH[e];
-        lo = fmin(lo, x);
-        hi = fmax(hi, x);
+        const int hw = reinterpret_cast<const int *>(sH)[2 * e + 1];
+        const int key = hw ^ ((hw >> 31) & 0x7fffffff);
+        kmin = min(kmin, key);
+        kmax = max(kmax, key);
     }
-    lo = warp_min(lo);
-    hi = warp_max(hi);
+    kmin = __reduce_min_sync(FULL_MASK, kmin);
+    kmax = __reduce_max_sync(FULL_MASK, kmax);
+    const int hwLo = kmin ^ ((kmin >> 31) & 0x7fffffff), hwHi = kmax ^ ((kmax >> 31) & 0x7fffffff);
+    const double lo = __hiloint2double(hwLo, hwLo < 0 ? -1 : 0);
+    const double hi = __hiloint2double(hwHi, hwHi < 0 ? 0 : -1);
     const double range = hi - lo;
-    const double scale = (range > 0.0) ? (double)QMAX / range : 0.0;
+    const double scale = (range > 1e-300 && range < INFINITY) ? (double)QMAX / range : 0.0;
 
     // ---- phase B: order.  256 events at a time through the register network.  One run goes
     //      straight to the order list; two runs are stored as keys and merged (merge path).
-    int Epad = (E > 256) ? 512 : 256;
+    constexpr int LB = EMAX - 256;       // capacity of the second run (EMAX = 384 or 512)
+    int Epad = (E > 256) ? EMAX : 256;
     asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
     // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
     // accumulated while the ordered events are still in registers
@@ -526,22 +576,26 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & 511u);
                 const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & 511u);
                 w[k] = a | (b << 16);
-                cnt_apply_bf<NW>(local, (a == 0xffffu) ? (uint32_t)(KIND_NONE << 10) : desc[a]);
-                cnt_apply_bf<NW>(local, (b == 0xffffu) ? (uint32_t)(KIND_NONE << 10) : desc[b]);
+                cnt_accumulate<NW>(local, (a == 0xffffu) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
+                                                         : (uint32_t)desc[a], tab);
+                cnt_accumulate<NW>(local, (b == 0xffffu) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
+                                                         : (uint32_t)desc[b], tab);
             }
             *reinterpret_cast<uint4 *>(order + 8 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else {
+        } else if (base == 0 || 8 * lane < LB) {
+            // second run: only its first LB keys can be real (E <= EMAX), padding sorts last
             uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
             dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
             dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
         }
     }
     __syncwarp();
-    if (EMAX > 256 && Epad == 512) {
-        // merge path: lane produces outputs [16*lane, 16*lane+16) of the two ascending runs
+    if (EMAX > 256 && Epad != 256) {
+        // merge path: lane produces outputs [per*lane, per*lane+per) of the two ascending runs
+        constexpr int PERM = EMAX / 32;
         const uint32_t *A = keys, *B = keys + 256;
-        const int diag = 16 * lane;
-        int a0 = max(0, diag - 256), a1 = min(diag, 256);
+        const int diag = PERM * lane;
+        int a0 = max(0, diag - LB), a1 = min(diag, 256);
         while (a0 < a1) {
             const int mid = (a0 + a1) >> 1;
             if (A[mid] <= B[diag - 1 - mid])
@@ -550,20 +604,20 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 a1 = mid;
         }
         int i = a0, j = diag - a0;
-        uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < 256) ? B[j] : KEY_PAD;
+        uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < LB) ? B[j] : KEY_PAD;
 #pragma unroll 1
-        for (int q = 0; q < 16; q++) {
+        for (int q = 0; q < PERM; q++) {
             const bool takeA = ka <= kb;
             const uint32_t out = takeA ? ka : kb;
             order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & 511u);
-            cnt_apply_bf<NW>(local, (out == KEY_PAD) ? (uint32_t)(KIND_NONE << 10)
-                                                    : desc[out & 511u]);
+            cnt_accumulate<NW>(local, (out == KEY_PAD) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
+                                                      : (uint32_t)desc[out & 511u], tab);
             if (takeA) {
                 i++;
                 ka = (i < 256) ? A[i] : KEY_PAD;
             } else {
                 j++;
-                kb = (j < 256) ? B[j] : KEY_PAD;
+                kb = (j < LB) ? B[j] : KEY_PAD;
             }
         }
         __syncwarp();
@@ -583,7 +637,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 const int idx = order[p0 + q];
                 if (idx == 0xffff)
                     break;
-                cnt_apply<NW>(local, desc[idx]);
+                cnt_accumulate<NW>(local, desc[idx], tab);
             }
         }
         // D: interval integration with a running lambda; also verifies the exact time order
@@ -608,31 +662,39 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             const uint32_t b32 = incl - local.w32 + 0x40004000u;      // biased, see CNT_BIAS
             double k0 = (double)((int)(b32 & 0xffffu) - CNT_BIAS);
             double k1 = (double)((int)(b32 >> 16) - CNT_BIAS);
-            const double i0 = tab->inv2N[0], i1 = tab->inv2N[1], m0 = tab->mu[0], m1 = tab->mu[1];
-            // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123)
-            double lambda = ((k0 * (k0 - 1.0)) * i0 + k0 * m0) + ((k1 * (k1 - 1.0)) * i1 + k1 * m1);
+            // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123), as
+            // k_c (k_c / (2 N_c) + (mu_c - 1 / (2 N_c)))
+            const double i0 = tab->inv2N[0], i1 = tab->inv2N[1];
+            const double b0 = tab->mu[0] - i0, b1 = tab->mu[1] - i1;
+            double lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
+            // event 0 is skipped (:101): lane 0 starts at its own first event (dt = 0) and
+            // takes that event's term out again below
+            double skipTerm = 0.0;
+            if (lane == 0) {
+                const int i00 = order[0];
+                if (i00 != 0xffff) {
+                    prevT = ev_time(i00);
+                    skipTerm = tab->clsTerm[desc[i00] >> 12];
+                }
+            }
 #pragma unroll 2
             for (int q = 0; q < per; q++) {
                 const int idx = order[p0 + q];
                 if (idx == 0xffff)
                     break;
                 const double x = ev_time(idx);
-                const uint32_t ds = desc[idx];
-                const int kind = (ds >> 10) & 3, from = (ds >> 5) & 1, to = ds & 1;
+                const int cls = desc[idx] >> 12;
                 const double dt = x - prevT;
                 inv |= dt < 0.0;
-                if (!first && dt > 0.0)                      // StructuredCoalescentTreeDensity.java:108
+                if (dt > 0.0)                                // StructuredCoalescentTreeDensity.java:108
                     acc -= dt * lambda;
                 prevT = x;
-                const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
-                const int a = (kind == KIND_MIGRATE) ? to : from;
-                const double term = tab->logM[from * 2 + to];   // log(1/N) or log(m)  (:127-137)
-                acc += (leave && !first) ? term : 0.0;
-                k0 += ((enter && a == 0) ? 1.0 : 0.0) - ((leave && from == 0) ? 1.0 : 0.0);
-                k1 += ((enter && a == 1) ? 1.0 : 0.0) - ((leave && from == 1) ? 1.0 : 0.0);
-                lambda = ((k0 * (k0 - 1.0)) * i0 + k0 * m0) + ((k1 * (k1 - 1.0)) * i1 + k1 * m1);
-                first = false;
+                acc += tab->clsTerm[cls];                    // log(1/N) or log(m)  (:127-137)
+                k0 += tab->clsDk[0][cls];
+                k1 += tab->clsDk[1][cls];
+                lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
             }
+            acc -= skipTerm;
         } else {
             Counts<NW> base;
 #pragma unroll
@@ -708,12 +770,12 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     return warp_sum_down(acc);
 }
 
-// EMAX = 256: every tree of the batch is known to have <= 256 events (smaller shared-memory
-// footprint).  EMAX = 512: trees up to 512 events; larger ones are queued for the CTA-per-tree
+// EMAX = 256 / 384: every tree of the batch is known to have <= 256 / 384 events (smaller
+// shared-memory footprint: 4 CTAs = 32 warps per SM instead of 3).  EMAX = 512: trees up to 512 events; larger ones are queued for the CTA-per-tree
 // kernel.  Persistent warps, one tree at a time per warp: lane 0 launches the bulk copies of
 // the tree's array slices (TMA engine), the warp waits on its mbarrier, orders and scans.
 template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int EMAX>
-__global__ void __launch_bounds__(W_WARPS * 32, 3)
+__global__ void __launch_bounds__(W_WARPS * 32, (EMAX <= 384) ? 4 : 3)
 k1_density_warp(const K1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -1105,6 +1167,8 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
     }
     if (maxEvents > 0 && maxEvents <= 256)          // one launch, nothing can be queued
         return launch_warp_any<NW, 256>(ctx, p);
+    if (maxEvents > 0 && maxEvents <= 384)          // 4 CTAs (32 warps) per SM still fit
+        return launch_warp_any<NW, 384>(ctx, p);
     if (maxEvents > 0 && maxEvents <= 512)
         return launch_warp_any<NW, 512>(ctx, p);
     // some trees may exceed the warp path: they are queued and consumed by the block kernel;

@@ -210,10 +210,11 @@ def _pad_changes(tree, target_M):
 
 
 @pytest.mark.parametrize("n,targets", [(128, (255, 256, 257, 258)), (250, (510, 511, 512, 513, 514)),
-                                       (64, (127, 128, 129))])
+                                       (64, (127, 128, 129)), (190, (381, 382, 383, 384)),
+                                       (190, (383, 384, 385, 386)), (150, (299, 300, 383, 384))])
 def test_event_count_boundaries(ctx, n, targets):
-    """E = nodes + changes right at the 256 / 512 limits of the warp path (one run, two runs
-    + merge, hand-over to the CTA kernel)."""
+    """E = nodes + changes right at the 256 / 384 / 512 limits of the warp path (one run, two
+    runs + merge in the 384- and 512-event stages, hand-over to the CTA kernel)."""
     m, N = mtt.synthetic_model(2)
     pool = mtt.simulate_trees(64, n, 2, m * 0.01, N, seed=600 + n)      # few migrations
     trees, want_E = [], []

@@ -151,6 +151,15 @@ int orc_branch_type_prob(const orc_unif_model *um, double tBottom, double tTop, 
                          int nChg, const double *chgTime, const int32_t *chgType, int typeTop,
                          double *logProb);
 
+/* ---------------------------------------------------------------- next row: untyped density
+ * distributions/StructuredCoalescentUntypedTreeDensity.java (orc_untyped.c). */
+int orc_poisson_window(double lam, const double *u, int64_t nU, int64_t *pos, int *out);
+int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
+                         const int32_t *parent, const double *height, const uint8_t *leafType,
+                         const int32_t *leafOrder, const double *u, int64_t nU, double *logW,
+                         int64_t *uUsed, int32_t *nodeTypeOut, int32_t *nEventsOut);
+double orc_untyped_combine(const double *logW, int nParticles);
+
 /* ---------------------------------------------------------------- piece 2: peeling */
 
 /* BEAST 2 HKY.getTransitionProbabilities restated [EXT].

@@ -577,13 +577,68 @@ def bench_retype(args):
         "gpu_launches": int(ctx.launch_count() - l0)}))
 
 
+def bench_untyped(args):
+    """untyped-tree particle density, trees x particles in one call."""
+    import multitypetree_b200 as mtt
+    from multitypetree_b200.uniformization import UniformizationModels
+    from multitypetree_b200.untyped import untyped_logp_batch
+    world, rank, local = dist_setup(args.gpus)
+    d, n = 2, (args.tips or 100)
+    B = args.batch if args.batch != (1 << 19) else 64
+    P, W = 256, 2048
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=6000 + rank * B)
+    trees = [tb.tree(b) for b in range(B)]
+    rng = np.random.default_rng(6000 + rank)
+    orders = np.concatenate([rng.permutation(n).astype(np.int32) for _ in range(B * P)])
+    u = rng.random(B * P * W)
+    uOff = np.arange(B * P + 1, dtype=np.int64) * W
+    ctx = mtt.Context(local)
+    um = UniformizationModels(m, ctx=ctx)
+    for _ in range(args.warmup):
+        r = untyped_logp_batch(um, N, trees, P, orders, u, uOff, ctx=ctx)
+    barrier(world)
+    l0 = ctx.launch_count()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        r = untyped_logp_batch(um, N, trees, P, orders, u, uOff, ctx=ctx)
+    barrier(world)
+    dt = max_over_ranks(time.perf_counter() - t0, world)
+    if rank != 0:
+        return
+    # CPU baseline: the oracle restatement, one thread, a bounded sample of the same particles
+    from oracle import oracle as orc
+    o = orc.UnifModel(m)
+    sample = min(B * P, 2048)
+    c0 = time.perf_counter()
+    worst = 0.0
+    for q in range(sample):
+        t = trees[q // P]
+        ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[q * n:(q + 1) * n],
+                                  u[uOff[q]:uOff[q + 1]])
+        worst = max(worst, abs(ro["logW"] - r["logW"].ravel()[q]) / max(1.0, abs(ro["logW"])))
+    cdt = time.perf_counter() - c0
+    print(json.dumps({
+        "metric": "untyped-tree density: particle evaluations/s (end to end, host buffers)",
+        "value": B * P * world * args.steps / dt, "unit": "particles/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "untyped density: %d trees x %d particles per GPU, %d tips, d=%d"
+                               % (B, P, n, d), "tree_evals_per_s": B * world * args.steps / dt},
+        "cpu_baseline": {"value": sample / cdt, "unit": "particles/s", "cores": 1, "kind": "port",
+                         "sample": "%d particles of the same batch, oracle/orc_untyped.c" % sample},
+        "parity_max_rel_err_vs_oracle": worst,
+        "gpu_launches": int(ctx.launch_count() - l0)}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_sharded", "retype"])
+    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_sharded", "retype", "untyped"])
     ap.add_argument("--tips", type=int, default=0)
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--batch", type=int, default=1 << 19, help="trees per GPU per step")
@@ -597,6 +652,8 @@ def main():
         return bench_peel_sharded(args)
     if args.workload == "retype":
         return bench_retype(args)
+    if args.workload == "untyped":
+        return bench_untyped(args)
     return bench_density(args)
 
 

@@ -171,6 +171,27 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
                           uint8_t *outChgType, double *logProb, int32_t *status,
                           int32_t *nVirt, int64_t *uUsed);
 
+/* ------------------------------------------------------------------ next row: untyped density
+ * Replaces distributions/StructuredCoalescentUntypedTreeDensity.java:116-207 (calculateLogP)
+ * with :216-290 (colourFirstLineage), :292-316 (colourLineage), :386-512 (addTypeChanges):
+ * the importance-sampling estimate of the structured-coalescent density of an UNTYPED tree,
+ * batched over nTrees trees x nParticles particles (one warp per particle).
+ * Models: those installed by mtt_unif_set_models with sym = 0 (backward rates = Q's
+ * off-diagonals); model[nTrees] (may be NULL = model 0); N[nModels][d] population sizes.
+ * Tree t = nodes nodeOff[t]..nodeOff[t+1] in BEAST numbering (leaves first, odd count <= 1024),
+ * parent -1 = root; leafType[node] is read for leaves only.
+ * Randomness (caller's Randomizer): leafOrder holds, tree-major then particle-major, one
+ * permutation of the tree's leaves per particle (Randomizer.shuffled, :129); particle
+ * q = t * nParticles + p consumes uniforms[uOff[q] .. uOff[q+1]) in the reference's order.
+ * Outputs: logP[nTrees]; optional per particle logW, status (MTT_ST_OK or
+ * MTT_ST_NEED_MORE_UNIFORMS: resubmit with longer windows), uUsed. */
+int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles, const int32_t *model,
+                           const double *N, const int64_t *nodeOff, const double *height,
+                           const int32_t *parent, const uint8_t *leafType,
+                           const int32_t *leafOrder, const double *uniforms,
+                           const int64_t *uOff, double *logP, double *logW, int32_t *status,
+                           int64_t *uUsed);
+
 /* ------------------------------------------------------------------ piece 2: peeling
  * Replaces BEAST 2 core beast.base.evolution.likelihood.TreeLikelihood.calculateLogP +
  * BeerLikelihoodCore as wired by the reference at examples/structuredCoalescent.xml:568-572

@@ -44,6 +44,8 @@ ABI = {
     "mtt_unif_expm_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_unif_branch_logp_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP,
                                              VP]),
+    "mtt_untyped_logp_batch": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP,
+                                        VP, VP, VP, VP, VP]),
     "mtt_unif_retype_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP,
                                         C.c_int, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_peel_create": (C.c_int, [VP, C.c_int, C.c_int64, C.c_int, C.POINTER(VP)]),

@@ -12,6 +12,7 @@
 // R^k, expm(QL) and the sampled type paths are bit-identical to the CPU restatement for the
 // same uniform stream (only libm log/exp may differ in the last ulp).
 #include "mtt_common.cuh"
+#include "k3_device.cuh"
 
 #include <math.h>
 #include <string.h>
@@ -20,46 +21,6 @@
 #include <vector>
 
 namespace {
-
-constexpr int U_WARPS = 4;          // warps per CTA
-constexpr int U_TCAP = 512;         // virtual events kept in shared memory per warp
-
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-// one copy each of the long libm / division sequences (instruction-cache footprint)
-__device__ __noinline__ double log_ni(double x) { return log(x); }
-__device__ __noinline__ double exp_ni(double x) { return exp(x); }
-__device__ __noinline__ double div_ni(double a, double b) { return __ddiv_rn(a, b); }
-
-// (row << 8 | col) of every element index of a d x d matrix: filled once per warp so that the
-// hot loops need no integer division
-__device__ __forceinline__ void fill_rc(uint16_t *rc, int d, int lane)
-{
-    #pragma unroll 1
-    for (int e = lane; e < d * d; e += 32)
-        rc[e] = (uint16_t)(((e / d) << 8) | (e % d));
-    __syncwarp();
-}
-#define RC_ROW(v) ((int)(v) >> 8)
-#define RC_COL(v) ((int)(v) & 255)
-
-// C = A * B (d x d, row-major, shared memory); C must not alias A or B.  Deliberately NOT
-// inlined: expm calls it ~10 times and the kernels must stay instruction-cache resident
-// (the fully inlined expm was 4400 SASS instructions and stalled on instruction fetch).
-__device__ __noinline__ void mm(int d, const double *A, const double *B, double *C,
-                                const uint16_t *rc, int lane)
-{
-    #pragma unroll 1
-    for (int e = lane; e < d * d; e += 32) {
-        const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
-        double s = 0.0;
-        for (int k = 0; k < d; k++)
-            s = add_rn(s, mul_rn(A[i * d + k], B[k * d + j]));
-        C[e] = s;
-    }
-    __syncwarp();
-}
 
 // ---- updateMatrices (SCMigrationModel.java:150-201), one warp per model ------------------
 __global__ void k3_update_matrices(int nModels, int d, const double *m, int sym, double *Q,
@@ -157,152 +118,6 @@ __global__ void k3_rpow_extend(int nModels, int d, const double *R, double *pow,
     }
 }
 
-// ---- jblas MatrixFunctions.expm restated [EXT]: Pade-13 scaling & squaring + LU solve ------
-__constant__ double PADE[14] = {
-    1.0, 0.5, 0.12, 0.01833333333333333, 0.0019927536231884053, 1.630434782608695E-4,
-    1.0351966873706E-5, 5.175983436853E-7, 2.0431513566525E-8, 6.306022705717593E-10,
-    1.4837700484041396E-11, 2.5291534915979653E-13, 2.8101705462199615E-15,
-    1.5440497506703084E-17};
-
-__device__ __forceinline__ double pade_poly(double eye, double a2, double a4, double a6, int c0)
-{
-    // ((eye*c[c0] + A2*c[c0+2]) + A4*c[c0+4]) + A6*c[c0+6]
-    return add_rn(add_rn(add_rn(mul_rn(eye, PADE[c0]), mul_rn(a2, PADE[c0 + 2])),
-                         mul_rn(a4, PADE[c0 + 4])),
-                  mul_rn(a6, PADE[c0 + 6]));
-}
-
-// LU with partial pivoting, F = D^-1 N left in N (unblocked right-looking elimination)
-__device__ __noinline__ void lu_solve(int d, double *D, double *N, const uint16_t *rc, int lane)
-{
-    for (int k = 0; k < d; k++) {
-        int p = k;
-        double best = fabs(D[k * d + k]);
-        for (int i = k + 1; i < d; i++) {
-            const double v = fabs(D[i * d + k]);
-            if (v > best) {
-                best = v;
-                p = i;
-            }
-        }
-        __syncwarp();
-        if (p != k) {
-            #pragma unroll 1
-            for (int j = lane; j < d; j += 32) {
-                double t = D[k * d + j]; D[k * d + j] = D[p * d + j]; D[p * d + j] = t;
-                t = N[k * d + j]; N[k * d + j] = N[p * d + j]; N[p * d + j] = t;
-            }
-            __syncwarp();
-        }
-        const double pivot = D[k * d + k];
-        #pragma unroll 1
-        for (int i = k + 1 + lane; i < d; i += 32)
-            D[i * d + k] = div_ni(D[i * d + k], pivot);
-        __syncwarp();
-        const int rows = d - k - 1;
-        #pragma unroll 1
-        for (int e = lane; e < rows * d; e += 32) {
-            const int i = k + 1 + RC_ROW(rc[e]), j = RC_COL(rc[e]);
-            const double l = D[i * d + k];
-            if (j > k)
-                D[i * d + j] = sub_rn(D[i * d + j], mul_rn(l, D[k * d + j]));
-            N[i * d + j] = sub_rn(N[i * d + j], mul_rn(l, N[k * d + j]));
-        }
-        __syncwarp();
-    }
-    for (int k = d - 1; k >= 0; k--) {
-        const double pivot = D[k * d + k];
-        __syncwarp();
-        #pragma unroll 1
-        for (int j = lane; j < d; j += 32)
-            N[k * d + j] = div_ni(N[k * d + j], pivot);
-        __syncwarp();
-        #pragma unroll 1
-        for (int e = lane; e < k * d; e += 32) {
-            const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
-            N[i * d + j] = sub_rn(N[i * d + j], mul_rn(D[i * d + k], N[k * d + j]));
-        }
-        __syncwarp();
-    }
-}
-
-// expm(Q * L) with Q in global/shared memory; `buf` = 8 d*d shared-memory matrices of this
-// warp.  Returns a pointer (inside buf) to the result.
-__device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, double *buf,
-                                              const uint16_t *rc, int lane)
-{
-    const int dd = d * d;
-    double *As = buf, *A2 = buf + dd, *A4 = buf + 2 * dd, *A6 = buf + 3 * dd, *T = buf + 4 * dd,
-           *U = buf + 5 * dd, *V = buf + 6 * dd, *W = buf + 7 * dd;
-    double nm = 0.0;
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32) {
-        const double a = mul_rn(Q[e], L);                   // Q.mul(L)
-        As[e] = a;
-        nm = fmax(nm, fabs(a));
-    }
-    nm = warp_max(nm);
-    int j = 0;
-    if (nm > 0.0) {
-        const double f = floor(log_ni(nm) / log_ni(2.0));
-        if (f > -1.0)
-            j = 1 + (int)f;
-    }
-    const double scale = scalbn(1.0, j);
-    __syncwarp();
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32)
-        As[e] = div_ni(As[e], scale);
-    __syncwarp();
-    mm(d, As, As, A2, rc, lane);
-    mm(d, A2, A2, A4, rc, lane);
-    mm(d, A4, A2, A6, rc, lane);
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32)
-        T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 6);
-    __syncwarp();
-    mm(d, T, A6, U, rc, lane);
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32) {
-        const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
-        U[e] = add_rn(add_rn(add_rn(mul_rn(eye, PADE[0]), mul_rn(A2[e], PADE[2])),
-                             mul_rn(A4[e], PADE[4])),
-                      U[e]);
-    }
-    __syncwarp();
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32)
-        T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 7);
-    __syncwarp();
-    mm(d, T, A6, V, rc, lane);
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32) {
-        const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
-        V[e] = add_rn(add_rn(add_rn(mul_rn(eye, PADE[1]), mul_rn(A2[e], PADE[3])),
-                             mul_rn(A4[e], PADE[5])),
-                      V[e]);
-    }
-    __syncwarp();
-    mm(d, As, V, W, rc, lane);                                  // AV
-    double *Nn = A2, *D = A4;                               // A2, A4 are dead from here
-    #pragma unroll 1
-    for (int e = lane; e < dd; e += 32) {
-        const double u = U[e], av = W[e];
-        Nn[e] = add_rn(u, av);
-        D[e] = sub_rn(u, av);
-    }
-    __syncwarp();
-    lu_solve(d, D, Nn, rc, lane);
-    double *F = Nn, *G = T;
-    for (int k = 0; k < j; k++) {                           // F = F * F, j times
-        mm(d, F, F, G, rc, lane);
-        double *t = F;
-        F = G;
-        G = t;
-    }
-    return F;
-}
-
 __global__ void k3_expm_batch(long long n, int d, const double *Q, const int *model,
                               const double *L, double *out)
 {
@@ -390,27 +205,6 @@ struct RetypeParams {
     int scratchCap;
 };
 
-// ascending bitonic sort of npad (power of two) doubles by one warp
-__device__ __forceinline__ void warp_sort_doubles(double *x, int npad, int lane)
-{
-    for (int size = 2; size <= npad; size <<= 1) {
-        for (int stride = size >> 1; stride > 0; stride >>= 1) {
-            for (int i = lane; i < (npad >> 1); i += 32) {
-                const int a = 2 * i - (i & (stride - 1));
-                int b = a + stride;
-                if (stride == (size >> 1))
-                    b = (a & ~(size - 1)) + (size - 1 - (a & (size - 1)));
-                const double xa = x[a], xb = x[b];
-                if (xa > xb) {
-                    x[a] = xb;
-                    x[b] = xa;
-                }
-            }
-            __syncwarp();
-        }
-    }
-}
-
 __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
 {
     extern __shared__ double sm[];
@@ -444,116 +238,20 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
         }
         const int mdl = p.model[br];
         const double *Q = p.Q + (size_t)mdl * dd, *R = p.R + (size_t)mdl * dd;
-        const double *tab = p.pow + (size_t)mdl * p.powCap * dd;
-        const int size = p.meta[2 * mdl], steady = p.meta[2 * mdl + 1];
-        const int steadyN = steady ? size : -1;                          // RpowSteadyN :460-473
         const double t0 = p.tBottom[br], t1 = p.tTop[br];
         const int a = p.typeBottom[br], b = p.typeTop[br];
-        const double L = sub_rn(t1, t0);                                 // :124
-        const double muL = mul_rn(p.mu[mdl], L);                         // :130
-        const double *E = expm_QL(d, Q, L, buf, rc, lane);                   // :132-134
-        const double Pba = E[a * d + b];
-        __syncwarp();
-
-        int st = MTT_ST_OK, nVirt = -1, nChg = 0;
+        const size_t w = (size_t)blockIdx.x * U_WARPS + warp;
+        const BranchSample bs = sample_branch<false>(
+            d, Q, R, p.pow + (size_t)mdl * p.powCap * dd, p.meta[2 * mdl], p.meta[2 * mdl + 1],
+            p.mu[mdl], t0, t1, a, b, p.nVirtForced ? p.nVirtForced[br] : -1, u, nU, pos, buf, rc,
+            sTimes, sTypes, p.scratchT + w * p.scratchCap, p.scratchTy + w * p.scratchCap,
+            p.scratchCap, lane);
+        int st = bs.st, nChg = 0;
+        const int nVirt = bs.nVirt;
+        const double Pba = bs.Pba;
+        const double *times = bs.times;
+        const uint8_t *types = bs.types;
         double lp = -INFINITY;
-        if (Pba == 0.0)                                                  // :137-138
-            st = MTT_ST_NO_VALID_PATH;
-        else if (Pba > 1.0 || Pba < 0.0)                                 // :141-144
-            st = MTT_ST_PBA_RUBBISH;
-
-        // ---- drawEventCount (:74-105)
-        if (st == MTT_ST_OK) {
-            const int forced = p.nVirtForced ? p.nVirtForced[br] : -1;
-            if (forced >= 0) {
-                nVirt = forced;
-            } else if (pos >= nU) {
-                st = MTT_ST_NEED_MORE_UNIFORMS;
-            } else {
-                const double uu = u[pos++];                              // :79
-                double Plow = 0.0;
-                double acc = sub_rn(-muL, log_ni(Pba));                     // :81
-                const double log_muL = log_ni(muL);                         // :82
-                int n = 0;
-                while (true) {
-                    if (n >= size && !steady) {
-                        st = MTT_ST_NEED_MORE_POWERS;
-                        break;
-                    }
-                    const double Rn = tab[(size_t)min(n, size - 1) * dd + a * d + b];
-                    Plow = add_rn(Plow, exp_ni(add_rn(log_ni(Rn), acc)));      // :86
-                    if (Plow > uu) {                                     // :88-89
-                        nVirt = n;
-                        break;
-                    }
-                    n += 1;
-                    acc = add_rn(acc, sub_rn(log_muL, log_ni((double)n)));  // :92
-                    if (!(steadyN < 0 || n < steadyN)) {                 // :94
-                        st = MTT_ST_NEEDS_POISSON_TAIL;                  // :96-102 -> host
-                        nVirt = n;                                       // thresh
-                        break;
-                    }
-                }
-            }
-        }
-        // a steady table answers any n; otherwise powers up to nVirt must exist
-        if (st == MTT_ST_OK && nVirt >= size && !steady)
-            st = MTT_ST_NEED_MORE_POWERS;
-        if (st == MTT_ST_OK && pos + 2LL * nVirt > nU)
-            st = MTT_ST_NEED_MORE_UNIFORMS;
-        double *times = sTimes;
-        uint8_t *types = sTypes;
-        if (st == MTT_ST_OK && nVirt > U_TCAP) {
-            if (nVirt > p.scratchCap) {
-                st = MTT_ST_NEED_MORE_POWERS;   // host grows the scratch along with the table
-            } else {
-                const size_t w = (size_t)blockIdx.x * U_WARPS + warp;
-                times = p.scratchT + w * p.scratchCap;
-                types = p.scratchTy + w * p.scratchCap;
-            }
-        }
-
-        if (st == MTT_ST_OK) {
-            // ---- times of the virtual events (:154-157)
-            int npad = 1;
-            while (npad < nVirt)
-                npad <<= 1;
-            if (nVirt == 0)
-                npad = 0;
-            for (int i = lane; i < npad; i += 32)
-                times[i] = (i < nVirt) ? add_rn(mul_rn(u[pos + i], L), t0) : INFINITY;
-            pos += nVirt;
-            __syncwarp();
-            warp_sort_doubles(times, npad, lane);
-
-            // ---- forward-backward sampling of the types (:163-194)
-            int prev = a;
-            for (int i = 1; i <= nVirt; i++) {
-                const double *Rhi = tab + (size_t)min(nVirt - i + 1, size - 1) * dd;
-                const double *Rlo = tab + (size_t)min(nVirt - i, size - 1) * dd;
-                double u2 = mul_rn(u[pos++], Rhi[prev * d + b]);         // :165-166
-                double prod = 0.0;
-                if (lane < d)
-                    prod = mul_rn(R[prev * d + lane], Rlo[lane * d + b]);
-                int c = 0;
-                bool fell = true;
-                for (c = 0; c < d; c++) {
-                    u2 = sub_rn(u2, __shfl_sync(FULL_MASK, prod, c));    // :170-171
-                    if (u2 < 0.0) {
-                        fell = false;
-                        break;
-                    }
-                }
-                if (fell) {                                              // :179-190
-                    st = MTT_ST_FB_FELL_THROUGH;
-                    break;
-                }
-                if (lane == 0)
-                    types[i - 1] = (uint8_t)c;
-                prev = c;
-            }
-            __syncwarp();
-        }
 
         if (st == MTT_ST_OK) {
             // ---- real changes + path probability (:196-221)
@@ -644,6 +342,11 @@ int ensure_powers(mtt_ctx *ctx, int K)
 size_t expm_smem(int d) { return (size_t)U_WARPS * 8 * d * d * 8; }
 
 }  // namespace
+
+int mtt_unif_ensure_powers(mtt_ctx *ctx, int K)
+{
+    return ensure_powers(ctx, K);
+}
 
 extern "C" {
 

@@ -42,10 +42,15 @@ enum BufId {
     BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
     BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6,
+    BUF_P_MODEL, BUF_P_N, BUF_P_NODEOFF, BUF_P_HEIGHT, BUF_P_PARENT, BUF_P_LEAFTYPE,
+    BUF_P_ORDEROFF, BUF_P_ORDER, BUF_P_U, BUF_P_UOFF, BUF_P_LOGW, BUF_P_STATUS, BUF_P_USED,
+    BUF_P_LOGP,
     BUF_COUNT
 };
 
 int mtt_fail(mtt_ctx *ctx, int code, const char *fmt, ...);
+// piece 3: make sure R^0..R^K exist for every installed model (k3_unif.cu)
+int mtt_unif_ensure_powers(mtt_ctx *ctx, int K);
 // grow-only device buffer with 256 B of slack past `bytes` (bulk copies over-read <= 15 B)
 void *mtt_buf(mtt_ctx *ctx, int id, size_t bytes);
 

@@ -75,6 +75,13 @@ def lib():
         L.orc_backward_rate.argtypes = [VP, C.c_int, C.c_int]
         L.orc_resolve_dense.restype = None
         L.orc_resolve_dense.argtypes = [VP, VP, VP]
+        L.orc_untyped_particle.restype = C.c_int
+        L.orc_untyped_particle.argtypes = [VP, VP, C.c_int, VP, VP, VP, VP, VP, C.c_int64, VP,
+                                           VP, VP, VP]
+        L.orc_untyped_combine.restype = C.c_double
+        L.orc_untyped_combine.argtypes = [VP, C.c_int]
+        L.orc_poisson_window.restype = C.c_int
+        L.orc_poisson_window.argtypes = [C.c_double, VP, C.c_int64, VP, VP]
         _lib = L
     return _lib
 
@@ -192,6 +199,33 @@ class UnifModel:
         st = L.orc_branch_type_prob(C.byref(self._s), tBottom, tTop, typeBottom, len(ct), _p(ct),
                                     _p(cty), typeTop, C.byref(lp))
         return st, lp.value
+
+
+def untyped_particle(um: "UnifModel", N, parent, height, leafType, leafOrder, u):
+    """One particle of StructuredCoalescentUntypedTreeDensity.calculateLogP (:121-189):
+    returns dict(status, logW, uUsed, nodeType, nEvents)."""
+    L = lib()
+    N = _c(N, np.float64)
+    parent = _c(parent, np.int32)
+    height = _c(height, np.float64)
+    leafType = _c(leafType, np.uint8)
+    leafOrder = _c(leafOrder, np.int32)
+    u = _c(u, np.float64)
+    n = len(parent)
+    logW = C.c_double()
+    used = C.c_int64()
+    nodeType = np.zeros(n, np.int32)
+    nEv = C.c_int32()
+    st = L.orc_untyped_particle(C.byref(um._s), _p(N), n, _p(parent), _p(height), _p(leafType),
+                                _p(leafOrder), _p(u), len(u), C.byref(logW), C.byref(used),
+                                _p(nodeType), C.byref(nEv))
+    return dict(status=st, logW=logW.value, uUsed=used.value, nodeType=nodeType, nEvents=nEv.value)
+
+
+def untyped_combine(logW):
+    """log(mean(exp(logW))) as the reference computes it (:193-201)."""
+    logW = _c(logW, np.float64)
+    return lib().orc_untyped_combine(_p(logW), len(logW))
 
 
 def expm(A):

@@ -1,0 +1,133 @@
+"""StructuredCoalescentUntypedTreeDensity on the device (csrc/k4_untyped.cu)
+against the CPU oracle (oracle/orc_untyped.c) particle by particle for the same leaf orders and
+uniform windows, plus the oracle itself against the exact two-leaf marginal density."""
+import numpy as np
+import pytest
+import scipy.linalg as sl
+
+import multitypetree_b200 as mtt
+from multitypetree_b200.uniformization import Randomizer, UniformizationModels
+from multitypetree_b200.untyped import (StructuredCoalescentUntypedTreeDensity, shuffled,
+                                        untyped_logp_batch)
+from oracle import oracle as orc
+
+
+def _exact_two_leaf(m, N, a, b, T):
+    """log density of a two-leaf untyped tree with coalescence time T: the pair process
+    (type of lineage 1, type of lineage 2) killed at rate 1/N_c while both sit in deme c."""
+    d = len(N)
+    Q = np.array(m, float)
+    for i in range(d):
+        Q[i, i] = -(Q[i].sum() - Q[i, i])
+    G = np.kron(Q, np.eye(d)) + np.kron(np.eye(d), Q)
+    for c in range(d):
+        G[c * d + c, c * d + c] -= 1.0 / N[c]
+    E = sl.expm(G * T)
+    return np.log(sum(E[a * d + b, c * d + c] / N[c] for c in range(d)))
+
+
+def test_oracle_particle_estimator_converges_to_exact_two_leaf_density():
+    m = np.array([[0, 0.3], [0.2, 0]])
+    N = np.array([5.0, 10.0])
+    um = orc.UnifModel(m)
+    parent = np.array([2, 2, -1], np.int32)
+    rng = np.random.default_rng(7)
+    for a, b, T in ((0, 0, 3.0), (0, 1, 3.0), (1, 0, 8.0)):
+        height = np.array([0.0, 0.0, T])
+        ws = []
+        for _ in range(20000):
+            r = orc.untyped_particle(um, N, parent, height, [a, b, 0], rng.permutation(2),
+                                     rng.random(512))
+            assert r["status"] == 0
+            ws.append(r["logW"])
+        ws = np.array(ws)
+        w = np.exp(ws - ws.max())
+        se = w.std() / w.mean() / np.sqrt(len(w))
+        assert abs(orc.untyped_combine(ws) - _exact_two_leaf(m, N, a, b, T)) < 5 * se + 1e-12
+
+
+def _inputs(trees, P, win, seed):
+    rng = np.random.default_rng(seed)
+    orders = [rng.permutation(t.getLeafNodeCount()).astype(np.int32) for t in trees
+              for _ in range(P)]
+    u = rng.random(len(trees) * P * win)
+    uOff = np.arange(len(trees) * P + 1, dtype=np.int64) * win
+    return orders, u, uOff
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,n,scale", [(2, 8, 1.0), (2, 40, 1.0), (3, 25, 0.5), (4, 60, 2.0),
+                                       (10, 30, 1.0), (16, 12, 1.0)])
+def test_particles_match_oracle(ctx, d, n, scale):
+    """Every particle: same log weight (1e-9), same number of uniforms consumed -- i.e. the
+    same sampled typing -- and the combined estimate, for random trees and models."""
+    m, N = mtt.synthetic_model(d)
+    m = m * scale
+    trees = [mtt.simulate_trees(3, n, d, m, N, seed=90 + d).tree(b) for b in range(3)]
+    P, win = 12, 4096
+    orders, u, uOff = _inputs(trees, P, win, 5 + d)
+    um = UniformizationModels(m, ctx=ctx)
+    r = untyped_logp_batch(um, N, trees, P, np.concatenate(orders), u, uOff, ctx=ctx)
+    o = orc.UnifModel(m)
+    for b, t in enumerate(trees):
+        ws = []
+        for p in range(P):
+            q = b * P + p
+            ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[q],
+                                      u[uOff[q]:uOff[q + 1]])
+            assert ro["status"] == r["status"][b, p] == 0
+            assert ro["uUsed"] == r["uUsed"][b, p], (b, p)
+            assert r["logW"][b, p] == pytest.approx(ro["logW"], rel=1e-9, abs=1e-9), (b, p)
+            ws.append(ro["logW"])
+        assert r["logP"][b] == pytest.approx(orc.untyped_combine(ws), rel=1e-9)
+
+
+@pytest.mark.gpu
+def test_window_too_short_is_reported(ctx):
+    m, N = mtt.synthetic_model(2)
+    t = mtt.simulate_trees(1, 30, 2, m, N, seed=4).tree(0)
+    orders, u, uOff = _inputs([t], 4, 8, 1)
+    um = UniformizationModels(m, ctx=ctx)
+    r = untyped_logp_batch(um, N, [t], 4, np.concatenate(orders), u, uOff, ctx=ctx)
+    assert np.all(r["status"] == 5)
+    o = orc.UnifModel(m)
+    ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[0], u[:8])
+    assert ro["status"] == 5
+
+
+@pytest.mark.gpu
+def test_disconnected_model_gives_reference_infinities(ctx):
+    """No path between the types (Pba == 0): the Java subtracts -Infinity from the particle
+    weight (:136, :311-313); the device reproduces the resulting +inf / NaN pattern."""
+    m = np.array([[0.0, 0.0], [0.0, 0.0]]) + np.array([[0, 1e-300], [1e-300, 0]]) * 0
+    m = np.array([[0.0, 0.5], [0.0, 0.0]])          # 1 -> 0 impossible backward in time
+    N = np.array([1.0, 1.0])
+    t = mtt.MultiTypeTreeFromNewick("((a[&t=0]:1,b[&t=1]:1)[&t=0]:1,c[&t=0]:2)[&t=0]:0;", "t")
+    orders, u, uOff = _inputs([t], 6, 256, 3)
+    um = UniformizationModels(m, ctx=ctx)
+    r = untyped_logp_batch(um, N, [t], 6, np.concatenate(orders), u, uOff, ctx=ctx)
+    o = orc.UnifModel(m)
+    for p in range(6):
+        ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[p],
+                                  u[uOff[p]:uOff[p + 1]])
+        a, b = r["logW"][0, p], ro["logW"]
+        assert (np.isnan(a) and np.isnan(b)) or a == b or a == pytest.approx(b, rel=1e-9)
+
+
+@pytest.mark.gpu
+def test_estimator_on_device_converges_to_exact_two_leaf_density(ctx):
+    m = np.array([[0, 0.3], [0.2, 0]])
+    N = np.array([5.0, 10.0])
+    model = mtt.SCMigrationModel([0.3, 0.2], N, mtt.TypeSet("0", "1"), ctx=ctx)
+    t = mtt.MultiTypeTreeFromNewick("(a[&t=0]:3,b[&t=1]:3)[&t=0]:0;", "t")
+    dens = StructuredCoalescentUntypedTreeDensity(model, t, nParticles=50000,
+                                                  randomizer=Randomizer(11), ctx=ctx)
+    est = dens.calculateLogP()
+    assert est == pytest.approx(_exact_two_leaf(m, N, 0, 1, 3.0), abs=0.02)
+    assert dens.isStochastic() and dens.requiresRecalculation()
+
+
+def test_shuffled_is_a_permutation():
+    rng = Randomizer(3)
+    for n in (1, 2, 7, 100):
+        assert sorted(shuffled(rng, n)) == list(range(n))

@@ -36,6 +36,9 @@ public final class MttNative implements AutoCloseable {
     private static final MethodHandle UNIF_RETYPE = h("mtt_unif_retype_batch", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
             JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle UNTYPED_LOGP = h("mtt_untyped_logp_batch", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
+            ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle PEEL_CREATE = h("mtt_peel_create", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS));
     private static final MethodHandle PEEL_DESTROY = h("mtt_peel_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
@@ -129,6 +132,22 @@ public final class MttNative implements AutoCloseable {
         try {
             check((int) UNIF_RETYPE.invoke(ctx, nJobs, brOff, model, tBottom, tTop, typeBottom, typeTop, nVirtForced,
                     uniforms, uOff, outCap, nChg, outChgTime, outChgType, logProb, status, nVirt, uUsed));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
+    /** mtt_untyped_logp_batch: nTrees x nParticles importance-sampling particles, one call. */
+    public void untypedLogPBatch(long nTrees, int nParticles, MemorySegment model, MemorySegment N,
+                                 MemorySegment nodeOff, MemorySegment height, MemorySegment parent,
+                                 MemorySegment leafType, MemorySegment leafOrder, MemorySegment uniforms,
+                                 MemorySegment uOff, MemorySegment logP, MemorySegment logW,
+                                 MemorySegment status, MemorySegment uUsed) {
+        try {
+            check((int) UNTYPED_LOGP.invoke(ctx, nTrees, nParticles, model, N, nodeOff, height, parent, leafType,
+                    leafOrder, uniforms, uOff, logP, logW, status, uUsed));
         } catch (RuntimeException e) {
             throw e;
         } catch (Throwable t) {

@@ -585,7 +585,7 @@ def bench_untyped(args):
     world, rank, local = dist_setup(args.gpus)
     d, n = 2, (args.tips or 100)
     B = args.batch if args.batch != (1 << 19) else 64
-    P, W = 256, 2048
+    P, W = 256, 1024
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(B, n, d, m, N, seed=6000 + rank * B)
     trees = [tb.tree(b) for b in range(B)]
@@ -595,6 +595,8 @@ def bench_untyped(args):
     uOff = np.arange(B * P + 1, dtype=np.int64) * W
     ctx = mtt.Context(local)
     um = UniformizationModels(m, ctx=ctx)
+    L = mtt.lib()
+    pinned = [a for a in (u, orders) if L.mtt_host_register(a.ctypes.data, a.nbytes) == 0]
     for _ in range(args.warmup):
         r = untyped_logp_batch(um, N, trees, P, orders, u, uOff, ctx=ctx)
     barrier(world)
@@ -625,7 +627,8 @@ def bench_untyped(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "untyped density: %d trees x %d particles per GPU, %d tips, d=%d"
-                               % (B, P, n, d), "tree_evals_per_s": B * world * args.steps / dt},
+                               % (B, P, n, d), "tree_evals_per_s": B * world * args.steps / dt,
+                   "uniform_window": W, "pinned": len(pinned) == 2},
         "cpu_baseline": {"value": sample / cdt, "unit": "particles/s", "cores": 1, "kind": "port",
                          "sample": "%d particles of the same batch, oracle/orc_untyped.c" % sample},
         "parity_max_rel_err_vs_oracle": worst,

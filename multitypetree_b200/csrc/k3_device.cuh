@@ -269,7 +269,7 @@ __device__ __forceinline__ BranchSample sample_branch(
     int d, const double *Q, const double *R, const double *tab, int size, int steady, double mu,
     double t0, double t1, int a, int b, int forced, const double *u, long long nU,
     long long &pos, double *buf, const uint16_t *rc, double *sTimes, uint8_t *sTypes,
-    double *gTimes, uint8_t *gTypes, int scratchCap, int lane)
+    double *gTimes, uint8_t *gTypes, int scratchCap, int lane, int stageCap = U_TCAP)
 {
     const int dd = d * d;
     const int steadyN = steady ? size : -1;                          // RpowSteadyN :460-473
@@ -340,7 +340,7 @@ __device__ __forceinline__ BranchSample sample_branch(
         st = MTT_ST_NEED_MORE_UNIFORMS;
     double *times = sTimes;
     uint8_t *types = sTypes;
-    if (st == MTT_ST_OK && nVirt > U_TCAP) {
+    if (st == MTT_ST_OK && nVirt > stageCap) {
         if (nVirt > scratchCap) {
             st = MTT_ST_NEED_MORE_POWERS;   // host grows the scratch along with the table
         } else {

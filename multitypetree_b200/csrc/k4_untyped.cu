@@ -30,13 +30,17 @@
 namespace {
 
 constexpr int P_WARPS = 4;           // warps (particles) per CTA
-constexpr int P_ECAP = 1024;         // events of one typed tree (nodes + migrations)
-constexpr int P_NCAP = 1024;         // nodes of one tree
+constexpr int P_ECAP = 1024;         // most events of one typed tree (nodes + migrations)
+constexpr int P_NCAP = 1024;         // most nodes of one tree
+// The stage of a warp is sized per call (eCap events, tCap virtual events per lineage, nCap
+// nodes) so that small trees leave room for more resident warps; a particle that outgrows it
+// reports MTT_ST_SKIPPED / MTT_ST_NEED_MORE_POWERS and the host relaunches with a larger stage.
 enum { PK_SAMPLE = 0, PK_COALESCE = 1, PK_MIGRATE = 2 };
 
 struct ParticleParams {
     long long nTrees;
     int nParticles, d, powCap;
+    int eCap, tCap, nCap;            // stage capacities (multiples of 8)
     const double *Q, *R, *mu, *pow;
     const int *meta;
     const int *model;                // per tree
@@ -54,11 +58,13 @@ struct ParticleParams {
     long long *uUsed;
 };
 
-__host__ __device__ __forceinline__ size_t particle_smem_doubles(int d)
+__host__ __device__ __forceinline__ size_t particle_smem_doubles(int d, int eCap, int tCap,
+                                                                int nCap)
 {
-    return (size_t)8 * d * d + U_TCAP + U_TCAP / 8 + P_ECAP /* evTime */ +
-           P_ECAP / 4 /* ord u16 */ + P_ECAP / 4 /* evDesc u16 */ + P_NCAP / 8 /* nodeType */ +
-           32 * MTT_MAX_DEMES / 2 /* per-lane counts, int */ + 2 * MTT_MAX_DEMES /* N, muOut */;
+    const int dPad = (d + 1) & ~1;
+    return (size_t)8 * d * d + tCap + tCap / 8 + eCap /* evTime */ + eCap / 4 /* ord u16 */ +
+           eCap / 4 /* evDesc u16 */ + nCap / 8 /* nodeType */ +
+           32 * dPad / 2 /* per-lane counts, int */ + 2 * dPad /* N, muOut */;
 }
 
 __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParams p)
@@ -73,17 +79,17 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
     uint16_t *rc = rcAll[warp];
     fill_rc(rc, d, lane);
 
-    double *buf = sm + (size_t)warp * particle_smem_doubles(d);
+    const int eCap = p.eCap, tCap = p.tCap, nCap = p.nCap, dPad = (d + 1) & ~1;
+    double *buf = sm + (size_t)warp * particle_smem_doubles(d, eCap, tCap, nCap);
     double *sTimes = buf + 8 * dd;
-    uint8_t *sTypes = reinterpret_cast<uint8_t *>(sTimes + U_TCAP);
-    double *evTime = sTimes + U_TCAP + U_TCAP / 8;
-    uint16_t *ord = reinterpret_cast<uint16_t *>(evTime + P_ECAP);
-    uint16_t *evDesc = ord + P_ECAP;
-    int8_t *nodeType = reinterpret_cast<int8_t *>(evDesc + P_ECAP);
-    int *cnt = reinterpret_cast<int *>(nodeType + P_NCAP) + lane * MTT_MAX_DEMES;
-    double *sN = reinterpret_cast<double *>(reinterpret_cast<int *>(nodeType + P_NCAP) +
-                                            32 * MTT_MAX_DEMES);
-    double *sMuOut = sN + MTT_MAX_DEMES;
+    uint8_t *sTypes = reinterpret_cast<uint8_t *>(sTimes + tCap);
+    double *evTime = sTimes + tCap + tCap / 8;
+    uint16_t *ord = reinterpret_cast<uint16_t *>(evTime + eCap);
+    uint16_t *evDesc = ord + eCap;
+    int8_t *nodeType = reinterpret_cast<int8_t *>(evDesc + eCap);
+    int *cnt = reinterpret_cast<int *>(nodeType + nCap) + lane * dPad;
+    double *sN = reinterpret_cast<double *>(reinterpret_cast<int *>(nodeType + nCap) + 32 * dPad);
+    double *sMuOut = sN + dPad;
 
     const long long tree = q / p.nParticles;
     const int part = (int)(q - tree * p.nParticles);
@@ -118,7 +124,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
     double w = 0.0;
     // every lane runs the same scalar control flow; lane 0 owns the shared-memory writes
     auto emit = [&](int kind, int type, int dest, double time) {
-        if (lane == 0 && nEv < P_ECAP) {
+        if (lane == 0 && nEv < eCap) {
             evTime[nEv] = time;
             evDesc[nEv] = (uint16_t)(kind << 8 | type << 4 | dest);
         }
@@ -192,7 +198,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
         const int b = nodeType[anc];
         const BranchSample bs = sample_branch<true>(d, Q, R, tab, size, steady, mu, t0, t1, a, b,
                                                     -1, u, nU, pos, buf, rc, sTimes, sTypes,
-                                                    nullptr, nullptr, 0, lane);
+                                                    nullptr, nullptr, 0, lane, tCap);
         if (bs.st == MTT_ST_NEED_MORE_UNIFORMS || bs.st == MTT_ST_NEED_MORE_POWERS) {
             st = bs.st;
             break;
@@ -238,7 +244,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
         w = sub_rn(w, lp);                                                       // :136
         __syncwarp();
     }
-    if (st == MTT_ST_OK && nEv > P_ECAP)
+    if (st == MTT_ST_OK && nEv > eCap)
         st = MTT_ST_SKIPPED;             // more events than the stage holds (host reports it)
 
     double total = 0.0;
@@ -383,8 +389,10 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
     std::vector<int32_t> hModel(nTrees, 0);
     std::vector<long long> hOrderOff(nTrees + 1, 0);
     double maxMuL = 0.0;
+    int64_t maxNodes = 0;
     for (int64_t t = 0; t < nTrees; t++) {
         const int64_t n0 = nodeOff[t], n = nodeOff[t + 1] - n0;
+        maxNodes = n > maxNodes ? n : maxNodes;
         if (n < 3 || (n & 1) == 0 || n > P_NCAP)
             return mtt_fail(ctx, MTT_ERR_TOO_LARGE,
                             "untyped density: tree %lld has %lld nodes (supported: odd, 3..%d)",
@@ -441,17 +449,27 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
     MTT_CUDA(ctx, cudaMemcpyAsync(dU, uniforms, nU * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dUOff, uOff, (nPart + 1) * 8, cudaMemcpyHostToDevice, s));
 
-    const size_t smem = (size_t)P_WARPS * particle_smem_doubles(d) * 8;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k4_particles, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+    // stage capacities: start from the tree size / the expected number of virtual events and
+    // grow on demand
+    int nCap = 8 * (int)((maxNodes + 7) / 8);
+    int eCap = 64;
+    while (eCap < 2 * maxNodes && eCap < P_ECAP)
+        eCap <<= 1;
+    int tCap = 32;
+    while (tCap < K && tCap < U_TCAP)
+        tCap <<= 1;
     const unsigned blocks = (unsigned)((nPart + P_WARPS - 1) / P_WARPS);
     std::vector<int32_t> hSt(nPart);
     for (int attempt = 0;; attempt++) {
         int rc = mtt_unif_ensure_powers(ctx, K);
         if (rc != MTT_OK)
             return rc;
+        const size_t smem = (size_t)P_WARPS * particle_smem_doubles(d, eCap, tCap, nCap) * 8;
+        MTT_CUDA(ctx, cudaFuncSetAttribute(k4_particles,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         ParticleParams p;
         p.nTrees = nTrees; p.nParticles = nParticles; p.d = d; p.powCap = ctx->unifPowCap;
+        p.eCap = eCap; p.tCap = tCap; p.nCap = nCap;
         p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
         p.mu = (const double *)ctx->bufs[BUF_U_MU].p;
         p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
@@ -463,22 +481,27 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         MTT_CHECK_LAUNCH(ctx);
         MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dStatus, nPart * 4, cudaMemcpyDeviceToHost, s));
         MTT_CUDA(ctx, cudaStreamSynchronize(s));
-        bool more = false;
+        bool morePow = false, moreEv = false;
         for (int64_t i = 0; i < nPart; i++) {
-            if (hSt[i] == MTT_ST_NEED_MORE_POWERS)
-                more = true;
-            if (hSt[i] == MTT_ST_SKIPPED)
-                return mtt_fail(ctx, MTT_ERR_TOO_LARGE,
-                                "untyped density: particle %lld needs more than %d events",
-                                (long long)i, P_ECAP);
+            morePow |= hSt[i] == MTT_ST_NEED_MORE_POWERS;
+            moreEv |= hSt[i] == MTT_ST_SKIPPED;
         }
-        if (!more)
+        if (!morePow && !moreEv)
             break;
-        if (K >= U_TCAP || attempt >= 8)
+        if ((moreEv && eCap >= P_ECAP) || attempt >= 12)
+            return mtt_fail(ctx, MTT_ERR_TOO_LARGE,
+                            "untyped density: a particle needs more than %d events", P_ECAP);
+        if (morePow && K >= U_TCAP && tCap >= U_TCAP)
             return mtt_fail(ctx, MTT_ERR_TOO_LARGE,
                             "untyped density: a lineage needs more than %d virtual events",
                             U_TCAP);
-        K = (2 * K + 64 > U_TCAP) ? U_TCAP : 2 * K + 64;
+        if (moreEv)
+            eCap <<= 1;
+        if (morePow) {              // the R^k table or the virtual-event stage was too short
+            K = (2 * K + 64 > U_TCAP) ? U_TCAP : 2 * K + 64;
+            while (tCap < K && tCap < U_TCAP)
+                tCap <<= 1;
+        }
     }
     k4_combine<<<(unsigned)((nTrees + 3) / 4), 128, 0, s>>>(nTrees, nParticles, dLogW, dLogP);
     MTT_CHECK_LAUNCH(ctx);

@@ -57,7 +57,8 @@ def _inputs(trees, P, win, seed):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("d,n,scale", [(2, 8, 1.0), (2, 40, 1.0), (3, 25, 0.5), (4, 60, 2.0),
-                                       (10, 30, 1.0), (16, 12, 1.0)])
+                                       (10, 30, 1.0), (16, 12, 1.0),
+                                       (2, 10, 30.0)])     # many migrations: the stage grows
 def test_particles_match_oracle(ctx, d, n, scale):
     """Every particle: same log weight (1e-9), same number of uniforms consumed -- i.e. the
     same sampled typing -- and the combined estimate, for random trees and models."""

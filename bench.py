@@ -554,6 +554,7 @@ def bench_retype(args):
     W = 256
     u = rng.random(nJobs * W)
     uOff = np.arange(nJobs + 1) * W
+    pinned = mtt.lib().mtt_host_register(u.ctypes.data, u.nbytes) == 0
     for _ in range(args.warmup):
         r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=32, model=model)
     barrier(world)
@@ -572,7 +573,8 @@ def bench_retype(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
         "config": {"workload": "cfg5: %d chains x %d NodeRetype-shaped jobs (3 branches), d=10"
-                               % (chains * world, jobs_per_chain)},
+                               % (chains * world, jobs_per_chain), "uniform_window": W,
+                   "pinned": bool(pinned)},
         "ok_fraction": float((r["status"] == 0).mean()),
         "gpu_launches": int(ctx.launch_count() - l0)}))
 

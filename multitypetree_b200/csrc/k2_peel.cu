@@ -115,7 +115,7 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
-           int *info, int *maxSlotsAll)
+           int *info, int *maxSlotsAll, int xl)
 {
     extern __shared__ int smi[];
     const int N = 2 * n - 1, nOps = n - 1;
@@ -298,9 +298,17 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         }
         // internal child: row-major P[i][j] (row = parent state) for the mat-vec; tip child:
         // TRANSPOSED, so that the column of the observed state is 4 contiguous doubles
+        // xl (categories across lanes): the 8 double2 of the C matrices of one child are
+        // interleaved, [pair][category], so that the lanes of a pattern read adjacent 16-byte
+        // words
         const bool tip = child < n;
-        for (int e = 0; e < 16; e++)
-            M[e] = tip ? T[(e & 3) * 4 + (e >> 2)] : T[e];
+        for (int e = 0; e < 16; e++) {
+            const double v = tip ? T[(e & 3) * 4 + (e >> 2)] : T[e];
+            if (xl)
+                mats[(size_t)(k * 2 + j) * C * 16 + ((size_t)(e >> 1) * C + c) * 2 + (e & 1)] = v;
+            else
+                M[e] = v;
+        }
     }
     __syncthreads();
     if (tid == 0) {
@@ -325,7 +333,9 @@ struct PeelCfg {
 // one child's contribution for PPT patterns of one category:
 //   a[u][i] = sum_j M[i][j] x[u][j]      (internal child; x from registers or its slot)
 //   a[u][i] = M[i][state_u] or 1         (tip child)
-template <int PPT>
+// MS = distance in doubles between consecutive double2 of the matrix (2, or 2 C when the
+// categories' matrices are interleaved).
+template <int PPT, int MS>
 __device__ __forceinline__ void child_term(bool isTip, const double *M, const double (&x)[PPT][4],
                                            const int (&tip)[PPT], double (&a)[PPT][4])
 {
@@ -334,9 +344,9 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
 #pragma unroll
         for (int u = 0; u < PPT; u++) {
             const bool known = tip[u] < 4;                          // gap / ambiguity: unknown
-            const double *col = M + (known ? tip[u] * 4 : 0);
+            const double *col = M + (known ? tip[u] * 2 * MS : 0);
             const double2 c01 = *reinterpret_cast<const double2 *>(col);
-            const double2 c23 = *reinterpret_cast<const double2 *>(col + 2);
+            const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
             a[u][0] = known ? c01.x : 1.0;
             a[u][1] = known ? c01.y : 1.0;
             a[u][2] = known ? c23.x : 1.0;
@@ -345,8 +355,8 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
     } else {
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 4);
-            const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 4 + 2);
+            const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 2 * MS);
+            const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 2 * MS + MS);
 #pragma unroll
             for (int u = 0; u < PPT; u++) {
                 double s = m01.x * x[u][0];
@@ -359,9 +369,20 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
     }
 }
 
-// TPT threads per CTA, PPT patterns per thread: a tile is TPT * PPT patterns
-// (pattern of (thread, u) = tile * TPT * PPT + u * TPT + tid, so global reads stay coalesced)
-template <int C, int TPT, int PPT>
+// rate categories across lanes: C = 2, 4, 8
+__host__ __device__ constexpr bool cats_across_lanes(int C)
+{
+    return C == 2 || C == 4 || C == 8;
+}
+
+// TPT threads per CTA, PPT patterns per thread.
+// XL = false: a thread owns all C categories of its patterns; a tile is TPT * PPT patterns
+//   (pattern of (thread, u) = tile * TPT * PPT + u * TPT + tid, so global reads stay coalesced).
+// XL = true (C = 2, 4, 8): the C categories of a pattern sit in C adjacent lanes, each thread
+//   carries ONE category -- the register and shared-memory footprint of the C = 1 kernel, so
+//   residency does not collapse with the category count; a tile is (TPT / C) * PPT patterns.
+//   The per-pattern rescaling maximum and the root sum over categories are lane-group shuffles.
+template <int C, int TPT, int PPT, bool XL>
 __global__ void __launch_bounds__(TPT)
 k2_peel(int n, long long P, long long pStride, const uint8_t *states, const double *weights,
         const uint8_t *constMask, const double *site, double pInv, const PeelOp *opsAll,
@@ -376,10 +397,15 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     double *stackBase = reinterpret_cast<double *>(smem + 2 * Cfg::STAGE_BYTES + 16);
     __shared__ double red[(TPT + 31) / 32];
 
+    constexpr int CR = XL ? 1 : C;            // categories held per thread
+    constexpr int LPP = XL ? C : 1;           // lanes per pattern
+    constexpr int TPP = TPT / LPP;            // patterns per u-slice of the tile
+    constexpr int MS = XL ? 2 * C : 2;        // double2 stride inside a staged matrix
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int cat = XL ? (tid & (C - 1)) : 0;
     const int tile = blockIdx.x, b = blockIdx.y;
     const int nOps = n - 1;
-    const long long p0 = (long long)tile * TPT * PPT + tid;   // + u * TPT; < pStride
+    const long long p0 = (long long)tile * TPP * PPT + tid / LPP;   // + u * TPP; < pStride
     const PeelOp *ops = opsAll + (size_t)b * nOps;
     const double *mats = matsAll + (size_t)b * nOps * Cfg::MAT_DOUBLES_PER_OP;
     const int treeInfo = info[b];
@@ -389,8 +415,8 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             partial[(size_t)b * nTiles + tile] = NAN;
         if (patternLogL)
             for (int u = 0; u < PPT; u++)
-                if (p0 + u * TPT < P)
-                    patternLogL[p0 + u * TPT] = NAN;
+                if (p0 + u * TPP < P)
+                    patternLogL[p0 + u * TPP] = NAN;
         return;
     }
     if (tid == 0) {
@@ -420,23 +446,23 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             const uint8_t *row = states + (size_t)(-op.c1 - 1) * pStride + p0;
 #pragma unroll
             for (int u = 0; u < PPT; u++)
-                t1[u] = __ldg(row + u * TPT);
+                t1[u] = __ldg(row + u * TPP);
         }
         if (op.c2 < 0) {
             const uint8_t *row = states + (size_t)(-op.c2 - 1) * pStride + p0;
 #pragma unroll
             for (int u = 0; u < PPT; u++)
-                t2[u] = __ldg(row + u * TPT);
+                t2[u] = __ldg(row + u * TPP);
         }
     };
 
-    double prev[PPT][C][4];          // result of the previous op (top of the stack, in registers)
+    double prev[PPT][CR][4];         // result of the previous op (top of the stack, in registers)
     double logScale[PPT];
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
         logScale[u] = 0.0;
 #pragma unroll
-        for (int c = 0; c < C; c++)
+        for (int c = 0; c < CR; c++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
                 prev[u][c][i] = 1.0;
@@ -467,14 +493,15 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             }
             if (k + 1 < cnt)
                 load_tips(sOps[k + 1], nt1, nt2);
-            double nw[PPT][C][4];
+            double nw[PPT][CR][4];
             int mxhi[PPT];       // partials are >= 0: their order is the order of the high words
 #pragma unroll
             for (int u = 0; u < PPT; u++)
                 mxhi[u] = 0;
 #pragma unroll
-            for (int c = 0; c < C; c++) {
-                const double *M1 = sMats + (size_t)k * Cfg::MAT_DOUBLES_PER_OP + c * 16;
+            for (int c = 0; c < CR; c++) {
+                const double *M1 = sMats + (size_t)k * Cfg::MAT_DOUBLES_PER_OP +
+                                   (XL ? cat * 2 : c * 16);
                 const double *M2 = M1 + C * 16;
                 double x[PPT][4], a[PPT][4], bb[PPT][4];
                 // child 1
@@ -486,7 +513,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                             for (int i = 0; i < 4; i++)
                                 x[u][i] = prev[u][c][i];
                     } else {
-                        const double *src = stackBase + ((size_t)(op.c1 * C + c) * 4) * PPT * TPT + tid;
+                        const double *src = stackBase + ((size_t)(op.c1 * CR + c) * 4) * PPT * TPT + tid;
 #pragma unroll
                         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -494,7 +521,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                                 x[u][i] = src[(i * PPT + u) * TPT];
                     }
                 }
-                child_term<PPT>(op.c1 < 0, M1, x, t1, a);
+                child_term<PPT, MS>(op.c1 < 0, M1, x, t1, a);
                 // child 2
                 if (op.c2 >= 0) {
                     if (op.flags & OP_C2_PREV) {
@@ -504,7 +531,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                             for (int i = 0; i < 4; i++)
                                 x[u][i] = prev[u][c][i];
                     } else {
-                        const double *src = stackBase + ((size_t)(op.c2 * C + c) * 4) * PPT * TPT + tid;
+                        const double *src = stackBase + ((size_t)(op.c2 * CR + c) * 4) * PPT * TPT + tid;
 #pragma unroll
                         for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -512,7 +539,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                                 x[u][i] = src[(i * PPT + u) * TPT];
                     }
                 }
-                child_term<PPT>(op.c2 < 0, M2, x, t2, bb);
+                child_term<PPT, MS>(op.c2 < 0, M2, x, t2, bb);
 #pragma unroll
                 for (int u = 0; u < PPT; u++)
 #pragma unroll
@@ -526,16 +553,29 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             // on the high word is conservative; the exact maximum is formed only when needed.
 #pragma unroll
             for (int u = 0; u < PPT; u++) {
-                if (mxhi[u] <= __double2hiint(SCALING_THRESHOLD)) {
+                if (XL) {
+                    // maximum over the pattern's categories = over its lane group
+#pragma unroll
+                    for (int o = 1; o < LPP; o <<= 1)
+                        mxhi[u] = max(mxhi[u], __shfl_xor_sync(FULL_MASK, mxhi[u], o));
+                }
+                const bool low = mxhi[u] <= __double2hiint(SCALING_THRESHOLD);
+                // (the shuffles below need the whole warp: the branch is taken warp-wide)
+                if (XL ? __any_sync(FULL_MASK, low) : low) {
                     double mx = 0.0;
 #pragma unroll
-                    for (int c = 0; c < C; c++)
+                    for (int c = 0; c < CR; c++)
 #pragma unroll
                         for (int i = 0; i < 4; i++)
                             mx = fmax(mx, nw[u][c][i]);
-                    if (mx < SCALING_THRESHOLD) {
+                    if (XL) {
 #pragma unroll
-                        for (int c = 0; c < C; c++)
+                        for (int o = 1; o < LPP; o <<= 1)
+                            mx = fmax(mx, __shfl_xor_sync(FULL_MASK, mx, o));
+                    }
+                    if (low && mx < SCALING_THRESHOLD) {
+#pragma unroll
+                        for (int c = 0; c < CR; c++)
 #pragma unroll
                             for (int i = 0; i < 4; i++)
                                 nw[u][c][i] /= mx;
@@ -546,14 +586,14 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
 #pragma unroll
             for (int u = 0; u < PPT; u++)
 #pragma unroll
-                for (int c = 0; c < C; c++)
+                for (int c = 0; c < CR; c++)
 #pragma unroll
                     for (int i = 0; i < 4; i++)
                         prev[u][c][i] = nw[u][c][i];
             if (op.flags & OP_STORE) {
-                double *dst = stackBase + ((size_t)(op.dst * C) * 4) * PPT * TPT + tid;
+                double *dst = stackBase + ((size_t)(op.dst * CR) * 4) * PPT * TPT + tid;
 #pragma unroll
-                for (int c = 0; c < C; c++)
+                for (int c = 0; c < CR; c++)
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
@@ -569,14 +609,25 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     double contrib = 0.0;
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
-        const long long p = p0 + u * TPT;
+        const long long p = p0 + u * TPP;
         double root[4];
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-            double r = prev[u][0][i] * catProps[0];
+            double r;
+            if (XL) {
+                // sum over the lane group in category order 0, 1, .., C-1
+                const double mine = prev[u][0][i] * catProps[cat];
+                const int base = lane & ~(LPP - 1);
+                r = __shfl_sync(FULL_MASK, mine, base);
 #pragma unroll
-            for (int c = 1; c < C; c++)
-                r += prev[u][c][i] * catProps[c];
+                for (int c = 1; c < LPP; c++)
+                    r += __shfl_sync(FULL_MASK, mine, base + c);
+            } else {
+                r = prev[u][0][i] * catProps[0];
+#pragma unroll
+                for (int c = 1; c < CR; c++)
+                    r += prev[u][c][i] * catProps[c];
+            }
             root[i] = r;
         }
         if (pInv > 0.0) {
@@ -591,9 +642,9 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
         for (int i = 0; i < 4; i++)
             sum += freqs[i] * root[i];
         const double ll = log(sum) + logScale[u];
-        if (patternLogL && p < P)
+        if (patternLogL && p < P && cat == 0)
             patternLogL[p] = ll;
-        if (p < P)
+        if (p < P && cat == 0)
             contrib += ll * weights[p];
     }
     contrib = warp_sum_down(contrib);
@@ -660,9 +711,11 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
 {
     mtt_ctx *ctx = h->ctx;
     using Cfg = PeelCfg<C>;
-    const int nTiles = (int)(h->pStride / (TPT * PPT));
-    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * PPT * TPT * 8;
-    auto kern = k2_peel<C, TPT, PPT>;
+    constexpr bool XL = cats_across_lanes(C);
+    constexpr int CR = XL ? 1 : C;
+    const int nTiles = (int)(h->pStride / ((TPT / (XL ? C : 1)) * PPT));
+    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * CR * 4 * PPT * TPT * 8;
+    auto kern = k2_peel<C, TPT, PPT, XL>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     dim3 grid((unsigned)nTiles, (unsigned)B);
@@ -680,27 +733,30 @@ template <int C>
 int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *patternLogL)
 {
     using Cfg = PeelCfg<C>;
+    constexpr int LPP = cats_across_lanes(C) ? C : 1;      // lanes per pattern
+    constexpr int CR = cats_across_lanes(C) ? 1 : C;       // categories per thread
+    constexpr int MAXPPT = cats_across_lanes(C) ? 2 : Cfg::MAX_PPT;
     auto need = [&](int t, int ppt) {
-        return 2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * C * 4 * ppt * t * 8;
+        return 2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * CR * 4 * ppt * t * 8;
     };
     const size_t budget = 110 * 1024;
-    if (Cfg::MAX_PPT == 2 && need(128, 2) <= budget) {
-        *nTilesOut = (int)(h->pStride / 256);
-        return launch_peel_t<C, 128, Cfg::MAX_PPT>(h, B, nSlots, patternLogL);
+    if (MAXPPT == 2 && need(128, 2) <= budget) {
+        *nTilesOut = (int)(h->pStride / (256 / LPP));
+        return launch_peel_t<C, 128, MAXPPT>(h, B, nSlots, patternLogL);
     }
     if (need(128, 1) <= budget) {
-        *nTilesOut = (int)(h->pStride / 128);
+        *nTilesOut = (int)(h->pStride / (128 / LPP));
         return launch_peel_t<C, 128, 1>(h, B, nSlots, patternLogL);
     }
     if (need(64, 1) <= budget) {
-        *nTilesOut = (int)(h->pStride / 64);
+        *nTilesOut = (int)(h->pStride / (64 / LPP));
         return launch_peel_t<C, 64, 1>(h, B, nSlots, patternLogL);
     }
     if (need(32, 1) > 227 * 1024)
         return mtt_fail(h->ctx, MTT_ERR_TOO_LARGE,
                         "peeling: %d parked partial vectors x %d categories exceed shared memory",
                         nSlots, C);
-    *nTilesOut = (int)(h->pStride / 32);
+    *nTilesOut = (int)(h->pStride / (32 / LPP));
     return launch_peel_t<C, 32, 1>(h, B, nSlots, patternLogL);
 }
 
@@ -710,7 +766,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
 {
     mtt_ctx *ctx = h->ctx;
     const int n = h->nTips, C = h->nCat, N = 2 * n - 1, nOps = n - 1;
-    const int maxTiles = (int)(h->pStride / 32);
+    const int maxTiles = (int)(h->pStride / 4);     // smallest tile: 32 threads / 8 categories
     int nTiles = 0;
     int rc;
     if ((rc = grow(ctx, h->dOps, h->opsCap, (size_t)B * nOps * sizeof(PeelOp))) != MTT_OK)
@@ -734,7 +790,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
     MTT_CUDA(ctx, cudaMemsetAsync(h->dMaxSlots, 0, sizeof(int), ctx->stream));
     k2_prepare<<<(unsigned)B, PREP_THREADS, prepSmem, ctx->stream>>>(
         n, C, dParent, dHeight, dMatsIn, h->dSite, h->branchRate, h->kappa, (PeelOp *)h->dOps,
-        h->dMats, h->dInfo, h->dMaxSlots);
+        h->dMats, h->dInfo, h->dMaxSlots, cats_across_lanes(C) ? 1 : 0);
     MTT_CHECK_LAUNCH(ctx);
     // the number of parked partial vectors sizes the peel kernel's shared memory (a few for
     // coalescent-shaped trees, up to floor(log2 n) for balanced ones): read it back

@@ -203,6 +203,7 @@ struct RetypeParams {
     double *scratchT;        // [warps][scratchCap] spill for nVirt > U_TCAP
     uint8_t *scratchTy;
     int scratchCap;
+    int tCap;                // virtual events kept in shared memory per warp (<= U_TCAP)
 };
 
 __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
@@ -216,10 +217,10 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
     __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
     uint16_t *rc = rcAll[threadIdx.x >> 5];
     fill_rc(rc, d, threadIdx.x & 31);
-    const size_t perWarp = (size_t)8 * dd + U_TCAP + U_TCAP / 8;
+    const size_t perWarp = (size_t)8 * dd + p.tCap + p.tCap / 8;
     double *buf = sm + (size_t)warp * perWarp;
     double *sTimes = buf + 8 * dd;
-    uint8_t *sTypes = reinterpret_cast<uint8_t *>(sTimes + U_TCAP);
+    uint8_t *sTypes = reinterpret_cast<uint8_t *>(sTimes + p.tCap);
 
     const double *u = p.uniforms + p.uOff[job];
     const long long nU = p.uOff[job + 1] - p.uOff[job];
@@ -245,7 +246,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
             d, Q, R, p.pow + (size_t)mdl * p.powCap * dd, p.meta[2 * mdl], p.meta[2 * mdl + 1],
             p.mu[mdl], t0, t1, a, b, p.nVirtForced ? p.nVirtForced[br] : -1, u, nU, pos, buf, rc,
             sTimes, sTypes, p.scratchT + w * p.scratchCap, p.scratchTy + w * p.scratchCap,
-            p.scratchCap, lane);
+            p.scratchCap, lane, p.tCap);
         int st = bs.st, nChg = 0;
         const int nVirt = bs.nVirt;
         const double Pba = bs.Pba;
@@ -596,14 +597,19 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         MTT_CUDA(ctx, cudaMemcpyAsync(dForced, nVirtForced, nBr * 4, cudaMemcpyHostToDevice, s));
 
     const unsigned blocks = (unsigned)((nJobs + U_WARPS - 1) / U_WARPS);
-    const size_t smem = (size_t)U_WARPS * (8 * dd + U_TCAP + U_TCAP / 8) * 8;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_retype, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
     std::vector<int32_t> hSt(nBr);
     for (int attempt = 0; attempt < 12; attempt++) {
         int rc = ensure_powers(ctx, K);
         if (rc != MTT_OK)
             return rc;
+        // shared-memory stage sized for the expected number of virtual events (more resident
+        // warps for short branches); longer draws use the global scratch below
+        int tCap = 32;
+        while (tCap < K && tCap < U_TCAP)
+            tCap <<= 1;
+        const size_t smem = (size_t)U_WARPS * (8 * dd + tCap + tCap / 8) * 8;
+        MTT_CUDA(ctx, cudaFuncSetAttribute(k3_retype, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
         int scratchCap = 0;
         double *scrT = nullptr;
         uint8_t *scrTy = nullptr;
@@ -623,7 +629,7 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         p.typeTop = dB; p.nVirtForced = dForced; p.uniforms = dU; p.uOff = dUOff;
         p.nChg = dNChg; p.outChgTime = dOCT; p.outChgType = dOCTy; p.logProb = dLP;
         p.status = dSt; p.nVirt = dNVirt; p.uUsed = dUsed;
-        p.scratchT = scrT; p.scratchTy = scrTy; p.scratchCap = scratchCap;
+        p.scratchT = scrT; p.scratchTy = scrTy; p.scratchCap = scratchCap; p.tCap = tCap;
         k3_retype<<<blocks, U_WARPS * 32, smem, s>>>(p);
         MTT_CHECK_LAUNCH(ctx);
         MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dSt, nBr * 4, cudaMemcpyDeviceToHost, s));

@@ -7,8 +7,9 @@
 // then walks it.  Here the flattened tree (height / nodeType / chgCount / chgTime / chgType,
 // include/mtt_b200.h) is turned into events, ordered and scanned inside one kernel:
 //
-//   k1_density_warp   one WARP per tree (E = nodes + changes <= 512).  Persistent warps, 24
-//                     resident per SM; lane 0 stages the tree's five array slices into the
+//   k1_density_warp   one WARP per tree (E = nodes + changes <= 512).  Persistent warps, 32
+//                     resident per SM when the batch's trees have <= 384 events (24 in the
+//                     512-event stage); lane 0 stages the tree's five array slices into the
 //                     warp's shared-memory stage with 1-D bulk async copies (TMA engine,
 //                     mbarrier completion).  Events are ordered by a register-resident bitonic
 //                     network over packed 32-bit keys (23-bit quantised time | 9-bit event

@@ -8,7 +8,6 @@ Inputs keep the reference's names: ``migrationModel``, ``nParticles``, ``typeLab
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Optional, Sequence
 
 import numpy as np

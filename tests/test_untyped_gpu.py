@@ -84,6 +84,34 @@ def test_particles_match_oracle(ctx, d, n, scale):
 
 
 @pytest.mark.gpu
+def test_per_tree_models_and_size_limit(ctx):
+    """model[] selects the migration model per tree; a tree beyond the documented node limit is
+    refused loudly (MTT_ERR_TOO_LARGE), never truncated."""
+    d = 3
+    m0, N = mtt.synthetic_model(d)
+    ms = np.stack([m0, 0.3 * m0])
+    Ns = np.stack([N, 2.0 * N])
+    trees = [mtt.simulate_trees(2, 15, d, m0, N, seed=40).tree(b) for b in range(2)]
+    P, win = 5, 2048
+    orders, u, uOff = _inputs(trees, P, win, 9)
+    um = UniformizationModels(ms, ctx=ctx)
+    r = untyped_logp_batch(um, Ns, trees, P, np.concatenate(orders), u, uOff, model=[1, 0],
+                           ctx=ctx)
+    for b, t in enumerate(trees):
+        mdl = [1, 0][b]
+        o = orc.UnifModel(ms[mdl])
+        for p in range(P):
+            q = b * P + p
+            ro = orc.untyped_particle(o, Ns[mdl], t.parent, t.height, t.nodeType, orders[q],
+                                      u[uOff[q]:uOff[q + 1]])
+            assert r["logW"][b, p] == pytest.approx(ro["logW"], rel=1e-9, abs=1e-9)
+    big = mtt.simulate_trees(1, 600, d, m0, N, seed=41).tree(0)          # 1199 nodes > 1024
+    orders, u, uOff = _inputs([big], 1, 64, 2)
+    with pytest.raises(mtt.MttError, match="nodes"):
+        untyped_logp_batch(um, Ns, [big], 1, np.concatenate(orders), u, uOff, ctx=ctx)
+
+
+@pytest.mark.gpu
 def test_window_too_short_is_reported(ctx):
     m, N = mtt.synthetic_model(2)
     t = mtt.simulate_trees(1, 30, 2, m, N, seed=4).tree(0)

@@ -364,7 +364,7 @@ def bench_peel(args):
                                                simulate_alignment)
     world, rank, local = dist_setup(args.gpus)
     cores = os.cpu_count() or 1
-    n, d, sites, B = 1000, 4, 10000, args.batch if args.batch != (1 << 19) else 64
+    n, d, sites, B = 1000, 4, 10000, args.batch if args.batch != (1 << 19) else 512
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(B, n, d, m, N, seed=3000 + rank * B, nThreads=max(1, cores // world))
     nN = 2 * n - 1
@@ -419,7 +419,7 @@ def bench_peel(args):
     if rank != 0:
         return
     from oracle import oracle as orc
-    k = min(B, 8)
+    k = min(B, 64)          # ~20 CPU-seconds of the restated BeerLikelihoodCore
     t0 = time.perf_counter()
     want = orc.tree_likelihood_batch(al.patterns, al.patternWeight, par[:k], hgt[:k], [clock], [1.0],
                                      f, 2.0, nThreads=min(cores, k))

@@ -26,6 +26,7 @@
 #include "mtt_common.cuh"
 
 #include <math.h>
+#include <stdlib.h>
 
 #include <algorithm>
 #include <vector>
@@ -65,7 +66,7 @@ struct PeelOp {
     int flags;      // bit 0 / 1: child 1 / 2 is the result of the previous op (still in
                     // registers); bit 2: this result must be parked in its slot
 };
-constexpr int OP_C1_PREV = 1, OP_C2_PREV = 2, OP_STORE = 4;
+constexpr int OP_C1_PREV = 1, OP_STORE = 4;
 
 // ---- HKY.getTransitionProbabilities [EXT] (closed form) ---------------
 __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double distance,
@@ -259,10 +260,14 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         const int c2 = rightFirst ? left[v] : right[v];
         PeelOp op;
         // post-order: an internal second child is always the previous op; an internal first
-        // child is the previous op when the second child is a tip; otherwise it was parked
-        op.flags = (c2 >= n) ? OP_C2_PREV : ((c1 >= n) ? OP_C1_PREV : 0);
-        op.c1 = (c1 < n) ? -(c1 + 1) : ((op.flags & OP_C1_PREV) ? 0 : (int)pd[v]);
-        op.c2 = (c2 < n) ? -(c2 + 1) : 0;
+        // child is the previous op when the second child is a tip; otherwise it was parked.
+        // The op lists the previous-op child (if any) as its child 1, so that the kernel reads
+        // child 1 from registers and child 2 from a tip row or a parked slot -- never both ways.
+        const bool swapKids = c2 >= n;
+        const int ka = swapKids ? c2 : c1, kb = swapKids ? c1 : c2;
+        op.flags = (ka >= n) ? OP_C1_PREV : 0;
+        op.c1 = (ka < n) ? -(ka + 1) : 0;
+        op.c2 = (kb < n) ? -(kb + 1) : (int)pd[v];
         op.dst = 0;
         if (v != root) {
             const int pp = parent[v];
@@ -283,7 +288,9 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         const int v = n + idx / (2 * C), j = (idx / C) & 1, c = idx % C;
         const int k = istart[v] + isize[v] - 1;
         const bool rightFirst = need[v] & 0x80;
-        const int child = (j == 0) == rightFirst ? right[v] : left[v];
+        const int first = rightFirst ? right[v] : left[v], second = rightFirst ? left[v] : right[v];
+        const bool swapKids = second >= n;                  // same rule as for the op above
+        const int child = ((j == 0) != swapKids) ? first : second;
         double *M = mats + ((size_t)(k * 2 + j) * C + c) * 16;
         double T[16];
         if (matsIn) {
@@ -340,17 +347,36 @@ __device__ __forceinline__ void child_term(bool isTip, const double *M, const do
                                            const int (&tip)[PPT], double (&a)[PPT][4])
 {
     if (isTip) {
-        // M is transposed for tip children: column of the observed state = M[4 s .. 4 s + 3]
+        // M is transposed for tip children: column of the observed state = M[4 s .. 4 s + 3].
+        // Gaps / ambiguity codes (state >= 4) contribute 1; a warp without any takes the
+        // select-free path (isTip is uniform over the CTA, so the vote is convergent).
+        bool unknown = false;
 #pragma unroll
-        for (int u = 0; u < PPT; u++) {
-            const bool known = tip[u] < 4;                          // gap / ambiguity: unknown
-            const double *col = M + (known ? tip[u] * 2 * MS : 0);
-            const double2 c01 = *reinterpret_cast<const double2 *>(col);
-            const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
-            a[u][0] = known ? c01.x : 1.0;
-            a[u][1] = known ? c01.y : 1.0;
-            a[u][2] = known ? c23.x : 1.0;
-            a[u][3] = known ? c23.y : 1.0;
+        for (int u = 0; u < PPT; u++)
+            unknown |= tip[u] >= 4;
+        if (!__any_sync(FULL_MASK, unknown)) {
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                const double *col = M + tip[u] * 2 * MS;
+                const double2 c01 = *reinterpret_cast<const double2 *>(col);
+                const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
+                a[u][0] = c01.x;
+                a[u][1] = c01.y;
+                a[u][2] = c23.x;
+                a[u][3] = c23.y;
+            }
+        } else {
+#pragma unroll
+            for (int u = 0; u < PPT; u++) {
+                const bool known = tip[u] < 4;                      // gap / ambiguity: unknown
+                const double *col = M + (known ? tip[u] * 2 * MS : 0);
+                const double2 c01 = *reinterpret_cast<const double2 *>(col);
+                const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
+                a[u][0] = known ? c01.x : 1.0;
+                a[u][1] = known ? c01.y : 1.0;
+                a[u][2] = known ? c23.x : 1.0;
+                a[u][3] = known ? c23.y : 1.0;
+            }
         }
     } else {
 #pragma unroll
@@ -456,7 +482,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
         }
     };
 
-    double prev[PPT][CR][4];         // result of the previous op (top of the stack, in registers)
+    double prev[CR][PPT][4];         // result of the previous op (top of the stack, in registers)
     double logScale[PPT];
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
@@ -465,7 +491,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
         for (int c = 0; c < CR; c++)
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                prev[u][c][i] = 1.0;
+                prev[c][u][i] = 1.0;
     }
     uint32_t phaseBits = 0;
     for (int s = 0; s < nStages; s++) {
@@ -493,7 +519,6 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             }
             if (k + 1 < cnt)
                 load_tips(sOps[k + 1], nt1, nt2);
-            double nw[PPT][CR][4];
             int mxhi[PPT];       // partials are >= 0: their order is the order of the high words
 #pragma unroll
             for (int u = 0; u < PPT; u++)
@@ -504,48 +529,24 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                                    (XL ? cat * 2 : c * 16);
                 const double *M2 = M1 + C * 16;
                 double x[PPT][4], a[PPT][4], bb[PPT][4];
-                // child 1
-                if (op.c1 >= 0) {
-                    if (op.flags & OP_C1_PREV) {
-#pragma unroll
-                        for (int u = 0; u < PPT; u++)
-#pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                x[u][i] = prev[u][c][i];
-                    } else {
-                        const double *src = stackBase + ((size_t)(op.c1 * CR + c) * 4) * PPT * TPT + tid;
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int u = 0; u < PPT; u++)
-                                x[u][i] = src[(i * PPT + u) * TPT];
-                    }
-                }
-                child_term<PPT, MS>(op.c1 < 0, M1, x, t1, a);
-                // child 2
+                // child 1: a tip, or the previous op's result (registers)
+                child_term<PPT, MS>(op.c1 < 0, M1, prev[c], t1, a);
+                // child 2: a tip, or a parked vector
                 if (op.c2 >= 0) {
-                    if (op.flags & OP_C2_PREV) {
+                    const double *src = stackBase + ((size_t)(op.c2 * CR + c) * 4) * PPT * TPT + tid;
+#pragma unroll
+                    for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int u = 0; u < PPT; u++)
-#pragma unroll
-                            for (int i = 0; i < 4; i++)
-                                x[u][i] = prev[u][c][i];
-                    } else {
-                        const double *src = stackBase + ((size_t)(op.c2 * CR + c) * 4) * PPT * TPT + tid;
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int u = 0; u < PPT; u++)
-                                x[u][i] = src[(i * PPT + u) * TPT];
-                    }
+                            x[u][i] = src[(i * PPT + u) * TPT];
                 }
                 child_term<PPT, MS>(op.c2 < 0, M2, x, t2, bb);
 #pragma unroll
                 for (int u = 0; u < PPT; u++)
 #pragma unroll
                     for (int i = 0; i < 4; i++) {
-                        nw[u][c][i] = a[u][i] * bb[u][i];
-                        mxhi[u] = max(mxhi[u], __double2hiint(nw[u][c][i]));
+                        prev[c][u][i] = a[u][i] * bb[u][i];
+                        mxhi[u] = max(mxhi[u], __double2hiint(prev[c][u][i]));
                     }
             }
             // BeerLikelihoodCore.scalePartials [EXT]: rescale when the largest partial of the
@@ -567,7 +568,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                     for (int c = 0; c < CR; c++)
 #pragma unroll
                         for (int i = 0; i < 4; i++)
-                            mx = fmax(mx, nw[u][c][i]);
+                            mx = fmax(mx, prev[c][u][i]);
                     if (XL) {
 #pragma unroll
                         for (int o = 1; o < LPP; o <<= 1)
@@ -578,18 +579,11 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                         for (int c = 0; c < CR; c++)
 #pragma unroll
                             for (int i = 0; i < 4; i++)
-                                nw[u][c][i] /= mx;
+                                prev[c][u][i] /= mx;
                         logScale[u] += log(mx);
                     }
                 }
             }
-#pragma unroll
-            for (int u = 0; u < PPT; u++)
-#pragma unroll
-                for (int c = 0; c < CR; c++)
-#pragma unroll
-                    for (int i = 0; i < 4; i++)
-                        prev[u][c][i] = nw[u][c][i];
             if (op.flags & OP_STORE) {
                 double *dst = stackBase + ((size_t)(op.dst * CR) * 4) * PPT * TPT + tid;
 #pragma unroll
@@ -598,7 +592,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                     for (int i = 0; i < 4; i++)
 #pragma unroll
                         for (int u = 0; u < PPT; u++)
-                            dst[((c * 4 + i) * PPT + u) * TPT] = nw[u][c][i];
+                            dst[((c * 4 + i) * PPT + u) * TPT] = prev[c][u][i];
             }
         }
         __syncthreads();       // every thread is done with this stage's ops and matrices
@@ -616,17 +610,17 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             double r;
             if (XL) {
                 // sum over the lane group in category order 0, 1, .., C-1
-                const double mine = prev[u][0][i] * catProps[cat];
+                const double mine = prev[0][u][i] * catProps[cat];
                 const int base = lane & ~(LPP - 1);
                 r = __shfl_sync(FULL_MASK, mine, base);
 #pragma unroll
                 for (int c = 1; c < LPP; c++)
                     r += __shfl_sync(FULL_MASK, mine, base + c);
             } else {
-                r = prev[u][0][i] * catProps[0];
+                r = prev[0][u][i] * catProps[0];
 #pragma unroll
                 for (int c = 1; c < CR; c++)
-                    r += prev[u][c][i] * catProps[c];
+                    r += prev[c][u][i] * catProps[c];
             }
             root[i] = r;
         }

@@ -45,6 +45,7 @@ struct mtt_peel {
     void *dOps = nullptr; size_t opsCap = 0;
     double *dMats = nullptr; size_t matsCap = 0;
     double *dPart = nullptr; size_t partCap = 0;
+    double *dCold = nullptr; size_t coldCap = 0;   // parked vectors beyond the shared-memory slots
     int *dParent = nullptr; size_t parentCap = 0;
     double *dHeight = nullptr; size_t heightCap = 0;
     double *dMatsIn = nullptr; size_t matsInCap = 0;
@@ -267,7 +268,9 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
         const int ka = swapKids ? c2 : c1, kb = swapKids ? c1 : c2;
         op.flags = (ka >= n) ? OP_C1_PREV : 0;
         op.c1 = (ka < n) ? -(ka + 1) : 0;
-        op.c2 = (kb < n) ? -(kb + 1) : (int)pd[v];
+        // a parked first child sits in slot (live vectors the second child needs) - 1: slots
+        // are numbered from the leaves up, so the small subtrees -- most of them -- use slots 0, 1
+        op.c2 = (kb < n) ? -(kb + 1) : (int)(need[c2] & 0x7f) - 1;
         op.dst = 0;
         if (v != root) {
             const int pp = parent[v];
@@ -275,9 +278,9 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
             const int pFirst = pRightFirst ? right[pp] : left[pp];
             const int pSecond = pRightFirst ? left[pp] : right[pp];
             if (pFirst == v && pSecond >= n) {      // my result waits for the sibling subtree
-                op.dst = pd[pp];
+                op.dst = (int)(need[pSecond] & 0x7f) - 1;
                 op.flags |= OP_STORE;
-                myMax = max(myMax, (int)pd[pp] + 1);
+                myMax = max(myMax, (int)op.dst + 1);
             }
         }
         ops[istart[v] + isize[v] - 1] = op;
@@ -331,10 +334,9 @@ template <int C>
 struct PeelCfg {
     // small stages: shared memory decides how many CTAs (warps) an SM holds, and the kernel
     // is latency-bound on dependent fp64 chains, so residency matters more than stage depth
-    static constexpr int OPS_PER_STAGE = (C == 1) ? 16 : (C == 2 ? 8 : 4);
+    static constexpr int OPS_PER_STAGE = (C == 1) ? 8 : 4;
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
-    static constexpr int MAX_PPT = (C <= 4) ? 2 : 1;   // patterns per thread (register budget)
 };
 
 // one child's contribution for PPT patterns of one category:
@@ -413,7 +415,7 @@ __global__ void __launch_bounds__(TPT)
 k2_peel(int n, long long P, long long pStride, const uint8_t *states, const double *weights,
         const uint8_t *constMask, const double *site, double pInv, const PeelOp *opsAll,
         const double *matsAll, const int *info, int nSlots, double *partial, int nTiles,
-        double *patternLogL)
+        double *patternLogL, int smemSlots, double *cold, int treeBase)
 {
     using Cfg = PeelCfg<C>;
     extern __shared__ __align__(16) unsigned char smem[];
@@ -429,7 +431,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     constexpr int MS = XL ? 2 * C : 2;        // double2 stride inside a staged matrix
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int cat = XL ? (tid & (C - 1)) : 0;
-    const int tile = blockIdx.x, b = blockIdx.y;
+    const int tile = blockIdx.x, b = blockIdx.y + treeBase;
     const int nOps = n - 1;
     const long long p0 = (long long)tile * TPP * PPT + tid / LPP;   // + u * TPP; < pStride
     const PeelOp *ops = opsAll + (size_t)b * nOps;
@@ -493,6 +495,15 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             for (int i = 0; i < 4; i++)
                 prev[c][u][i] = 1.0;
     }
+    // parked vectors: slots [0, smemSlots) in shared memory, the rarely used deeper ones in this
+    // CTA's piece of the global scratch (thread-contiguous, so the accesses coalesce)
+    constexpr size_t SLOT_DOUBLES = (size_t)CR * 4 * PPT * TPT;
+    double *coldBase = cold + ((size_t)blockIdx.y * gridDim.x + tile) *
+                                  (size_t)max(nSlots - smemSlots, 0) * SLOT_DOUBLES;
+    auto slot_ptr = [&](int slot) -> double * {
+        return (slot < smemSlots) ? stackBase + (size_t)slot * SLOT_DOUBLES
+                                  : coldBase + (size_t)(slot - smemSlots) * SLOT_DOUBLES;
+    };
     uint32_t phaseBits = 0;
     for (int s = 0; s < nStages; s++) {
         if (tid == 0 && s + 1 < nStages)
@@ -533,12 +544,22 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                 child_term<PPT, MS>(op.c1 < 0, M1, prev[c], t1, a);
                 // child 2: a tip, or a parked vector
                 if (op.c2 >= 0) {
-                    const double *src = stackBase + ((size_t)(op.c2 * CR + c) * 4) * PPT * TPT + tid;
+                    if (op.c2 < smemSlots) {
+                        const double *src = stackBase + (size_t)op.c2 * SLOT_DOUBLES +
+                                            (size_t)c * 4 * PPT * TPT + tid;
 #pragma unroll
-                    for (int i = 0; i < 4; i++)
+                        for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int u = 0; u < PPT; u++)
-                            x[u][i] = src[(i * PPT + u) * TPT];
+                            for (int u = 0; u < PPT; u++)
+                                x[u][i] = src[(i * PPT + u) * TPT];
+                    } else {
+                        const double *src = slot_ptr(op.c2) + (size_t)c * 4 * PPT * TPT + tid;
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+#pragma unroll
+                            for (int u = 0; u < PPT; u++)
+                                x[u][i] = __ldcg(src + (i * PPT + u) * TPT);
+                    }
                 }
                 child_term<PPT, MS>(op.c2 < 0, M2, x, t2, bb);
 #pragma unroll
@@ -585,7 +606,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
                 }
             }
             if (op.flags & OP_STORE) {
-                double *dst = stackBase + ((size_t)(op.dst * CR) * 4) * PPT * TPT + tid;
+                double *dst = slot_ptr(op.dst) + tid;
 #pragma unroll
                 for (int c = 0; c < CR; c++)
 #pragma unroll
@@ -701,23 +722,36 @@ int grow(mtt_ctx *ctx, T *&ptr, size_t &cap, size_t bytes)
 }
 
 template <int C, int TPT, int PPT>
-int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
+int launch_peel_t(mtt_peel *h, long long B, int nSlots, int smemSlots, double *patternLogL)
 {
     mtt_ctx *ctx = h->ctx;
     using Cfg = PeelCfg<C>;
     constexpr bool XL = cats_across_lanes(C);
     constexpr int CR = XL ? 1 : C;
+    constexpr size_t SLOT_BYTES = (size_t)CR * 4 * PPT * TPT * 8;
     const int nTiles = (int)(h->pStride / ((TPT / (XL ? C : 1)) * PPT));
-    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)nSlots * CR * 4 * PPT * TPT * 8;
+    smemSlots = std::min(smemSlots, nSlots);
+    const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)smemSlots * SLOT_BYTES;
     auto kern = k2_peel<C, TPT, PPT, XL>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
-    dim3 grid((unsigned)nTiles, (unsigned)B);
-    kern<<<grid, TPT, smem, ctx->stream>>>(h->nTips, h->nPatterns, h->pStride, h->dStates,
-                                           h->dWeights, h->dConst, h->dSite, h->pInv,
-                                           (const PeelOp *)h->dOps, h->dMats, h->dInfo, nSlots,
-                                           h->dPart, nTiles, patternLogL);
-    MTT_CHECK_LAUNCH(ctx);
+    // global scratch for the deeper slots, at most ~1 GB: larger batches run in sub-batches
+    const size_t coldPerTree = (size_t)nTiles * (size_t)(nSlots - smemSlots) * SLOT_BYTES;
+    long long sub = B;
+    if (coldPerTree > 0)
+        sub = std::max(1LL, std::min(B, (long long)((1ull << 30) / coldPerTree)));
+    int rc = grow(ctx, h->dCold, h->coldCap, (size_t)sub * coldPerTree + 256);
+    if (rc != MTT_OK)
+        return rc;
+    for (long long b0 = 0; b0 < B; b0 += sub) {
+        dim3 grid((unsigned)nTiles, (unsigned)std::min(sub, B - b0));
+        kern<<<grid, TPT, smem, ctx->stream>>>(h->nTips, h->nPatterns, h->pStride, h->dStates,
+                                               h->dWeights, h->dConst, h->dSite, h->pInv,
+                                               (const PeelOp *)h->dOps, h->dMats, h->dInfo,
+                                               nSlots, h->dPart, nTiles, patternLogL, smemSlots,
+                                               h->dCold, (int)b0);
+        MTT_CHECK_LAUNCH(ctx);
+    }
     return MTT_OK;
 }
 
@@ -726,32 +760,24 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, double *patternLogL)
 template <int C>
 int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *patternLogL)
 {
-    using Cfg = PeelCfg<C>;
     constexpr int LPP = cats_across_lanes(C) ? C : 1;      // lanes per pattern
     constexpr int CR = cats_across_lanes(C) ? 1 : C;       // categories per thread
-    constexpr int MAXPPT = cats_across_lanes(C) ? 2 : Cfg::MAX_PPT;
-    auto need = [&](int t, int ppt) {
-        return 2 * (size_t)Cfg::STAGE_BYTES + 16 + (size_t)nSlots * CR * 4 * ppt * t * 8;
-    };
-    const size_t budget = 110 * 1024;
-    if (MAXPPT == 2 && need(128, 2) <= budget) {
+    // Shared memory holds the two shallowest slots -- with slots numbered from the leaves up
+    // they take ~90 % of the parked traffic of coalescent-shaped trees -- and the deeper ones
+    // go to the L2-resident global scratch, so that six CTAs (24 warps) stay resident per SM
+    // whatever the depth of the tree.  With CR > 1 categories per thread a slot is CR times
+    // larger: fall back to smaller tiles as before.
+    constexpr int SMEM_SLOTS = 2;
+    if (CR <= 2) {
         *nTilesOut = (int)(h->pStride / (256 / LPP));
-        return launch_peel_t<C, 128, MAXPPT>(h, B, nSlots, patternLogL);
+        return launch_peel_t<C, 128, 2>(h, B, nSlots, SMEM_SLOTS, patternLogL);
     }
-    if (need(128, 1) <= budget) {
+    if (CR <= 4) {
         *nTilesOut = (int)(h->pStride / (128 / LPP));
-        return launch_peel_t<C, 128, 1>(h, B, nSlots, patternLogL);
+        return launch_peel_t<C, 128, 1>(h, B, nSlots, SMEM_SLOTS, patternLogL);
     }
-    if (need(64, 1) <= budget) {
-        *nTilesOut = (int)(h->pStride / (64 / LPP));
-        return launch_peel_t<C, 64, 1>(h, B, nSlots, patternLogL);
-    }
-    if (need(32, 1) > 227 * 1024)
-        return mtt_fail(h->ctx, MTT_ERR_TOO_LARGE,
-                        "peeling: %d parked partial vectors x %d categories exceed shared memory",
-                        nSlots, C);
-    *nTilesOut = (int)(h->pStride / (32 / LPP));
-    return launch_peel_t<C, 32, 1>(h, B, nSlots, patternLogL);
+    *nTilesOut = (int)(h->pStride / (64 / LPP));
+    return launch_peel_t<C, 64, 1>(h, B, nSlots, SMEM_SLOTS, patternLogL);
 }
 
 // run the pipeline on device-resident parent/height (or matsIn) for a chunk of trees
@@ -872,7 +898,7 @@ int mtt_peel_destroy(mtt_peel *h)
         return MTT_OK;
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->stream);
-    void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart,
+    void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart, h->dCold,
                     h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots};
     if (h->hMaxSlots)
         cudaFreeHost(h->hMaxSlots);

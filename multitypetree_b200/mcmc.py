@@ -14,7 +14,7 @@ more ``nextDouble`` only if ``logAlpha < 0``.
 from __future__ import annotations
 
 import math
-from typing import List, Optional, Sequence
+from typing import List, Sequence
 
 import numpy as np
 

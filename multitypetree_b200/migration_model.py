@@ -12,7 +12,6 @@ from typing import Optional, Sequence
 
 import numpy as np
 
-from . import _lib
 
 
 class TypeSet:

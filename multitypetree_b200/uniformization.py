@@ -10,12 +10,11 @@ what stays in Java in the real plugin: choosing the node and its new type with t
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence
+from typing import Optional, Sequence
 
 import numpy as np
 
 from . import _lib
-from .tree import MultiTypeTree
 
 ST_OK, ST_NO_VALID_PATH, ST_PBA_RUBBISH, ST_FB_FELL_THROUGH = 0, 1, 2, 3
 ST_NEEDS_POISSON_TAIL, ST_NEED_MORE_UNIFORMS, ST_NEED_MORE_POWERS, ST_SKIPPED = 4, 5, 6, 7

@@ -1,6 +1,5 @@
 """Device-resident timing of the peeling kernels (development probe)."""
 import sys
-import time
 
 import numpy as np
 import torch

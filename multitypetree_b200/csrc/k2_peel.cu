@@ -334,7 +334,7 @@ template <int C>
 struct PeelCfg {
     // small stages: shared memory decides how many CTAs (warps) an SM holds, and the kernel
     // is latency-bound on dependent fp64 chains, so residency matters more than stage depth
-    static constexpr int OPS_PER_STAGE = (C == 1) ? 8 : 4;
+    static constexpr int OPS_PER_STAGE = (C <= 4) ? 8 : 4;
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
 };

@@ -292,9 +292,9 @@ __device__ __forceinline__ StageLayout make_layout(const K1Params &p, const Tree
 // one elected lane: arm the stage's mbarrier and launch the bulk copies
 template <bool HAS_PARENT, int EMAX>
 __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
+                                           const StageLayout &L,
                                            WarpStage<HAS_PARENT, EMAX> *st, uint64_t *bar)
 {
-    const StageLayout L = make_layout<HAS_PARENT>(p, s);
     mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szT + L.szCT + L.szK + L.szP);
     bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
     if (L.szC) {
@@ -813,9 +813,9 @@ k1_density_warp(const K1Params p)
                 p.queue[1 + slot] = (int)t;
             }
         } else {
-            if (lane == 0)
-                issue_tree<HAS_PARENT, EMAX>(p, cur, &ws->st, (uint64_t *)&ws->bar);
             const StageLayout L = make_layout<HAS_PARENT>(p, cur);
+            if (lane == 0)
+                issue_tree<HAS_PARENT, EMAX>(p, cur, L, &ws->st, (uint64_t *)&ws->bar);
             if (PER_TREE_MODEL) {
                 fill_model_tab(tab, p.m + t * d * d, p.N + t * d, d, lane, 32);
                 __syncwarp();

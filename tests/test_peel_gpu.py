@@ -128,6 +128,40 @@ def test_unbalanced_and_balanced_topologies(ctx):
         tl.close()
 
 
+def test_deep_trees_in_sub_batches(ctx):
+    """Balanced 256-tip trees park 8 partial vectors: two in shared memory, six in the global
+    scratch.  With 20 k patterns and 700 trees that scratch passes 1 GB, so the batch runs in
+    sub-batches (of 276 or 331 trees, for 6 or 5 scratch slots); trees on both sides of every
+    possible seam must still match the oracle."""
+    n, B, sites = 256, 700, 20000
+    N = 2 * n - 1
+    parent = np.full(N, -1, np.int32)
+    height = np.zeros(N)
+    level, nxt, hh = list(range(n)), n, 0.02
+    while len(level) > 1:
+        new = []
+        for a, b in zip(level[::2], level[1::2]):
+            parent[a] = parent[b] = nxt
+            height[nxt] = hh
+            new.append(nxt)
+            nxt += 1
+        level, hh = new, hh + 0.02
+    f = np.array([.25] * 4)
+    rng = np.random.default_rng(8)
+    states = rng.integers(0, 4, size=(n, sites)).astype(np.uint8)      # all columns distinct
+    al = Alignment(states=states, compress=False)
+    sm = SiteModel(HKY(2.0, f))
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    par = np.repeat(parent[None], B, axis=0)
+    hgt = height[None] * (1.0 + 0.001 * np.arange(B)[:, None])
+    got = tl.calculateLogPBatch(par, hgt)
+    pick = [0, 1, 274, 275, 276, 277, 329, 330, 331, 332, 550, 551, 552, 553, 661, 662, 663, 699]
+    want = _oracle(al, par[pick], hgt[pick], sm)
+    np.testing.assert_allclose(got[pick], want, rtol=RTOL)
+    assert np.all(np.diff(got) != 0) and np.all(np.isfinite(got))
+    tl.close()
+
+
 def test_explicit_matrices_mode(ctx):
     """mtt_peel_logl_batch_mats: caller-provided per-node transition matrices (any model)."""
     n, B = 40, 6

@@ -193,12 +193,13 @@ def bench_density(args):
     L.mtt_sc_set_max_tree_events(ctx.handle, int(ev.max()))
 
     dm, dN = to_dev(m), to_dev(N)
-    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgCount, tb.chgBase,
+    # change lists in the owner layout (mtt_sc_logp_owner_batch*): what the kernels read
+    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgNode, tb.chgBase,
                                tb.chgTime, tb.chgType)]
     logP = torch.zeros(B, dtype=torch.float64, device="cuda")
 
     def step(Bs=B, out=logP):
-        ctx.check(L.mtt_sc_logp_batch_dev(
+        ctx.check(L.mtt_sc_logp_owner_batch_dev(
             ctx.handle, Bs, 2, 1, dm.data_ptr(), dN.data_ptr(), dev[0].data_ptr(),
             dev[1].data_ptr(), None, dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
             dev[5].data_ptr(), dev[6].data_ptr(), 0, out.data_ptr(), None))
@@ -243,7 +244,7 @@ def bench_density(args):
 
     # ---- end to end through the C-ABI with pinned host buffers
     host = [np.ascontiguousarray(x) for x in (m, N, tb.nodeOff, tb.height, tb.nodeType,
-                                              tb.chgCount, tb.chgBase, tb.chgTime, tb.chgType)]
+                                              tb.chgNode, tb.chgBase, tb.chgTime, tb.chgType)]
     out_h = np.empty(B, np.float64)
     pinned = []
     for a in host + [out_h]:
@@ -253,7 +254,7 @@ def bench_density(args):
     d2h = int(out_h.nbytes)
 
     def e2e_step():
-        ctx.check(L.mtt_sc_logp_batch(
+        ctx.check(L.mtt_sc_logp_owner_batch(
             ctx.handle, B, 2, 1, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(host[2]),
             _lib.ptr(host[3]), None, _lib.ptr(host[4]), _lib.ptr(host[5]), _lib.ptr(host[6]),
             _lib.ptr(host[7]), _lib.ptr(host[8]), 0, _lib.ptr(out_h), None))
@@ -383,7 +384,7 @@ def bench_peel(args):
     dpar, dhgt = to_dev(par), to_dev(hgt)
     out = torch.zeros(B, dtype=torch.float64, device="cuda")
     dm, dN = to_dev(m), to_dev(N)
-    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgCount, tb.chgBase,
+    dev = [to_dev(x) for x in (tb.nodeOff, tb.height, tb.nodeType, tb.chgNode, tb.chgBase,
                                tb.chgTime, tb.chgType)]
     dens = torch.zeros(B, dtype=torch.float64, device="cuda")
     L.mtt_sc_set_max_tree_events(ctx.handle, int(tb.n_events().max()))
@@ -391,7 +392,7 @@ def bench_peel(args):
     def step():
         ctx.check(L.mtt_peel_logl_batch_dev(tl.handle, B, dpar.data_ptr(), dhgt.data_ptr(),
                                             out.data_ptr()))
-        ctx.check(L.mtt_sc_logp_batch_dev(
+        ctx.check(L.mtt_sc_logp_owner_batch_dev(
             ctx.handle, B, d, 1, dm.data_ptr(), dN.data_ptr(), dev[0].data_ptr(),
             dev[1].data_ptr(), None, dev[2].data_ptr(), dev[3].data_ptr(), dev[4].data_ptr(),
             dev[5].data_ptr(), dev[6].data_ptr(), 0, dens.data_ptr(), None))

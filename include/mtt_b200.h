@@ -115,6 +115,26 @@ int mtt_sc_logp_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const
                           const uint16_t *chgCount, const int64_t *chgBase,
                           const double *chgTime, const uint8_t *chgType, int checkValidity,
                           double *logP, uint8_t *valid);
+/* The same two calls with the change lists in the OWNER layout, which is what the kernels read
+ * (the calls above expand their per-node counts into it on the device first):
+ *   chgNode[changes]   tree-local number of the node each change sits above; the changes of one
+ *                      node are adjacent and ordered child -> parent, nodes in increasing order.
+ * 2 bytes per change instead of 2 bytes per node: about 12 % less to move for a 100-tip tree
+ * with 40 changes, and no prefix sum on the device. */
+int mtt_sc_logp_owner_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                            const double *N, const int64_t *nodeOff, const double *height,
+                            const int32_t *parent, const uint8_t *nodeType,
+                            const uint16_t *chgNode, const int64_t *chgBase,
+                            const double *chgTime, const uint8_t *chgType, int checkValidity,
+                            double *logP, uint8_t *valid);
+int mtt_sc_logp_owner_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                const double *m, const double *N, const int64_t *nodeOff,
+                                const double *height, const int32_t *parent,
+                                const uint8_t *nodeType, const uint16_t *chgNode,
+                                const int64_t *chgBase, const double *chgTime,
+                                const uint8_t *chgType, int checkValidity, double *logP,
+                                uint8_t *valid);
+
 /* Optional hint for the _dev entry: an upper bound on nodes + changes of any tree in later
  * batches (0 = unknown).  With a bound <= 256 the large-tree kernel launch is skipped. */
 int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents);

@@ -44,7 +44,7 @@ struct K1Params {
     const double *height;
     const int *parent;
     const uint8_t *nodeType;
-    const uint16_t *chgCount;
+    const uint16_t *chgNode;     // tree-local number of the node that owns each change
     const long long *chgBase;
     const double *chgTime;
     const uint8_t *chgType;
@@ -278,7 +278,7 @@ __device__ __forceinline__ StageLayout make_layout(const K1Params &p, const Tree
     L.tOff = a;
     slice_of(p.chgType + s.c0, (uint32_t)s.M, a, L.szCT);
     L.ctOff = L.szT + a;
-    slice_of(p.chgCount + s.n0, 2u * s.n, a, L.szK);
+    slice_of(p.chgNode + s.c0, 2u * s.M, a, L.szK);
     L.kOff = a;
     L.pOff = 0;
     L.szP = 0;
@@ -302,9 +302,9 @@ __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
                  L.szC, bar);
         bulk_g2s(st->type + L.szT, (const unsigned char *)(p.chgType + s.c0) - (L.ctOff - L.szT),
                  L.szCT, bar);
+        bulk_g2s(st->cnt, (const unsigned char *)(p.chgNode + s.c0) - L.kOff, L.szK, bar);
     }
     bulk_g2s(st->type, (const unsigned char *)(p.nodeType + s.n0) - L.tOff, L.szT, bar);
-    bulk_g2s(st->cnt, (const unsigned char *)(p.chgCount + s.n0) - L.kOff, L.szK, bar);
     if (HAS_PARENT)
         bulk_g2s(st->par, (const unsigned char *)(p.parent + s.n0) - L.pOff, L.szP, bar);
 }
@@ -410,7 +410,7 @@ __device__ __forceinline__ void cnt_accumulate(Counts<NW> &c, uint32_t ds, const
 
 // One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
 // the validity verdict (all lanes).  Scratch aliases: `keys` doubles as a byte array during
-// phase A (before the sort writes it); the stage's chgCount region, dead after phase A,
+// phase A (before the sort writes it); the stage's chgNode region, dead after phase A,
 // receives the time-ordered event index list.
 template <int NW, bool HAS_PARENT, int EMAX>
 __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
@@ -424,102 +424,80 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     const double *sC = reinterpret_cast<const double *>(st->time + L.cOff);
     const uint8_t *sT = st->type + L.tOff;
     const uint8_t *sCT = st->type + L.ctOff;
-    const uint16_t *sK = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);
+    const uint16_t *sO = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);   // change owners
     const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
     uint16_t *order = reinterpret_cast<uint16_t *>(st->cnt);      // written after phase A
     auto ev_time = [&](int e) -> double { return (e < n) ? sH[e] : sC[e - n]; };
 
     // ---- phase A: event descriptors  kind | from | to  (COALESCE carries to = from so that
     //      the event term is always tab->logM[from * d + to])
+    // Every change names the node that owns it (chgNode), changes of one node are adjacent and
+    // ordered child -> parent: the first change of a branch leaves the node's type, any other
+    // one the type its predecessor entered.  No prefix sum, no scatter.
     bool ok = true;
-    {
-        // lane owns nodes [per*lane, per*lane+per): exclusive offset of its first change
-        const int per = (n + 31) >> 5;
-        const int e0 = per * lane, e1 = min(e0 + per, n);
-        int mine = 0;
-#pragma unroll 1
-        for (int e = e0; e < e1; e++)
-            mine += sK[e];
-        int incl = mine;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int v = __shfl_up_sync(FULL_MASK, incl, o);
-            if (lane >= o)
-                incl += v;
-        }
-        int off = incl - mine;
-        const bool sane = __all_sync(FULL_MASK, incl <= M);  // chgCount consistent with chgBase
-        ok = sane;
-        if (!HAS_PARENT) {
-            // first change of every branch takes its `from` type from the node: scatter it
-            uint8_t *firstFrom = reinterpret_cast<uint8_t *>(keys);
-            for (int i = lane * 16; i < M; i += 512)
-                *reinterpret_cast<uint4 *>(firstFrom + i) = make_uint4(~0u, ~0u, ~0u, ~0u);
-            __syncwarp();
-            if (sane && mine > 0) {
-#pragma unroll 1
-                for (int e = e0; e < e1; e++) {
-                    const int c = sK[e];
-                    if (c)
-                        firstFrom[off] = sT[e];
-                    off += c;
-                }
-            }
 #pragma unroll 2
-            for (int e = lane; e < n; e += 32) {
-                const int type = sT[e];
-                desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
-                                                   : (KIND_COALESCE << 10 | type << 5 | type)) |
-                          cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
-            }
-            __syncwarp();
-            if (sane) {
+    for (int e = lane; e < n; e += 32) {
+        const int type = sT[e];
+        desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
+                                           : (KIND_COALESCE << 10 | type << 5 | type)) |
+                  cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
+    }
+    if (!HAS_PARENT) {
 #pragma unroll 1
-                for (int c = lane; c < M; c += 32) {
-                    const int f = firstFrom[c];
-                    const int from = (f != 0xff) ? f : (int)sCT[c - 1];
-                    desc[n + c] = (uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]) |
-                                  cls_bits<NW>(KIND_MIGRATE, from);
-                }
-            } else {
-                for (int c = lane; c < M; c += 32)
-                    desc[n + c] = (uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0);
-            }
-        } else {
-            // node-centric walk with the validity chain of MultiTypeTree.java:396-429
-#pragma unroll 1
-            for (int e = e0; e < e1; e++) {
-                const int c = sane ? (int)sK[e] : 0;
-                int type = sT[e];
-                desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
-                                                   : (KIND_COALESCE << 10 | type << 5 | type)) |
-                          cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
-                const int par = sP[e];
-                const bool isRoot = par < 0;
-                double lastT = sH[e];
-#pragma unroll 1
-                for (int q = 0; q < c; q++) {
-                    const int to = sCT[off + q];
-                    // root-branch changes are ignored (StructuredCoalescentTreeDensity.java:161-162)
-                    desc[n + off + q] =
-                        (uint16_t)((isRoot ? KIND_NONE : KIND_MIGRATE) << 10 | type << 5 | to) |
-                        cls_bits<NW>(isRoot ? KIND_NONE : KIND_MIGRATE, type);
-                    const double tq = sC[off + q];
-                    ok = ok && !(lastT > tq);                // :404-405
-                    lastT = tq;
-                    type = to;
-                }
-                off += c;
-                if (!isRoot) {
-                    ok = ok && !(lastT > sH[par]);           // :401, :408-409
-                    ok = ok && (type == (int)sT[par]);       // :421-422
-                }
-            }
-            if (!sane)
-                for (int c = lane; c < M; c += 32)
-                    desc[n + c] = (uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0);
-            ok = __all_sync(FULL_MASK, ok);
+        for (int c = lane; c < M; c += 32) {
+            const int node = sO[c];
+            const bool first = (c == 0) || ((int)sO[c - 1] != node);
+            const bool bad = node >= n;                      // owner outside the tree
+            const int from = first ? (int)sT[bad ? 0 : node] : (int)sCT[c - 1];
+            desc[n + c] = bad ? ((uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0))
+                              : ((uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]) |
+                                 cls_bits<NW>(KIND_MIGRATE, from));
+            ok = ok && !bad;
         }
+        ok = __all_sync(FULL_MASK, ok);
+    } else {
+        // with parent[]: the validity chain of MultiTypeTree.java:396-429 rides along
+        uint8_t *hasChg = reinterpret_cast<uint8_t *>(keys);
+        for (int i = lane * 16; i < n; i += 512)
+            *reinterpret_cast<uint4 *>(hasChg + i) = make_uint4(0u, 0u, 0u, 0u);
+        __syncwarp();
+#pragma unroll 1
+        for (int c = lane; c < M; c += 32) {
+            const int node = sO[c];
+            const bool bad = node >= n;
+            const int nd = bad ? 0 : node;
+            const bool first = (c == 0) || ((int)sO[c - 1] != node);
+            const bool last = (c == M - 1) || ((int)sO[c + 1] != node);
+            const int par = sP[nd];
+            const bool isRoot = par < 0;
+            const int from = first ? (int)sT[nd] : (int)sCT[c - 1];
+            const int to = sCT[c];
+            // root-branch changes are ignored (StructuredCoalescentTreeDensity.java:161-162)
+            desc[n + c] = (bad || isRoot)
+                              ? ((uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0))
+                              : ((uint16_t)(KIND_MIGRATE << 10 | from << 5 | to) |
+                                 cls_bits<NW>(KIND_MIGRATE, from));
+            const double tc = sC[c];
+            const double before = first ? sH[nd] : sC[c - 1];
+            ok = ok && !bad && !(before > tc);               // :404-405
+            if (last && !isRoot && !bad) {
+                ok = ok && !(tc > sH[par]);                  // :401, :408-409
+                ok = ok && (to == (int)sT[par]);             // :421-422
+            }
+            if (first && !bad)
+                hasChg[nd] = 1;
+        }
+        __syncwarp();
+#pragma unroll 1
+        for (int e = lane; e < n; e += 32) {                 // branches without changes
+            const int par = sP[e];
+            if (par >= 0 && !hasChg[e]) {
+                ok = ok && !(sH[e] > sH[par]);
+                ok = ok && (sT[e] == sT[par]);
+            }
+        }
+        ok = __all_sync(FULL_MASK, ok);
+        __syncwarp();                                        // hasChg aliases the sort keys
     }
     okOut = ok;
     __syncwarp();
@@ -861,7 +839,6 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
     uint32_t *offs = reinterpret_cast<uint32_t *>(keys + Ecap);      // Ecap entries
     __shared__ double redD[BLK_THREADS / 32 * 2];
     __shared__ unsigned long long redC[BLK_THREADS / 32][NW];
-    __shared__ uint32_t redU[BLK_THREADS / 32];
     __shared__ int sFlag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -878,7 +855,7 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
         const double *H = p.height + n0;
         const double *CT = p.chgTime + c0;
         const uint8_t *T = p.nodeType + n0, *CTy = p.chgType + c0;
-        const uint16_t *K = p.chgCount + n0;
+        const uint16_t *O = p.chgNode + c0;         // change owners
         const int *P = p.parent ? p.parent + n0 : nullptr;
 
         __syncthreads();
@@ -907,35 +884,12 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
             redD[warp] = lo;
             redD[nWarps + warp] = hi;
         }
-        // ---- exclusive scan of change counts -> offs[]
-        const int per = (n + BLK_THREADS - 1) / BLK_THREADS;
-        const int b0 = min(tid * per, n), b1 = min(b0 + per, n);
-        uint32_t s = 0;
-        for (int e = b0; e < b1; e++)
-            s += K[e];
-        uint32_t incl = s;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
-            if (lane >= o)
-                incl += v;
-        }
-        if (lane == 31)
-            redU[warp] = incl;
         __syncthreads();
         lo = redD[0];
         hi = redD[nWarps];
         for (int w = 1; w < nWarps; w++) {
             lo = fmin(lo, redD[w]);
             hi = fmax(hi, redD[nWarps + w]);
-        }
-        uint32_t wbase = 0;
-        for (int w = 0; w < warp; w++)
-            wbase += redU[w];
-        uint32_t run = wbase + incl - s;
-        for (int e = b0; e < b1; e++) {
-            offs[e] = run;
-            run += K[e];
         }
         const double range = hi - lo;
         const double scale = (range > 0.0) ? 274877906943.0 / range : 0.0;   // 2^38 - 1
@@ -946,32 +900,49 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
         while (Epad < E)
             Epad <<= 1;
         bool ok = true;
+        uint8_t *hasChg = reinterpret_cast<uint8_t *>(offs);          // n bytes, validity only
         for (int e = tid; e < n; e += BLK_THREADS) {
-            int type = T[e];
             keys[e] = block_key(H[e], lo, scale, e,
-                                ((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | type << 5);
-            const int c = K[e];
-            const uint32_t off = offs[e];
-            const int par = P ? P[e] : 0;
+                                ((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | T[e] << 5);
+            if (P)
+                hasChg[e] = 0;
+        }
+        __syncthreads();
+        for (int c = tid; c < M; c += BLK_THREADS) {
+            const int node = O[c];
+            const bool bad = node >= n;
+            const int nd = bad ? 0 : node;
+            const bool first = (c == 0) || ((int)O[c - 1] != node);
+            const bool last = (c == M - 1) || ((int)O[c + 1] != node);
+            const int par = P ? P[nd] : 0;
             const bool isRoot = P && par < 0;
-            double lastT = H[e];
-            for (int j = 0; j < c; j++) {
-                int to = CTy[off + j];
-                double tj = CT[off + j];
-                if (isRoot)
-                    keys[n + off + j] = ~0ull;       // ignored (:161-162): sorts with the padding
-                else
-                    keys[n + off + j] = block_key(tj, lo, scale, n + off + j,
-                                                  KIND_MIGRATE << 10 | type << 5 | to);
-                if (P) {
-                    ok = ok && !(lastT > tj);
-                    lastT = tj;
+            const int from = first ? (int)T[nd] : (int)CTy[c - 1];
+            const int to = CTy[c];
+            const double tc = CT[c];
+            if (bad || isRoot)
+                keys[n + c] = ~0ull;                 // ignored (:161-162): sorts with the padding
+            else
+                keys[n + c] = block_key(tc, lo, scale, n + c, KIND_MIGRATE << 10 | from << 5 | to);
+            ok = ok && !bad;
+            if (P) {
+                const double before = first ? H[nd] : CT[c - 1];
+                ok = ok && !(before > tc);
+                if (last && !isRoot && !bad) {
+                    ok = ok && !(tc > H[par]);
+                    ok = ok && (to == (int)T[par]);
                 }
-                type = to;
+                if (first && !bad)
+                    hasChg[nd] = 1;
             }
-            if (P && !isRoot) {
-                ok = ok && !(lastT > H[par]);
-                ok = ok && (type == (int)T[par]);
+        }
+        if (P) {
+            __syncthreads();
+            for (int e = tid; e < n; e += BLK_THREADS) {
+                const int par = P[e];
+                if (par >= 0 && !hasChg[e]) {
+                    ok = ok && !(H[e] > H[par]);
+                    ok = ok && (T[e] == T[par]);
+                }
             }
         }
         for (int e = E + tid; e < Epad; e += BLK_THREADS)
@@ -1184,11 +1155,46 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
     return MTT_OK;
 }
 
+// Per-node change counts -> per-change owner list (the layout the kernels read), one warp per
+// tree.  Counts that do not add up to the tree's number of changes leave 0xffff owners behind,
+// which the density kernels treat as a malformed tree.
+__global__ void k1_expand_counts(long long B, const long long *nodeOff, const uint16_t *chgCount,
+                                 const long long *chgBase, uint16_t *chgNode)
+{
+    const long long t = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (t >= B)
+        return;
+    const long long n0 = nodeOff[t], c0 = chgBase[t];
+    const int n = (int)(nodeOff[t + 1] - n0), M = (int)(chgBase[t + 1] - c0);
+    const uint16_t *K = chgCount + n0;
+    uint16_t *O = chgNode + c0;
+    for (int c = lane; c < M; c += 32)
+        O[c] = 0xffff;
+    __syncwarp();
+    int carry = 0;
+    for (int base = 0; base < n; base += 32) {
+        const int e = base + lane;
+        const int k = (e < n) ? (int)K[e] : 0;
+        int incl = k;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, incl, o);
+            if (lane >= o)
+                incl += v;
+        }
+        const int off = carry + incl - k;
+        for (int j = 0; j < k && off + j < M; j++)
+            O[off + j] = (uint16_t)e;
+        carry += __shfl_sync(FULL_MASK, incl, 31);
+    }
+}
+
 }  // namespace
 
 int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
                   const double *N, const int64_t *nodeOff, const double *height,
-                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
+                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgNode,
                   const int64_t *chgBase, const double *chgTime, const uint8_t *chgType,
                   int checkValidity, double *logP, uint8_t *valid, long long maxEvents)
 {
@@ -1203,7 +1209,7 @@ int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double 
     K1Params p;
     p.B = B; p.d = d; p.nModels = nModels; p.m = m; p.N = N;
     p.nodeOff = (const long long *)nodeOff; p.height = height; p.parent = parent;
-    p.nodeType = nodeType; p.chgCount = chgCount; p.chgBase = (const long long *)chgBase;
+    p.nodeType = nodeType; p.chgNode = chgNode; p.chgBase = (const long long *)chgBase;
     p.chgTime = chgTime; p.chgType = chgType; p.checkValidity = checkValidity;
     p.logP = logP; p.valid = valid;
     // work queue for the block kernel: [0] = count (zero between calls), [1..] = tree indices
@@ -1221,4 +1227,15 @@ int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double 
     if (d <= 8)
         return launch_all<2>(ctx, p, maxEvents);
     return launch_all<4>(ctx, p, maxEvents);
+}
+
+int mtt_k1_expand_counts(mtt_ctx *ctx, int64_t B, const int64_t *nodeOff,
+                         const uint16_t *chgCount, const int64_t *chgBase, uint16_t *chgNode)
+{
+    if (B <= 0)
+        return MTT_OK;
+    k1_expand_counts<<<(unsigned)((B + 7) / 8), 256, 0, ctx->stream>>>(
+        B, (const long long *)nodeOff, chgCount, (const long long *)chgBase, chgNode);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
 }

@@ -163,9 +163,46 @@ int mtt_host_unregister(void *ptr)
 
 int mtt_k1_launch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
                   const double *N, const int64_t *nodeOff, const double *height,
-                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgCount,
+                  const int32_t *parent, const uint8_t *nodeType, const uint16_t *chgNode,
                   const int64_t *chgBase, const double *chgTime, const uint8_t *chgType,
                   int checkValidity, double *logP, uint8_t *valid, long long maxEvents);
+int mtt_k1_expand_counts(mtt_ctx *ctx, int64_t B, const int64_t *nodeOff,
+                         const uint16_t *chgCount, const int64_t *chgBase, uint16_t *chgNode);
+
+// device-resident inputs; `owners` = chgNode layout, otherwise per-node counts (expanded here)
+static int sc_logp_dev(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t nModels,
+                       const double *m, const double *N, const int64_t *nodeOff,
+                       const double *height, const int32_t *parent, const uint8_t *nodeType,
+                       const uint16_t *chgCountOrNode, bool owners, const int64_t *chgBase,
+                       const double *chgTime, const uint8_t *chgType, int checkValidity,
+                       double *logP, uint8_t *valid)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgCountOrNode || !chgBase ||
+        !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: NULL argument", who);
+    if (B == 0)
+        return MTT_OK;
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const uint16_t *chgNode = chgCountOrNode;
+    if (!owners) {
+        // the kernels read the owner list: expand the counts (needs the number of changes)
+        int64_t changes = 0;
+        MTT_CUDA(ctx, cudaMemcpyAsync(&changes, chgBase + B, 8, cudaMemcpyDeviceToHost,
+                                      ctx->stream));
+        MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+        uint16_t *dO = (uint16_t *)mtt_buf(ctx, BUF_D_CHGNODE, (size_t)changes * 2);
+        if (!dO)
+            return MTT_ERR_CUDA;
+        int rc = mtt_k1_expand_counts(ctx, B, nodeOff, chgCountOrNode, chgBase, dO);
+        if (rc != MTT_OK)
+            return rc;
+        chgNode = dO;
+    }
+    return mtt_k1_launch(ctx, B, d, nModels, m, N, nodeOff, height, parent, nodeType, chgNode,
+                         chgBase, chgTime, chgType, checkValidity, logP, valid, ctx->k1MaxEvents);
+}
 
 extern "C" int mtt_sc_logp_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
                                      const double *m, const double *N, const int64_t *nodeOff,
@@ -175,41 +212,51 @@ extern "C" int mtt_sc_logp_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nMo
                                      const uint8_t *chgType, int checkValidity, double *logP,
                                      uint8_t *valid)
 {
-    if (!ctx)
-        return MTT_ERR_INVALID_ARG;
-    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgCount || !chgBase || !logP)
-        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch_dev: NULL argument");
-    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
-    return mtt_k1_launch(ctx, B, d, nModels, m, N, nodeOff, height, parent, nodeType, chgCount,
-                         chgBase, chgTime, chgType, checkValidity, logP, valid, ctx->k1MaxEvents);
+    return sc_logp_dev(ctx, "mtt_sc_logp_batch_dev", B, d, nModels, m, N, nodeOff, height, parent,
+                       nodeType, chgCount, false, chgBase, chgTime, chgType, checkValidity, logP,
+                       valid);
 }
 
-extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
-                                 const double *m, const double *N, const int64_t *nodeOff,
-                                 const double *height, const int32_t *parent,
-                                 const uint8_t *nodeType, const uint16_t *chgCount,
-                                 const int64_t *chgBase, const double *chgTime,
-                                 const uint8_t *chgType, int checkValidity, double *logP,
-                                 uint8_t *valid)
+extern "C" int mtt_sc_logp_owner_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                           const double *m, const double *N,
+                                           const int64_t *nodeOff, const double *height,
+                                           const int32_t *parent, const uint8_t *nodeType,
+                                           const uint16_t *chgNode, const int64_t *chgBase,
+                                           const double *chgTime, const uint8_t *chgType,
+                                           int checkValidity, double *logP, uint8_t *valid)
+{
+    return sc_logp_dev(ctx, "mtt_sc_logp_owner_batch_dev", B, d, nModels, m, N, nodeOff, height,
+                       parent, nodeType, chgNode, true, chgBase, chgTime, chgType, checkValidity,
+                       logP, valid);
+}
+
+// host buffers
+static int sc_logp_host(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t nModels,
+                        const double *m, const double *N, const int64_t *nodeOff,
+                        const double *height, const int32_t *parent, const uint8_t *nodeType,
+                        const uint16_t *chgCountOrNode, bool owners, const int64_t *chgBase,
+                        const double *chgTime, const uint8_t *chgType, int checkValidity,
+                        double *logP, uint8_t *valid)
 {
     if (!ctx)
         return MTT_ERR_INVALID_ARG;
-    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgCount || !chgBase || !logP)
-        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch: NULL argument");
+    if (B < 0 || !m || !N || !nodeOff || !height || !nodeType || !chgBase || !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: NULL argument", who);
     if (B == 0)
         return MTT_OK;
     if (nModels != 1 && nModels != B)
-        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_logp_batch: nModels must be 1 or B");
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: nModels must be 1 or B", who);
     if (checkValidity && !parent)
-        return mtt_fail(ctx, MTT_ERR_INVALID_ARG,
-                        "mtt_sc_logp_batch: checkValidity requires parent[]");
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: checkValidity requires parent[]", who);
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
 
     const int64_t nodes = nodeOff[B] - nodeOff[0], changes = chgBase[B] - chgBase[0];
     if (nodeOff[0] != 0 || chgBase[0] != 0)
         return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "nodeOff[0] and chgBase[0] must be 0");
-    if (changes > 0 && (!chgTime || !chgType))
-        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "chgTime/chgType NULL with changes present");
+    if (changes > 0 && (!chgTime || !chgType || (owners && !chgCountOrNode)))
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "chgTime/chgType/chgNode NULL with changes present");
+    if (!owners && !chgCountOrNode)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: chgCount is NULL", who);
     long long maxEv = 0;
     for (int64_t b = 0; b < B; b++) {
         long long e = (nodeOff[b + 1] - nodeOff[b]) + (chgBase[b + 1] - chgBase[b]);
@@ -232,14 +279,15 @@ extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels
     int64_t *dChgBase = (int64_t *)mtt_buf(ctx, BUF_D_CHGBASE, (B + 1) * 8);
     double *dH = (double *)mtt_buf(ctx, BUF_D_HEIGHT, nodes * 8);
     uint8_t *dT = (uint8_t *)mtt_buf(ctx, BUF_D_NODETYPE, nodes);
-    uint16_t *dK = (uint16_t *)mtt_buf(ctx, BUF_D_CHGCOUNT, nodes * 2);
+    uint16_t *dK = owners ? nullptr : (uint16_t *)mtt_buf(ctx, BUF_D_CHGCOUNT, nodes * 2);
+    uint16_t *dO = (uint16_t *)mtt_buf(ctx, BUF_D_CHGNODE, changes * 2);
     double *dCT = (double *)mtt_buf(ctx, BUF_D_CHGTIME, changes * 8);
     uint8_t *dCTy = (uint8_t *)mtt_buf(ctx, BUF_D_CHGTYPE, changes);
     int32_t *dP = parent ? (int32_t *)mtt_buf(ctx, BUF_D_PARENT, nodes * 4) : nullptr;
     double *dLogP = (double *)mtt_buf(ctx, BUF_D_LOGP, B * 8);
     uint8_t *dValid = (valid && parent) ? (uint8_t *)mtt_buf(ctx, BUF_D_VALID, B) : nullptr;
-    if (!dM || !dN || !dNodeOff || !dChgBase || !dH || !dT || !dK || !dCT || !dCTy || !dLogP ||
-        (parent && !dP) || (valid && parent && !dValid))
+    if (!dM || !dN || !dNodeOff || !dChgBase || !dH || !dT || (!owners && !dK) || !dO || !dCT ||
+        !dCTy || !dLogP || (parent && !dP) || (valid && parent && !dValid))
         return MTT_ERR_CUDA;
 
     MTT_CUDA(ctx, cudaMemcpyAsync(dM, m, md, cudaMemcpyHostToDevice, s));
@@ -248,16 +296,24 @@ extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels
     MTT_CUDA(ctx, cudaMemcpyAsync(dChgBase, chgBase, (B + 1) * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dH, height, nodes * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dT, nodeType, nodes, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dK, chgCount, nodes * 2, cudaMemcpyHostToDevice, s));
+    if (!owners)
+        MTT_CUDA(ctx, cudaMemcpyAsync(dK, chgCountOrNode, nodes * 2, cudaMemcpyHostToDevice, s));
     if (changes > 0) {
         MTT_CUDA(ctx, cudaMemcpyAsync(dCT, chgTime, changes * 8, cudaMemcpyHostToDevice, s));
         MTT_CUDA(ctx, cudaMemcpyAsync(dCTy, chgType, changes, cudaMemcpyHostToDevice, s));
+        if (owners)
+            MTT_CUDA(ctx, cudaMemcpyAsync(dO, chgCountOrNode, changes * 2, cudaMemcpyHostToDevice,
+                                          s));
     }
     if (parent)
         MTT_CUDA(ctx, cudaMemcpyAsync(dP, parent, nodes * 4, cudaMemcpyHostToDevice, s));
-
-    int rc = mtt_k1_launch(ctx, B, d, nModels, dM, dN, dNodeOff, dH, dP, dT, dK, dChgBase, dCT,
-                           dCTy, checkValidity, dLogP, dValid, maxEv > 0 ? maxEv : 1);
+    int rc = MTT_OK;
+    if (!owners)
+        rc = mtt_k1_expand_counts(ctx, B, dNodeOff, dK, dChgBase, dO);
+    if (rc != MTT_OK)
+        return rc;
+    rc = mtt_k1_launch(ctx, B, d, nModels, dM, dN, dNodeOff, dH, dP, dT, dO, dChgBase, dCT, dCTy,
+                       checkValidity, dLogP, dValid, maxEv > 0 ? maxEv : 1);
     if (rc != MTT_OK)
         return rc;
     MTT_CUDA(ctx, cudaMemcpyAsync(logP, dLogP, B * 8, cudaMemcpyDeviceToHost, s));
@@ -269,7 +325,32 @@ extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels
     return MTT_OK;
 }
 
-// hint for the device-pointer entry point (upper bound on nodes+changes per tree; 0 unknown)
+extern "C" int mtt_sc_logp_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                 const double *m, const double *N, const int64_t *nodeOff,
+                                 const double *height, const int32_t *parent,
+                                 const uint8_t *nodeType, const uint16_t *chgCount,
+                                 const int64_t *chgBase, const double *chgTime,
+                                 const uint8_t *chgType, int checkValidity, double *logP,
+                                 uint8_t *valid)
+{
+    return sc_logp_host(ctx, "mtt_sc_logp_batch", B, d, nModels, m, N, nodeOff, height, parent,
+                        nodeType, chgCount, false, chgBase, chgTime, chgType, checkValidity, logP,
+                        valid);
+}
+
+extern "C" int mtt_sc_logp_owner_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                       const double *m, const double *N, const int64_t *nodeOff,
+                                       const double *height, const int32_t *parent,
+                                       const uint8_t *nodeType, const uint16_t *chgNode,
+                                       const int64_t *chgBase, const double *chgTime,
+                                       const uint8_t *chgType, int checkValidity, double *logP,
+                                       uint8_t *valid)
+{
+    return sc_logp_host(ctx, "mtt_sc_logp_owner_batch", B, d, nModels, m, N, nodeOff, height,
+                        parent, nodeType, chgNode, true, chgBase, chgTime, chgType, checkValidity,
+                        logP, valid);
+}
+
 extern "C" int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents)
 {
     if (!ctx)

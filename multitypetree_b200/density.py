@@ -13,9 +13,11 @@ from .tree import MultiTypeTree, TreeBatch
 
 
 def sc_logp_batch(batch: TreeBatch, m: np.ndarray, N: np.ndarray, checkValidity: bool = False,
-                  ctx=None, with_parent: bool = None, want_valid: bool = False):
-    """logP of every tree of ``batch`` (mtt_sc_logp_batch, host buffers).
-    m: [d,d] (shared model) or [B,d,d]; N: [d] or [B,d]."""
+                  ctx=None, with_parent: bool = None, want_valid: bool = False,
+                  layout: str = "owner"):
+    """logP of every tree of ``batch`` (host buffers).  m: [d,d] (shared model) or [B,d,d];
+    N: [d] or [B,d].  layout "owner": mtt_sc_logp_owner_batch with the per-change owner list
+    (what the kernels read); "counts": mtt_sc_logp_batch with per-node change counts."""
     ctx = ctx or _lib.default_context()
     L = _lib.lib()
     B = batch.B
@@ -27,14 +29,19 @@ def sc_logp_batch(batch: TreeBatch, m: np.ndarray, N: np.ndarray, checkValidity:
         with_parent = checkValidity or want_valid
     logP = np.empty(B, np.float64)
     valid = np.empty(B, np.uint8) if want_valid else None
+    if layout not in ("owner", "counts"):
+        raise ValueError("layout must be 'owner' or 'counts'")
+    owner = layout == "owner"
     args = [_lib.as_c(batch.nodeOff, np.int64), _lib.as_c(batch.height, np.float64),
             _lib.as_c(batch.parent, np.int32) if with_parent else None,
-            _lib.as_c(batch.nodeType, np.uint8), _lib.as_c(batch.chgCount, np.uint16),
+            _lib.as_c(batch.nodeType, np.uint8),
+            _lib.as_c(batch.chgNode if owner else batch.chgCount, np.uint16),
             _lib.as_c(batch.chgBase, np.int64), _lib.as_c(batch.chgTime, np.float64),
             _lib.as_c(batch.chgType, np.uint8)]
-    ctx.check(L.mtt_sc_logp_batch(ctx.handle, B, d, nModels, _lib.ptr(m), _lib.ptr(N),
-                                  *[_lib.ptr(a) for a in args], int(bool(checkValidity)),
-                                  _lib.ptr(logP), _lib.ptr(valid)))
+    fn = L.mtt_sc_logp_owner_batch if owner else L.mtt_sc_logp_batch
+    ctx.check(fn(ctx.handle, B, d, nModels, _lib.ptr(m), _lib.ptr(N),
+                 *[_lib.ptr(a) for a in args], int(bool(checkValidity)),
+                 _lib.ptr(logP), _lib.ptr(valid)))
     return (logP, valid.astype(bool)) if want_valid else logP
 
 

@@ -215,6 +215,22 @@ class TreeBatch:
     def B(self) -> int:
         return len(self.nodeOff) - 1
 
+    @property
+    def chgNode(self) -> np.ndarray:
+        """u16 [changes]: tree-local number of the node that owns each change -- the OWNER
+        layout of ``mtt_sc_logp_owner_batch`` (derived once from ``chgCount`` and cached)."""
+        cached = self.__dict__.get("_chgNode")
+        if cached is None or len(cached) != len(self.chgTime):
+            csum = np.concatenate([[0], np.cumsum(self.chgCount, dtype=np.int64)])
+            if not np.array_equal(csum[self.nodeOff], self.chgBase):
+                raise ValueError("chgCount does not add up to chgBase: no owner list exists for "
+                                 "this batch (the counts layout reports such trees as invalid)")
+            local = np.arange(len(self.chgCount), dtype=np.int64) - np.repeat(
+                self.nodeOff[:-1], np.diff(self.nodeOff))
+            cached = np.repeat(local, self.chgCount).astype(np.uint16)
+            self.__dict__["_chgNode"] = cached
+        return cached
+
     def n_events(self) -> np.ndarray:
         """E = nodes + changes per tree (the unit of algorithmic traffic)."""
         return np.diff(self.nodeOff) + np.diff(self.chgBase)

@@ -12,10 +12,14 @@ RTOL = 1e-9
 
 
 def _check(tb, m, N, ctx, **kw):
+    """both wire layouts of the change lists (per-change owners, per-node counts) against the
+    oracle; they must also agree with each other bit for bit (same kernels behind both)"""
     want = orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL)
-    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx, **kw)
+    got = mtt.sc_logp_batch(tb, m, N, ctx=ctx, layout="owner", **kw)
     assert got.shape == want.shape
     np.testing.assert_allclose(got, want, rtol=RTOL, atol=0)
+    alt = mtt.sc_logp_batch(tb, m, N, ctx=ctx, layout="counts", **kw)
+    assert np.array_equal(got, alt, equal_nan=True)
     return got
 
 
@@ -165,6 +169,28 @@ def test_root_branch_changes_ignored(ctx):
                        np.append(b.chgType, [1, 0]).astype(np.uint8))
     got = mtt.sc_logp_batch(b2, m, N, ctx=ctx, with_parent=True)
     assert abs(got[0] - expected) < 1e-5
+
+
+def test_malformed_change_lists(ctx):
+    """Counts that do not add up to chgBase, or owners outside the tree: never a crash; the
+    tree is reported invalid and -inf under checkValidity, in both layouts."""
+    tb, m, N, _ = load_density_fixture("true64")
+    bad = mtt.TreeBatch(tb.nodeOff, tb.height, tb.parent, tb.nodeType, tb.chgCount.copy(),
+                        tb.chgBase, tb.chgTime, tb.chgType)
+    bad.chgCount[5] += 3
+    lp, valid = mtt.sc_logp_batch(bad, m, N, checkValidity=True, ctx=ctx, want_valid=True,
+                                  layout="counts")
+    assert not valid[0] and lp[0] == -np.inf
+    with pytest.raises(ValueError):
+        bad.chgNode
+    own = mtt.TreeBatch(tb.nodeOff, tb.height, tb.parent, tb.nodeType, tb.chgCount, tb.chgBase,
+                        tb.chgTime, tb.chgType)
+    o = tb.chgNode.copy()
+    o[3] = 60000
+    own.__dict__["_chgNode"] = o
+    lp, valid = mtt.sc_logp_batch(own, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+    assert not valid[0] and lp[0] == -np.inf
+    assert np.isfinite(mtt.sc_logp_batch(own, m, N, ctx=ctx)[0])     # ignored change, no crash
 
 
 def test_batch_size_independence_and_determinism(ctx):

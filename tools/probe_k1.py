@@ -31,7 +31,7 @@ def main():
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
-    arrs = [dev(x) for x in (m, N, tb.nodeOff, tb.height, tb.parent, tb.nodeType, tb.chgCount,
+    arrs = [dev(x) for x in (m, N, tb.nodeOff, tb.height, tb.parent, tb.nodeType, tb.chgNode,
                              tb.chgBase, tb.chgTime, tb.chgType)]
     logP = torch.zeros(B, dtype=torch.float64, device="cuda")
     for hint, with_parent in ((int(tb.n_events().max()), False), (0, False),
@@ -40,7 +40,7 @@ def main():
         def run():
             p = [a.data_ptr() for a in arrs]
             par = p[4] if with_parent else None
-            ctx.check(L.mtt_sc_logp_batch_dev(ctx.handle, B, d, 1, p[0], p[1], p[2], p[3], par,
+            ctx.check(L.mtt_sc_logp_owner_batch_dev(ctx.handle, B, d, 1, p[0], p[1], p[2], p[3], par,
                                               p[5], p[6], p[7], p[8], p[9], int(with_parent),
                                               logP.data_ptr(), None))
         for _ in range(3):

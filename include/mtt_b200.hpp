@@ -315,7 +315,7 @@ struct TreeBatch {
     std::vector<double> height, chgTime;
     std::vector<int32_t> parent;
     std::vector<uint8_t> nodeType, chgType;
-    std::vector<uint16_t> chgCount;
+    std::vector<uint16_t> chgNode;                      // owner (tree-local node) of every change
     int64_t size() const { return (int64_t)nodeOff.size() - 1; }
     void add(const MultiTypeTree &t)
     {
@@ -325,11 +325,11 @@ struct TreeBatch {
             parent.push_back(t.parent[i]);
             nodeType.push_back(t.nodeType[i]);
             const bool root = t.parent[i] < 0;          // root-branch changes are not exported
-            chgCount.push_back(root ? 0 : (uint16_t)t.changeTimes[i].size());
             if (!root)
                 for (size_t k = 0; k < t.changeTimes[i].size(); k++) {
                     chgTime.push_back(t.changeTimes[i][k]);
                     chgType.push_back(t.changeTypes[i][k]);
+                    chgNode.push_back((uint16_t)i);
                 }
         }
         nodeOff.push_back((int64_t)height.size());
@@ -366,10 +366,12 @@ public:
         std::vector<uint8_t> valid((size_t)b.size());
         static const double zero = 0.0;
         static const uint8_t zero8 = 0;
-        ctx_.check(mtt_sc_logp_batch(
+        static const uint16_t zero16 = 0;
+        ctx_.check(mtt_sc_logp_owner_batch(
             ctx_.get(), b.size(), model_.getNTypes(), 1, m.data(), N.data(), b.nodeOff.data(),
             b.height.data(), check_ ? b.parent.data() : nullptr, b.nodeType.data(),
-            b.chgCount.data(), b.chgBase.data(), b.chgTime.empty() ? &zero : b.chgTime.data(),
+            b.chgNode.empty() ? &zero16 : b.chgNode.data(), b.chgBase.data(),
+            b.chgTime.empty() ? &zero : b.chgTime.data(),
             b.chgType.empty() ? &zero8 : b.chgType.data(), check_ ? 1 : 0, out.data(),
             check_ ? valid.data() : nullptr));
         return out;

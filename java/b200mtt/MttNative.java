@@ -26,7 +26,7 @@ public final class MttNative implements AutoCloseable {
     private static final MethodHandle CTX_CREATE = h("mtt_ctx_create", FunctionDescriptor.of(JAVA_INT, JAVA_INT, ADDRESS));
     private static final MethodHandle CTX_DESTROY = h("mtt_ctx_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle LAST_ERROR = h("mtt_last_error", FunctionDescriptor.of(ADDRESS, ADDRESS));
-    private static final MethodHandle SC_LOGP = h("mtt_sc_logp_batch", FunctionDescriptor.of(JAVA_INT,
+    private static final MethodHandle SC_LOGP = h("mtt_sc_logp_owner_batch", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_LONG, JAVA_INT, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
             ADDRESS, ADDRESS, ADDRESS, ADDRESS, JAVA_INT, ADDRESS, ADDRESS));
     private static final MethodHandle UNIF_SET = h("mtt_unif_set_models", FunctionDescriptor.of(JAVA_INT,
@@ -84,14 +84,14 @@ public final class MttNative implements AutoCloseable {
             throw new IllegalStateException("libmtt_b200 error " + rc + ": " + lastError(ctx));
     }
 
-    /** mtt_sc_logp_batch: all segments are off-heap (Arena) buffers in the layout of mtt_b200.h. */
+    /** mtt_sc_logp_owner_batch: all segments are off-heap (Arena) buffers in the layout of mtt_b200.h. */
     public void scLogPBatch(long B, int d, long nModels, MemorySegment m, MemorySegment N,
                             MemorySegment nodeOff, MemorySegment height, MemorySegment parent,
-                            MemorySegment nodeType, MemorySegment chgCount, MemorySegment chgBase,
+                            MemorySegment nodeType, MemorySegment chgNode, MemorySegment chgBase,
                             MemorySegment chgTime, MemorySegment chgType, boolean checkValidity,
                             MemorySegment logP, MemorySegment valid) {
         try {
-            check((int) SC_LOGP.invoke(ctx, B, d, nModels, m, N, nodeOff, height, parent, nodeType, chgCount,
+            check((int) SC_LOGP.invoke(ctx, B, d, nModels, m, N, nodeOff, height, parent, nodeType, chgNode,
                     chgBase, chgTime, chgType, checkValidity ? 1 : 0, logP, valid));
         } catch (RuntimeException e) {
             throw e;

@@ -3,7 +3,7 @@
  * (distributions/StructuredCoalescentTreeDensity.java:41-253): same Inputs ("multiTypeTree" from
  * MultiTypeTreeDistribution.java:35-36, "migrationModel", "checkValidity"), same contract of
  * calculateLogP(); the event sequence, validity check and interval scan run on the B200 through
- * mtt_sc_logp_batch.  Register in version.xml as
+ * mtt_sc_logp_owner_batch.  Register in version.xml as
  *   <provider classname="b200mtt.StructuredCoalescentTreeDensity"/>
  * and use spec="b200mtt.StructuredCoalescentTreeDensity" in the XML.  NOT compiled here (no JDK).
  */
@@ -69,7 +69,7 @@ public class StructuredCoalescentTreeDensity extends MultiTypeTreeDistribution {
         }
         flat.flatten(mtTree);
         nativeLib.scLogPBatch(1, d, 1, m, N, flat.nodeOff, flat.height,
-                checkValidity ? flat.parent : MemorySegment.NULL, flat.nodeType, flat.chgCount,
+                checkValidity ? flat.parent : MemorySegment.NULL, flat.nodeType, flat.chgNode,
                 flat.chgBase, flat.chgTime, flat.chgType, checkValidity, logPOut,
                 checkValidity ? validOut : MemorySegment.NULL);
         logP = logPOut.get(JAVA_DOUBLE, 0);      // -inf when checkValidity && !isValid (:90-91)

@@ -16,7 +16,7 @@ import static java.lang.foreign.ValueLayout.*;
 
 final class TreeFlattener {
     final Arena arena = Arena.ofShared();
-    MemorySegment nodeOff, height, parent, nodeType, chgCount, chgBase, chgTime, chgType;
+    MemorySegment nodeOff, height, parent, nodeType, chgNode, chgBase, chgTime, chgType;
     private int nodeCap = 0, chgCap = 0;
 
     /** Flatten one tree (B = 1).  Root-branch changes are not exported (density ignores them:
@@ -32,7 +32,6 @@ final class TreeFlattener {
             height = arena.allocate(8L * n + 16, 16);
             parent = arena.allocate(4L * n + 16, 16);
             nodeType = arena.allocate(n + 16, 16);
-            chgCount = arena.allocate(2L * n + 16, 16);
             nodeOff = arena.allocate(16, 8);
             chgBase = arena.allocate(16, 8);
         }
@@ -40,6 +39,7 @@ final class TreeFlattener {
             chgCap = Math.max(M, 2 * chgCap + 16);
             chgTime = arena.allocate(8L * chgCap + 16, 16);
             chgType = arena.allocate(chgCap + 16, 16);
+            chgNode = arena.allocate(2L * chgCap + 16, 16);   // owner (node Nr) of every change
         }
         nodeOff.setAtIndex(JAVA_LONG, 0, 0);
         nodeOff.setAtIndex(JAVA_LONG, 1, n);
@@ -50,10 +50,10 @@ final class TreeFlattener {
             parent.setAtIndex(JAVA_INT, nr, node.isRoot() ? -1 : node.getParent().getNr());
             nodeType.set(JAVA_BYTE, nr, (byte) node.getNodeType());
             int k = node.isRoot() ? 0 : node.getChangeCount();
-            chgCount.setAtIndex(JAVA_SHORT, nr, (short) k);
             for (int i = 0; i < k; i++) {                // youngest -> oldest
                 chgTime.setAtIndex(JAVA_DOUBLE, c, node.getChangeTime(i));
                 chgType.set(JAVA_BYTE, c, (byte) node.getChangeType(i));
+                chgNode.setAtIndex(JAVA_SHORT, c, (short) nr);
                 c++;
             }
         }

@@ -284,8 +284,9 @@ class TreeBatch:
                          self.chgBase[b0:b1 + 1] - c0, self.chgTime[c0:c1], self.chgType[c0:c1])
 
     def nbytes(self) -> int:
-        return sum(a.nbytes for a in (self.nodeOff, self.height, self.nodeType, self.chgCount,
-                                      self.chgBase, self.chgTime, self.chgType))
+        """bytes the density path moves for this batch in the owner layout (parent[] excluded)"""
+        return sum(a.nbytes for a in (self.nodeOff, self.height, self.nodeType, self.chgBase,
+                                      self.chgTime, self.chgType)) + 2 * len(self.chgTime)
 
 
 # ---------------------------------------------------------------------------- Newick

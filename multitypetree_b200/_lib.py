@@ -68,7 +68,7 @@ ABI = {
 HOST = {
     "mtt_sim_run": (VP, [C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP, C.c_uint64, C.c_int]),
     "mtt_sim_total_changes": (C.c_int64, [VP]),
-    "mtt_sim_export": (None, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),
+    "mtt_sim_export": (None, [VP, VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_sim_free": (None, [VP]),
     "mtt_rng_new": (VP, [C.c_int64]),
     "mtt_rng_free": (None, [VP]),

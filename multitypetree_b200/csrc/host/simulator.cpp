@@ -203,7 +203,7 @@ int64_t mtt_sim_total_changes(const void *h)
 // chgTime/chgType [total changes].
 void mtt_sim_export(const void *h, int64_t *nodeOff, double *height, int32_t *parent,
                     uint8_t *nodeType, uint16_t *chgCount, int64_t *chgBase, double *chgTime,
-                    uint8_t *chgType)
+                    uint8_t *chgType, uint16_t *chgNode)
 {
     const SimBatch *sb = (const SimBatch *)h;
     const int nNodes = 2 * sb->nLeaves - 1;
@@ -232,6 +232,8 @@ void mtt_sim_export(const void *h, int64_t *nodeOff, double *height, int32_t *pa
             const int64_t k = c + pos[ch.node]++;
             chgTime[k] = ch.time;
             chgType[k] = ch.type;
+            if (chgNode)
+                chgNode[k] = (uint16_t)ch.node;        // owner layout of mtt_sc_logp_owner_batch
         }
         c += run;
     }

@@ -279,9 +279,13 @@ class TreeBatch:
     def slice(self, b0: int, b1: int) -> "TreeBatch":
         n0, n1 = int(self.nodeOff[b0]), int(self.nodeOff[b1])
         c0, c1 = int(self.chgBase[b0]), int(self.chgBase[b1])
-        return TreeBatch(self.nodeOff[b0:b1 + 1] - n0, self.height[n0:n1], self.parent[n0:n1],
-                         self.nodeType[n0:n1], self.chgCount[n0:n1],
-                         self.chgBase[b0:b1 + 1] - c0, self.chgTime[c0:c1], self.chgType[c0:c1])
+        out = TreeBatch(self.nodeOff[b0:b1 + 1] - n0, self.height[n0:n1], self.parent[n0:n1],
+                        self.nodeType[n0:n1], self.chgCount[n0:n1],
+                        self.chgBase[b0:b1 + 1] - c0, self.chgTime[c0:c1], self.chgType[c0:c1])
+        owners = self.__dict__.get("_chgNode")
+        if owners is not None and len(owners) == len(self.chgTime):
+            out.__dict__["_chgNode"] = owners[c0:c1]
+        return out
 
     def nbytes(self) -> int:
         """bytes the density path moves for this batch in the owner layout (parent[] excluded)"""
@@ -483,9 +487,11 @@ def simulate_trees(B: int, nLeaves: int, d: int, m: np.ndarray, N: np.ndarray,
                        np.zeros(B * nNodes, np.int32), np.zeros(B * nNodes, np.uint8),
                        np.zeros(B * nNodes, np.uint16), np.zeros(B + 1, np.int64),
                        np.zeros(tot, np.float64), np.zeros(tot, np.uint8))
+        owners = np.zeros(tot, np.uint16)
         L.mtt_sim_export(h, _lib.ptr(tb.nodeOff), _lib.ptr(tb.height), _lib.ptr(tb.parent),
                          _lib.ptr(tb.nodeType), _lib.ptr(tb.chgCount), _lib.ptr(tb.chgBase),
-                         _lib.ptr(tb.chgTime), _lib.ptr(tb.chgType))
+                         _lib.ptr(tb.chgTime), _lib.ptr(tb.chgType), _lib.ptr(owners))
+        tb.__dict__["_chgNode"] = owners
     finally:
         L.mtt_sim_free(h)
     return tb

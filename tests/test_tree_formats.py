@@ -63,3 +63,25 @@ def test_newick_parser_metadata_forms():
     c = mtt.MultiTypeTreeFromNewick(
         "(a[&loc=NewZealand]:1,b[&loc=HongKong]:1)[&loc=HongKong]:0;", "loc", typeSet=ts)
     assert list(c.nodeType) == [1, 0, 0]
+
+
+def test_owner_list_layouts_agree():
+    """chgNode (owner layout of mtt_sc_logp_owner_batch): the simulator's native export, the
+    list derived from per-node counts, and slices of either are the same thing."""
+    m, N = mtt.synthetic_model(3)
+    tb = mtt.simulate_trees(200, 40, 3, m, N, seed=12)
+    native = tb.chgNode.copy()
+    tb.__dict__.pop("_chgNode")
+    derived = tb.chgNode
+    assert np.array_equal(native, derived) and derived.dtype == np.uint16
+    assert len(derived) == len(tb.chgTime) == int(tb.chgBase[-1])
+    # every change's owner carries that many changes, in node order
+    for b in (0, 57, 199):
+        n0, c0, c1 = int(tb.nodeOff[b]), int(tb.chgBase[b]), int(tb.chgBase[b + 1])
+        own = derived[c0:c1].astype(int)
+        assert np.all(np.diff(own) >= 0)
+        assert np.array_equal(np.bincount(own, minlength=79), tb.chgCount[n0:n0 + 79])
+    part = tb.slice(50, 120)
+    assert np.array_equal(part.chgNode, derived[int(tb.chgBase[50]):int(tb.chgBase[120])])
+    rebuilt = mtt.TreeBatch.from_trees([tb.tree(b) for b in range(5)])
+    assert np.array_equal(rebuilt.chgNode, derived[:int(tb.chgBase[5])])

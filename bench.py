@@ -552,17 +552,40 @@ def bench_retype(args):
     a = rng.integers(0, d, nBr)
     b = rng.integers(0, d, nBr)
     model = np.repeat(np.arange(chains), 3 * jobs_per_chain)
-    W = 256
+    # Uniform windows: a job rarely needs more than a few dozen uniforms (1 + 2 nVirt per branch),
+    # so the first pass ships 96 per job; jobs that report MTT_ST_NEED_MORE_UNIFORMS are
+    # resubmitted with 1024, inside the timed region; likewise 16 returned changes per branch first,
+    # 64 for the branches that had more.
+    W, W2 = 96, 1024
     u = rng.random(nJobs * W)
+    u2 = rng.random(32768 * W2)
     uOff = np.arange(nJobs + 1) * W
     pinned = mtt.lib().mtt_host_register(u.ctypes.data, u.nbytes) == 0
+    br3 = np.arange(nBr).reshape(nJobs, 3)
+
+    CAP, CAP2 = 16, 64       # changes returned per branch: first pass / resubmission
+
+    def step():
+        r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=CAP, model=model)
+        redo = (r["status"].reshape(nJobs, 3) == 5) | (r["nChg"].reshape(nJobs, 3) > CAP)
+        short = np.nonzero(redo.any(axis=1))[0]
+        if len(short):
+            if len(short) > 32768:
+                raise RuntimeError("too many short windows: %d" % len(short))
+            idx = br3[short].ravel()
+            r2 = um.retype(np.arange(len(short) + 1) * 3, t0_[idx], t1_[idx], a[idx], b[idx],
+                           u2[:len(short) * W2], np.arange(len(short) + 1) * W2, outCap=CAP2,
+                           model=model[idx])
+            r["status"][idx] = r2["status"]
+        return r, len(short)
+
     for _ in range(args.warmup):
-        r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=32, model=model)
+        r, nShort = step()
     barrier(world)
     l0 = ctx.launch_count()
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        r = um.retype(brOff, t0_, t1_, a, b, u, uOff, outCap=32, model=model)
+        r, nShort = step()
     barrier(world)
     dt = max_over_ranks(time.perf_counter() - t0, world)
     if rank != 0:
@@ -575,6 +598,7 @@ def bench_retype(args):
         "data": "synthetic",
         "config": {"workload": "cfg5: %d chains x %d NodeRetype-shaped jobs (3 branches), d=10"
                                % (chains * world, jobs_per_chain), "uniform_window": W,
+                   "resubmitted_jobs_per_step": int(nShort), "resubmit_window": W2,
                    "pinned": bool(pinned)},
         "ok_fraction": float((r["status"] == 0).mean()),
         "gpu_launches": int(ctx.launch_count() - l0)}))

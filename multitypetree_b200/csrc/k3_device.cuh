@@ -11,6 +11,7 @@ namespace {
 
 constexpr int U_WARPS = 4;          // warps per CTA
 constexpr int U_TCAP = 512;         // virtual events kept in shared memory per warp
+constexpr int U_LOGN = 4096;        // entries of the log(n) table
 
 __device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
 __device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
@@ -136,15 +137,16 @@ __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, 
     nm = warp_max(nm);
     int j = 0;
     if (nm > 0.0) {
-        const double f = floor(log_ni(nm) / log_ni(2.0));
+        // log(2.0) is the correctly rounded constant on host and device alike
+        const double f = floor(log_ni(nm) / 0.6931471805599453);
         if (f > -1.0)
             j = 1 + (int)f;
     }
-    const double scale = scalbn(1.0, j);
+    const double invScale = scalbn(1.0, -j);     // dividing by 2^j == multiplying by 2^-j, exactly
     __syncwarp();
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
-        As[e] = div_ni(As[e], scale);
+        As[e] = mul_rn(As[e], invScale);
     __syncwarp();
     mm(d, As, As, A2, rc, lane);
     mm(d, A2, A2, A4, rc, lane);
@@ -254,7 +256,7 @@ __device__ __noinline__ bool poisson_window(double lam, const double *u, long lo
 
 struct BranchSample {
     int st, nVirt;
-    double Pba;
+    double Pba, logPba;  // logPba: NaN unless the event count was drawn (then log(Pba))
     double *times;       // sorted times of the virtual events
     uint8_t *types;      // type after each virtual event
 };
@@ -262,11 +264,13 @@ struct BranchSample {
 // retypeBranch up to and including the forward-backward pass (:124-194), by one warp.  On
 // MTT_ST_OK the nVirt sorted virtual-event times and sampled types are in .times / .types
 // (shared memory, or the caller's global scratch when nVirt > U_TCAP).  tab / size / steady
-// describe the model's R^k table.  TAIL_ON_DEVICE draws the steady-state Poisson tail
+// describe the model's R^k table, logTab the elementwise log of it, logN[n] = log(n).
+// TAIL_ON_DEVICE draws the steady-state Poisson tail
 // (:96-102) from the window instead of handing it to the host.
 template <bool TAIL_ON_DEVICE>
 __device__ __forceinline__ BranchSample sample_branch(
-    int d, const double *Q, const double *R, const double *tab, int size, int steady, double mu,
+    int d, const double *Q, const double *R, const double *tab, const double *logTab,
+    const double *logN, int size, int steady, double mu,
     double t0, double t1, int a, int b, int forced, const double *u, long long nU,
     long long &pos, double *buf, const uint16_t *rc, double *sTimes, uint8_t *sTypes,
     double *gTimes, uint8_t *gTypes, int scratchCap, int lane, int stageCap = U_TCAP)
@@ -280,6 +284,7 @@ __device__ __forceinline__ BranchSample sample_branch(
     __syncwarp();
 
     int st = MTT_ST_OK, nVirt = -1;
+    double logPba = NAN;
     if (Pba == 0.0)                                                  // :137-138
         st = MTT_ST_NO_VALID_PATH;
     else if (Pba > 1.0 || Pba < 0.0)                                 // :141-144
@@ -294,7 +299,8 @@ __device__ __forceinline__ BranchSample sample_branch(
         } else {
             const double uu = u[pos++];                              // :79
             double Plow = 0.0;
-            double acc = sub_rn(-muL, log_ni(Pba));                     // :81
+            logPba = log_ni(Pba);
+            double acc = sub_rn(-muL, logPba);                          // :81
             const double log_muL = log_ni(muL);                         // :82
             int n = 0;
             while (true) {
@@ -302,14 +308,15 @@ __device__ __forceinline__ BranchSample sample_branch(
                     st = MTT_ST_NEED_MORE_POWERS;
                     break;
                 }
-                const double Rn = tab[(size_t)min(n, size - 1) * dd + a * d + b];
-                Plow = add_rn(Plow, exp_ni(add_rn(log_ni(Rn), acc)));      // :86
+                // log(R^n[a,b]) and log(n) come from tables filled with the same log()
+                const double logRn = logTab[(size_t)min(n, size - 1) * dd + a * d + b];
+                Plow = add_rn(Plow, exp_ni(add_rn(logRn, acc)));           // :86
                 if (Plow > uu) {                                     // :88-89
                     nVirt = n;
                     break;
                 }
                 n += 1;
-                acc = add_rn(acc, sub_rn(log_muL, log_ni((double)n)));  // :92
+                acc = add_rn(acc, sub_rn(log_muL, n < U_LOGN ? logN[n] : log_ni((double)n)));  // :92
                 if (!(steadyN < 0 || n < steadyN)) {                 // :94
                     st = MTT_ST_NEEDS_POISSON_TAIL;                  // :96-102 -> host
                     nVirt = n;                                       // thresh
@@ -394,6 +401,7 @@ __device__ __forceinline__ BranchSample sample_branch(
     r.st = st;
     r.nVirt = nVirt;
     r.Pba = Pba;
+    r.logPba = logPba;
     r.times = times;
     r.types = types;
     return r;

@@ -118,6 +118,26 @@ __global__ void k3_rpow_extend(int nModels, int d, const double *R, double *pow,
     }
 }
 
+// elementwise log of the valid part of every model's R^k table (drawEventCount reads
+// log(R^n[a,b]) once per candidate n: tabulating it takes the log out of the sampler's loop)
+__global__ void k3_log_table(int nModels, int dd, int powCap, const int *meta, const double *pow,
+                             double *logPow)
+{
+    const int model = blockIdx.y;
+    const long long n = (long long)meta[2 * model] * dd;
+    const size_t base = (size_t)model * powCap * dd;
+    for (long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x; e < n;
+         e += (long long)gridDim.x * blockDim.x)
+        logPow[base + e] = log_ni(pow[base + e]);
+}
+
+__global__ void k3_log_n(double *logN)
+{
+    const int n = blockIdx.x * blockDim.x + threadIdx.x;
+    if (n < U_LOGN)
+        logN[n] = log_ni((double)n);
+}
+
 __global__ void k3_expm_batch(long long n, int d, const double *Q, const int *model,
                               const double *L, double *out)
 {
@@ -185,7 +205,7 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
 struct RetypeParams {
     long long nJobs;
     int d, powCap, outCap;
-    const double *Q, *R, *mu, *pow;
+    const double *Q, *R, *mu, *pow, *logPow, *logN;
     const int *meta;
     const long long *brOff;
     const int *model;
@@ -243,7 +263,8 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
         const int a = p.typeBottom[br], b = p.typeTop[br];
         const size_t w = (size_t)blockIdx.x * U_WARPS + warp;
         const BranchSample bs = sample_branch<false>(
-            d, Q, R, p.pow + (size_t)mdl * p.powCap * dd, p.meta[2 * mdl], p.meta[2 * mdl + 1],
+            d, Q, R, p.pow + (size_t)mdl * p.powCap * dd, p.logPow + (size_t)mdl * p.powCap * dd,
+            p.logN, p.meta[2 * mdl], p.meta[2 * mdl + 1],
             p.mu[mdl], t0, t1, a, b, p.nVirtForced ? p.nVirtForced[br] : -1, u, nU, pos, buf, rc,
             sTimes, sTypes, p.scratchT + w * p.scratchCap, p.scratchTy + w * p.scratchCap,
             p.scratchCap, lane, p.tCap);
@@ -275,7 +296,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
                 }
             }
             lp = add_rn(lp, mul_rn(Q[prevType * d + prevType], sub_rn(t1, prevTime)));
-            lp = sub_rn(lp, log_ni(Pba));
+            lp = sub_rn(lp, isnan(bs.logPba) ? log_ni(Pba) : bs.logPba);
         }
         __syncwarp();
         if (lane == 0) {
@@ -330,6 +351,13 @@ int ensure_powers(mtt_ctx *ctx, int K)
         nM, d, (const double *)ctx->bufs[BUF_U_R].p, (double *)ctx->bufs[BUF_U_POW].p,
         ctx->unifPowCap, meta, K);
     MTT_CHECK_LAUNCH(ctx);
+    double *logPow = (double *)mtt_buf(ctx, BUF_U_LOGPOW, (size_t)nM * ctx->unifPowCap * dd * 8);
+    if (!logPow)
+        return MTT_ERR_CUDA;
+    k3_log_table<<<dim3(32, (unsigned)nM), 256, 0, s>>>(nM, dd, ctx->unifPowCap, meta,
+                                                        (const double *)ctx->bufs[BUF_U_POW].p,
+                                                        logPow);
+    MTT_CHECK_LAUNCH(ctx);
     std::vector<int> h(2 * nM);
     MTT_CUDA(ctx, cudaMemcpyAsync(h.data(), meta, sizeof(int) * 2 * nM, cudaMemcpyDeviceToHost, s));
     MTT_CUDA(ctx, cudaStreamSynchronize(s));
@@ -375,6 +403,11 @@ int mtt_unif_set_models(mtt_ctx *ctx, int nModels, int d, const double *m, int s
     const int wpb = 4;
     k3_update_matrices<<<(nModels + wpb - 1) / wpb, wpb * 32, 0, s>>>(nModels, d, dM, sym, dQ, dR,
                                                                       dMu);
+    MTT_CHECK_LAUNCH(ctx);
+    double *logN = (double *)mtt_buf(ctx, BUF_U_LOGN, U_LOGN * 8);
+    if (!logN)
+        return MTT_ERR_CUDA;
+    k3_log_n<<<U_LOGN / 256, 256, 0, s>>>(logN);
     MTT_CHECK_LAUNCH(ctx);
     if (ctx->unifModels != nModels || ctx->unifD != d) {
         // table geometry changed: release it
@@ -624,6 +657,8 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         p.nJobs = nJobs; p.d = d; p.powCap = ctx->unifPowCap; p.outCap = outCap;
         p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
         p.mu = (const double *)ctx->bufs[BUF_U_MU].p; p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
+        p.logPow = (const double *)ctx->bufs[BUF_U_LOGPOW].p;
+        p.logN = (const double *)ctx->bufs[BUF_U_LOGN].p;
         p.meta = (const int *)ctx->bufs[BUF_U_META].p;
         p.brOff = dBrOff; p.model = dModel; p.tBottom = dT0; p.tTop = dT1; p.typeBottom = dA;
         p.typeTop = dB; p.nVirtForced = dForced; p.uniforms = dU; p.uOff = dUOff;

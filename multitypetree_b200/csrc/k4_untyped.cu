@@ -41,7 +41,7 @@ struct ParticleParams {
     long long nTrees;
     int nParticles, d, powCap;
     int eCap, tCap, nCap;            // stage capacities (multiples of 8)
-    const double *Q, *R, *mu, *pow;
+    const double *Q, *R, *mu, *pow, *logPow, *logN;
     const int *meta;
     const int *model;                // per tree
     const double *N;                 // [nModels][d]
@@ -96,6 +96,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
     const int mdl = p.model[tree];
     const double *Q = p.Q + (size_t)mdl * dd, *R = p.R + (size_t)mdl * dd;
     const double *tab = p.pow + (size_t)mdl * p.powCap * dd;
+    const double *logTab = p.logPow + (size_t)mdl * p.powCap * dd;
     const int size = p.meta[2 * mdl], steady = p.meta[2 * mdl + 1];
     const double mu = p.mu[mdl];
     const long long n0 = p.nodeOff[tree];
@@ -196,7 +197,8 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
             anc = parent[anc];
         const double t0 = height[leaf], t1 = height[anc];
         const int b = nodeType[anc];
-        const BranchSample bs = sample_branch<true>(d, Q, R, tab, size, steady, mu, t0, t1, a, b,
+        const BranchSample bs = sample_branch<true>(d, Q, R, tab, logTab, p.logN, size, steady, mu, t0,
+                                                    t1, a, b,
                                                     -1, u, nU, pos, buf, rc, sTimes, sTypes,
                                                     nullptr, nullptr, 0, lane, tCap);
         if (bs.st == MTT_ST_NEED_MORE_UNIFORMS || bs.st == MTT_ST_NEED_MORE_POWERS) {
@@ -240,7 +242,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
             }
             prevNode = parent[prevNode];
         }
-        lp = sub_rn(lp, log_ni(bs.Pba));
+        lp = sub_rn(lp, isnan(bs.logPba) ? log_ni(bs.Pba) : bs.logPba);
         w = sub_rn(w, lp);                                                       // :136
         __syncwarp();
     }
@@ -473,6 +475,8 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
         p.mu = (const double *)ctx->bufs[BUF_U_MU].p;
         p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
+        p.logPow = (const double *)ctx->bufs[BUF_U_LOGPOW].p;
+        p.logN = (const double *)ctx->bufs[BUF_U_LOGN].p;
         p.meta = (const int *)ctx->bufs[BUF_U_META].p;
         p.model = dModel; p.N = dN; p.nodeOff = dNodeOff; p.height = dHeight; p.parent = dParent;
         p.leafType = dLeafType; p.orderOff = dOrderOff; p.leafOrder = dOrder; p.uniforms = dU;

@@ -39,7 +39,7 @@ enum BufId {
     BUF_D_MODEL = 0, BUF_D_N, BUF_D_NODEOFF, BUF_D_HEIGHT, BUF_D_PARENT, BUF_D_NODETYPE,
     BUF_D_CHGCOUNT, BUF_D_CHGBASE, BUF_D_CHGTIME, BUF_D_CHGTYPE, BUF_D_LOGP, BUF_D_VALID,
     BUF_D_QUEUE, BUF_D_CHGNODE,
-    BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
+    BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
     BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6,
     BUF_P_MODEL, BUF_P_N, BUF_P_NODEOFF, BUF_P_HEIGHT, BUF_P_PARENT, BUF_P_LEAFTYPE,

@@ -210,8 +210,9 @@ __device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, i
 // over shared memory.
 constexpr int W_WARPS = 8;                // warps per CTA
 constexpr uint32_t KEY_PAD = 0xffffffffu;
-constexpr int IDX_BITS = 9;               // event index inside a tree (E <= 512)
-constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;
+// sort key = quantised time | event index inside the tree: 9 index bits up to 512 events,
+// 10 in the 1024-event stage (one bit less of time resolution; ties are repaired exactly)
+__host__ __device__ constexpr int idx_bits(int EMAX) { return EMAX > 512 ? 10 : 9; }
 
 template <bool HAS_PARENT, int EMAX>
 struct WarpStage {
@@ -228,6 +229,7 @@ struct WarpSmem {
     alignas(16) uint32_t keys[EMAX];      // time-ordered (quantised time | event index)
     alignas(8) unsigned long long bar;
     alignas(8) uint16_t desc[EMAX];       // kind | from | to per event
+    alignas(16) uint32_t keys2[EMAX > 512 ? EMAX : 4];   // second buffer of the 4-run merge
 };
 
 struct TreeSpan {
@@ -415,9 +417,12 @@ __device__ __forceinline__ void cnt_accumulate(Counts<NW> &c, uint32_t ds, const
 template <int NW, bool HAS_PARENT, int EMAX>
 __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                                             const StageLayout &L, uint16_t *desc,
-                                            uint32_t *keys, int n, int M, const ModelTab *tab,
-                                            int d, int lane, bool &okOut)
+                                            uint32_t *keys, uint32_t *keys2, int n, int M,
+                                            const ModelTab *tab, int d, int lane, bool &okOut)
 {
+    constexpr int IDX_BITS = idx_bits(EMAX);
+    constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
+    constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;
     const int E = n + M;
     const int nLeaves = (n + 1) >> 1;
     const double *sH = reinterpret_cast<const double *>(st->time + L.hOff);
@@ -525,8 +530,9 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
 
     // ---- phase B: order.  256 events at a time through the register network.  One run goes
     //      straight to the order list; two runs are stored as keys and merged (merge path).
-    constexpr int LB = EMAX - 256;       // capacity of the second run (EMAX = 384 or 512)
-    int Epad = (E > 256) ? EMAX : 256;
+    constexpr int E2 = EMAX < 512 ? EMAX : 512;      // stage size of the two-run case
+    constexpr int LB = E2 - 256;                     // capacity of its second run
+    int Epad = (E > 256) ? ((EMAX > 512 && E > 512) ? EMAX : E2) : 256;
     asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
     // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
     // accumulated while the ordered events are still in registers
@@ -552,8 +558,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
             uint32_t w[4];
 #pragma unroll
             for (int k = 0; k < 4; k++) {
-                const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & 511u);
-                const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & 511u);
+                const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & IDX_MASK);
+                const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & IDX_MASK);
                 w[k] = a | (b << 16);
                 cnt_accumulate<NW>(local, (a == 0xffffu) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
                                                          : (uint32_t)desc[a], tab);
@@ -561,8 +567,8 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                                                          : (uint32_t)desc[b], tab);
             }
             *reinterpret_cast<uint4 *>(order + 8 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else if (base == 0 || 8 * lane < LB) {
-            // second run: only its first LB keys can be real (E <= EMAX), padding sorts last
+        } else if (Epad > 512 || base == 0 || 8 * lane < LB) {
+            // two runs: only the first LB keys of the second can be real, padding sorts last
             uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
             dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
             dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
@@ -570,11 +576,46 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
     }
     __syncwarp();
     if (EMAX > 256 && Epad != 256) {
-        // merge path: lane produces outputs [per*lane, per*lane+per) of the two ascending runs
-        constexpr int PERM = EMAX / 32;
+        // merge path: lane produces outputs [per*lane, per*lane+per) of two ascending runs
+        auto merge_keys = [&](const uint32_t *A, const uint32_t *B, uint32_t *out) {
+            // two 256-key runs -> 512 keys (first level of the four-run case)
+            const int diag = 16 * lane;
+            int a0 = max(0, diag - 256), a1 = min(diag, 256);
+            while (a0 < a1) {
+                const int mid = (a0 + a1) >> 1;
+                if (A[mid] <= B[diag - 1 - mid])
+                    a0 = mid + 1;
+                else
+                    a1 = mid;
+            }
+            int i = a0, j = diag - a0;
+            uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < 256) ? B[j] : KEY_PAD;
+#pragma unroll 1
+            for (int q = 0; q < 16; q++) {
+                const bool takeA = ka <= kb;
+                out[diag + q] = takeA ? ka : kb;
+                if (takeA) {
+                    i++;
+                    ka = (i < 256) ? A[i] : KEY_PAD;
+                } else {
+                    j++;
+                    kb = (j < 256) ? B[j] : KEY_PAD;
+                }
+            }
+        };
         const uint32_t *A = keys, *B = keys + 256;
-        const int diag = PERM * lane;
-        int a0 = max(0, diag - LB), a1 = min(diag, 256);
+        int la = 256, lb = LB;
+        if (EMAX > 512 && Epad > 512) {
+            merge_keys(keys, keys + 256, keys2);
+            merge_keys(keys + 512, keys + 768, keys2 + 512);
+            __syncwarp();
+            A = keys2;
+            B = keys2 + 512;
+            la = lb = 512;
+        }
+        const int perm = Epad >> 5;
+        const int diag = perm * lane;
+        int a0 = max(0, diag - lb), a1 = min(diag, la);
         while (a0 < a1) {
             const int mid = (a0 + a1) >> 1;
             if (A[mid] <= B[diag - 1 - mid])
@@ -583,20 +624,20 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                 a1 = mid;
         }
         int i = a0, j = diag - a0;
-        uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < LB) ? B[j] : KEY_PAD;
+        uint32_t ka = (i < la) ? A[i] : KEY_PAD, kb = (j < lb) ? B[j] : KEY_PAD;
 #pragma unroll 1
-        for (int q = 0; q < PERM; q++) {
+        for (int q = 0; q < perm; q++) {
             const bool takeA = ka <= kb;
             const uint32_t out = takeA ? ka : kb;
-            order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & 511u);
+            order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & IDX_MASK);
             cnt_accumulate<NW>(local, (out == KEY_PAD) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
-                                                      : (uint32_t)desc[out & 511u], tab);
+                                                      : (uint32_t)desc[out & IDX_MASK], tab);
             if (takeA) {
                 i++;
-                ka = (i < 256) ? A[i] : KEY_PAD;
+                ka = (i < la) ? A[i] : KEY_PAD;
             } else {
                 j++;
-                kb = (j < LB) ? B[j] : KEY_PAD;
+                kb = (j < lb) ? B[j] : KEY_PAD;
             }
         }
         __syncwarp();
@@ -754,7 +795,7 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
 // kernel.  Persistent warps, one tree at a time per warp: lane 0 launches the bulk copies of
 // the tree's array slices (TMA engine), the warp waits on its mbarrier, orders and scans.
 template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int EMAX>
-__global__ void __launch_bounds__(W_WARPS * 32, (EMAX <= 384) ? 4 : 3)
+__global__ void __launch_bounds__(W_WARPS * 32, (EMAX <= 384) ? 4 : (EMAX <= 512 ? 3 : 1))
 k1_density_warp(const K1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -802,7 +843,8 @@ k1_density_warp(const K1Params p)
             phase ^= 1u;
             bool ok = true;
             const double acc = process_tree<NW, HAS_PARENT, EMAX>(&ws->st, L, ws->desc, ws->keys,
-                                                                 cur.n, cur.M, tab, d, lane, ok);
+                                                                 ws->keys2, cur.n, cur.M, tab, d,
+                                                                 lane, ok);
             if (lane == 0) {
                 if (HAS_PARENT && p.valid)
                     p.valid[t] = ok ? 1 : 0;
@@ -1143,6 +1185,8 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
         return launch_warp_any<NW, 384>(ctx, p);
     if (maxEvents > 0 && maxEvents <= 512)
         return launch_warp_any<NW, 512>(ctx, p);
+    if (maxEvents > 0 && maxEvents <= 1024)         // four sorted runs, two merge levels
+        return launch_warp_any<NW, 1024>(ctx, p);
     // some trees may exceed the warp path: they are queued and consumed by the block kernel;
     // the queue counter is zeroed again for the next call
     int rc = launch_warp_any<NW, 512>(ctx, p);

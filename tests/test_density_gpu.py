@@ -57,9 +57,11 @@ def test_simulated_small_trees(ctx, n, d, B):
     _check(tb, m, N, ctx, checkValidity=True)
 
 
-@pytest.mark.parametrize("n,d,B", [(300, 2, 64), (1000, 4, 32), (5000, 8, 8), (7000, 2, 2)])
+@pytest.mark.parametrize("n,d,B", [(300, 2, 64), (400, 3, 200), (350, 10, 64), (1000, 4, 32),
+                                   (5000, 8, 8), (7000, 2, 2)])
 def test_simulated_large_trees(ctx, n, d, B):
-    """CTA-per-tree path (512 < E <= 16384): configs 3 and 4 tree sizes."""
+    """1024-event warp stage (512 < E <= 1024) and the CTA-per-tree path (E <= 16384):
+    configs 3 and 4 tree sizes."""
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(B, n, d, m, N, seed=3000 + n)
     _check(tb, m, N, ctx)
@@ -237,10 +239,14 @@ def _pad_changes(tree, target_M):
 
 @pytest.mark.parametrize("n,targets", [(128, (255, 256, 257, 258)), (250, (510, 511, 512, 513, 514)),
                                        (64, (127, 128, 129)), (190, (381, 382, 383, 384)),
-                                       (190, (383, 384, 385, 386)), (150, (299, 300, 383, 384))])
+                                       (190, (383, 384, 385, 386)), (150, (299, 300, 383, 384)),
+                                       (450, (1021, 1022, 1023, 1024)),
+                                       (450, (1023, 1024, 1025, 1026)),
+                                       (300, (599, 767, 768, 769, 770))])
 def test_event_count_boundaries(ctx, n, targets):
-    """E = nodes + changes right at the 256 / 384 / 512 limits of the warp path (one run, two
-    runs + merge in the 384- and 512-event stages, hand-over to the CTA kernel)."""
+    """E = nodes + changes right at the 256 / 384 / 512 / 768 / 1024 limits of the warp path (one
+    run, two runs + merge in the 384- and 512-event stages, three and four runs with two merge
+    levels in the 1024-event stage, hand-over to the CTA kernel)."""
     m, N = mtt.synthetic_model(2)
     pool = mtt.simulate_trees(64, n, 2, m * 0.01, N, seed=600 + n)      # few migrations
     trees, want_E = [], []

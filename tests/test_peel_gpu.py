@@ -30,7 +30,8 @@ def _oracle(al, par, hgt, sm, clock=1.0, nThreads=8):
 @pytest.mark.parametrize("n,sites,gamma,pInv,missing,B", [
     (2, 50, 0, 0.0, 0.0, 4), (3, 200, 0, 0.0, 0.0, 8), (5, 300, 4, 0.0, 0.1, 16),
     (17, 1000, 0, 0.2, 0.0, 16), (64, 2000, 4, 0.1, 0.05, 8), (128, 2000, 0, 0.0, 0.0, 8),
-    (100, 700, 2, 0.0, 0.0, 8), (33, 400, 8, 0.3, 0.2, 4), (200, 513, 3, 0.0, 0.0, 5)])
+    (100, 700, 2, 0.0, 0.0, 8), (33, 400, 8, 0.3, 0.2, 4), (200, 513, 3, 0.0, 0.0, 5),
+    (40, 300, 5, 0.0, 0.1, 3), (40, 300, 6, 0.1, 0.0, 3), (300, 260, 7, 0.0, 0.0, 3)])
 def test_logl_matches_oracle(ctx, n, sites, gamma, pInv, missing, B):
     par, hgt, _ = _trees(B, n, seed=10 + n)
     f = np.array([.1, .2, .3, .4])

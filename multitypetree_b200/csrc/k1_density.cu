@@ -208,7 +208,8 @@ __device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, i
 // unrolled version (13k SASS instructions) spent most of its cycles in instruction-fetch
 // stalls.  Only the 256-key sorting network is unrolled; everything else is a rolled loop
 // over shared memory.
-constexpr int W_WARPS = 8;                // warps per CTA
+// warps per CTA: 8, or 5 in the 1024-event stage so that two CTAs (10 warps) fit an SM
+__host__ __device__ constexpr int warps_per_cta(int EMAX) { return EMAX > 512 ? 5 : 8; }
 constexpr uint32_t KEY_PAD = 0xffffffffu;
 // sort key = quantised time | event index inside the tree: 9 index bits up to 512 events,
 // 10 in the 1024-event stage (one bit less of time resolution; ties are repaired exactly)
@@ -795,11 +796,13 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
 // kernel.  Persistent warps, one tree at a time per warp: lane 0 launches the bulk copies of
 // the tree's array slices (TMA engine), the warp waits on its mbarrier, orders and scans.
 template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int EMAX>
-__global__ void __launch_bounds__(W_WARPS * 32, (EMAX <= 384) ? 4 : (EMAX <= 512 ? 3 : 1))
+__global__ void __launch_bounds__(warps_per_cta(EMAX) * 32,
+                                  (EMAX <= 384) ? 4 : (EMAX <= 512 ? 3 : 2))
 k1_density_warp(const K1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tabs = reinterpret_cast<ModelTab *>(smem_raw);
+    constexpr int W_WARPS = warps_per_cta(EMAX);
     constexpr int nTabs = PER_TREE_MODEL ? W_WARPS : 1;
     using WS = WarpSmem<HAS_PARENT, EMAX>;
     WS *wsAll = reinterpret_cast<WS *>(smem_raw + sizeof(ModelTab) * nTabs);
@@ -1119,7 +1122,7 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
 template <int NW, bool HP, bool PT, int EMAX>
 int launch_warp(mtt_ctx *ctx, const K1Params &p)
 {
-    constexpr int W = W_WARPS;
+    constexpr int W = warps_per_cta(EMAX);
     size_t smem = sizeof(ModelTab) * (PT ? W : 1) + sizeof(WarpSmem<HP, EMAX>) * W;
     auto kern = k1_density_warp<NW, HP, PT, EMAX>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -1188,8 +1191,10 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
     if (maxEvents > 0 && maxEvents <= 1024)         // four sorted runs, two merge levels
         return launch_warp_any<NW, 1024>(ctx, p);
     // some trees may exceed the warp path: they are queued and consumed by the block kernel;
-    // the queue counter is zeroed again for the next call
-    int rc = launch_warp_any<NW, 512>(ctx, p);
+    // the queue counter is zeroed again for the next call.  A known bound above 1024 means
+    // mid-size and large trees: the 1024-event stage takes what it can.
+    int rc = (maxEvents > 1024) ? launch_warp_any<NW, 1024>(ctx, p)
+                                : launch_warp_any<NW, 512>(ctx, p);
     if (rc != MTT_OK)
         return rc;
     rc = launch_block<NW>(ctx, p, Ecap, 1, 0);

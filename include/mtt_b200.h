@@ -28,13 +28,18 @@
  *   parent  [nodes] int32  tree-local parent Nr, -1 for the root (may be NULL when neither
  *                          validity checking nor peeling is requested)
  *   nodeType[nodes] uint8  MultiTypeNode.getNodeType()           (MultiTypeNode.java:100-102)
- *   chgCount[nodes] uint16 MultiTypeNode.getChangeCount()        (:43-45); the root entry
- *                          must be 0 unless parent[] is given (root-branch changes are
- *                          ignored, distributions/StructuredCoalescentTreeDensity.java:161-162)
- *   chgBase [B+1]  int64   offsets into chgTime/chgType; a tree's changes are stored node by
- *                          node in Nr order, each branch youngest -> oldest
+ *   chgBase [B+1]  int64   offsets into chgTime/chgType/chgNode; a tree's changes are stored
+ *                          node by node in Nr order, each branch youngest -> oldest
  *   chgTime [changes] f64  MultiTypeNode.getChangeTime(idx)      (:65-67)
  *   chgType [changes] uint8 MultiTypeNode.getChangeType(idx)     (:54-56)
+ *   which branch a change sits on, in one of two encodings:
+ *   chgNode [changes] uint16 tree-local Nr of the node below the change (OWNER layout,
+ *                          mtt_sc_logp_owner_batch*: what the kernels read), or
+ *   chgCount[nodes] uint16 MultiTypeNode.getChangeCount()        (:43-45) (COUNTS layout,
+ *                          mtt_sc_logp_batch*: expanded to the owner layout on the device).
+ *                          Root-branch changes must not be listed unless parent[] is given
+ *                          (they are ignored, distributions/StructuredCoalescentTreeDensity
+ *                          .java:161-162)
  * Compact integer widths are part of the contract: the density path is HBM/PCIe bound and
  * these arrays ARE its traffic (12 bytes per event algorithmic).
  */

@@ -243,6 +243,12 @@ int mtt_peel_set_hky(mtt_peel *h, double kappa);
  * parent/height [B][2*nTips-1] (tree SoA above).  logL[B] = sum_p weight_p * logL_p. */
 int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
                         double *logL);
+/* same with a substitution / clock parameter set PER TREE -- kappa[B] and branchRate[B] (NULL =
+ * the handle's rate): B parameter proposals (BEAST ScaleOperator on hky.kappa / mutationRate,
+ * examples/structuredCoalescent.xml:629-640) or B chains with their own parameters in one call. */
+int mtt_peel_logl_batch_params(mtt_peel *h, int64_t B, const int32_t *parent,
+                               const double *height, const double *kappa,
+                               const double *branchRate, double *logL);
 /* same with explicit transition matrices mats[B][2*nTips-1][nCat][16] (row = parent state),
  * for substitution models other than HKY (root entry unused). */
 int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,

@@ -51,6 +51,7 @@ struct mtt_peel {
     double *dMatsIn = nullptr; size_t matsInCap = 0;
     double *dLogL = nullptr; size_t logLCap = 0;
     int *dInfo = nullptr; size_t infoCap = 0;   // per tree: max slots used (or -1 = bad tree)
+    double *dTreeParams = nullptr; size_t treeParamsCap = 0;   // per tree (kappa, branchRate)
     int *dMaxSlots = nullptr;                   // max over the chunk of the above
     int *hMaxSlots = nullptr;                   // pinned host copy
 };
@@ -117,7 +118,7 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
-           int *info, int *maxSlotsAll, int xl)
+           int *info, int *maxSlotsAll, int xl, const double *treeParams)
 {
     extern __shared__ int smi[];
     const int N = 2 * n - 1, nOps = n - 1;
@@ -252,6 +253,10 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
     // ---- emission: ops and, in op order, the transition matrices of both children
     // mats[op][child j][category c][16]
     const double *catRates = site, *freqs = site + 2 * C;
+    if (treeParams) {                       // this tree's own (kappa, clock rate)
+        kappa = treeParams[2 * (size_t)b];
+        branchRate = treeParams[2 * (size_t)b + 1];
+    }
     const double *height = heightAll ? heightAll + (size_t)b * N : nullptr;
     const double *matsIn = matsInAll ? matsInAll + (size_t)b * N * C * 16 : nullptr;
     int myMax = 0;
@@ -782,7 +787,8 @@ int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *pa
 
 // run the pipeline on device-resident parent/height (or matsIn) for a chunk of trees
 int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeight,
-               const double *dMatsIn, double *dLogL, double *patternLogL)
+               const double *dMatsIn, double *dLogL, double *patternLogL,
+               const double *dTreeParams = nullptr)
 {
     mtt_ctx *ctx = h->ctx;
     const int n = h->nTips, C = h->nCat, N = 2 * n - 1, nOps = n - 1;
@@ -810,7 +816,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
     MTT_CUDA(ctx, cudaMemsetAsync(h->dMaxSlots, 0, sizeof(int), ctx->stream));
     k2_prepare<<<(unsigned)B, PREP_THREADS, prepSmem, ctx->stream>>>(
         n, C, dParent, dHeight, dMatsIn, h->dSite, h->branchRate, h->kappa, (PeelOp *)h->dOps,
-        h->dMats, h->dInfo, h->dMaxSlots, cats_across_lanes(C) ? 1 : 0);
+        h->dMats, h->dInfo, h->dMaxSlots, cats_across_lanes(C) ? 1 : 0, dTreeParams);
     MTT_CHECK_LAUNCH(ctx);
     // the number of parked partial vectors sizes the peel kernel's shared memory (a few for
     // coalescent-shaped trees, up to floor(log2 n) for balanced ones): read it back
@@ -899,7 +905,8 @@ int mtt_peel_destroy(mtt_peel *h)
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->stream);
     void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart, h->dCold,
-                    h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots};
+                    h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots,
+                    h->dTreeParams};
     if (h->hMaxSlots)
         cudaFreeHost(h->hMaxSlots);
     for (void *p : ptrs)
@@ -1002,7 +1009,8 @@ int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const
 }
 
 static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
-                     const double *mats, double *logL, double *patternLogL)
+                     const double *mats, double *logL, double *patternLogL,
+                     const double *kappaPerTree = nullptr, const double *ratePerTree = nullptr)
 {
     mtt_ctx *ctx = h->ctx;
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1043,7 +1051,20 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
         }
         if (patternLogL)
             dPat = h->dHeight;
-        rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat);
+        const double *dTP = nullptr;
+        if (kappaPerTree) {
+            std::vector<double> tp((size_t)nb * 2);
+            for (long long i = 0; i < nb; i++) {
+                tp[2 * i] = kappaPerTree[b0 + i];
+                tp[2 * i + 1] = ratePerTree ? ratePerTree[b0 + i] : h->branchRate;
+            }
+            if ((rc = grow(ctx, h->dTreeParams, h->treeParamsCap, (size_t)nb * 16)) != MTT_OK)
+                return rc;
+            MTT_CUDA(ctx, cudaMemcpy(h->dTreeParams, tp.data(), (size_t)nb * 16,
+                                     cudaMemcpyHostToDevice));
+            dTP = h->dTreeParams;
+        }
+        rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat, dTP);
         if (rc != MTT_OK)
             return rc;
         // the upload buffers are reused by the next chunk
@@ -1069,6 +1090,20 @@ int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const dou
     if (B == 0)
         return MTT_OK;
     return peel_host(h, B, parent, height, nullptr, logL, nullptr);
+}
+
+int mtt_peel_logl_batch_params(mtt_peel *h, int64_t B, const int32_t *parent,
+                               const double *height, const double *kappa,
+                               const double *branchRate, double *logL)
+{
+    int rc = check_ready(h, false);
+    if (rc != MTT_OK)
+        return rc;
+    if (B < 0 || !parent || !height || !kappa || !logL)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_batch_params: bad arguments");
+    if (B == 0)
+        return MTT_OK;
+    return peel_host(h, B, parent, height, nullptr, logL, nullptr, kappa, branchRate);
 }
 
 int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,

@@ -176,6 +176,23 @@ class TreeLikelihood:
                                                       _lib.ptr(out)))
         return out
 
+    def calculateLogPBatchParams(self, parent: np.ndarray, height: np.ndarray, kappa,
+                                 branchRate=None) -> np.ndarray:
+        """One (kappa, clock rate) per tree: B parameter proposals or B chains in one call
+        (mtt_peel_logl_batch_params).  branchRate None = the handle's rate for every tree; it
+        multiplies the category rates exactly as ``mutationRate * clock rate`` does in
+        ``update_models``."""
+        par = _lib.as_c(parent, np.int32)
+        h = _lib.as_c(height, np.float64)
+        B = par.shape[0]
+        kap = _lib.as_c(np.broadcast_to(np.asarray(kappa, np.float64), (B,)), np.float64)
+        rate = None if branchRate is None else _lib.as_c(
+            np.broadcast_to(np.asarray(branchRate, np.float64), (B,)), np.float64)
+        out = np.empty(B, np.float64)
+        self.ctx.check(_lib.lib().mtt_peel_logl_batch_params(
+            self._h, B, _lib.ptr(par), _lib.ptr(h), _lib.ptr(kap), _lib.ptr(rate), _lib.ptr(out)))
+        return out
+
     def calculateLogPBatchMats(self, parent: np.ndarray, mats: np.ndarray) -> np.ndarray:
         """Explicit transition matrices mats[B][2n-1][nCat][16] (any substitution model)."""
         par = _lib.as_c(parent, np.int32)

@@ -163,6 +163,32 @@ def test_deep_trees_in_sub_batches(ctx):
     tl.close()
 
 
+def test_per_tree_substitution_parameters(ctx):
+    """mtt_peel_logl_batch_params: one (kappa, clock rate) per tree -- B parameter proposals or
+    B chains in a single call -- against the oracle evaluated tree by tree."""
+    n, B = 60, 12
+    par, hgt, _ = _trees(B, n, seed=91)
+    f = np.array([.15, .35, .3, .2])
+    tips = simulate_alignment(par[0], hgt[0], 600, 2.0, f, 0.05, seed=4, missing=0.03)
+    al = Alignment(states=tips)
+    for gamma in (0, 4):
+        sm = SiteModel(HKY(2.0, f), mutationRate=0.05, gammaCategoryCount=gamma, shape=0.7)
+        tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+        rng = np.random.default_rng(gamma)
+        kappa = rng.uniform(0.5, 6.0, B)
+        rate = rng.uniform(0.3, 3.0, B)
+        got = tl.calculateLogPBatchParams(par, hgt, kappa, rate)
+        rates, props = sm.category_rates_and_proportions()
+        want = np.array([orc.tree_likelihood(al.patterns, al.patternWeight, par[b], hgt[b],
+                                             rates, props, f, kappa[b], branchRate=rate[b])
+                         for b in range(B)])
+        np.testing.assert_allclose(got, want, rtol=RTOL)
+        # rate omitted = the handle's clock rate; a scalar kappa broadcasts
+        same = tl.calculateLogPBatchParams(par, hgt, 2.0)
+        np.testing.assert_allclose(same, tl.calculateLogPBatch(par, hgt), rtol=1e-14)
+        tl.close()
+
+
 def test_explicit_matrices_mode(ctx):
     """mtt_peel_logl_batch_mats: caller-provided per-node transition matrices (any model)."""
     n, B = 40, 6

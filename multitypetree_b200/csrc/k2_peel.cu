@@ -9,17 +9,21 @@
 // Design (full re-evaluation of B candidate trees that share one alignment):
 //   k2_prepare  one CTA per tree.  Builds child lists from parent[], orders the post-order
 //               traversal Sethi-Ullman style (the child needing more live partials first) so
-//               that at most ~log2(n)+1 partial vectors are ever live, assigns each internal
-//               node a slot, and writes the traversal as a list of ops together with the two
-//               child transition matrices of every op IN OP ORDER (HKY closed form evaluated
-//               here from the node heights, or copied from caller matrices).
+//               that at most ~log2(n)+1 partial vectors are ever live, numbers the slots of
+//               parked vectors from the leaves up (small subtrees use slots 0, 1), and writes
+//               the traversal as a list of ops together with the two child transition matrices
+//               of every op IN OP ORDER (HKY closed form evaluated here from the node heights,
+//               or copied from caller matrices).
 //   k2_peel     grid = (pattern tiles, trees).  A CTA owns a tile of patterns of one tree and
-//               runs the WHOLE traversal for it: the live partial vectors stay in shared
-//               memory (thread-private columns: no synchronisation between ops), op lists and
-//               transition matrices stream through shared memory in stages with 1-D bulk async
-//               copies (TMA engine, mbarrier completion), tips are read as 1-byte states.
-//               Partials never touch HBM: traffic is tip states + the op/matrix stream, and the
-//               kernel is bound by the FP64 pipe and shared-memory bandwidth instead of HBM.
+//               runs the WHOLE traversal for it: the previous op's result stays in registers,
+//               parked partial vectors are thread-private columns (no synchronisation between
+//               ops) -- slots 0-1 in shared memory, the rarely used deeper ones in an
+//               L2-resident global scratch -- op lists and transition matrices stream through
+//               shared memory in stages with 1-D bulk async copies (TMA engine, mbarrier
+//               completion), tips are read as 1-byte states.  Partials make no round trip
+//               through HBM: traffic is tip states + the op/matrix stream, and the kernel is
+//               bound by instruction issue / the FP64 pipe instead of HBM.  Rate categories
+//               (2, 4, 8) sit in adjacent lanes, one category per thread.
 //   k2_finalize fixed-order sum of the per-tile partial sums -> logL[tree].
 // fp64 throughout; rescaling follows BeerLikelihoodCore.scalePartials (threshold 1e-100,
 // always on -- results agree with the unscaled path to rounding whenever that path is finite).
@@ -424,7 +428,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
 {
     using Cfg = PeelCfg<C>;
     extern __shared__ __align__(16) unsigned char smem[];
-    // layout: [2 stages: ops | mats][barriers][stack nSlots*C*4*PPT*TPT doubles]
+    // layout: [2 stages: ops | mats][barriers][smemSlots parked vectors of CR*4*PPT*TPT doubles]
     unsigned char *stageBase = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::STAGE_BYTES);
     double *stackBase = reinterpret_cast<double *>(smem + 2 * Cfg::STAGE_BYTES + 16);

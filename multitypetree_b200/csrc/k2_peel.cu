@@ -113,12 +113,13 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 // rounds is the depth of the tree):
 //   bottom-up  isize(v) = internal nodes in the subtree, need(v) = Sethi-Ullman label + which
 //              child is evaluated first (the one needing more live partial vectors)
-//   top-down   istart(v) = index of the first op of the subtree, pd(v) = parked vectors live
-//              while the subtree is evaluated
+//   top-down   istart(v) = index of the first op of the subtree
 //   emission   op index of v = istart(v) + isize(v) - 1 (post-order: first subtree, second
 //              subtree, node); a first child whose sibling is internal parks its result in
-//              slot pd(parent); matrices of both children written in op order.
-// shared: int left[N], right[N]; u16 isize[N], istart[N]; u8 need[N], pd[N], state[N]
+//              slot need(sibling) - 1 -- above everything the sibling's subtree will park, so
+//              slots are numbered from the leaves up; matrices of both children written in op
+//              order.
+// shared: int left[N], right[N]; u16 isize[N], istart[N]; u8 need[N], (spare)[N], state[N]
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
@@ -128,7 +129,7 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
     const int N = 2 * n - 1, nOps = n - 1;
     int *left = smi, *right = smi + N;
     uint16_t *isize = reinterpret_cast<uint16_t *>(smi + 2 * N), *istart = isize + N;
-    uint8_t *need = reinterpret_cast<uint8_t *>(istart + N), *pd = need + N, *state = pd + N;
+    uint8_t *need = reinterpret_cast<uint8_t *>(istart + N), *state = need + 2 * N;
     __shared__ int sRoot, sBad, sMaxSlots, sProgress;
 
     const int b = blockIdx.x, tid = threadIdx.x;
@@ -215,7 +216,6 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
     // ---- top-down sweep (state: 1 = not yet placed, 3 = placed)
     if (tid == 0) {
         istart[root] = 0;
-        pd[root] = 0;
         state[root] = 3;
     }
     for (int round = 0; round < N; round++) {
@@ -232,14 +232,7 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
                 continue;
             const bool pRightFirst = need[pp] & 0x80;
             const int first = pRightFirst ? right[pp] : left[pp];
-            const int second = pRightFirst ? left[pp] : right[pp];
-            if (v == first) {
-                istart[v] = istart[pp];
-                pd[v] = pd[pp];
-            } else {
-                istart[v] = (uint16_t)(istart[pp] + isize[first]);
-                pd[v] = (uint8_t)(pd[pp] + ((first >= n && second >= n) ? 1 : 0));
-            }
+            istart[v] = (v == first) ? istart[pp] : (uint16_t)(istart[pp] + isize[first]);
             state[v] = 4;
             progressed = true;
         }

@@ -58,13 +58,20 @@ class ClockSampler:
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        # One poller for the whole job: rank 0 watches every GPU in use (eight concurrent
+        # nvidia-smi loops take driver locks that show up in steps with a host sync).
         self.index, self.lines, self.proc = index, [], None
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.active = int(os.environ.get("RANK", "0")) == 0
 
     def __enter__(self):
+        if not self.active:
+            return self
         try:
+            gpus = ",".join(str(i) for i in range(self.world)) if self.world > 1 else str(self.index)
             self.proc = subprocess.Popen(
-                ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                ["nvidia-smi", "-i", gpus, "--query-gpu=" + self.Q,
+                 "--format=csv,noheader,nounits", "-lms", "200"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()

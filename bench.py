@@ -375,8 +375,10 @@ def bench_peel(args):
     nN = 2 * n - 1
     par, hgt = tb.parent.reshape(B, nN), tb.height.reshape(B, nN)
     f = np.array([.25] * 4)
-    clock = 0.2 / float(hgt[0].max())
+    # one alignment for the whole job: every rank evolves the same sites down the same reference
+    # tree at the same clock rate, so the ranks do equal work (weak scaling over trees)
     ref = mtt.simulate_trees(1, n, d, m, N, seed=3000)
+    clock = 0.2 / float(ref.height.max())
     al = Alignment(states=simulate_alignment(ref.parent, ref.height, sites, 2.0, f, clock, seed=3000))
     P = al.getPatternCount()
     ctx = mtt.Context(local)
@@ -412,6 +414,9 @@ def bench_peel(args):
             step()
         e1.record(stream)
         barrier(world)
+    own_ms = e0.elapsed_time(e1) / args.steps
+    if world > 1:
+        print("rank %d: %.3f ms/step" % (rank, own_ms), file=sys.stderr, flush=True)
     ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     launches = ctx.launch_count() - l0
     # e2e: host buffers through the C-ABI

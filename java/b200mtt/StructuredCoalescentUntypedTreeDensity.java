@@ -52,20 +52,19 @@ public class StructuredCoalescentUntypedTreeDensity extends TreeDistribution {
         nParticles = nParticlesInput.get();
         tree = (Tree) treeInput.get();
         migrationModel = migrationModelInput.get();
-        // leaf types from the trait set named typeLabel, indexed as the reference does (:88-111)
-        TraitSet typeTraitSet = null;
-        for (TraitSet traitSet : tree.m_traitList.get())
-            if (traitSet.getTraitName().equals(typeLabelInput.get()))
-                typeTraitSet = traitSet;
-        if (typeTraitSet == null)
-            throw new IllegalArgumentException("Trait set (with name '" + typeLabelInput.get() + "') must be provided.");
-        TreeSet<String> typeSet = new TreeSet<>();
-        for (String taxon : tree.getTaxaNames())
-            typeSet.add(typeTraitSet.getStringValue(taxon));
-        List<String> typeList = new ArrayList<>(typeSet);
+        // Leaf types: index of each leaf's trait value in the sorted set of distinct values of
+        // the trait named typeLabel (same numbering as the reference, :88-111).
+        final String label = typeLabelInput.get();
+        TraitSet types = tree.m_traitList.get().stream()
+                .filter(t -> t.getTraitName().equals(label)).findFirst()
+                .orElseThrow(() -> new IllegalArgumentException(
+                        "Trait set (with name '" + label + "') must be provided."));
+        final TraitSet traits = types;
+        List<String> sortedValues = new ArrayList<>(new TreeSet<>(
+                java.util.Arrays.stream(tree.getTaxaNames()).map(traits::getStringValue).toList()));
         leafTypes = new int[tree.getLeafNodeCount()];
-        for (Node leaf : tree.getExternalNodes())
-            leafTypes[leaf.getNr()] = typeList.indexOf(typeTraitSet.getStringValue(leaf.getID()));
+        for (int nr = 0; nr < leafTypes.length; nr++)
+            leafTypes[nr] = sortedValues.indexOf(traits.getStringValue(tree.getNode(nr).getID()));
         nativeLib = new MttNative(deviceInput.get());
     }
 

@@ -59,11 +59,14 @@ def _same_tree(a: mtt.MultiTypeTree, b: mtt.MultiTypeTree):
             assert a.changeTypes[v] == b.changeTypes[v], v
 
 
-def _lockstep(name, model, steps, seed, backend=None, rel=0.0):
+def _lockstep(name, model, steps, seed, backend=None, rel=0.0, start=None):
     """`steps` proposals of operator `name`: product mirror (device, or `backend`) against the
     object-graph restatement.  Finite proposals are kept (the tree evolves), -inf ones restored."""
     make, ref_call = OPERATORS[name]
-    tb, _, _, _ = load_density_fixture("true64")
+    if start is None:
+        tb, _, _, _ = load_density_fixture("true64")
+    else:
+        tb = mtt.TreeBatch.from_trees([start])
     tg = tb.tree(0)
     rng_g, rng_o = Randomizer(seed), Randomizer(seed)
     op = make(tg, model, randomizer=rng_g)
@@ -109,6 +112,52 @@ def test_operator_host_logic_matches_object_graph_restatement(name):
     # still a valid multi-type tree with a finite density (CPU oracle, validity on)
     lp = orc.sc_logp_batch(mtt.TreeBatch.from_trees([tg]), *model.dense(), checkValidity=True)
     assert np.isfinite(lp[0])
+
+
+@pytest.mark.parametrize("nLeaves", [3, 4, 6])
+@pytest.mark.parametrize("name", ["TypedWilsonBalding", "TypedSubtreeExchange-narrow",
+                                  "NodeShiftRetype", "NodeRetype", "MultiTypeUniform"])
+def test_operators_on_tiny_trees(name, nLeaves):
+    """Three to six leaves: root moves of TypedWilsonBalding (forward and backward), exchanges
+    next to the root and root retyping happen every few proposals instead of every few hundred."""
+    model = _model()
+    m, N = model.dense()
+    start = mtt.simulate_trees(1, nLeaves, 2, m, N, leafTimes=np.zeros(nLeaves), seed=70 + nLeaves,
+                               nThreads=1).tree(0)
+    if name == "TypedSubtreeExchange-narrow" and nLeaves == 3:
+        pytest.skip("a narrow exchange on three leaves can never be finite")
+    tg, finite = _lockstep(name, model, 400, seed=5 + nLeaves, backend=OracleUnifModels(m),
+                           rel=0.0, start=start)
+    assert finite > 40
+    lp = orc.sc_logp_batch(mtt.TreeBatch.from_trees([tg]), m, N, checkValidity=True)
+    assert np.isfinite(lp[0])
+
+
+def test_mcmc_driver_statistics_on_cpu(monkeypatch):
+    """The Metropolis-Hastings driver (mcmc.py) with NodeShiftRetype on two leaves of types
+    (1, 0), density and branch sampler answered by the CPU oracle: root height mean 19 and
+    variance 291 as in operators/NSR_Test.java, here with loose tolerances (short chains)."""
+    import multitypetree_b200.mcmc as mcmc_mod
+    model = mtt.SCMigrationModel([0.1, 0.1], [7.0, 7.0], mtt.TypeSet("A", "B"))
+    m, N = model.dense()
+    backend = OracleUnifModels(m)
+    monkeypatch.setattr(mcmc_mod, "sc_logp_batch",
+                        lambda batch, mm, NN, checkValidity=False, ctx=None:
+                        orc.sc_logp_batch(batch, mm, NN, checkValidity=checkValidity))
+    chains = []
+    for c in range(24):
+        tree = mtt.simulate_trees(1, 2, 2, m, N, leafTypes=[1, 0], leafTimes=np.zeros(2),
+                                  seed=300 + c, nThreads=1).tree(0)
+        rng = Randomizer(900 + c)
+        op = ops.NodeShiftRetype(tree, model, randomizer=rng)
+        op._models = lambda: backend
+        chains.append(Chain(tree, model, [op], rng))
+    ens = MCMCEnsemble(chains, ctx=object())
+    ens.run(2500, logEvery=10)
+    s = ens.height_stats(0.0)               # chains start from exact draws: no burn-in needed
+    assert s["ess"] > 300
+    assert abs(s["mean"] - 19.0) < 2.5
+    assert abs(s["var"] - 291.0) < 120.0
 
 
 def test_run_proposals_lockstep_equals_one_by_one():

@@ -241,6 +241,18 @@ def test_operator_on_device_matches_oracle_stream(ctx, name):
     assert dens.calculateLogP() == pytest.approx(want, rel=1e-9)
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["TypedWilsonBalding", "NodeShiftRetype"])
+def test_root_moves_on_device(ctx, name):
+    """Four leaves: the root moves of TypedWilsonBalding / NodeShiftRetype come up every few
+    proposals; device-backed mirror against the oracle-backed restatement."""
+    model = _model(ctx)
+    m, N = model.dense()
+    start = mtt.simulate_trees(1, 4, 2, m, N, leafTimes=np.zeros(4), seed=74, nThreads=1).tree(0)
+    tg, finite = _lockstep(name, model, 300, seed=9, rel=1e-9, start=start)
+    assert finite > 40 and tg.isValid(ctx)
+
+
 def _ensemble(ctx, nChains, newick, make_ops, seed0, typeLabel="deme", tree_factory=None):
     model = mtt.SCMigrationModel([0.1, 0.1], [7.0, 7.0], mtt.TypeSet("A", "B"), ctx=ctx)
     chains = []

@@ -4,12 +4,12 @@
 Headline workload (BASELINE.json configs[1], "cfg2"): batched structured-coalescent logP of
 simulated 2-deme 100-tip multi-type trees, density only.  One step = one pass of the density
 kernel over one batch of B trees per GPU (B = 2^19 by default = 128 x the 4096-tree batch the
-config names, so that the ~1.35 GB of inputs exceed the 126 MB L2; the literal 4096-tree batch
+config names, so that the ~1.2 GB of inputs exceed the 126 MB L2; the literal 4096-tree batch
 is timed as well, with an L2 flush before every launch, and reported under "cfg2_b4096").
 
   value         trees/s, inputs resident in HBM, CUDA-event timed, max over ranks
-  e2e           same metric through the reference-facing C-ABI call mtt_sc_logp_batch with
-                pinned HOST buffers: host->device copies and the device->host read of logP are
+  e2e           same metric through the reference-facing C-ABI call mtt_sc_logp_owner_batch
+                with pinned HOST buffers: host->device copies and the device->host read of logP are
                 inside the timed region
   roofline      algorithmic bytes (12 B per event + 8 B per tree) / kernel time vs
                 the measured HBM copy bandwidth in MEASURED_PEAKS.json
@@ -17,7 +17,8 @@ is timed as well, with an L2 flush before every launch, and reported under "cfg2
 
   --impl reference   times the reference's CPU algorithm (oracle port; no JVM exists here) on
                      the same config with all host threads.
-  --workload peel|retype   the other pieces (configs 3 and 5) as separate bench lines.
+  --workload peel|peel_sharded|retype|untyped   the other pieces (configs 3, 4 and 5, and the
+                     untyped-tree particle density) as separate bench lines.
 
 Multi-GPU: one process per GPU (torchrun); trees are sharded across ranks, no collective on
 the data path (weak scaling).

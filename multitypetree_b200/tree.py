@@ -210,6 +210,9 @@ class TreeBatch:
     chgBase: np.ndarray    # i64 [B+1]
     chgTime: np.ndarray    # f64 [changes]
     chgType: np.ndarray    # u8  [changes]
+    # owner layout of the change lists (see chgNode); filled by the simulator / set_owner_list,
+    # otherwise derived from chgCount on first use
+    owners: Optional[np.ndarray] = field(default=None, repr=False, compare=False)
 
     @property
     def B(self) -> int:
@@ -219,7 +222,7 @@ class TreeBatch:
     def chgNode(self) -> np.ndarray:
         """u16 [changes]: tree-local number of the node that owns each change -- the OWNER
         layout of ``mtt_sc_logp_owner_batch`` (derived once from ``chgCount`` and cached)."""
-        cached = self.__dict__.get("_chgNode")
+        cached = self.owners
         if cached is None or len(cached) != len(self.chgTime):
             csum = np.concatenate([[0], np.cumsum(self.chgCount, dtype=np.int64)])
             if not np.array_equal(csum[self.nodeOff], self.chgBase):
@@ -228,8 +231,12 @@ class TreeBatch:
             local = np.arange(len(self.chgCount), dtype=np.int64) - np.repeat(
                 self.nodeOff[:-1], np.diff(self.nodeOff))
             cached = np.repeat(local, self.chgCount).astype(np.uint16)
-            self.__dict__["_chgNode"] = cached
+            self.owners = cached
         return cached
+
+    def set_owner_list(self, chgNode: Optional[np.ndarray]) -> None:
+        """Install an owner list (u16 [changes]) as is, or drop the cached one (None)."""
+        self.owners = None if chgNode is None else np.ascontiguousarray(chgNode, np.uint16)
 
     def n_events(self) -> np.ndarray:
         """E = nodes + changes per tree (the unit of algorithmic traffic)."""
@@ -282,9 +289,8 @@ class TreeBatch:
         out = TreeBatch(self.nodeOff[b0:b1 + 1] - n0, self.height[n0:n1], self.parent[n0:n1],
                         self.nodeType[n0:n1], self.chgCount[n0:n1],
                         self.chgBase[b0:b1 + 1] - c0, self.chgTime[c0:c1], self.chgType[c0:c1])
-        owners = self.__dict__.get("_chgNode")
-        if owners is not None and len(owners) == len(self.chgTime):
-            out.__dict__["_chgNode"] = owners[c0:c1]
+        if self.owners is not None and len(self.owners) == len(self.chgTime):
+            out.owners = self.owners[c0:c1]
         return out
 
     def nbytes(self) -> int:
@@ -491,7 +497,7 @@ def simulate_trees(B: int, nLeaves: int, d: int, m: np.ndarray, N: np.ndarray,
         L.mtt_sim_export(h, _lib.ptr(tb.nodeOff), _lib.ptr(tb.height), _lib.ptr(tb.parent),
                          _lib.ptr(tb.nodeType), _lib.ptr(tb.chgCount), _lib.ptr(tb.chgBase),
                          _lib.ptr(tb.chgTime), _lib.ptr(tb.chgType), _lib.ptr(owners))
-        tb.__dict__["_chgNode"] = owners
+        tb.owners = owners
     finally:
         L.mtt_sim_free(h)
     return tb

@@ -189,7 +189,7 @@ def test_malformed_change_lists(ctx):
                         tb.chgTime, tb.chgType)
     o = tb.chgNode.copy()
     o[3] = 60000
-    own.__dict__["_chgNode"] = o
+    own.set_owner_list(o)
     lp, valid = mtt.sc_logp_batch(own, m, N, checkValidity=True, ctx=ctx, want_valid=True)
     assert not valid[0] and lp[0] == -np.inf
     assert np.isfinite(mtt.sc_logp_batch(own, m, N, ctx=ctx)[0])     # ignored change, no crash

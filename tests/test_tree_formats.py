@@ -71,7 +71,7 @@ def test_owner_list_layouts_agree():
     m, N = mtt.synthetic_model(3)
     tb = mtt.simulate_trees(200, 40, 3, m, N, seed=12)
     native = tb.chgNode.copy()
-    tb.__dict__.pop("_chgNode")
+    tb.set_owner_list(None)
     derived = tb.chgNode
     assert np.array_equal(native, derived) and derived.dtype == np.uint16
     assert len(derived) == len(tb.chgTime) == int(tb.chgBase[-1])

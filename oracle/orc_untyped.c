@@ -13,6 +13,9 @@
  *   - uniforms u[0..nU) in the reference's order: per first-lineage step one for
  *     nextExponential (-log(1-u)/aTot, [EXT]) and one for the type choice (:265); per other
  *     lineage the stream of retypeBranch.
+ * PARITY UNPINNED by any reference test (the reference only has statistical MCMC tests, and this
+ * density is itself a Monte-Carlo estimate); the restatement is checked against the exact
+ * two-leaf marginal density (tests/test_untyped_gpu.py).
  * The steady-state Poisson tail (:371-377) is drawn from the same window by orc_poisson_window
  * (multiplicative method below 40, inversion by summation above): distributionally exact,
  * not stream-compatible with a JVM -- BEAST's own nextPoisson is [EXT] and unpinned.

@@ -39,6 +39,16 @@ __device__ __forceinline__ void fill_rc(uint16_t *rc, int d, int lane)
 __device__ __noinline__ void mm(int d, const double *A, const double *B, double *C,
                                 const uint16_t *rc, int lane)
 {
+    if (d == 2) {
+        // two demes (the common case): four lanes, two products each, same rounding sequence
+        if (lane < 4) {
+            const int i = lane >> 1, j = lane & 1;
+            double s = add_rn(0.0, mul_rn(A[2 * i], B[j]));
+            C[lane] = add_rn(s, mul_rn(A[2 * i + 1], B[2 + j]));
+        }
+        __syncwarp();
+        return;
+    }
     #pragma unroll 1
     for (int e = lane; e < d * d; e += 32) {
         const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);

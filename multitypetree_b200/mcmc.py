@@ -132,6 +132,8 @@ class MCMCEnsemble:
 
     # -- util/MultiTypeTreeStatLogger.java: root-height mean / variance / ESS after burn-in
     def height_stats(self, burninFrac: float = 0.1):
+        """mean / variance / ESS over all chains, plus between-chain standard errors of the mean
+        and of the variance (the chains are independent, so these need no autocorrelation model)"""
         kept = []
         ess = 0.0
         for h in self.heights:
@@ -139,8 +141,15 @@ class MCMCEnsemble:
             kept.append(h)
             ess += effective_sample_size(h)
         allh = np.concatenate(kept)
+        C = len(kept)
+        cm = np.array([h.mean() for h in kept])
+        c2 = np.array([(h ** 2).mean() for h in kept])
+        se_mean = float(cm.std(ddof=1) / np.sqrt(C)) if C > 1 else float("nan")
+        # var = E[h^2] - mean^2: delta method on the chain-level moments
+        g = c2 - 2.0 * allh.mean() * cm
+        se_var = float(g.std(ddof=1) / np.sqrt(C)) if C > 1 else float("nan")
         return dict(mean=float(allh.mean()), var=float(allh.var(ddof=1)), ess=float(ess),
-                    n=len(allh))
+                    n=len(allh), se_mean=se_mean, se_var=se_var)
 
 
 class MCMC(MCMCEnsemble):

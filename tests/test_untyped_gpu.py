@@ -160,3 +160,124 @@ def test_shuffled_is_a_permutation():
     rng = Randomizer(3)
     for n in (1, 2, 7, 100):
         assert sorted(shuffled(rng, n)) == list(range(n))
+
+
+def _py_particle(um, N, parent, height, leafType, order, u):
+    """Pure-Python restatement of one particle (StructuredCoalescentUntypedTreeDensity.java
+    :121-189, :216-316, :452-502) on top of the oracle's branch sampler: an independent check of
+    orc_untyped.c's typing walk, event list, stable sort and density scan."""
+    d = um.d
+    Q = um.Q
+    n = len(parent)
+    nLeaves = (n + 1) // 2
+    nodeType = [int(leafType[i]) if i < nLeaves else -1 for i in range(n)]
+    events = []          # (time, seq, kind, type, dest)
+    pos, w = 0, 0.0
+
+    def add(kind, ty, dest, t):
+        events.append((float(t), len(events), kind, ty, dest))
+
+    for li, leaf in enumerate(order):
+        leaf = int(leaf)
+        if li == 0:
+            time, ty, nxt = float(height[leaf]), nodeType[leaf], int(parent[leaf])
+            add("S", ty, 0, time)
+            lp = 0.0
+            while True:
+                aTot = 0.0
+                for c in range(d):
+                    if c != ty:
+                        aTot += Q[ty, c]
+                newTime = time + (-1.0 * np.log(1 - u[pos]) / aTot)
+                pos += 1
+                while nxt >= 0 and height[nxt] < newTime:
+                    nodeType[nxt] = ty
+                    add("C", ty, 0, height[nxt])
+                    lp += -aTot * (height[nxt] - time)
+                    time = float(height[nxt])
+                    nxt = int(parent[nxt])
+                if nxt < 0:
+                    break
+                lp += -aTot * (newTime - time)
+                time = newTime
+                uu = u[pos] * aTot
+                pos += 1
+                new = None
+                for c in range(d):
+                    if c == ty:
+                        continue
+                    uu -= Q[ty, c]
+                    if uu < 0.0:
+                        new = c
+                        break
+                assert new is not None
+                add("M", ty, new, time)
+                lp += np.log(Q[ty, new])
+                ty = new
+            w -= lp
+            continue
+        add("S", nodeType[leaf], 0, height[leaf])
+        anc = int(parent[leaf])
+        while nodeType[anc] < 0:
+            anc = int(parent[anc])
+        r = um.retype_branch(float(height[leaf]), float(height[anc]), nodeType[leaf],
+                             nodeType[anc], u[pos:], cap=1024)
+        assert r["status"] == 0
+        pos += r["uUsed"]
+        prevType, prevNode = nodeType[leaf], leaf
+        for k in range(r["nChg"]):
+            add("M", prevType, int(r["chgType"][k]), r["chgTime"][k])
+            while height[prevNode] < r["chgTime"][k]:
+                if prevNode >= nLeaves:
+                    nodeType[prevNode] = prevType
+                    add("C", prevType, 0, height[prevNode])
+                prevNode = int(parent[prevNode])
+            prevType = int(r["chgType"][k])
+        while height[prevNode] < height[anc]:
+            if prevNode >= nLeaves:
+                nodeType[prevNode] = prevType
+                add("C", prevType, 0, height[prevNode])
+            prevNode = int(parent[prevNode])
+        w -= r["logProb"]
+    events.sort(key=lambda e: (e[0], e[1]))
+    cnt = [1 if events[0][3] == c else 0 for c in range(d)]
+    for i in range(1, len(events)):
+        t, _, kind, ty, dest = events[i]
+        dt = t - events[i - 1][0]
+        if dt > 0:
+            lam = 0.0
+            for c in range(d):
+                k = cnt[c]
+                lam += k * (k - 1) / (2.0 * N[c])
+                for cp in range(d):
+                    if cp != c:
+                        lam += k * Q[c, cp]
+            w += -dt * lam
+        if kind == "C":
+            w += np.log(1.0 / N[ty])
+            cnt[ty] -= 1
+        elif kind == "M":
+            w += np.log(Q[ty, dest])
+            cnt[ty] -= 1
+            cnt[dest] += 1
+        else:
+            cnt[ty] += 1
+    return w, pos, nodeType, len(events)
+
+
+@pytest.mark.parametrize("d,n", [(2, 6), (3, 12), (5, 20)])
+def test_oracle_particle_matches_python_restatement(d, n):
+    m, N = mtt.synthetic_model(d)
+    um = orc.UnifModel(m)
+    rng = np.random.default_rng(d)
+    for b in range(3):
+        t = mtt.simulate_trees(3, n, d, m, N, seed=500 + d).tree(b)
+        for _ in range(6):
+            order = rng.permutation(n)
+            u = rng.random(2048)
+            want = orc.untyped_particle(um, N, t.parent, t.height, t.nodeType, order, u)
+            got = _py_particle(um, N, t.parent, t.height, t.nodeType, order, u)
+            assert want["status"] == 0
+            assert got[1] == want["uUsed"] and got[3] == want["nEvents"]
+            assert list(got[2]) == list(want["nodeType"])
+            assert got[0] == pytest.approx(want["logW"], rel=1e-12, abs=1e-12)

@@ -296,7 +296,7 @@ def bench_density(args):
         "data": "synthetic (structured-coalescent Gillespie simulator, SURVEY 8d; seeds 2000+)",
         "config": {
             "workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
-                        "density only (extraction + time ordering + interval scan on device)",
+                        "density only (event extraction + time ordering + interval scan)",
             "batch_per_gpu": B, "tips": 100, "demes": 2,
             "events_per_tree_mean": float(ev.mean()), "events_per_tree_max": int(ev.max()),
             "input_bytes_per_gpu": int(tb.nbytes()),
@@ -350,7 +350,8 @@ def bench_reference(args):
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (same generator and seeds as the GPU arm)",
         "config": {"workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
-                               "density only", "batch_per_step": sample, "tips": 100, "demes": 2},
+                               "density only (event extraction + time ordering + interval scan)",
+                   "batch_per_step": sample, "tips": 100, "demes": 2},
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
                          "sample": "%d trees per step; C restatement of "
                                    "StructuredCoalescentTreeDensity (the reference is Java and no "

@@ -161,6 +161,21 @@ def make_cfg2(B, rank, n=100, d=2, threads=8):
     return tb, m, N
 
 
+def cfg2_config(tb, B, world):
+    """The `config` object of the cfg2 line: built by BOTH arms from the same generated batch,
+    so that the driver sees the same workload description on either side."""
+    ev = tb.n_events()
+    return {
+        "workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
+                    "density only (event extraction + time ordering + interval scan)",
+        "batch_per_gpu": B, "tips": 100, "demes": 2,
+        "events_per_tree_mean": float(ev.mean()), "events_per_tree_max": int(ev.max()),
+        "input_bytes_per_gpu": int(tb.nbytes()),
+        "l2": "inputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (tb.nbytes() / 1e9),
+        "parallelism": "trees sharded across %d GPU(s), no data-path collective" % world,
+    }
+
+
 def cpu_density(tb, m, N, sample, threads):
     """oracle faithful path (the reference's O(E x active) algorithm) on `sample` trees."""
     from oracle import oracle as orc
@@ -294,15 +309,7 @@ def bench_density(args):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (structured-coalescent Gillespie simulator, SURVEY 8d; seeds 2000+)",
-        "config": {
-            "workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
-                        "density only (event extraction + time ordering + interval scan)",
-            "batch_per_gpu": B, "tips": 100, "demes": 2,
-            "events_per_tree_mean": float(ev.mean()), "events_per_tree_max": int(ev.max()),
-            "input_bytes_per_gpu": int(tb.nbytes()),
-            "l2": "inputs (%.2f GB) exceed the 126 MB L2; no flush needed" % (tb.nbytes() / 1e9),
-            "parallelism": "trees sharded across %d GPU(s), no data-path collective" % world,
-        },
+        "config": cfg2_config(tb, B, world),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
@@ -334,8 +341,11 @@ def bench_reference(args):
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    sample = 1 << 17
-    tb, m, N = make_cfg2(sample, 0, threads=cores)
+    # the GPU arm's batch (same generator, seed and size); each step times a bounded sample of it
+    B = args.batch
+    full, m, N = make_cfg2(B, 0, threads=cores)
+    sample = min(B, 1 << 17)
+    tb = full.slice(0, sample)
     from oracle import oracle as orc
     for _ in range(max(1, min(args.warmup, 3))):
         orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL, nThreads=cores)
@@ -348,12 +358,10 @@ def bench_reference(args):
         "impl": "reference", "metric": METRIC, "value": v, "unit": "evals/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (same generator and seeds as the GPU arm)",
-        "config": {"workload": "cfg2: batched structured-coalescent logP, 2-deme 100-tip trees, "
-                               "density only (event extraction + time ordering + interval scan)",
-                   "batch_per_step": sample, "tips": 100, "demes": 2},
+        "data": "synthetic (structured-coalescent Gillespie simulator, SURVEY 8d; seeds 2000+)",
+        "config": cfg2_config(full, B, world),
         "cpu_baseline": {"value": v, "unit": "evals/s", "cores": cores, "kind": "port",
-                         "sample": "%d trees per step; C restatement of "
+                         "sample": "the first %d trees of the batch per step; C restatement of "
                                    "StructuredCoalescentTreeDensity (the reference is Java and no "
                                    "JVM exists on this box)" % sample},
         "e2e": {"value": v, "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},

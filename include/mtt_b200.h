@@ -256,6 +256,16 @@ int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, cons
 /* device-pointer variant of mtt_peel_logl_batch (async on the ctx stream) */
 int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
                             double *logL);
+/* Pattern shards with a proportion of invariant sites: BEAST's TreeLikelihood returns the
+ * evaluation without partial rescaling unless ANY pattern of the alignment underflowed in it
+ * (then the rescaled evaluation, which treats pInv differently).  A shard cannot make that
+ * choice alone, so this entry returns, per tree, parts[0][B] = the unscaled sum over this
+ * handle's patterns, parts[1][B] = the rescaled sum, parts[2][B] = number of tiles that saw an
+ * underflow; add the three over the shards (one all-reduce of 3 B doubles) and take
+ * parts[2] > 0 ? parts[1] : parts[0].  With pInv = 0 both sums are the same number.
+ * Device pointers, async on the ctx stream. */
+int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
+                                  const double *height, double *parts);
 /* per-pattern log-likelihoods of ONE tree (TreeLikelihood.getPatternLogLikelihoods) */
 int mtt_peel_pattern_logl(mtt_peel *h, const int32_t *parent, const double *height,
                           double *patternLogL);

@@ -62,6 +62,7 @@ ABI = {
     "mtt_peel_logl_batch_params": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
     "mtt_peel_logl_batch_mats": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
+    "mtt_peel_logl_parts_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_pattern_logl": (C.c_int, [VP, VP, VP, VP]),
 }
 
@@ -73,7 +74,7 @@ HOST = {
     "mtt_sim_free": (None, [VP]),
     "mtt_rng_new": (VP, [C.c_int64]),
     "mtt_rng_free": (None, [VP]),
-    "mtt_rng_set_seed": (None, [VP, C.c_int64]),
+    "mtt_rng_set_seed": (C.c_int, [VP, C.c_int64]),
     "mtt_rng_next_double": (C.c_double, [VP]),
     "mtt_rng_next_int": (C.c_int32, [VP, C.c_int32]),
     "mtt_rng_next_doubles": (None, [VP, C.c_int64, VP]),

@@ -75,14 +75,25 @@ struct MTFast {
 
 extern "C" {
 
+// A seed whose low 32 bits are zero would leave the generator in the all-zero state (every draw
+// 0 forever, and the operators' rejection loops would never end); BEAST's Randomizer refuses a
+// zero seed, so do these entries: mtt_rng_new returns NULL, mtt_rng_set_seed returns -1.
 void *mtt_rng_new(int64_t seed)
 {
+    if ((uint32_t)seed == 0u)
+        return nullptr;
     MTFast *r = new MTFast();
     r->seed(seed);
     return r;
 }
 void mtt_rng_free(void *h) { delete (MTFast *)h; }
-void mtt_rng_set_seed(void *h, int64_t seed) { ((MTFast *)h)->seed(seed); }
+int mtt_rng_set_seed(void *h, int64_t seed)
+{
+    if (!h || (uint32_t)seed == 0u)
+        return -1;
+    ((MTFast *)h)->seed(seed);
+    return 0;
+}
 double mtt_rng_next_double(void *h) { return ((MTFast *)h)->nextDouble(); }
 int32_t mtt_rng_next_int(void *h, int32_t n) { return n > 0 ? ((MTFast *)h)->nextInt(n) : -1; }
 void mtt_rng_next_doubles(void *h, int64_t n, double *out)

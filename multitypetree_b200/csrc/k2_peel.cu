@@ -425,7 +425,7 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     unsigned char *stageBase = smem;
     uint64_t *bars = reinterpret_cast<uint64_t *>(smem + 2 * Cfg::STAGE_BYTES);
     double *stackBase = reinterpret_cast<double *>(smem + 2 * Cfg::STAGE_BYTES + 16);
-    __shared__ double red[(TPT + 31) / 32];
+    __shared__ double red[3 * ((TPT + 31) / 32)];
 
     constexpr int CR = XL ? 1 : C;            // categories held per thread
     constexpr int LPP = XL ? C : 1;           // lanes per pattern
@@ -441,12 +441,15 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
     const int treeInfo = info[b];
 
     if (treeInfo < 0 || treeInfo > nSlots) {                 // malformed tree: NaN, loudly
-        if (tid == 0)
-            partial[(size_t)b * nTiles + tile] = NAN;
+        if (tid == 0) {
+            double *out = partial + ((size_t)b * nTiles + tile) * 3;
+            out[0] = out[1] = NAN;
+            out[2] = 0.0;
+        }
         if (patternLogL)
             for (int u = 0; u < PPT; u++)
                 if (p0 + u * TPP < P)
-                    patternLogL[p0 + u * TPP] = NAN;
+                    patternLogL[p0 + u * TPP] = patternLogL[pStride + p0 + u * TPP] = NAN;
         return;
     }
     if (tid == 0) {
@@ -623,7 +626,8 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
 
     // root (= result of the last op): integratePartials, proportion invariant, frequencies, log
     const double *catProps = site + C, *freqs = site + 2 * C;
-    double contrib = 0.0;
+    double contribU = 0.0, contribQ = 0.0;
+    bool anyUnder = false;
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
         const long long p = p0 + u * TPP;
@@ -647,45 +651,117 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             }
             root[i] = r;
         }
+        // Proportion invariant (TreeLikelihood.calculateLogP [EXT]): pInv is added to the root
+        // partials of constant patterns.  BEAST evaluates WITHOUT rescaling first and only
+        // repeats the evaluation with rescaling when that returned -infinity; in the rescaled
+        // pass it still adds pInv to the (now rescaled) root partials.  Both values are formed:
+        //   llU  the unscaled pass, computed safely: pInv enters at the root's scale, e^-logScale
+        //   llQ  the rescaled pass, literally (root + pInv, then + logScale)
+        // together with "would the unscaled pass have underflowed to log(0) here"; k2_finalize
+        // picks the sum BEAST would have returned.  The two agree whenever no rescaling
+        // happened on the way to the root (logScale == 0) or pInv == 0.
+        double sumU = 0.0, sumQ = 0.0, offsU = logScale[u];
+        bool hasInv = false;
         if (pInv > 0.0) {
             const int cm = constMask[p];
+            hasInv = cm != 0;
+            // pInv at the root's scale; far below the double range the root is scaled down
+            // instead (it underflows gracefully, as it does in BEAST's unscaled pass)
+            double invU = pInv, rootMul = 1.0;
+            offsU = logScale[u];
+            if (hasInv && offsU != 0.0) {
+                if (offsU > -300.0) {
+                    invU = pInv * exp(-offsU);
+                } else {
+                    rootMul = exp(offsU);
+                    offsU = 0.0;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const bool on = cm & (1 << i);
+                const double r = root[i] * rootMul;
+                sumU += freqs[i] * (on ? r + invU : r);
+                sumQ += freqs[i] * (on ? root[i] + pInv : root[i]);
+            }
+        } else {
 #pragma unroll
             for (int i = 0; i < 4; i++)
-                if (cm & (1 << i))
-                    root[i] += pInv;
+                sumU += freqs[i] * root[i];
+            sumQ = sumU;
         }
-        double sum = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; i++)
-            sum += freqs[i] * root[i];
-        const double ll = log(sum) + logScale[u];
-        if (patternLogL && p < P && cat == 0)
-            patternLogL[p] = ll;
-        if (p < P && cat == 0)
-            contrib += ll * weights[p];
+        const double llU = log(sumU) + offsU;
+        const double llQ = (sumQ == sumU && offsU == logScale[u]) ? llU : log(sumQ) + logScale[u];
+        // log of the smallest subnormal: below it the unscaled root sum is exactly 0
+        const bool under = !hasInv && !(llU >= -744.4400719213812);
+        if (patternLogL && p < P && cat == 0) {
+            patternLogL[p] = llU;
+            patternLogL[pStride + p] = llQ;
+        }
+        if (p < P && cat == 0) {
+            contribU += llU * weights[p];
+            contribQ += llQ * weights[p];
+            anyUnder |= under;
+        }
     }
-    contrib = warp_sum_down(contrib);
-    if (lane == 0)
-        red[warp] = contrib;
+    contribU = warp_sum_down(contribU);
+    contribQ = warp_sum_down(contribQ);
+    anyUnder = __any_sync(FULL_MASK, anyUnder);
+    if (lane == 0) {
+        red[warp] = contribU;
+        red[(TPT + 31) / 32 + warp] = contribQ;
+        red[2 * ((TPT + 31) / 32) + warp] = anyUnder ? 1.0 : 0.0;
+    }
     __syncthreads();
     if (tid == 0) {
-        double t = 0.0;
+        double tU = 0.0, tQ = 0.0, f = 0.0;
 #pragma unroll
-        for (int w = 0; w < (TPT + 31) / 32; w++)
-            t += red[w];
-        partial[(size_t)b * nTiles + tile] = t;
+        for (int w = 0; w < (TPT + 31) / 32; w++) {
+            tU += red[w];
+            tQ += red[(TPT + 31) / 32 + w];
+            f += red[2 * ((TPT + 31) / 32) + w];
+        }
+        double *out = partial + ((size_t)b * nTiles + tile) * 3;
+        out[0] = tU;
+        out[1] = tQ;
+        out[2] = f;
     }
 }
 
-__global__ void k2_finalize(long long B, int nTiles, const double *partial, double *logL)
+// Per tree: fixed-order sums of the tile results.  BEAST's TreeLikelihood [EXT] returns the
+// unscaled evaluation unless it is -infinity (some pattern underflowed), in which case the
+// rescaled evaluation is returned: picked here from the two sums every tile delivers.
+// `mode` (optional, per tree): 1 = the rescaled evaluation was picked.
+__global__ void k2_finalize(long long B, int nTiles, const double *partial, double *logL,
+                            int *mode, double *parts, long long partsStride)
 {
     const long long b = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= B)
         return;
-    double s = 0.0;
-    for (int t = 0; t < nTiles; t++)
-        s += partial[(size_t)b * nTiles + t];
-    logL[b] = s;
+    double sU = 0.0, sQ = 0.0, f = 0.0;
+    for (int t = 0; t < nTiles; t++) {
+        const double *in = partial + ((size_t)b * nTiles + t) * 3;
+        sU += in[0];
+        sQ += in[1];
+        f += in[2];
+    }
+    if (logL)
+        logL[b] = (f > 0.0) ? sQ : sU;
+    if (mode)
+        mode[b] = f > 0.0;
+    if (parts) {           // a pattern shard: the pick is made after the sum over shards
+        parts[b] = sU;
+        parts[partsStride + b] = sQ;
+        parts[2 * partsStride + b] = f;
+    }
+}
+
+// per-pattern output of a single tree: keep the evaluation k2_finalize picked
+__global__ void k2_pick_patterns(long long P, long long pStride, const int *mode, double *pat)
+{
+    const long long p = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P && mode[0])
+        pat[p] = pat[pStride + p];
 }
 
 // constant-site masks (TreeLikelihood.calcConstantPatternIndices [EXT]): pattern p is constant
@@ -785,7 +861,8 @@ int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *pa
 // run the pipeline on device-resident parent/height (or matsIn) for a chunk of trees
 int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeight,
                const double *dMatsIn, double *dLogL, double *patternLogL,
-               const double *dTreeParams = nullptr)
+               const double *dTreeParams = nullptr, double *dParts = nullptr,
+               long long partsStride = 0)
 {
     mtt_ctx *ctx = h->ctx;
     const int n = h->nTips, C = h->nCat, N = 2 * n - 1, nOps = n - 1;
@@ -796,7 +873,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
         return rc;
     if ((rc = grow(ctx, h->dMats, h->matsCap, (size_t)B * nOps * 2 * C * 16 * 8)) != MTT_OK)
         return rc;
-    if ((rc = grow(ctx, h->dPart, h->partCap, (size_t)B * maxTiles * 8)) != MTT_OK)
+    if ((rc = grow(ctx, h->dPart, h->partCap, (size_t)B * maxTiles * 24)) != MTT_OK)
         return rc;
     if ((rc = grow(ctx, h->dInfo, h->infoCap, (size_t)B * 4)) != MTT_OK)
         return rc;
@@ -835,8 +912,16 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
     }
     if (rc != MTT_OK)
         return rc;
-    k2_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(B, nTiles, h->dPart, dLogL);
+    // dInfo is consumed by now: its first word doubles as the picked-evaluation flag of a
+    // single-tree per-pattern request
+    k2_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(
+        B, nTiles, h->dPart, dLogL, patternLogL ? h->dInfo : nullptr, dParts, partsStride);
     MTT_CHECK_LAUNCH(ctx);
+    if (patternLogL) {
+        k2_pick_patterns<<<(unsigned)((h->nPatterns + 255) / 256), 256, 0, ctx->stream>>>(
+            h->nPatterns, h->pStride, h->dInfo, patternLogL);
+        MTT_CHECK_LAUNCH(ctx);
+    }
     return MTT_OK;
 }
 
@@ -1005,6 +1090,28 @@ int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const
     return MTT_OK;
 }
 
+int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
+                                  const double *height, double *parts)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    mtt_ctx *ctx = h->ctx;
+    if (B < 0 || !parent || !height || !parts)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_parts_batch_dev: bad arguments");
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int N = 2 * h->nTips - 1;
+    const long long chunk = chunk_trees(h);
+    for (long long b0 = 0; b0 < B; b0 += chunk) {
+        const long long nb = std::min(chunk, (long long)B - b0);
+        rc = peel_chunk(h, nb, parent + b0 * N, height + b0 * N, nullptr, nullptr, nullptr,
+                        nullptr, parts + b0, (long long)B);
+        if (rc != MTT_OK)
+            return rc;
+    }
+    return MTT_OK;
+}
+
 static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
                      const double *mats, double *logL, double *patternLogL,
                      const double *kappaPerTree = nullptr, const double *ratePerTree = nullptr)
@@ -1021,7 +1128,7 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
     if (patternLogL) {
         // reuse the weights-sized scratch behind dPart for the per-pattern output
         if ((rc = grow(ctx, h->dHeight, h->heightCap,
-                       std::max((size_t)N * 8, (size_t)h->pStride * 8))) != MTT_OK)
+                       std::max((size_t)N * 8, (size_t)h->pStride * 16))) != MTT_OK)
             return rc;
     }
     for (long long b0 = 0; b0 < B; b0 += chunk) {

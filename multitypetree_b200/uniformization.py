@@ -26,15 +26,19 @@ class Randomizer:
 
     def __init__(self, seed: int = 127):
         self._h = _lib.lib().mtt_rng_new(seed)
+        if not self._h:
+            raise ValueError("Non zero random seed required (low 32 bits of %d are zero)" % seed)
 
     def __del__(self):
         try:
-            _lib.lib().mtt_rng_free(self._h)
+            if self._h:
+                _lib.lib().mtt_rng_free(self._h)
         except Exception:
             pass
 
     def setSeed(self, seed: int):
-        _lib.lib().mtt_rng_set_seed(self._h, seed)
+        if _lib.lib().mtt_rng_set_seed(self._h, seed) != 0:
+            raise ValueError("Non zero random seed required (low 32 bits of %d are zero)" % seed)
 
     def nextDouble(self) -> float:
         return _lib.lib().mtt_rng_next_double(self._h)

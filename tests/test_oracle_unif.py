@@ -133,3 +133,17 @@ def test_randomizer_stream_properties():
     ints = [a.nextInt(7) for _ in range(2000)] + [a.nextInt(8) for _ in range(2000)]
     assert min(ints) == 0 and max(ints[:2000]) == 6 and max(ints[2000:]) == 7
     assert Randomizer(1).nextDouble() != Randomizer(2).nextDouble()
+
+
+def test_randomizer_rejects_zero_seed():
+    """A zero seed (BEAST: 'Non zero random seed required') would freeze the Knuth-seeded
+    generator at 0 forever; seeds with zero low 32 bits are the same state."""
+    import pytest
+    from multitypetree_b200.uniformization import Randomizer
+    for bad in (0, 1 << 32, 5 << 32):
+        with pytest.raises(ValueError):
+            Randomizer(bad)
+    r = Randomizer(7)
+    with pytest.raises(ValueError):
+        r.setSeed(0)
+    assert 0.0 < r.nextDouble() < 1.0

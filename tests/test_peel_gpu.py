@@ -92,6 +92,39 @@ def test_large_trees_need_rescaling(ctx, n, P, rate):
     tl.close()
 
 
+@pytest.mark.parametrize("n,rate,gamma", [(300, 50.0, 0), (420, 50.0, 4), (1000, 50.0, 0),
+                                          (1000, 0.02, 2), (600, 50.0, 0)])
+def test_proportion_invariant_with_rescaling(ctx, n, rate, gamma):
+    """pInv > 0 on trees whose partials need rescaling, with constant and all-missing
+    patterns.  BEAST returns the evaluation WITHOUT rescaling when it is finite (n = 300-420
+    at saturation: ~4^-n per pattern, below the 1e-100 rescaling threshold but above the double
+    range's floor) and the rescaled one -- which adds pInv to the already rescaled root
+    partials -- only after a -infinity (n = 1000).  The kernel always rescales and must
+    return BEAST's number in both regimes (oracle: useScaling=2)."""
+    par, hgt, _ = _trees(2, n, d=2, seed=7 * n)
+    f = np.array([.3, .2, .2, .3])
+    tips = simulate_alignment(par[0], hgt[0], 120, 2.0, f, rate, seed=n, missing=0.02)
+    const = np.repeat(np.arange(4, dtype=np.int32)[None, :], n, axis=0)      # AAAA.., CCCC.., ...
+    holes = const.copy()
+    holes[::3] = 4                                                           # constant + gaps
+    allmiss = np.full((n, 1), 4, np.int32)
+    al = Alignment(states=np.concatenate([tips, const, holes, allmiss], axis=1), compress=False)
+    sm = SiteModel(HKY(2.0, f), mutationRate=rate, gammaCategoryCount=gamma, shape=0.5,
+                   proportionInvariant=0.25)
+    tl = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    got = tl.calculateLogPBatch(par, hgt)
+    want = _oracle(al, par, hgt, sm)
+    assert np.all(np.isfinite(want))
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    # per-pattern values of the first tree follow the same choice
+    tl.tree = type("T", (), {"parent": par[0], "height": hgt[0]})()
+    rates, props = sm.category_rates_and_proportions()
+    _, pat = orc.tree_likelihood(al.patterns, al.patternWeight, par[0], hgt[0], rates, props, f,
+                                 2.0, pInv=0.25, useScaling=2, want_patterns=True)
+    np.testing.assert_allclose(tl.getPatternLogLikelihoods(), pat, rtol=RTOL)
+    tl.close()
+
+
 def test_unbalanced_and_balanced_topologies(ctx):
     """Caterpillar (depth n) and perfectly balanced trees: the traversal planner must keep the
     number of live partial vectors within its log2(n)+1 bound for both."""

@@ -140,8 +140,14 @@ int mtt_sc_logp_owner_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
                                 const uint8_t *chgType, int checkValidity, double *logP,
                                 uint8_t *valid);
 
-/* Optional hint for the _dev entry: an upper bound on nodes + changes of any tree in later
- * batches (0 = unknown).  With a bound <= 256 the large-tree kernel launch is skipped. */
+/* Optional hint for the _dev entries: an upper bound on nodes + changes of any tree in later
+ * batches (0 = unknown; it stays set on the ctx until changed).  With a bound <= 1022 the batch
+ * is ONE kernel launch sized for that bound.  The bound is a promise: a tree that exceeds it is
+ * not evaluated and its logP is NaN (valid = 0) -- an error the caller can see, never a
+ * silently missing result.
+ * Malformed input is reported the same way: a node or change type >= d, or a parent index
+ * outside the tree, gives logP = NaN.  A change that names an owner outside the tree is
+ * ignored (the tree is invalid: -infinity under checkValidity). */
 int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents);
 
 /* ------------------------------------------------------------------ piece 3: uniformization

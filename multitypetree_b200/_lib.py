@@ -11,7 +11,7 @@ import os
 import numpy as np
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_PKG, "libmtt_b200.so")
+LIB_PATH = os.environ.get("MTT_B200_LIB") or os.path.join(_PKG, "libmtt_b200.so")
 
 _lib = None
 

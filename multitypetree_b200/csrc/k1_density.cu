@@ -55,16 +55,25 @@ struct K1Params {
 };
 
 // ---- per-model tables (shared memory) ------------------------------------------------
+// two-deme path: everything an event does, looked up by its class = 2 * kind + from
+// (SAMPLE 0/1, COALESCE 2/3, MIGRATE 4/5 with to = 1 - from, NONE 6/7).  An event's
+// descriptor is the byte offset of its record, 16 * class: records of different classes lie in
+// different shared-memory banks, so a warp's look-ups never conflict.
+struct ClsRec {
+    double term;                     // log(1/N) / log(m) event term
+    uint32_t dk0hi, dk1hi;           // high words of the doubles -1.0 / 0.0 / +1.0: change of
+                                     // the lineage count of deme 0 / 1 (their low words are 0)
+};
+constexpr int D8_SHIFT = 4;          // log2(sizeof(ClsRec))
+constexpr int D8_MIGRATE = 4 << D8_SHIFT, D8_NONE = 6 << D8_SHIFT;
+
 struct ModelTab {
     double inv2N[MTT_MAX_DEMES];     // 1 / (2 N_c)
     double mu[MTT_MAX_DEMES];        // sum_{c' != c} m(c,c')
     double logInvN[MTT_MAX_DEMES];   // log(1.0 / N_c)      (StructuredCoalescentTreeDensity.java:130)
     double logM[MTT_MAX_DEMES * MTT_MAX_DEMES];   // log(m(c,c'))   (:136)
-    // two-deme path: everything an event does, looked up by its class = 2 * kind + from
-    // (SAMPLE 0/1, COALESCE 2/3, MIGRATE 4/5 with to = 1 - from, NONE 6/7)
-    double clsTerm[8];               // log(1/N) / log(m) event term
-    double clsDk[2][8];              // change of the lineage count of deme 0 / 1
-    uint32_t clsDelta[8];            // the same as a packed pair of 16-bit fields
+    alignas(16) ClsRec cls[8];
+    uint32_t clsDelta[8];            // the count changes as a packed pair of 16-bit fields
 };
 
 // cooperative fill by `nthr` threads with index `tid`
@@ -84,25 +93,31 @@ __device__ __forceinline__ void fill_model_tab(ModelTab *t, const double *m, con
     for (int e = tid; e < d * d; e += nthr)
         t->logM[e] = (e / d == e % d) ? log(1.0 / N[e / d]) : log(m[e]);   // diagonal: coalescence
     if (d <= 2) {
+        // a single deme still reads the second deme's coefficients (as zeros)
+        for (int c = d + tid; c < 2; c += nthr) {
+            t->inv2N[c] = 0.0;
+            t->mu[c] = 0.0;
+        }
         for (int c = tid; c < 8; c += nthr) {
             const int kind = c >> 1, from = c & 1, to = 1 - from;
-            double term = 0.0, dk[2] = {0.0, 0.0};
+            double term = 0.0, dFrom = 0.0, dTo = 0.0;       // count changes of `from` / `to`
             if (from < d) {
                 if (kind == KIND_SAMPLE) {
-                    dk[from] = 1.0;
+                    dFrom = 1.0;
                 } else if (kind == KIND_COALESCE) {
-                    dk[from] = -1.0;
+                    dFrom = -1.0;
                     term = log(1.0 / N[from]);
                 } else if (kind == KIND_MIGRATE && to < d) {
-                    dk[from] = -1.0;
-                    dk[to] = 1.0;
+                    dFrom = -1.0;
+                    dTo = 1.0;
                     term = log(m[from * d + to]);
                 }
             }
-            t->clsTerm[c] = term;
-            t->clsDk[0][c] = dk[0];
-            t->clsDk[1][c] = dk[1];
-            t->clsDelta[c] = (uint32_t)((int)dk[0] + (int)dk[1] * 65536);
+            const double dk0 = from == 0 ? dFrom : dTo, dk1 = from == 0 ? dTo : dFrom;
+            t->cls[c].term = term;
+            t->cls[c].dk0hi = (uint32_t)__double2hiint(dk0);
+            t->cls[c].dk1hi = (uint32_t)__double2hiint(dk1);
+            t->clsDelta[c] = (uint32_t)((int)dk0 + (int)dk1 * 65536);
         }
     }
 }
@@ -196,40 +211,66 @@ __device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, i
     int kind = (desc >> 10) & 3, from = (desc >> 5) & 31, to = desc & 31;
     if (kind == KIND_COALESCE)
         return t->logInvN[from];
-    if (kind == KIND_MIGRATE)
-        return t->logM[from * d + to];
+    if (kind == KIND_MIGRATE)      // m(i,i) = 0 in the reference (SCMigrationModel.java:253-255)
+        return from == to ? -INFINITY : t->logM[from * d + to];
     return 0.0;
 }
 
 // =====================================================================================
 // warp-per-tree kernel
 // =====================================================================================
+// A staged tree is addressed by SLOT: the index of an event's time in the stage's array of
+// doubles.  Node e sits in slot e, change c in slot cs + c (cs = n, n + 1 or n + 2: the bulk
+// copies land on 16-byte boundaries); `desc[slot]` describes the event.  Every slot of the
+// padded range [0, Epad) that holds no event -- the gap before the changes, the tail, ignored
+// root-branch changes -- is turned into a twin of node 0: the same time, a descriptor that
+// does nothing.  A twin adds exactly 0 to the sum (its interval has length 0), so nothing
+// downstream needs a sentinel, a bound or a predicate: the sort takes Epad keys, the scan
+// takes Epad events.  The number of twins depends only on n + M, never on the alignment of
+// the tree inside the batch, so a tree's logP does not depend on where it sits.
+//
+// Trees with n + M + 2 <= 256 (config 2) take the register path: times are read once (range
+// and sort keys come from the same registers), the ordered keys never leave the registers
+// (each lane owns the 8 consecutive positions the network leaves it with) and the interval
+// scan is fully unrolled.  Larger trees go through shared memory: sorted runs of 256 keys,
+// merge path, rolled scan loops.
+//
 // The kernel body must stay resident in the 32 KB instruction cache: an earlier fully
 // unrolled version (13k SASS instructions) spent most of its cycles in instruction-fetch
-// stalls.  Only the 256-key sorting network is unrolled; everything else is a rolled loop
-// over shared memory.
+// stalls.
 // warps per CTA: 8, or 5 in the 1024-event stage so that two CTAs (10 warps) fit an SM
 __host__ __device__ constexpr int warps_per_cta(int EMAX) { return EMAX > 512 ? 5 : 8; }
-constexpr uint32_t KEY_PAD = 0xffffffffu;
-// sort key = quantised time | event index inside the tree: 9 index bits up to 512 events,
-// 10 in the 1024-event stage (one bit less of time resolution; ties are repaired exactly)
+// sort key = quantised time | slot: 9 slot bits up to 512 slots, 10 in the 1024-event stage
+// (one bit less of time resolution; ties are repaired exactly)
 __host__ __device__ constexpr int idx_bits(int EMAX) { return EMAX > 512 ? 10 : 9; }
+// a tree fits a stage when n + M + 2 <= EMAX (up to two alignment slots before the changes)
+constexpr int SLOT_SLACK = 2;
+
+template <int NW>
+struct DescOf {
+    using T = uint16_t;      // kind | from | to
+};
+template <>
+struct DescOf<0> {
+    using T = uint8_t;       // 32 * class
+};
 
 template <bool HAS_PARENT, int EMAX>
 struct WarpStage {
     alignas(16) unsigned char time[8 * EMAX + 64];   // heights | change times
     alignas(16) unsigned char type[EMAX + 64];       // node types | change types
-    alignas(16) unsigned char cnt[2 * EMAX + 32];    // change counts
+    alignas(16) unsigned char cnt[2 * EMAX + 32];    // change owners; later the order list
     alignas(16) unsigned char par[HAS_PARENT ? 4 * EMAX + 32 : 16];
 };
 
-template <bool HAS_PARENT, int EMAX>
+template <int NW, bool HAS_PARENT, int EMAX>
 struct WarpSmem {
     WarpStage<HAS_PARENT, EMAX> st;       // one staged tree; latency is hidden by the other
-                                          // resident warps (24 per SM), not by prefetching
-    alignas(16) uint32_t keys[EMAX];      // time-ordered (quantised time | event index)
+                                          // resident warps, not by prefetching
+    // sorted runs of the multi-run path; with parent[] also the validity pass's byte flags
+    alignas(16) uint32_t keys[(EMAX > 256 || HAS_PARENT) ? EMAX : 4];
     alignas(8) unsigned long long bar;
-    alignas(8) uint16_t desc[EMAX];       // kind | from | to per event
+    alignas(16) unsigned char desc[(NW == 0 ? 1 : 2) * (EMAX + 32)];
     alignas(16) uint32_t keys2[EMAX > 512 ? EMAX : 4];   // second buffer of the 4-run merge
 };
 
@@ -298,8 +339,18 @@ __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
                                            const StageLayout &L,
                                            WarpStage<HAS_PARENT, EMAX> *st, uint64_t *bar)
 {
+#if defined(MTT_K1_EXP_ONECOPY)      // experiment: only the heights are staged (results are garbage)
+    mbar_arrive_expect_tx(bar, L.szH);
+    if (L.szH)
+        bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
+    return;
+#elif defined(MTT_K1_EXP_NOCOPY)     // experiment: nothing is staged
+    mbar_arrive_expect_tx(bar, 0);
+    return;
+#endif
     mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szT + L.szCT + L.szK + L.szP);
-    bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
+    if (L.szH)
+        bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
     if (L.szC) {
         bulk_g2s(st->time + L.szH, (const unsigned char *)(p.chgTime + s.c0) - (L.cOff - L.szH),
                  L.szC, bar);
@@ -307,9 +358,34 @@ __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
                  L.szCT, bar);
         bulk_g2s(st->cnt, (const unsigned char *)(p.chgNode + s.c0) - L.kOff, L.szK, bar);
     }
-    bulk_g2s(st->type, (const unsigned char *)(p.nodeType + s.n0) - L.tOff, L.szT, bar);
-    if (HAS_PARENT)
+    if (L.szT)
+        bulk_g2s(st->type, (const unsigned char *)(p.nodeType + s.n0) - L.tOff, L.szT, bar);
+    if (HAS_PARENT && L.szP)
         bulk_g2s(st->par, (const unsigned char *)(p.parent + s.n0) - L.pOff, L.szP, bar);
+}
+
+// L2 prefetch of a slice's 16 B-aligned superset (what the bulk copy will read)
+__device__ __forceinline__ void prefetch_slice(const void *src, uint32_t bytes)
+{
+    if (bytes) {
+        const uint32_t a = (uint32_t)((uintptr_t)src & 15);
+        asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"((const unsigned char *)src - a),
+                     "r"((a + bytes + 15u) & ~15u)
+                     : "memory");
+    }
+}
+
+// one elected lane: pull the next tree of this warp into L2 while the current one is worked on
+template <bool HAS_PARENT>
+__device__ __forceinline__ void prefetch_tree(const K1Params &p, const TreeSpan &s)
+{
+    prefetch_slice(p.height + s.n0, 8u * s.n);
+    prefetch_slice(p.nodeType + s.n0, (uint32_t)s.n);
+    prefetch_slice(p.chgTime + s.c0, 8u * s.M);
+    prefetch_slice(p.chgType + s.c0, (uint32_t)s.M);
+    prefetch_slice(p.chgNode + s.c0, 2u * s.M);
+    if (HAS_PARENT)
+        prefetch_slice(p.parent + s.n0, 4u * s.n);
 }
 
 __device__ __forceinline__ void ce_u32(uint32_t &a, uint32_t &b)
@@ -373,11 +449,11 @@ __device__ __forceinline__ void warp_sort256(uint32_t (&v)[8], int lane)
 }
 
 // The warp path keeps its running counts BIASED by CNT_BIAS per 16-bit field.  Events with
-// exactly equal times are processed in index order, which need not be a valid lineage order
+// exactly equal times are processed in slot order, which need not be a valid lineage order
 // (a coalescence may be seen before the same-time migration that brings its child into the
 // deme), so a count can be -1 transiently; the bias keeps such a field from borrowing from
 // its neighbour, and lambda -- a polynomial in the counts -- is updated consistently through
-// the transient.  Intervals are only integrated at dt > 0, when the counts are true again.
+// the transient.  An interval only contributes at dt > 0, when the counts are true again.
 constexpr int CNT_BIAS = 0x4000;
 constexpr unsigned long long CNT_BIAS_WORD = 0x4000400040004000ull;
 
@@ -394,194 +470,479 @@ __device__ __forceinline__ int cnt_get(const Counts<NW> &c, int deme)
     return (int)((w >> (16 * (deme & 3))) & 0xffffu) - CNT_BIAS;
 }
 
-// two-deme path: the event class 2 * kind + from rides in bits 12..14 of the descriptor
-template <int NW>
-__device__ __forceinline__ uint16_t cls_bits(int kind, int from)
-{
-    return (NW == 0) ? (uint16_t)((kind * 2 + (from & 1)) << 12) : (uint16_t)0;
-}
-
 // count deltas of one ordered event added to the lane's packed sum
 template <int NW>
 __device__ __forceinline__ void cnt_accumulate(Counts<NW> &c, uint32_t ds, const ModelTab *tab)
 {
     if constexpr (NW == 0)
-        c.w32 += tab->clsDelta[ds >> 12];
+        c.w32 += *reinterpret_cast<const uint32_t *>(
+            reinterpret_cast<const unsigned char *>(tab->clsDelta) + (ds >> 2));
     else
         cnt_apply_bf<NW>(c, ds);
 }
 
-// One staged tree (E = n + M <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
-// the validity verdict (all lanes).  Scratch aliases: `keys` doubles as a byte array during
-// phase A (before the sort writes it); the stage's chgNode region, dead after phase A,
-// receives the time-ordered event index list.
-template <int NW, bool HAS_PARENT, int EMAX>
-__device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
-                                            const StageLayout &L, uint16_t *desc,
-                                            uint32_t *keys, uint32_t *keys2, int n, int M,
-                                            const ModelTab *tab, int d, int lane, bool &okOut)
+// Quantisation of event times for the sort keys.  The range comes from the high words of the
+// times (min / max as integers: three reductions cover every sign combination); lo is rounded
+// down and hi up by less than 2^-20 relative.  q(t) = low word of (t - lo) * scale + 2^52.
+struct Quant {
+    double lo, scale;
+};
+
+struct HiWordRange {
+    int smin, smax;
+    uint32_t umax;
+    __device__ __forceinline__ void init()
+    {
+        smin = 0x7fffffff;
+        smax = (int)0x80000000;
+        umax = 0u;
+    }
+    __device__ __forceinline__ void add(double t)
+    {
+        const int hw = __double2hiint(t);
+        smin = min(smin, hw);
+        smax = max(smax, hw);
+        umax = max(umax, (uint32_t)hw);
+    }
+};
+
+template <int IDX_BITS>
+__device__ __forceinline__ Quant make_quant(HiWordRange r)
 {
+    constexpr double QMAX = (double)((1u << (32 - IDX_BITS)) - 2u);
+    r.smin = __reduce_min_sync(FULL_MASK, r.smin);
+    r.smax = __reduce_max_sync(FULL_MASK, r.smax);
+    r.umax = __reduce_max_sync(FULL_MASK, r.umax);
+    // a negative time exists <=> umax has the sign bit: the most negative one has the largest
+    // unsigned high word; otherwise the smallest signed one is the minimum.  The maximum is
+    // the largest signed word unless every time is negative (then the smallest word).
+    const int hwLo = ((int)r.umax < 0) ? (int)r.umax : r.smin;
+    const int hwHi = (r.smax >= 0) ? r.smax : r.smin;
+    Quant q;
+    q.lo = __hiloint2double(hwLo, hwLo < 0 ? -1 : 0);
+    const double hi = __hiloint2double(hwHi, hwHi < 0 ? 0 : -1);
+    const double range = hi - q.lo;
+    q.scale = 0.0;
+    if (range > 1e-30 && range < 1e30)
+        // reciprocal in single precision, biased so that (hi - lo) * scale <= QMAX
+        q.scale = (double)__frcp_rd(__double2float_ru(range)) * (QMAX * (1.0 - 1.0 / 262144.0));
+    else if (range > 1e-300 && range < INFINITY)
+        q.scale = QMAX * (1.0 - 1.0 / 262144.0) / range;
+    return q;
+}
+
+template <int IDX_BITS>
+__device__ __forceinline__ uint32_t quant_key(const Quant &q, double t, uint32_t slot)
+{
+    const double v = fma(t - q.lo, q.scale, 4503599627370496.0);     // + 2^52
+    return ((uint32_t)__double2loint(v) << IDX_BITS) | slot;
+}
+
+// One staged tree (n + M + 2 <= EMAX).  Returns the warp-reduced logP in lane 0; `okOut` is
+// the validity verdict, `badOut` "malformed input" (all lanes).  The stage's chgNode region,
+// dead after phase A, receives the time-ordered slot list when one is needed.
+template <int NW, bool HAS_PARENT, int EMAX>
+__device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *ws,
+                                            const StageLayout &L, int n, int M,
+                                            const ModelTab *tab, int d, int lane, bool &okOut,
+                                            bool &badOut)
+{
+    using DT = typename DescOf<NW>::T;
     constexpr int IDX_BITS = idx_bits(EMAX);
     constexpr uint32_t IDX_MASK = (1u << IDX_BITS) - 1u;
-    constexpr uint32_t QMAX = (1u << (32 - IDX_BITS)) - 2u;
+    WarpStage<HAS_PARENT, EMAX> *st = &ws->st;
     const int E = n + M;
     const int nLeaves = (n + 1) >> 1;
-    const double *sH = reinterpret_cast<const double *>(st->time + L.hOff);
-    const double *sC = reinterpret_cast<const double *>(st->time + L.cOff);
+    double *tm = reinterpret_cast<double *>(st->time + L.hOff);          // indexed by slot
+    const int cs = (int)((L.cOff - L.hOff) >> 3);                        // slot of change 0
+    const int Stot = cs + M;
     const uint8_t *sT = st->type + L.tOff;
     const uint8_t *sCT = st->type + L.ctOff;
     const uint16_t *sO = reinterpret_cast<const uint16_t *>(st->cnt + L.kOff);   // change owners
     const int *sP = reinterpret_cast<const int *>(st->par + L.pOff);
-    uint16_t *order = reinterpret_cast<uint16_t *>(st->cnt);      // written after phase A
-    auto ev_time = [&](int e) -> double { return (e < n) ? sH[e] : sC[e - n]; };
+    // descriptors by slot; the two-deme bytes are shifted like the staged node types so that
+    // four of them are written per 32-bit word of types
+    DT *desc = reinterpret_cast<DT *>(ws->desc) + (NW == 0 ? L.tOff : 0u);
+    uint16_t *order = reinterpret_cast<uint16_t *>(st->cnt);             // written after phase A
+    const unsigned char *clsBytes = reinterpret_cast<const unsigned char *>(tab->cls);
+    const unsigned char *dltBytes = reinterpret_cast<const unsigned char *>(tab->clsDelta);
 
-    // ---- phase A: event descriptors  kind | from | to  (COALESCE carries to = from so that
-    //      the event term is always tab->logM[from * d + to])
-    // Every change names the node that owns it (chgNode), changes of one node are adjacent and
-    // ordered child -> parent: the first change of a branch leaves the node's type, any other
-    // one the type its predecessor entered.  No prefix sum, no scatter.
-    bool ok = true;
+    constexpr int E2 = EMAX < 512 ? EMAX : 512;      // stage size of the two-run case
+    const bool fast = E + SLOT_SLACK <= 256;
+    int Epad = fast ? 256 : ((EMAX > 512 && E + SLOT_SLACK > 512) ? EMAX : E2);
+
+    // ---- phase A: event descriptors.  Every change names the node that owns it (chgNode),
+    //      changes of one node are adjacent and ordered child -> parent: the first change of a
+    //      branch leaves the node's type, any other one the type its predecessor entered.
+    bool bad = false, ok = true, selfMig = false;
+    if constexpr (NW == 0) {
+        const uint32_t *tyW = reinterpret_cast<const uint32_t *>(st->type);
+        uint32_t *dW = reinterpret_cast<uint32_t *>(ws->desc);
+        const int nb = (int)L.tOff + nLeaves;                // first internal node's byte
+        const int wb = nb >> 2;
+        const uint32_t part = 0x20202020u << (8 * (nb & 3));
+        const int nW = ((int)L.tOff + n + 3) >> 2;
+        uint32_t seen = 0;
+#pragma unroll 1
+        for (int w = lane; w < nW; w += 32) {
+            const uint32_t t4 = tyW[w];
+            seen |= t4;
+            const uint32_t add = (w > wb) ? 0x20202020u : ((w == wb) ? part : 0u);
+            dW[w] = ((t4 & 0x01010101u) << D8_SHIFT) + add;         // SAMPLE / COALESCE of deme t
+        }
+        // a type >= 2: possibly a neighbour's byte in the first or last word -- look again
+        if (__any_sync(FULL_MASK, (seen & (d >= 2 ? 0xfefefefeu : 0xffffffffu)) != 0u)) {
+#pragma unroll 1
+            for (int e = lane; e < n; e += 32)
+                bad |= (int)sT[e] >= d;
+        }
+    } else {
 #pragma unroll 2
-    for (int e = lane; e < n; e += 32) {
-        const int type = sT[e];
-        desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
-                                           : (KIND_COALESCE << 10 | type << 5 | type)) |
-                  cls_bits<NW>(e < nLeaves ? KIND_SAMPLE : KIND_COALESCE, type);
+        for (int e = lane; e < n; e += 32) {
+            const int type = sT[e];
+            bad |= type >= d;
+            desc[e] = (DT)((e < nLeaves) ? (KIND_SAMPLE << 10 | type << 5)
+                                         : (KIND_COALESCE << 10 | type << 5 | type));
+        }
     }
+    __syncwarp();
+    constexpr DT DESC_NONE = (NW == 0) ? (DT)D8_NONE : (DT)(KIND_NONE << 10);
     if (!HAS_PARENT) {
 #pragma unroll 1
         for (int c = lane; c < M; c += 32) {
             const int node = sO[c];
             const bool first = (c == 0) || ((int)sO[c - 1] != node);
-            const bool bad = node >= n;                      // owner outside the tree
-            const int from = first ? (int)sT[bad ? 0 : node] : (int)sCT[c - 1];
-            desc[n + c] = bad ? ((uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0))
-                              : ((uint16_t)(KIND_MIGRATE << 10 | from << 5 | sCT[c]) |
-                                 cls_bits<NW>(KIND_MIGRATE, from));
-            ok = ok && !bad;
+            const bool oob = node >= n;                      // owner outside the tree
+            const int from = first ? (int)sT[oob ? 0 : node] : (int)sCT[c - 1];
+            const int to = sCT[c];
+            bad |= (from >= d) | (to >= d);
+            ok = ok && !oob;
+            // a change into the type it leaves: the reference's rate m(i,i) is 0, the term
+            // log(0) (SCMigrationModel.java:253-255); the counts do not move
+            selfMig |= (from == to) && !oob;
+            desc[cs + c] = (from == to || oob) ? DESC_NONE   // (an owner-less change is ignored)
+                           : (NW == 0)  ? (DT)(D8_MIGRATE + ((from & 1) << D8_SHIFT))
+                                        : (DT)(KIND_MIGRATE << 10 | (from & 31) << 5 | (to & 31));
         }
-        ok = __all_sync(FULL_MASK, ok);
     } else {
         // with parent[]: the validity chain of MultiTypeTree.java:396-429 rides along
-        uint8_t *hasChg = reinterpret_cast<uint8_t *>(keys);
+        uint8_t *hasChg = reinterpret_cast<uint8_t *>(ws->keys);     // free until the sort
         for (int i = lane * 16; i < n; i += 512)
             *reinterpret_cast<uint4 *>(hasChg + i) = make_uint4(0u, 0u, 0u, 0u);
         __syncwarp();
 #pragma unroll 1
         for (int c = lane; c < M; c += 32) {
             const int node = sO[c];
-            const bool bad = node >= n;
-            const int nd = bad ? 0 : node;
+            const bool oob = node >= n;
+            const int nd = oob ? 0 : node;
             const bool first = (c == 0) || ((int)sO[c - 1] != node);
             const bool last = (c == M - 1) || ((int)sO[c + 1] != node);
             const int par = sP[nd];
             const bool isRoot = par < 0;
             const int from = first ? (int)sT[nd] : (int)sCT[c - 1];
             const int to = sCT[c];
+            bad |= (from >= d) | (to >= d) | (par >= n);
+            selfMig |= (from == to) && !isRoot && !oob;
             // root-branch changes are ignored (StructuredCoalescentTreeDensity.java:161-162)
-            desc[n + c] = (bad || isRoot)
-                              ? ((uint16_t)(KIND_NONE << 10) | cls_bits<NW>(KIND_NONE, 0))
-                              : ((uint16_t)(KIND_MIGRATE << 10 | from << 5 | to) |
-                                 cls_bits<NW>(KIND_MIGRATE, from));
-            const double tc = sC[c];
-            const double before = first ? sH[nd] : sC[c - 1];
-            ok = ok && !bad && !(before > tc);               // :404-405
-            if (last && !isRoot && !bad) {
-                ok = ok && !(tc > sH[par]);                  // :401, :408-409
+            desc[cs + c] = (oob || isRoot || from == to)
+                               ? DESC_NONE
+                               : ((NW == 0) ? (DT)(D8_MIGRATE + ((from & 1) << D8_SHIFT))
+                                            : (DT)(KIND_MIGRATE << 10 | (from & 31) << 5 |
+                                                   (to & 31)));
+            const double tc = tm[cs + c];
+            const double before = first ? tm[nd] : tm[cs + c - 1];
+            ok = ok && !oob && !(before > tc);               // :404-405
+            if (last && !isRoot && !oob && par < n) {
+                ok = ok && !(tc > tm[par]);                  // :401, :408-409
                 ok = ok && (to == (int)sT[par]);             // :421-422
             }
-            if (first && !bad)
+            if (first && !oob)
                 hasChg[nd] = 1;
         }
         __syncwarp();
 #pragma unroll 1
         for (int e = lane; e < n; e += 32) {                 // branches without changes
             const int par = sP[e];
-            if (par >= 0 && !hasChg[e]) {
-                ok = ok && !(sH[e] > sH[par]);
+            bad |= par >= n;
+            if (par >= 0 && par < n && !hasChg[e]) {
+                ok = ok && !(tm[e] > tm[par]);
                 ok = ok && (sT[e] == sT[par]);
             }
         }
-        ok = __all_sync(FULL_MASK, ok);
-        __syncwarp();                                        // hasChg aliases the sort keys
+        __syncwarp();
+    }
+    // ---- twins of node 0 in every slot without an event
+    {
+        const double t0 = (n > 0) ? tm[0] : 0.0;
+        __syncwarp();
+        if (lane < cs - n) {
+            tm[n + lane] = t0;
+            desc[n + lane] = DESC_NONE;
+        }
+#pragma unroll 1
+        for (int s = Stot + lane; s < Epad; s += 32) {
+            tm[s] = t0;
+            desc[s] = DESC_NONE;
+        }
+        if (HAS_PARENT) {
+#pragma unroll 1
+            for (int c = lane; c < M; c += 32)
+                if (desc[cs + c] == DESC_NONE)
+                    tm[cs + c] = t0;
+        }
+    }
+    {   // one reduction for the three verdicts
+        const uint32_t f = __reduce_or_sync(FULL_MASK, (bad ? 1u : 0u) | (ok ? 0u : 2u) |
+                                                           (selfMig ? 4u : 0u));
+        bad = f & 1u;
+        ok = !(f & 3u);
+        selfMig = f & 4u;
     }
     okOut = ok;
+    badOut = bad;
     __syncwarp();
 
-    // ---- time range over the node heights (interleaved, conflict-free reads).  Change times
-    //      of a valid tree lie inside it; anything outside just saturates the quantised key
-    //      and is put in exact order by the repair pass below.
-    // Only the high words are compared (as order-preserving integers): lo is rounded down and
-    // hi up by less than 2^-20 relative, which quantisation does not notice.
-    int kmin = 0x7fffffff, kmax = (int)0x80000000;
-#pragma unroll 2
-    for (int e = lane; e < n; e += 32) {
-        const int hw = reinterpret_cast<const int *>(sH)[2 * e + 1];
-        const int key = hw ^ ((hw >> 31) & 0x7fffffff);
-        kmin = min(kmin, key);
-        kmax = max(kmax, key);
-    }
-    kmin = __reduce_min_sync(FULL_MASK, kmin);
-    kmax = __reduce_max_sync(FULL_MASK, kmax);
-    const int hwLo = kmin ^ ((kmin >> 31) & 0x7fffffff), hwHi = kmax ^ ((kmax >> 31) & 0x7fffffff);
-    const double lo = __hiloint2double(hwLo, hwLo < 0 ? -1 : 0);
-    const double hi = __hiloint2double(hwHi, hwHi < 0 ? 0 : -1);
-    const double range = hi - lo;
-    const double scale = (range > 1e-300 && range < INFINITY) ? (double)QMAX / range : 0.0;
-
-    // ---- phase B: order.  256 events at a time through the register network.  One run goes
-    //      straight to the order list; two runs are stored as keys and merged (merge path).
-    constexpr int E2 = EMAX < 512 ? EMAX : 512;      // stage size of the two-run case
-    constexpr int LB = E2 - 256;                     // capacity of its second run
-    int Epad = (E > 256) ? ((EMAX > 512 && E > 512) ? EMAX : E2) : 256;
-    asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
-    // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
-    // accumulated while the ordered events are still in registers
-    Counts<NW> local;
-    cnt_zero<NW>(local);
-#pragma unroll 1
-    for (int base = 0; base < Epad; base += 256) {
+    double acc;
+    if (fast) {
+        // =========================== register path: 256 slots, 8 per lane ================
         uint32_t key[8];
+        {
+            double t[8];
+            HiWordRange hr;
+            hr.init();
 #pragma unroll
-        for (int k = 0; k < 8; k++) {
-            const int e = base + lane + 32 * k;
-            uint32_t kk = KEY_PAD;
-            if (e < E && !(HAS_PARENT && ((desc[e] >> 10) & 3) == KIND_NONE)) {
-                uint32_t q = (uint32_t)((ev_time(e) - lo) * scale);
-                q = min(q, QMAX);
-                kk = (q << IDX_BITS) | (uint32_t)e;
+            for (int k = 0; k < 8; k++) {
+                t[k] = tm[lane + 32 * k];
+                hr.add(t[k]);
             }
-            key[k] = kk;
+            const Quant qz = make_quant<IDX_BITS>(hr);
+#pragma unroll
+            for (int k = 0; k < 8; k++)
+                key[k] = quant_key<IDX_BITS>(qz, t[k], (uint32_t)(lane + 32 * k));
         }
         warp_sort256(key, lane);
-        if (Epad == 256) {
-            // event indices, 0xffff for padding; 8 x u16 = one 16-byte store per lane
-            uint32_t w[4];
 #pragma unroll
-            for (int k = 0; k < 4; k++) {
-                const uint32_t a = (key[2 * k] == KEY_PAD) ? 0xffffu : (key[2 * k] & IDX_MASK);
-                const uint32_t b = (key[2 * k + 1] == KEY_PAD) ? 0xffffu : (key[2 * k + 1] & IDX_MASK);
-                w[k] = a | (b << 16);
-                cnt_accumulate<NW>(local, (a == 0xffffu) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
-                                                         : (uint32_t)desc[a], tab);
-                cnt_accumulate<NW>(local, (b == 0xffffu) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
-                                                         : (uint32_t)desc[b], tab);
+        for (int r = 0; r < 8; r++)
+            key[r] &= IDX_MASK;                              // slots, in time order
+        bool repaired = false;
+        for (;;) {
+            // time of the last event before my chunk = the previous lane's last event
+            // (lane 0: my own first event, dt = 0)
+            const double xLast = tm[key[7]], xFirst = tm[key[0]];
+            double prevT = __shfl_up_sync(FULL_MASK, xLast, 1);
+            if (lane == 0)
+                prevT = xFirst;
+            int invAcc = 0;
+            acc = 0.0;
+            if constexpr (NW == 0) {
+                uint32_t dsc[8];
+                uint32_t local = 0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    dsc[r] = desc[key[r]];
+                    local += *reinterpret_cast<const uint32_t *>(dltBytes + (dsc[r] >> 2));
+                }
+                uint32_t incl = local;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= o)
+                        incl += v;
+                }
+                const uint32_t b32 = incl - local + 0x40004000u;      // biased, see CNT_BIAS
+                double k0 = (double)((int)(b32 & 0xffffu) - CNT_BIAS);
+                double k1 = (double)((int)(b32 >> 16) - CNT_BIAS);
+                // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123), as
+                // k_c (k_c / (2 N_c) + (mu_c - 1 / (2 N_c)))
+                const double i0 = tab->inv2N[0], i1 = tab->inv2N[1];
+                const double b0 = tab->mu[0] - i0, b1 = tab->mu[1] - i1;
+                double lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
+                double firstTerm = 0.0;
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const double x = (r == 0) ? xFirst : (r == 7) ? xLast : tm[key[r]];
+                    const uint4 rec = *reinterpret_cast<const uint4 *>(clsBytes + dsc[r]);
+                    const double dt = x - prevT;
+                    invAcc |= __double2hiint(dt);            // sign bit: dt < 0
+                    acc = fma(-dt, lambda, acc);             // dt = 0 adds nothing  (:108)
+                    prevT = x;
+                    // log(1/N) or log(m)  (:127-137)
+                    const double term = __hiloint2double((int)rec.y, (int)rec.x);
+                    if (r == 0)
+                        firstTerm = term;
+                    acc += term;
+                    k0 += __hiloint2double((int)rec.z, 0);
+                    k1 += __hiloint2double((int)rec.w, 0);
+                    lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
+                    if (r & 1)       // keep the scheduler from hoisting all 32 loads (spills)
+                        asm volatile("" ::: "memory");
+                }
+                if (lane == 0)
+                    acc -= firstTerm;                        // event 0 is skipped (:101)
+            } else {
+                Counts<NW> local;
+                cnt_zero<NW>(local);
+#pragma unroll
+                for (int r = 0; r < 8; r++)
+                    cnt_apply_bf<NW>(local, desc[key[r]]);
+                Counts<NW> base;
+#pragma unroll
+                for (int i = 0; i < NW; i++) {
+                    unsigned long long incl = local.w[i];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned long long v = shfl_up_u64(incl, o);
+                        if (lane >= o)
+                            incl += v;
+                    }
+                    base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
+                }
+                double lambda = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < d; c++) {
+                    const double kd = (double)cnt_get<NW>(base, c);
+                    lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+                }
+                bool first = (lane == 0);                    // event 0 is skipped (:101)
+#pragma unroll
+                for (int r = 0; r < 8; r++) {
+                    const double x = (r == 0) ? xFirst : (r == 7) ? xLast : tm[key[r]];
+                    const uint32_t ds = desc[key[r]];
+                    const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+                    const double dt = x - prevT;
+                    invAcc |= __double2hiint(dt);
+                    acc = fma(-dt, lambda, acc);
+                    prevT = x;
+                    // Branch-free (lanes hold different event kinds): a lineage leaves deme
+                    // `from` (COALESCE, MIGRATE) and / or enters deme `a` (SAMPLE, MIGRATE).
+                    // MIGRATE has a != from, so both updates can use the counts before the
+                    // event.  NONE does neither.
+                    const bool leave = (kind == KIND_COALESCE) | (kind == KIND_MIGRATE);
+                    const bool enter = (kind == KIND_SAMPLE) | (kind == KIND_MIGRATE);
+                    const int a = (kind == KIND_MIGRATE) ? to : from;
+                    const double term = tab->logM[from * d + to];   // log(1/N) or log(m)
+                    acc += (leave && !first) ? term : 0.0;
+                    const double kl = (double)cnt_get<NW>(base, from),
+                                 ke = (double)cnt_get<NW>(base, a);
+                    const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
+                    const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
+                    lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
+                    cnt_add<NW>(base, from, -(long long)leave);
+                    cnt_add<NW>(base, a, (long long)enter);
+                    first = false;
+                }
             }
-            *reinterpret_cast<uint4 *>(order + 8 * lane) = make_uint4(w[0], w[1], w[2], w[3]);
-        } else if (Epad > 512 || base == 0 || 8 * lane < LB) {
-            // two runs: only the first LB keys of the second can be real, padding sorts last
-            uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
-            dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
-            dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
+            if (repaired || !__any_sync(FULL_MASK, invAcc < 0))
+                break;                                       // (NaN times cannot be ordered)
+            repaired = true;
+            // rare: quantisation ties out of exact order -> odd-even transposition on the
+            // exact times, through the order list in shared memory
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                order[8 * lane + r] = (uint16_t)key[r];
+            __syncwarp();
+            bool swapped = true;
+            while (swapped) {
+                swapped = false;
+#pragma unroll 1
+                for (int parity = 0; parity < 2; parity++) {
+#pragma unroll 1
+                    for (int a = parity + 2 * lane; a + 1 < 256; a += 64) {
+                        const int ia = order[a], ib = order[a + 1];
+                        if (tm[ia] > tm[ib]) {
+                            order[a] = (uint16_t)ib;
+                            order[a + 1] = (uint16_t)ia;
+                            swapped = true;
+                        }
+                    }
+                    __syncwarp();
+                }
+                swapped = __any_sync(FULL_MASK, swapped);
+            }
+#pragma unroll
+            for (int r = 0; r < 8; r++)
+                key[r] = order[8 * lane + r];
         }
+        return selfMig ? -INFINITY : warp_sum_down(acc);
     }
-    __syncwarp();
-    if (EMAX > 256 && Epad != 256) {
-        // merge path: lane produces outputs [per*lane, per*lane+per) of two ascending runs
-        auto merge_keys = [&](const uint32_t *A, const uint32_t *B, uint32_t *out) {
-            // two 256-key runs -> 512 keys (first level of the four-run case)
-            const int diag = 16 * lane;
-            int a0 = max(0, diag - 256), a1 = min(diag, 256);
+
+    if constexpr (EMAX > 256) {
+        // =========================== shared-memory path: sorted runs + merge path =========
+        uint32_t *keys = ws->keys, *keys2 = ws->keys2;
+        constexpr int LB = E2 - 256;                     // capacity of the second run
+        asm volatile("" : "+r"(Epad));       // opaque trip count: keeps the sort loop from being peeled
+        Quant qz;
+        {
+            HiWordRange hr;
+            hr.init();
+#pragma unroll 2
+            for (int s = lane; s < Epad; s += 32)
+                hr.add(tm[s]);
+            qz = make_quant<IDX_BITS>(hr);
+        }
+#pragma unroll 1
+        for (int base = 0; base < Epad; base += 256) {
+            uint32_t key[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int s = base + lane + 32 * k;
+                // slots past Epad only exist in the two-run stage (Epad = 384): sort last
+                key[k] = (s < Epad) ? quant_key<IDX_BITS>(qz, tm[s], (uint32_t)s) : 0xffffffffu;
+            }
+            warp_sort256(key, lane);
+            if (Epad > 512 || base == 0 || 8 * lane < LB) {
+                // two runs: only the first LB keys of the second are real
+                uint4 *dst = reinterpret_cast<uint4 *>(keys + base + 8 * lane);
+                dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
+                dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
+            }
+        }
+        __syncwarp();
+        // packed count deltas of the positions this lane will own ([per*lane, per*lane+per)),
+        // accumulated while the merged keys pass through registers
+        Counts<NW> local;
+        cnt_zero<NW>(local);
+        {
+            // merge path: lane produces outputs [per*lane, per*lane+per) of two ascending runs
+            auto merge_keys = [&](const uint32_t *A, const uint32_t *B, uint32_t *out) {
+                // two 256-key runs -> 512 keys (first level of the four-run case)
+                const int diag = 16 * lane;
+                int a0 = max(0, diag - 256), a1 = min(diag, 256);
+                while (a0 < a1) {
+                    const int mid = (a0 + a1) >> 1;
+                    if (A[mid] <= B[diag - 1 - mid])
+                        a0 = mid + 1;
+                    else
+                        a1 = mid;
+                }
+                int i = a0, j = diag - a0;
+                uint32_t ka = (i < 256) ? A[i] : 0xffffffffu, kb = (j < 256) ? B[j] : 0xffffffffu;
+#pragma unroll 1
+                for (int q = 0; q < 16; q++) {
+                    const bool takeA = ka <= kb;
+                    out[diag + q] = takeA ? ka : kb;
+                    if (takeA) {
+                        i++;
+                        ka = (i < 256) ? A[i] : 0xffffffffu;
+                    } else {
+                        j++;
+                        kb = (j < 256) ? B[j] : 0xffffffffu;
+                    }
+                }
+            };
+            const uint32_t *A = keys, *B = keys + 256;
+            int la = 256, lb = Epad - 256;
+            if (EMAX > 512 && Epad > 512) {
+                merge_keys(keys, keys + 256, keys2);
+                merge_keys(keys + 512, keys + 768, keys2 + 512);
+                __syncwarp();
+                A = keys2;
+                B = keys2 + 512;
+                la = lb = 512;
+            }
+            const int perm = Epad >> 5;
+            const int diag = perm * lane;
+            int a0 = max(0, diag - lb), a1 = min(diag, la);
             while (a0 < a1) {
                 const int mid = (a0 + a1) >> 1;
                 if (A[mid] <= B[diag - 1 - mid])
@@ -590,221 +951,162 @@ __device__ __noinline__ double process_tree(WarpStage<HAS_PARENT, EMAX> *st,
                     a1 = mid;
             }
             int i = a0, j = diag - a0;
-            uint32_t ka = (i < 256) ? A[i] : KEY_PAD, kb = (j < 256) ? B[j] : KEY_PAD;
+            uint32_t ka = (i < la) ? A[i] : 0xffffffffu, kb = (j < lb) ? B[j] : 0xffffffffu;
 #pragma unroll 1
-            for (int q = 0; q < 16; q++) {
+            for (int q = 0; q < perm; q++) {
                 const bool takeA = ka <= kb;
-                out[diag + q] = takeA ? ka : kb;
+                const uint32_t slot = (takeA ? ka : kb) & IDX_MASK;
+                order[diag + q] = (uint16_t)slot;
+                cnt_accumulate<NW>(local, (uint32_t)desc[slot], tab);
                 if (takeA) {
                     i++;
-                    ka = (i < 256) ? A[i] : KEY_PAD;
+                    ka = (i < la) ? A[i] : 0xffffffffu;
                 } else {
                     j++;
-                    kb = (j < 256) ? B[j] : KEY_PAD;
+                    kb = (j < lb) ? B[j] : 0xffffffffu;
                 }
             }
-        };
-        const uint32_t *A = keys, *B = keys + 256;
-        int la = 256, lb = LB;
-        if (EMAX > 512 && Epad > 512) {
-            merge_keys(keys, keys + 256, keys2);
-            merge_keys(keys + 512, keys + 768, keys2 + 512);
             __syncwarp();
-            A = keys2;
-            B = keys2 + 512;
-            la = lb = 512;
         }
-        const int perm = Epad >> 5;
-        const int diag = perm * lane;
-        int a0 = max(0, diag - lb), a1 = min(diag, la);
-        while (a0 < a1) {
-            const int mid = (a0 + a1) >> 1;
-            if (A[mid] <= B[diag - 1 - mid])
-                a0 = mid + 1;
-            else
-                a1 = mid;
-        }
-        int i = a0, j = diag - a0;
-        uint32_t ka = (i < la) ? A[i] : KEY_PAD, kb = (j < lb) ? B[j] : KEY_PAD;
-#pragma unroll 1
-        for (int q = 0; q < perm; q++) {
-            const bool takeA = ka <= kb;
-            const uint32_t out = takeA ? ka : kb;
-            order[diag + q] = (out == KEY_PAD) ? (uint16_t)0xffff : (uint16_t)(out & IDX_MASK);
-            cnt_accumulate<NW>(local, (out == KEY_PAD) ? (uint32_t)(KIND_NONE << 10 | 6 << 12)
-                                                      : (uint32_t)desc[out & IDX_MASK], tab);
-            if (takeA) {
-                i++;
-                ka = (i < la) ? A[i] : KEY_PAD;
-            } else {
-                j++;
-                kb = (j < lb) ? B[j] : KEY_PAD;
-            }
-        }
-        __syncwarp();
-    }
 
-    // ---- phases C / D over the order list; lane owns positions [per*lane, per*lane+per)
-    const int per = Epad >> 5;
-    const int p0 = per * lane;
-    double acc;
-    bool recount = false;                // only after a repair pass changed the order list
-    for (;;) {
-        // C: warp prefix sum of the per-lane count deltas -> counts before my chunk
-        if (recount) {
-            cnt_zero<NW>(local);
+        // ---- scan over the order list; lane owns positions [per*lane, per*lane+per)
+        const int per = Epad >> 5;
+        const int p0 = per * lane;
+        bool recount = false;                // only after a repair pass changed the order list
+        for (;;) {
+            if (recount) {
+                cnt_zero<NW>(local);
 #pragma unroll 1
-            for (int q = 0; q < per; q++) {
-                const int idx = order[p0 + q];
-                if (idx == 0xffff)
-                    break;
-                cnt_accumulate<NW>(local, desc[idx], tab);
+                for (int q = 0; q < per; q++)
+                    cnt_accumulate<NW>(local, (uint32_t)desc[order[p0 + q]], tab);
             }
-        }
-        // D: interval integration with a running lambda; also verifies the exact time order
-        double prevT = -INFINITY;
-        bool first = (lane == 0);                            // event 0 is skipped (:101)
-        if (lane > 0) {
-            const int ip = order[p0 - 1];
-            if (ip != 0xffff)
-                prevT = ev_time(ip);
-        }
-        bool inv = false;
-        acc = 0.0;
-        if constexpr (NW == 0) {
-            // ---- two demes: counts as two doubles, lambda evaluated directly
-            uint32_t incl = local.w32;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
-                if (lane >= o)
-                    incl += v;
-            }
-            const uint32_t b32 = incl - local.w32 + 0x40004000u;      // biased, see CNT_BIAS
-            double k0 = (double)((int)(b32 & 0xffffu) - CNT_BIAS);
-            double k1 = (double)((int)(b32 >> 16) - CNT_BIAS);
-            // lambda = sum_c k_c (k_c - 1) / (2 N_c) + k_c mu_c   (:109-123), as
-            // k_c (k_c / (2 N_c) + (mu_c - 1 / (2 N_c)))
-            const double i0 = tab->inv2N[0], i1 = tab->inv2N[1];
-            const double b0 = tab->mu[0] - i0, b1 = tab->mu[1] - i1;
-            double lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
-            // event 0 is skipped (:101): lane 0 starts at its own first event (dt = 0) and
-            // takes that event's term out again below
-            double skipTerm = 0.0;
-            if (lane == 0) {
-                const int i00 = order[0];
-                if (i00 != 0xffff) {
-                    prevT = ev_time(i00);
-                    skipTerm = tab->clsTerm[desc[i00] >> 12];
-                }
-            }
-#pragma unroll 2
-            for (int q = 0; q < per; q++) {
-                const int idx = order[p0 + q];
-                if (idx == 0xffff)
-                    break;
-                const double x = ev_time(idx);
-                const int cls = desc[idx] >> 12;
-                const double dt = x - prevT;
-                inv |= dt < 0.0;
-                if (dt > 0.0)                                // StructuredCoalescentTreeDensity.java:108
-                    acc -= dt * lambda;
-                prevT = x;
-                acc += tab->clsTerm[cls];                    // log(1/N) or log(m)  (:127-137)
-                k0 += tab->clsDk[0][cls];
-                k1 += tab->clsDk[1][cls];
-                lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
-            }
-            acc -= skipTerm;
-        } else {
-            Counts<NW> base;
-#pragma unroll
-            for (int i = 0; i < NW; i++) {
-                unsigned long long incl = local.w[i];
+            double prevT = tm[order[lane == 0 ? 0 : p0 - 1]];
+            int invAcc = 0;
+            acc = 0.0;
+            if constexpr (NW == 0) {
+                uint32_t incl = local.w32;
 #pragma unroll
                 for (int o = 1; o < 32; o <<= 1) {
-                    const unsigned long long v = shfl_up_u64(incl, o);
+                    const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
                     if (lane >= o)
                         incl += v;
                 }
-                base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
-            }
-            // lambda at the start of my chunk
-            double lambda = 0.0;
-#pragma unroll 1
-            for (int c = 0; c < d; c++) {
-                const double kd = (double)cnt_get<NW>(base, c);
-                lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
-            }
+                const uint32_t b32 = incl - local.w32 + 0x40004000u;
+                double k0 = (double)((int)(b32 & 0xffffu) - CNT_BIAS);
+                double k1 = (double)((int)(b32 >> 16) - CNT_BIAS);
+                const double i0 = tab->inv2N[0], i1 = tab->inv2N[1];
+                const double b0 = tab->mu[0] - i0, b1 = tab->mu[1] - i1;
+                double lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
+                if (lane == 0)       // event 0 is skipped (:101): its term is taken out again
+                    acc = -reinterpret_cast<const ClsRec *>(clsBytes + desc[order[0]])->term;
 #pragma unroll 2
-            for (int q = 0; q < per; q++) {
-                const int idx = order[p0 + q];
-                if (idx == 0xffff)
-                    break;
-                const double x = ev_time(idx);
-                const uint32_t ds = desc[idx];
-                const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
-                const double dt = x - prevT;
-                inv |= dt < 0.0;
-                if (!first && dt > 0.0)                      // StructuredCoalescentTreeDensity.java:108
-                    acc -= dt * lambda;
-                prevT = x;
-                // Branch-free (lanes hold different event kinds): a lineage leaves deme `from`
-                // (COALESCE, MIGRATE) and / or enters deme `a` (SAMPLE, MIGRATE).  MIGRATE has
-                // a != from, so both updates can use the counts before the event.
-                const bool leave = kind != KIND_SAMPLE, enter = kind != KIND_COALESCE;
-                const int a = (kind == KIND_MIGRATE) ? to : from;
-                const double term = tab->logM[from * d + to];   // log(1/N) or log(m)  (:127-137)
-                acc += (leave && !first) ? term : 0.0;
-                const double kl = (double)cnt_get<NW>(base, from), ke = (double)cnt_get<NW>(base, a);
-                const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
-                const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
-                lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
-                cnt_add<NW>(base, from, -(long long)leave);
-                cnt_add<NW>(base, a, (long long)enter);
-                first = false;
-            }
-        }
-        if (!__any_sync(FULL_MASK, inv))
-            break;
-        // rare: quantisation ties out of exact order -> odd-even transposition on exact times
-        bool swapped = true;
-        while (swapped) {
-            swapped = false;
-#pragma unroll 1
-            for (int parity = 0; parity < 2; parity++) {
-#pragma unroll 1
-                for (int a = parity + 2 * lane; a + 1 < Epad; a += 64) {
-                    const int ia = order[a], ib = order[a + 1];
-                    if (ia != 0xffff && ib != 0xffff && ev_time(ia) > ev_time(ib)) {
-                        order[a] = (uint16_t)ib;
-                        order[a + 1] = (uint16_t)ia;
-                        swapped = true;
-                    }
+                for (int q = 0; q < per; q++) {
+                    const int slot = order[p0 + q];
+                    const double x = tm[slot];
+                    const ClsRec *rec = reinterpret_cast<const ClsRec *>(clsBytes + desc[slot]);
+                    const double dt = x - prevT;
+                    invAcc |= __double2hiint(dt);
+                    acc = fma(-dt, lambda, acc);
+                    prevT = x;
+                    acc += rec->term;
+                    k0 += __hiloint2double((int)rec->dk0hi, 0);
+                    k1 += __hiloint2double((int)rec->dk1hi, 0);
+                    lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
                 }
-                __syncwarp();
+            } else {
+                Counts<NW> base;
+#pragma unroll
+                for (int i = 0; i < NW; i++) {
+                    unsigned long long incl = local.w[i];
+#pragma unroll
+                    for (int o = 1; o < 32; o <<= 1) {
+                        const unsigned long long v = shfl_up_u64(incl, o);
+                        if (lane >= o)
+                            incl += v;
+                    }
+                    base.w[i] = incl - local.w[i] + CNT_BIAS_WORD;
+                }
+                double lambda = 0.0;
+#pragma unroll 1
+                for (int c = 0; c < d; c++) {
+                    const double kd = (double)cnt_get<NW>(base, c);
+                    lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+                }
+                bool first = (lane == 0);
+#pragma unroll 2
+                for (int q = 0; q < per; q++) {
+                    const int slot = order[p0 + q];
+                    const double x = tm[slot];
+                    const uint32_t ds = desc[slot];
+                    const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+                    const double dt = x - prevT;
+                    invAcc |= __double2hiint(dt);
+                    acc = fma(-dt, lambda, acc);
+                    prevT = x;
+                    const bool leave = (kind == KIND_COALESCE) | (kind == KIND_MIGRATE);
+                    const bool enter = (kind == KIND_SAMPLE) | (kind == KIND_MIGRATE);
+                    const int a = (kind == KIND_MIGRATE) ? to : from;
+                    const double term = tab->logM[from * d + to];
+                    acc += (leave && !first) ? term : 0.0;
+                    const double kl = (double)cnt_get<NW>(base, from),
+                                 ke = (double)cnt_get<NW>(base, a);
+                    const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
+                    const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
+                    lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
+                    cnt_add<NW>(base, from, -(long long)leave);
+                    cnt_add<NW>(base, a, (long long)enter);
+                    first = false;
+                }
             }
-            swapped = __any_sync(FULL_MASK, swapped);
+            if (recount || !__any_sync(FULL_MASK, invAcc < 0))
+                break;                                       // (NaN times cannot be ordered)
+            // rare: quantisation ties out of exact order -> odd-even transposition on exact times
+            bool swapped = true;
+            while (swapped) {
+                swapped = false;
+#pragma unroll 1
+                for (int parity = 0; parity < 2; parity++) {
+#pragma unroll 1
+                    for (int a = parity + 2 * lane; a + 1 < Epad; a += 64) {
+                        const int ia = order[a], ib = order[a + 1];
+                        if (tm[ia] > tm[ib]) {
+                            order[a] = (uint16_t)ib;
+                            order[a + 1] = (uint16_t)ia;
+                            swapped = true;
+                        }
+                    }
+                    __syncwarp();
+                }
+                swapped = __any_sync(FULL_MASK, swapped);
+            }
+            recount = true;
         }
-        recount = true;
+        return selfMig ? -INFINITY : warp_sum_down(acc);
     }
-    return warp_sum_down(acc);
+    return NAN;      // not reached: the 256-slot stage only takes trees of the register path
 }
 
-// EMAX = 256 / 384: every tree of the batch is known to have <= 256 / 384 events (smaller
-// shared-memory footprint: 4 CTAs = 32 warps per SM instead of 3).  EMAX = 512: trees up to 512 events; larger ones are queued for the CTA-per-tree
-// kernel.  Persistent warps, one tree at a time per warp: lane 0 launches the bulk copies of
-// the tree's array slices (TMA engine), the warp waits on its mbarrier, orders and scans.
+// EMAX = 256 / 384 / 512 / 1024: every tree with n + M + 2 <= EMAX is evaluated here (4 CTAs =
+// 32 warps per SM up to 384, 3 CTAs at 512, 2 CTAs of 5 warps at 1024); larger ones are queued
+// for the CTA-per-tree kernel, or -- when the caller promised a bound and no such kernel
+// follows (p.queue == NULL) -- reported as NaN.  Persistent warps, one tree at a time per
+// warp: lane 0 launches the bulk copies of the tree's array slices (TMA engine), the warp
+// waits on its mbarrier, orders and scans.
+// CTAs per SM of the stages up to 384 slots: shared memory allows four, but three (24 warps,
+// 80 registers per thread) run as fast and leave the register path free of spills
+#ifndef MTT_K1_MINB
+#define MTT_K1_MINB 3
+#endif
 template <int NW, bool HAS_PARENT, bool PER_TREE_MODEL, int EMAX>
 __global__ void __launch_bounds__(warps_per_cta(EMAX) * 32,
-                                  (EMAX <= 384) ? 4 : (EMAX <= 512 ? 3 : 2))
+                                  (EMAX <= 384) ? MTT_K1_MINB : (EMAX <= 512 ? 3 : 2))
 k1_density_warp(const K1Params p)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tabs = reinterpret_cast<ModelTab *>(smem_raw);
     constexpr int W_WARPS = warps_per_cta(EMAX);
     constexpr int nTabs = PER_TREE_MODEL ? W_WARPS : 1;
-    using WS = WarpSmem<HAS_PARENT, EMAX>;
+    using WS = WarpSmem<NW, HAS_PARENT, EMAX>;
     WS *wsAll = reinterpret_cast<WS *>(smem_raw + sizeof(ModelTab) * nTabs);
 
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -820,38 +1122,55 @@ k1_density_warp(const K1Params p)
     }
     __syncthreads();
 
-    const long long nWarpsTotal = (long long)gridDim.x * W_WARPS;
-    long long t = (long long)blockIdx.x * W_WARPS + warp;
+    // (tree indices fit 32 bits: mtt_k1_launch refuses B >= 2^31)
+    const int nWarpsTotal = (int)gridDim.x * W_WARPS, B = (int)p.B;
     uint32_t phase = 0;
+    int t = (int)blockIdx.x * W_WARPS + warp;
     TreeSpan cur = load_span(p, t);
 
 #pragma unroll 1
-    for (; t < p.B; t += nWarpsTotal) {
-        const TreeSpan nxt = load_span(p, t + nWarpsTotal);     // offsets of my next tree
-        if (cur.n + cur.M > EMAX) {
-            // too large for the warp path: queue for k1_density_block
+    for (; t < B; t += nWarpsTotal) {
+        // offsets of my next tree: the loads complete under this tree's work
+        const TreeSpan nxt = load_span(p, (long long)t + nWarpsTotal);
+        if (cur.n + cur.M + SLOT_SLACK > EMAX) {
             if (lane == 0) {
-                const int slot = atomicAdd(&p.queue[0], 1);
-                p.queue[1 + slot] = (int)t;
+                if (p.queue) {       // too large for the warp path: queue for k1_density_block
+                    const int slot = atomicAdd(&p.queue[0], 1);
+                    p.queue[1 + slot] = (int)t;
+                } else {             // beyond the bound the caller gave: an error, loudly
+                    p.logP[t] = NAN;
+                    if (HAS_PARENT && p.valid)
+                        p.valid[t] = 0;
+                }
             }
         } else {
             const StageLayout L = make_layout<HAS_PARENT>(p, cur);
             if (lane == 0)
                 issue_tree<HAS_PARENT, EMAX>(p, cur, L, &ws->st, (uint64_t *)&ws->bar);
             if (PER_TREE_MODEL) {
-                fill_model_tab(tab, p.m + t * d * d, p.N + t * d, d, lane, 32);
+                fill_model_tab(tab, p.m + (long long)t * d * d, p.N + (long long)t * d, d, lane, 32);
                 __syncwarp();
             }
+#ifdef MTT_K1_L2_PREFETCH     // measured slower (405 vs 442 M trees/s): off
+            if (lane == 0)
+                prefetch_tree<HAS_PARENT>(p, nxt);       // (an empty span past the batch's end)
+#endif
             mbar_wait((uint64_t *)&ws->bar, phase);
             phase ^= 1u;
-            bool ok = true;
-            const double acc = process_tree<NW, HAS_PARENT, EMAX>(&ws->st, L, ws->desc, ws->keys,
-                                                                 ws->keys2, cur.n, cur.M, tab, d,
-                                                                 lane, ok);
+            bool ok = true, bad = false;
+#ifdef MTT_K1_EXP_TWICE       // experiment: the work of two trees per staged tree
+            (void)process_tree<NW, HAS_PARENT, EMAX>(ws, L, cur.n, cur.M, tab, d, lane, ok, bad);
+            __syncwarp();
+#endif
+            const double acc = process_tree<NW, HAS_PARENT, EMAX>(ws, L, cur.n, cur.M, tab, d,
+                                                                 lane, ok, bad);
             if (lane == 0) {
                 if (HAS_PARENT && p.valid)
                     p.valid[t] = ok ? 1 : 0;
-                p.logP[t] = (HAS_PARENT && p.checkValidity && !ok) ? -INFINITY : acc;   // :90-91
+                // malformed input (owner / parent / type out of range, a change into its own
+                // type): NaN; an invalid tree with checkValidity: -infinity (:90-91)
+                p.logP[t] = bad ? NAN
+                                : ((HAS_PARENT && p.checkValidity && !ok) ? -INFINITY : acc);
             }
             __syncwarp();      // the stage is free again
         }
@@ -1123,7 +1442,7 @@ template <int NW, bool HP, bool PT, int EMAX>
 int launch_warp(mtt_ctx *ctx, const K1Params &p)
 {
     constexpr int W = warps_per_cta(EMAX);
-    size_t smem = sizeof(ModelTab) * (PT ? W : 1) + sizeof(WarpSmem<HP, EMAX>) * W;
+    size_t smem = sizeof(ModelTab) * (PT ? W : 1) + sizeof(WarpSmem<NW, HP, EMAX>) * W;
     auto kern = k1_density_warp<NW, HP, PT, EMAX>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
@@ -1171,6 +1490,15 @@ int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long l
 }
 
 // maxEvents: > 0 upper bound on nodes + changes of any tree, 0 unknown
+#ifdef MTT_K1_PROBE      // development only: compile just the headline instantiation
+template <int NW>
+int launch_all(mtt_ctx *ctx, const K1Params &p, long long)
+{
+    K1Params q = p;
+    q.queue = nullptr;
+    return launch_warp<0, false, false, 384>(ctx, q);
+}
+#else
 template <int NW>
 int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
 {
@@ -1182,14 +1510,20 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
         if (Ecap > MTT_MAX_TREE_EVENTS)
             Ecap = MTT_MAX_TREE_EVENTS;
     }
-    if (maxEvents > 0 && maxEvents <= 256)          // one launch, nothing can be queued
-        return launch_warp_any<NW, 256>(ctx, p);
-    if (maxEvents > 0 && maxEvents <= 384)          // 4 CTAs (32 warps) per SM still fit
-        return launch_warp_any<NW, 384>(ctx, p);
-    if (maxEvents > 0 && maxEvents <= 512)
-        return launch_warp_any<NW, 512>(ctx, p);
-    if (maxEvents > 0 && maxEvents <= 1024)         // four sorted runs, two merge levels
-        return launch_warp_any<NW, 1024>(ctx, p);
+    // A stage of EMAX slots takes trees with nodes + changes + 2 <= EMAX.  With a bound that
+    // fits a stage: ONE launch and no queue -- a tree beyond the promised bound is reported
+    // as NaN (an error of the caller), never silently skipped.
+    if (maxEvents > 0 && maxEvents + SLOT_SLACK <= 1024) {
+        K1Params q = p;
+        q.queue = nullptr;
+        if (maxEvents + SLOT_SLACK <= 256)
+            return launch_warp_any<NW, 256>(ctx, q);
+        if (maxEvents + SLOT_SLACK <= 384)          // 4 CTAs (32 warps) per SM still fit
+            return launch_warp_any<NW, 384>(ctx, q);
+        if (maxEvents + SLOT_SLACK <= 512)
+            return launch_warp_any<NW, 512>(ctx, q);
+        return launch_warp_any<NW, 1024>(ctx, q);   // four sorted runs, two merge levels
+    }
     // some trees may exceed the warp path: they are queued and consumed by the block kernel;
     // the queue counter is zeroed again for the next call.  A known bound above 1024 means
     // mid-size and large trees: the 1024-event stage takes what it can.
@@ -1203,6 +1537,8 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
     MTT_CUDA(ctx, cudaMemsetAsync(p.queue, 0, sizeof(int), ctx->stream));
     return MTT_OK;
 }
+
+#endif
 
 // Per-node change counts -> per-change owner list (the layout the kernels read), one warp per
 // tree.  Counts that do not add up to the tree's number of changes leave 0xffff owners behind,

@@ -184,6 +184,10 @@ static int sc_logp_dev(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t 
         return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: NULL argument", who);
     if (B == 0)
         return MTT_OK;
+    if (nModels != 1 && nModels != B)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: nModels must be 1 or B", who);
+    if (checkValidity && !parent)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: checkValidity requires parent[]", who);
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
     const uint16_t *chgNode = chgCountOrNode;
     if (!owners) {

@@ -282,3 +282,88 @@ def test_ties_and_zero_length_branches(ctx):
     assert np.all(got == got[0]) and np.isfinite(got[0])
     want = orc.sc_logp_batch(tb, m, N, variant=orc.SUFFSTAT)
     np.testing.assert_allclose(got, want, rtol=1e-12)
+
+
+def test_single_deme(ctx):
+    """d = 1 (the two-deme specialisation with an empty second deme): Kingman's coalescent."""
+    m, N = np.zeros((1, 1)), np.array([1.7])
+    tb = mtt.simulate_trees(64, 40, 1, m, N, seed=11)
+    assert tb.chgTime.size == 0
+    got = _check(tb, m, N, ctx)
+    assert np.all(np.isfinite(got))
+    _check(tb, m, N, ctx, checkValidity=True)
+
+
+def test_types_out_of_range_and_self_changes(ctx):
+    """A node / change type >= d is malformed input: NaN, never a silently wrong number.  A
+    change into the type it leaves has rate m(i,i) = 0 in the reference
+    (SCMigrationModel.java:253-255): log(0) = -infinity."""
+    m, N = mtt.synthetic_model(2)
+    pool = mtt.simulate_trees(8, 30, 2, m, N, seed=5)
+    trees = [pool.tree(i) for i in range(8)]
+    trees[1].nodeType[3] = 7                                   # leaf type outside the model
+    trees[2].nodeType[40] = 2                                  # internal node type = d
+    b3 = next(i for i in range(59) if trees[3].getChangeCount(i) > 0)
+    trees[3].changeTypes[b3][0] = 9                            # change type outside the model
+    b4 = next(i for i in range(59) if trees[4].getChangeCount(i) > 0)
+    trees[4].changeTypes[b4][0] = int(trees[4].nodeType[b4])   # self change
+    tb = mtt.TreeBatch.from_trees(trees)
+    for chk in (False, True):
+        lp = mtt.sc_logp_batch(tb, m, N, checkValidity=chk, ctx=ctx)
+        assert np.isnan(lp[1]) and np.isnan(lp[2]) and np.isnan(lp[3])
+        assert lp[4] == -np.inf
+        ok = [0, 5, 6, 7]
+        np.testing.assert_allclose(lp[ok], orc.sc_logp_batch(pool, m, N)[ok], rtol=RTOL)
+    assert orc.sc_logp_batch(tb.slice(4, 5), m, N)[0] == -np.inf
+    # the same for more than two demes (the general descriptor path)
+    m4, N4 = mtt.synthetic_model(4)
+    pool = mtt.simulate_trees(4, 30, 4, m4, N4, seed=6)
+    trees = [pool.tree(i) for i in range(4)]
+    trees[1].nodeType[2] = 4
+    b2 = next(i for i in range(59) if trees[2].getChangeCount(i) > 0)
+    trees[2].changeTypes[b2][0] = int(trees[2].nodeType[b2])
+    lp = mtt.sc_logp_batch(mtt.TreeBatch.from_trees(trees), m4, N4, ctx=ctx)
+    assert np.isnan(lp[1]) and lp[2] == -np.inf
+    np.testing.assert_allclose(lp[[0, 3]], orc.sc_logp_batch(pool, m4, N4)[[0, 3]], rtol=RTOL)
+
+
+def test_event_bound_hint_is_a_promise(ctx):
+    """mtt_sc_set_max_tree_events on the device-pointer entry: a tree beyond the promised bound
+    is reported as NaN (never left unwritten), and the next call without a bound is unaffected."""
+    import torch
+    from multitypetree_b200 import _lib
+    L = _lib.lib()
+    m, N = mtt.synthetic_model(2)
+    small = mtt.simulate_trees(30, 50, 2, m, N, seed=1)
+    big = mtt.simulate_trees(2, 300, 2, m, N, seed=2)
+    tb = mtt.TreeBatch.from_trees([small.tree(i) for i in range(15)] + [big.tree(0)] +
+                                  [small.tree(i) for i in range(15, 30)] + [big.tree(1)])
+    want = orc.sc_logp_batch(tb, m, N)
+
+    def dev(a):
+        t = torch.from_numpy(np.ascontiguousarray(a).ravel())
+        out = torch.zeros(t.numel() + 64, dtype=t.dtype, device="cuda")
+        out[:t.numel()] = t.cuda()
+        return out
+    arrs = [dev(x) for x in (m, N, tb.nodeOff, tb.height, tb.nodeType, tb.chgNode, tb.chgBase,
+                             tb.chgTime, tb.chgType)]
+    p = [a.data_ptr() for a in arrs]
+    try:
+        for hint in (200, 0, 300, 0):
+            logP = torch.full((tb.B,), 123.0, dtype=torch.float64, device="cuda")
+            ctx.check(L.mtt_sc_set_max_tree_events(ctx.handle, hint))
+            ctx.check(L.mtt_sc_logp_owner_batch_dev(ctx.handle, tb.B, 2, 1, p[0], p[1], p[2], p[3],
+                                                    None, p[4], p[5], p[6], p[7], p[8], 0,
+                                                    logP.data_ptr(), None))
+            ctx.synchronize()
+            got = logP.cpu().numpy()
+            beyond = tb.n_events() > hint if hint else np.zeros(tb.B, bool)
+            assert beyond.sum() == (2 if hint else 0)
+            assert np.all(np.isnan(got[beyond]))
+            np.testing.assert_allclose(got[~beyond], want[~beyond], rtol=RTOL)
+        # checkValidity without parent[] is refused by the device-pointer entry too
+        rc = L.mtt_sc_logp_owner_batch_dev(ctx.handle, tb.B, 2, 1, p[0], p[1], p[2], p[3], None,
+                                           p[4], p[5], p[6], p[7], p[8], 1, logP.data_ptr(), None)
+        assert rc != 0
+    finally:
+        L.mtt_sc_set_max_tree_events(ctx.handle, 0)

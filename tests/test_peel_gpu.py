@@ -121,7 +121,7 @@ def test_proportion_invariant_with_rescaling(ctx, n, rate, gamma):
     rates, props = sm.category_rates_and_proportions()
     _, pat = orc.tree_likelihood(al.patterns, al.patternWeight, par[0], hgt[0], rates, props, f,
                                  2.0, pInv=0.25, useScaling=2, want_patterns=True)
-    np.testing.assert_allclose(tl.getPatternLogLikelihoods(), pat, rtol=RTOL)
+    np.testing.assert_allclose(tl.getPatternLogLikelihoods(), pat, rtol=RTOL, atol=1e-12)
     tl.close()
 
 

@@ -1151,9 +1151,29 @@ k1_density_warp(const K1Params p)
                 fill_model_tab(tab, p.m + (long long)t * d * d, p.N + (long long)t * d, d, lane, 32);
                 __syncwarp();
             }
-#ifdef MTT_K1_L2_PREFETCH     // measured slower (405 vs 442 M trees/s): off
+#ifdef MTT_K1_L2_PREFETCH     // bulk (TMA) prefetch: measured slower (405 vs 442 M trees/s): off
             if (lane == 0)
                 prefetch_tree<HAS_PARENT>(p, nxt);       // (an empty span past the batch's end)
+#endif
+#ifdef MTT_K1_LINE_PREFETCH
+            {   // one 128 B line of my next tree per lane into L2 (lanes 0-15 heights, 16-21
+                // change times, 22-25 node types, 26-27 change types, 28-31 owners)
+                const unsigned char *a;
+                uint32_t bytes, i;
+                if (lane < 16) {
+                    a = (const unsigned char *)(p.height + nxt.n0); bytes = 8u * nxt.n; i = lane;
+                } else if (lane < 22) {
+                    a = (const unsigned char *)(p.chgTime + nxt.c0); bytes = 8u * nxt.M; i = lane - 16;
+                } else if (lane < 26) {
+                    a = (const unsigned char *)(p.nodeType + nxt.n0); bytes = nxt.n; i = lane - 22;
+                } else if (lane < 28) {
+                    a = (const unsigned char *)(p.chgType + nxt.c0); bytes = nxt.M; i = lane - 26;
+                } else {
+                    a = (const unsigned char *)(p.chgNode + nxt.c0); bytes = 2u * nxt.M; i = lane - 28;
+                }
+                if (128u * i < bytes + 127u && bytes)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(a + 128u * i));
+            }
 #endif
             mbar_wait((uint64_t *)&ws->bar, phase);
             phase ^= 1u;

@@ -313,9 +313,9 @@ def bench_density(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm, "unit": "GB/s",
                      "frac": achieved / hbm,
                      # dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture
-                     # (profiles/r2_k1_density_ncu.txt: 152.30 MB for 65536 of these trees),
+                     # (profiles/r2_k1_density_ncu.txt: 153.69 MB for 65536 of these trees),
                      # scaled to this launch's tree count
-                     "traffic": 152.30e6 / 65536 * B, "peak_source": hbm_src,
+                     "traffic": 153.69e6 / 65536 * B, "peak_source": hbm_src,
                      "kernel": "k1_density_warp", "algorithmic_bytes_per_launch": alg_bytes,
                      "kernel_ms": kernel_ms},
         "cpu_baseline": {"value": cpu_v, "unit": "evals/s", "cores": cores, "kind": "port",

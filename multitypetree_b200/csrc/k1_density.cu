@@ -348,6 +348,19 @@ __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
     mbar_arrive_expect_tx(bar, 0);
     return;
 #endif
+#ifdef MTT_K1_LANE_STAGE      // measured neutral (500 vs 504 M trees/s): off
+    // The TMA engine takes ~50 cycles per request whatever its size: only the two time arrays
+    // (85 % of the bytes) and parent[] go through it, the three small arrays are fetched by
+    // the lanes (stage_small).
+    mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szP);
+    if (L.szH)
+        bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
+    if (L.szC)
+        bulk_g2s(st->time + L.szH, (const unsigned char *)(p.chgTime + s.c0) - (L.cOff - L.szH),
+                 L.szC, bar);
+    if (HAS_PARENT && L.szP)
+        bulk_g2s(st->par, (const unsigned char *)(p.parent + s.n0) - L.pOff, L.szP, bar);
+#else
     mbar_arrive_expect_tx(bar, L.szH + L.szC + L.szT + L.szCT + L.szK + L.szP);
     if (L.szH)
         bulk_g2s(st->time, (const unsigned char *)(p.height + s.n0) - L.hOff, L.szH, bar);
@@ -362,6 +375,36 @@ __device__ __forceinline__ void issue_tree(const K1Params &p, const TreeSpan &s,
         bulk_g2s(st->type, (const unsigned char *)(p.nodeType + s.n0) - L.tOff, L.szT, bar);
     if (HAS_PARENT && L.szP)
         bulk_g2s(st->par, (const unsigned char *)(p.parent + s.n0) - L.pOff, L.szP, bar);
+#endif
+}
+
+// The whole warp: node types, change types and change owners as 16-byte chunks, one per lane
+// and round, into the same places the bulk copies would put them.
+template <bool HAS_PARENT, int EMAX>
+__device__ __forceinline__ void stage_small(const K1Params &p, const TreeSpan &s,
+                                            const StageLayout &L,
+                                            WarpStage<HAS_PARENT, EMAX> *st, int lane)
+{
+    const uint32_t cT = L.szT >> 4, cCT = L.szCT >> 4, cK = L.szK >> 4;
+    const unsigned char *gT = (const unsigned char *)(p.nodeType + s.n0) - L.tOff;
+    const unsigned char *gCT = (const unsigned char *)(p.chgType + s.c0) - (L.ctOff - L.szT);
+    const unsigned char *gK = (const unsigned char *)(p.chgNode + s.c0) - L.kOff;
+#pragma unroll 1
+    for (uint32_t c = lane; c < cT + cCT + cK; c += 32) {
+        const unsigned char *src;
+        unsigned char *dst;
+        if (c < cT) {
+            src = gT + 16u * c;
+            dst = st->type + 16u * c;
+        } else if (c < cT + cCT) {
+            src = gCT + 16u * (c - cT);
+            dst = st->type + L.szT + 16u * (c - cT);
+        } else {
+            src = gK + 16u * (c - cT - cCT);
+            dst = st->cnt + 16u * (c - cT - cCT);
+        }
+        *reinterpret_cast<uint4 *>(dst) = __ldg(reinterpret_cast<const uint4 *>(src));
+    }
 }
 
 // L2 prefetch of a slice's 16 B-aligned superset (what the bulk copy will read)
@@ -571,6 +614,29 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
     const bool fast = E + SLOT_SLACK <= 256;
     int Epad = fast ? 256 : ((EMAX > 512 && E + SLOT_SLACK > 512) ? EMAX : E2);
 
+#ifdef MTT_K1_EXP_NOPHASEA
+    if (fast) {
+        uint32_t key[8];
+        double t[8];
+        HiWordRange hr;
+        hr.init();
+#pragma unroll
+        for (int k = 0; k < 8; k++) {
+            t[k] = tm[lane + 32 * k];
+            hr.add(t[k]);
+        }
+        const Quant qz = make_quant<IDX_BITS>(hr);
+#pragma unroll
+        for (int k = 0; k < 8; k++)
+            key[k] = quant_key<IDX_BITS>(qz, t[k], (uint32_t)(lane + 32 * k));
+        okOut = true; badOut = false;
+        return (double)(key[0] + key[3] + key[7] + key[1] + key[2] + key[4] + key[5] + key[6]);
+    }
+#endif
+#ifdef MTT_K1_EXP_NOKEYS
+    okOut = true; badOut = false;
+    return tm[lane];
+#endif
     // ---- phase A: event descriptors.  Every change names the node that owns it (chgNode),
     //      changes of one node are adjacent and ordered child -> parent: the first change of a
     //      branch leaves the node's type, any other one the type its predecessor entered.
@@ -720,10 +786,15 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
             for (int k = 0; k < 8; k++)
                 key[k] = quant_key<IDX_BITS>(qz, t[k], (uint32_t)(lane + 32 * k));
         }
+#ifndef MTT_K1_EXP_NOSORT       // (experiment: cost of everything but the ordering network)
         warp_sort256(key, lane);
+#endif
 #pragma unroll
         for (int r = 0; r < 8; r++)
             key[r] &= IDX_MASK;                              // slots, in time order
+#ifdef MTT_K1_EXP_NOSCAN        // (experiment: cost of everything but the scan)
+        return (double)(key[0] + key[3] + key[7]);
+#endif
         bool repaired = false;
         for (;;) {
             // time of the last event before my chunk = the previous lane's last event
@@ -757,7 +828,6 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
                 const double i0 = tab->inv2N[0], i1 = tab->inv2N[1];
                 const double b0 = tab->mu[0] - i0, b1 = tab->mu[1] - i1;
                 double lambda = k0 * (k0 * i0 + b0) + k1 * (k1 * i1 + b1);
-                double firstTerm = 0.0;
 #pragma unroll
                 for (int r = 0; r < 8; r++) {
                     const double x = (r == 0) ? xFirst : (r == 7) ? xLast : tm[key[r]];
@@ -768,8 +838,6 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
                     prevT = x;
                     // log(1/N) or log(m)  (:127-137)
                     const double term = __hiloint2double((int)rec.y, (int)rec.x);
-                    if (r == 0)
-                        firstTerm = term;
                     acc += term;
                     k0 += __hiloint2double((int)rec.z, 0);
                     k1 += __hiloint2double((int)rec.w, 0);
@@ -777,8 +845,8 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
                     if (r & 1)       // keep the scheduler from hoisting all 32 loads (spills)
                         asm volatile("" ::: "memory");
                 }
-                if (lane == 0)
-                    acc -= firstTerm;                        // event 0 is skipped (:101)
+                if (lane == 0)                               // event 0 is skipped (:101)
+                    acc -= reinterpret_cast<const ClsRec *>(clsBytes + dsc[0])->term;
             } else {
                 Counts<NW> local;
                 cnt_zero<NW>(local);
@@ -832,6 +900,9 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
                     first = false;
                 }
             }
+#ifdef MTT_K1_EXP_NOSORT
+            break;
+#endif
             if (repaired || !__any_sync(FULL_MASK, invAcc < 0))
                 break;                                       // (NaN times cannot be ordered)
             repaired = true;
@@ -1127,11 +1198,20 @@ k1_density_warp(const K1Params p)
     uint32_t phase = 0;
     int t = (int)blockIdx.x * W_WARPS + warp;
     TreeSpan cur = load_span(p, t);
+#ifdef MTT_K1_STAGGER       // experiment: spread the warps of an SM over the phases of a tree
+    __nanosleep((unsigned)(MTT_K1_STAGGER * (warp + W_WARPS * (blockIdx.x % 3))));
+#endif
 
 #pragma unroll 1
     for (; t < B; t += nWarpsTotal) {
+#ifdef MTT_K1_NO_SPAN_PREFETCH
+        if (t != (int)blockIdx.x * W_WARPS + warp)
+            cur = load_span(p, t);
+        const TreeSpan nxt = cur;
+#else
         // offsets of my next tree: the loads complete under this tree's work
         const TreeSpan nxt = load_span(p, (long long)t + nWarpsTotal);
+#endif
         if (cur.n + cur.M + SLOT_SLACK > EMAX) {
             if (lane == 0) {
                 if (p.queue) {       // too large for the warp path: queue for k1_density_block
@@ -1147,6 +1227,9 @@ k1_density_warp(const K1Params p)
             const StageLayout L = make_layout<HAS_PARENT>(p, cur);
             if (lane == 0)
                 issue_tree<HAS_PARENT, EMAX>(p, cur, L, &ws->st, (uint64_t *)&ws->bar);
+#ifdef MTT_K1_LANE_STAGE
+            stage_small<HAS_PARENT, EMAX>(p, cur, L, &ws->st, lane);
+#endif
             if (PER_TREE_MODEL) {
                 fill_model_tab(tab, p.m + (long long)t * d * d, p.N + (long long)t * d, d, lane, 32);
                 __syncwarp();
@@ -1177,6 +1260,7 @@ k1_density_warp(const K1Params p)
 #endif
             mbar_wait((uint64_t *)&ws->bar, phase);
             phase ^= 1u;
+            __syncwarp();        // the lanes' own stores (stage_small) are visible to the warp
             bool ok = true, bad = false;
 #ifdef MTT_K1_EXP_TWICE       // experiment: the work of two trees per staged tree
             (void)process_tree<NW, HAS_PARENT, EMAX>(ws, L, cur.n, cur.M, tab, d, lane, ok, bad);

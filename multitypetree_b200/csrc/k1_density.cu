@@ -223,7 +223,7 @@ __device__ __forceinline__ double event_term(uint32_t desc, const ModelTab *t, i
 // doubles.  Node e sits in slot e, change c in slot cs + c (cs = n, n + 1 or n + 2: the bulk
 // copies land on 16-byte boundaries); `desc[slot]` describes the event.  Every slot of the
 // padded range [0, Epad) that holds no event -- the gap before the changes, the tail, ignored
-// root-branch changes -- is turned into a twin of node 0: the same time, a descriptor that
+// root-branch changes -- is turned into a twin of the last node: the same time, a descriptor that
 // does nothing.  A twin adds exactly 0 to the sum (its interval has length 0), so nothing
 // downstream needs a sentinel, a bound or a predicate: the sort takes Epad keys, the scan
 // takes Epad events.  The number of twins depends only on n + M, never on the alignment of
@@ -737,9 +737,12 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
         }
         __syncwarp();
     }
-    // ---- twins of node 0 in every slot without an event
+    // ---- twins in every slot without an event.  They copy the LAST node (the root in BEAST's
+    //      usual numbering, else some internal node): its time is shared with no other event,
+    //      so practically never does a real event have to be carried past the block of twins
+    //      by the exact-order repair (which a crowded leaf time would make likely).
     {
-        const double t0 = (n > 0) ? tm[0] : 0.0;
+        const double t0 = (n > 0) ? tm[n - 1] : 0.0;
         __syncwarp();
         if (lane < cs - n) {
             tm[n + lane] = t0;
@@ -1285,32 +1288,42 @@ k1_density_warp(const K1Params p)
 // =====================================================================================
 // CTA-per-tree kernel (queue consumer; also the direct path when every tree is large)
 // =====================================================================================
-constexpr int BLK_THREADS = 512;
+// Trees beyond the warp stages (configs 3 and 4: 2.1 k and 10.4 k events), up to
+// MTT_MAX_TREE_EVENTS.  The same plan as the warp path, spread over a CTA: S = the event count
+// rounded up to whole runs; every warp orders runs of 256 slots in registers (warp_sort256),
+// the runs are merged level by level with merge path (every thread produces 8 consecutive
+// outputs per step), quantisation ties are put in exact order by odd-even passes over equal
+// quanta, and each thread scans S / THREADS consecutive positions after a CTA-wide prefix sum
+// of the packed lineage counts.  Slots without an event are twins of the last node, as above.
+// Shared memory: two key buffers, the descriptors and -- when it fits -- the event times
+// (18 bytes per slot, else 10 and the times are read through L1 / L2).
+struct CtaQuant {
+    double lo, scale;
+    int shift;                         // slot bits of the key
+};
 
-__device__ __forceinline__ unsigned long long block_key(double x, double lo, double scale,
-                                                        int idx, uint32_t desc)
-{
-    // 38-bit quantised time | 14-bit index | 12-bit descriptor
-    unsigned long long q = (unsigned long long)((x - lo) * scale);
-    if (q > 0x3fffffffffull)
-        q = 0x3fffffffffull;
-    return (q << 26) | ((unsigned long long)idx << 12) | (desc & 0xfffu);
-}
-
-template <int NW>
-__global__ void __launch_bounds__(BLK_THREADS)
-k1_density_block(const K1Params p, int Ecap, int useQueue)
+template <int NW, int THREADS>
+__global__ void __launch_bounds__(THREADS)
+k1_density_cta(const K1Params p, int Scap, int tmInSmem, int useQueue)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tab = reinterpret_cast<ModelTab *>(smem_raw);
-    unsigned long long *keys = reinterpret_cast<unsigned long long *>(smem_raw + sizeof(ModelTab));
-    uint32_t *offs = reinterpret_cast<uint32_t *>(keys + Ecap);      // Ecap entries
-    __shared__ double redD[BLK_THREADS / 32 * 2];
-    __shared__ unsigned long long redC[BLK_THREADS / 32][NW];
+    unsigned char *sm = smem_raw + sizeof(ModelTab);
+    double *tmS = nullptr;
+    if (tmInSmem) {
+        tmS = reinterpret_cast<double *>(sm);
+        sm += (size_t)Scap * 8;
+    }
+    uint32_t *keysA = reinterpret_cast<uint32_t *>(sm);
+    uint32_t *keysB = keysA + Scap;
+    uint16_t *desc = reinterpret_cast<uint16_t *>(keysB + Scap);
+    constexpr int NWARPS = THREADS / 32;
+    __shared__ double redD[NWARPS];
+    __shared__ unsigned long long redC[NWARPS][NW];
+    __shared__ int redI[3 * NWARPS];
     __shared__ int sFlag;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int nWarps = BLK_THREADS / 32;
     const int d = p.d;
     const long long nWork = useQueue ? (long long)p.queue[0] : p.B;
 
@@ -1325,61 +1338,51 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
         const uint8_t *T = p.nodeType + n0, *CTy = p.chgType + c0;
         const uint16_t *O = p.chgNode + c0;         // change owners
         const int *P = p.parent ? p.parent + n0 : nullptr;
+        constexpr int RUN = 256 > THREADS ? 256 : THREADS;     // S is a multiple of both
+        const int S = (E + RUN - 1) / RUN * RUN;
 
-        __syncthreads();
-        if (E > Ecap) {   // beyond the smem sort capacity: report NaN (host maps it to an error)
+        __syncthreads();                            // the previous tree is done with smem
+        if (S > Scap || E == 0) {   // beyond the capacity: NaN (host maps it to an error)
             if (tid == 0) {
-                p.logP[t] = NAN;
+                p.logP[t] = (E == 0) ? 0.0 : NAN;
                 if (p.valid)
-                    p.valid[t] = 0;
+                    p.valid[t] = E == 0;
             }
             continue;
         }
         const bool perTree = p.nModels > 1;
         fill_model_tab(tab, p.m + (perTree ? t * d * d : 0), p.N + (perTree ? t * d : 0), d, tid,
-                       BLK_THREADS);
+                       THREADS);
 
-        // ---- time range over node heights and change times
-        double lo = INFINITY, hi = -INFINITY;
-        for (int e = tid; e < E; e += BLK_THREADS) {
-            double x = (e < n) ? H[e] : CT[e - n];
-            lo = fmin(lo, x);
-            hi = fmax(hi, x);
-        }
-        lo = warp_min(lo);
-        hi = warp_max(hi);
-        if (lane == 0) {
-            redD[warp] = lo;
-            redD[nWarps + warp] = hi;
-        }
-        __syncthreads();
-        lo = redD[0];
-        hi = redD[nWarps];
-        for (int w = 1; w < nWarps; w++) {
-            lo = fmin(lo, redD[w]);
-            hi = fmax(hi, redD[nWarps + w]);
-        }
-        const double range = hi - lo;
-        const double scale = (range > 0.0) ? 274877906943.0 / range : 0.0;   // 2^38 - 1
-        __syncthreads();
-
-        // ---- keys (node-centric) + validity
-        int Epad = 1;
-        while (Epad < E)
-            Epad <<= 1;
-        bool ok = true;
-        uint8_t *hasChg = reinterpret_cast<uint8_t *>(offs);          // n bytes, validity only
-        for (int e = tid; e < n; e += BLK_THREADS) {
-            keys[e] = block_key(H[e], lo, scale, e,
-                                ((e < nLeaves) ? KIND_SAMPLE : KIND_COALESCE) << 10 | T[e] << 5);
+        // ---- descriptors, staged times, validity, time range (high words)
+        bool ok = true, bad = false, selfMig = false;
+        HiWordRange hr;
+        hr.init();
+        const double t0 = H[n - 1];                 // twins copy the last node (see above)
+        uint8_t *hasChg = reinterpret_cast<uint8_t *>(keysB);         // n bytes, validity only
+        for (int e = tid; e < n; e += THREADS) {
+            const double x = H[e];
+            const int type = T[e];
+            hr.add(x);
+            if (tmS)
+                tmS[e] = x;
+            bad |= type >= d;
+            desc[e] = (uint16_t)((e < nLeaves) ? (KIND_SAMPLE << 10 | (type & 31) << 5)
+                                               : (KIND_COALESCE << 10 | (type & 31) << 5 |
+                                                  (type & 31)));
             if (P)
                 hasChg[e] = 0;
         }
+        for (int s2 = E + tid; s2 < S; s2 += THREADS) {               // twins of the last node
+            if (tmS)
+                tmS[s2] = t0;
+            desc[s2] = (uint16_t)(KIND_NONE << 10);
+        }
         __syncthreads();
-        for (int c = tid; c < M; c += BLK_THREADS) {
+        for (int c = tid; c < M; c += THREADS) {
             const int node = O[c];
-            const bool bad = node >= n;
-            const int nd = bad ? 0 : node;
+            const bool oob = node >= n;
+            const int nd = oob ? 0 : node;
             const bool first = (c == 0) || ((int)O[c - 1] != node);
             const bool last = (c == M - 1) || ((int)O[c + 1] != node);
             const int par = P ? P[nd] : 0;
@@ -1387,108 +1390,227 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
             const int from = first ? (int)T[nd] : (int)CTy[c - 1];
             const int to = CTy[c];
             const double tc = CT[c];
-            if (bad || isRoot)
-                keys[n + c] = ~0ull;                 // ignored (:161-162): sorts with the padding
-            else
-                keys[n + c] = block_key(tc, lo, scale, n + c, KIND_MIGRATE << 10 | from << 5 | to);
-            ok = ok && !bad;
+            bad |= (from >= d) | (to >= d) | (P && par >= n);
+            ok = ok && !oob;
+            // ignored (:161-162), owner-less or self changes do nothing; the first two also
+            // leave the time axis (twins of node 0)
+            const bool gone = oob || isRoot;
+            selfMig |= (from == to) && !gone;
+            desc[n + c] = (gone || from == to)
+                              ? (uint16_t)(KIND_NONE << 10)
+                              : (uint16_t)(KIND_MIGRATE << 10 | (from & 31) << 5 | (to & 31));
+            if (tmS)
+                tmS[n + c] = (gone || from == to) ? t0 : tc;
+            if (!gone && from != to)
+                hr.add(tc);
             if (P) {
                 const double before = first ? H[nd] : CT[c - 1];
                 ok = ok && !(before > tc);
-                if (last && !isRoot && !bad) {
+                if (last && !isRoot && !oob && par < n) {
                     ok = ok && !(tc > H[par]);
                     ok = ok && (to == (int)T[par]);
                 }
-                if (first && !bad)
+                if (first && !oob)
                     hasChg[nd] = 1;
             }
         }
         if (P) {
             __syncthreads();
-            for (int e = tid; e < n; e += BLK_THREADS) {
+            for (int e = tid; e < n; e += THREADS) {
                 const int par = P[e];
-                if (par >= 0 && !hasChg[e]) {
+                bad |= par >= n;
+                if (par >= 0 && par < n && !hasChg[e]) {
                     ok = ok && !(H[e] > H[par]);
                     ok = ok && (T[e] == T[par]);
                 }
             }
         }
-        for (int e = E + tid; e < Epad; e += BLK_THREADS)
-            keys[e] = ~0ull;
-        if (tid == 0)
-            sFlag = 1;
-        __syncthreads();
-        if (!ok)
-            sFlag = 0;
-
-        // ---- bitonic sort in shared memory (ascending)
-        for (int size = 2; size <= Epad; size <<= 1) {
-            for (int stride = size >> 1; stride > 0; stride >>= 1) {
-                __syncthreads();
-                for (int i = tid; i < (Epad >> 1); i += BLK_THREADS) {
-                    const int a = 2 * i - (i & (stride - 1));
-                    int b = a + stride;                       // half cleaner
-                    if (stride == (size >> 1))                // merge start: reflected partner
-                        b = (a & ~(size - 1)) + (size - 1 - (a & (size - 1)));
-                    unsigned long long ka = keys[a], kb = keys[b];
-                    if (ka > kb) {
-                        keys[a] = kb;
-                        keys[b] = ka;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const bool treeOk = sFlag != 0;
-
-        // ---- chunked scan: thread owns sorted positions [q0, q1)
-        const int chunk = (Epad + BLK_THREADS - 1) / BLK_THREADS;
-        const int q0 = min(tid * chunk, Epad), q1 = min(q0 + chunk, Epad);
-        auto evTime = [&](unsigned long long k) -> double {
-            if (k == ~0ull)
-                return INFINITY;
-            int idx = (int)((k >> 12) & 0x3fff);
-            return (idx < n) ? H[idx] : CT[idx - n];
+        // event time by slot: staged, or through the caches (a change that does nothing is a
+        // twin of the last node, like the padding)
+        auto ev_time = [&](int slot) -> double {
+            if (tmS)
+                return tmS[slot];
+            if (slot < n)
+                return H[slot];
+            if (slot >= E || ((desc[slot] >> 10) & 3) == KIND_NONE)
+                return t0;
+            return CT[slot - n];
         };
-        // repair pass: quantisation ties may be out of exact order (rare; 38-bit quanta)
+        // CTA-wide reductions of the range and the verdicts
         {
-            bool again = true;
-            while (again) {
-                __syncthreads();
-                if (tid == 0)
-                    sFlag = 0;
-                __syncthreads();
-                bool bad = false;
-                for (int par2 = 0; par2 < 2; par2++) {
-                    for (int i = tid; 2 * i + par2 + 1 < Epad; i += BLK_THREADS) {
-                        int a = 2 * i + par2;
-                        unsigned long long ka = keys[a], kb = keys[a + 1];
-                        if ((ka >> 26) == (kb >> 26) && ka != ~0ull && kb != ~0ull) {
-                            if (evTime(ka) > evTime(kb)) {
-                                keys[a] = kb;
-                                keys[a + 1] = ka;
-                                bad = true;
-                            }
-                        }
-                    }
-                    __syncthreads();
-                }
-                if (bad)
-                    sFlag = 1;
-                __syncthreads();
-                again = sFlag != 0;
+            const int smin = __reduce_min_sync(FULL_MASK, hr.smin);
+            const int smax = __reduce_max_sync(FULL_MASK, hr.smax);
+            const uint32_t umax = __reduce_max_sync(FULL_MASK, hr.umax);
+            const uint32_t f = __reduce_or_sync(FULL_MASK, (bad ? 1u : 0u) | (ok ? 0u : 2u) |
+                                                               (selfMig ? 4u : 0u));
+            if (tid == 0)
+                sFlag = 0;
+            __syncthreads();
+            if (lane == 0) {
+                redI[warp] = smin;
+                redI[NWARPS + warp] = smax;
+                redI[2 * NWARPS + warp] = (int)umax;
+                atomicOr(&sFlag, (int)f);
             }
+            __syncthreads();
+            hr.init();
+            for (int w = 0; w < NWARPS; w++) {
+                hr.smin = min(hr.smin, redI[w]);
+                hr.smax = max(hr.smax, redI[NWARPS + w]);
+                hr.umax = max(hr.umax, (uint32_t)redI[2 * NWARPS + w]);
+            }
+            bad = sFlag & 1;
+            ok = !(sFlag & 3);
+            selfMig = sFlag & 4;
+        }
+        // Quantisation: slot bits = ceil(log2 S), the rest of the key is time.  With 10^4
+        // events only 18 bits are left, and coalescent times crowd just after every sampling
+        // date (thousands of lineages -> spacings of 1e-7): a uniform grid would put dozens of
+        // events into one quantum.  The grid is equalised instead: a histogram of the times
+        // over KB uniform bins, and every bin gets a share of the quanta proportional to its
+        // events (at least one), i.e. the key is a piecewise-linear, monotone map of time that
+        // is steep where the events are dense.
+        CtaQuant qz;
+        qz.shift = 32 - __clz(S - 1);
+        const uint32_t slotMask = (1u << qz.shift) - 1u;
+        const double QTOT = (double)((1u << (32 - qz.shift)) - 2u);
+        int KB = 1 << (31 - __clz(S >> 2));
+        KB = min(KB, 1024);
+        uint32_t *hist = keysB, *qstart = keysB + KB;      // (keysB is free until the merges)
+        {
+            const int hwLo = ((int)hr.umax < 0) ? (int)hr.umax : hr.smin;
+            const int hwHi = (hr.smax >= 0) ? hr.smax : hr.smin;
+            qz.lo = __hiloint2double(hwLo, hwLo < 0 ? -1 : 0);
+            const double hi = __hiloint2double(hwHi, hwHi < 0 ? 0 : -1);
+            const double range = hi - qz.lo;
+            qz.scale = (range > 1e-300 && range < INFINITY)
+                           ? (double)KB * (1.0 - 1.0 / 1048576.0) / range : 0.0;   // bins per time
+        }
+        for (int i = tid; i < KB; i += THREADS)
+            hist[i] = 0u;
+        __syncthreads();
+        for (int slot = tid; slot < S; slot += THREADS) {
+            const int b = min(KB - 1, max(0, (int)((ev_time(slot) - qz.lo) * qz.scale)));
+            atomicAdd(&hist[b], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {                                   // exclusive prefix of the bins' quanta
+            uint32_t carry = 0;
+            for (int b0 = 0; b0 < KB; b0 += 32) {
+                const uint32_t qn = 1u + (uint32_t)((QTOT - (double)KB) * (double)hist[b0 + lane] /
+                                                    (double)S);
+                uint32_t incl = qn;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const uint32_t v = __shfl_up_sync(FULL_MASK, incl, o);
+                    if (lane >= o)
+                        incl += v;
+                }
+                qstart[b0 + lane] = carry + incl - qn;
+                carry += __shfl_sync(FULL_MASK, incl, 31);
+            }
+            if (lane == 0)
+                qstart[KB] = carry;
+        }
+        __syncthreads();
+        auto quant = [&](double x) -> uint32_t {
+            const double f = (x - qz.lo) * qz.scale;
+            const int b = min(KB - 1, max(0, (int)f));
+            const uint32_t q0 = qstart[b], qn = qstart[b + 1] - q0;
+            const uint32_t in = (uint32_t)max(0.0, (f - (double)b) * (double)qn);
+            return q0 + min(qn - 1u, in);
+        };
+
+        // ---- runs of 256 slots, ordered in registers
+        for (int run = warp; run < S / 256; run += NWARPS) {
+            uint32_t key[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int slot = 256 * run + lane + 32 * k;
+                key[k] = (quant(ev_time(slot)) << qz.shift) | (uint32_t)slot;
+            }
+            warp_sort256(key, lane);
+            uint4 *dst = reinterpret_cast<uint4 *>(keysA + 256 * run + 8 * lane);
+            dst[0] = make_uint4(key[0], key[1], key[2], key[3]);
+            dst[1] = make_uint4(key[4], key[5], key[6], key[7]);
+        }
+        __syncthreads();
+
+        // ---- merge levels (merge path): every thread writes 8 consecutive outputs per step
+        uint32_t *src = keysA, *dst = keysB;
+        for (int L = 256; L < S; L <<= 1) {
+            for (int o = tid * 8; o < S; o += THREADS * 8) {
+                const int base = o & ~(2 * L - 1);
+                const int la = min(L, S - base), lb = max(0, min(L, S - base - L));
+                const uint32_t *A = src + base, *B = src + base + L;
+                const int diag = o - base;
+                int a0 = max(0, diag - lb), a1 = min(diag, la);
+                while (a0 < a1) {
+                    const int mid = (a0 + a1) >> 1;
+                    if (A[mid] <= B[diag - 1 - mid])
+                        a0 = mid + 1;
+                    else
+                        a1 = mid;
+                }
+                int i = a0, j = diag - a0;
+                uint32_t ka = (i < la) ? A[i] : 0xffffffffu, kb = (j < lb) ? B[j] : 0xffffffffu;
+                uint32_t out[8];
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    const bool takeA = ka <= kb;
+                    out[q] = takeA ? ka : kb;
+                    if (takeA) {
+                        i++;
+                        ka = (i < la) ? A[i] : 0xffffffffu;
+                    } else {
+                        j++;
+                        kb = (j < lb) ? B[j] : 0xffffffffu;
+                    }
+                }
+                uint4 *w = reinterpret_cast<uint4 *>(dst + o);
+                w[0] = make_uint4(out[0], out[1], out[2], out[3]);
+                w[1] = make_uint4(out[4], out[5], out[6], out[7]);
+            }
+            __syncthreads();
+            uint32_t *tmp = src;
+            src = dst;
+            dst = tmp;
         }
 
+        // ---- exact order inside equal quanta: odd-even passes until nothing moves
+        for (;;) {
+            bool moved = false;
+            __syncthreads();
+            if (tid == 0)
+                sFlag = 0;
+            for (int parity = 0; parity < 2; parity++) {
+                __syncthreads();
+                for (int a = 2 * tid + parity; a + 1 < S; a += 2 * THREADS) {
+                    const uint32_t ka = src[a], kb = src[a + 1];
+                    if ((ka >> qz.shift) == (kb >> qz.shift) &&
+                        ev_time((int)(ka & slotMask)) > ev_time((int)(kb & slotMask))) {
+                        src[a] = kb;
+                        src[a + 1] = ka;
+                        moved = true;
+                    }
+                }
+            }
+            if (moved)
+                sFlag = 1;
+            __syncthreads();
+            if (!sFlag)
+                break;
+        }
+
+        // ---- scan: thread owns sorted positions [q0, q0 + chunk)
+        const int chunk = S / THREADS;
+        const int q0 = tid * chunk;
         Counts<NW> local;
 #pragma unroll
         for (int i = 0; i < NW; i++)
             local.w[i] = 0;
-        for (int q = q0; q < q1; q++) {
-            unsigned long long k = keys[q];
-            if (k != ~0ull)
-                cnt_apply<NW>(local, (uint32_t)(k & 0xfff));
-        }
+        for (int q = q0; q < q0 + chunk; q++)
+            cnt_apply<NW>(local, desc[src[q] & slotMask]);
         Counts<NW> base;
 #pragma unroll
         for (int i = 0; i < NW; i++) {
@@ -1505,26 +1627,39 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
         }
         __syncthreads();
 #pragma unroll
-        for (int i = 0; i < NW; i++)
+        for (int i = 0; i < NW; i++) {
             for (int w = 0; w < warp; w++)
                 base.w[i] += redC[w][i];
-
-        double prevT = (q0 > 0 && q0 < Epad) ? evTime(keys[q0 - 1]) : 0.0;
+            base.w[i] += CNT_BIAS_WORD;              // see CNT_BIAS: equal-time transients
+        }
+        double lambda = 0.0;
+        for (int c = 0; c < d; c++) {
+            const double kd = (double)cnt_get<NW>(base, c);
+            lambda += (kd * (kd - 1.0)) * tab->inv2N[c] + kd * tab->mu[c];
+        }
+        double prevT = ev_time((int)(src[q0 > 0 ? q0 - 1 : 0] & slotMask));
         double acc = 0.0;
-        for (int q = q0; q < q1; q++) {
-            unsigned long long k = keys[q];
-            if (k == ~0ull)
-                break;
-            double x = evTime(k);
-            uint32_t desc = (uint32_t)(k & 0xfff);
-            if (q > 0) {
-                double dt = x - prevT;
-                if (dt > 0.0)
-                    acc -= dt * cnt_lambda<NW>(base, tab, d);
-                acc += event_term(desc, tab, d);
-            }
-            cnt_apply<NW>(base, desc);
+        bool first = (tid == 0);                     // event 0 is skipped (:101)
+        for (int q = q0; q < q0 + chunk; q++) {
+            const int slot = (int)(src[q] & slotMask);
+            const double x = ev_time(slot);
+            const uint32_t ds = desc[slot];
+            const int kind = (ds >> 10) & 3, from = (ds >> 5) & 31, to = ds & 31;
+            const double dt = x - prevT;
+            acc = fma(-dt, lambda, acc);
             prevT = x;
+            const bool leave = (kind == KIND_COALESCE) | (kind == KIND_MIGRATE);
+            const bool enter = (kind == KIND_SAMPLE) | (kind == KIND_MIGRATE);
+            const int a = (kind == KIND_MIGRATE) ? to : from;
+            const double term = tab->logM[from * d + to];   // log(1/N) or log(m)  (:127-137)
+            acc += (leave && !first) ? term : 0.0;
+            const double kl = (double)cnt_get<NW>(base, from), ke = (double)cnt_get<NW>(base, a);
+            const double dl = (2.0 * (kl - 1.0)) * tab->inv2N[from] + tab->mu[from];
+            const double de = (2.0 * ke) * tab->inv2N[a] + tab->mu[a];
+            lambda += (enter ? de : 0.0) - (leave ? dl : 0.0);
+            cnt_add<NW>(base, from, -(long long)leave);
+            cnt_add<NW>(base, a, (long long)enter);
+            first = false;
         }
         acc = warp_sum_down(acc);
         __syncthreads();
@@ -1533,11 +1668,13 @@ k1_density_block(const K1Params p, int Ecap, int useQueue)
         __syncthreads();
         if (tid == 0) {
             double tot = 0.0;
-            for (int w = 0; w < nWarps; w++)
+            for (int w = 0; w < NWARPS; w++)
                 tot += redD[w];
             if (P && p.valid)
-                p.valid[t] = treeOk ? 1 : 0;
-            p.logP[t] = (P && p.checkValidity && !treeOk) ? -INFINITY : tot;
+                p.valid[t] = ok ? 1 : 0;
+            p.logP[t] = bad ? NAN
+                            : ((P && p.checkValidity && !ok) ? -INFINITY
+                                                             : (selfMig ? -INFINITY : tot));
         }
     }
 }
@@ -1574,23 +1711,36 @@ int launch_warp_any(mtt_ctx *ctx, const K1Params &p)
               : launch_warp<NW, false, false, EMAX>(ctx, p);
 }
 
-template <int NW>
-int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long long nWorkHint)
+template <int NW, int THREADS>
+int launch_cta_t(mtt_ctx *ctx, const K1Params &p, int Scap, int useQueue, long long nWorkHint)
 {
-    size_t smem = sizeof(ModelTab) + (size_t)Ecap * 12;
-    auto kern = k1_density_block<(NW == 0) ? 1 : NW>;
+    // 10 bytes per slot for the keys and descriptors, 8 more when the times are staged too
+    const size_t fixed = sizeof(ModelTab) + 16;
+    int tmInSmem = fixed + (size_t)Scap * 18 <= 200 * 1024;
+    size_t smem = fixed + (size_t)Scap * (tmInSmem ? 18 : 10);
+    auto kern = k1_density_cta<(NW == 0) ? 1 : NW, THREADS>;
     MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)smem));
     int perSM = 1;
-    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, BLK_THREADS, smem));
+    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, THREADS, smem));
     if (perSM < 1)
         perSM = 1;
     long long grid = (long long)ctx->numSMs * perSM;
     if (nWorkHint > 0 && nWorkHint < grid)
         grid = nWorkHint;
-    kern<<<(unsigned)grid, BLK_THREADS, smem, ctx->stream>>>(p, Ecap, useQueue);
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(p, Scap, tmInSmem, useQueue);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
+}
+
+// Ecap: upper bound on the events of any tree the kernel will see
+template <int NW>
+int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long long nWorkHint)
+{
+    // 256 threads up to 4096 slots (several CTAs per SM), 512 beyond (one or two CTAs per SM)
+    if (Ecap <= 4096)
+        return launch_cta_t<NW, 256>(ctx, p, (Ecap + 255) / 256 * 256, useQueue, nWorkHint);
+    return launch_cta_t<NW, 512>(ctx, p, (Ecap + 511) / 512 * 512, useQueue, nWorkHint);
 }
 
 // maxEvents: > 0 upper bound on nodes + changes of any tree, 0 unknown
@@ -1606,14 +1756,8 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long)
 template <int NW>
 int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
 {
-    int Ecap = MTT_MAX_TREE_EVENTS;
-    if (maxEvents > 0) {
-        Ecap = 1024;
-        while (Ecap < maxEvents)
-            Ecap <<= 1;
-        if (Ecap > MTT_MAX_TREE_EVENTS)
-            Ecap = MTT_MAX_TREE_EVENTS;
-    }
+    const int Ecap = (maxEvents > 0 && maxEvents < MTT_MAX_TREE_EVENTS) ? (int)maxEvents
+                                                                       : MTT_MAX_TREE_EVENTS;
     // A stage of EMAX slots takes trees with nodes + changes + 2 <= EMAX.  With a bound that
     // fits a stage: ONE launch and no queue -- a tree beyond the promised bound is reported
     // as NaN (an error of the caller), never silently skipped.

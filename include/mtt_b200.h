@@ -269,7 +269,9 @@ int mtt_peel_logl_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent, const
  * handle's patterns, parts[1][B] = the rescaled sum, parts[2][B] = number of tiles that saw an
  * underflow; add the three over the shards (one all-reduce of 3 B doubles) and take
  * parts[2] > 0 ? parts[1] : parts[0].  With pInv = 0 both sums are the same number.
- * Device pointers, async on the ctx stream. */
+ * The _dev entry takes device pointers and is asynchronous on the ctx stream. */
+int mtt_peel_logl_parts_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                              double *parts);
 int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
                                   const double *height, double *parts);
 /* per-pattern log-likelihoods of ONE tree (TreeLikelihood.getPatternLogLikelihoods) */

@@ -62,6 +62,7 @@ ABI = {
     "mtt_peel_logl_batch_params": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
     "mtt_peel_logl_batch_mats": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
+    "mtt_peel_logl_parts_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_parts_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_pattern_logl": (C.c_int, [VP, VP, VP, VP]),
 }

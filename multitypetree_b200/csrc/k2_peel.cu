@@ -1114,7 +1114,8 @@ int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
 
 static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
                      const double *mats, double *logL, double *patternLogL,
-                     const double *kappaPerTree = nullptr, const double *ratePerTree = nullptr)
+                     const double *kappaPerTree = nullptr, const double *ratePerTree = nullptr,
+                     double *partsHost = nullptr)
 {
     mtt_ctx *ctx = h->ctx;
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1122,8 +1123,10 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
     const int N = 2 * h->nTips - 1, C = h->nCat;
     const long long chunk = chunk_trees(h);
     int rc;
-    if ((rc = grow(ctx, h->dLogL, h->logLCap, (size_t)std::max<int64_t>(B, 1) * 8)) != MTT_OK)
+    // dLogL: logL[B], followed by parts[3][B] when the caller wants the two sums separately
+    if ((rc = grow(ctx, h->dLogL, h->logLCap, (size_t)std::max<int64_t>(B, 1) * 8 * 4)) != MTT_OK)
         return rc;
+    double *dParts = partsHost ? h->dLogL + B : nullptr;
     double *dPat = nullptr;
     if (patternLogL) {
         // reuse the weights-sized scratch behind dPart for the per-pattern output
@@ -1168,7 +1171,8 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
                                      cudaMemcpyHostToDevice));
             dTP = h->dTreeParams;
         }
-        rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat, dTP);
+        rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat, dTP,
+                        dParts ? dParts + b0 : nullptr, (long long)B);
         if (rc != MTT_OK)
             return rc;
         // the upload buffers are reused by the next chunk
@@ -1179,8 +1183,24 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
     if (patternLogL)
         MTT_CUDA(ctx, cudaMemcpyAsync(patternLogL, dPat, (size_t)h->nPatterns * 8,
                                       cudaMemcpyDeviceToHost, s));
+    if (partsHost)
+        MTT_CUDA(ctx, cudaMemcpyAsync(partsHost, dParts, (size_t)B * 24, cudaMemcpyDeviceToHost,
+                                      s));
     MTT_CUDA(ctx, cudaStreamSynchronize(s));
     return MTT_OK;
+}
+
+int mtt_peel_logl_parts_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                              double *parts)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    if (B < 0 || !parent || !height || !parts)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_parts_batch: bad arguments");
+    if (B == 0)
+        return MTT_OK;
+    return peel_host(h, B, parent, height, nullptr, nullptr, nullptr, nullptr, nullptr, parts);
 }
 
 int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,

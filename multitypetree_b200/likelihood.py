@@ -176,6 +176,19 @@ class TreeLikelihood:
                                                       _lib.ptr(out)))
         return out
 
+    def calculateLogPParts(self, parent: np.ndarray, height: np.ndarray) -> np.ndarray:
+        """parts[3][B] over this handle's patterns (a pattern shard): the sum of BEAST's unscaled
+        evaluation, the sum of its rescaled evaluation, and the number of tiles in which the
+        unscaled one underflowed (mtt_peel_logl_parts_batch).  Summed over the shards,
+        ``parts[2] > 0 ? parts[1] : parts[0]`` is the alignment's logL."""
+        par = _lib.as_c(parent, np.int32)
+        h = _lib.as_c(height, np.float64)
+        B = par.shape[0]
+        out = np.empty((3, B), np.float64)
+        self.ctx.check(_lib.lib().mtt_peel_logl_parts_batch(self._h, B, _lib.ptr(par),
+                                                            _lib.ptr(h), _lib.ptr(out)))
+        return out
+
     def calculateLogPBatchParams(self, parent: np.ndarray, height: np.ndarray, kappa,
                                  branchRate=None) -> np.ndarray:
         """One (kappa, clock rate) per tree: B parameter proposals or B chains in one call

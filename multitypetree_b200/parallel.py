@@ -82,3 +82,12 @@ def pattern_sharded_logl(compute_partial: Callable[[], np.ndarray], group=None) 
     """logL[B] over ALL patterns from this rank's partial sums over ITS pattern shard
     (a TreeLikelihood built on ``alignment.shard(rank, world)``): one all-reduce."""
     return allreduce_sum(np.asarray(compute_partial(), np.float64).copy(), group)
+
+
+def pattern_sharded_logl_parts(compute_parts: Callable[[], np.ndarray], group=None) -> np.ndarray:
+    """The same for alignments with a proportion of invariant sites: `compute_parts` returns this
+    rank's parts[3][B] of mtt_peel_logl_parts_batch_dev (unscaled sum, rescaled sum, number of
+    tiles that saw an underflow); BEAST's choice between the two evaluations is made after the
+    all-reduce, over ALL patterns."""
+    parts = allreduce_sum(np.asarray(compute_parts(), np.float64).copy(), group)
+    return np.where(parts[2] > 0, parts[1], parts[0])

@@ -268,6 +268,37 @@ def test_pattern_shards_sum_to_whole(ctx):
     whole.close()
 
 
+def test_pattern_shards_with_invariant_sites(ctx):
+    """pInv > 0 on a tree whose unscaled evaluation underflows for SOME patterns only: the
+    choice between BEAST's two evaluations is global, so the shards return both sums
+    (mtt_peel_logl_parts_batch) and the choice is made after adding them up."""
+    n, B = 1000, 2
+    par, hgt, _ = _trees(B, n, seed=77)
+    f = np.array([.3, .2, .2, .3])
+    tips = simulate_alignment(par[0], hgt[0], 200, 2.0, f, 50.0, seed=2)
+    const = np.repeat(np.arange(4, dtype=np.int32)[None, :], n, axis=0)
+    al = Alignment(states=np.concatenate([const, tips, const], axis=1), compress=False)
+    sm = SiteModel(HKY(2.0, f), mutationRate=50.0, proportionInvariant=0.2)
+    want = _oracle(al, par, hgt, sm)
+    assert np.all(np.isfinite(want))
+    parts = np.zeros((3, B))
+    for r in range(4):
+        sh = TreeLikelihood(data=al.shard(r, 4), siteModel=sm, ctx=ctx)
+        parts += sh.calculateLogPParts(par, hgt)
+        sh.close()
+    assert np.all(parts[2] > 0)                     # some shard saw the underflow
+    got = np.where(parts[2] > 0, parts[1], parts[0])
+    np.testing.assert_allclose(got, want, rtol=RTOL)
+    whole = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    np.testing.assert_allclose(whole.calculateLogPBatch(par, hgt), want, rtol=RTOL)
+    whole.close()
+    # a shard of constant patterns alone would have picked the other evaluation
+    first = TreeLikelihood(data=Alignment(states=const, compress=False), siteModel=sm, ctx=ctx)
+    p0 = first.calculateLogPParts(par, hgt)
+    assert np.all(p0[2] == 0) and np.all(np.abs(p0[0] - p0[1]) > 1.0)
+    first.close()
+
+
 def test_malformed_tree_is_reported_not_silently_wrong(ctx):
     n = 10
     par, hgt, _ = _trees(2, n, seed=3)

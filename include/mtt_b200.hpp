@@ -4,7 +4,10 @@
 // names, call order and error behaviour as
 //   evolution/tree/TypeSet.java, evolution/tree/SCMigrationModel.java:38-66, 93-144, 252-375,
 //   evolution/tree/MultiTypeTreeFromNewick.java:30-43 + MultiTypeTree.java:538-665,
-//   distributions/StructuredCoalescentTreeDensity.java:43-147.
+//   distributions/StructuredCoalescentTreeDensity.java:43-147,
+//   operators/UniformizationRetypeOperator.java:74-275 + operators/NodeRetype.java:31-63,
+//   and BEAST 2's Alignment / HKY / SiteModel / TreeLikelihood [EXT] as the reference wires them
+//   (examples/structuredCoalescent.xml:532-572).
 // The Java shims in java/b200mtt/ do exactly what these classes do (flatten, call, unflatten).
 // No arithmetic of the hot path lives here; it all runs behind the C-ABI on the GPU.
 #pragma once
@@ -12,12 +15,25 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <limits>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <vector>
 
 #include "mtt_b200.h"
+
+// host-side Randomizer stream that lives in the same shared object (csrc/host/randomizer.cpp)
+extern "C" {
+void *mtt_rng_new(int64_t seed);
+void mtt_rng_free(void *h);
+int mtt_rng_set_seed(void *h, int64_t seed);
+double mtt_rng_next_double(void *h);
+int32_t mtt_rng_next_int(void *h, int32_t n);
+void mtt_rng_peek_doubles(const void *h, int64_t n, double *out);
+void mtt_rng_skip_doubles(void *h, int64_t n);
+}
 
 namespace mtt {
 
@@ -170,6 +186,22 @@ public:
 
     int getNodeCount() const { return (int)height.size(); }
     int getLeafNodeCount() const { return (getNodeCount() + 1) / 2; }
+    int getInternalNodeCount() const { return getNodeCount() - getLeafNodeCount(); }
+    bool isRoot(int node) const { return parent[node] < 0; }
+    // children in BEAST's left / right order: the order of appearance in parent[] (for a tree
+    // read from Newick: the order of the Newick string)
+    int getLeft(int node) const { return children(node).first; }
+    int getRight(int node) const { return children(node).second; }
+    void clearChanges(int node)
+    {
+        changeTimes[node].clear();
+        changeTypes[node].clear();
+    }
+    void addChange(int node, int newType, double time)
+    {
+        changeTimes[node].push_back(time);
+        changeTypes[node].push_back((uint8_t)newType);
+    }
     int getChangeCount(int node) const { return (int)changeTimes[node].size(); }
     int getFinalType(int node) const
     {
@@ -223,6 +255,19 @@ public:
     }
 
 private:
+    std::pair<int, int> children(int node) const
+    {
+        if (kids_.size() != height.size()) {
+            kids_.assign(height.size(), {-1, -1});
+            for (int v = 0; v < (int)parent.size(); v++)
+                if (parent[v] >= 0) {
+                    auto &k = kids_[parent[v]];
+                    (k.first < 0 ? k.first : k.second) = v;
+                }
+        }
+        return kids_[node];
+    }
+    mutable std::vector<std::pair<int, int>> kids_;
     struct Flat {
         std::vector<int> children;
         int type = -1;
@@ -383,6 +428,375 @@ private:
     const MultiTypeTree &tree_;
     bool check_;
     const Context &ctx_;
+};
+
+
+// ------------------------------------------------------------------------------------------
+// BEAST Randomizer stream (MersenneTwisterFast [EXT]) -- the generator of csrc/host/randomizer.cpp
+class Randomizer {
+public:
+    explicit Randomizer(int64_t seed = 127) : h_(mtt_rng_new(seed))
+    {
+        if (!h_)
+            throw std::invalid_argument("Non zero random seed required");
+    }
+    ~Randomizer() { mtt_rng_free(h_); }
+    Randomizer(const Randomizer &) = delete;
+    Randomizer &operator=(const Randomizer &) = delete;
+    double nextDouble() { return mtt_rng_next_double(h_); }
+    int nextInt(int n) { return mtt_rng_next_int(h_, n); }
+    void peekDoubles(int64_t n, double *out) const { mtt_rng_peek_doubles(h_, n, out); }
+    void skipDoubles(int64_t n) { mtt_rng_skip_doubles(h_, n); }
+    // Poisson draw of the steady-state tail (UniformizationRetypeOperator.java:100-102);
+    // distributionally exact, not stream-compatible with a JVM ([EXT], see uniformization.py)
+    int nextPoisson(double lam)
+    {
+        if (lam < 40) {
+            const double p = std::exp(-lam);
+            double r = 1.0;
+            for (int n = 0;; n++) {
+                r *= nextDouble();
+                if (r < p)
+                    return n;
+            }
+        }
+        const double u = nextDouble();
+        int n = 0;
+        double logp = -lam, cdf = std::exp(logp);
+        while (cdf < u && n < 10 * lam + 100) {
+            n++;
+            logp += std::log(lam) - std::log((double)n);
+            cdf += std::exp(logp);
+        }
+        return n;
+    }
+
+private:
+    void *h_;
+};
+
+// ------------------------------------------------------------------------------------------
+// piece 2: BEAST 2 Alignment / HKY / SiteModel / TreeLikelihood [EXT] over mtt_peel_*
+inline int nucleotideState(char ch)
+{
+    switch (ch) {
+    case 'A': case 'a': return 0;
+    case 'C': case 'c': return 1;
+    case 'G': case 'g': return 2;
+    case 'T': case 't': case 'U': case 'u': return 3;
+    default: return 4;                       // gap / ambiguity code: missing data
+    }
+}
+
+// Alignment.calcPatterns: distinct columns (sorted) with integer weights
+class Alignment {
+public:
+    Alignment(const std::vector<std::string> &taxa, const std::vector<std::string> &sequences)
+        : taxa_(taxa)
+    {
+        const size_t nT = sequences.size(), nS = nT ? sequences[0].size() : 0;
+        std::map<std::vector<int32_t>, int32_t> cols;
+        for (size_t s = 0; s < nS; s++) {
+            std::vector<int32_t> col(nT);
+            for (size_t t = 0; t < nT; t++)
+                col[t] = nucleotideState(sequences[t][s]);
+            cols[col]++;
+        }
+        const size_t P = cols.size();
+        patterns.assign(nT * P, 0);
+        size_t p = 0;
+        for (auto &kv : cols) {
+            for (size_t t = 0; t < nT; t++)
+                patterns[t * P + p] = kv.first[t];
+            patternWeight.push_back(kv.second);
+            p++;
+        }
+        siteCount_ = (int)nS;
+    }
+    int getTaxonCount() const { return (int)taxa_.size(); }
+    int getPatternCount() const { return (int)patternWeight.size(); }
+    int getSiteCount() const { return siteCount_; }
+    std::vector<int32_t> patterns;           // [taxon][pattern]
+    std::vector<int32_t> patternWeight;
+
+private:
+    std::vector<std::string> taxa_;
+    int siteCount_ = 0;
+};
+
+struct HKY {                                 // Inputs kappa, frequencies
+    double kappa = 2.0;
+    double frequencies[4] = {0.25, 0.25, 0.25, 0.25};
+};
+
+// SiteModel: Inputs substModel, mutationRate, proportionInvariant (one rate category here; the
+// discrete-gamma quantiles live in the Python mirror, likelihood.py)
+struct SiteModel {
+    HKY substModel;
+    double mutationRate = 1.0;
+    double proportionInvariant = 0.0;
+};
+
+class TreeLikelihood {                       // Inputs data, tree, siteModel, branchRateModel
+public:
+    TreeLikelihood(const Alignment &data, const SiteModel &siteModel, double clockRate,
+                   const Context &ctx)
+        : data_(data), site_(siteModel), ctx_(ctx)
+    {
+        ctx_.check(mtt_peel_create(ctx_.get(), data.getTaxonCount(), data.getPatternCount(), 1, &h_));
+        ctx_.check(mtt_peel_set_tip_states(h_, data.patterns.data()));
+        ctx_.check(mtt_peel_set_pattern_weights(h_, data.patternWeight.data()));
+        const double pVar = 1.0 - site_.proportionInvariant;
+        const double rate = site_.mutationRate / pVar, prop = pVar;
+        ctx_.check(mtt_peel_set_site_model(h_, &rate, &prop, site_.substModel.frequencies,
+                                           site_.proportionInvariant, clockRate));
+        ctx_.check(mtt_peel_set_hky(h_, site_.substModel.kappa));
+    }
+    ~TreeLikelihood() { mtt_peel_destroy(h_); }
+    TreeLikelihood(const TreeLikelihood &) = delete;
+    TreeLikelihood &operator=(const TreeLikelihood &) = delete;
+    double calculateLogP(const MultiTypeTree &tree)
+    {
+        if (tree.getLeafNodeCount() != data_.getTaxonCount())
+            throw std::invalid_argument("The number of nodes in the tree does not match the "
+                                        "number of sequences");
+        ctx_.check(mtt_peel_logl_batch(h_, 1, tree.parent.data(), tree.height.data(), &logP));
+        return logP;
+    }
+    double logP = NAN;
+
+private:
+    const Alignment &data_;
+    SiteModel site_;
+    const Context &ctx_;
+    mtt_peel *h_ = nullptr;
+};
+
+// ------------------------------------------------------------------------------------------
+// piece 3: operators/UniformizationRetypeOperator.java + operators/NodeRetype.java.
+// One NodeRetype per chain (its own tree and Randomizer); `NodeRetypeEnsemble::proposal()`
+// advances all chains by one proposal in lock step -- ONE mtt_unif_branch_logp_batch and ONE
+// mtt_unif_retype_batch per step for the whole ensemble (config 5: 64 chains), the jobs that
+// need host action (longer uniform window, Poisson tail) being resubmitted.
+class NodeRetypeEnsemble {
+public:
+    struct Chain {
+        MultiTypeTree *tree;
+        Randomizer *rng;
+        int model;                           // row of the model set installed on the ctx
+    };
+    // m: nModels dense d x d backward-rate matrices; useSymmetrizedRates as in the reference
+    NodeRetypeEnsemble(const Context &ctx, int nModels, int d, const std::vector<double> &m,
+                       bool useSymmetrizedRates = false, int uniformWindow = 256)
+        : ctx_(ctx), d_(d), window_(uniformWindow)
+    {
+        ctx_.check(mtt_unif_set_models(ctx_.get(), nModels, d, m.data(), useSymmetrizedRates));
+        mu_.resize(nModels);
+        std::vector<double> Q(d * d), R(d * d);
+        for (int k = 0; k < nModels; k++)
+            ctx_.check(mtt_unif_get_matrices(ctx_.get(), k, Q.data(), R.data(), &mu_[k]));
+    }
+    void add(MultiTypeTree &tree, Randomizer &rng, int model = 0)
+    {
+        chains_.push_back(Chain{&tree, &rng, model});
+    }
+    size_t size() const { return chains_.size(); }
+
+    // One NodeRetype.proposal() per chain; returns the log Hastings ratios
+    // (-infinity where the reference returns Double.NEGATIVE_INFINITY, NodeRetype.java:57-58).
+    std::vector<double> proposal()
+    {
+        const size_t C = chains_.size();
+        std::vector<double> logHR(C, 0.0);
+        std::vector<int> node(C);
+        std::vector<std::vector<int>> br(C);
+        // ---- node choice (:36-37) and probability of the current typing (:40-44)
+        B_.clear();
+        std::vector<int64_t> off{0};
+        std::vector<double> ct;
+        std::vector<uint8_t> cty;
+        for (size_t c = 0; c < C; c++) {
+            MultiTypeTree &t = *chains_[c].tree;
+            node[c] = t.getLeafNodeCount() + chains_[c].rng->nextInt(t.getInternalNodeCount());
+            if (!t.isRoot(node[c]))
+                br[c].push_back(node[c]);
+            br[c].push_back(t.getLeft(node[c]));
+            br[c].push_back(t.getRight(node[c]));
+            for (int nd : br[c]) {
+                pushBranch(t, nd, chains_[c].model);
+                ct.insert(ct.end(), t.changeTimes[nd].begin(), t.changeTimes[nd].end());
+                cty.insert(cty.end(), t.changeTypes[nd].begin(), t.changeTypes[nd].end());
+                off.push_back((int64_t)ct.size());
+            }
+        }
+        std::vector<double> lp(B_.t0.size());
+        std::vector<int32_t> st(B_.t0.size());
+        ct.push_back(0.0);
+        cty.push_back(0);
+        ctx_.check(mtt_unif_branch_logp_batch(ctx_.get(), (int64_t)lp.size(), B_.mdl.data(),
+                                              B_.t0.data(), B_.t1.data(), B_.a.data(), B_.b.data(),
+                                              off.data(), ct.data(), cty.data(), lp.data(),
+                                              st.data()));
+        size_t k = 0;
+        for (size_t c = 0; c < C; c++)
+            for (size_t i = 0; i < br[c].size(); i++)
+                logHR[c] += lp[k++];
+        // ---- new node type (:47-48), then the branches node -> left -> right (:52-56)
+        for (size_t c = 0; c < C; c++)
+            chains_[c].tree->nodeType[node[c]] = (uint8_t)chains_[c].rng->nextInt(d_);
+        struct Job {
+            size_t chain;
+            size_t start = 0;
+            int window;
+            std::vector<int32_t> forced;
+            bool failed = false;
+        };
+        std::vector<Job> pending;
+        for (size_t c = 0; c < C; c++) {
+            Job j;
+            j.chain = c;
+            j.window = window_;
+            j.forced.assign(br[c].size(), -1);
+            pending.push_back(j);
+        }
+        std::vector<char> noPath(C, 0);
+        while (!pending.empty()) {
+            B_.clear();
+            std::vector<int64_t> brOff{0}, uOff{0};
+            std::vector<int32_t> forced;
+            std::vector<double> us;
+            int outCap = 0;
+            for (Job &j : pending) {
+                MultiTypeTree &t = *chains_[j.chain].tree;
+                for (size_t i = j.start; i < br[j.chain].size(); i++) {
+                    pushBranch(t, br[j.chain][i], chains_[j.chain].model);
+                    forced.push_back(j.forced[i]);
+                }
+                brOff.push_back((int64_t)B_.t0.size());
+                us.resize(us.size() + j.window);
+                chains_[j.chain].rng->peekDoubles(j.window, us.data() + us.size() - j.window);
+                uOff.push_back((int64_t)us.size());
+                outCap = std::max(outCap, j.window);
+            }
+            const size_t nBr = B_.t0.size();
+            std::vector<int32_t> nChg(nBr), status(nBr), nVirt(nBr);
+            std::vector<double> oct(nBr * outCap), olp(nBr);
+            std::vector<uint8_t> octy(nBr * outCap);
+            std::vector<int64_t> used(pending.size());
+            ctx_.check(mtt_unif_retype_batch(ctx_.get(), (int64_t)pending.size(), brOff.data(),
+                                             B_.mdl.data(), B_.t0.data(), B_.t1.data(), B_.a.data(),
+                                             B_.b.data(), forced.data(), us.data(), uOff.data(),
+                                             outCap, nChg.data(), oct.data(), octy.data(),
+                                             olp.data(), status.data(), nVirt.data(), used.data()));
+            std::vector<Job> next;
+            for (size_t ji = 0; ji < pending.size(); ji++) {
+                Job &j = pending[ji];
+                const size_t lo = (size_t)brOff[ji], hi = (size_t)brOff[ji + 1];
+                bool more = false;
+                for (size_t x = lo; x < hi; x++)
+                    more |= status[x] == MTT_ST_NEED_MORE_UNIFORMS;
+                if (more) {                              // nothing consumed: a longer window
+                    j.window *= 4;
+                    next.push_back(j);
+                    continue;
+                }
+                MultiTypeTree &t = *chains_[j.chain].tree;
+                size_t kOk = hi - lo;
+                for (size_t x = lo; x < hi; x++)
+                    if (status[x] != MTT_ST_OK) {
+                        kOk = x - lo;
+                        break;
+                    }
+                for (size_t i = 0; i < kOk; i++) {       // branches retyped successfully
+                    const int nd = br[j.chain][j.start + i];
+                    t.clearChanges(nd);
+                    for (int q = 0; q < nChg[lo + i]; q++)
+                        t.addChange(nd, octy[(lo + i) * outCap + q], oct[(lo + i) * outCap + q]);
+                    logHR[j.chain] -= olp[lo + i];
+                }
+                chains_[j.chain].rng->skipDoubles(used[ji]);
+                if (kOk == hi - lo)
+                    continue;                            // job done
+                const int why = status[lo + kOk];
+                if (why == MTT_ST_NO_VALID_PATH) {       // NoValidPathException (:137-140)
+                    noPath[j.chain] = 1;
+                    continue;
+                }
+                if (why == MTT_ST_NEEDS_POISSON_TAIL) {  // (:96-102)
+                    const int thresh = nVirt[lo + kOk];
+                    const double muL = mu_[chains_[j.chain].model] *
+                                       (B_.t1[lo + kOk] - B_.t0[lo + kOk]);
+                    int nv;
+                    do
+                        nv = chains_[j.chain].rng->nextPoisson(muL);
+                    while (nv < thresh);
+                    j.forced[j.start + kOk] = nv;
+                    j.start += kOk;
+                    next.push_back(j);
+                    continue;
+                }
+                // Pba rubbish / forward-backward fell through: retypeBranch returned -Infinity
+                // and the proposal carries on with the remaining branches (:141-144, :179-190)
+                logHR[j.chain] = -std::numeric_limits<double>::infinity();
+                j.failed = true;
+                j.start += kOk + 1;
+                if (j.start < br[j.chain].size())
+                    next.push_back(j);
+            }
+            pending.swap(next);
+        }
+        for (size_t c = 0; c < C; c++)
+            if (noPath[c])
+                logHR[c] = -std::numeric_limits<double>::infinity();
+        return logHR;
+    }
+
+private:
+    struct Branches {
+        std::vector<double> t0, t1;
+        std::vector<uint8_t> a, b;
+        std::vector<int32_t> mdl;
+        void clear()
+        {
+            t0.clear();
+            t1.clear();
+            a.clear();
+            b.clear();
+            mdl.clear();
+        }
+    } B_;
+    void pushBranch(const MultiTypeTree &t, int nd, int model)
+    {
+        const int p = t.parent[nd];
+        B_.t0.push_back(t.height[nd]);
+        B_.t1.push_back(t.height[p]);
+        B_.a.push_back(t.nodeType[nd]);
+        B_.b.push_back(t.nodeType[p]);
+        B_.mdl.push_back(model);
+    }
+    const Context &ctx_;
+    int d_, window_;
+    std::vector<double> mu_;
+    std::vector<Chain> chains_;
+};
+
+// operators/NodeRetype.java as a single-chain operator: Inputs multiTypeTree, migrationModel,
+// useSymmetrizedRates
+class NodeRetype {
+public:
+    NodeRetype(MultiTypeTree &multiTypeTree, const SCMigrationModel &migrationModel,
+               Randomizer &randomizer, const Context &ctx, bool useSymmetrizedRates = false)
+    {
+        std::vector<double> m, N;
+        migrationModel.dense(m, N);
+        ens_.reset(new NodeRetypeEnsemble(ctx, 1, migrationModel.getNTypes(), m,
+                                          useSymmetrizedRates));
+        ens_->add(multiTypeTree, randomizer, 0);
+    }
+    double proposal() { return ens_->proposal()[0]; }
+
+private:
+    std::unique_ptr<NodeRetypeEnsemble> ens_;
 };
 
 }  // namespace mtt

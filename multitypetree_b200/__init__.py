@@ -6,7 +6,8 @@ tests, the benchmark and as a model for the Java shims in ``java/``.
 """
 from ._lib import Context, MttError, default_context, lib  # noqa: F401
 from .tree import (MultiTypeTree, MultiTypeTreeFromNewick, TreeBatch,  # noqa: F401
-                   read_nexus_tree, simulate_trees, synthetic_model)
+                   read_nexus_tree, read_nexus_trees, simulate_trees,
+                   synthetic_model)
 from .migration_model import SCMigrationModel, TypeSet  # noqa: F401
 from .density import StructuredCoalescentTreeDensity, sc_logp_batch, tree_validity  # noqa: F401
 from .uniformization import Randomizer, UniformizationModels  # noqa: F401
@@ -17,7 +18,7 @@ from .mcmc import MCMC, Chain, MCMCEnsemble  # noqa: F401
 
 __all__ = [
     "Context", "MttError", "default_context", "lib", "MultiTypeTree",
-    "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "simulate_trees",
+    "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "read_nexus_trees", "simulate_trees",
     "synthetic_model", "SCMigrationModel", "TypeSet", "StructuredCoalescentTreeDensity",
     "sc_logp_batch", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",
     "NodeShiftRetype", "TypedSubtreeExchange", "TypedWilsonBalding", "MultiTypeTreeScale",

@@ -192,6 +192,35 @@ class MultiTypeTree:
             pieces[v] = "%s:%r" % (s, float(self.height[int(self.parent[v])]) - t_prev)
         return pieces[root]
 
+    # ---- Loggable (MultiTypeTree.java:795-831): the NEXUS tree log BEAST writes and resumes from
+    def _taxon(self, i: int) -> str:
+        return self.taxa[i] if self.taxa and i < len(self.taxa) and self.taxa[i] else str(i)
+
+    def init(self, stream, typeLabel: str = "type") -> None:
+        """Header of the tree log: taxa block and the Translate table (leaf Nr + 1 -> taxon)."""
+        n = self.getLeafNodeCount()
+        stream.write("#NEXUS\n\nBegin taxa;\n\tDimensions ntax=%d;\n\t\tTaxlabels\n" % n)
+        for i in range(n):
+            stream.write("\t\t\t%s\n" % self._taxon(i))
+        stream.write("\t\t\t;\nEnd;\nBegin trees;\n\tTranslate\n")
+        for i in range(n):
+            stream.write("\t\t\t%d %s%s\n" % (i + 1, self._taxon(i), "," if i < n - 1 else ""))
+        stream.write("\t\t\t;")
+        self._logLabel = typeLabel
+
+    def log(self, sample: int, stream) -> None:
+        """One ``tree STATE_i = <flat Newick with translated leaf numbers>;`` statement."""
+        saved = self.taxa
+        self.taxa = [str(i + 1) for i in range(self.getLeafNodeCount())]
+        try:
+            nw = self.getFlattenedNewick(getattr(self, "_logLabel", "type"))
+        finally:
+            self.taxa = saved
+        stream.write("\ntree STATE_%d = %s" % (sample, nw))
+
+    def close(self, stream) -> None:
+        stream.write("\nEnd;\n")
+
     def isValid(self, ctx=None) -> bool:
         """MultiTypeTree.isValid (MultiTypeTree.java:396-429), evaluated on the device."""
         from .density import tree_validity
@@ -459,11 +488,17 @@ def MultiTypeTreeFromNewick(value: str, typeLabel: str = "type", typeSet=None) -
 
 def read_nexus_tree(path: str) -> str:
     """First ``tree NAME = ...;`` Newick string of a NEXUS file."""
+    return read_nexus_trees(path)[0]
+
+
+def read_nexus_trees(path: str) -> List[str]:
+    """Every ``tree NAME = ...;`` Newick string of a NEXUS tree log, in file order."""
     txt = open(path).read()
-    m = re.search(r"tree\s+\S+\s*=\s*(?:\[&R\]\s*)?(.*?;)", txt, re.S | re.I)
-    if not m:
+    out = [m.group(1).strip() for m in
+           re.finditer(r"tree\s+\S+\s*=\s*(?:\[&R\]\s*)?(.*?;)", txt, re.S | re.I)]
+    if not out:
         raise ValueError("no tree statement in %s" % path)
-    return m.group(1).strip()
+    return out
 
 
 # ---------------------------------------------------------------------------- simulation

@@ -85,3 +85,26 @@ def test_owner_list_layouts_agree():
     assert np.array_equal(part.chgNode, derived[int(tb.chgBase[50]):int(tb.chgBase[120])])
     rebuilt = mtt.TreeBatch.from_trees([tb.tree(b) for b in range(5)])
     assert np.array_equal(rebuilt.chgNode, derived[:int(tb.chgBase[5])])
+
+
+def test_nexus_tree_log_round_trip(tmp_path):
+    """Loggable init / log / close (MultiTypeTree.java:795-831): the NEXUS tree log BEAST writes
+    can be read back tree by tree (translated leaf numbers are Nr + 1)."""
+    m, N = mtt.synthetic_model(2)
+    tb = mtt.simulate_trees(3, 12, 2, m, N, seed=9, nThreads=1)
+    trees = [tb.tree(i) for i in range(3)]
+    path = tmp_path / "run.trees"
+    with open(path, "w") as f:
+        trees[0].init(f, "location")
+        for i, t in enumerate(trees):
+            t._logLabel = "location"
+            t.log(1000 * i, f)
+        trees[0].close(f)
+    txt = open(path).read()
+    assert txt.startswith("#NEXUS") and "Dimensions ntax=12;" in txt and "tree STATE_2000 = " in txt
+    back = mtt.read_nexus_trees(str(path))
+    assert len(back) == 3
+    for nw, t in zip(back, trees):
+        t2 = mtt.MultiTypeTreeFromNewick(nw, "location")
+        assert _same_tree(t, t2)
+        assert sorted(t2.taxa) == sorted(str(i + 1) for i in range(12))

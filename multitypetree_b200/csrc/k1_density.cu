@@ -1304,7 +1304,7 @@ struct CtaQuant {
 
 template <int NW, int THREADS>
 __global__ void __launch_bounds__(THREADS)
-k1_density_cta(const K1Params p, int Scap, int tmInSmem, int useQueue)
+k1_density_cta(const K1Params p, int Scap, int tmInSmem, int useQueue, int minS, int nanBeyond)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     ModelTab *tab = reinterpret_cast<ModelTab *>(smem_raw);
@@ -1342,6 +1342,8 @@ k1_density_cta(const K1Params p, int Scap, int tmInSmem, int useQueue)
         const int S = (E + RUN - 1) / RUN * RUN;
 
         __syncthreads();                            // the previous tree is done with smem
+        if ((minS > 0 && S <= minS) || (S > Scap && !nanBeyond))
+            continue;               // another launch of this call takes this size class
         if (S > Scap || E == 0) {   // beyond the capacity: NaN (host maps it to an error)
             if (tid == 0) {
                 p.logP[t] = (E == 0) ? 0.0 : NAN;
@@ -1712,7 +1714,8 @@ int launch_warp_any(mtt_ctx *ctx, const K1Params &p)
 }
 
 template <int NW, int THREADS>
-int launch_cta_t(mtt_ctx *ctx, const K1Params &p, int Scap, int useQueue, long long nWorkHint)
+int launch_cta_t(mtt_ctx *ctx, const K1Params &p, int Scap, int useQueue, long long nWorkHint,
+                 int minS, int nanBeyond)
 {
     // 10 bytes per slot for the keys and descriptors, 8 more when the times are staged too
     const size_t fixed = sizeof(ModelTab) + 16;
@@ -1728,19 +1731,29 @@ int launch_cta_t(mtt_ctx *ctx, const K1Params &p, int Scap, int useQueue, long l
     long long grid = (long long)ctx->numSMs * perSM;
     if (nWorkHint > 0 && nWorkHint < grid)
         grid = nWorkHint;
-    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(p, Scap, tmInSmem, useQueue);
+    kern<<<(unsigned)grid, THREADS, smem, ctx->stream>>>(p, Scap, tmInSmem, useQueue, minS, nanBeyond);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
 }
 
-// Ecap: upper bound on the events of any tree the kernel will see
+// Ecap: upper bound on the events of any tree the kernel will see.  Without one
+// (Ecap = MTT_MAX_TREE_EVENTS) the queue is served by three launches, one per size class, so
+// that mid-size trees do not pay for the shared memory of the largest possible one.
 template <int NW>
 int launch_block(mtt_ctx *ctx, const K1Params &p, int Ecap, int useQueue, long long nWorkHint)
 {
     // 256 threads up to 4096 slots (several CTAs per SM), 512 beyond (one or two CTAs per SM)
-    if (Ecap <= 4096)
-        return launch_cta_t<NW, 256>(ctx, p, (Ecap + 255) / 256 * 256, useQueue, nWorkHint);
-    return launch_cta_t<NW, 512>(ctx, p, (Ecap + 511) / 512 * 512, useQueue, nWorkHint);
+    if (Ecap < MTT_MAX_TREE_EVENTS) {
+        if (Ecap <= 4096)
+            return launch_cta_t<NW, 256>(ctx, p, (Ecap + 255) / 256 * 256, useQueue, nWorkHint, 0, 1);
+        return launch_cta_t<NW, 512>(ctx, p, (Ecap + 511) / 512 * 512, useQueue, nWorkHint, 0, 1);
+    }
+    int rc = launch_cta_t<NW, 256>(ctx, p, 2304, useQueue, nWorkHint, 0, 0);
+    if (rc == MTT_OK)
+        rc = launch_cta_t<NW, 256>(ctx, p, 4096, useQueue, nWorkHint, 2304, 0);
+    if (rc == MTT_OK)
+        rc = launch_cta_t<NW, 512>(ctx, p, MTT_MAX_TREE_EVENTS, useQueue, nWorkHint, 4096, 1);
+    return rc;
 }
 
 // maxEvents: > 0 upper bound on nodes + changes of any tree, 0 unknown

@@ -278,6 +278,33 @@ int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
 int mtt_peel_pattern_logl(mtt_peel *h, const int32_t *parent, const double *height,
                           double *patternLogL);
 
+/* ------------------------------------------------------------------ next row: tree simulation
+ * Replaces evolution/tree/StructuredCoalescentMultiTypeTree.java:191-442 (simulateTree,
+ * updatePropensities, getNextEvent, updateTree): B structured-coalescent multi-type trees
+ * simulated on the device (one thread per tree), written as the flattened tree SoA above in
+ * the owner layout -- synthetic inputs for the density / peeling entries without a trip through
+ * the host, and the ground truth of the reference's operator tests
+ * (util/UtilMethods.java:29-47, 10^5 replicates).  m, N, leafTypes[nLeaves],
+ * leafTimes[nLeaves] are host arrays; tree b uses the stream seeded with seed + b.  The event
+ * loop and the draw order are those of the host generator (mtt_sim_run): same seed, same tree
+ * (times equal to rounding).  Nodes: leaves 0..nLeaves-1 as given, internal nodes in order of
+ * creation (= increasing height), root last. */
+typedef struct mtt_sim mtt_sim;
+int mtt_sim_trees_create(mtt_ctx *ctx, int64_t B, int nLeaves, int d, const double *m,
+                         const double *N, const uint8_t *leafTypes, const double *leafTimes,
+                         uint64_t seed, mtt_sim **out);
+int mtt_sim_trees_destroy(mtt_sim *h);
+int64_t mtt_sim_trees_total_changes(const mtt_sim *h);
+/* device pointers of the simulated batch (owned by the handle); any argument may be NULL */
+int mtt_sim_trees_device(const mtt_sim *h, const int64_t **nodeOff, const double **height,
+                         const int32_t **parent, const uint8_t **nodeType,
+                         const uint16_t **chgNode, const int64_t **chgBase,
+                         const double **chgTime, const uint8_t **chgType);
+/* copy to host arrays sized B+1 / B*(2*nLeaves-1) / total_changes; any argument may be NULL */
+int mtt_sim_trees_export(const mtt_sim *h, int64_t *nodeOff, double *height, int32_t *parent,
+                         uint8_t *nodeType, uint16_t *chgNode, int64_t *chgBase, double *chgTime,
+                         uint8_t *chgType);
+
 #ifdef __cplusplus
 }
 #endif

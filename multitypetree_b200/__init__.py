@@ -5,7 +5,7 @@ this package is the thin host-side mirror of the reference's plugin interface us
 tests, the benchmark and as a model for the Java shims in ``java/``.
 """
 from ._lib import Context, MttError, default_context, lib  # noqa: F401
-from .tree import (MultiTypeTree, MultiTypeTreeFromNewick, TreeBatch,  # noqa: F401
+from .tree import (DeviceTreeBatch, MultiTypeTree, MultiTypeTreeFromNewick, TreeBatch,  # noqa: F401
                    read_nexus_tree, read_nexus_trees, simulate_trees,
                    synthetic_model)
 from .migration_model import SCMigrationModel, TypeSet  # noqa: F401
@@ -17,7 +17,7 @@ from .operators import (MultiTypeTreeScale, MultiTypeUniform, NodeRetype,  # noq
 from .mcmc import MCMC, Chain, MCMCEnsemble  # noqa: F401
 
 __all__ = [
-    "Context", "MttError", "default_context", "lib", "MultiTypeTree",
+    "Context", "MttError", "default_context", "lib", "DeviceTreeBatch", "MultiTypeTree",
     "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "read_nexus_trees", "simulate_trees",
     "synthetic_model", "SCMigrationModel", "TypeSet", "StructuredCoalescentTreeDensity",
     "sc_logp_batch", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",

@@ -65,6 +65,12 @@ ABI = {
     "mtt_peel_logl_parts_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_parts_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_pattern_logl": (C.c_int, [VP, VP, VP, VP]),
+    "mtt_sim_trees_create": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP,
+                                       C.c_uint64, C.POINTER(VP)]),
+    "mtt_sim_trees_destroy": (C.c_int, [VP]),
+    "mtt_sim_trees_total_changes": (C.c_int64, [VP]),
+    "mtt_sim_trees_device": (C.c_int, [VP] + [C.POINTER(VP)] * 8),
+    "mtt_sim_trees_export": (C.c_int, [VP] * 9),
 }
 
 # host-side helpers that live in the same shared object (not part of the drop-in boundary)

@@ -7,6 +7,7 @@ All arithmetic on these trees happens in the CUDA library; this module only move
 """
 from __future__ import annotations
 
+import ctypes as C
 import re
 from dataclasses import dataclass, field
 from typing import List, Optional, Sequence
@@ -536,6 +537,65 @@ def simulate_trees(B: int, nLeaves: int, d: int, m: np.ndarray, N: np.ndarray,
     finally:
         L.mtt_sim_free(h)
     return tb
+
+
+class DeviceTreeBatch:
+    """B trees simulated ON the device (mtt_sim_trees_create, csrc/k5_simulate.cu; SURVEY 8f
+    rank 4): the flattened tree SoA in the owner layout, resident in HBM.  ``pointers()`` gives
+    the device addresses for the ``*_dev`` entries, ``to_host()`` a TreeBatch."""
+
+    def __init__(self, B: int, nLeaves: int, d: int, m: np.ndarray, N: np.ndarray,
+                 leafTypes=None, leafTimes=None, seed: int = 1, ctx=None):
+        self.ctx = ctx or _lib.default_context()
+        self.B, self.nLeaves, self.d = int(B), int(nLeaves), int(d)
+        m = _lib.as_c(m, np.float64).reshape(d, d)
+        N = _lib.as_c(N, np.float64)
+        if leafTypes is None:
+            leafTypes = np.arange(nLeaves) % d
+        if leafTimes is None:
+            leafTimes = 0.5 * (np.arange(nLeaves) % 4)
+        lt = _lib.as_c(leafTypes, np.uint8)
+        ltm = _lib.as_c(leafTimes, np.float64)
+        self._h = _lib.VP()
+        self.ctx.check(_lib.lib().mtt_sim_trees_create(
+            self.ctx.handle, self.B, self.nLeaves, self.d, _lib.ptr(m), _lib.ptr(N), _lib.ptr(lt),
+            _lib.ptr(ltm), seed, C.byref(self._h)))
+        self.total_changes = int(_lib.lib().mtt_sim_trees_total_changes(self._h))
+
+    def pointers(self) -> dict:
+        names = ("nodeOff", "height", "parent", "nodeType", "chgNode", "chgBase", "chgTime",
+                 "chgType")
+        out = [_lib.VP() for _ in names]
+        self.ctx.check(_lib.lib().mtt_sim_trees_device(self._h, *[C.byref(x) for x in out]))
+        return {k: v.value for k, v in zip(names, out)}
+
+    def to_host(self) -> "TreeBatch":
+        B, nN, tot = self.B, 2 * self.nLeaves - 1, self.total_changes
+        tb = TreeBatch(np.zeros(B + 1, np.int64), np.zeros(B * nN, np.float64),
+                       np.zeros(B * nN, np.int32), np.zeros(B * nN, np.uint8),
+                       np.zeros(B * nN, np.uint16), np.zeros(B + 1, np.int64),
+                       np.zeros(tot, np.float64), np.zeros(tot, np.uint8))
+        owners = np.zeros(tot, np.uint16)
+        self.ctx.check(_lib.lib().mtt_sim_trees_export(
+            self._h, _lib.ptr(tb.nodeOff), _lib.ptr(tb.height), _lib.ptr(tb.parent),
+            _lib.ptr(tb.nodeType), _lib.ptr(owners), _lib.ptr(tb.chgBase), _lib.ptr(tb.chgTime),
+            _lib.ptr(tb.chgType)))
+        tb.set_owner_list(owners)
+        if tot:                          # per-node change counts from the owner list
+            tree = np.searchsorted(tb.chgBase, np.arange(tot), side="right") - 1
+            np.add.at(tb.chgCount, tree * nN + owners.astype(np.int64), 1)
+        return tb
+
+    def close(self):
+        if self._h:
+            _lib.lib().mtt_sim_trees_destroy(self._h)
+            self._h = _lib.VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def synthetic_model(d: int):

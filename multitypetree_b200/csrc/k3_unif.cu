@@ -525,38 +525,34 @@ int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t n, const int32_t *model,
     cudaStream_t s = ctx->stream;
     const int d = ctx->unifD;
     const int64_t nChg = chgOff[n];
-    int *dModel = (int *)mtt_buf(ctx, BUF_U_IN0, n * 4);
-    double *dT0 = (double *)mtt_buf(ctx, BUF_U_IN1, n * 8);
-    double *dT1 = (double *)mtt_buf(ctx, BUF_U_IN2, n * 8);
-    uint8_t *dA = (uint8_t *)mtt_buf(ctx, BUF_U_IN3, n);
-    uint8_t *dB = (uint8_t *)mtt_buf(ctx, BUF_U_IN4, n);
-    long long *dOff = (long long *)mtt_buf(ctx, BUF_U_IN5, (n + 1) * 8);
-    double *dCT = (double *)mtt_buf(ctx, BUF_U_IN6, nChg * 8);
-    uint8_t *dCTy = (uint8_t *)mtt_buf(ctx, BUF_U_IN7, nChg);
-    double *dLP = (double *)mtt_buf(ctx, BUF_U_OUT0, n * 8);
-    int *dSt = (int *)mtt_buf(ctx, BUF_U_OUT1, n * 4);
-    if (!dModel || !dT0 || !dT1 || !dA || !dB || !dOff || !dCT || !dCTy || !dLP || !dSt)
-        return MTT_ERR_CUDA;
-    MTT_CUDA(ctx, cudaMemcpyAsync(dModel, model, n * 4, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dT0, tBottom, n * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dT1, tTop, n * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dA, typeBottom, n, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dB, typeTop, n, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dOff, chgOff, (n + 1) * 8, cudaMemcpyHostToDevice, s));
-    if (nChg > 0) {
-        MTT_CUDA(ctx, cudaMemcpyAsync(dCT, chgTime, nChg * 8, cudaMemcpyHostToDevice, s));
-        MTT_CUDA(ctx, cudaMemcpyAsync(dCTy, chgType, nChg, cudaMemcpyHostToDevice, s));
-    }
+    int *dModel;
+    double *dT0, *dT1, *dCT, *dLP;
+    uint8_t *dA, *dB, *dCTy;
+    long long *dOff;
+    int *dSt;
+    Xfer x(ctx);
+    x.in(model, (size_t)n, BUF_U_IN0, &dModel);
+    x.in(tBottom, (size_t)n, BUF_U_IN1, &dT0);
+    x.in(tTop, (size_t)n, BUF_U_IN2, &dT1);
+    x.in(typeBottom, (size_t)n, BUF_U_IN3, &dA);
+    x.in(typeTop, (size_t)n, BUF_U_IN4, &dB);
+    x.in((const long long *)chgOff, (size_t)n + 1, BUF_U_IN5, &dOff);
+    x.in(chgTime, (size_t)nChg, BUF_U_IN6, &dCT);
+    x.in(chgType, (size_t)nChg, BUF_U_IN7, &dCTy);
+    x.out(logProb, (size_t)n, BUF_U_OUT0, &dLP);
+    x.out(status, (size_t)n, BUF_U_OUT1, &dSt);
+    int rc = x.prepare();
+    if (rc == MTT_OK)
+        rc = x.upload();
+    if (rc != MTT_OK)
+        return rc;
     MTT_CUDA(ctx, cudaFuncSetAttribute(k3_branch_logp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)expm_smem(d)));
     k3_branch_logp<<<(unsigned)((n + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
         n, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel, dT0, dT1, dA, dB, dOff, dCT, dCTy, dLP,
         dSt);
     MTT_CHECK_LAUNCH(ctx);
-    MTT_CUDA(ctx, cudaMemcpyAsync(logProb, dLP, n * 8, cudaMemcpyDeviceToHost, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(status, dSt, n * 4, cudaMemcpyDeviceToHost, s));
-    MTT_CUDA(ctx, cudaStreamSynchronize(s));
-    return MTT_OK;
+    return x.download();
 }
 
 int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
@@ -599,38 +595,38 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "mu*L = %g is too large", maxMuL);
     int K = (int)(maxMuL + 10.0 * sqrt(maxMuL) + 32.0);
 
-    int *dModel = (int *)mtt_buf(ctx, BUF_U_IN0, nBr * 4);
-    double *dT0 = (double *)mtt_buf(ctx, BUF_U_IN1, nBr * 8);
-    double *dT1 = (double *)mtt_buf(ctx, BUF_U_IN2, nBr * 8);
-    uint8_t *dA = (uint8_t *)mtt_buf(ctx, BUF_U_IN3, nBr);
-    uint8_t *dB = (uint8_t *)mtt_buf(ctx, BUF_U_IN4, nBr);
-    long long *dBrOff = (long long *)mtt_buf(ctx, BUF_U_IN5, (nJobs + 1) * 8);
-    double *dU = (double *)mtt_buf(ctx, BUF_U_IN6, nU * 8);
-    long long *dUOff = (long long *)mtt_buf(ctx, BUF_U_IN7, (nJobs + 1) * 8);
-    int *dForced = nVirtForced ? (int *)mtt_buf(ctx, BUF_U_IN8, nBr * 4) : nullptr;
-    int *dNChg = (int *)mtt_buf(ctx, BUF_U_OUT0, nBr * 4);
-    double *dOCT = (double *)mtt_buf(ctx, BUF_U_OUT1, (size_t)nBr * outCap * 8);
-    uint8_t *dOCTy = (uint8_t *)mtt_buf(ctx, BUF_U_OUT2, (size_t)nBr * outCap);
-    double *dLP = (double *)mtt_buf(ctx, BUF_U_OUT3, nBr * 8);
-    int *dSt = (int *)mtt_buf(ctx, BUF_U_OUT4, nBr * 4 * 2);     // status | nVirt
-    long long *dUsed = (long long *)mtt_buf(ctx, BUF_U_OUT5, nJobs * 8);
-    if (!dModel || !dT0 || !dT1 || !dA || !dB || !dBrOff || !dU || !dUOff || !dNChg || !dOCT ||
-        !dOCTy || !dLP || !dSt || !dUsed || (nVirtForced && !dForced))
-        return MTT_ERR_CUDA;
-    int *dNVirt = dSt + nBr;
-    MTT_CUDA(ctx, cudaMemcpyAsync(dModel, model, nBr * 4, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dT0, tBottom, nBr * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dT1, tTop, nBr * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dA, typeBottom, nBr, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dB, typeTop, nBr, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dBrOff, brOff, (nJobs + 1) * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dU, uniforms, nU * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dUOff, uOff, (nJobs + 1) * 8, cudaMemcpyHostToDevice, s));
+    int *dModel, *dForced = nullptr, *dNChg, *dSt, *dNVirt;
+    double *dT0, *dT1, *dU, *dOCT, *dLP;
+    uint8_t *dA, *dB, *dOCTy;
+    long long *dBrOff, *dUOff, *dUsed;
+    Xfer x(ctx);
+    x.in(model, (size_t)nBr, BUF_U_IN0, &dModel);
+    x.in(tBottom, (size_t)nBr, BUF_U_IN1, &dT0);
+    x.in(tTop, (size_t)nBr, BUF_U_IN2, &dT1);
+    x.in(typeBottom, (size_t)nBr, BUF_U_IN3, &dA);
+    x.in(typeTop, (size_t)nBr, BUF_U_IN4, &dB);
+    x.in((const long long *)brOff, (size_t)nJobs + 1, BUF_U_IN5, &dBrOff);
+    x.in(uniforms, (size_t)nU, BUF_U_IN6, &dU);
+    x.in((const long long *)uOff, (size_t)nJobs + 1, BUF_U_IN7, &dUOff);
     if (nVirtForced)
-        MTT_CUDA(ctx, cudaMemcpyAsync(dForced, nVirtForced, nBr * 4, cudaMemcpyHostToDevice, s));
+        x.in(nVirtForced, (size_t)nBr, BUF_U_IN8, &dForced);
+    x.out(nChg, (size_t)nBr, BUF_U_OUT0, &dNChg);
+    x.out(outChgTime, (size_t)nBr * outCap, BUF_U_OUT1, &dOCT);
+    x.out(outChgType, (size_t)nBr * outCap, BUF_U_OUT2, &dOCTy);
+    x.out(logProb, (size_t)nBr, BUF_U_OUT3, &dLP);
+    x.out(status, (size_t)nBr, BUF_U_OUT4, &dSt);
+    x.out(nVirt, (size_t)nBr, BUF_U_OUT7, &dNVirt);
+    x.out((long long *)uUsed, (size_t)nJobs, BUF_U_OUT5, &dUsed);
+    {
+        int rc = x.prepare();
+        if (rc == MTT_OK)
+            rc = x.upload();
+        if (rc != MTT_OK)
+            return rc;
+    }
 
     const unsigned blocks = (unsigned)((nJobs + U_WARPS - 1) / U_WARPS);
-    std::vector<int32_t> hSt(nBr);
+    std::vector<int32_t> hSt(x.staged() ? 0 : nBr);
     for (int attempt = 0; attempt < 12; attempt++) {
         int rc = ensure_powers(ctx, K);
         if (rc != MTT_OK)
@@ -667,11 +663,21 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         p.scratchT = scrT; p.scratchTy = scrTy; p.scratchCap = scratchCap; p.tCap = tCap;
         k3_retype<<<blocks, U_WARPS * 32, smem, s>>>(p);
         MTT_CHECK_LAUNCH(ctx);
-        MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dSt, nBr * 4, cudaMemcpyDeviceToHost, s));
-        MTT_CUDA(ctx, cudaStreamSynchronize(s));
+        // small calls: all outputs come back in one copy and the status is read from it; large
+        // calls fetch the status alone first
+        const int32_t *stHost = hSt.data();
+        if (x.staged()) {
+            rc = x.download();
+            if (rc != MTT_OK)
+                return rc;
+            stHost = status;
+        } else {
+            MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dSt, nBr * 4, cudaMemcpyDeviceToHost, s));
+            MTT_CUDA(ctx, cudaStreamSynchronize(s));
+        }
         bool more = false;
         for (int64_t i = 0; i < nBr; i++)
-            if (hSt[i] == MTT_ST_NEED_MORE_POWERS)
+            if (stHost[i] == MTT_ST_NEED_MORE_POWERS)
                 more = true;
         if (!more)
             break;
@@ -679,19 +685,9 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         if (attempt == 11)
             return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "R^k table would exceed %d powers", K);
     }
-    memcpy(status, hSt.data(), nBr * 4);
-    MTT_CUDA(ctx, cudaMemcpyAsync(nChg, dNChg, nBr * 4, cudaMemcpyDeviceToHost, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(nVirt, dNVirt, nBr * 4, cudaMemcpyDeviceToHost, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(logProb, dLP, nBr * 8, cudaMemcpyDeviceToHost, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(uUsed, dUsed, nJobs * 8, cudaMemcpyDeviceToHost, s));
-    if (outCap > 0) {
-        MTT_CUDA(ctx, cudaMemcpyAsync(outChgTime, dOCT, (size_t)nBr * outCap * 8,
-                                      cudaMemcpyDeviceToHost, s));
-        MTT_CUDA(ctx, cudaMemcpyAsync(outChgType, dOCTy, (size_t)nBr * outCap,
-                                      cudaMemcpyDeviceToHost, s));
-    }
-    MTT_CUDA(ctx, cudaStreamSynchronize(s));
-    return MTT_OK;
+    if (x.staged())
+        return MTT_OK;                 // everything arrived with the last download
+    return x.download();
 }
 
 }  // extern "C"

@@ -33,6 +33,9 @@ struct mtt_ctx {
     std::vector<int> unifPowSize;       // powers valid per model
     std::vector<int> unifSteady;        // steady flag per model
     std::vector<double> unifMu;         // host copy of mu per model
+    // pinned staging of small calls (Xfer below)
+    void *pinIn = nullptr, *pinOut = nullptr;
+    size_t pinInCap = 0, pinOutCap = 0;
 };
 
 enum BufId {
@@ -41,10 +44,11 @@ enum BufId {
     BUF_D_QUEUE, BUF_D_CHGNODE,
     BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
-    BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6,
+    BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6, BUF_U_OUT7,
     BUF_P_MODEL, BUF_P_N, BUF_P_NODEOFF, BUF_P_HEIGHT, BUF_P_PARENT, BUF_P_LEAFTYPE,
     BUF_P_ORDEROFF, BUF_P_ORDER, BUF_P_U, BUF_P_UOFF, BUF_P_LOGW, BUF_P_STATUS, BUF_P_USED,
     BUF_P_LOGP,
+    BUF_STAGE_IN, BUF_STAGE_OUT,
     BUF_COUNT
 };
 
@@ -53,6 +57,53 @@ int mtt_fail(mtt_ctx *ctx, int code, const char *fmt, ...);
 int mtt_unif_ensure_powers(mtt_ctx *ctx, int K);
 // grow-only device buffer with 256 B of slack past `bytes` (bulk copies over-read <= 15 B)
 void *mtt_buf(mtt_ctx *ctx, int id, size_t bytes);
+
+// Host <-> device transfer plan of one host-buffer call.  Small calls -- the latency-bound
+// sweeps of a few dozen chains -- pack every input into ONE pinned staging buffer and every
+// output into another: two copies per call instead of some fifteen from pageable memory.
+// Large calls copy array by array (packing would cost a pass over the host data).
+class Xfer {
+public:
+    explicit Xfer(mtt_ctx *ctx, size_t stagedLimit = (size_t)1 << 20) : ctx_(ctx), limit_(stagedLimit) {}
+    // declare an input / output array; *dptr receives its device address in prepare()
+    template <typename T>
+    void in(const T *src, size_t count, int bufId, T **dptr)
+    {
+        ins_.push_back(Item{(void *)src, count * sizeof(T), bufId, (void **)dptr, 0});
+    }
+    template <typename T>
+    void out(T *dst, size_t count, int bufId, T **dptr)
+    {
+        outs_.push_back(Item{(void *)dst, count * sizeof(T), bufId, (void **)dptr, 0});
+    }
+    bool staged() const { return staged_; }
+    int prepare();      // device (and staging) memory, device addresses
+    int upload();       // inputs -> device, asynchronous on the ctx stream
+    int download();     // outputs -> host, synchronises the stream
+    // staged mode: the host copy of an output after download_raw() (no scatter yet)
+    template <typename T>
+    const T *peek(const T *dst) const
+    {
+        for (const Item &o : outs_)
+            if (o.host == (const void *)dst)
+                return staged_ ? (const T *)((const char *)ctx_->pinOut + o.off) : nullptr;
+        return nullptr;
+    }
+
+private:
+    struct Item {
+        void *host;
+        size_t bytes;
+        int bufId;
+        void **dptr;
+        size_t off;
+    };
+    mtt_ctx *ctx_;
+    size_t limit_;
+    bool staged_ = false;
+    size_t inBytes_ = 0, outBytes_ = 0;
+    std::vector<Item> ins_, outs_;
+};
 
 #define MTT_CUDA(ctx, expr)                                                              \
     do {                                                                                 \

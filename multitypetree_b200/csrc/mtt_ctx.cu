@@ -43,6 +43,101 @@ void *mtt_buf(mtt_ctx *ctx, int id, size_t bytes)
     return b.p;
 }
 
+// ------------------------------------------------------------------ Xfer (mtt_common.cuh)
+static int grow_pinned(mtt_ctx *ctx, void *&p, size_t &cap, size_t bytes)
+{
+    if (bytes <= cap)
+        return MTT_OK;
+    if (p) {
+        cudaStreamSynchronize(ctx->stream);
+        cudaFreeHost(p);
+        p = nullptr;
+        cap = 0;
+    }
+    const size_t want = bytes + bytes / 2 + 65536;
+    MTT_CUDA(ctx, cudaMallocHost(&p, want));
+    cap = want;
+    return MTT_OK;
+}
+
+int Xfer::prepare()
+{
+    size_t in = 0, out = 0;
+    for (Item &i : ins_) {
+        i.off = in;
+        in = (in + i.bytes + 255) & ~(size_t)255;
+    }
+    for (Item &o : outs_) {
+        o.off = out;
+        out = (out + o.bytes + 255) & ~(size_t)255;
+    }
+    inBytes_ = in;
+    outBytes_ = out;
+    staged_ = in + out <= limit_;
+    if (staged_) {
+        char *dIn = (char *)mtt_buf(ctx_, BUF_STAGE_IN, in);
+        char *dOut = (char *)mtt_buf(ctx_, BUF_STAGE_OUT, out);
+        if (!dIn || !dOut)
+            return MTT_ERR_CUDA;
+        int rc = grow_pinned(ctx_, ctx_->pinIn, ctx_->pinInCap, in);
+        if (rc == MTT_OK)
+            rc = grow_pinned(ctx_, ctx_->pinOut, ctx_->pinOutCap, out);
+        if (rc != MTT_OK)
+            return rc;
+        for (Item &i : ins_)
+            *i.dptr = dIn + i.off;
+        for (Item &o : outs_)
+            *o.dptr = dOut + o.off;
+        return MTT_OK;
+    }
+    for (Item &i : ins_)
+        if (!(*i.dptr = mtt_buf(ctx_, i.bufId, i.bytes)))
+            return MTT_ERR_CUDA;
+    for (Item &o : outs_)
+        if (!(*o.dptr = mtt_buf(ctx_, o.bufId, o.bytes)))
+            return MTT_ERR_CUDA;
+    return MTT_OK;
+}
+
+int Xfer::upload()
+{
+    cudaStream_t s = ctx_->stream;
+    if (staged_) {
+        // the previous call's copy out of the staging buffer has completed (calls block)
+        for (const Item &i : ins_)
+            if (i.bytes)
+                memcpy((char *)ctx_->pinIn + i.off, i.host, i.bytes);
+        if (inBytes_)
+            MTT_CUDA(ctx_, cudaMemcpyAsync(ctx_->bufs[BUF_STAGE_IN].p, ctx_->pinIn, inBytes_,
+                                           cudaMemcpyHostToDevice, s));
+        return MTT_OK;
+    }
+    for (const Item &i : ins_)
+        if (i.bytes)
+            MTT_CUDA(ctx_, cudaMemcpyAsync(*i.dptr, i.host, i.bytes, cudaMemcpyHostToDevice, s));
+    return MTT_OK;
+}
+
+int Xfer::download()
+{
+    cudaStream_t s = ctx_->stream;
+    if (staged_) {
+        if (outBytes_)
+            MTT_CUDA(ctx_, cudaMemcpyAsync(ctx_->pinOut, ctx_->bufs[BUF_STAGE_OUT].p, outBytes_,
+                                           cudaMemcpyDeviceToHost, s));
+        MTT_CUDA(ctx_, cudaStreamSynchronize(s));
+        for (const Item &o : outs_)
+            if (o.bytes)
+                memcpy(o.host, (const char *)ctx_->pinOut + o.off, o.bytes);
+        return MTT_OK;
+    }
+    for (const Item &o : outs_)
+        if (o.bytes)
+            MTT_CUDA(ctx_, cudaMemcpyAsync(o.host, *o.dptr, o.bytes, cudaMemcpyDeviceToHost, s));
+    MTT_CUDA(ctx_, cudaStreamSynchronize(s));
+    return MTT_OK;
+}
+
 extern "C" {
 
 int mtt_abi_version(void)
@@ -105,6 +200,10 @@ int mtt_ctx_destroy(mtt_ctx *ctx)
     for (auto &b : ctx->bufs)
         if (b.p)
             cudaFree(b.p);
+    if (ctx->pinIn)
+        cudaFreeHost(ctx->pinIn);
+    if (ctx->pinOut)
+        cudaFreeHost(ctx->pinOut);
     if (ctx->ownStream)
         cudaStreamDestroy(ctx->ownStream);
     delete ctx;

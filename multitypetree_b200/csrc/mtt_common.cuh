@@ -33,6 +33,9 @@ struct mtt_ctx {
     std::vector<int> unifPowSize;       // powers valid per model
     std::vector<int> unifSteady;        // steady flag per model
     std::vector<double> unifMu;         // host copy of mu per model
+    // copy stream + events of the chunked host-buffer density entry (mtt_ctx.cu)
+    cudaStream_t copyStream = nullptr;
+    std::vector<cudaEvent_t> events;
     // pinned staging of small calls (Xfer below)
     void *pinIn = nullptr, *pinOut = nullptr;
     size_t pinInCap = 0, pinOutCap = 0;

@@ -200,6 +200,10 @@ int mtt_ctx_destroy(mtt_ctx *ctx)
     for (auto &b : ctx->bufs)
         if (b.p)
             cudaFree(b.p);
+    for (cudaEvent_t ev : ctx->events)
+        cudaEventDestroy(ev);
+    if (ctx->copyStream)
+        cudaStreamDestroy(ctx->copyStream);
     if (ctx->pinIn)
         cudaFreeHost(ctx->pinIn);
     if (ctx->pinOut)
@@ -397,31 +401,68 @@ static int sc_logp_host(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t
     MTT_CUDA(ctx, cudaMemcpyAsync(dN, N, nd, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dNodeOff, nodeOff, (B + 1) * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dChgBase, chgBase, (B + 1) * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dH, height, nodes * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dT, nodeType, nodes, cudaMemcpyHostToDevice, s));
-    if (!owners)
-        MTT_CUDA(ctx, cudaMemcpyAsync(dK, chgCountOrNode, nodes * 2, cudaMemcpyHostToDevice, s));
-    if (changes > 0) {
-        MTT_CUDA(ctx, cudaMemcpyAsync(dCT, chgTime, changes * 8, cudaMemcpyHostToDevice, s));
-        MTT_CUDA(ctx, cudaMemcpyAsync(dCTy, chgType, changes, cudaMemcpyHostToDevice, s));
-        if (owners)
-            MTT_CUDA(ctx, cudaMemcpyAsync(dO, chgCountOrNode, changes * 2, cudaMemcpyHostToDevice,
-                                          s));
+
+    // Large batches are cut into chunks of trees: the arrays of chunk k+1 cross the PCIe link
+    // (copy stream) while chunk k is evaluated and its results go back (ctx stream).  The link
+    // is the bottleneck of this entry; the pipeline hides everything else behind it.
+    const size_t bytes = (size_t)nodes * (8 + 1 + (owners ? 0 : 2) + (parent ? 4 : 0)) +
+                         (size_t)changes * (8 + 1 + (owners ? 2 : 0));
+    const int nChunks = (bytes > ((size_t)32 << 20) && B >= 1024) ? 8 : 1;
+    cudaStream_t cs = s;
+    if (nChunks > 1) {
+        if (!ctx->copyStream)
+            MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        while ((int)ctx->events.size() < nChunks + 1) {
+            cudaEvent_t ev;
+            MTT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->events.push_back(ev);
+        }
+        cs = ctx->copyStream;
+        // the copy stream starts after whatever the ctx stream still has in flight on these
+        // buffers (an earlier call's kernels) and after the offsets above
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[nChunks], s));
+        MTT_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->events[nChunks], 0));
     }
-    if (parent)
-        MTT_CUDA(ctx, cudaMemcpyAsync(dP, parent, nodes * 4, cudaMemcpyHostToDevice, s));
     int rc = MTT_OK;
-    if (!owners)
-        rc = mtt_k1_expand_counts(ctx, B, dNodeOff, dK, dChgBase, dO);
-    if (rc != MTT_OK)
-        return rc;
-    rc = mtt_k1_launch(ctx, B, d, nModels, dM, dN, dNodeOff, dH, dP, dT, dO, dChgBase, dCT, dCTy,
-                       checkValidity, dLogP, dValid, maxEv > 0 ? maxEv : 1);
-    if (rc != MTT_OK)
-        return rc;
-    MTT_CUDA(ctx, cudaMemcpyAsync(logP, dLogP, B * 8, cudaMemcpyDeviceToHost, s));
-    if (dValid)
-        MTT_CUDA(ctx, cudaMemcpyAsync(valid, dValid, B, cudaMemcpyDeviceToHost, s));
+    for (int k = 0; k < nChunks; k++) {
+        const int64_t b0 = B * k / nChunks, b1 = B * (k + 1) / nChunks, Bk = b1 - b0;
+        if (Bk == 0)
+            continue;
+        const int64_t n0 = nodeOff[b0], n1 = nodeOff[b1], c0 = chgBase[b0], c1 = chgBase[b1];
+        const size_t nn = (size_t)(n1 - n0), nc = (size_t)(c1 - c0);
+        MTT_CUDA(ctx, cudaMemcpyAsync(dH + n0, height + n0, nn * 8, cudaMemcpyHostToDevice, cs));
+        MTT_CUDA(ctx, cudaMemcpyAsync(dT + n0, nodeType + n0, nn, cudaMemcpyHostToDevice, cs));
+        if (!owners)
+            MTT_CUDA(ctx, cudaMemcpyAsync(dK + n0, chgCountOrNode + n0, nn * 2,
+                                          cudaMemcpyHostToDevice, cs));
+        if (nc > 0) {
+            MTT_CUDA(ctx, cudaMemcpyAsync(dCT + c0, chgTime + c0, nc * 8, cudaMemcpyHostToDevice, cs));
+            MTT_CUDA(ctx, cudaMemcpyAsync(dCTy + c0, chgType + c0, nc, cudaMemcpyHostToDevice, cs));
+            if (owners)
+                MTT_CUDA(ctx, cudaMemcpyAsync(dO + c0, chgCountOrNode + c0, nc * 2,
+                                              cudaMemcpyHostToDevice, cs));
+        }
+        if (parent)
+            MTT_CUDA(ctx, cudaMemcpyAsync(dP + n0, parent + n0, nn * 4, cudaMemcpyHostToDevice, cs));
+        if (nChunks > 1) {
+            MTT_CUDA(ctx, cudaEventRecord(ctx->events[k], cs));
+            MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[k], 0));
+        }
+        if (!owners)
+            rc = mtt_k1_expand_counts(ctx, Bk, dNodeOff + b0, dK, dChgBase + b0, dO);
+        if (rc != MTT_OK)
+            return rc;
+        const bool perTree = nModels > 1;
+        rc = mtt_k1_launch(ctx, Bk, d, perTree ? Bk : 1, dM + (perTree ? b0 * d * d : 0),
+                           dN + (perTree ? b0 * d : 0), dNodeOff + b0, dH, dP, dT, dO,
+                           dChgBase + b0, dCT, dCTy, checkValidity, dLogP + b0,
+                           dValid ? dValid + b0 : nullptr, maxEv > 0 ? maxEv : 1);
+        if (rc != MTT_OK)
+            return rc;
+        MTT_CUDA(ctx, cudaMemcpyAsync(logP + b0, dLogP + b0, Bk * 8, cudaMemcpyDeviceToHost, s));
+        if (dValid)
+            MTT_CUDA(ctx, cudaMemcpyAsync(valid + b0, dValid + b0, Bk, cudaMemcpyDeviceToHost, s));
+    }
     MTT_CUDA(ctx, cudaStreamSynchronize(s));
     if (valid && !parent)
         memset(valid, 1, (size_t)B);

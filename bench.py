@@ -289,10 +289,43 @@ def bench_density(args):
     barrier(world)
     e2e_s = max_over_ranks(time.perf_counter() - t0, world)
     e2e_value = B * world * e2e_steps / e2e_s
-    for a in pinned:
-        L.mtt_host_unregister(a.ctypes.data)
     # device-resident and end-to-end paths must agree bit for bit
     assert np.array_equal(out_h, logP.cpu().numpy()), "e2e and device-resident results differ"
+
+    # ---- the same trees through the fixed-tips entry: all trees of the workload are over one
+    #      taxon set (as all trees of a BEAST analysis are), so the tips are installed once
+    #      outside the timed region (like the alignment of the peeling handle) and a step moves
+    #      only internal nodes and change lists.  Reported beside `e2e`, not instead of it.
+    nL = 100
+    nN = 2 * nL - 1
+    H2 = tb.height.reshape(B, nN)
+    T2 = tb.nodeType.reshape(B, nN)
+    assert np.all(H2[:, :nL] == H2[0, :nL]) and np.all(T2[:, :nL] == T2[0, :nL])
+    tipH, tipT = np.ascontiguousarray(H2[0, :nL]), np.ascontiguousarray(T2[0, :nL])
+    ctx.check(L.mtt_sc_set_tips(ctx.handle, nL, _lib.ptr(tipH), _lib.ptr(tipT)))
+    intH, intT = np.ascontiguousarray(H2[:, nL:]), np.ascontiguousarray(T2[:, nL:])
+    out_t = np.empty(B, np.float64)
+    pinned_t = [a for a in (intH, intT, out_t) if L.mtt_host_register(a.ctypes.data, a.nbytes) == 0]
+    h2d_t = int(intH.nbytes + intT.nbytes + sum(host[i].nbytes for i in (0, 1, 5, 6, 7, 8)))
+
+    def tips_step():
+        ctx.check(L.mtt_sc_logp_tips_batch(
+            ctx.handle, B, 2, 1, _lib.ptr(host[0]), _lib.ptr(host[1]), _lib.ptr(intH), None,
+            _lib.ptr(intT), _lib.ptr(host[5]), _lib.ptr(host[6]), _lib.ptr(host[7]),
+            _lib.ptr(host[8]), 0, _lib.ptr(out_t), None))
+
+    for _ in range(2):
+        tips_step()
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        tips_step()
+    barrier(world)
+    tips_s = max_over_ranks(time.perf_counter() - t0, world)
+    tips_value = B * world * e2e_steps / tips_s
+    assert np.array_equal(out_t, out_h), "fixed-tips and general entries differ"
+    for a in pinned + pinned_t:
+        L.mtt_host_unregister(a.ctypes.data)
 
     if rank != 0:
         return
@@ -325,6 +358,11 @@ def bench_density(args):
         "e2e": {"value": e2e_value, "unit": "evals/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h, "steps": e2e_steps,
                 "pinned": len(pinned) == len(host) + 1},
+        "e2e_fixed_tips": {"value": tips_value, "unit": "evals/s", "h2d_bytes_per_step": h2d_t,
+                           "d2h_bytes_per_step": d2h, "steps": e2e_steps,
+                           "note": "mtt_sc_set_tips once + mtt_sc_logp_tips_batch per step: the "
+                                   "trees share their 100 tips, only internal nodes and change "
+                                   "lists cross the link; results bit-identical to e2e"},
         "gpu_launches": int(launches),
         "clocks": clk.summary(),
         "cfg2_b4096": small,

@@ -140,6 +140,22 @@ int mtt_sc_logp_owner_batch_dev(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
                                 const uint8_t *chgType, int checkValidity, double *logP,
                                 uint8_t *valid);
 
+/* Trees over ONE taxon set.  The tips are data -- tip dates and tip types are fixed for a whole
+ * analysis -- so they are installed once, like the alignment of the peeling handle, and a call
+ * moves only what a proposal can change: the heights and types of the nLeaves-1 internal nodes
+ * (node nLeaves + i is entry i) and the change lists in the owner layout.  For a 100-tip tree
+ * with 40 changes that is 1.35 KB instead of 2.26 KB over the host link, which is what bounds
+ * the host-buffer entries.  Results are bit-identical to mtt_sc_logp_owner_batch on the same
+ * trees.  leafHeight[nLeaves], leafType[nLeaves]; intHeight / intType [B][nLeaves-1];
+ * parent [B][2*nLeaves-1] (NULL without validity checking). */
+int mtt_sc_set_tips(mtt_ctx *ctx, int nLeaves, const double *leafHeight, const uint8_t *leafType);
+int mtt_sc_logp_tips_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels, const double *m,
+                           const double *N, const double *intHeight, const int32_t *parent,
+                           const uint8_t *intType, const uint16_t *chgNode,
+                           const int64_t *chgBase, const double *chgTime,
+                           const uint8_t *chgType, int checkValidity, double *logP,
+                           uint8_t *valid);
+
 /* Optional hint for the _dev entries: an upper bound on nodes + changes of any tree in later
  * batches (0 = unknown; it stays set on the ctx until changed).  With a bound <= 1022 the batch
  * is ONE kernel launch sized for that bound.  The bound is a promise: a tree that exceeds it is

@@ -9,7 +9,8 @@ from .tree import (DeviceTreeBatch, MultiTypeTree, MultiTypeTreeFromNewick, Tree
                    read_nexus_tree, read_nexus_trees, simulate_trees,
                    synthetic_model)
 from .migration_model import SCMigrationModel, TypeSet  # noqa: F401
-from .density import StructuredCoalescentTreeDensity, sc_logp_batch, tree_validity  # noqa: F401
+from .density import (StructuredCoalescentTreeDensity, sc_logp_batch,  # noqa: F401
+                      sc_logp_tips_batch, set_tips, tree_validity)
 from .uniformization import Randomizer, UniformizationModels  # noqa: F401
 from .operators import (MultiTypeTreeScale, MultiTypeUniform, NodeRetype,  # noqa: F401
                         NodeShiftRetype, TypedSubtreeExchange, TypedWilsonBalding,
@@ -20,7 +21,7 @@ __all__ = [
     "Context", "MttError", "default_context", "lib", "DeviceTreeBatch", "MultiTypeTree",
     "MultiTypeTreeFromNewick", "TreeBatch", "read_nexus_tree", "read_nexus_trees", "simulate_trees",
     "synthetic_model", "SCMigrationModel", "TypeSet", "StructuredCoalescentTreeDensity",
-    "sc_logp_batch", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",
+    "sc_logp_batch", "sc_logp_tips_batch", "set_tips", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",
     "NodeShiftRetype", "TypedSubtreeExchange", "TypedWilsonBalding", "MultiTypeTreeScale",
     "MultiTypeUniform", "run_proposals", "MCMC", "Chain", "MCMCEnsemble",
 ]

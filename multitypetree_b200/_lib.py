@@ -42,6 +42,9 @@ ABI = {
     "mtt_sc_logp_owner_batch_dev": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int64, VP, VP, VP, VP,
                                               VP, VP, VP, VP, VP, VP, C.c_int, VP, VP]),
     "mtt_sc_set_max_tree_events": (C.c_int, [VP, C.c_int64]),
+    "mtt_sc_set_tips": (C.c_int, [VP, C.c_int, VP, VP]),
+    "mtt_sc_logp_tips_batch": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int64, VP, VP, VP, VP, VP,
+                                         VP, VP, VP, VP, C.c_int, VP, VP]),
     "mtt_unif_set_models": (C.c_int, [VP, C.c_int, C.c_int, VP, C.c_int]),
     "mtt_unif_get_matrices": (C.c_int, [VP, C.c_int, VP, VP, VP]),
     "mtt_unif_rpow": (C.c_int, [VP, C.c_int, C.c_int, VP, VP]),

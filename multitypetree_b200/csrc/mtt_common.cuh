@@ -27,6 +27,7 @@ struct mtt_ctx {
     std::vector<DevBuf> bufs;
     // piece 1: caller's bound on nodes+changes per tree for the _dev entry (0 = unknown)
     long long k1MaxEvents = 0;
+    int tipCount = 0;                   // leaves installed by mtt_sc_set_tips (0 = none)
     // piece 3 state
     int unifModels = 0, unifD = 0, unifSym = 0;
     int unifPowCap = 0;                 // powers allocated per model (entries 0..cap-1)
@@ -44,7 +45,7 @@ struct mtt_ctx {
 enum BufId {
     BUF_D_MODEL = 0, BUF_D_N, BUF_D_NODEOFF, BUF_D_HEIGHT, BUF_D_PARENT, BUF_D_NODETYPE,
     BUF_D_CHGCOUNT, BUF_D_CHGBASE, BUF_D_CHGTIME, BUF_D_CHGTYPE, BUF_D_LOGP, BUF_D_VALID,
-    BUF_D_QUEUE, BUF_D_CHGNODE,
+    BUF_D_QUEUE, BUF_D_CHGNODE, BUF_D_TIPH, BUF_D_TIPT, BUF_D_INTH, BUF_D_INTT,
     BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
     BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6, BUF_U_OUT7,

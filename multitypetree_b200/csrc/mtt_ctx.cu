@@ -2,6 +2,8 @@
 #include "mtt_common.cuh"
 
 #include <stdarg.h>
+
+#include <algorithm>
 #include <stdio.h>
 #include <string.h>
 
@@ -493,6 +495,175 @@ extern "C" int mtt_sc_logp_owner_batch(mtt_ctx *ctx, int64_t B, int d, int64_t n
     return sc_logp_host(ctx, "mtt_sc_logp_owner_batch", B, d, nModels, m, N, nodeOff, height,
                         parent, nodeType, chgNode, true, chgBase, chgTime, chgType, checkValidity,
                         logP, valid);
+}
+
+// ------------------------------------------------------------------ trees over one taxon set
+// leaves from the installed tip arrays, internal nodes from the call's arrays -> full tree SoA
+__global__ void k1_expand_tips(long long B, int nL, const double *leafH, const uint8_t *leafT,
+                               const double *intH, const uint8_t *intT, long long t0,
+                               double *height, uint8_t *nodeType, long long *nodeOff)
+{
+    const int nN = 2 * nL - 1, nI = nL - 1;
+    const long long total = B * nN;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+         i += (long long)gridDim.x * blockDim.x) {
+        const long long t = i / nN;
+        const int e = (int)(i - t * nN);
+        const long long g = (t0 + t) * nN + e;
+        if (e < nL) {
+            height[g] = leafH[e];
+            nodeType[g] = leafT[e];
+        } else {
+            height[g] = intH[(t0 + t) * nI + (e - nL)];
+            nodeType[g] = intT[(t0 + t) * nI + (e - nL)];
+        }
+        if (e == 0)
+            nodeOff[t0 + t] = (t0 + t) * nN;
+        if (i == total - 1)
+            nodeOff[t0 + B] = (t0 + B) * nN;
+    }
+}
+
+extern "C" int mtt_sc_set_tips(mtt_ctx *ctx, int nLeaves, const double *leafHeight,
+                               const uint8_t *leafType)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (nLeaves < 2 || !leafHeight || !leafType)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_sc_set_tips: bad arguments");
+    if (2 * nLeaves - 1 > 65535)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "mtt_sc_set_tips: more than 32768 tips");
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    double *dH = (double *)mtt_buf(ctx, BUF_D_TIPH, (size_t)nLeaves * 8);
+    uint8_t *dT = (uint8_t *)mtt_buf(ctx, BUF_D_TIPT, (size_t)nLeaves);
+    if (!dH || !dT)
+        return MTT_ERR_CUDA;
+    MTT_CUDA(ctx, cudaMemcpyAsync(dH, leafHeight, (size_t)nLeaves * 8, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dT, leafType, (size_t)nLeaves, cudaMemcpyHostToDevice,
+                                  ctx->stream));
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+    ctx->tipCount = nLeaves;
+    return MTT_OK;
+}
+
+extern "C" int mtt_sc_logp_tips_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nModels,
+                                      const double *m, const double *N, const double *intHeight,
+                                      const int32_t *parent, const uint8_t *intType,
+                                      const uint16_t *chgNode, const int64_t *chgBase,
+                                      const double *chgTime, const uint8_t *chgType,
+                                      int checkValidity, double *logP, uint8_t *valid)
+{
+    const char *who = "mtt_sc_logp_tips_batch";
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (ctx->tipCount < 2)
+        return mtt_fail(ctx, MTT_ERR_STATE, "%s: mtt_sc_set_tips has not been called", who);
+    if (B < 0 || !m || !N || !intHeight || !intType || !chgBase || !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: NULL argument", who);
+    if (B == 0)
+        return MTT_OK;
+    if (nModels != 1 && nModels != B)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: nModels must be 1 or B", who);
+    if (checkValidity && !parent)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "%s: checkValidity requires parent[]", who);
+    MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+    const int nL = ctx->tipCount, nN = 2 * nL - 1, nI = nL - 1;
+    const int64_t nodes = B * nN, changes = chgBase[B] - chgBase[0];
+    if (chgBase[0] != 0)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "chgBase[0] must be 0");
+    if (changes > 0 && (!chgTime || !chgType || !chgNode))
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "chgTime/chgType/chgNode NULL with changes present");
+    long long maxEv = 0;
+    for (int64_t b = 0; b < B; b++) {
+        if (chgBase[b + 1] < chgBase[b])
+            return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "offsets of tree %lld not monotone", (long long)b);
+        maxEv = std::max<long long>(maxEv, nN + (chgBase[b + 1] - chgBase[b]));
+    }
+    if (maxEv > MTT_MAX_TREE_EVENTS)
+        return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "a tree has %lld events (nodes + changes); limit is %d",
+                        maxEv, MTT_MAX_TREE_EVENTS);
+    cudaStream_t s = ctx->stream;
+    const size_t md = (size_t)nModels * d * d * 8, nd = (size_t)nModels * d * 8;
+    double *dM = (double *)mtt_buf(ctx, BUF_D_MODEL, md);
+    double *dN = (double *)mtt_buf(ctx, BUF_D_N, nd);
+    int64_t *dNodeOff = (int64_t *)mtt_buf(ctx, BUF_D_NODEOFF, (B + 1) * 8);
+    int64_t *dChgBase = (int64_t *)mtt_buf(ctx, BUF_D_CHGBASE, (B + 1) * 8);
+    double *dH = (double *)mtt_buf(ctx, BUF_D_HEIGHT, nodes * 8);
+    uint8_t *dT = (uint8_t *)mtt_buf(ctx, BUF_D_NODETYPE, nodes);
+    double *dIH = (double *)mtt_buf(ctx, BUF_D_INTH, (size_t)B * nI * 8);
+    uint8_t *dIT = (uint8_t *)mtt_buf(ctx, BUF_D_INTT, (size_t)B * nI);
+    uint16_t *dO = (uint16_t *)mtt_buf(ctx, BUF_D_CHGNODE, changes * 2);
+    double *dCT = (double *)mtt_buf(ctx, BUF_D_CHGTIME, changes * 8);
+    uint8_t *dCTy = (uint8_t *)mtt_buf(ctx, BUF_D_CHGTYPE, changes);
+    int32_t *dP = parent ? (int32_t *)mtt_buf(ctx, BUF_D_PARENT, nodes * 4) : nullptr;
+    double *dLogP = (double *)mtt_buf(ctx, BUF_D_LOGP, B * 8);
+    uint8_t *dValid = (valid && parent) ? (uint8_t *)mtt_buf(ctx, BUF_D_VALID, B) : nullptr;
+    if (!dM || !dN || !dNodeOff || !dChgBase || !dH || !dT || !dIH || !dIT || !dO || !dCT ||
+        !dCTy || !dLogP || (parent && !dP) || (valid && parent && !dValid))
+        return MTT_ERR_CUDA;
+    const double *dTipH = (const double *)ctx->bufs[BUF_D_TIPH].p;
+    const uint8_t *dTipT = (const uint8_t *)ctx->bufs[BUF_D_TIPT].p;
+    MTT_CUDA(ctx, cudaMemcpyAsync(dM, m, md, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dN, N, nd, cudaMemcpyHostToDevice, s));
+    MTT_CUDA(ctx, cudaMemcpyAsync(dChgBase, chgBase, (B + 1) * 8, cudaMemcpyHostToDevice, s));
+    const size_t bytes = (size_t)B * nI * 9 + (size_t)nodes * (parent ? 4 : 0) + (size_t)changes * 11;
+    const int nChunks = (bytes > ((size_t)32 << 20) && B >= 1024) ? 8 : 1;
+    cudaStream_t cs = s;
+    if (nChunks > 1) {
+        if (!ctx->copyStream)
+            MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        while ((int)ctx->events.size() < nChunks + 1) {
+            cudaEvent_t ev;
+            MTT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->events.push_back(ev);
+        }
+        cs = ctx->copyStream;
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[nChunks], s));
+        MTT_CUDA(ctx, cudaStreamWaitEvent(cs, ctx->events[nChunks], 0));
+    }
+    for (int k = 0; k < nChunks; k++) {
+        const int64_t b0 = B * k / nChunks, b1 = B * (k + 1) / nChunks, Bk = b1 - b0;
+        if (Bk == 0)
+            continue;
+        const int64_t c0 = chgBase[b0], c1 = chgBase[b1];
+        const size_t nc = (size_t)(c1 - c0);
+        MTT_CUDA(ctx, cudaMemcpyAsync(dIH + b0 * nI, intHeight + b0 * nI, (size_t)Bk * nI * 8,
+                                      cudaMemcpyHostToDevice, cs));
+        MTT_CUDA(ctx, cudaMemcpyAsync(dIT + b0 * nI, intType + b0 * nI, (size_t)Bk * nI,
+                                      cudaMemcpyHostToDevice, cs));
+        if (nc > 0) {
+            MTT_CUDA(ctx, cudaMemcpyAsync(dCT + c0, chgTime + c0, nc * 8, cudaMemcpyHostToDevice, cs));
+            MTT_CUDA(ctx, cudaMemcpyAsync(dCTy + c0, chgType + c0, nc, cudaMemcpyHostToDevice, cs));
+            MTT_CUDA(ctx, cudaMemcpyAsync(dO + c0, chgNode + c0, nc * 2, cudaMemcpyHostToDevice, cs));
+        }
+        if (parent)
+            MTT_CUDA(ctx, cudaMemcpyAsync(dP + b0 * nN, parent + b0 * nN, (size_t)Bk * nN * 4,
+                                          cudaMemcpyHostToDevice, cs));
+        if (nChunks > 1) {
+            MTT_CUDA(ctx, cudaEventRecord(ctx->events[k], cs));
+            MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[k], 0));
+        }
+        const long long total = (long long)Bk * nN;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+        k1_expand_tips<<<grid, 256, 0, s>>>(Bk, nL, dTipH, dTipT, dIH, dIT, b0, dH, dT,
+                                            (long long *)dNodeOff);
+        MTT_CHECK_LAUNCH(ctx);
+        const bool perTree = nModels > 1;
+        int rc = mtt_k1_launch(ctx, Bk, d, perTree ? Bk : 1, dM + (perTree ? b0 * d * d : 0),
+                               dN + (perTree ? b0 * d : 0), dNodeOff + b0, dH, dP, dT, dO,
+                               dChgBase + b0, dCT, dCTy, checkValidity, dLogP + b0,
+                               dValid ? dValid + b0 : nullptr, maxEv);
+        if (rc != MTT_OK)
+            return rc;
+        MTT_CUDA(ctx, cudaMemcpyAsync(logP + b0, dLogP + b0, Bk * 8, cudaMemcpyDeviceToHost, s));
+        if (dValid)
+            MTT_CUDA(ctx, cudaMemcpyAsync(valid + b0, dValid + b0, Bk, cudaMemcpyDeviceToHost, s));
+    }
+    MTT_CUDA(ctx, cudaStreamSynchronize(s));
+    if (valid && !parent)
+        memset(valid, 1, (size_t)B);
+    return MTT_OK;
 }
 
 extern "C" int mtt_sc_set_max_tree_events(mtt_ctx *ctx, int64_t maxEvents)

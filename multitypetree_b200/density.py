@@ -45,6 +45,55 @@ def sc_logp_batch(batch: TreeBatch, m: np.ndarray, N: np.ndarray, checkValidity:
     return (logP, valid.astype(bool)) if want_valid else logP
 
 
+def set_tips(leafHeight, leafType, ctx=None) -> None:
+    """Install the tips every later ``sc_logp_tips_batch`` call shares (mtt_sc_set_tips): tip
+    dates and tip types are data, fixed for a whole analysis."""
+    ctx = ctx or _lib.default_context()
+    h = _lib.as_c(leafHeight, np.float64)
+    t = _lib.as_c(leafType, np.uint8)
+    if h.shape != t.shape or h.ndim != 1:
+        raise ValueError("leafHeight and leafType must be 1-d arrays of equal length")
+    ctx.check(_lib.lib().mtt_sc_set_tips(ctx.handle, len(h), _lib.ptr(h), _lib.ptr(t)))
+    ctx._tips = (h.copy(), t.copy())
+
+
+def sc_logp_tips_batch(batch: TreeBatch, m: np.ndarray, N: np.ndarray,
+                       checkValidity: bool = False, ctx=None, want_valid: bool = False):
+    """logP of every tree of ``batch`` through mtt_sc_logp_tips_batch: all trees are over the
+    taxon set installed by ``set_tips``; only internal-node heights / types and the change lists
+    cross the host link.  Bit-identical to ``sc_logp_batch``."""
+    ctx = ctx or _lib.default_context()
+    tips = getattr(ctx, "_tips", None)
+    if tips is None:
+        raise ValueError("set_tips has not been called on this context")
+    nL = len(tips[0])
+    nN, B = 2 * nL - 1, batch.B
+    if not np.array_equal(batch.nodeOff, np.arange(B + 1, dtype=np.int64) * nN):
+        raise ValueError("every tree must have %d nodes" % nN)
+    H = np.asarray(batch.height).reshape(B, nN)
+    T = np.asarray(batch.nodeType).reshape(B, nN)
+    if B and not (np.array_equal(H[:, :nL], np.broadcast_to(tips[0], (B, nL))) and
+                  np.array_equal(T[:, :nL], np.broadcast_to(tips[1], (B, nL)))):
+        raise ValueError("a tree's tips differ from the installed ones")
+    m = _lib.as_c(m, np.float64)
+    N = _lib.as_c(N, np.float64)
+    d = m.shape[-1]
+    nModels = 1 if m.ndim == 2 else m.shape[0]
+    with_parent = checkValidity or want_valid
+    intH = _lib.as_c(H[:, nL:], np.float64)
+    intT = _lib.as_c(T[:, nL:], np.uint8)
+    par = _lib.as_c(batch.parent, np.int32) if with_parent else None
+    logP = np.empty(B, np.float64)
+    valid = np.empty(B, np.uint8) if want_valid else None
+    ctx.check(_lib.lib().mtt_sc_logp_tips_batch(
+        ctx.handle, B, d, nModels, _lib.ptr(m), _lib.ptr(N), _lib.ptr(intH), _lib.ptr(par),
+        _lib.ptr(intT), _lib.ptr(_lib.as_c(batch.chgNode, np.uint16)),
+        _lib.ptr(_lib.as_c(batch.chgBase, np.int64)), _lib.ptr(_lib.as_c(batch.chgTime, np.float64)),
+        _lib.ptr(_lib.as_c(batch.chgType, np.uint8)), int(bool(checkValidity)), _lib.ptr(logP),
+        _lib.ptr(valid)))
+    return (logP, valid.astype(bool)) if want_valid else logP
+
+
 def tree_validity(batch: TreeBatch, ctx=None) -> np.ndarray:
     """MultiTypeTree.isValid for every tree (MultiTypeTree.java:396-429)."""
     d = int(max(batch.nodeType.max(initial=0), batch.chgType.max(initial=0))) + 1

@@ -367,3 +367,40 @@ def test_event_bound_hint_is_a_promise(ctx):
         assert rc != 0
     finally:
         L.mtt_sc_set_max_tree_events(ctx.handle, 0)
+
+
+def test_fixed_tips_entry_is_bit_identical(ctx):
+    """mtt_sc_set_tips + mtt_sc_logp_tips_batch: trees over one taxon set, tips installed once;
+    the results are the general entry's bit for bit (shared and per-tree models, validity)."""
+    for n, d, B in ((100, 2, 3000), (30, 4, 500), (400, 3, 40), (1000, 4, 6)):
+        m, N = mtt.synthetic_model(d)
+        tb = mtt.simulate_trees(B, n, d, m, N, seed=40 + n)
+        mtt.set_tips(tb.height[:n], tb.nodeType[:n], ctx=ctx)
+        want, wv = mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+        got, gv = mtt.sc_logp_tips_batch(tb, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+        assert np.array_equal(got, want) and np.array_equal(gv, wv)
+        assert np.array_equal(mtt.sc_logp_tips_batch(tb, m, N, ctx=ctx),
+                              mtt.sc_logp_batch(tb, m, N, ctx=ctx))
+    # one model per tree
+    m, N = mtt.synthetic_model(2)
+    tb = mtt.simulate_trees(64, 50, 2, m, N, seed=3)
+    mm = np.stack([m * (1 + 0.01 * i) for i in range(64)])
+    NN = np.stack([N * (1 + 0.02 * i) for i in range(64)])
+    mtt.set_tips(tb.height[:50], tb.nodeType[:50], ctx=ctx)
+    assert np.array_equal(mtt.sc_logp_tips_batch(tb, mm, NN, ctx=ctx),
+                          mtt.sc_logp_batch(tb, mm, NN, ctx=ctx))
+    # a tree over other tips is refused by the mirror; a fresh context has no tips
+    other = mtt.simulate_trees(2, 50, 2, m, N, leafTimes=np.arange(50) * 0.1, seed=4)
+    with pytest.raises(ValueError):
+        mtt.sc_logp_tips_batch(other, m, N, ctx=ctx)
+    c2 = mtt.Context(0)
+    with pytest.raises(ValueError):
+        mtt.sc_logp_tips_batch(tb, m, N, ctx=c2)
+    from multitypetree_b200 import _lib
+    rc = _lib.lib().mtt_sc_logp_tips_batch(c2.handle, 1, 2, 1, _lib.ptr(m), _lib.ptr(N),
+                                           _lib.ptr(tb.height), None, _lib.ptr(tb.nodeType),
+                                           _lib.ptr(tb.chgNode), _lib.ptr(tb.chgBase),
+                                           _lib.ptr(tb.chgTime), _lib.ptr(tb.chgType), 0,
+                                           _lib.ptr(np.zeros(1)), None)
+    assert rc != 0
+    c2.close()

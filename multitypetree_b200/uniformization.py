@@ -158,11 +158,25 @@ class UniformizationModels:
             _lib.ptr(b), _lib.ptr(off), _lib.ptr(ct), _lib.ptr(cty), _lib.ptr(lp), _lib.ptr(st)))
         return lp, st
 
+    @staticmethod
+    def retype_buffers(nJobs: int, nBr: int, outCap: int, pin: bool = False) -> dict:
+        """Output buffers of ``retype`` for reuse across calls (``out=``); with ``pin`` they are
+        page-locked (mtt_host_register) so the read-back runs at the link rate."""
+        out = dict(nChg=np.empty(nBr, np.int32), chgTime=np.zeros((nBr, outCap)),
+                   chgType=np.zeros((nBr, outCap), np.uint8), logProb=np.empty(nBr),
+                   status=np.empty(nBr, np.int32), nVirt=np.empty(nBr, np.int32),
+                   uUsed=np.empty(nJobs, np.int64))
+        if pin:
+            for v in out.values():
+                _lib.lib().mtt_host_register(v.ctypes.data, v.nbytes)
+        return out
+
     def retype(self, brOff, tBottom, tTop, typeBottom, typeTop, uniforms, uOff, outCap=64,
-               model=None, nVirtForced=None):
+               model=None, nVirtForced=None, out=None):
         """retypeBranch for a batch of jobs (mtt_unif_retype_batch).  Returns a dict of
         per-branch arrays nChg, chgTime [nBr,outCap], chgType, logProb, status, nVirt and
-        per-job uUsed."""
+        per-job uUsed (``out``: buffers from ``retype_buffers`` to write into; entries of
+        chgTime / chgType beyond a branch's nChg are then left as they were)."""
         self._activate()
         brOff = _lib.as_c(brOff, np.int64)
         nJobs = len(brOff) - 1
@@ -175,17 +189,15 @@ class UniformizationModels:
         uOff = _lib.as_c(uOff, np.int64)
         mdl = np.zeros(nBr, np.int32) if model is None else _lib.as_c(model, np.int32)
         forced = None if nVirtForced is None else _lib.as_c(nVirtForced, np.int32)
-        nChg = np.empty(nBr, np.int32)
-        oct_ = np.zeros((nBr, outCap))
-        octy = np.zeros((nBr, outCap), np.uint8)
-        lp = np.empty(nBr)
-        st = np.empty(nBr, np.int32)
-        nv = np.empty(nBr, np.int32)
-        used = np.empty(nJobs, np.int64)
+        if out is None:
+            out = self.retype_buffers(nJobs, nBr, outCap)
+        elif out["chgTime"].shape != (nBr, outCap) or len(out["uUsed"]) != nJobs:
+            raise ValueError("out buffers do not match this call")
+        nChg, oct_, octy, lp, st, nv, used = (out[k] for k in (
+            "nChg", "chgTime", "chgType", "logProb", "status", "nVirt", "uUsed"))
         self.ctx.check(_lib.lib().mtt_unif_retype_batch(
             self.ctx.handle, nJobs, _lib.ptr(brOff), _lib.ptr(mdl), _lib.ptr(t0), _lib.ptr(t1),
             _lib.ptr(a), _lib.ptr(b), _lib.ptr(forced), _lib.ptr(u), _lib.ptr(uOff), outCap,
             _lib.ptr(nChg), _lib.ptr(oct_), _lib.ptr(octy), _lib.ptr(lp), _lib.ptr(st),
             _lib.ptr(nv), _lib.ptr(used)))
-        return dict(nChg=nChg, chgTime=oct_, chgType=octy, logProb=lp, status=st, nVirt=nv,
-                    uUsed=used)
+        return out

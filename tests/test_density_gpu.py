@@ -404,3 +404,40 @@ def test_fixed_tips_entry_is_bit_identical(ctx):
                                            _lib.ptr(np.zeros(1)), None)
     assert rc != 0
     c2.close()
+
+
+def _relabel(t, rng):
+    """The same tree with leaves permuted among themselves and internal nodes among themselves
+    (BEAST keeps leaves first; everything else about node numbers is arbitrary after a few
+    topology moves: internal nodes are not sorted by height and the root is not the last)."""
+    n, N = t.getLeafNodeCount(), t.getNodeCount()
+    new = np.concatenate([rng.permutation(n), n + rng.permutation(N - n)])     # old -> new
+    height, parent = np.zeros(N), np.full(N, -1, np.int32)
+    nodeType = np.zeros(N, np.uint8)
+    times, types = [None] * N, [None] * N
+    for old in range(N):
+        k = int(new[old])
+        height[k], nodeType[k] = t.height[old], t.nodeType[old]
+        parent[k] = -1 if t.parent[old] < 0 else int(new[t.parent[old]])
+        times[k], types[k] = list(t.changeTimes[old]), list(t.changeTypes[old])
+    return mtt.MultiTypeTree(height, parent, nodeType, times, types)
+
+
+@pytest.mark.parametrize("n,d,B", [(100, 2, 256), (60, 5, 128), (300, 2, 24), (1000, 4, 6)])
+def test_node_numbering_does_not_matter(ctx, n, d, B):
+    """Register path, shared-memory path and CTA path on trees whose nodes are numbered at
+    random: same logP as the simulator's numbering (internal nodes by height, root last) up to
+    the order of the floating-point sums, and as the oracle."""
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(B, n, d, m, N, seed=900 + n)
+    rng = np.random.default_rng(n)
+    shuffled = mtt.TreeBatch.from_trees([_relabel(tb.tree(i), rng) for i in range(B)])
+    roots = np.nonzero(shuffled.parent.reshape(B, -1) < 0)[1]
+    assert np.any(roots != 2 * n - 2)
+    base = mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx)
+    got, valid = mtt.sc_logp_batch(shuffled, m, N, checkValidity=True, ctx=ctx, want_valid=True)
+    assert valid.all()
+    np.testing.assert_allclose(got, base, rtol=1e-12)
+    np.testing.assert_allclose(got, orc.sc_logp_batch(shuffled, m, N, checkValidity=True),
+                               rtol=RTOL)
+    np.testing.assert_allclose(mtt.sc_logp_batch(shuffled, m, N, ctx=ctx), base, rtol=1e-12)

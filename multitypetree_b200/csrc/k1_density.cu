@@ -1215,7 +1215,13 @@ k1_density_warp(const K1Params p)
         // offsets of my next tree: the loads complete under this tree's work
         const TreeSpan nxt = load_span(p, (long long)t + nWarpsTotal);
 #endif
-        if (cur.n + cur.M + SLOT_SLACK > EMAX) {
+        if (cur.n == 0) {            // no nodes: an empty sum
+            if (lane == 0) {
+                p.logP[t] = cur.M == 0 ? 0.0 : NAN;
+                if (HAS_PARENT && p.valid)
+                    p.valid[t] = cur.M == 0;
+            }
+        } else if (cur.n + cur.M + SLOT_SLACK > EMAX) {
             if (lane == 0) {
                 if (p.queue) {       // too large for the warp path: queue for k1_density_block
                     const int slot = atomicAdd(&p.queue[0], 1);

@@ -441,3 +441,26 @@ def test_node_numbering_does_not_matter(ctx, n, d, B):
     np.testing.assert_allclose(got, orc.sc_logp_batch(shuffled, m, N, checkValidity=True),
                                rtol=RTOL)
     np.testing.assert_allclose(mtt.sc_logp_batch(shuffled, m, N, ctx=ctx), base, rtol=1e-12)
+
+
+def test_degenerate_trees_inside_a_batch(ctx):
+    """A single-leaf tree (one SAMPLE event, which is event 0 and skipped: logP = 0) and an empty
+    tree (no nodes) between ordinary trees: no crash, no effect on the neighbours."""
+    m, N = mtt.synthetic_model(2)
+    tb = mtt.simulate_trees(4, 20, 2, m, N, seed=8)
+    want = orc.sc_logp_batch(tb, m, N)
+    nN = 39
+    one = np.array([0.3])
+    nodeOff = np.array([0, nN, nN + 1, nN + 1, 2 * nN + 1, 3 * nN + 1, 4 * nN + 1], np.int64)
+    height = np.concatenate([tb.height[:nN], one, tb.height[nN:]])
+    parent = np.concatenate([tb.parent[:nN], [-1], tb.parent[nN:]]).astype(np.int32)
+    nodeType = np.concatenate([tb.nodeType[:nN], [1], tb.nodeType[nN:]]).astype(np.uint8)
+    chgCount = np.concatenate([tb.chgCount[:nN], [0], tb.chgCount[nN:]]).astype(np.uint16)
+    cb = tb.chgBase
+    chgBase = np.array([cb[0], cb[1], cb[1], cb[1], cb[2], cb[3], cb[4]], np.int64)
+    mixed = mtt.TreeBatch(nodeOff, height, parent, nodeType, chgCount, chgBase, tb.chgTime,
+                          tb.chgType)
+    for chk in (False, True):
+        got = mtt.sc_logp_batch(mixed, m, N, checkValidity=chk, ctx=ctx)
+        assert got[1] == 0.0 and got[2] == 0.0
+        np.testing.assert_allclose(got[[0, 3, 4, 5]], want, rtol=RTOL)

@@ -7,25 +7,27 @@
 // then walks it.  Here the flattened tree (height / nodeType / chgCount / chgTime / chgType,
 // include/mtt_b200.h) is turned into events, ordered and scanned inside one kernel:
 //
-//   k1_density_warp   one WARP per tree (E = nodes + changes <= 512).  Persistent warps, 32
-//                     resident per SM when the batch's trees have <= 384 events (24 in the
-//                     512-event stage); lane 0 stages the tree's five array slices into the
-//                     warp's shared-memory stage with 1-D bulk async copies (TMA engine,
-//                     mbarrier completion).  Events are ordered by a register-resident bitonic
-//                     network over packed 32-bit keys (23-bit quantised time | 9-bit event
-//                     index; shuffles across lanes), 256 at a time; a second run is merged by
-//                     merge path.  The per-deme lineage counts come from a warp prefix sum of
-//                     packed (biased) 16-bit count fields; every lane then integrates its 8
-//                     (16) consecutive intervals with a running lambda and verifies the exact
-//                     fp64 time order (quantisation ties are repaired, rarely).  fp64
-//                     throughout; no atomics on the result.
-//   k1_density_block  one CTA per tree for larger trees (E <= 16384), fed from the queue the
-//                     warp kernel fills: shared-memory bitonic sort of 64-bit keys
-//                     (38-bit quantised time | index | descriptor), same scan.
+//   k1_density_warp   one WARP per tree, up to 1022 events (stages of 256 / 384 / 512 / 1024
+//                     slots).  Persistent warps, 24 resident per SM up to 384 slots; lane 0
+//                     stages the tree's five array slices into the warp's shared-memory stage
+//                     with 1-D bulk async copies (TMA engine, mbarrier completion).  Events are
+//                     addressed by stage SLOT; slots without an event are harmless twins of the
+//                     last node, so no pass carries a bound.  Trees up to 254 events (config 2)
+//                     stay in registers: times read once, a bitonic network over 256 packed
+//                     32-bit keys (23-bit quantised time | 9-bit slot; shuffles across lanes),
+//                     a warp prefix sum of packed (biased) 16-bit lineage counts, a fully
+//                     unrolled scan of each lane's 8 consecutive intervals that also verifies
+//                     the exact fp64 order (quantisation ties are repaired, rarely).  Larger
+//                     trees: sorted runs of 256 in shared memory, merge path, rolled scan.
+//   k1_density_cta    one CTA per tree beyond that (configs 3 and 4, up to 16384 events), fed
+//                     from the queue the warp kernel fills: register-sorted runs per warp,
+//                     merge-path levels across the CTA, an equalised time grid for the keys,
+//                     the same scan after a CTA-wide prefix sum.
 //
-// HBM traffic per tree is the input arrays once (<= 12 B per event) + 8 B out.  At the
-// 2-deme / 100-tip size the kernel is bound by instruction issue (the ordering network), not by
-// HBM bandwidth: see DESIGN.md section 4.1 and profiles/.
+// fp64 throughout; no atomics on the result.  HBM traffic per tree is the input arrays once
+// (<= 12 B per event) + 8 B out.  The staging alone runs at the HBM roofline; at the 2-deme /
+// 100-tip size the kernel as a whole is bound by the ordering network (ALU pipe / issue slots):
+// see DESIGN.md section 4.1 and profiles/.
 #include "mtt_common.cuh"
 
 #include <math.h>
@@ -1160,8 +1162,8 @@ __device__ __forceinline__ double process_tree(WarpSmem<NW, HAS_PARENT, EMAX> *w
     return NAN;      // not reached: the 256-slot stage only takes trees of the register path
 }
 
-// EMAX = 256 / 384 / 512 / 1024: every tree with n + M + 2 <= EMAX is evaluated here (4 CTAs =
-// 32 warps per SM up to 384, 3 CTAs at 512, 2 CTAs of 5 warps at 1024); larger ones are queued
+// EMAX = 256 / 384 / 512 / 1024: every tree with n + M + 2 <= EMAX is evaluated here (3 CTAs =
+// 24 warps per SM up to 512, 2 CTAs of 5 warps at 1024); larger ones are queued
 // for the CTA-per-tree kernel, or -- when the caller promised a bound and no such kernel
 // follows (p.queue == NULL) -- reported as NaN.  Persistent warps, one tree at a time per
 // warp: lane 0 launches the bulk copies of the tree's array slices (TMA engine), the warp
@@ -1223,7 +1225,7 @@ k1_density_warp(const K1Params p)
             }
         } else if (cur.n + cur.M + SLOT_SLACK > EMAX) {
             if (lane == 0) {
-                if (p.queue) {       // too large for the warp path: queue for k1_density_block
+                if (p.queue) {       // too large for the warp path: queue for k1_density_cta
                     const int slot = atomicAdd(&p.queue[0], 1);
                     p.queue[1 + slot] = (int)t;
                 } else {             // beyond the bound the caller gave: an error, loudly
@@ -1785,7 +1787,7 @@ int launch_all(mtt_ctx *ctx, const K1Params &p, long long maxEvents)
         q.queue = nullptr;
         if (maxEvents + SLOT_SLACK <= 256)
             return launch_warp_any<NW, 256>(ctx, q);
-        if (maxEvents + SLOT_SLACK <= 384)          // 4 CTAs (32 warps) per SM still fit
+        if (maxEvents + SLOT_SLACK <= 384)          // the smaller stage of config 2
             return launch_warp_any<NW, 384>(ctx, q);
         if (maxEvents + SLOT_SLACK <= 512)
             return launch_warp_any<NW, 512>(ctx, q);

@@ -271,6 +271,12 @@ int mtt_peel_logl_batch(mtt_peel *h, int64_t B, const int32_t *parent, const dou
 int mtt_peel_logl_batch_params(mtt_peel *h, int64_t B, const int32_t *parent,
                                const double *height, const double *kappa,
                                const double *branchRate, double *logL);
+/* same under a relaxed clock (UCRelaxedClockModel / RandomLocalClockModel of
+ * fxtemplates/MTTClockModels.xml:40-120): branchRates[B][2*nTips-1] holds
+ * branchRateModel.getRateForBranch(node) for the branch above every node (the root's entry is
+ * unused) and replaces the handle's strict-clock rate. */
+int mtt_peel_logl_batch_rates(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                              const double *branchRates, double *logL);
 /* same with explicit transition matrices mats[B][2*nTips-1][nCat][16] (row = parent state),
  * for substitution models other than HKY (root entry unused). */
 int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,

@@ -63,6 +63,7 @@ ABI = {
     "mtt_peel_set_hky": (C.c_int, [VP, C.c_double]),
     "mtt_peel_logl_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_batch_params": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP]),
+    "mtt_peel_logl_batch_rates": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP]),
     "mtt_peel_logl_batch_mats": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_parts_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),

@@ -56,6 +56,7 @@ struct mtt_peel {
     double *dLogL = nullptr; size_t logLCap = 0;
     int *dInfo = nullptr; size_t infoCap = 0;   // per tree: max slots used (or -1 = bad tree)
     double *dTreeParams = nullptr; size_t treeParamsCap = 0;   // per tree (kappa, branchRate)
+    double *dNodeRates = nullptr; size_t nodeRatesCap = 0;     // per branch clock rates
     int *dMaxSlots = nullptr;                   // max over the chunk of the above
     int *hMaxSlots = nullptr;                   // pinned host copy
 };
@@ -123,7 +124,8 @@ __device__ __forceinline__ void hky_matrix(double kappa, const double *f, double
 __global__ void __launch_bounds__(PREP_THREADS)
 k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const double *matsInAll,
            const double *site, double branchRate, double kappa, PeelOp *opsAll, double *matsAll,
-           int *info, int *maxSlotsAll, int xl, const double *treeParams)
+           int *info, int *maxSlotsAll, int xl, const double *treeParams,
+           const double *nodeRatesAll)
 {
     extern __shared__ int smi[];
     const int N = 2 * n - 1, nOps = n - 1;
@@ -303,8 +305,11 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
             for (int e = 0; e < 16; e++)
                 T[e] = src[e];
         } else {
-            // TreeLikelihood.traverse [EXT]: jointBranchRate = categoryRate * branchRate
-            const double jointBranchRate = catRates[c] * branchRate;
+            // TreeLikelihood.traverse [EXT]: jointBranchRate = categoryRate * branchRate, the
+            // branch rate being branchRateModel.getRateForBranch(node): one number under a
+            // strict clock, one per branch under a relaxed one
+            const double br = nodeRatesAll ? nodeRatesAll[(size_t)b * N + child] : branchRate;
+            const double jointBranchRate = catRates[c] * br;
             const double distance = (height[v] - height[child]) * jointBranchRate;
             hky_matrix(kappa, freqs, distance, T);
         }
@@ -862,7 +867,7 @@ int launch_peel(mtt_peel *h, long long B, int nSlots, int *nTilesOut, double *pa
 int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeight,
                const double *dMatsIn, double *dLogL, double *patternLogL,
                const double *dTreeParams = nullptr, double *dParts = nullptr,
-               long long partsStride = 0)
+               long long partsStride = 0, const double *dNodeRates = nullptr)
 {
     mtt_ctx *ctx = h->ctx;
     const int n = h->nTips, C = h->nCat, N = 2 * n - 1, nOps = n - 1;
@@ -890,7 +895,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
     MTT_CUDA(ctx, cudaMemsetAsync(h->dMaxSlots, 0, sizeof(int), ctx->stream));
     k2_prepare<<<(unsigned)B, PREP_THREADS, prepSmem, ctx->stream>>>(
         n, C, dParent, dHeight, dMatsIn, h->dSite, h->branchRate, h->kappa, (PeelOp *)h->dOps,
-        h->dMats, h->dInfo, h->dMaxSlots, cats_across_lanes(C) ? 1 : 0, dTreeParams);
+        h->dMats, h->dInfo, h->dMaxSlots, cats_across_lanes(C) ? 1 : 0, dTreeParams, dNodeRates);
     MTT_CHECK_LAUNCH(ctx);
     // the number of parked partial vectors sizes the peel kernel's shared memory (a few for
     // coalescent-shaped trees, up to floor(log2 n) for balanced ones): read it back
@@ -988,7 +993,7 @@ int mtt_peel_destroy(mtt_peel *h)
     cudaStreamSynchronize(h->ctx->stream);
     void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart, h->dCold,
                     h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots,
-                    h->dTreeParams};
+                    h->dTreeParams, h->dNodeRates};
     if (h->hMaxSlots)
         cudaFreeHost(h->hMaxSlots);
     for (void *p : ptrs)
@@ -1115,7 +1120,7 @@ int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
 static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
                      const double *mats, double *logL, double *patternLogL,
                      const double *kappaPerTree = nullptr, const double *ratePerTree = nullptr,
-                     double *partsHost = nullptr)
+                     double *partsHost = nullptr, const double *nodeRates = nullptr)
 {
     mtt_ctx *ctx = h->ctx;
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -1171,8 +1176,16 @@ static int peel_host(mtt_peel *h, int64_t B, const int32_t *parent, const double
                                      cudaMemcpyHostToDevice));
             dTP = h->dTreeParams;
         }
+        const double *dNR = nullptr;
+        if (nodeRates) {                 // relaxed clock: one rate per branch
+            if ((rc = grow(ctx, h->dNodeRates, h->nodeRatesCap, (size_t)nb * N * 8)) != MTT_OK)
+                return rc;
+            MTT_CUDA(ctx, cudaMemcpyAsync(h->dNodeRates, nodeRates + b0 * N, (size_t)nb * N * 8,
+                                          cudaMemcpyHostToDevice, s));
+            dNR = h->dNodeRates;
+        }
         rc = peel_chunk(h, nb, h->dParent, dH, dM, h->dLogL + b0, dPat, dTP,
-                        dParts ? dParts + b0 : nullptr, (long long)B);
+                        dParts ? dParts + b0 : nullptr, (long long)B, dNR);
         if (rc != MTT_OK)
             return rc;
         // the upload buffers are reused by the next chunk
@@ -1228,6 +1241,20 @@ int mtt_peel_logl_batch_params(mtt_peel *h, int64_t B, const int32_t *parent,
     if (B == 0)
         return MTT_OK;
     return peel_host(h, B, parent, height, nullptr, logL, nullptr, kappa, branchRate);
+}
+
+int mtt_peel_logl_batch_rates(mtt_peel *h, int64_t B, const int32_t *parent, const double *height,
+                              const double *branchRates, double *logL)
+{
+    int rc = check_ready(h, true);
+    if (rc != MTT_OK)
+        return rc;
+    if (B < 0 || !parent || !height || !branchRates || !logL)
+        return mtt_fail(h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_logl_batch_rates: bad arguments");
+    if (B == 0)
+        return MTT_OK;
+    return peel_host(h, B, parent, height, nullptr, logL, nullptr, nullptr, nullptr, nullptr,
+                     branchRates);
 }
 
 int mtt_peel_logl_batch_mats(mtt_peel *h, int64_t B, const int32_t *parent, const double *mats,

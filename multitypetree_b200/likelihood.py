@@ -206,6 +206,22 @@ class TreeLikelihood:
             self._h, B, _lib.ptr(par), _lib.ptr(h), _lib.ptr(kap), _lib.ptr(rate), _lib.ptr(out)))
         return out
 
+    def calculateLogPBatchRates(self, parent: np.ndarray, height: np.ndarray,
+                                branchRates: np.ndarray) -> np.ndarray:
+        """Relaxed clock: branchRates[B][2*nTips-1] = branchRateModel.getRateForBranch(node) for
+        the branch above every node (mtt_peel_logl_batch_rates); replaces the strict-clock
+        rate of the handle."""
+        par = _lib.as_c(parent, np.int32)
+        h = _lib.as_c(height, np.float64)
+        r = _lib.as_c(branchRates, np.float64)
+        if r.shape != h.shape:
+            raise ValueError("branchRates must have the shape of height")
+        B = par.shape[0]
+        out = np.empty(B, np.float64)
+        self.ctx.check(_lib.lib().mtt_peel_logl_batch_rates(self._h, B, _lib.ptr(par), _lib.ptr(h),
+                                                            _lib.ptr(r), _lib.ptr(out)))
+        return out
+
     def calculateLogPBatchMats(self, parent: np.ndarray, mats: np.ndarray) -> np.ndarray:
         """Explicit transition matrices mats[B][2n-1][nCat][16] (any substitution model)."""
         par = _lib.as_c(parent, np.int32)

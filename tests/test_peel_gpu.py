@@ -268,6 +268,39 @@ def test_pattern_shards_sum_to_whole(ctx):
     whole.close()
 
 
+def test_relaxed_clock_branch_rates(ctx):
+    """mtt_peel_logl_batch_rates: one clock rate per branch (UCRelaxedClockModel of
+    fxtemplates/MTTClockModels.xml).  Equal rates reproduce the strict clock bit for bit; random
+    rates agree with the oracle fed the corresponding HKY matrices."""
+    n, B = 40, 6
+    par, hgt, _ = _trees(B, n, seed=12)
+    f = np.array([.15, .35, .3, .2])
+    al = Alignment(states=simulate_alignment(par[0], hgt[0], 600, 2.2, f, 0.1, seed=4, missing=0.05))
+    sm = SiteModel(HKY(2.2, f), mutationRate=0.1, gammaCategoryCount=4, shape=0.7,
+                   proportionInvariant=0.1)
+    strict = TreeLikelihood(data=al, siteModel=sm, branchRateModel=StrictClockModel(1.7), ctx=ctx)
+    base = strict.calculateLogPBatch(par, hgt)
+    assert np.array_equal(strict.calculateLogPBatchRates(par, hgt, np.full(hgt.shape, 1.7)), base)
+    rng = np.random.default_rng(3)
+    rates = rng.lognormal(0.0, 0.5, hgt.shape)
+    got = strict.calculateLogPBatchRates(par, hgt, rates)
+    catRates, props = sm.category_rates_and_proportions()
+    N = 2 * n - 1
+    for b in range(B):
+        mats = np.zeros((N, len(catRates), 16))
+        for v in range(N):
+            if par[b, v] < 0:
+                continue
+            for c, cr in enumerate(catRates):
+                dist = (hgt[b, par[b, v]] - hgt[b, v]) * cr * rates[b, v]
+                mats[v, c] = orc.hky_matrix(2.2, f, dist).ravel()
+        want = orc.tree_likelihood_mats(al.patterns, al.patternWeight, par[b], mats, props, f,
+                                        pInv=0.1)
+        assert got[b] == pytest.approx(want, rel=RTOL)
+    assert np.all(np.abs(got - base) > 1e-3)
+    strict.close()
+
+
 def test_pattern_shards_with_invariant_sites(ctx):
     """pInv > 0 on a tree whose unscaled evaluation underflows for SOME patterns only: the
     choice between BEAST's two evaluations is global, so the shards return both sums

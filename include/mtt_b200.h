@@ -300,6 +300,38 @@ int mtt_peel_logl_parts_batch_dev(mtt_peel *h, int64_t B, const int32_t *parent,
 int mtt_peel_pattern_logl(mtt_peel *h, const int32_t *parent, const double *height,
                           double *patternLogL);
 
+/* Resident chains: incremental peeling.  Replaces what TreeLikelihood [EXT] does between MCMC
+ * steps -- BeerLikelihoodCore keeps two banks of partials per node
+ * (currentPartialsIndex / storedPartialsIndex), TreeLikelihood.traverse recomputes only the
+ * nodes above a dirty one, store() / restore() flip the banks -- for nChains chains that share
+ * the alignment of `h`.  The partials of every internal node of every chain stay in HBM
+ * (nChains x 2 x (nTips-1) x (4 nCat + 1) x patterns x 8 bytes; TOO_LARGE when that does not fit).
+ *   update  evaluates one proposal per chain: parent / height [nChains][2 nTips - 1]; optional
+ *           branchRates (same shape, relaxed clock), kappa[nChains], clockRate[nChains] (NULL =
+ *           the handle's values).  The proposal is compared with the chain's ACCEPTED tree and
+ *           only the internal nodes above a changed branch are recomputed (all of them the first
+ *           time, or when kappa / the strict clock rate / the site model / the alignment changed).
+ *           dirty (optional, [nChains][2 nTips - 1]): the nodes that MAY differ, as
+ *           Node.isDirty() != IS_CLEAN -- only those are compared, which makes a step
+ *           O(dirty x depth) on the host; NULL compares every node.  A node that differs but is
+ *           not flagged is the caller's error, as in BEAST.  logL[nChains]: the proposal's
+ *           log-likelihood (the accepted one where nothing changed; NaN for a malformed tree,
+ *           which leaves the chain untouched).
+ *   accept  accept[k] != 0 (or accept == NULL): the proposal becomes chain k's accepted state
+ *           (BEAST: the next store()); 0: it is dropped (restore()).  A proposal still unanswered
+ *           at the next update counts as rejected.  Host-side only.
+ * Results agree with mtt_peel_logl_batch on the same trees to rounding (the per-pattern log
+ * scale factors are summed per subtree instead of along the traversal).  */
+typedef struct mtt_peel_chains mtt_peel_chains;
+int mtt_peel_chains_create(mtt_peel *h, int nChains, mtt_peel_chains **out);
+int mtt_peel_chains_destroy(mtt_peel_chains *s);
+int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
+                           const double *branchRates, const double *kappa,
+                           const double *clockRate, const uint8_t *dirty, double *logL);
+int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept);
+/* nodes recomputed by the last update, over all chains */
+int64_t mtt_peel_chains_last_entries(const mtt_peel_chains *s);
+
 /* ------------------------------------------------------------------ next row: tree simulation
  * Replaces evolution/tree/StructuredCoalescentMultiTypeTree.java:191-442 (simulateTree,
  * updatePropensities, getNextEvent, updateTree): B structured-coalescent multi-type trees

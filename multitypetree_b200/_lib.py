@@ -69,6 +69,11 @@ ABI = {
     "mtt_peel_logl_parts_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_logl_parts_batch_dev": (C.c_int, [VP, C.c_int64, VP, VP, VP]),
     "mtt_peel_pattern_logl": (C.c_int, [VP, VP, VP, VP]),
+    "mtt_peel_chains_create": (C.c_int, [VP, C.c_int, C.POINTER(VP)]),
+    "mtt_peel_chains_destroy": (C.c_int, [VP]),
+    "mtt_peel_chains_update": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP]),
+    "mtt_peel_chains_accept": (C.c_int, [VP, VP]),
+    "mtt_peel_chains_last_entries": (C.c_int64, [VP]),
     "mtt_sim_trees_create": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP,
                                        C.c_uint64, C.POINTER(VP)]),
     "mtt_sim_trees_destroy": (C.c_int, [VP]),

@@ -27,7 +27,7 @@
 //   k2_finalize fixed-order sum of the per-tile partial sums -> logL[tree].
 // fp64 throughout; rescaling follows BeerLikelihoodCore.scalePartials (threshold 1e-100,
 // always on -- results agree with the unscaled path to rounding whenever that path is finite).
-#include "mtt_common.cuh"
+#include "k2_peel.cuh"
 
 #include <math.h>
 #include <stdlib.h>
@@ -35,35 +35,9 @@
 #include <algorithm>
 #include <vector>
 
-struct mtt_peel {
-    mtt_ctx *ctx = nullptr;
-    int nTips = 0, nCat = 0;
-    long long nPatterns = 0, pStride = 0;      // pStride: padded row length of tipStates
-    uint8_t *dStates = nullptr;                // [nTips][pStride]
-    double *dWeights = nullptr;                // [pStride] (0 beyond nPatterns)
-    uint8_t *dConst = nullptr;                 // [pStride] bit k: pattern constant for state k
-    double *dSite = nullptr;                   // catRates[C] | catProps[C] | freqs[4]
-    double pInv = 0.0, branchRate = 1.0, kappa = 1.0;
-    bool haveStates = false, haveWeights = false, haveSite = false, haveHky = false;
-    // per-call scratch (grow only)
-    void *dOps = nullptr; size_t opsCap = 0;
-    double *dMats = nullptr; size_t matsCap = 0;
-    double *dPart = nullptr; size_t partCap = 0;
-    double *dCold = nullptr; size_t coldCap = 0;   // parked vectors beyond the shared-memory slots
-    int *dParent = nullptr; size_t parentCap = 0;
-    double *dHeight = nullptr; size_t heightCap = 0;
-    double *dMatsIn = nullptr; size_t matsInCap = 0;
-    double *dLogL = nullptr; size_t logLCap = 0;
-    int *dInfo = nullptr; size_t infoCap = 0;   // per tree: max slots used (or -1 = bad tree)
-    double *dTreeParams = nullptr; size_t treeParamsCap = 0;   // per tree (kappa, branchRate)
-    double *dNodeRates = nullptr; size_t nodeRatesCap = 0;     // per branch clock rates
-    int *dMaxSlots = nullptr;                   // max over the chunk of the above
-    int *hMaxSlots = nullptr;                   // pinned host copy
-};
-
 namespace {
 
-constexpr int TP = 256;                 // pattern padding granule (largest tile: 128 threads x 2)
+constexpr int TP = MTT_PEEL_TP;
 constexpr int PREP_THREADS = 256;
 constexpr int MAX_SLOTS = 24;
 
@@ -74,40 +48,6 @@ struct PeelOp {
                     // registers); bit 2: this result must be parked in its slot
 };
 constexpr int OP_C1_PREV = 1, OP_STORE = 4;
-
-// ---- HKY.getTransitionProbabilities [EXT] (closed form) ---------------
-__device__ __forceinline__ void hky_matrix(double kappa, const double *f, double distance,
-                                           double *matrix)
-{
-    const double freqA = f[0], freqC = f[1], freqG = f[2], freqT = f[3];
-    const double freqR = freqA + freqG, freqY = freqC + freqT;
-    const double tab1A = freqA * ((1 / freqR) - 1), tab3A = freqA / freqR, tab2A = 1 - tab3A;
-    const double tab1C = freqC * ((1 / freqY) - 1), tab3C = freqC / freqY, tab2C = 1 - tab3C;
-    const double tab1G = freqG * ((1 / freqR) - 1), tab3G = tab2A, tab2G = tab3A;
-    const double tab1T = freqT * ((1 / freqY) - 1), tab3T = tab2C, tab2T = tab3C;
-    const double beta = -1.0 / (2.0 * (freqR * freqY + kappa * (freqA * freqG + freqC * freqT)));
-    const double A_R = 1.0 + freqR * (kappa - 1), A_Y = 1.0 + freqY * (kappa - 1);
-    const double xx = beta * distance;
-    const double bbR = exp(xx * A_R), bbY = exp(xx * A_Y), aa = exp(xx);
-    const double oneminusa = 1 - aa;
-    const double t1Aaa = tab1A * aa, t1Gaa = tab1G * aa, t1Caa = tab1C * aa, t1Taa = tab1T * aa;
-    matrix[0] = freqA + t1Aaa + (tab2A * bbR);
-    matrix[1] = freqC * oneminusa;
-    matrix[2] = freqG + t1Gaa - (tab3G * bbR);
-    matrix[3] = freqT * oneminusa;
-    matrix[4] = freqA * oneminusa;
-    matrix[5] = freqC + t1Caa + (tab2C * bbY);
-    matrix[6] = freqG * oneminusa;
-    matrix[7] = freqT + t1Taa - (tab3T * bbY);
-    matrix[8] = freqA + t1Aaa - (tab3A * bbR);
-    matrix[9] = matrix[1];
-    matrix[10] = freqG + t1Gaa + (tab2G * bbR);
-    matrix[11] = matrix[3];
-    matrix[12] = matrix[4];
-    matrix[13] = freqC + t1Caa - (tab3C * bbY);
-    matrix[14] = matrix[6];
-    matrix[15] = freqT + t1Taa + (tab2T * bbY);
-}
 
 // ---- k2_prepare ------------------------------------------------------------------------
 // One CTA per tree; every step is parallel over nodes (level-synchronous sweeps; the number of
@@ -335,7 +275,6 @@ k2_prepare(int n, int C, const int *parentAll, const double *heightAll, const do
 }
 
 // ---- k2_peel ---------------------------------------------------------------------------
-constexpr double SCALING_THRESHOLD = 1.0E-100;     // BeerLikelihoodCore.scalingThreshold
 
 template <int C>
 struct PeelCfg {
@@ -345,64 +284,6 @@ struct PeelCfg {
     static constexpr int MAT_DOUBLES_PER_OP = 2 * C * 16;
     static constexpr int STAGE_BYTES = OPS_PER_STAGE * (16 + MAT_DOUBLES_PER_OP * 8);
 };
-
-// one child's contribution for PPT patterns of one category:
-//   a[u][i] = sum_j M[i][j] x[u][j]      (internal child; x from registers or its slot)
-//   a[u][i] = M[i][state_u] or 1         (tip child)
-// MS = distance in doubles between consecutive double2 of the matrix (2, or 2 C when the
-// categories' matrices are interleaved).
-template <int PPT, int MS>
-__device__ __forceinline__ void child_term(bool isTip, const double *M, const double (&x)[PPT][4],
-                                           const int (&tip)[PPT], double (&a)[PPT][4])
-{
-    if (isTip) {
-        // M is transposed for tip children: column of the observed state = M[4 s .. 4 s + 3].
-        // Gaps / ambiguity codes (state >= 4) contribute 1; a warp without any takes the
-        // select-free path (isTip is uniform over the CTA, so the vote is convergent).
-        bool unknown = false;
-#pragma unroll
-        for (int u = 0; u < PPT; u++)
-            unknown |= tip[u] >= 4;
-        if (!__any_sync(FULL_MASK, unknown)) {
-#pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                const double *col = M + tip[u] * 2 * MS;
-                const double2 c01 = *reinterpret_cast<const double2 *>(col);
-                const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
-                a[u][0] = c01.x;
-                a[u][1] = c01.y;
-                a[u][2] = c23.x;
-                a[u][3] = c23.y;
-            }
-        } else {
-#pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                const bool known = tip[u] < 4;                      // gap / ambiguity: unknown
-                const double *col = M + (known ? tip[u] * 2 * MS : 0);
-                const double2 c01 = *reinterpret_cast<const double2 *>(col);
-                const double2 c23 = *reinterpret_cast<const double2 *>(col + MS);
-                a[u][0] = known ? c01.x : 1.0;
-                a[u][1] = known ? c01.y : 1.0;
-                a[u][2] = known ? c23.x : 1.0;
-                a[u][3] = known ? c23.y : 1.0;
-            }
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const double2 m01 = *reinterpret_cast<const double2 *>(M + i * 2 * MS);
-            const double2 m23 = *reinterpret_cast<const double2 *>(M + i * 2 * MS + MS);
-#pragma unroll
-            for (int u = 0; u < PPT; u++) {
-                double s = m01.x * x[u][0];
-                s += m01.y * x[u][1];
-                s += m23.x * x[u][2];
-                s += m23.y * x[u][3];
-                a[u][i] = s;
-            }
-        }
-    }
-}
 
 // rate categories across lanes: C = 2, 4, 8
 __host__ __device__ constexpr bool cats_across_lanes(int C)
@@ -656,49 +537,9 @@ k2_peel(int n, long long P, long long pStride, const uint8_t *states, const doub
             }
             root[i] = r;
         }
-        // Proportion invariant (TreeLikelihood.calculateLogP [EXT]): pInv is added to the root
-        // partials of constant patterns.  BEAST evaluates WITHOUT rescaling first and only
-        // repeats the evaluation with rescaling when that returned -infinity; in the rescaled
-        // pass it still adds pInv to the (now rescaled) root partials.  Both values are formed:
-        //   llU  the unscaled pass, computed safely: pInv enters at the root's scale, e^-logScale
-        //   llQ  the rescaled pass, literally (root + pInv, then + logScale)
-        // together with "would the unscaled pass have underflowed to log(0) here"; k2_finalize
-        // picks the sum BEAST would have returned.  The two agree whenever no rescaling
-        // happened on the way to the root (logScale == 0) or pInv == 0.
-        double sumU = 0.0, sumQ = 0.0, offsU = logScale[u];
-        bool hasInv = false;
-        if (pInv > 0.0) {
-            const int cm = constMask[p];
-            hasInv = cm != 0;
-            // pInv at the root's scale; far below the double range the root is scaled down
-            // instead (it underflows gracefully, as it does in BEAST's unscaled pass)
-            double invU = pInv, rootMul = 1.0;
-            offsU = logScale[u];
-            if (hasInv && offsU != 0.0) {
-                if (offsU > -300.0) {
-                    invU = pInv * exp(-offsU);
-                } else {
-                    rootMul = exp(offsU);
-                    offsU = 0.0;
-                }
-            }
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const bool on = cm & (1 << i);
-                const double r = root[i] * rootMul;
-                sumU += freqs[i] * (on ? r + invU : r);
-                sumQ += freqs[i] * (on ? root[i] + pInv : root[i]);
-            }
-        } else {
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                sumU += freqs[i] * root[i];
-            sumQ = sumU;
-        }
-        const double llU = log(sumU) + offsU;
-        const double llQ = (sumQ == sumU && offsU == logScale[u]) ? llU : log(sumQ) + logScale[u];
-        // log of the smallest subnormal: below it the unscaled root sum is exactly 0
-        const bool under = !hasInv && !(llU >= -744.4400719213812);
+        double llU, llQ;
+        bool under;
+        root_pattern_logl(root, logScale[u], pInv, constMask, p, freqs, llU, llQ, under);
         if (patternLogL && p < P && cat == 0) {
             patternLogL[p] = llU;
             patternLogL[pStride + p] = llQ;
@@ -785,23 +626,6 @@ __global__ void k2_const_mask(int n, long long P, long long pStride, const uint8
                 m &= (1 << s);
         }
     mask[p] = (uint8_t)m;
-}
-
-template <typename T>
-int grow(mtt_ctx *ctx, T *&ptr, size_t &cap, size_t bytes)
-{
-    if (bytes + 256 <= cap)
-        return MTT_OK;
-    if (ptr) {
-        MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-        cudaFree(ptr);
-        ptr = nullptr;
-        cap = 0;
-    }
-    size_t want = bytes + bytes / 8 + 4096;
-    MTT_CUDA(ctx, cudaMalloc((void **)&ptr, want));
-    cap = want;
-    return MTT_OK;
 }
 
 template <int C, int TPT, int PPT>
@@ -951,6 +775,21 @@ int check_ready(mtt_peel *h, bool needHky)
 
 }  // namespace
 
+int k2_check_ready(mtt_peel *h, bool needHky)
+{
+    return check_ready(h, needHky);
+}
+
+int k2_run_finalize(mtt_peel *h, long long B, int nTiles, const double *partial, double *logL,
+                    int *mode, double *parts, long long partsStride)
+{
+    mtt_ctx *ctx = h->ctx;
+    k2_finalize<<<(unsigned)((B + 127) / 128), 128, 0, ctx->stream>>>(B, nTiles, partial, logL,
+                                                                      mode, parts, partsStride);
+    MTT_CHECK_LAUNCH(ctx);
+    return MTT_OK;
+}
+
 extern "C" {
 
 int mtt_peel_create(mtt_ctx *ctx, int nTips, int64_t nPatterns, int nCat, mtt_peel **out)
@@ -1023,6 +862,7 @@ int mtt_peel_set_tip_states(mtt_peel *h, const int32_t *states)
     MTT_CHECK_LAUNCH(ctx);
     MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h->haveStates = true;
+    h->version++;
     return MTT_OK;
 }
 
@@ -1039,6 +879,7 @@ int mtt_peel_set_pattern_weights(mtt_peel *h, const int32_t *weights)
                                   ctx->stream));
     MTT_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
     h->haveWeights = true;
+    h->version++;
     return MTT_OK;
 }
 
@@ -1062,6 +903,7 @@ int mtt_peel_set_site_model(mtt_peel *h, const double *catRates, const double *c
     h->pInv = pInv;
     h->branchRate = branchRate;
     h->haveSite = true;
+    h->version++;
     return MTT_OK;
 }
 
@@ -1071,6 +913,7 @@ int mtt_peel_set_hky(mtt_peel *h, double kappa)
         return MTT_ERR_INVALID_ARG;
     h->kappa = kappa;
     h->haveHky = true;
+    h->version++;
     return MTT_OK;
 }
 

@@ -240,6 +240,10 @@ class TreeLikelihood:
             _lib.ptr(_lib.as_c(t.height, np.float64)), _lib.ptr(out)))
         return out
 
+    def chains(self, nChains: int) -> "PeelChains":
+        """Resident chains with incremental updates over this handle's alignment."""
+        return PeelChains(self, nChains)
+
     @property
     def handle(self):
         return self._h
@@ -248,6 +252,69 @@ class TreeLikelihood:
         if self._h:
             _lib.lib().mtt_peel_destroy(self._h)
             self._h = _lib.VP()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class PeelChains:
+    """What BEAST's ``TreeLikelihood`` does between MCMC steps (dirty-node updates of the
+    partials ``BeerLikelihoodCore`` keeps per node, ``store`` / ``restore``), for ``nChains``
+    chains at once: the partials of every chain stay in HBM, ``update`` evaluates one proposal per
+    chain by recomputing only the nodes above what changed, ``accept`` keeps or drops the
+    proposals (mtt_peel_chains_*)."""
+
+    def __init__(self, likelihood: TreeLikelihood, nChains: int):
+        self.likelihood, self.ctx, self.nChains = likelihood, likelihood.ctx, int(nChains)
+        self._s = _lib.VP()
+        self.ctx.check(_lib.lib().mtt_peel_chains_create(likelihood.handle, self.nChains,
+                                                         C.byref(self._s)))
+
+    def update(self, parent: np.ndarray, height: np.ndarray, branchRates=None, kappa=None,
+               clockRate=None, dirty=None) -> np.ndarray:
+        """parent/height [nChains][2*nTips-1] of the proposals -> logL[nChains].  `dirty`
+        (optional, same shape, nonzero = the node may differ from the chain's accepted tree,
+        ``Node.isDirty()``) restricts the comparison to the flagged nodes."""
+        K = self.nChains
+        par = _lib.as_c(parent, np.int32)
+        h = _lib.as_c(height, np.float64)
+        if par.shape != h.shape or par.shape[0] != K:
+            raise ValueError("parent/height must be [nChains][2*nTips-1]")
+        r = None if branchRates is None else _lib.as_c(branchRates, np.float64)
+        if r is not None and r.shape != h.shape:
+            raise ValueError("branchRates must have the shape of height")
+        kap = None if kappa is None else _lib.as_c(
+            np.broadcast_to(np.asarray(kappa, np.float64), (K,)), np.float64)
+        clk = None if clockRate is None else _lib.as_c(
+            np.broadcast_to(np.asarray(clockRate, np.float64), (K,)), np.float64)
+        d = None if dirty is None else _lib.as_c(np.asarray(dirty) != 0, np.uint8)
+        if d is not None and d.shape != h.shape:
+            raise ValueError("dirty must have the shape of height")
+        out = np.empty(K, np.float64)
+        self.ctx.check(_lib.lib().mtt_peel_chains_update(
+            self._s, _lib.ptr(par), _lib.ptr(h), _lib.ptr(r), _lib.ptr(kap), _lib.ptr(clk),
+            _lib.ptr(d), _lib.ptr(out)))
+        return out
+
+    def accept(self, mask=None) -> None:
+        """mask[nChains] (None = all): nonzero keeps the chain's proposal, zero drops it."""
+        m = None if mask is None else _lib.as_c(np.asarray(mask) != 0, np.uint8)
+        if m is not None and m.shape != (self.nChains,):
+            raise ValueError("mask must be [nChains]")
+        self.ctx.check(_lib.lib().mtt_peel_chains_accept(self._s, _lib.ptr(m)))
+
+    @property
+    def last_entries(self) -> int:
+        """Internal nodes recomputed by the last update, over all chains."""
+        return int(_lib.lib().mtt_peel_chains_last_entries(self._s))
+
+    def close(self):
+        if self._s:
+            _lib.lib().mtt_peel_chains_destroy(self._s)
+            self._s = _lib.VP()
 
     def __del__(self):
         try:

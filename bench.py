@@ -509,6 +509,129 @@ def bench_peel(args):
         "parity_max_rel_err_vs_oracle": rel}))
 
 
+def bench_peel_chains(args):
+    """cfg3 shape, MCMC regime: 64 resident chains, one node-height proposal per chain and step
+    (MultiTypeUniform), incremental peeling (mtt_peel_chains_update) + accept / reject, against a
+    full re-evaluation of the same proposals (mtt_peel_logl_batch).  Host-buffer API on both
+    sides: the planner's host time is part of the number."""
+    import torch
+    import multitypetree_b200 as mtt
+    from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, TreeLikelihood,
+                                               simulate_alignment)
+    world, rank, local = dist_setup(args.gpus)
+    cores = os.cpu_count() or 1
+    n = args.tips or 1000
+    d, sites = 4, args.sites or 10000
+    K = args.batch if args.batch != (1 << 19) else 64
+    m, N = mtt.synthetic_model(d)
+    tb = mtt.simulate_trees(K, n, d, m, N, seed=3000 + rank * K, nThreads=max(1, cores // world))
+    nN = 2 * n - 1
+    par, hgt = tb.parent.reshape(K, nN).copy(), tb.height.reshape(K, nN).copy()
+    f = np.array([.25] * 4)
+    ref = mtt.simulate_trees(1, n, d, m, N, seed=3000)
+    clock = 0.2 / float(ref.height.max())
+    al = Alignment(states=simulate_alignment(ref.parent, ref.height, sites, 2.0, f, clock, seed=3000))
+    P = al.getPatternCount()
+    ctx = mtt.Context(local)
+    stream = torch.cuda.Stream()
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f), mutationRate=clock), ctx=ctx)
+    ch = tl.chains(K)
+    # children of every node (the topology does not change in this workload)
+    kids = np.full((K, nN, 2), -1, np.int64)
+    for k in range(K):
+        order = np.argsort(par[k], kind="stable")
+        order = order[par[k][order] >= 0]
+        kids[k, par[k][order][0::2], 0] = order[0::2]
+        kids[k, par[k][order][1::2], 1] = order[1::2]
+    rows = np.arange(K)
+    rng = np.random.default_rng(3000 + rank)
+
+    def propose():
+        v = rng.integers(n, nN, K)
+        lo = np.maximum(hgt[rows, kids[rows, v, 0]], hgt[rows, kids[rows, v, 1]])
+        pp = par[rows, v]
+        hi = np.where(pp >= 0, hgt[rows, np.maximum(pp, 0)], lo + 1.0)
+        ph = hgt.copy()
+        ph[rows, v] = lo + (hi - lo) * rng.uniform(0.05, 0.95, K)
+        dirty = np.zeros((K, nN), np.uint8)
+        dirty[rows, v] = 1
+        return ph, dirty
+
+    first = ch.update(par, hgt)
+    ch.accept()
+    full0 = tl.calculateLogPBatch(par, hgt)
+    t_upd = t_full = dev_ms = 0.0
+    entries = dev_entries = 0
+    err = 0.0
+    launches = 0
+    # pass 1 (warm-up + timed steps): throughput through the host API; pass 2 (as many steps
+    # again): the same with the library's CUDA events around its launch, for the device time --
+    # reading the events back costs host time, so it is not part of pass 1
+    with ClockSampler(local) as clk:
+        for it in range(args.warmup + 2 * args.steps):
+            ph, dirty = propose()
+            timed = args.warmup <= it < args.warmup + args.steps
+            if it == args.warmup + args.steps:
+                ch.set_timing(True)
+            acc = rng.random(K) < 0.5
+            lf0 = ctx.launch_count()
+            t0 = time.perf_counter()
+            got = ch.update(par, ph, dirty=dirty)
+            ch.accept(acc)
+            dt = time.perf_counter() - t0
+            if timed:
+                t_upd += dt
+                entries += ch.last_entries
+                launches += ctx.launch_count() - lf0        # (not the comparison's below)
+            elif it >= args.warmup + args.steps:
+                dev_ms += ch.last_device_ms
+                dev_entries += ch.last_entries
+            t0 = time.perf_counter()
+            want = tl.calculateLogPBatch(par, ph)
+            if timed:
+                t_full += time.perf_counter() - t0
+            err = max(err, float(np.max(np.abs(got - want) / np.abs(want))))
+            hgt[acc] = ph[acc]
+    barrier(world)
+    t_upd = max_over_ranks(t_upd * 1e3, world) / 1e3
+    if rank != 0:
+        return
+    steps = args.steps
+    C = 1
+    stride = (P + 255) // 256 * 256
+    alg = dev_entries * stride * 2.0 * (32 * C + 8)     # one vector read + one written per entry
+    hbm, src = peaks()
+    print(json.dumps({
+        "metric": "cfg3 MCMC regime: proposals evaluated/s (incremental peeling, resident chains)",
+        "value": K * world * steps / t_upd, "unit": "chain-steps/s", "n_gpus": world,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": t_upd / steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": "cfg3 shape: %d chains x %d-tip trees x %d patterns, one node-height "
+                               "proposal per chain and step, accept with probability 1/2"
+                               % (K, n, P), "chains_per_gpu": K,
+                   "nodes_recomputed_per_proposal": entries / (K * steps),
+                   "resident_bytes": int(K) * 2 * (n - 1) * (4 * C + 1) * stride * 8},
+        "roofline": {"bound": "hbm", "achieved": alg / (dev_ms * 1e-3) / 1e9 if dev_ms else None,
+                     "peak": hbm, "unit": "GB/s",
+                     "frac": alg / (dev_ms * 1e-3) / 1e9 / hbm if dev_ms else None,
+                     "traffic": None, "peak_source": src, "kernel": "k2_peel_update",
+                     "device_ms_per_step": dev_ms / steps,
+                     "note": "CUDA events around the launch of every update of a second pass of "
+                             "%d steps; algorithmic bytes = (32 C + 8) read + written per pattern "
+                             "and recomputed node" % steps},
+        "full_reevaluation": {"value": K * steps / t_full, "unit": "chain-steps/s",
+                              "note": "mtt_peel_logl_batch on the same proposals, host buffers"},
+        "e2e": {"value": K * world * steps / t_upd, "unit": "chain-steps/s",
+                "h2d_bytes_per_step": int(entries / steps * 80 + 4 * (2 * K + 1) + 8 * K),
+                "d2h_bytes_per_step": int(8 * K),
+                "note": "the API takes host buffers: value is already end to end"},
+        "gpu_launches": int(launches), "clocks": clk.summary(),
+        "parity_max_rel_err_vs_full": err}))
+
+
 def bench_peel_sharded(args):
     """cfg4 shape: 8-deme 5000-tip trees, site patterns sharded across ranks (125k patterns per
     GPU = 1M over 8 GPUs), per-rank partial logL combined with one NCCL all-reduce."""
@@ -736,7 +859,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_sharded", "retype", "untyped"])
+    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_chains", "peel_sharded", "retype", "untyped"])
     ap.add_argument("--tips", type=int, default=0)
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--batch", type=int, default=1 << 19, help="trees per GPU per step")
@@ -746,6 +869,8 @@ def main():
         return bench_reference(args)
     if args.workload == "peel":
         return bench_peel(args)
+    if args.workload == "peel_chains":
+        return bench_peel_chains(args)
     if args.workload == "peel_sharded":
         return bench_peel_sharded(args)
     if args.workload == "retype":

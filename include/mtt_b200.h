@@ -331,6 +331,10 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
 int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept);
 /* nodes recomputed by the last update, over all chains */
 int64_t mtt_peel_chains_last_entries(const mtt_peel_chains *s);
+/* measurement: bracket the kernel launches of every update with CUDA events on the ctx stream;
+ * last_device_ms = the last update's device time (0 when nothing was launched) */
+int mtt_peel_chains_set_timing(mtt_peel_chains *s, int on);
+double mtt_peel_chains_last_device_ms(const mtt_peel_chains *s);
 
 /* ------------------------------------------------------------------ next row: tree simulation
  * Replaces evolution/tree/StructuredCoalescentMultiTypeTree.java:191-442 (simulateTree,

@@ -830,6 +830,8 @@ int mtt_peel_destroy(mtt_peel *h)
         return MTT_OK;
     cudaSetDevice(h->ctx->device);
     cudaStreamSynchronize(h->ctx->stream);
+    for (mtt_peel_chains *c : h->chains)
+        k2_chains_release(c);               // chains that outlive their handle lose the device side
     void *ptrs[] = {h->dStates, h->dWeights, h->dConst, h->dSite, h->dOps, h->dMats, h->dPart, h->dCold,
                     h->dParent, h->dHeight, h->dMatsIn, h->dLogL, h->dInfo, h->dMaxSlots,
                     h->dTreeParams, h->dNodeRates};

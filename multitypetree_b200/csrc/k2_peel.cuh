@@ -3,6 +3,9 @@
 #pragma once
 #include "mtt_common.cuh"
 
+struct mtt_peel_chains;
+void k2_chains_release(mtt_peel_chains *s);      // k2_update.cu
+
 struct mtt_peel {
     mtt_ctx *ctx = nullptr;
     int nTips = 0, nCat = 0;
@@ -14,6 +17,7 @@ struct mtt_peel {
     double pInv = 0.0, branchRate = 1.0, kappa = 1.0;
     bool haveStates = false, haveWeights = false, haveSite = false, haveHky = false;
     long long version = 0;                     // bumped by every setter (resident chains go stale)
+    std::vector<mtt_peel_chains *> chains;     // resident chains built on this handle
     // per-call scratch (grow only)
     void *dOps = nullptr; size_t opsCap = 0;
     double *dMats = nullptr; size_t matsCap = 0;

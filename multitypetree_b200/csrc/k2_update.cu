@@ -13,15 +13,20 @@
 //                    flags dirty -- plus kappa and the strict-clock rate), applied in place under
 //                    an undo journal, and the nodes to recompute are listed in post-order: the
 //                    union of the paths from the changes to the root.  O(changes x depth).
-//   k2_update_mats   transition matrices of the two child branches of every listed node (the
-//                    closed form of k2_prepare, same argument order: bit-identical matrices).
-//   k2_peel_update   grid = (pattern tiles, chains), a thread owns one pattern column.  A CTA
-//                    walks its chain's list; the child that is the previous entry's result stays
-//                    in registers (on a path to the root that is every entry but the first), the
-//                    other child is read from its resident vector -- fetched one entry ahead --
-//                    or from the tip states; every result is written to the bank the accepted
-//                    state does not use.  Per-node rescaling as in k2_peel, the log scale factor
-//                    kept CUMULATIVE per subtree (row 4 C), so the root needs no sum over nodes.
+//   k2_peel_update   the one kernel of an update; grid = (pattern tiles, chains with a list, the
+//                    longest lists first), a thread owns one pattern column.  A CTA walks its
+//                    chain's list in stages of 16 entries: the entries arrive by asynchronous
+//                    copies one stage ahead, the transition matrices of their child branches are
+//                    evaluated into shared memory from the entries (the closed form of
+//                    k2_prepare, same argument order: bit-identical matrices).  The child that is
+//                    the previous entry's result stays in registers (on a path to the root that
+//                    is every entry but the first); the other child is read from its resident
+//                    vector -- its lines pulled into L2 for the whole stage up front, the
+//                    registers filled one entry ahead -- or from the tip states; every result is
+//                    written to the bank the accepted state does not use.  Per-node rescaling as
+//                    in k2_peel, the log scale factor kept CUMULATIVE per subtree (row 4 C), so
+//                    the root needs no sum over nodes.  The chain's last tile to finish adds the
+//                    tile sums up in tile order (what k2_finalize does).
 //                    HBM-bound: (32 C + 8) bytes read + as many written per pattern and entry.
 //   accept / reject  host-side: the proposal's banks, tree and logL become the accepted ones, or
 //                    are forgotten.  No device work.
@@ -35,23 +40,34 @@
 
 namespace {
 
-struct UpdOp {          // 48 bytes
+struct UpdOp {          // 80 bytes
     int v;              // node recomputed (>= nTips)
     int c1, c2;         // children (node numbers); c1 is the previous entry's node when bit 0 is set
-    int flags;          // bit 0: child 1 = previous result; bit 1: bank written; bits 2, 3: banks of
-                        // child 1, child 2 (internal, resident); bits 8..: chain
+    int flags;          // bit 0: child 1 = previous result; bits 8..: chain
     double dh1, dh2;    // height(v) - height(child)
     double br1, br2;    // clock rate of the child branches
+    // offsets (in doubles, row 0, pattern 0) into the resident store: the vector written -- in
+    // the bank the accepted state does not use -- and the vectors of internal children
+    long long dstOff, c1Off, c2Off;
+    long long pad;
 };
-constexpr int UF_PREV = 1, UF_DST_BANK = 2, UF_C1_BANK = 4, UF_C2_BANK = 8;
+static_assert(sizeof(UpdOp) == 80, "UpdOp is staged by 16-byte copies");
+constexpr int UF_PREV = 1;
 
 // Host-side state of one chain: the ACCEPTED tree (with child lists and the bank every internal
 // node's accepted partials sit in), modified in place by a proposal under an undo journal, so a
 // step costs O(changed nodes x depth), not O(nodes).
 struct Chain {
-    std::vector<int> parent, left, right, mark, walk;
-    std::vector<double> height, rate;
-    std::vector<uint8_t> bank;          // per internal node
+    // everything the planner asks about a node sits in one 40-byte record: a step of a walk to
+    // the root or an entry of the list touches one or two cache lines, not eight arrays
+    struct Node {
+        int parent = -2;                // -2: no tree yet
+        int left = -1, right = -1;
+        int mark = 0, walk = 0;         // epoch / walk that reached the node (plan_chain)
+        int bank = 0;                   // bank of the accepted partials (internal nodes)
+        double height = 0.0, rate = 0.0;
+    };
+    std::vector<Node> nd;
     int root = -1, rootCount = 0, epoch = 0, walkId = 0;
     double kappa = 0.0, clock = 0.0, logL = 0.0;
     bool valid = false, pending = false;
@@ -78,20 +94,20 @@ struct Chain {
         oldValid = valid;
         pending = true;
     }
-    void undo(int n)
+    void undo()
     {
         for (size_t i = undoKids.size(); i-- > 0;) {
-            left[undoKids[i].node] = undoKids[i].left;
-            right[undoKids[i].node] = undoKids[i].right;
+            nd[undoKids[i].node].left = undoKids[i].left;
+            nd[undoKids[i].node].right = undoKids[i].right;
         }
         for (size_t i = undoNodes.size(); i-- > 0;) {
             const NodeUndo &u = undoNodes[i];
-            parent[u.node] = u.parent;
-            height[u.node] = u.height;
-            rate[u.node] = u.rate;
+            nd[u.node].parent = u.parent;
+            nd[u.node].height = u.height;
+            nd[u.node].rate = u.rate;
         }
         for (int v : flipped)
-            bank[v - n] ^= 1;
+            nd[v].bank ^= 1;
         root = oldRoot;
         rootCount = oldRootCount;
         kappa = oldKappa;
@@ -119,66 +135,108 @@ struct mtt_peel_chains {
     int K = 0;
     long long version = -1;             // h->version the accepted states were computed under
     double *dStore = nullptr;           // resident partials
-    double *dMats = nullptr; size_t matsCap = 0;
-    double *dPart = nullptr; size_t partCap = 0;
+    double *dPart = nullptr; size_t partCap = 0;     // tile sums [chain][tile][3]
+    int *dDone = nullptr;               // tiles finished per chain (self-resetting)
     std::vector<Chain> chains;
     // planner scratch
     std::vector<UpdOp> ops;
-    std::vector<int> opOff, stack;
+    std::vector<int> opOff, stack, order;
     long long lastOps = 0;
+    // optional device timing of the launches of an update (mtt_peel_chains_set_timing)
+    bool timing = false;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    float lastMs = 0.0f;
 };
 
 namespace {
 
-// transition matrices of the listed nodes: [entry][child][category][16]; internal child row-major,
-// tip child transposed (child_term)
-__global__ void k2_update_mats(int n, int C, long long nEntries, const UpdOp *ops,
-                               const double *kappaPerChain, const double *site, double *mats)
-{
-    const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    if (idx >= nEntries * 2 * C)
-        return;
-    const long long k = idx / (2 * C);
-    const int j = (int)(idx / C) & 1, c = (int)(idx % C);
-    const UpdOp op = ops[k];
-    const double *catRates = site, *freqs = site + 2 * C;
-    const int child = j ? op.c2 : op.c1;
-    const double jointBranchRate = catRates[c] * (j ? op.br2 : op.br1);
-    const double distance = (j ? op.dh2 : op.dh1) * jointBranchRate;
-    double T[16];
-    hky_matrix(kappaPerChain[op.flags >> 8], freqs, distance, T);
-    double *M = mats + ((size_t)(k * 2 + j) * C + c) * 16;
-    const bool tip = child < n;
-#pragma unroll
-    for (int e = 0; e < 16; e++)
-        M[e] = tip ? T[(e & 3) * 4 + (e >> 2)] : T[e];
-}
-
 constexpr int UPD_THREADS = 128;
 
+__device__ __forceinline__ void cp_async16(void *dst, const void *src)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit()
+{
+    asm volatile("cp.async.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
+// entries per stage: list entries + their matrices go through shared memory, double-buffered
+__host__ __device__ constexpr int upd_stage_entries(int C)
+{
+    return C <= 2 ? 16 : (C <= 4 ? 8 : 4);
+}
+
 template <int C>
-__global__ void __launch_bounds__(UPD_THREADS)
+#ifndef MTT_K2U_MINB
+#define MTT_K2U_MINB 6
+#endif
+__global__ void __launch_bounds__(UPD_THREADS, C == 1 ? MTT_K2U_MINB : 1)
 k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
                const double *weights, const uint8_t *constMask, const double *site, double pInv,
-               const UpdOp *ops, const int *opOff, const double *mats, double *store,
-               double *partial, int nTiles)
+               const UpdOp *ops, const int *opOff, const int *chainOrder,
+               const double *kappaPerChain, double *store, double *partial, int nTiles,
+               int *tilesDone, double *logL)
 {
+    constexpr int CH = upd_stage_entries(C);
+    constexpr int OPB = (int)sizeof(UpdOp), MATB = 2 * C * 16 * 8, STAGE = CH * (OPB + MATB);
+    __shared__ __align__(16) unsigned char stage[2][STAGE];
     __shared__ double red[3 * (UPD_THREADS / 32)];
+    __shared__ int sLast;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int tile = blockIdx.x, chain = blockIdx.y;
+    // chains in order of decreasing list length: the long walks start first (only chains with a
+    // non-empty list are launched)
+    const int tile = blockIdx.x, chain = chainOrder[blockIdx.y];
     const long long p = (long long)tile * UPD_THREADS + tid;        // < pStride
     const int k0 = opOff[chain], k1 = opOff[chain + 1];
     double *out = partial + ((size_t)chain * nTiles + tile) * 3;
-    if (k0 == k1) {                     // nothing changed: the host keeps the accepted logL
-        if (tid == 0)
-            out[0] = out[1] = out[2] = 0.0;
-        return;
-    }
     constexpr int ROWS = 4 * C + 1;
-    const size_t nInt = (size_t)(n - 1);
-    auto vec = [&](int node, int bank) -> double * {
-        return store + ((((size_t)chain * 2 + bank) * nInt + (size_t)(node - n)) * ROWS) * pStride + p;
+    const double kappa = kappaPerChain[chain];
+    double *const mine = store + p;     // + vector offset + row * pStride
+
+    // a stage: CH list entries (asynchronous copies, one stage ahead) and the transition
+    // matrices of their child branches, evaluated here from the entries -- the closed form of
+    // k2_prepare with the same argument order, so the matrices are bit-identical to the full
+    // evaluation's: [entry][child][category][16], internal child row-major, tip child transposed
+    auto issue = [&](int j) {
+        const int e0 = k0 + j * CH, cnt = min(CH, k1 - e0);
+        unsigned char *dst = stage[j & 1];
+        const unsigned char *srcO = reinterpret_cast<const unsigned char *>(ops + e0);
+        for (int o = tid * 16; o < cnt * OPB; o += UPD_THREADS * 16)
+            cp_async16(dst + o, srcO + o);
+        cp_async_commit();
     };
+    auto matrices = [&](int j) {
+        const int cnt = min(CH, k1 - k0 - j * CH);
+        const UpdOp *sOps = reinterpret_cast<const UpdOp *>(stage[j & 1]);
+        double *sMats = reinterpret_cast<double *>(stage[j & 1] + CH * OPB);
+        const double *catRates = site, *freqs = site + 2 * C;
+        for (int idx = tid; idx < cnt * 2 * C; idx += UPD_THREADS) {
+            const int e = idx / (2 * C), jj = (idx / C) & 1, c = idx % C;
+            const UpdOp &op = sOps[e];
+            const int child = jj ? op.c2 : op.c1;
+            const double jointBranchRate = catRates[c] * (jj ? op.br2 : op.br1);
+            const double distance = (jj ? op.dh2 : op.dh1) * jointBranchRate;
+            double T[16];
+            hky_matrix(kappa, freqs, distance, T);
+            double *M = sMats + ((size_t)(e * 2 + jj) * C + c) * 16;
+            const bool tip = child < n;
+#pragma unroll
+            for (int q = 0; q < 16; q++)
+                M[q] = tip ? T[(q & 3) * 4 + (q >> 2)] : T[q];
+        }
+    };
+    const int nStages = (k1 - k0 + CH - 1) / CH;
+    issue(0);
+    cp_async_wait<0>();
+    __syncthreads();
+    matrices(0);
 
     double prev[C][1][4], prevScale = 0.0;
     // child 2 of the entry about to run, fetched one entry ahead
@@ -188,88 +246,108 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
         if (op.c2 < n) {
             nTip[0] = __ldg(states + (size_t)op.c2 * pStride + p);
         } else {
-            const double *src = vec(op.c2, (op.flags & UF_C2_BANK) ? 1 : 0);
+            const double *src = mine + op.c2Off;
 #pragma unroll
-            for (int c = 0; c < C; c++)
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    nx[c][0][i] = __ldcg(src + (size_t)(c * 4 + i) * pStride);
-            nScale = __ldcg(src + (size_t)(4 * C) * pStride);
+            for (int r = 0; r < 4 * C; r++, src += pStride)
+                nx[r >> 2][0][r & 3] = __ldcg(src);
+            nScale = __ldcg(src);
         }
     };
-    UpdOp op = ops[k0];
-    fetch2(op);
 #pragma unroll 1
-    for (int k = k0; k < k1; k++) {
-        const double *M1 = mats + (size_t)k * 2 * C * 16, *M2 = M1 + C * 16;
-        // child 1: the previous result, a tip, or (first entry of a path) a resident vector
-        int t1[1] = {4};
-        double ls = 0.0;
-        if (op.flags & UF_PREV) {
-            ls = prevScale;
-        } else if (op.c1 < n) {
-            t1[0] = __ldg(states + (size_t)op.c1 * pStride + p);
-        } else {
-            const double *src = vec(op.c1, (op.flags & UF_C1_BANK) ? 1 : 0);
+    for (int j = 0; j < nStages; j++) {
+        if (j + 1 < nStages)
+            issue(j + 1);               // the other buffer was released by the barrier below
+        __syncthreads();                // this stage's matrices are in place
+        const UpdOp *sOps = reinterpret_cast<const UpdOp *>(stage[j & 1]);
+        const double *sMats = reinterpret_cast<const double *>(stage[j & 1] + CH * OPB);
+        const int cnt = min(CH, k1 - k0 - j * CH);
+        // The resident children of a path do not depend on the entries before them: pull the
+        // lines of the whole stage into L2 now (one lane per 128-byte line), so that the
+        // register fetch one entry ahead is an L2 hit and the walk is not a chain of HBM
+        // latencies.
+        if ((lane & 15) == 0) {
+            for (int e = 1; e < cnt; e++) {
+                if (sOps[e].c2 < n)
+                    continue;
+                const double *src = mine + sOps[e].c2Off;
 #pragma unroll
-            for (int c = 0; c < C; c++)
-#pragma unroll
-                for (int i = 0; i < 4; i++)
-                    prev[c][0][i] = __ldcg(src + (size_t)(c * 4 + i) * pStride);
-            ls = __ldcg(src + (size_t)(4 * C) * pStride);
-        }
-        // child 2 (already here); start on the next entry's
-        double x2[C][1][4];
-        int t2[1] = {nTip[0]};
-#pragma unroll
-        for (int c = 0; c < C; c++)
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                x2[c][0][i] = nx[c][0][i];
-        if (op.c2 >= n)
-            ls += nScale;
-        const UpdOp cur = op;
-        if (k + 1 < k1) {
-            op = ops[k + 1];
-            fetch2(op);
-        }
-        int mxhi = 0;
-#pragma unroll
-        for (int c = 0; c < C; c++) {
-            double a[1][4], bb[1][4];
-            child_term<1, 2>(cur.c1 < n, M1 + c * 16, prev[c], t1, a);
-            child_term<1, 2>(cur.c2 < n, M2 + c * 16, x2[c], t2, bb);
-#pragma unroll
-            for (int i = 0; i < 4; i++) {
-                prev[c][0][i] = a[0][i] * bb[0][i];
-                mxhi = max(mxhi, __double2hiint(prev[c][0][i]));
+                for (int r = 0; r < ROWS; r++, src += pStride)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(src));
             }
         }
-        // BeerLikelihoodCore.scalePartials [EXT], as in k2_peel
-        if (mxhi <= __double2hiint(SCALING_THRESHOLD)) {
-            double mx = 0.0;
+        fetch2(sOps[0]);
+#pragma unroll 1
+        for (int e = 0; e < cnt; e++) {
+            const UpdOp &op = sOps[e];
+            const int c1 = op.c1, c2 = op.c2, flags = op.flags;
+            const double *M1 = sMats + (size_t)e * 2 * C * 16, *M2 = M1 + C * 16;
+            // child 1: the previous result, a tip, or (first entry of a path) a resident vector
+            int t1[1] = {4};
+            double ls = 0.0;
+            if (flags & UF_PREV) {
+                ls = prevScale;
+            } else if (c1 < n) {
+                t1[0] = __ldg(states + (size_t)c1 * pStride + p);
+            } else {
+                const double *src = mine + op.c1Off;
+#pragma unroll
+                for (int r = 0; r < 4 * C; r++, src += pStride)
+                    prev[r >> 2][0][r & 3] = __ldcg(src);
+                ls = __ldcg(src);
+            }
+            // child 2 (already here); start on the next entry's
+            double x2[C][1][4];
+            int t2[1] = {nTip[0]};
 #pragma unroll
             for (int c = 0; c < C; c++)
 #pragma unroll
                 for (int i = 0; i < 4; i++)
-                    mx = fmax(mx, prev[c][0][i]);
-            if (mx < SCALING_THRESHOLD) {
+                    x2[c][0][i] = nx[c][0][i];
+            if (c2 >= n)
+                ls += nScale;
+            double *dst = mine + op.dstOff;
+            if (e + 1 < cnt)
+                fetch2(sOps[e + 1]);
+            int mxhi = 0;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                double a[1][4], bb[1][4];
+                child_term<1, 2>(c1 < n, M1 + c * 16, prev[c], t1, a);
+                child_term<1, 2>(c2 < n, M2 + c * 16, x2[c], t2, bb);
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    prev[c][0][i] = a[0][i] * bb[0][i];
+                    mxhi = max(mxhi, __double2hiint(prev[c][0][i]));
+                }
+            }
+            // BeerLikelihoodCore.scalePartials [EXT], as in k2_peel
+            if (mxhi <= __double2hiint(SCALING_THRESHOLD)) {
+                double mx = 0.0;
 #pragma unroll
                 for (int c = 0; c < C; c++)
 #pragma unroll
                     for (int i = 0; i < 4; i++)
-                        prev[c][0][i] /= mx;
-                ls += log(mx);
+                        mx = fmax(mx, prev[c][0][i]);
+                if (mx < SCALING_THRESHOLD) {
+#pragma unroll
+                    for (int c = 0; c < C; c++)
+#pragma unroll
+                        for (int i = 0; i < 4; i++)
+                            prev[c][0][i] /= mx;
+                    ls += log(mx);
+                }
             }
+            prevScale = ls;
+#pragma unroll
+            for (int r = 0; r < 4 * C; r++, dst += pStride)
+                *dst = prev[r >> 2][0][r & 3];
+            *dst = ls;
         }
-        prevScale = ls;
-        double *dst = vec(cur.v, (cur.flags & UF_DST_BANK) ? 1 : 0);
-#pragma unroll
-        for (int c = 0; c < C; c++)
-#pragma unroll
-            for (int i = 0; i < 4; i++)
-                dst[(size_t)(c * 4 + i) * pStride] = prev[c][0][i];
-        dst[(size_t)(4 * C) * pStride] = ls;
+        if (j + 1 < nStages) {
+            cp_async_wait<0>();
+            __syncthreads();            // the next stage's entries have landed
+            matrices(j + 1);
+        }
     }
 
     // the last entry is the root
@@ -313,18 +391,44 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
         out[0] = tU;
         out[1] = tQ;
         out[2] = f;
+        // the chain's last tile to finish adds the tile sums up, in tile order (k2_finalize)
+        __threadfence();
+        sLast = atomicAdd(&tilesDone[chain], 1) == nTiles - 1;
+    }
+    __syncthreads();
+    if (sLast && warp == 0) {
+        __threadfence();
+        const double *in = partial + (size_t)chain * nTiles * 3;
+        double sU = 0.0, sQ = 0.0, fl = 0.0;
+        for (int t0 = 0; t0 < nTiles; t0 += 32) {
+            const int t = t0 + lane;
+            const double u = t < nTiles ? __ldcg(in + (size_t)t * 3) : 0.0;
+            const double q = t < nTiles ? __ldcg(in + (size_t)t * 3 + 1) : 0.0;
+            const double g = t < nTiles ? __ldcg(in + (size_t)t * 3 + 2) : 0.0;
+            // lane order = tile order
+            for (int l = 0; l < 32 && t0 + l < nTiles; l++) {
+                sU += __shfl_sync(FULL_MASK, u, l);
+                sQ += __shfl_sync(FULL_MASK, q, l);
+                fl += __shfl_sync(FULL_MASK, g, l);
+            }
+        }
+        if (lane == 0) {
+            logL[chain] = (fl > 0.0) ? sQ : sU;
+            tilesDone[chain] = 0;       // ready for the next update
+        }
     }
 }
 
 template <int C>
-int launch_update(mtt_peel_chains *s, const UpdOp *dOps, const int *dOpOff, int nTiles)
+int launch_update(mtt_peel_chains *s, const UpdOp *dOps, const int *dOpOff, const int *dOrder,
+                  int nActive, int nTiles, const double *dKappa, double *dLogL)
 {
     mtt_peel *h = s->h;
     mtt_ctx *ctx = h->ctx;
-    dim3 grid((unsigned)nTiles, (unsigned)s->K);
+    dim3 grid((unsigned)nTiles, (unsigned)nActive);
     k2_peel_update<C><<<grid, UPD_THREADS, 0, ctx->stream>>>(
         h->nTips, h->nPatterns, h->pStride, h->dStates, h->dWeights, h->dConst, h->dSite, h->pInv,
-        dOps, dOpOff, s->dMats, s->dStore, s->dPart, nTiles);
+        dOps, dOpOff, dOrder, dKappa, s->dStore, s->dPart, nTiles, s->dDone, dLogL);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
 }
@@ -347,14 +451,25 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
     std::vector<int> &changed = c.changed;
     changed.clear();
     auto differs = [&](int i) {
-        return parent[i] != c.parent[i] || height[i] != c.height[i] ||
-               (rate ? rate[i] : clock) != c.rate[i];
+        return parent[i] != c.nd[i].parent || height[i] != c.nd[i].height ||
+               (rate ? rate[i] : clock) != c.nd[i].rate;
     };
     if (all) {
         for (int i = 0; i < N; i++)
             changed.push_back(i);
     } else if (dirty) {
-        for (int i = 0; i < N; i++)
+        // a handful of flags in N bytes: skip eight clean nodes at a time
+        int i = 0;
+        for (; i + 8 <= N; i += 8) {
+            uint64_t w;
+            memcpy(&w, dirty + i, 8);
+            if (!w)
+                continue;
+            for (int j = i; j < i + 8; j++)
+                if (dirty[j] && differs(j))
+                    changed.push_back(j);
+        }
+        for (; i < N; i++)
             if (dirty[i] && differs(i))
                 changed.push_back(i);
     } else {
@@ -365,10 +480,10 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
     if (changed.empty())
         return true;
     auto fail = [&]() {
-        c.undo(n);
+        c.undo();
         return false;
     };
-    auto journalKids = [&](int v) { c.undoKids.push_back({v, c.left[v], c.right[v]}); };
+    auto journalKids = [&](int v) { c.undoKids.push_back({v, c.nd[v].left, c.nd[v].right}); };
     // detach the nodes whose parent changes, then attach them to their new parents
     std::vector<int> &touched = s->stack;
     touched.clear();
@@ -376,15 +491,15 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
         const int pp = parent[i];
         if (pp >= N || pp == i || (pp >= 0 && pp < n))
             return fail();
-        c.undoNodes.push_back({i, c.parent[i], c.height[i], c.rate[i]});
-        if (pp != c.parent[i]) {
-            const int old = c.parent[i];
+        c.undoNodes.push_back({i, c.nd[i].parent, c.nd[i].height, c.nd[i].rate});
+        if (pp != c.nd[i].parent) {
+            const int old = c.nd[i].parent;
             if (old >= n && old < N) {
                 journalKids(old);
-                if (c.left[old] == i)
-                    c.left[old] = -1;
-                else if (c.right[old] == i)
-                    c.right[old] = -1;
+                if (c.nd[old].left == i)
+                    c.nd[old].left = -1;
+                else if (c.nd[old].right == i)
+                    c.nd[old].right = -1;
                 touched.push_back(old);
             } else if (old == -1) {
                 c.rootCount--;
@@ -396,15 +511,15 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
     moved.clear();
     for (int i : changed) {
         const int pp = parent[i];
-        if (i >= n && (all || height[i] != c.height[i]))
+        if (i >= n && (all || height[i] != c.nd[i].height))
             moved.push_back(i);
-        if (pp != c.parent[i]) {
+        if (pp != c.nd[i].parent) {
             if (pp >= 0) {
                 journalKids(pp);
-                if (c.left[pp] < 0)
-                    c.left[pp] = i;
-                else if (c.right[pp] < 0)
-                    c.right[pp] = i;
+                if (c.nd[pp].left < 0)
+                    c.nd[pp].left = i;
+                else if (c.nd[pp].right < 0)
+                    c.nd[pp].right = i;
                 else
                     return fail();                  // a third child
                 touched.push_back(pp);
@@ -412,20 +527,21 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
                 c.rootCount++;
                 c.root = i;
             }
-            c.parent[i] = pp;
+            c.nd[i].parent = pp;
         }
-        c.height[i] = height[i];
-        c.rate[i] = rate ? rate[i] : clock;
+        c.nd[i].height = height[i];
+        c.nd[i].rate = rate ? rate[i] : clock;
     }
     if (c.rootCount != 1 || c.root < n)
         return fail();
     for (int v : touched)
-        if (c.left[v] < 0 || c.right[v] < 0)
+        if (c.nd[v].left < 0 || c.nd[v].right < 0)
             return fail();                          // an internal node left with one child
     // walks from the changes up to the root (or to a node already marked in this call); meeting
     // a node marked by the SAME walk means a cycle
     if (c.epoch == 0x7fffffff) {
-        c.mark.assign(N, 0);
+        for (Chain::Node &x : c.nd)
+            x.mark = 0;
         c.epoch = 0;
     }
     c.epoch++;
@@ -434,26 +550,26 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
         const int id = ++c.walkId;
         int steps = 0;
         while (u >= 0) {
-            if (c.mark[u] == c.epoch) {
-                if (c.walk[u] == id)
+            if (c.nd[u].mark == c.epoch) {
+                if (c.nd[u].walk == id)
                     return false;
                 return true;
             }
-            c.mark[u] = c.epoch;
-            c.walk[u] = id;
-            u = c.parent[u];
+            c.nd[u].mark = c.epoch;
+            c.nd[u].walk = id;
+            u = c.nd[u].parent;
             if (++steps > N)
                 return false;
         }
         return true;
     };
     for (int i : changed)
-        if (c.parent[i] >= 0 && !walkUp(c.parent[i]))
+        if (c.nd[i].parent >= 0 && !walkUp(c.nd[i].parent))
             return fail();
     for (int i : moved)
         if (!walkUp(i))
             return fail();
-    if (c.mark[c.root] != c.epoch)
+    if (c.nd[c.root].mark != c.epoch)
         return true;                                // e.g. only the root's branch rate changed
     // post-order over the marked nodes; a marked child is visited last so that it is the
     // previous entry of its parent (two marked children: the other one is read back from HBM).
@@ -465,8 +581,8 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
     while (!stack.empty()) {
         const int v = stack.back();
         stack.pop_back();
-        const int l = c.left[v], r = c.right[v];
-        const bool lu = l >= n && c.mark[l] == c.epoch, ru = r >= n && c.mark[r] == c.epoch;
+        const int l = c.nd[v].left, r = c.nd[v].right;
+        const bool lu = l >= n && c.nd[l].mark == c.epoch, ru = r >= n && c.nd[r].mark == c.epoch;
         UpdOp op;
         memset(&op, 0, sizeof(op));
         op.v = v;
@@ -474,14 +590,12 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
         op.c1 = c1;
         op.c2 = c2;
         op.flags = (k << 8) | ((lu || ru) ? UF_PREV : 0);
-        c.bank[v - n] ^= 1;                          // the bank the accepted state does not use
+        c.nd[v].bank ^= 1;                          // the bank the accepted state does not use
         c.flipped.push_back(v);
-        if (c.bank[v - n])
-            op.flags |= UF_DST_BANK;
-        op.dh1 = c.height[v] - c.height[c1];
-        op.dh2 = c.height[v] - c.height[c2];
-        op.br1 = c.rate[c1];
-        op.br2 = c.rate[c2];
+        op.dh1 = c.nd[v].height - c.nd[c1].height;
+        op.dh2 = c.nd[v].height - c.nd[c2].height;
+        op.br1 = c.nd[c1].rate;
+        op.br2 = c.nd[c2].rate;
         s->ops.push_back(op);
         if (ru && lu)
             stack.push_back(c2);
@@ -489,18 +603,42 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
             stack.push_back(c1);
     }
     std::reverse(s->ops.begin() + first, s->ops.end());
-    // banks of resident children, known once every listed node has its new bank
+    // where the vectors live, known once every listed node has its new bank
+    const long long rows = 4 * s->h->nCat + 1, nInt = n - 1;
+    auto vecOff = [&](int node) {
+        return (((long long)k * 2 + c.nd[node].bank) * nInt + (node - n)) * rows * s->h->pStride;
+    };
     for (size_t e = first; e < s->ops.size(); e++) {
         UpdOp &op = s->ops[e];
-        if (op.c1 >= n && c.bank[op.c1 - n])
-            op.flags |= UF_C1_BANK;
-        if (op.c2 >= n && c.bank[op.c2 - n])
-            op.flags |= UF_C2_BANK;
+        op.dstOff = vecOff(op.v);
+        op.c1Off = op.c1 >= n ? vecOff(op.c1) : 0;
+        op.c2Off = op.c2 >= n ? vecOff(op.c2) : 0;
     }
     return true;
 }
 
 }  // namespace
+
+// free the device side; called by mtt_peel_destroy for chains that outlive their handle (they
+// answer MTT_ERR_STATE from then on)
+void k2_chains_release(mtt_peel_chains *s)
+{
+    if (!s->h)
+        return;
+    cudaSetDevice(s->h->ctx->device);
+    cudaStreamSynchronize(s->h->ctx->stream);
+    for (void *p : {(void *)s->dStore, (void *)s->dPart, (void *)s->dDone})
+        if (p)
+            cudaFree(p);
+    if (s->ev0)
+        cudaEventDestroy(s->ev0);
+    if (s->ev1)
+        cudaEventDestroy(s->ev1);
+    s->dStore = s->dPart = nullptr;
+    s->dDone = nullptr;
+    s->ev0 = s->ev1 = nullptr;
+    s->h = nullptr;
+}
 
 extern "C" {
 
@@ -525,23 +663,22 @@ int mtt_peel_chains_create(mtt_peel *h, int nChains, mtt_peel_chains **out)
     s->h = h;
     s->K = nChains;
     cudaError_t e = cudaMalloc((void **)&s->dStore, bytes + 256);
+    if (e == cudaSuccess)
+        e = cudaMalloc((void **)&s->dDone, (size_t)nChains * sizeof(int));
+    if (e == cudaSuccess)
+        e = cudaMemset(s->dDone, 0, (size_t)nChains * sizeof(int));
     if (e != cudaSuccess) {
+        if (s->dStore)
+            cudaFree(s->dStore);
         delete s;
         return mtt_fail(ctx, MTT_ERR_CUDA, "mtt_peel_chains_create: cudaMalloc(%zu) failed: %s",
                         bytes, cudaGetErrorString(e));
     }
     const int N = 2 * h->nTips - 1;
     s->chains.resize(nChains);
-    for (Chain &c : s->chains) {
-        c.parent.assign(N, -2);             // -2: no tree yet
-        c.left.assign(N, -1);
-        c.right.assign(N, -1);
-        c.mark.assign(N, 0);
-        c.walk.assign(N, 0);
-        c.height.assign(N, 0.0);
-        c.rate.assign(N, 0.0);
-        c.bank.assign(h->nTips - 1, 0);
-    }
+    for (Chain &c : s->chains)
+        c.nd.assign(N, Chain::Node());
+    h->chains.push_back(s);
     *out = s;
     return MTT_OK;
 }
@@ -550,11 +687,11 @@ int mtt_peel_chains_destroy(mtt_peel_chains *s)
 {
     if (!s)
         return MTT_OK;
-    cudaSetDevice(s->h->ctx->device);
-    cudaStreamSynchronize(s->h->ctx->stream);
-    for (void *p : {(void *)s->dStore, (void *)s->dMats, (void *)s->dPart})
-        if (p)
-            cudaFree(p);
+    if (s->h) {
+        std::vector<mtt_peel_chains *> &v = s->h->chains;
+        v.erase(std::remove(v.begin(), v.end(), s), v.end());
+        k2_chains_release(s);
+    }
     delete s;
     return MTT_OK;
 }
@@ -563,8 +700,8 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
                            const double *branchRates, const double *kappa,
                            const double *clockRate, const uint8_t *dirty, double *logL)
 {
-    if (!s)
-        return MTT_ERR_INVALID_ARG;
+    if (!s || !s->h)
+        return MTT_ERR_STATE;               // (the handle was destroyed)
     mtt_peel *h = s->h;
     mtt_ctx *ctx = h->ctx;
     int rc = k2_check_ready(h, kappa == nullptr);
@@ -576,7 +713,7 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
     const int n = h->nTips, N = 2 * n - 1, C = h->nCat, K = s->K;
     for (Chain &c : s->chains)
         if (c.pending)
-            c.undo(n);                      // an unanswered proposal counts as rejected
+            c.undo();                      // an unanswered proposal counts as rejected
     if (s->version != h->version) {         // alignment / site model changed: nothing is reusable
         for (Chain &c : s->chains)
             c.valid = false;
@@ -601,10 +738,9 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
     }
     const long long nEntries = (long long)s->ops.size();
     s->lastOps = nEntries;
+    s->lastMs = 0.0f;
     if (nEntries > 0) {
         const int nTiles = (int)(h->pStride / UPD_THREADS);
-        if ((rc = grow(ctx, s->dMats, s->matsCap, (size_t)nEntries * 2 * C * 16 * 8)) != MTT_OK)
-            return rc;
         if ((rc = grow(ctx, s->dPart, s->partCap, (size_t)K * nTiles * 24)) != MTT_OK)
             return rc;
         Xfer x(ctx);
@@ -612,33 +748,45 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
         int *dOpOff = nullptr;
         double *dKappa = nullptr, *dLogL = nullptr;
         std::vector<double> got(K);
+        // chains with something to do, the longest lists first
+        std::vector<int> &order = s->order;
+        order.clear();
+        for (int k = 0; k < K; k++)
+            if (s->opOff[k + 1] > s->opOff[k])
+                order.push_back(k);
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+            return s->opOff[a + 1] - s->opOff[a] > s->opOff[b + 1] - s->opOff[b];
+        });
+        const int nActive = (int)order.size();
+        int *dOrder = nullptr;
         x.in(s->ops.data(), s->ops.size(), BUF_C_OPS, &dOps);
         x.in(s->opOff.data(), s->opOff.size(), BUF_C_OPOFF, &dOpOff);
+        x.in(order.data(), order.size(), BUF_C_ORDER, &dOrder);
         x.in(kap.data(), kap.size(), BUF_C_KAPPA, &dKappa);
         x.out(got.data(), got.size(), BUF_C_LOGL, &dLogL);
         if ((rc = x.prepare()) != MTT_OK || (rc = x.upload()) != MTT_OK)
             return rc;
-        const long long nMat = nEntries * 2 * C;
-        k2_update_mats<<<(unsigned)((nMat + 127) / 128), 128, 0, ctx->stream>>>(
-            n, C, nEntries, dOps, dKappa, h->dSite, s->dMats);
-        MTT_CHECK_LAUNCH(ctx);
+        if (s->timing)
+            MTT_CUDA(ctx, cudaEventRecord(s->ev0, ctx->stream));
         switch (C) {
-        case 1: rc = launch_update<1>(s, dOps, dOpOff, nTiles); break;
-        case 2: rc = launch_update<2>(s, dOps, dOpOff, nTiles); break;
-        case 3: rc = launch_update<3>(s, dOps, dOpOff, nTiles); break;
-        case 4: rc = launch_update<4>(s, dOps, dOpOff, nTiles); break;
-        case 5: rc = launch_update<5>(s, dOps, dOpOff, nTiles); break;
-        case 6: rc = launch_update<6>(s, dOps, dOpOff, nTiles); break;
-        case 7: rc = launch_update<7>(s, dOps, dOpOff, nTiles); break;
-        case 8: rc = launch_update<8>(s, dOps, dOpOff, nTiles); break;
+        case 1: rc = launch_update<1>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 2: rc = launch_update<2>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 3: rc = launch_update<3>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 4: rc = launch_update<4>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 5: rc = launch_update<5>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 6: rc = launch_update<6>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 7: rc = launch_update<7>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+        case 8: rc = launch_update<8>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
         default: rc = mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: nCat=%d outside [1,8]", C);
         }
         if (rc != MTT_OK)
             return rc;
-        if ((rc = k2_run_finalize(h, K, nTiles, s->dPart, dLogL, nullptr, nullptr, 0)) != MTT_OK)
-            return rc;
+        if (s->timing)
+            MTT_CUDA(ctx, cudaEventRecord(s->ev1, ctx->stream));
         if ((rc = x.download()) != MTT_OK)
             return rc;
+        if (s->timing)
+            MTT_CUDA(ctx, cudaEventElapsedTime(&s->lastMs, s->ev0, s->ev1));
         for (int k = 0; k < K; k++)
             if (s->opOff[k + 1] > s->opOff[k])
                 s->chains[k].logL = got[k];
@@ -657,9 +805,8 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
 
 int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept)
 {
-    if (!s)
-        return MTT_ERR_INVALID_ARG;
-    const int n = s->h->nTips;
+    if (!s || !s->h)
+        return MTT_ERR_STATE;
     for (int k = 0; k < s->K; k++) {
         Chain &c = s->chains[k];
         if (!c.pending)
@@ -667,7 +814,7 @@ int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept)
         if (!accept || accept[k])
             c.commit();
         else
-            c.undo(n);
+            c.undo();
     }
     return MTT_OK;
 }
@@ -675,6 +822,25 @@ int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept)
 int64_t mtt_peel_chains_last_entries(const mtt_peel_chains *s)
 {
     return s ? s->lastOps : 0;
+}
+
+int mtt_peel_chains_set_timing(mtt_peel_chains *s, int on)
+{
+    if (!s || !s->h)
+        return MTT_ERR_STATE;
+    mtt_ctx *ctx = s->h->ctx;
+    if (on && !s->ev0) {
+        MTT_CUDA(ctx, cudaSetDevice(ctx->device));
+        MTT_CUDA(ctx, cudaEventCreate(&s->ev0));
+        MTT_CUDA(ctx, cudaEventCreate(&s->ev1));
+    }
+    s->timing = on != 0;
+    return MTT_OK;
+}
+
+double mtt_peel_chains_last_device_ms(const mtt_peel_chains *s)
+{
+    return s ? (double)s->lastMs : 0.0;
 }
 
 }  // extern "C"

@@ -260,6 +260,14 @@ class TreeLikelihood:
             pass
 
 
+def _flags(a) -> np.ndarray:
+    """Byte flags (nonzero = set) without a copy when `a` already is a byte / bool array."""
+    a = np.asarray(a)
+    if a.dtype == np.bool_ or a.dtype == np.uint8:
+        return np.ascontiguousarray(a).view(np.uint8)
+    return _lib.as_c(a != 0, np.uint8)
+
+
 class PeelChains:
     """What BEAST's ``TreeLikelihood`` does between MCMC steps (dirty-node updates of the
     partials ``BeerLikelihoodCore`` keeps per node, ``store`` / ``restore``), for ``nChains``
@@ -290,7 +298,7 @@ class PeelChains:
             np.broadcast_to(np.asarray(kappa, np.float64), (K,)), np.float64)
         clk = None if clockRate is None else _lib.as_c(
             np.broadcast_to(np.asarray(clockRate, np.float64), (K,)), np.float64)
-        d = None if dirty is None else _lib.as_c(np.asarray(dirty) != 0, np.uint8)
+        d = None if dirty is None else _flags(dirty)
         if d is not None and d.shape != h.shape:
             raise ValueError("dirty must have the shape of height")
         out = np.empty(K, np.float64)
@@ -301,7 +309,7 @@ class PeelChains:
 
     def accept(self, mask=None) -> None:
         """mask[nChains] (None = all): nonzero keeps the chain's proposal, zero drops it."""
-        m = None if mask is None else _lib.as_c(np.asarray(mask) != 0, np.uint8)
+        m = None if mask is None else _flags(mask)
         if m is not None and m.shape != (self.nChains,):
             raise ValueError("mask must be [nChains]")
         self.ctx.check(_lib.lib().mtt_peel_chains_accept(self._s, _lib.ptr(m)))
@@ -310,6 +318,14 @@ class PeelChains:
     def last_entries(self) -> int:
         """Internal nodes recomputed by the last update, over all chains."""
         return int(_lib.lib().mtt_peel_chains_last_entries(self._s))
+
+    def set_timing(self, on: bool = True) -> None:
+        self.ctx.check(_lib.lib().mtt_peel_chains_set_timing(self._s, int(on)))
+
+    @property
+    def last_device_ms(self) -> float:
+        """Device time of the last update's launches (after ``set_timing``)."""
+        return float(_lib.lib().mtt_peel_chains_last_device_ms(self._s))
 
     def close(self):
         if self._s:

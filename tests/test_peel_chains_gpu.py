@@ -257,3 +257,19 @@ def test_chains_malformed_proposal_leaves_the_chain_alone(ctx):
     assert np.array_equal(again, base)
     ch.close()
     tl.close()
+
+
+def test_chains_outliving_their_handle_fail_loudly(ctx):
+    n, K = 8, 2
+    par, hgt = _trees(K, n, seed=9)
+    f = np.array([.25, .25, .25, .25])
+    tips = simulate_alignment(par[0], hgt[0], 100, 2.0, f, 0.1, seed=2)
+    tl = TreeLikelihood(data=Alignment(states=tips), siteModel=SiteModel(HKY(2.0, f), 0.1), ctx=ctx)
+    ch = tl.chains(K)
+    ch.update(par, hgt)
+    tl.close()                                      # frees the chains' device side too
+    with pytest.raises(mtt.MttError):
+        ch.update(par, hgt)
+    with pytest.raises(mtt.MttError):
+        ch.accept()
+    ch.close()

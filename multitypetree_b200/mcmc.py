@@ -7,6 +7,12 @@ the device path: proposals by operators.py (uniformization kernels), target dens
 retype call, one batched branch-probability call and ONE density launch over C trees instead
 of C x 3 tiny launches.  A single chain is the C = 1 case (``MCMC``).
 
+With a ``TreeLikelihood`` the target is the posterior of the reference's config 1
+(examples/structuredCoalescent.xml:560-572: structured-coalescent density + tree likelihood);
+the likelihood term runs on resident chains (``PeelChains``): a proposal recomputes only the
+partials above what it changed, accept / reject keeps or drops them -- what BEAST's
+``TreeLikelihood`` does with dirty nodes and ``store`` / ``restore``.
+
 Per step and chain, in BEAST's order: operator choice (one ``nextDouble``), ``proposal()``,
 then -- unless the proposal returned -inf -- ``logAlpha = newLogP - oldLogP + logHR`` and one
 more ``nextDouble`` only if ``logAlpha < 0``.
@@ -78,11 +84,26 @@ def effective_sample_size(x: np.ndarray, maxLag: int = 2000) -> float:
 class MCMCEnsemble:
     """C chains advanced in lock step against the structured-coalescent tree density."""
 
-    def __init__(self, chains: Sequence[Chain], ctx=None):
+    def __init__(self, chains: Sequence[Chain], ctx=None, treeLikelihood=None,
+                 incremental: bool = True):
         self.chains = list(chains)
         self.ctx = ctx or _lib.default_context()
         self.heights: List[List[float]] = [[] for _ in self.chains]
+        # tree likelihood term (optional): resident chains, or a full re-evaluation of every
+        # proposal (incremental=False; the two agree to rounding)
+        self.treeLikelihood = treeLikelihood
+        self._peel = None
+        if treeLikelihood is not None and incremental:
+            self._peel = treeLikelihood.chains(len(self.chains))
         self._evaluate(range(len(self.chains)), init=True)
+
+    def _likelihood(self, trees) -> np.ndarray:
+        """Tree likelihood of one tree per chain (all chains, in chain order)."""
+        par = np.stack([np.asarray(t.parent, np.int32) for t in trees])
+        hgt = np.stack([np.asarray(t.height, np.float64) for t in trees])
+        if self._peel is not None:
+            return self._peel.update(par, hgt)
+        return self.treeLikelihood.calculateLogPBatch(par, hgt)
 
     # one density launch over the listed chains' current trees
     def _density(self, idx: Sequence[int]) -> np.ndarray:
@@ -103,6 +124,12 @@ class MCMCEnsemble:
         lp = self._density(idx)
         for i, v in zip(idx, lp):
             self.chains[i].logP = float(v)
+        if self.treeLikelihood is not None:
+            lik = self._likelihood([c.tree for c in self.chains])
+            if self._peel is not None:
+                self._peel.accept()
+            for i in idx:
+                self.chains[i].logP += float(lik[i])
 
     def step(self) -> None:
         chains = self.chains
@@ -111,6 +138,15 @@ class MCMCEnsemble:
         hrs = run_proposals([c.operators[k] for c, k in zip(chains, picks)])
         live = [i for i, hr in enumerate(hrs) if hr != float("-inf")]
         newLogP = dict(zip(live, self._density(live))) if live else {}
+        if self.treeLikelihood is not None and live:
+            # a failed proposal may have left its tree half edited: those chains show their
+            # saved tree (nothing to recompute) and are rejected below
+            alive = set(live)
+            lik = self._likelihood([c.tree if i in alive else saved[i]
+                                    for i, c in enumerate(chains)])
+            for i in live:
+                newLogP[i] = float(newLogP[i]) + float(lik[i])
+        accepted = np.zeros(len(chains), np.uint8)
         for i, c in enumerate(chains):
             c.proposed[picks[i]] += 1
             accept = False
@@ -120,8 +156,11 @@ class MCMCEnsemble:
             if accept:
                 c.logP = float(newLogP[i])
                 c.accepted[picks[i]] += 1
+                accepted[i] = 1
             else:
                 c.tree.assignFrom(saved[i])
+        if self._peel is not None and live:
+            self._peel.accept(accepted)
 
     def run(self, chainLength: int, logEvery: int = 100) -> None:
         for it in range(chainLength):
@@ -155,5 +194,7 @@ class MCMCEnsemble:
 class MCMC(MCMCEnsemble):
     """Single chain (BEAST ``MCMC`` with one State, one Distribution, a list of operators)."""
 
-    def __init__(self, tree, migrationModel, operators, randomizer, checkValidity=False, ctx=None):
-        super().__init__([Chain(tree, migrationModel, operators, randomizer, checkValidity)], ctx)
+    def __init__(self, tree, migrationModel, operators, randomizer, checkValidity=False, ctx=None,
+                 treeLikelihood=None, incremental=True):
+        super().__init__([Chain(tree, migrationModel, operators, randomizer, checkValidity)], ctx,
+                         treeLikelihood, incremental)

@@ -342,3 +342,60 @@ def test_reference_STX_NR_MTU_TS_Test(ctx):
     print("STX", s, h.mean(), h.var(ddof=1))
     assert s["ess"] > 400
     _within(s, h.mean(), h.var(ddof=1), 1.0, 30.0)
+
+
+@pytest.mark.gpu
+def test_posterior_ensemble_incremental_likelihood_follows_full_evaluation(ctx):
+    """The posterior of config 1 (examples/structuredCoalescent.xml:560-572: structured-coalescent
+    density + TreeLikelihood) sampled by the operators of its schedule (:646-665).  The tree
+    likelihood term on resident chains (dirty-node updates, accept / reject) must drive the
+    chains exactly where a full re-evaluation of every proposal drives them: same seeds, same
+    accept decisions, same trees, log-posteriors equal to 1e-9."""
+    from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, TreeLikelihood,
+                                               simulate_alignment)
+    n, K, steps = 12, 6, 400
+    leafTypes = [i % 2 for i in range(n)]
+    start = [_simulated_start(leafTypes, 300 + c) for c in range(K)]
+    f = np.array([.25, .25, .25, .25])
+    t0 = start[0]
+    tips = simulate_alignment(np.asarray(t0.parent), np.asarray(t0.height), 300, 2.0, f, 0.01,
+                              seed=4)
+    al = Alignment(states=tips)
+    runs = []
+    for incremental in (True, False):
+        tl = TreeLikelihood(data=al, siteModel=SiteModel(HKY(2.0, f), mutationRate=0.01), ctx=ctx)
+        model = mtt.SCMigrationModel([0.1, 0.1], [7.0, 7.0], mtt.TypeSet("A", "B"), ctx=ctx)
+        chains = []
+        for c in range(K):
+            tree = start[c].copy()
+            rng = Randomizer(77 + c)
+            chains.append(Chain(tree, model, [
+                ops.TypedSubtreeExchange(tree, model, randomizer=rng),
+                ops.TypedWilsonBalding(tree, model, alpha=0.2, randomizer=rng),
+                ops.NodeRetype(tree, model, randomizer=rng),
+                ops.NodeShiftRetype(tree, model, randomizer=rng),
+                ops.MultiTypeUniform(tree, model, randomizer=rng),
+                ops.MultiTypeTreeScale(tree, model, scaleFactor=0.9, randomizer=rng)], rng))
+        ens = MCMCEnsemble(chains, ctx=ctx, treeLikelihood=tl, incremental=incremental)
+        trace = []
+        for _ in range(steps):
+            ens.step()
+            trace.append([c.logP for c in ens.chains])
+        runs.append((np.array(trace), [c.accepted.copy() for c in ens.chains],
+                     [np.asarray(c.tree.parent).copy() for c in ens.chains],
+                     [np.asarray(c.tree.height).copy() for c in ens.chains]))
+        if incremental:
+            # far fewer nodes than a full evaluation, and the accepted state is what a fresh
+            # evaluation of the final trees gives
+            par = np.stack([np.asarray(c.tree.parent, np.int32) for c in ens.chains])
+            hgt = np.stack([np.asarray(c.tree.height) for c in ens.chains])
+            lik = tl.calculateLogPBatch(par, hgt)
+            dens = ens._density(range(K))
+            np.testing.assert_allclose([c.logP for c in ens.chains], dens + lik, rtol=1e-9)
+        tl.close()
+    (ta, acca, pa, ha), (tb_, accb, pb, hb) = runs
+    assert sum(int(a.sum()) for a in acca) > K * steps // 20          # the chains moved
+    for c in range(K):
+        assert np.array_equal(acca[c], accb[c])
+        assert np.array_equal(pa[c], pb[c]) and np.array_equal(ha[c], hb[c])
+    np.testing.assert_allclose(ta, tb_, rtol=1e-9)

@@ -564,12 +564,67 @@ public:
         return logP;
     }
     double logP = NAN;
+    mtt_peel *handle() const { return h_; }
+    const Context &context() const { return ctx_; }
+    int getTaxonCount() const { return data_.getTaxonCount(); }
 
 private:
     const Alignment &data_;
     SiteModel site_;
     const Context &ctx_;
     mtt_peel *h_ = nullptr;
+};
+
+// What TreeLikelihood [EXT] does BETWEEN MCMC steps, for many chains at once: the partials of
+// every internal node stay in HBM (BeerLikelihoodCore's two banks per node), a proposal
+// recomputes only the nodes above what it changed (TreeLikelihood.traverse / Node.isDirty()),
+// accept() keeps or drops it (store / restore).  One tree per chain, over the likelihood's
+// alignment (mtt_peel_chains_*).
+class PeelChains {
+public:
+    PeelChains(const TreeLikelihood &likelihood, int nChains)
+        : ctx_(likelihood.context()), K_(nChains), n_(likelihood.getTaxonCount())
+    {
+        ctx_.check(mtt_peel_chains_create(likelihood.handle(), nChains, &s_));
+    }
+    ~PeelChains() { mtt_peel_chains_destroy(s_); }
+    PeelChains(const PeelChains &) = delete;
+    PeelChains &operator=(const PeelChains &) = delete;
+    // the proposals' trees, one per chain -> their log-likelihoods
+    std::vector<double> update(const std::vector<const MultiTypeTree *> &trees)
+    {
+        if ((int)trees.size() != K_)
+            throw std::invalid_argument("PeelChains::update: one tree per chain");
+        const size_t N = 2 * (size_t)n_ - 1;
+        par_.resize(K_ * N);
+        hgt_.resize(K_ * N);
+        for (int k = 0; k < K_; k++) {
+            if (trees[k]->getLeafNodeCount() != n_)
+                throw std::invalid_argument("The number of nodes in the tree does not match the "
+                                            "number of sequences");
+            std::copy(trees[k]->parent.begin(), trees[k]->parent.end(), par_.begin() + k * N);
+            std::copy(trees[k]->height.begin(), trees[k]->height.end(), hgt_.begin() + k * N);
+        }
+        std::vector<double> logL(K_);
+        ctx_.check(mtt_peel_chains_update(s_, par_.data(), hgt_.data(), nullptr, nullptr, nullptr,
+                                          nullptr, logL.data()));
+        return logL;
+    }
+    // keep[k] != 0: chain k's proposal becomes its accepted state; empty = all
+    void accept(const std::vector<uint8_t> &keep = {})
+    {
+        if (!keep.empty() && (int)keep.size() != K_)
+            throw std::invalid_argument("PeelChains::accept: one flag per chain");
+        ctx_.check(mtt_peel_chains_accept(s_, keep.empty() ? nullptr : keep.data()));
+    }
+    long long lastEntries() const { return (long long)mtt_peel_chains_last_entries(s_); }
+
+private:
+    const Context &ctx_;
+    int K_, n_;
+    mtt_peel_chains *s_ = nullptr;
+    std::vector<int32_t> par_;
+    std::vector<double> hgt_;
 };
 
 // ------------------------------------------------------------------------------------------

@@ -49,6 +49,13 @@ public final class MttNative implements AutoCloseable {
     private static final MethodHandle PEEL_SET_HKY = h("mtt_peel_set_hky", FunctionDescriptor.of(JAVA_INT, ADDRESS, JAVA_DOUBLE));
     private static final MethodHandle PEEL_LOGL = h("mtt_peel_logl_batch", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_LONG, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle CHAINS_CREATE = h("mtt_peel_chains_create", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, JAVA_INT, ADDRESS));
+    private static final MethodHandle CHAINS_DESTROY = h("mtt_peel_chains_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
+    private static final MethodHandle CHAINS_UPDATE = h("mtt_peel_chains_update", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle CHAINS_ACCEPT = h("mtt_peel_chains_accept", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, ADDRESS));
 
     /** status codes of mtt_unif_* (MTT_ST_*) */
     public static final int ST_OK = 0, ST_NO_VALID_PATH = 1, ST_PBA_RUBBISH = 2, ST_FB_FELL_THROUGH = 3,
@@ -180,7 +187,34 @@ public final class MttNative implements AutoCloseable {
         public void logLBatch(long B, MemorySegment parent, MemorySegment height, MemorySegment logL) {
             call(PEEL_LOGL, h, B, parent, height, logL);
         }
+        /** Resident chains on this handle's alignment (mtt_peel_chains_*). */
+        public Chains newChains(int nChains) { return new Chains(h, nChains); }
         @Override public void close() { call(PEEL_DESTROY, h); }
+    }
+
+    /** Partials resident in HBM, dirty-node updates, accept / reject (mtt_peel_chains_*). */
+    public final class Chains implements AutoCloseable {
+        private final MemorySegment s;
+
+        Chains(MemorySegment peel, int nChains) {
+            try (Arena a = Arena.ofConfined()) {
+                MemorySegment out = a.allocate(ADDRESS);
+                check((int) CHAINS_CREATE.invoke(peel, nChains, out));
+                s = out.get(ADDRESS, 0);
+            } catch (RuntimeException e) {
+                throw e;
+            } catch (Throwable t) {
+                throw new RuntimeException(t);
+            }
+        }
+
+        /** branchRates, kappa, clockRate, dirty may be MemorySegment.NULL */
+        public void update(MemorySegment parent, MemorySegment height, MemorySegment branchRates,
+                           MemorySegment kappa, MemorySegment clockRate, MemorySegment dirty, MemorySegment logL) {
+            call(CHAINS_UPDATE, s, parent, height, branchRates, kappa, clockRate, dirty, logL);
+        }
+        public void accept(MemorySegment mask) { call(CHAINS_ACCEPT, s, mask); }
+        @Override public void close() { call(CHAINS_DESTROY, s); }
     }
 
     public Peel newPeel(int nTips, long nPatterns, int nCat) { return new Peel(nTips, nPatterns, nCat); }

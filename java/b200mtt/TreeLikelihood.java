@@ -3,7 +3,10 @@
  * reference wires (examples/structuredCoalescent.xml:568-572; fxtemplates/MultiTypeTree.xml:184-197):
  * Inputs "data", "tree", "siteModel", "branchRateModel" are inherited from GenericTreeLikelihood;
  * nucleotide data, HKY, gamma categories / proportion invariant, strict clock.  Peeling runs on the
- * B200 through mtt_peel_logl_batch.  NOT compiled here (no JDK).
+ * B200 on ONE resident chain (mtt_peel_chains_*): the partials of every internal node stay in HBM,
+ * calculateLogP() recomputes the nodes above the dirty ones (Node.isDirty(), as
+ * TreeLikelihood.traverse [EXT]), accept() / restore() keep or drop the proposal -- the roles of
+ * BeerLikelihoodCore's currentPartialsIndex / storedPartialsIndex.  NOT compiled here (no JDK).
  */
 package b200mtt;
 
@@ -26,8 +29,11 @@ public class TreeLikelihood extends GenericTreeLikelihood {
 
     private MttNative nativeLib;
     private MttNative.Peel peel;
+    private MttNative.Chains chain;
     private Arena arena;
-    private MemorySegment parent, height, rates, props, freqs, out;
+    private MemorySegment parent, height, dirty, one, zero, rates, props, freqs, out;
+    private double[] lastRates, lastProps, lastFreqs;
+    private double lastPInv = Double.NaN, lastClock = Double.NaN, lastKappa = Double.NaN;
     private int nTips, nCat;
 
     @Override
@@ -62,6 +68,9 @@ public class TreeLikelihood extends GenericTreeLikelihood {
         parent = arena.allocate(4L * N, 16); height = arena.allocate(8L * N, 16);
         rates = arena.allocate(8L * nCat, 8); props = arena.allocate(8L * nCat, 8);
         freqs = arena.allocate(32, 8); out = arena.allocate(8, 8);
+        dirty = arena.allocate(N, 8); one = arena.allocate(1, 1); zero = arena.allocate(1, 1);
+        one.set(JAVA_BYTE, 0, (byte) 1);
+        chain = peel.newChains(1);
     }
 
     @Override
@@ -74,19 +83,41 @@ public class TreeLikelihood extends GenericTreeLikelihood {
         for (int c = 0; c < nCat; c++) { rates.setAtIndex(JAVA_DOUBLE, c, r[c]); props.setAtIndex(JAVA_DOUBLE, c, pr[c]); }
         for (int i = 0; i < 4; i++) freqs.setAtIndex(JAVA_DOUBLE, i, f[i]);
         double clockRate = clock == null ? 1.0 : clock.getRateForBranch(tree.getRoot().getLeft());   // strict clock
-        peel.setSiteModel(rates, props, freqs, site.getProportionInvariant(), clockRate);
-        peel.setHky(hky.kappaInput.get().getValue());
-        for (Node node : tree.getNodesAsArray()) {
-            parent.setAtIndex(JAVA_INT, node.getNr(), node.isRoot() ? -1 : node.getParent().getNr());
-            height.setAtIndex(JAVA_DOUBLE, node.getNr(), node.getHeight());
+        double kappa = hky.kappaInput.get().getValue(), pInv = site.getProportionInvariant();
+        // the setters make every resident partial stale: only call them when a value moved
+        if (!java.util.Arrays.equals(r, lastRates) || !java.util.Arrays.equals(pr, lastProps)
+                || !java.util.Arrays.equals(f, lastFreqs) || pInv != lastPInv || clockRate != lastClock) {
+            peel.setSiteModel(rates, props, freqs, pInv, clockRate);
+            lastRates = r.clone(); lastProps = pr.clone(); lastFreqs = f.clone(); lastPInv = pInv; lastClock = clockRate;
         }
-        peel.logLBatch(1, parent, height, out);
+        if (kappa != lastKappa) { peel.setHky(kappa); lastKappa = kappa; }
+        for (Node node : tree.getNodesAsArray()) {
+            int nr = node.getNr();
+            parent.setAtIndex(JAVA_INT, nr, node.isRoot() ? -1 : node.getParent().getNr());
+            height.setAtIndex(JAVA_DOUBLE, nr, node.getHeight());
+            dirty.set(JAVA_BYTE, nr, (byte) (node.isDirty() != beast.base.evolution.tree.Tree.IS_CLEAN ? 1 : 0));
+        }
+        // the flagged nodes are compared with the accepted tree; only the nodes above a real
+        // change are recomputed (all of them after a setter above)
+        chain.update(parent, height, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, dirty, out);
         logP = out.get(JAVA_DOUBLE, 0);
         return logP;
     }
 
+    /** BEAST calls store() before a proposal: the library's accepted state already is the stored one. */
+    @Override
+    public void store() { super.store(); }
+
+    /** proposal rejected: drop it (BeerLikelihoodCore.restore) */
+    @Override
+    public void restore() { chain.accept(zero); super.restore(); }
+
+    /** proposal accepted: its partials become the accepted ones */
+    @Override
+    protected void accept() { chain.accept(one); super.accept(); }
+
     @Override
     protected boolean requiresRecalculation() {
-        return true;      // full re-evaluation per call: ~25 us of kernel time for 1000 tips x 10k sites
+        return true;      // the library decides what to recompute (nothing when nothing changed)
     }
 }

@@ -96,6 +96,27 @@ int main(int argc, char **argv)
                     data.getPatternCount(), data.getSiteCount());
         if (!(std::fabs(got - want) <= 1e-9 * std::fabs(want)))
             return 1;
+
+        // resident chains: a height move on one of two chains, accept, reject
+        mtt::PeelChains chains(lik, 2);
+        mtt::MultiTypeTree a = tree, b = tree;
+        std::vector<double> l0 = chains.update({&a, &b});
+        chains.accept();
+        int v = b.parent[0];                           // (t1, t2), below the root
+        if (b.parent[v] < 0)
+            v = b.parent[2];
+        b.height[v] = 0.5 * (b.height[v] + b.height[b.parent[v]]);
+        std::vector<double> l1 = chains.update({&a, &b});
+        const long long entries = chains.lastEntries();
+        const double wantB = lik.calculateLogP(b);
+        chains.accept({1, 0});                         // chain 1 rejects: back to `tree`
+        std::vector<double> l2 = chains.update({&a, &tree});
+        std::printf("CHAINS %.12f %.12f moved %.12f full %.12f entries %lld then %lld\n", l0[0],
+                    l0[1], l1[1], wantB, entries, chains.lastEntries());
+        auto close = [](double x, double y) { return std::fabs(x - y) <= 1e-12 * std::fabs(y); };
+        if (!close(l0[0], got) || l0[1] != l0[0] || l1[0] != l0[0] || l2[1] != l0[1] ||
+            !close(l1[1], wantB) || entries < 1 || entries > 3 || chains.lastEntries() != 0)
+            return 1;
     }
 
     // ---------------------------------------------------------------- piece 3

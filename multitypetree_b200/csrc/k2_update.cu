@@ -236,7 +236,6 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
     issue(0);
     cp_async_wait<0>();
     __syncthreads();
-    matrices(0);
 
     double prev[C][1][4], prevScale = 0.0;
     // child 2 of the entry about to run, fetched one entry ahead
@@ -255,9 +254,10 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
     };
 #pragma unroll 1
     for (int j = 0; j < nStages; j++) {
+        // (this stage's entries have landed; the other buffer was released by the barrier at the
+        // end of the previous round)
         if (j + 1 < nStages)
-            issue(j + 1);               // the other buffer was released by the barrier below
-        __syncthreads();                // this stage's matrices are in place
+            issue(j + 1);
         const UpdOp *sOps = reinterpret_cast<const UpdOp *>(stage[j & 1]);
         const double *sMats = reinterpret_cast<const double *>(stage[j & 1] + CH * OPB);
         const int cnt = min(CH, k1 - k0 - j * CH);
@@ -276,6 +276,9 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
             }
         }
         fetch2(sOps[0]);
+        // ... and while those are in flight, the stage's transition matrices
+        matrices(j);
+        __syncthreads();
 #pragma unroll 1
         for (int e = 0; e < cnt; e++) {
             const UpdOp &op = sOps[e];
@@ -343,11 +346,9 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
                 *dst = prev[r >> 2][0][r & 3];
             *dst = ls;
         }
-        if (j + 1 < nStages) {
+        if (j + 1 < nStages)
             cp_async_wait<0>();
-            __syncthreads();            // the next stage's entries have landed
-            matrices(j + 1);
-        }
+        __syncthreads();                // done with this stage; the next one's entries have landed
     }
 
     // the last entry is the root

@@ -111,7 +111,7 @@ int main(int argc, char **argv)
         const double wantB = lik.calculateLogP(b);
         chains.accept({1, 0});                         // chain 1 rejects: back to `tree`
         std::vector<double> l2 = chains.update({&a, &tree});
-        std::printf("CHAINS %.12f %.12f moved %.12f full %.12f entries %lld then %lld\n", l0[0],
+        std::printf("RESIDENT %.12f %.12f moved %.12f full %.12f entries %lld then %lld\n", l0[0],
                     l0[1], l1[1], wantB, entries, chains.lastEntries());
         auto close = [](double x, double y) { return std::fabs(x - y) <= 1e-12 * std::fabs(y); };
         if (!close(l0[0], got) || l0[1] != l0[0] || l1[0] != l0[0] || l2[1] != l0[1] ||

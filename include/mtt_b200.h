@@ -328,6 +328,13 @@ int mtt_peel_chains_destroy(mtt_peel_chains *s);
 int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
                            const double *branchRates, const double *kappa,
                            const double *clockRate, const uint8_t *dirty, double *logL);
+/* update on a pattern shard (the handle holds a contiguous slice of the patterns, the chains'
+ * trees are replicated on every rank): parts[3][nChains] as mtt_peel_logl_parts_batch -- summed
+ * over the shards, parts[2] > 0 ? parts[1] : parts[0] is the proposal's log-likelihood; every
+ * rank then answers with the same accept mask */
+int mtt_peel_chains_update_parts(mtt_peel_chains *s, const int32_t *parent, const double *height,
+                                 const double *branchRates, const double *kappa,
+                                 const double *clockRate, const uint8_t *dirty, double *parts);
 int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept);
 /* nodes recomputed by the last update, over all chains */
 int64_t mtt_peel_chains_last_entries(const mtt_peel_chains *s);

@@ -69,7 +69,8 @@ struct Chain {
     };
     std::vector<Node> nd;
     int root = -1, rootCount = 0, epoch = 0, walkId = 0;
-    double kappa = 0.0, clock = 0.0, logL = 0.0;
+    double kappa = 0.0, clock = 0.0;
+    double logL[4] = {0.0, 0.0, 0.0, 0.0};      // picked evaluation, unscaled sum, rescaled sum, flag
     bool valid = false, pending = false;
     // journal of the pending proposal
     struct NodeUndo { int node, parent; double height, rate; };
@@ -78,7 +79,7 @@ struct Chain {
     std::vector<KidsUndo> undoKids;
     std::vector<int> flipped, changed, moved;
     int oldRoot = -1, oldRootCount = 0;
-    double oldKappa = 0.0, oldClock = 0.0, oldLogL = 0.0;
+    double oldKappa = 0.0, oldClock = 0.0, oldLogL[4] = {0.0, 0.0, 0.0, 0.0};
     bool oldValid = false;
 
     void begin()
@@ -90,7 +91,7 @@ struct Chain {
         oldRootCount = rootCount;
         oldKappa = kappa;
         oldClock = clock;
-        oldLogL = logL;
+        memcpy(oldLogL, logL, sizeof logL);
         oldValid = valid;
         pending = true;
     }
@@ -112,7 +113,7 @@ struct Chain {
         rootCount = oldRootCount;
         kappa = oldKappa;
         clock = oldClock;
-        logL = oldLogL;
+        memcpy(logL, oldLogL, sizeof logL);
         valid = oldValid;
         pending = false;
         undoNodes.clear();
@@ -182,7 +183,7 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
                const double *weights, const uint8_t *constMask, const double *site, double pInv,
                const UpdOp *ops, const int *opOff, const int *chainOrder,
                const double *kappaPerChain, double *store, double *partial, int nTiles,
-               int *tilesDone, double *logL)
+               int *tilesDone, double *logL, long long nChains)
 {
     constexpr int CH = upd_stage_entries(C);
     constexpr int OPB = (int)sizeof(UpdOp), MATB = 2 * C * 16 * 8, STAGE = CH * (OPB + MATB);
@@ -414,7 +415,12 @@ k2_peel_update(int n, long long P, long long pStride, const uint8_t *states,
             }
         }
         if (lane == 0) {
+            // logL[4][nChains]: the evaluation BEAST would return, and the parts a pattern shard
+            // hands to the all-reduce (unscaled sum, rescaled sum, tiles that underflowed)
             logL[chain] = (fl > 0.0) ? sQ : sU;
+            logL[nChains + chain] = sU;
+            logL[2 * nChains + chain] = sQ;
+            logL[3 * nChains + chain] = fl;
             tilesDone[chain] = 0;       // ready for the next update
         }
     }
@@ -429,7 +435,7 @@ int launch_update(mtt_peel_chains *s, const UpdOp *dOps, const int *dOpOff, cons
     dim3 grid((unsigned)nTiles, (unsigned)nActive);
     k2_peel_update<C><<<grid, UPD_THREADS, 0, ctx->stream>>>(
         h->nTips, h->nPatterns, h->pStride, h->dStates, h->dWeights, h->dConst, h->dSite, h->pInv,
-        dOps, dOpOff, dOrder, dKappa, s->dStore, s->dPart, nTiles, s->dDone, dLogL);
+        dOps, dOpOff, dOrder, dKappa, s->dStore, s->dPart, nTiles, s->dDone, dLogL, s->K);
     MTT_CHECK_LAUNCH(ctx);
     return MTT_OK;
 }
@@ -697,9 +703,9 @@ int mtt_peel_chains_destroy(mtt_peel_chains *s)
     return MTT_OK;
 }
 
-int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
-                           const double *branchRates, const double *kappa,
-                           const double *clockRate, const uint8_t *dirty, double *logL)
+static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
+                         const double *branchRates, const double *kappa, const double *clockRate,
+                         const uint8_t *dirty, double *logL, double *parts)
 {
     if (!s || !s->h)
         return MTT_ERR_STATE;               // (the handle was destroyed)
@@ -708,7 +714,7 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
     int rc = k2_check_ready(h, kappa == nullptr);
     if (rc != MTT_OK)
         return rc;
-    if (!parent || !height || !logL)
+    if (!parent || !height || (!logL && !parts))
         return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_peel_chains_update: bad arguments");
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
     const int n = h->nTips, N = 2 * n - 1, C = h->nCat, K = s->K;
@@ -748,7 +754,7 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
         UpdOp *dOps = nullptr;
         int *dOpOff = nullptr;
         double *dKappa = nullptr, *dLogL = nullptr;
-        std::vector<double> got(K);
+        std::vector<double> got((size_t)4 * K);
         // chains with something to do, the longest lists first
         std::vector<int> &order = s->order;
         order.clear();
@@ -790,18 +796,36 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
             MTT_CUDA(ctx, cudaEventElapsedTime(&s->lastMs, s->ev0, s->ev1));
         for (int k = 0; k < K; k++)
             if (s->opOff[k + 1] > s->opOff[k])
-                s->chains[k].logL = got[k];
+                for (int q = 0; q < 4; q++)
+                    s->chains[k].logL[q] = got[(size_t)q * K + k];
     }
     for (int k = 0; k < K; k++) {
         Chain &c = s->chains[k];
-        if (bad[k]) {
-            logL[k] = NAN;                  // malformed tree: NaN, loudly; the chain keeps its state
-            continue;
-        }
-        c.valid = true;                     // (of the proposal; undo() restores the old flag)
-        logL[k] = c.logL;                   // unchanged when nothing had to be recomputed
+        if (!bad[k])
+            c.valid = true;                 // (of the proposal; undo() restores the old flag)
+        // malformed tree: NaN, loudly, and the chain keeps its state; otherwise the proposal's
+        // values -- the accepted ones when nothing had to be recomputed
+        if (logL)
+            logL[k] = bad[k] ? NAN : c.logL[0];
+        if (parts)
+            for (int q = 0; q < 3; q++)
+                parts[(size_t)q * K + k] = bad[k] ? NAN : c.logL[q + 1];
     }
     return MTT_OK;
+}
+
+int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
+                           const double *branchRates, const double *kappa,
+                           const double *clockRate, const uint8_t *dirty, double *logL)
+{
+    return chains_update(s, parent, height, branchRates, kappa, clockRate, dirty, logL, nullptr);
+}
+
+int mtt_peel_chains_update_parts(mtt_peel_chains *s, const int32_t *parent, const double *height,
+                                 const double *branchRates, const double *kappa,
+                                 const double *clockRate, const uint8_t *dirty, double *parts)
+{
+    return chains_update(s, parent, height, branchRates, kappa, clockRate, dirty, nullptr, parts);
 }
 
 int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept)

@@ -282,10 +282,12 @@ class PeelChains:
                                                          C.byref(self._s)))
 
     def update(self, parent: np.ndarray, height: np.ndarray, branchRates=None, kappa=None,
-               clockRate=None, dirty=None) -> np.ndarray:
+               clockRate=None, dirty=None, parts: bool = False) -> np.ndarray:
         """parent/height [nChains][2*nTips-1] of the proposals -> logL[nChains].  `dirty`
         (optional, same shape, nonzero = the node may differ from the chain's accepted tree,
-        ``Node.isDirty()``) restricts the comparison to the flagged nodes."""
+        ``Node.isDirty()``) restricts the comparison to the flagged nodes.  ``parts=True`` (the
+        likelihood holds a pattern shard): parts[3][nChains] for the all-reduce over shards, see
+        ``parallel.pattern_sharded_logl_parts``."""
         K = self.nChains
         par = _lib.as_c(parent, np.int32)
         h = _lib.as_c(height, np.float64)
@@ -301,10 +303,10 @@ class PeelChains:
         d = None if dirty is None else _flags(dirty)
         if d is not None and d.shape != h.shape:
             raise ValueError("dirty must have the shape of height")
-        out = np.empty(K, np.float64)
-        self.ctx.check(_lib.lib().mtt_peel_chains_update(
-            self._s, _lib.ptr(par), _lib.ptr(h), _lib.ptr(r), _lib.ptr(kap), _lib.ptr(clk),
-            _lib.ptr(d), _lib.ptr(out)))
+        out = np.empty((3, K) if parts else K, np.float64)
+        fn = _lib.lib().mtt_peel_chains_update_parts if parts else _lib.lib().mtt_peel_chains_update
+        self.ctx.check(fn(self._s, _lib.ptr(par), _lib.ptr(h), _lib.ptr(r), _lib.ptr(kap),
+                          _lib.ptr(clk), _lib.ptr(d), _lib.ptr(out)))
         return out
 
     def accept(self, mask=None) -> None:

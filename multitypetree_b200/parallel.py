@@ -91,3 +91,13 @@ def pattern_sharded_logl_parts(compute_parts: Callable[[], np.ndarray], group=No
     all-reduce, over ALL patterns."""
     parts = allreduce_sum(np.asarray(compute_parts(), np.float64).copy(), group)
     return np.where(parts[2] > 0, parts[1], parts[0])
+
+
+def pattern_sharded_chains_update(chains, parent, height, group=None, **kw) -> np.ndarray:
+    """One proposal per resident chain when every rank holds a pattern shard (`chains` is a
+    ``PeelChains`` of a TreeLikelihood built on ``alignment.shard(rank, world)``; trees are
+    replicated): this rank's parts of ``mtt_peel_chains_update_parts``, one all-reduce of
+    3 x nChains doubles, BEAST's choice between its two evaluations over ALL patterns.  Every rank
+    gets the same logL[nChains] and must answer with the same ``chains.accept(mask)``."""
+    return pattern_sharded_logl_parts(lambda: chains.update(parent, height, parts=True, **kw),
+                                      group)

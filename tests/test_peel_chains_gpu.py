@@ -77,6 +77,8 @@ def _propose(rng, par, hgt, n):
 @pytest.mark.parametrize("n,sites,gamma,pInv,useDirty", [(40, 500, 0, 0.0, False),
                                                          (40, 500, 4, 0.1, True),
                                                          (17, 300, 3, 0.0, True),
+                                                         (2, 60, 0, 0.0, True),
+                                                         (3, 60, 2, 0.1, False),
                                                          (150, 260, 0, 0.2, False)])
 def test_chains_follow_full_evaluation(ctx, n, sites, gamma, pInv, useDirty):
     K, steps = 6, 40
@@ -119,7 +121,7 @@ def test_chains_follow_full_evaluation(ctx, n, sites, gamma, pInv, useDirty):
         else:
             ch.accept(acc)
         par[acc], hgt[acc], kap[acc], accLogL[acc] = ppar[acc], phgt[acc], pkap[acc], got[acc]
-    assert sawPartial
+    assert sawPartial or n <= 3
     # the accepted states survived all of that
     got = ch.update(par, hgt, kappa=kap)
     assert ch.last_entries == 0
@@ -273,3 +275,50 @@ def test_chains_outliving_their_handle_fail_loudly(ctx):
     with pytest.raises(mtt.MttError):
         ch.accept()
     ch.close()
+
+
+@pytest.mark.parametrize("n,rate,pInv", [(40, 0.05, 0.0), (1000, 50.0, 0.2)])
+def test_chains_on_pattern_shards_sum_to_the_whole(ctx, n, rate, pInv):
+    """config-4 regime: each rank holds a contiguous slice of the patterns and the chains' trees;
+    the per-shard parts, summed, give the whole alignment's value -- including BEAST's switch to
+    the rescaled evaluation, which no shard can decide alone (the 1000-tip case underflows)."""
+    from multitypetree_b200 import parallel
+    K, world = 3, 3
+    rng = np.random.default_rng(n)
+    par, hgt = _trees(K, n, d=4, seed=n + 1)
+    f = np.array([.3, .2, .2, .3])
+    tips = simulate_alignment(par[0], hgt[0], 700, 2.0, f, rate, seed=5)
+    al = Alignment(states=tips, compress=False)
+    sm = SiteModel(HKY(2.0, f), mutationRate=rate, proportionInvariant=pInv)
+    whole = TreeLikelihood(data=al, siteModel=sm, ctx=ctx)
+    shards = [TreeLikelihood(data=al.shard(r, world), siteModel=sm, ctx=ctx) for r in range(world)]
+    chains = [tl.chains(K) for tl in shards]
+
+    def sharded(par, hgt):
+        parts = sum(ch.update(par, hgt, parts=True) for ch in chains)      # the all-reduce
+        return np.where(parts[2] > 0, parts[1], parts[0])
+
+    got = sharded(par, hgt)
+    np.testing.assert_allclose(got, whole.calculateLogPBatch(par, hgt), rtol=RTOL_FULL)
+    np.testing.assert_allclose(got, _oracle(al, par, hgt, sm), rtol=RTOL)
+    for ch in chains:
+        ch.accept()
+    for step in range(5):
+        ppar, phgt = par.copy(), hgt.copy()
+        for k in range(K):
+            _propose(rng, ppar[k], phgt[k], n)
+        got = sharded(ppar, phgt)
+        assert sum(ch.last_entries for ch in chains) < world * K * (n - 1)
+        np.testing.assert_allclose(got, whole.calculateLogPBatch(ppar, phgt), rtol=RTOL_FULL)
+        acc = rng.random(K) < 0.5
+        for ch in chains:
+            ch.accept(acc)
+        par[acc], hgt[acc] = ppar[acc], phgt[acc]
+    # the helper of parallel.py outside torch.distributed is the single-shard case
+    one = whole.chains(K)
+    np.testing.assert_allclose(parallel.pattern_sharded_chains_update(one, par, hgt),
+                               whole.calculateLogPBatch(par, hgt), rtol=RTOL_FULL)
+    for x in chains + [one]:
+        x.close()
+    for tl in shards + [whole]:
+        tl.close()

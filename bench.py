@@ -516,6 +516,7 @@ def bench_peel_chains(args):
     sides: the planner's host time is part of the number."""
     import torch
     import multitypetree_b200 as mtt
+    from multitypetree_b200 import _lib
     from multitypetree_b200.likelihood import (Alignment, HKY, SiteModel, TreeLikelihood,
                                                simulate_alignment)
     world, rank, local = dist_setup(args.gpus)
@@ -526,7 +527,8 @@ def bench_peel_chains(args):
     m, N = mtt.synthetic_model(d)
     tb = mtt.simulate_trees(K, n, d, m, N, seed=3000 + rank * K, nThreads=max(1, cores // world))
     nN = 2 * n - 1
-    par, hgt = tb.parent.reshape(K, nN).copy(), tb.height.reshape(K, nN).copy()
+    par = np.ascontiguousarray(tb.parent.reshape(K, nN), np.int32).copy()
+    hgt = np.ascontiguousarray(tb.height.reshape(K, nN), np.float64).copy()
     f = np.array([.25] * 4)
     ref = mtt.simulate_trees(1, n, d, m, N, seed=3000)
     clock = 0.2 / float(ref.height.max())
@@ -559,9 +561,11 @@ def bench_peel_chains(args):
         dirty[rows, v] = 1
         return ph, dirty
 
-    first = ch.update(par, hgt)
+    ch.update(par, hgt)
     ch.accept()
-    full0 = tl.calculateLogPBatch(par, hgt)
+    L = _lib.lib()
+    got = np.empty(K, np.float64)
+    par_p, got_p = _lib.ptr(par), _lib.ptr(got)
     t_upd = t_full = dev_ms = 0.0
     entries = dev_entries = 0
     err = 0.0
@@ -575,12 +579,15 @@ def bench_peel_chains(args):
             timed = args.warmup <= it < args.warmup + args.steps
             if it == args.warmup + args.steps:
                 ch.set_timing(True)
-            acc = rng.random(K) < 0.5
+            acc = (rng.random(K) < 0.5).astype(np.uint8)
             lf0 = ctx.launch_count()
+            # the C-ABI calls a Java shim would make, on the caller's buffers
             t0 = time.perf_counter()
-            got = ch.update(par, ph, dirty=dirty)
-            ch.accept(acc)
+            ctx.check(L.mtt_peel_chains_update(ch._s, par_p, _lib.ptr(ph), None, None, None,
+                                               _lib.ptr(dirty), got_p))
+            ctx.check(L.mtt_peel_chains_accept(ch._s, _lib.ptr(acc)))
             dt = time.perf_counter() - t0
+            acc = acc != 0
             if timed:
                 t_upd += dt
                 entries += ch.last_entries

@@ -151,7 +151,10 @@ struct mtt_peel_chains {
 
 namespace {
 
-constexpr int UPD_THREADS = 128;
+#ifndef MTT_K2U_THREADS
+#define MTT_K2U_THREADS 128
+#endif
+constexpr int UPD_THREADS = MTT_K2U_THREADS;
 
 __device__ __forceinline__ void cp_async16(void *dst, const void *src)
 {
@@ -703,6 +706,63 @@ int mtt_peel_chains_destroy(mtt_peel_chains *s)
     return MTT_OK;
 }
 
+// device side of an update: the lists of all chains in one launch; got[4][K]
+static int chains_launch(mtt_peel_chains *s, const std::vector<double> &kap,
+                         std::vector<double> &got)
+{
+    mtt_peel *h = s->h;
+    mtt_ctx *ctx = h->ctx;
+    const int C = h->nCat, K = s->K;
+    int rc;
+    const int nTiles = (int)(h->pStride / UPD_THREADS);
+    if ((rc = grow(ctx, s->dPart, s->partCap, (size_t)K * nTiles * 24)) != MTT_OK)
+        return rc;
+    Xfer x(ctx);
+    UpdOp *dOps = nullptr;
+    int *dOpOff = nullptr;
+    double *dKappa = nullptr, *dLogL = nullptr;
+    // chains with something to do, the longest lists first
+    std::vector<int> &order = s->order;
+    order.clear();
+    for (int k = 0; k < K; k++)
+        if (s->opOff[k + 1] > s->opOff[k])
+            order.push_back(k);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return s->opOff[a + 1] - s->opOff[a] > s->opOff[b + 1] - s->opOff[b];
+    });
+    const int nActive = (int)order.size();
+    int *dOrder = nullptr;
+    x.in(s->ops.data(), s->ops.size(), BUF_C_OPS, &dOps);
+    x.in(s->opOff.data(), s->opOff.size(), BUF_C_OPOFF, &dOpOff);
+    x.in(order.data(), order.size(), BUF_C_ORDER, &dOrder);
+    x.in(kap.data(), kap.size(), BUF_C_KAPPA, &dKappa);
+    x.out(got.data(), got.size(), BUF_C_LOGL, &dLogL);
+    if ((rc = x.prepare()) != MTT_OK || (rc = x.upload()) != MTT_OK)
+        return rc;
+    if (s->timing)
+        MTT_CUDA(ctx, cudaEventRecord(s->ev0, ctx->stream));
+    switch (C) {
+    case 1: rc = launch_update<1>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 2: rc = launch_update<2>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 3: rc = launch_update<3>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 4: rc = launch_update<4>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 5: rc = launch_update<5>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 6: rc = launch_update<6>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 7: rc = launch_update<7>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    case 8: rc = launch_update<8>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
+    default: rc = mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: nCat=%d outside [1,8]", C);
+    }
+    if (rc != MTT_OK)
+        return rc;
+    if (s->timing)
+        MTT_CUDA(ctx, cudaEventRecord(s->ev1, ctx->stream));
+    if ((rc = x.download()) != MTT_OK)
+        return rc;
+    if (s->timing)
+        MTT_CUDA(ctx, cudaEventElapsedTime(&s->lastMs, s->ev0, s->ev1));
+    return MTT_OK;
+}
+
 static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
                          const double *branchRates, const double *kappa, const double *clockRate,
                          const uint8_t *dirty, double *logL, double *parts)
@@ -717,7 +777,7 @@ static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double
     if (!parent || !height || (!logL && !parts))
         return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_peel_chains_update: bad arguments");
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
-    const int n = h->nTips, N = 2 * n - 1, C = h->nCat, K = s->K;
+    const int n = h->nTips, N = 2 * n - 1, K = s->K;
     for (Chain &c : s->chains)
         if (c.pending)
             c.undo();                      // an unanswered proposal counts as rejected
@@ -747,53 +807,13 @@ static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double
     s->lastOps = nEntries;
     s->lastMs = 0.0f;
     if (nEntries > 0) {
-        const int nTiles = (int)(h->pStride / UPD_THREADS);
-        if ((rc = grow(ctx, s->dPart, s->partCap, (size_t)K * nTiles * 24)) != MTT_OK)
-            return rc;
-        Xfer x(ctx);
-        UpdOp *dOps = nullptr;
-        int *dOpOff = nullptr;
-        double *dKappa = nullptr, *dLogL = nullptr;
         std::vector<double> got((size_t)4 * K);
-        // chains with something to do, the longest lists first
-        std::vector<int> &order = s->order;
-        order.clear();
-        for (int k = 0; k < K; k++)
-            if (s->opOff[k + 1] > s->opOff[k])
-                order.push_back(k);
-        std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-            return s->opOff[a + 1] - s->opOff[a] > s->opOff[b + 1] - s->opOff[b];
-        });
-        const int nActive = (int)order.size();
-        int *dOrder = nullptr;
-        x.in(s->ops.data(), s->ops.size(), BUF_C_OPS, &dOps);
-        x.in(s->opOff.data(), s->opOff.size(), BUF_C_OPOFF, &dOpOff);
-        x.in(order.data(), order.size(), BUF_C_ORDER, &dOrder);
-        x.in(kap.data(), kap.size(), BUF_C_KAPPA, &dKappa);
-        x.out(got.data(), got.size(), BUF_C_LOGL, &dLogL);
-        if ((rc = x.prepare()) != MTT_OK || (rc = x.upload()) != MTT_OK)
+        if ((rc = chains_launch(s, kap, got)) != MTT_OK) {
+            for (Chain &c : s->chains)
+                if (c.pending)
+                    c.undo();               // no half-evaluated proposals: every chain as accepted
             return rc;
-        if (s->timing)
-            MTT_CUDA(ctx, cudaEventRecord(s->ev0, ctx->stream));
-        switch (C) {
-        case 1: rc = launch_update<1>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 2: rc = launch_update<2>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 3: rc = launch_update<3>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 4: rc = launch_update<4>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 5: rc = launch_update<5>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 6: rc = launch_update<6>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 7: rc = launch_update<7>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        case 8: rc = launch_update<8>(s, dOps, dOpOff, dOrder, nActive, nTiles, dKappa, dLogL); break;
-        default: rc = mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: nCat=%d outside [1,8]", C);
         }
-        if (rc != MTT_OK)
-            return rc;
-        if (s->timing)
-            MTT_CUDA(ctx, cudaEventRecord(s->ev1, ctx->stream));
-        if ((rc = x.download()) != MTT_OK)
-            return rc;
-        if (s->timing)
-            MTT_CUDA(ctx, cudaEventElapsedTime(&s->lastMs, s->ev0, s->ev1));
         for (int k = 0; k < K; k++)
             if (s->opOff[k + 1] > s->opOff[k])
                 for (int q = 0; q < 4; q++)

@@ -218,6 +218,24 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
                           uint8_t *outChgType, double *logProb, int32_t *status,
                           int32_t *nVirt, int64_t *uUsed);
 
+/* NodeRetype.proposal (operators/NodeRetype.java:31-63) in ONE device call: the probability of
+ * the current typing of nOld branches (:40-44, arguments and outputs of
+ * mtt_unif_branch_logp_batch) and the retyping of nJobs jobs (:52-56, arguments and outputs of
+ * mtt_unif_retype_batch).  The first draws no random numbers, so it runs beside the second on
+ * another stream; results are those of the two separate calls, bit for bit. */
+int mtt_unif_node_retype_batch(mtt_ctx *ctx, int64_t nOld, const int32_t *modelOld,
+                               const double *tBottomOld, const double *tTopOld,
+                               const uint8_t *typeBottomOld, const uint8_t *typeTopOld,
+                               const int64_t *chgOff, const double *chgTime,
+                               const uint8_t *chgType, double *logProbOld, int32_t *statusOld,
+                               int64_t nJobs, const int64_t *brOff, const int32_t *model,
+                               const double *tBottom, const double *tTop,
+                               const uint8_t *typeBottom, const uint8_t *typeTop,
+                               const int32_t *nVirtForced, const double *uniforms,
+                               const int64_t *uOff, int outCap, int32_t *nChg,
+                               double *outChgTime, uint8_t *outChgType, double *logProb,
+                               int32_t *status, int32_t *nVirt, int64_t *uUsed);
+
 /* ------------------------------------------------------------------ next row: untyped density
  * Replaces distributions/StructuredCoalescentUntypedTreeDensity.java:116-207 (calculateLogP)
  * with :216-290 (colourFirstLineage), :292-316 (colourLineage), :386-512 (addTypeChanges):

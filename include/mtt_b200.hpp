@@ -13,6 +13,7 @@
 #pragma once
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -630,9 +631,9 @@ private:
 // ------------------------------------------------------------------------------------------
 // piece 3: operators/UniformizationRetypeOperator.java + operators/NodeRetype.java.
 // One NodeRetype per chain (its own tree and Randomizer); `NodeRetypeEnsemble::proposal()`
-// advances all chains by one proposal in lock step -- ONE mtt_unif_branch_logp_batch and ONE
-// mtt_unif_retype_batch per step for the whole ensemble (config 5: 64 chains), the jobs that
-// need host action (longer uniform window, Poisson tail) being resubmitted.
+// advances all chains by one proposal in lock step -- ONE mtt_unif_node_retype_batch per step
+// for the whole ensemble (config 5: 64 chains), the jobs that need host action (longer uniform
+// window, Poisson tail) being resubmitted through mtt_unif_retype_batch.
 class NodeRetypeEnsemble {
 public:
     struct Chain {
@@ -642,7 +643,7 @@ public:
     };
     // m: nModels dense d x d backward-rate matrices; useSymmetrizedRates as in the reference
     NodeRetypeEnsemble(const Context &ctx, int nModels, int d, const std::vector<double> &m,
-                       bool useSymmetrizedRates = false, int uniformWindow = 256)
+                       bool useSymmetrizedRates = false, int uniformWindow = 128)
         : ctx_(ctx), d_(d), window_(uniformWindow)
     {
         ctx_.check(mtt_unif_set_models(ctx_.get(), nModels, d, m.data(), useSymmetrizedRates));
@@ -656,6 +657,10 @@ public:
         chains_.push_back(Chain{&tree, &rng, model});
     }
     size_t size() const { return chains_.size(); }
+    // measurement: wall time spent inside the two device calls, and retype calls made
+    double secondsInCalls[2] = {0.0, 0.0};
+    long long deviceCalls = 0;
+    long long resubmits[8] = {0, 0, 0, 0, 0, 0, 0, 0};   // by MTT_ST_* of the branch that stopped a job
 
     // One NodeRetype.proposal() per chain; returns the log Hastings ratios
     // (-infinity where the reference returns Double.NEGATIVE_INFINITY, NodeRetype.java:57-58).
@@ -684,18 +689,14 @@ public:
                 off.push_back((int64_t)ct.size());
             }
         }
-        std::vector<double> lp(B_.t0.size());
-        std::vector<int32_t> st(B_.t0.size());
+        // The probability of the current typing draws no random numbers, so it is evaluated in
+        // the same device call as the first round of retyping below (the old node types are
+        // captured here, before the new ones are drawn).
+        const Branches oldB = B_;
+        std::vector<double> lp(oldB.t0.size());
+        std::vector<int32_t> st(oldB.t0.size());
         ct.push_back(0.0);
         cty.push_back(0);
-        ctx_.check(mtt_unif_branch_logp_batch(ctx_.get(), (int64_t)lp.size(), B_.mdl.data(),
-                                              B_.t0.data(), B_.t1.data(), B_.a.data(), B_.b.data(),
-                                              off.data(), ct.data(), cty.data(), lp.data(),
-                                              st.data()));
-        size_t k = 0;
-        for (size_t c = 0; c < C; c++)
-            for (size_t i = 0; i < br[c].size(); i++)
-                logHR[c] += lp[k++];
         // ---- new node type (:47-48), then the branches node -> left -> right (:52-56)
         for (size_t c = 0; c < C; c++)
             chains_[c].tree->nodeType[node[c]] = (uint8_t)chains_[c].rng->nextInt(d_);
@@ -715,6 +716,7 @@ public:
             pending.push_back(j);
         }
         std::vector<char> noPath(C, 0);
+        bool firstRound = true;
         while (!pending.empty()) {
             B_.clear();
             std::vector<int64_t> brOff{0}, uOff{0};
@@ -738,11 +740,30 @@ public:
             std::vector<double> oct(nBr * outCap), olp(nBr);
             std::vector<uint8_t> octy(nBr * outCap);
             std::vector<int64_t> used(pending.size());
-            ctx_.check(mtt_unif_retype_batch(ctx_.get(), (int64_t)pending.size(), brOff.data(),
-                                             B_.mdl.data(), B_.t0.data(), B_.t1.data(), B_.a.data(),
-                                             B_.b.data(), forced.data(), us.data(), uOff.data(),
-                                             outCap, nChg.data(), oct.data(), octy.data(),
-                                             olp.data(), status.data(), nVirt.data(), used.data()));
+            const auto tc1 = std::chrono::steady_clock::now();
+            if (firstRound)
+                ctx_.check(mtt_unif_node_retype_batch(
+                    ctx_.get(), (int64_t)lp.size(), oldB.mdl.data(), oldB.t0.data(),
+                    oldB.t1.data(), oldB.a.data(), oldB.b.data(), off.data(), ct.data(),
+                    cty.data(), lp.data(), st.data(), (int64_t)pending.size(), brOff.data(),
+                    B_.mdl.data(), B_.t0.data(), B_.t1.data(), B_.a.data(), B_.b.data(),
+                    forced.data(), us.data(), uOff.data(), outCap, nChg.data(), oct.data(),
+                    octy.data(), olp.data(), status.data(), nVirt.data(), used.data()));
+            else
+                ctx_.check(mtt_unif_retype_batch(
+                    ctx_.get(), (int64_t)pending.size(), brOff.data(), B_.mdl.data(),
+                    B_.t0.data(), B_.t1.data(), B_.a.data(), B_.b.data(), forced.data(),
+                    us.data(), uOff.data(), outCap, nChg.data(), oct.data(), octy.data(),
+                    olp.data(), status.data(), nVirt.data(), used.data()));
+            secondsInCalls[1] += std::chrono::duration<double>(std::chrono::steady_clock::now() - tc1).count();
+            deviceCalls++;
+            if (firstRound) {
+                size_t k = 0;
+                for (size_t c = 0; c < C; c++)
+                    for (size_t i = 0; i < br[c].size(); i++)
+                        logHR[c] += lp[k++];
+                firstRound = false;
+            }
             std::vector<Job> next;
             for (size_t ji = 0; ji < pending.size(); ji++) {
                 Job &j = pending[ji];
@@ -751,6 +772,7 @@ public:
                 for (size_t x = lo; x < hi; x++)
                     more |= status[x] == MTT_ST_NEED_MORE_UNIFORMS;
                 if (more) {                              // nothing consumed: a longer window
+                    resubmits[MTT_ST_NEED_MORE_UNIFORMS]++;
                     j.window *= 4;
                     next.push_back(j);
                     continue;
@@ -773,6 +795,7 @@ public:
                 if (kOk == hi - lo)
                     continue;                            // job done
                 const int why = status[lo + kOk];
+                resubmits[why & 7]++;
                 if (why == MTT_ST_NO_VALID_PATH) {       // NoValidPathException (:137-140)
                     noPath[j.chain] = 1;
                     continue;

@@ -55,6 +55,9 @@ ABI = {
                                         VP, VP, VP, VP, VP]),
     "mtt_unif_retype_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP,
                                         C.c_int, VP, VP, VP, VP, VP, VP, VP]),
+    "mtt_unif_node_retype_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP,
+                                             C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP,
+                                             C.c_int, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_peel_create": (C.c_int, [VP, C.c_int, C.c_int64, C.c_int, C.POINTER(VP)]),
     "mtt_peel_destroy": (C.c_int, [VP]),
     "mtt_peel_set_tip_states": (C.c_int, [VP, VP]),

@@ -283,14 +283,22 @@ __device__ __forceinline__ BranchSample sample_branch(
     const double *logN, int size, int steady, double mu,
     double t0, double t1, int a, int b, int forced, const double *u, long long nU,
     long long &pos, double *buf, const uint16_t *rc, double *sTimes, uint8_t *sTypes,
-    double *gTimes, uint8_t *gTypes, int scratchCap, int lane, int stageCap = U_TCAP)
+    double *gTimes, uint8_t *gTypes, int scratchCap, int lane, int stageCap = U_TCAP,
+    const double *PbaPre = nullptr)
 {
     const int dd = d * d;
     const int steadyN = steady ? size : -1;                          // RpowSteadyN :460-473
     const double L = sub_rn(t1, t0);                                 // :124
     const double muL = mul_rn(mu, L);                         // :130
-    const double *E = expm_QL(d, Q, L, buf, rc, lane);                   // :132-134
-    const double Pba = E[a * d + b];
+    // expm(Q L)[a,b] (:132-134): evaluated here, or ahead of the sequential sampling by
+    // another warp running the same expm_QL (k3_pba) -- the same bits either way
+    double Pba;
+    if (PbaPre) {
+        Pba = *PbaPre;
+    } else {
+        const double *E = expm_QL(d, Q, L, buf, rc, lane);
+        Pba = E[a * d + b];
+    }
     __syncwarp();
 
     int st = MTT_ST_OK, nVirt = -1;

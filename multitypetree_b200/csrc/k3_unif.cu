@@ -157,6 +157,29 @@ __global__ void k3_expm_batch(long long n, int d, const double *Q, const int *mo
         out[item * dd + e] = F[e];
 }
 
+// expm(Q L)[a,b] of every branch of a retype batch, one warp per branch: the three matrix
+// exponentials of a NodeRetype job do not depend on its random numbers, so they run side by side
+// here instead of one after the other inside the job's (sequential) sampling warp
+__global__ void k3_pba(long long n, int d, const double *Qall, const int *model,
+                       const double *tBottom, const double *tTop, const uint8_t *typeBottom,
+                       const uint8_t *typeTop, double *pba)
+{
+    extern __shared__ double sm[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const long long br = (long long)blockIdx.x * U_WARPS + warp;
+    if (br >= n)
+        return;
+    const int dd = d * d;
+    __shared__ uint16_t rcAll[U_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
+    uint16_t *rc = rcAll[threadIdx.x >> 5];
+    fill_rc(rc, d, threadIdx.x & 31);
+    double *buf = sm + (size_t)warp * 8 * dd;
+    const double L = sub_rn(tTop[br], tBottom[br]);
+    const double *E = expm_QL(d, Qall + (size_t)model[br] * dd, L, buf, rc, lane);
+    if (lane == 0)
+        pba[br] = E[typeBottom[br] * d + typeTop[br]];
+}
+
 // ---- getBranchTypeProb (UniformizationRetypeOperator.java:233-275), one warp per branch ----
 __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int *model,
                                const double *tBottom, const double *tTop,
@@ -220,6 +243,7 @@ struct RetypeParams {
     double *logProb;
     int *status, *nVirt;
     long long *uUsed;
+    const double *pba;       // expm(Q L)[a,b] per branch (k3_pba), or NULL
     double *scratchT;        // [warps][scratchCap] spill for nVirt > U_TCAP
     uint8_t *scratchTy;
     int scratchCap;
@@ -267,7 +291,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
             p.logN, p.meta[2 * mdl], p.meta[2 * mdl + 1],
             p.mu[mdl], t0, t1, a, b, p.nVirtForced ? p.nVirtForced[br] : -1, u, nU, pos, buf, rc,
             sTimes, sTypes, p.scratchT + w * p.scratchCap, p.scratchTy + w * p.scratchCap,
-            p.scratchCap, lane, p.tCap);
+            p.scratchCap, lane, p.tCap, p.pba ? p.pba + br : nullptr);
         int st = bs.st, nChg = 0;
         const int nVirt = bs.nVirt;
         const double Pba = bs.Pba;
@@ -555,13 +579,30 @@ int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t n, const int32_t *model,
     return x.download();
 }
 
-int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
+}  // extern "C"
+
+namespace {
+
+// the branches whose CURRENT typing is evaluated in the same call (mtt_unif_node_retype_batch)
+struct OldTyping {
+    int64_t n;
+    const int32_t *model;
+    const double *tBottom, *tTop;
+    const uint8_t *typeBottom, *typeTop;
+    const int64_t *chgOff;
+    const double *chgTime;
+    const uint8_t *chgType;
+    double *logProb;
+    int32_t *status;
+};
+
+int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
                           const int32_t *model, const double *tBottom, const double *tTop,
                           const uint8_t *typeBottom, const uint8_t *typeTop,
                           const int32_t *nVirtForced, const double *uniforms,
                           const int64_t *uOff, int outCap, int32_t *nChg, double *outChgTime,
                           uint8_t *outChgType, double *logProb, int32_t *status, int32_t *nVirt,
-                          int64_t *uUsed)
+                          int64_t *uUsed, const OldTyping *old)
 {
     if (!ctx)
         return MTT_ERR_INVALID_ARG;
@@ -617,6 +658,23 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
     x.out(status, (size_t)nBr, BUF_U_OUT4, &dSt);
     x.out(nVirt, (size_t)nBr, BUF_U_OUT7, &dNVirt);
     x.out((long long *)uUsed, (size_t)nJobs, BUF_U_OUT5, &dUsed);
+    int *dOModel = nullptr, *dOSt = nullptr;
+    double *dOT0 = nullptr, *dOT1 = nullptr, *dOCT2 = nullptr, *dOLP = nullptr;
+    uint8_t *dOA = nullptr, *dOB = nullptr, *dOCTy2 = nullptr;
+    long long *dOOff = nullptr;
+    if (old) {
+        const size_t n = (size_t)old->n, nc = (size_t)old->chgOff[old->n];
+        x.in(old->model, n, BUF_U_LIN0, &dOModel);
+        x.in(old->tBottom, n, BUF_U_LIN1, &dOT0);
+        x.in(old->tTop, n, BUF_U_LIN2, &dOT1);
+        x.in(old->typeBottom, n, BUF_U_LIN3, &dOA);
+        x.in(old->typeTop, n, BUF_U_LIN4, &dOB);
+        x.in((const long long *)old->chgOff, n + 1, BUF_U_LIN5, &dOOff);
+        x.in(old->chgTime, nc, BUF_U_LIN6, &dOCT2);
+        x.in(old->chgType, nc, BUF_U_LIN7, &dOCTy2);
+        x.out(old->logProb, n, BUF_U_LOUT0, &dOLP);
+        x.out(old->status, n, BUF_U_LOUT1, &dOSt);
+    }
     {
         int rc = x.prepare();
         if (rc == MTT_OK)
@@ -624,6 +682,40 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         if (rc != MTT_OK)
             return rc;
     }
+    bool oldInFlight = false;
+    if (old && old->n > 0) {
+        // the probability of the current typing needs no random numbers: it runs on the second
+        // stream, beside the matrix exponentials and the sampling of the new typing
+        if (!ctx->copyStream)
+            MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        while (ctx->events.size() < 2) {
+            cudaEvent_t ev;
+            MTT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->events.push_back(ev);
+        }
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[0], s));
+        MTT_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->events[0], 0));
+        MTT_CUDA(ctx, cudaFuncSetAttribute(k3_branch_logp,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)expm_smem(d)));
+        k3_branch_logp<<<(unsigned)((old->n + U_WARPS - 1) / U_WARPS), U_WARPS * 32,
+                         expm_smem(d), ctx->copyStream>>>(
+            old->n, d, (const double *)ctx->bufs[BUF_U_Q].p, dOModel, dOT0, dOT1, dOA, dOB, dOOff,
+            dOCT2, dOCTy2, dOLP, dOSt);
+        MTT_CHECK_LAUNCH(ctx);
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[1], ctx->copyStream));
+        oldInFlight = true;
+    }
+
+    // the branches' matrix exponentials, all at once
+    double *dPba = (double *)mtt_buf(ctx, BUF_U_PBA, (size_t)nBr * 8);
+    if (!dPba)
+        return MTT_ERR_CUDA;
+    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_pba, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)expm_smem(d)));
+    k3_pba<<<(unsigned)((nBr + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
+        nBr, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel, dT0, dT1, dA, dB, dPba);
+    MTT_CHECK_LAUNCH(ctx);
 
     const unsigned blocks = (unsigned)((nJobs + U_WARPS - 1) / U_WARPS);
     std::vector<int32_t> hSt(x.staged() ? 0 : nBr);
@@ -661,8 +753,13 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         p.nChg = dNChg; p.outChgTime = dOCT; p.outChgType = dOCTy; p.logProb = dLP;
         p.status = dSt; p.nVirt = dNVirt; p.uUsed = dUsed;
         p.scratchT = scrT; p.scratchTy = scrTy; p.scratchCap = scratchCap; p.tCap = tCap;
+        p.pba = dPba;
         k3_retype<<<blocks, U_WARPS * 32, smem, s>>>(p);
         MTT_CHECK_LAUNCH(ctx);
+        if (oldInFlight) {              // its results travel with the first download
+            MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[1], 0));
+            oldInFlight = false;
+        }
         // small calls: all outputs come back in one copy and the status is read from it; large
         // calls fetch the status alone first
         const int32_t *stHost = hSt.data();
@@ -688,6 +785,60 @@ int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
     if (x.staged())
         return MTT_OK;                 // everything arrived with the last download
     return x.download();
+}
+
+}  // namespace
+
+extern "C" {
+
+int mtt_unif_retype_batch(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
+                          const int32_t *model, const double *tBottom, const double *tTop,
+                          const uint8_t *typeBottom, const uint8_t *typeTop,
+                          const int32_t *nVirtForced, const double *uniforms,
+                          const int64_t *uOff, int outCap, int32_t *nChg, double *outChgTime,
+                          uint8_t *outChgType, double *logProb, int32_t *status, int32_t *nVirt,
+                          int64_t *uUsed)
+{
+    return retype_impl(ctx, nJobs, brOff, model, tBottom, tTop, typeBottom, typeTop, nVirtForced,
+                       uniforms, uOff, outCap, nChg, outChgTime, outChgType, logProb, status,
+                       nVirt, uUsed, nullptr);
+}
+
+int mtt_unif_node_retype_batch(mtt_ctx *ctx, int64_t nOld, const int32_t *modelOld,
+                               const double *tBottomOld, const double *tTopOld,
+                               const uint8_t *typeBottomOld, const uint8_t *typeTopOld,
+                               const int64_t *chgOff, const double *chgTime,
+                               const uint8_t *chgType, double *logProbOld, int32_t *statusOld,
+                               int64_t nJobs, const int64_t *brOff, const int32_t *model,
+                               const double *tBottom, const double *tTop,
+                               const uint8_t *typeBottom, const uint8_t *typeTop,
+                               const int32_t *nVirtForced, const double *uniforms,
+                               const int64_t *uOff, int outCap, int32_t *nChg,
+                               double *outChgTime, uint8_t *outChgType, double *logProb,
+                               int32_t *status, int32_t *nVirt, int64_t *uUsed)
+{
+    if (!ctx)
+        return MTT_ERR_INVALID_ARG;
+    if (nOld < 0 || (nOld > 0 && (!modelOld || !tBottomOld || !tTopOld || !typeBottomOld ||
+                                  !typeTopOld || !chgOff || !logProbOld || !statusOld)))
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_unif_node_retype_batch: NULL argument");
+    if (nJobs <= 0 || nOld == 0) {      // nothing to overlap: the two plain calls
+        int rc = MTT_OK;
+        if (nOld > 0)
+            rc = mtt_unif_branch_logp_batch(ctx, nOld, modelOld, tBottomOld, tTopOld,
+                                            typeBottomOld, typeTopOld, chgOff, chgTime, chgType,
+                                            logProbOld, statusOld);
+        if (rc == MTT_OK && nJobs > 0)
+            rc = mtt_unif_retype_batch(ctx, nJobs, brOff, model, tBottom, tTop, typeBottom,
+                                       typeTop, nVirtForced, uniforms, uOff, outCap, nChg,
+                                       outChgTime, outChgType, logProb, status, nVirt, uUsed);
+        return rc;
+    }
+    const OldTyping old{nOld, modelOld, tBottomOld, tTopOld, typeBottomOld, typeTopOld, chgOff,
+                        chgTime, chgType, logProbOld, statusOld};
+    return retype_impl(ctx, nJobs, brOff, model, tBottom, tTop, typeBottom, typeTop, nVirtForced,
+                       uniforms, uOff, outCap, nChg, outChgTime, outChgType, logProb, status,
+                       nVirt, uUsed, &old);
 }
 
 }  // extern "C"

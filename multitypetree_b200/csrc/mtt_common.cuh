@@ -48,7 +48,9 @@ enum BufId {
     BUF_D_QUEUE, BUF_D_CHGNODE, BUF_D_TIPH, BUF_D_TIPT, BUF_D_INTH, BUF_D_INTT,
     BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
-    BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6, BUF_U_OUT7,
+    BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6, BUF_U_OUT7, BUF_U_PBA,
+    BUF_U_LIN0, BUF_U_LIN1, BUF_U_LIN2, BUF_U_LIN3, BUF_U_LIN4, BUF_U_LIN5, BUF_U_LIN6, BUF_U_LIN7,
+    BUF_U_LOUT0, BUF_U_LOUT1,
     BUF_P_MODEL, BUF_P_N, BUF_P_NODEOFF, BUF_P_HEIGHT, BUF_P_PARENT, BUF_P_LEAFTYPE,
     BUF_P_ORDEROFF, BUF_P_ORDER, BUF_P_U, BUF_P_UOFF, BUF_P_LOGW, BUF_P_STATUS, BUF_P_USED,
     BUF_P_LOGP,

@@ -5,7 +5,7 @@
 //                    ("CHAIN c sumLogHR nInf nChanges sumChangeTimes sumTypes") that the pytest
 //                    wrapper compares with the Python mirror run from the same seeds, and the
 //                    chain-steps per second of the native driver.
-// Usage: test_plugins <chains> <tips> <demes> <steps> [--time]
+// Usage: test_plugins <chains> <tips> <demes> <steps> [--time [uniform window]]
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -66,6 +66,7 @@ int main(int argc, char **argv)
     const int C = argc > 1 ? std::atoi(argv[1]) : 8, n = argc > 2 ? std::atoi(argv[2]) : 30,
               d = argc > 3 ? std::atoi(argv[3]) : 4, steps = argc > 4 ? std::atoi(argv[4]) : 20;
     const bool timing = argc > 5 && std::strcmp(argv[5], "--time") == 0;
+    const int window = argc > 6 ? std::atoi(argv[6]) : 128;
     mtt::Context ctx(0);
 
     // ---------------------------------------------------------------- piece 2
@@ -129,7 +130,7 @@ int main(int argc, char **argv)
     }
     std::vector<mtt::MultiTypeTree> trees = simulate(C, n, d, m, N, 5000);
     std::vector<std::unique_ptr<mtt::Randomizer>> rngs;
-    mtt::NodeRetypeEnsemble ens(ctx, 1, d, m, false);
+    mtt::NodeRetypeEnsemble ens(ctx, 1, d, m, false, window);
     for (int c = 0; c < C; c++) {
         rngs.emplace_back(new mtt::Randomizer(1000 + c));
         ens.add(trees[c], *rngs[c], 0);
@@ -161,6 +162,13 @@ int main(int argc, char **argv)
             std::printf("CHAIN %d %.12f %d %d %.12f %ld\n", c, sumHR[c], nInf[c],
                         trees[c].getTotalNumberOfChanges(), st, sty);
         }
+    std::printf("CALLS branch_logp %.1f us/step, retype %.1f us/step (%.2f calls/step)\n",
+                1e6 * ens.secondsInCalls[0] / steps, 1e6 * ens.secondsInCalls[1] / steps,
+                (double)ens.deviceCalls / steps);
+    std::printf("STOPS no-path %lld rubbish %lld fell-through %lld poisson-tail %lld more-uniforms %lld\n",
+                ens.resubmits[MTT_ST_NO_VALID_PATH], ens.resubmits[MTT_ST_PBA_RUBBISH],
+                ens.resubmits[MTT_ST_FB_FELL_THROUGH], ens.resubmits[MTT_ST_NEEDS_POISSON_TAIL],
+                ens.resubmits[MTT_ST_NEED_MORE_UNIFORMS]);
     std::printf("RATE %d chains x %d steps in %.3f s = %.0f chain-steps/s (%.2f us per chain-step)\n",
                 C, steps, secs, C * steps / secs, 1e6 * secs / (C * (double)steps));
     return 0;

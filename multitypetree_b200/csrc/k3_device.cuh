@@ -309,6 +309,8 @@ __device__ __forceinline__ BranchSample sample_branch(
         st = MTT_ST_PBA_RUBBISH;
 
     // ---- drawEventCount (:74-105)
+    // The loop is a chain of dependent operations; the table entries of step n + 1 (log R^n[a,b],
+    // log n) do not depend on it and are fetched one step ahead.
     if (st == MTT_ST_OK) {
         if (forced >= 0) {
             nVirt = forced;
@@ -320,21 +322,31 @@ __device__ __forceinline__ BranchSample sample_branch(
             logPba = log_ni(Pba);
             double acc = sub_rn(-muL, logPba);                          // :81
             const double log_muL = log_ni(muL);                         // :82
+            const int ab = a * d + b;
             int n = 0;
+            double curLogRn = (size > 0) ? logTab[ab] : 0.0;         // log R^0[a,b]
+            double curLogN = logN[1];                                // log(n) of the next step
             while (true) {
                 if (n >= size && !steady) {
                     st = MTT_ST_NEED_MORE_POWERS;
                     break;
                 }
+                const int n1 = n + 1;
+                double nxtLogRn = 0.0, nxtLogN = 0.0;
+                if (n1 < size || steady)
+                    nxtLogRn = logTab[(size_t)min(n1, size - 1) * dd + ab];
+                if (n1 + 1 < U_LOGN)
+                    nxtLogN = logN[n1 + 1];
                 // log(R^n[a,b]) and log(n) come from tables filled with the same log()
-                const double logRn = logTab[(size_t)min(n, size - 1) * dd + a * d + b];
-                Plow = add_rn(Plow, exp_ni(add_rn(logRn, acc)));           // :86
+                Plow = add_rn(Plow, exp_ni(add_rn(curLogRn, acc)));        // :86
                 if (Plow > uu) {                                     // :88-89
                     nVirt = n;
                     break;
                 }
                 n += 1;
-                acc = add_rn(acc, sub_rn(log_muL, n < U_LOGN ? logN[n] : log_ni((double)n)));  // :92
+                acc = add_rn(acc, sub_rn(log_muL, n < U_LOGN ? curLogN : log_ni((double)n)));  // :92
+                curLogRn = nxtLogRn;
+                curLogN = nxtLogN;
                 if (!(steadyN < 0 || n < steadyN)) {                 // :94
                     st = MTT_ST_NEEDS_POISSON_TAIL;                  // :96-102 -> host
                     nVirt = n;                                       // thresh
@@ -388,14 +400,25 @@ __device__ __forceinline__ BranchSample sample_branch(
         warp_sort_doubles(times, npad, lane);
 
         // ---- forward-backward sampling of the types (:163-194)
+        // Step i needs column b of R^(nVirt-i+1) and of R^(nVirt-i): lane c holds R^k[c,b].  The
+        // first is the previous step's second, and the next step's column does not depend on
+        // the type drawn here, so it is fetched one step ahead; R itself sits in the warp's
+        // shared scratch (free once Pba is known).
+        for (int e = lane; e < dd; e += 32)
+            buf[e] = R[e];
+        __syncwarp();
+        auto column = [&](int k) {
+            return lane < d ? tab[(size_t)min(k, size - 1) * dd + lane * d + b] : 0.0;
+        };
+        double hiCol = nVirt >= 1 ? column(nVirt) : 0.0;
+        double loCol = nVirt >= 1 ? column(nVirt - 1) : 0.0;
         int prev = a;
         for (int i = 1; i <= nVirt; i++) {
-            const double *Rhi = tab + (size_t)min(nVirt - i + 1, size - 1) * dd;
-            const double *Rlo = tab + (size_t)min(nVirt - i, size - 1) * dd;
-            double u2 = mul_rn(u[pos++], Rhi[prev * d + b]);         // :165-166
+            const double nxtCol = (i < nVirt) ? column(nVirt - i - 1) : 0.0;
+            double u2 = mul_rn(u[pos++], __shfl_sync(FULL_MASK, hiCol, prev));   // :165-166
             double prod = 0.0;
             if (lane < d)
-                prod = mul_rn(R[prev * d + lane], Rlo[lane * d + b]);
+                prod = mul_rn(buf[prev * d + lane], loCol);
             int c = 0;
             bool fell = true;
             for (c = 0; c < d; c++) {
@@ -412,6 +435,8 @@ __device__ __forceinline__ BranchSample sample_branch(
             if (lane == 0)
                 types[i - 1] = (uint8_t)c;
             prev = c;
+            hiCol = loCol;
+            loCol = nxtCol;
         }
         __syncwarp();
     }

@@ -711,7 +711,16 @@ public:
         for (size_t c = 0; c < C; c++) {
             Job j;
             j.chain = c;
-            j.window = window_;
+            // uniforms the job is expected to consume: per branch one for the event count and
+            // two per virtual event (Poisson(mu L), plus six standard deviations) -- so that a
+            // long branch does not cost the whole ensemble a second round
+            const MultiTypeTree &t = *chains_[c].tree;
+            double need = 0.0;
+            for (int nd : br[c]) {
+                const double muL = mu_[chains_[c].model] * (t.height[t.parent[nd]] - t.height[nd]);
+                need += 2.0 * (muL + 6.0 * std::sqrt(muL) + 8.0) + 1.0;
+            }
+            j.window = std::max(window_, ((int)need + 31) / 32 * 32);
             j.forced.assign(br[c].size(), -1);
             pending.push_back(j);
         }

@@ -67,7 +67,9 @@ public class NodeRetype extends UniformizationRetypeOperator {
                                   : new Node[]{node, node.getLeft(), node.getRight()};
         int nb = br.length;
 
-        // old path probabilities (getBranchTypeProb, :233-275)
+        // old path probabilities (getBranchTypeProb, :233-275).  (mtt_unif_node_retype_batch does
+        // this and the retyping below in ONE device call -- it needs a second set of branch
+        // buffers for the old node types; see mtt::NodeRetypeEnsemble in include/mtt_b200.hpp.)
         long c = 0;
         for (int i = 0; i < nb; i++) {
             MultiTypeNode s = (MultiTypeNode) br[i];

@@ -228,7 +228,15 @@ def test_chains_malformed_proposal_leaves_the_chain_alone(ctx):
     tips = simulate_alignment(par[0], hgt[0], 300, 2.0, f, 0.1, seed=2)
     tl = TreeLikelihood(data=Alignment(states=tips), siteModel=SiteModel(HKY(2.0, f), 0.1), ctx=ctx)
     ch = tl.chains(K)
+    # a malformed tree as the very first proposal of a chain: NaN, and the chain starts over
+    first = par.copy()
+    first[2, 0] = 0                                 # a node as its own parent
+    got = ch.update(first, hgt)
+    assert np.isnan(got[2]) and np.all(np.isfinite(np.delete(got, 2)))
+    ch.accept()
     base = ch.update(par, hgt)
+    assert ch.last_entries == n - 1                 # chain 2 had nothing accepted yet
+    np.testing.assert_allclose(base, tl.calculateLogPBatch(par, hgt), rtol=RTOL_FULL)
     ch.accept()
     bad = par.copy()
     root = [int(np.nonzero(par[k] < 0)[0][0]) for k in range(K)]

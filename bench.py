@@ -17,8 +17,9 @@ is timed as well, with an L2 flush before every launch, and reported under "cfg2
 
   --impl reference   times the reference's CPU algorithm (oracle port; no JVM exists here) on
                      the same config with all host threads.
-  --workload peel|peel_sharded|retype|untyped   the other pieces (configs 3, 4 and 5, and the
-                     untyped-tree particle density) as separate bench lines.
+  --workload peel|peel_chains|peel_sharded|retype|untyped   the other pieces (configs 3, 4 and
+                     5, incremental peeling on resident chains, and the untyped-tree particle
+                     density) as separate bench lines.
 
 Multi-GPU: one process per GPU (torchrun); trees are sharded across ranks, no collective on
 the data path (weak scaling).
@@ -467,13 +468,22 @@ def bench_peel(args):
         print("rank %d: %.3f ms/step" % (rank, own_ms), file=sys.stderr, flush=True)
     ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
     launches = ctx.launch_count() - l0
-    # e2e: host buffers through the C-ABI
+    # e2e: host buffers through the C-ABI (page-locked, as the contract asks: par / hgt are views
+    # of tb.parent / tb.height)
+    pinned = [a for a in (tb.parent, tb.height, tb.nodeType, tb.chgNode, tb.chgBase, tb.chgTime,
+                          tb.chgType, tb.nodeOff)
+              if L.mtt_host_register(a.ctypes.data, a.nbytes) == 0]
+    lp = tl.calculateLogPBatch(par, hgt)
+    ld = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
+    barrier(world)
     t0 = time.perf_counter()
     for _ in range(3):
         lp = tl.calculateLogPBatch(par, hgt)
         ld = mtt.sc_logp_batch(tb, m, N, ctx=ctx)
     barrier(world)
     e2e = B * world * 3 / max_over_ranks(time.perf_counter() - t0, world)
+    for a in pinned:
+        L.mtt_host_unregister(a.ctypes.data)
     if rank != 0:
         return
     from oracle import oracle as orc
@@ -504,7 +514,7 @@ def bench_peel(args):
                          "kind": "port", "sample": "%d trees, peeling only" % k},
         "e2e": {"value": e2e, "unit": "evals/s",
                 "h2d_bytes_per_step": int(par.nbytes + hgt.nbytes + tb.nbytes()),
-                "d2h_bytes_per_step": int(16 * B)},
+                "d2h_bytes_per_step": int(16 * B), "pinned": len(pinned) == 8},
         "gpu_launches": int(launches), "clocks": clk.summary(),
         "parity_max_rel_err_vs_oracle": rel}))
 

@@ -194,6 +194,17 @@ def cpu_density(tb, m, N, sample, threads):
     return sample * reps / dt, dt
 
 
+def fp64_peak():
+    """Sustained DFMA throughput of one B200 in TFLOP/s: measured by tools/ubench/dfma_peak.cu
+    (profiles/r2_dfma_peak.json), else nominal 148 SM x 64 DFMA/clk x 2 x 1.965 GHz."""
+    path = os.path.join(ROOT, "profiles", "r2_dfma_peak.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["dfma_tflops"]), "measured (profiles/r2_dfma_peak.json)"
+    except Exception:
+        return 148 * 64 * 2 * 1.965e9 / 1e12, "nominal"
+
+
 def bench_density(args):
     import torch
     import multitypetree_b200 as mtt
@@ -509,7 +520,9 @@ def bench_peel(args):
                      "peak_source": src, "kernel": "k2_peel",
                      "note": "algorithmic bytes of the materialised-partials model (SURVEY 8d); "
                              "the kernel keeps partials on chip, so frac may exceed 1",
-                     "fp64_tflops": flop * B / (ms * 1e-3) / 1e12},
+                     "fp64_tflops": flop * B / (ms * 1e-3) / 1e12,
+                     "fp64_peak_tflops": fp64_peak()[0], "fp64_peak_source": fp64_peak()[1],
+                     "fp64_frac": flop * B / (ms * 1e-3) / 1e12 / fp64_peak()[0]},
         "cpu_baseline": {"value": k / cpu_dt, "unit": "evals/s", "cores": min(cores, k),
                          "kind": "port", "sample": "%d trees, peeling only" % k},
         "e2e": {"value": e2e, "unit": "evals/s",

@@ -42,12 +42,35 @@ def _worker(rank, world, port, what, q):
                 sh.patterns, sh.patternWeight, par, hgt, [0.1], [1.0], f, 2.0))
             want = orc.tree_likelihood_batch(al.patterns, al.patternWeight, par, hgt, [0.1], [1.0],
                                              f, 2.0)
+        if what == "parts":
+            # pattern shards under a proportion of invariant sites: every rank hands (unscaled
+            # sum, rescaled sum, "the unscaled evaluation underflowed") to the all-reduce and
+            # BEAST's choice between the two is made over ALL patterns.  The
+            # per-rank evaluation is the oracle's two passes; -inf marks the underflow.
+            def shard_parts():
+                kw = dict(pInv=0.2)
+                u = orc.tree_likelihood_batch(sh.patterns, sh.patternWeight, par, hgt, [0.1 / 0.8],
+                                              [0.8], f, 2.0, useScaling=0, **kw)
+                r = orc.tree_likelihood_batch(sh.patterns, sh.patternWeight, par, hgt, [0.1 / 0.8],
+                                              [0.8], f, 2.0, useScaling=1, **kw)
+                flag = np.isinf(u).astype(np.float64)
+                return np.stack([np.where(np.isinf(u), 0.0, u), r, flag])
+
+            class FakeChains:                       # the shape of PeelChains.update(parts=True)
+                def update(self, parent, height, parts=False, **_):
+                    assert parts
+                    return shard_parts()
+            got = parallel.pattern_sharded_logl_parts(shard_parts)
+            got2 = parallel.pattern_sharded_chains_update(FakeChains(), par, hgt)
+            assert np.array_equal(got, got2)
+            want = orc.tree_likelihood_batch(al.patterns, al.patternWeight, par, hgt, [0.1 / 0.8],
+                                             [0.8], f, 2.0, pInv=0.2, useScaling=2)
         q.put((rank, float(np.max(np.abs(got - want) / np.abs(want)))))
     finally:
         dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("what", ["trees", "patterns"])
+@pytest.mark.parametrize("what", ["trees", "patterns", "parts"])
 def test_world_size_2(what):
     ctx = mp.get_context("spawn")
     q = ctx.Queue()

@@ -77,6 +77,8 @@ def _propose(rng, par, hgt, n):
 @pytest.mark.parametrize("n,sites,gamma,pInv,useDirty", [(40, 500, 0, 0.0, False),
                                                          (40, 500, 4, 0.1, True),
                                                          (17, 300, 3, 0.0, True),
+                                                         (24, 200, 8, 0.0, True),
+                                                         (24, 200, 6, 0.1, False),
                                                          (2, 60, 0, 0.0, True),
                                                          (3, 60, 2, 0.1, False),
                                                          (150, 260, 0, 0.2, False)])

@@ -356,6 +356,11 @@ int mtt_peel_chains_update_parts(mtt_peel_chains *s, const int32_t *parent, cons
 int mtt_peel_chains_accept(mtt_peel_chains *s, const uint8_t *accept);
 /* nodes recomputed by the last update, over all chains */
 int64_t mtt_peel_chains_last_entries(const mtt_peel_chains *s);
+/* integration aid: with on != 0, an update that is given a dirty mask still compares every node
+ * and fails with MTT_ERR_INVALID_ARG (naming the chain and the node) when one differs from the
+ * accepted tree without being flagged -- the mistake that otherwise goes unnoticed, here as in
+ * BEAST.  Costs the O(nodes) comparison the mask exists to avoid: for tests of a binding. */
+int mtt_peel_chains_set_verify(mtt_peel_chains *s, int on);
 /* measurement: bracket the kernel launches of every update with CUDA events on the ctx stream;
  * last_device_ms = the last update's device time (0 when nothing was launched) */
 int mtt_peel_chains_set_timing(mtt_peel_chains *s, int on);

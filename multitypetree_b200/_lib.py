@@ -79,6 +79,7 @@ ABI = {
     "mtt_peel_chains_accept": (C.c_int, [VP, VP]),
     "mtt_peel_chains_last_entries": (C.c_int64, [VP]),
     "mtt_peel_chains_set_timing": (C.c_int, [VP, C.c_int]),
+    "mtt_peel_chains_set_verify": (C.c_int, [VP, C.c_int]),
     "mtt_peel_chains_last_device_ms": (C.c_double, [VP]),
     "mtt_sim_trees_create": (C.c_int, [VP, C.c_int64, C.c_int, C.c_int, VP, VP, VP, VP,
                                        C.c_uint64, C.POINTER(VP)]),

@@ -143,6 +143,10 @@ struct mtt_peel_chains {
     std::vector<UpdOp> ops;
     std::vector<int> opOff, stack, order;
     long long lastOps = 0;
+    int unflagged = -1;                 // node found by the verification below
+    // integration aid (mtt_peel_chains_set_verify): with a dirty mask, compare ALL nodes anyway
+    // and fail the call when a node differs without being flagged
+    bool verify = false;
     // optional device timing of the launches of an update (mtt_peel_chains_set_timing)
     bool timing = false;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -468,6 +472,13 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
         for (int i = 0; i < N; i++)
             changed.push_back(i);
     } else if (dirty) {
+        if (s->verify)
+            for (int i = 0; i < N; i++)
+                if (!dirty[i] && differs(i)) {
+                    s->unflagged = i;       // reported by the caller of plan_chain
+                    c.undo();
+                    return false;
+                }
         // a handful of flags in N bytes: skip eight clean nodes at a time
         int i = 0;
         for (; i + 8 <= N; i += 8) {
@@ -796,10 +807,19 @@ static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double
         const double *rate = branchRates ? branchRates + (size_t)k * N : nullptr;
         kap[k] = kk;
         const size_t before = s->ops.size();
+        s->unflagged = -1;
         if (!plan_chain(s, k, parent + (size_t)k * N, height + (size_t)k * N, rate, clock, kk,
                         dirty ? dirty + (size_t)k * N : nullptr)) {
             s->ops.resize(before);
             bad[k] = 1;
+            if (s->unflagged >= 0) {
+                for (Chain &c : s->chains)
+                    if (c.pending)
+                        c.undo();
+                return mtt_fail(ctx, MTT_ERR_INVALID_ARG,
+                                "mtt_peel_chains_update: chain %d, node %d differs from the "
+                                "accepted tree but is not flagged dirty", k, s->unflagged);
+            }
         }
         s->opOff[k + 1] = (int)s->ops.size();
     }
@@ -880,6 +900,14 @@ int mtt_peel_chains_set_timing(mtt_peel_chains *s, int on)
         MTT_CUDA(ctx, cudaEventCreate(&s->ev1));
     }
     s->timing = on != 0;
+    return MTT_OK;
+}
+
+int mtt_peel_chains_set_verify(mtt_peel_chains *s, int on)
+{
+    if (!s || !s->h)
+        return MTT_ERR_STATE;
+    s->verify = on != 0;
     return MTT_OK;
 }
 

@@ -321,6 +321,10 @@ class PeelChains:
         """Internal nodes recomputed by the last update, over all chains."""
         return int(_lib.lib().mtt_peel_chains_last_entries(self._s))
 
+    def set_verify(self, on: bool = True) -> None:
+        """Debugging aid for bindings: fail an update whose dirty mask misses a changed node."""
+        self.ctx.check(_lib.lib().mtt_peel_chains_set_verify(self._s, int(on)))
+
     def set_timing(self, on: bool = True) -> None:
         self.ctx.check(_lib.lib().mtt_peel_chains_set_timing(self._s, int(on)))
 

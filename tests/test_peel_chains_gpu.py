@@ -332,3 +332,30 @@ def test_chains_on_pattern_shards_sum_to_the_whole(ctx, n, rate, pInv):
         x.close()
     for tl in shards + [whole]:
         tl.close()
+
+
+def test_chains_verify_mode_catches_an_unflagged_change(ctx):
+    n, K = 10, 2
+    par, hgt = _trees(K, n, seed=12)
+    f = np.array([.25, .25, .25, .25])
+    tips = simulate_alignment(par[0], hgt[0], 100, 2.0, f, 0.1, seed=2)
+    tl = TreeLikelihood(data=Alignment(states=tips), siteModel=SiteModel(HKY(2.0, f), 0.1), ctx=ctx)
+    ch = tl.chains(K)
+    base = ch.update(par, hgt)
+    ch.accept()
+    h2 = hgt.copy()
+    v = int(par[1, 0])
+    up = h2[1, par[1, v]] if par[1, v] >= 0 else h2[1, v] + 1.0
+    h2[1, v] = 0.5 * (h2[1, v] + up)
+    wrong = np.zeros(par.shape, np.uint8)           # the move is not flagged
+    stale = ch.update(par, h2, dirty=wrong)
+    assert np.array_equal(stale, base)              # unnoticed, as documented ...
+    ch.set_verify(True)
+    with pytest.raises(mtt.MttError, match="not flagged dirty"):
+        ch.update(par, h2, dirty=wrong)             # ... unless the binding is under test
+    right = wrong.copy()
+    right[1, v] = 1
+    got = ch.update(par, h2, dirty=right)
+    np.testing.assert_allclose(got, tl.calculateLogPBatch(par, h2), rtol=RTOL_FULL)
+    ch.close()
+    tl.close()

@@ -634,14 +634,15 @@ def bench_peel_chains(args):
     alg = dev_entries * stride * 2.0 * (32 * C + 8)     # one vector read + one written per entry
     hbm, src = peaks()
     print(json.dumps({
-        "metric": "cfg3 MCMC regime: proposals evaluated/s (incremental peeling, resident chains)",
+        "metric": "MCMC regime: proposals evaluated/s (incremental peeling, resident chains)",
         "value": K * world * steps / t_upd, "unit": "chain-steps/s", "n_gpus": world,
         "steps": steps, "warmup": args.warmup, "ms_per_step": t_upd / steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "cfg3 shape: %d chains x %d-tip trees x %d patterns, one node-height "
+        "config": {"workload": "%s: %d chains x %d-tip trees x %d patterns, one node-height "
                                "proposal per chain and step, accept with probability 1/2"
-                               % (K, n, P), "chains_per_gpu": K,
+                               % ("cfg3 shape" if n == 1000 else "resident chains", K, n, P),
+                   "chains_per_gpu": K,
                    "nodes_recomputed_per_proposal": entries / (K * steps),
                    "resident_bytes": int(K) * 2 * (n - 1) * (4 * C + 1) * stride * 8},
         "roofline": {"bound": "hbm", "achieved": alg / (dev_ms * 1e-3) / 1e9 if dev_ms else None,

@@ -346,6 +346,16 @@ int mtt_peel_chains_destroy(mtt_peel_chains *s);
 int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
                            const double *branchRates, const double *kappa,
                            const double *clockRate, const uint8_t *dirty, double *logL);
+/* update in sparse form: chain k's proposal is the list of nodes node[off[k] .. off[k+1]) that
+ * may differ from its accepted tree, with their new parent / height (/ branchRates, may be NULL
+ * under a strict clock) given PER LIST ENTRY -- what a BEAST shim has in hand (the dirty nodes)
+ * without flattening the whole tree.  Nodes not listed keep their accepted values; a node may be
+ * listed twice.  MTT_ERR_STATE when a chain has no accepted tree yet or its kappa / strict clock
+ * rate differs from the accepted one (the whole tree is dirty then: use mtt_peel_chains_update). */
+int mtt_peel_chains_update_sparse(mtt_peel_chains *s, const int64_t *off, const int32_t *node,
+                                  const int32_t *parent, const double *height,
+                                  const double *branchRates, const double *kappa,
+                                  const double *clockRate, double *logL);
 /* update on a pattern shard (the handle holds a contiguous slice of the patterns, the chains'
  * trees are replicated on every rank): parts[3][nChains] as mtt_peel_logl_parts_batch -- summed
  * over the shards, parts[2] > 0 ? parts[1] : parts[0] is the proposal's log-likelihood; every

@@ -54,6 +54,8 @@ public final class MttNative implements AutoCloseable {
     private static final MethodHandle CHAINS_DESTROY = h("mtt_peel_chains_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
     private static final MethodHandle CHAINS_UPDATE = h("mtt_peel_chains_update", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle CHAINS_UPDATE_SPARSE = h("mtt_peel_chains_update_sparse", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle CHAINS_ACCEPT = h("mtt_peel_chains_accept", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, ADDRESS));
 
@@ -212,6 +214,12 @@ public final class MttNative implements AutoCloseable {
         public void update(MemorySegment parent, MemorySegment height, MemorySegment branchRates,
                            MemorySegment kappa, MemorySegment clockRate, MemorySegment dirty, MemorySegment logL) {
             call(CHAINS_UPDATE, s, parent, height, branchRates, kappa, clockRate, dirty, logL);
+        }
+        /** the proposal as lists of changed nodes: off[nChains+1], then node / parent / height per entry */
+        public void updateSparse(MemorySegment off, MemorySegment node, MemorySegment parent, MemorySegment height,
+                                 MemorySegment branchRates, MemorySegment kappa, MemorySegment clockRate,
+                                 MemorySegment logL) {
+            call(CHAINS_UPDATE_SPARSE, s, off, node, parent, height, branchRates, kappa, clockRate, logL);
         }
         public void accept(MemorySegment mask) { call(CHAINS_ACCEPT, s, mask); }
         @Override public void close() { call(CHAINS_DESTROY, s); }

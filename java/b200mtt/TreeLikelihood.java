@@ -31,7 +31,8 @@ public class TreeLikelihood extends GenericTreeLikelihood {
     private MttNative.Peel peel;
     private MttNative.Chains chain;
     private Arena arena;
-    private MemorySegment parent, height, dirty, one, zero, rates, props, freqs, out;
+    private MemorySegment parent, height, dirtyNode, dirtyParent, dirtyHeight, off, one, zero, rates, props, freqs, out;
+    private boolean needFull = true;
     private double[] lastRates, lastProps, lastFreqs;
     private double lastPInv = Double.NaN, lastClock = Double.NaN, lastKappa = Double.NaN;
     private int nTips, nCat;
@@ -68,7 +69,9 @@ public class TreeLikelihood extends GenericTreeLikelihood {
         parent = arena.allocate(4L * N, 16); height = arena.allocate(8L * N, 16);
         rates = arena.allocate(8L * nCat, 8); props = arena.allocate(8L * nCat, 8);
         freqs = arena.allocate(32, 8); out = arena.allocate(8, 8);
-        dirty = arena.allocate(N, 8); one = arena.allocate(1, 1); zero = arena.allocate(1, 1);
+        dirtyNode = arena.allocate(4L * N, 16); dirtyParent = arena.allocate(4L * N, 16);
+        dirtyHeight = arena.allocate(8L * N, 16); off = arena.allocate(16, 8);
+        one = arena.allocate(1, 1); zero = arena.allocate(1, 1);
         one.set(JAVA_BYTE, 0, (byte) 1);
         chain = peel.newChains(1);
     }
@@ -89,17 +92,35 @@ public class TreeLikelihood extends GenericTreeLikelihood {
                 || !java.util.Arrays.equals(f, lastFreqs) || pInv != lastPInv || clockRate != lastClock) {
             peel.setSiteModel(rates, props, freqs, pInv, clockRate);
             lastRates = r.clone(); lastProps = pr.clone(); lastFreqs = f.clone(); lastPInv = pInv; lastClock = clockRate;
+            needFull = true;
         }
-        if (kappa != lastKappa) { peel.setHky(kappa); lastKappa = kappa; }
-        for (Node node : tree.getNodesAsArray()) {
-            int nr = node.getNr();
-            parent.setAtIndex(JAVA_INT, nr, node.isRoot() ? -1 : node.getParent().getNr());
-            height.setAtIndex(JAVA_DOUBLE, nr, node.getHeight());
-            dirty.set(JAVA_BYTE, nr, (byte) (node.isDirty() != beast.base.evolution.tree.Tree.IS_CLEAN ? 1 : 0));
+        if (kappa != lastKappa) { peel.setHky(kappa); lastKappa = kappa; needFull = true; }
+        if (needFull) {
+            // first evaluation, or a model parameter moved: the whole tree, every node recomputed
+            for (Node node : tree.getNodesAsArray()) {
+                int nr = node.getNr();
+                parent.setAtIndex(JAVA_INT, nr, node.isRoot() ? -1 : node.getParent().getNr());
+                height.setAtIndex(JAVA_DOUBLE, nr, node.getHeight());
+            }
+            chain.update(parent, height, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL,
+                    MemorySegment.NULL, out);
+            needFull = false;
+        } else {
+            // a tree move: only the dirty nodes cross the boundary; they are compared with the
+            // accepted tree and the nodes above a real change are recomputed
+            long c = 0;
+            for (Node node : tree.getNodesAsArray()) {
+                if (node.isDirty() == beast.base.evolution.tree.Tree.IS_CLEAN)
+                    continue;
+                dirtyNode.setAtIndex(JAVA_INT, c, node.getNr());
+                dirtyParent.setAtIndex(JAVA_INT, c, node.isRoot() ? -1 : node.getParent().getNr());
+                dirtyHeight.setAtIndex(JAVA_DOUBLE, c, node.getHeight());
+                c++;
+            }
+            off.setAtIndex(JAVA_LONG, 0, 0); off.setAtIndex(JAVA_LONG, 1, c);
+            chain.updateSparse(off, dirtyNode, dirtyParent, dirtyHeight, MemorySegment.NULL, MemorySegment.NULL,
+                    MemorySegment.NULL, out);
         }
-        // the flagged nodes are compared with the accepted tree; only the nodes above a real
-        // change are recomputed (all of them after a setter above)
-        chain.update(parent, height, MemorySegment.NULL, MemorySegment.NULL, MemorySegment.NULL, dirty, out);
         logP = out.get(JAVA_DOUBLE, 0);
         return logP;
     }
@@ -108,9 +129,10 @@ public class TreeLikelihood extends GenericTreeLikelihood {
     @Override
     public void store() { super.store(); }
 
-    /** proposal rejected: drop it (BeerLikelihoodCore.restore) */
+    /** proposal rejected: drop it (BeerLikelihoodCore.restore); a rejected model-parameter move
+     *  leaves the library's setters at the rejected value, so the next evaluation is a full one */
     @Override
-    public void restore() { chain.accept(zero); super.restore(); }
+    public void restore() { chain.accept(zero); lastKappa = Double.NaN; lastPInv = Double.NaN; super.restore(); }
 
     /** proposal accepted: its partials become the accepted ones */
     @Override

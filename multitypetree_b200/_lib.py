@@ -75,6 +75,7 @@ ABI = {
     "mtt_peel_chains_create": (C.c_int, [VP, C.c_int, C.POINTER(VP)]),
     "mtt_peel_chains_destroy": (C.c_int, [VP]),
     "mtt_peel_chains_update": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP]),
+    "mtt_peel_chains_update_sparse": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_peel_chains_update_parts": (C.c_int, [VP, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_peel_chains_accept": (C.c_int, [VP, VP]),
     "mtt_peel_chains_last_entries": (C.c_int64, [VP]),

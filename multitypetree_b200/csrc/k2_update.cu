@@ -65,10 +65,11 @@ struct Chain {
         int left = -1, right = -1;
         int mark = 0, walk = 0;         // epoch / walk that reached the node (plan_chain)
         int bank = 0;                   // bank of the accepted partials (internal nodes)
+        int seen = 0;                   // epoch of the sparse list that named the node
         double height = 0.0, rate = 0.0;
     };
     std::vector<Node> nd;
-    int root = -1, rootCount = 0, epoch = 0, walkId = 0;
+    int root = -1, rootCount = 0, epoch = 0, walkId = 0, seenEpoch = 0;
     double kappa = 0.0, clock = 0.0;
     double logL[4] = {0.0, 0.0, 0.0, 0.0};      // picked evaluation, unscaled sum, rescaled sum, flag
     bool valid = false, pending = false;
@@ -144,6 +145,9 @@ struct mtt_peel_chains {
     std::vector<int> opOff, stack, order;
     long long lastOps = 0;
     int unflagged = -1;                 // node found by the verification below
+    bool needFull = false;              // a sparse update met a chain without an accepted state
+    std::vector<int32_t> spParent;      // sparse updates: the listed nodes' values by node number
+    std::vector<double> spHeight, spRate;
     // integration aid (mtt_peel_chains_set_verify): with a dirty mask, compare ALL nodes anyway
     // and fail the call when a node differs without being flagged
     bool verify = false;
@@ -452,13 +456,20 @@ int launch_update(mtt_peel_chains *s, const UpdOp *dOps, const int *dOpOff, cons
 // changed (the child's height, clock rate or parent, or the node's own height) or a child is
 // listed itself -- the union of the paths from the changes to the root.  `dirty` (optional, N
 // flags) names the nodes that MAY differ from the accepted tree; without it every node is
-// compared.  Returns false for a malformed tree (the state is rolled back).
+// compared; `list` (optional, instead of dirty) is the same thing as a list of node numbers --
+// parent / height / rate are then only read at the listed nodes.  Returns false for a malformed
+// tree (the state is rolled back).
 bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *height,
-                const double *rate, double clock, double kappa, const uint8_t *dirty)
+                const double *rate, double clock, double kappa, const uint8_t *dirty,
+                const int32_t *list = nullptr, int nList = 0)
 {
     const int n = s->h->nTips, N = 2 * n - 1;
     Chain &c = s->chains[k];
     const bool all = !c.valid || kappa != c.kappa || (!rate && clock != c.clock);
+    if (all && list) {
+        s->needFull = true;             // a list cannot describe a whole tree
+        return false;
+    }
     c.begin();
     c.kappa = kappa;
     c.clock = clock;
@@ -471,6 +482,21 @@ bool plan_chain(mtt_peel_chains *s, int k, const int32_t *parent, const double *
     if (all) {
         for (int i = 0; i < N; i++)
             changed.push_back(i);
+    } else if (list) {
+        if (c.seenEpoch == 0x7fffffff) {
+            for (Chain::Node &x : c.nd)
+                x.seen = 0;
+            c.seenEpoch = 0;
+        }
+        const int tag = ++c.seenEpoch;
+        for (int j = 0; j < nList; j++) {
+            const int i = list[j];
+            if (c.nd[i].seen == tag)
+                continue;               // named twice
+            c.nd[i].seen = tag;
+            if (differs(i))
+                changed.push_back(i);
+        }
     } else if (dirty) {
         if (s->verify)
             for (int i = 0; i < N; i++)
@@ -774,9 +800,12 @@ static int chains_launch(mtt_peel_chains *s, const std::vector<double> &kap,
     return MTT_OK;
 }
 
+// spOff / spNode (sparse form): chain k's proposal is the list of nodes
+// spNode[spOff[k] .. spOff[k+1]) with parent / height / branchRates given per LIST ENTRY
 static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double *height,
                          const double *branchRates, const double *kappa, const double *clockRate,
-                         const uint8_t *dirty, double *logL, double *parts)
+                         const uint8_t *dirty, double *logL, double *parts,
+                         const int64_t *spOff = nullptr, const int32_t *spNode = nullptr)
 {
     if (!s || !s->h)
         return MTT_ERR_STATE;               // (the handle was destroyed)
@@ -804,14 +833,49 @@ static int chains_update(mtt_peel_chains *s, const int32_t *parent, const double
     for (int k = 0; k < K; k++) {
         const double kk = kappa ? kappa[k] : h->kappa;
         const double clock = clockRate ? clockRate[k] : h->branchRate;
-        const double *rate = branchRates ? branchRates + (size_t)k * N : nullptr;
+        const double *rate = (branchRates && !spOff) ? branchRates + (size_t)k * N : nullptr;
         kap[k] = kk;
         const size_t before = s->ops.size();
         s->unflagged = -1;
-        if (!plan_chain(s, k, parent + (size_t)k * N, height + (size_t)k * N, rate, clock, kk,
-                        dirty ? dirty + (size_t)k * N : nullptr)) {
+        s->needFull = false;
+        bool planned;
+        if (spOff) {
+            // the listed nodes' values, by node number (only those entries are read)
+            s->spParent.resize(N);
+            s->spHeight.resize(N);
+            s->spRate.resize(N);
+            const int64_t lo = spOff[k], hi = spOff[k + 1];
+            bool inRange = hi >= lo;
+            for (int64_t j = lo; j < hi && inRange; j++) {
+                const int i = spNode[j];
+                if (i < 0 || i >= N) {
+                    inRange = false;
+                    break;
+                }
+                s->spParent[i] = parent[j];
+                s->spHeight[i] = height[j];
+                if (branchRates)
+                    s->spRate[i] = branchRates[j];
+            }
+            planned = inRange &&
+                      plan_chain(s, k, s->spParent.data(), s->spHeight.data(),
+                                 branchRates ? s->spRate.data() : nullptr, clock, kk, nullptr,
+                                 spNode + lo, (int)(hi - lo));
+        } else {
+            planned = plan_chain(s, k, parent + (size_t)k * N, height + (size_t)k * N, rate, clock,
+                                 kk, dirty ? dirty + (size_t)k * N : nullptr);
+        }
+        if (!planned) {
             s->ops.resize(before);
             bad[k] = 1;
+            if (s->needFull) {
+                for (Chain &c : s->chains)
+                    if (c.pending)
+                        c.undo();
+                return mtt_fail(ctx, MTT_ERR_STATE,
+                                "mtt_peel_chains_update_sparse: chain %d has no accepted tree "
+                                "(or its kappa / clock rate changed): a full update is needed", k);
+            }
             if (s->unflagged >= 0) {
                 for (Chain &c : s->chains)
                     if (c.pending)
@@ -859,6 +923,20 @@ int mtt_peel_chains_update(mtt_peel_chains *s, const int32_t *parent, const doub
                            const double *clockRate, const uint8_t *dirty, double *logL)
 {
     return chains_update(s, parent, height, branchRates, kappa, clockRate, dirty, logL, nullptr);
+}
+
+int mtt_peel_chains_update_sparse(mtt_peel_chains *s, const int64_t *off, const int32_t *node,
+                                  const int32_t *parent, const double *height,
+                                  const double *branchRates, const double *kappa,
+                                  const double *clockRate, double *logL)
+{
+    if (s && s->h && (!off || (!node && off[s->K] > 0)))
+        return mtt_fail(s->h->ctx, MTT_ERR_INVALID_ARG, "mtt_peel_chains_update_sparse: bad arguments");
+    static const int32_t none32 = 0;
+    static const double none64 = 0.0;
+    // (an empty proposal has no arrays to point at)
+    return chains_update(s, parent ? parent : &none32, height ? height : &none64, branchRates,
+                         kappa, clockRate, nullptr, logL, nullptr, off, node ? node : &none32);
 }
 
 int mtt_peel_chains_update_parts(mtt_peel_chains *s, const int32_t *parent, const double *height,

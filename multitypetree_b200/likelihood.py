@@ -309,6 +309,31 @@ class PeelChains:
                           _lib.ptr(clk), _lib.ptr(d), _lib.ptr(out)))
         return out
 
+    def update_sparse(self, off, node, parent, height, branchRates=None, kappa=None,
+                      clockRate=None) -> np.ndarray:
+        """The proposals as lists of changed nodes: chain k names node[off[k]:off[k+1]] with
+        their new parent / height (/ clock rate) per list entry (mtt_peel_chains_update_sparse);
+        everything else stays as accepted.  -> logL[nChains]."""
+        K = self.nChains
+        off = _lib.as_c(off, np.int64)
+        node = _lib.as_c(node, np.int32)
+        par = _lib.as_c(parent, np.int32)
+        h = _lib.as_c(height, np.float64)
+        if off.shape != (K + 1,) or not (node.shape == par.shape == h.shape == (int(off[-1]),)):
+            raise ValueError("off must be [nChains+1]; node/parent/height one entry per listed node")
+        r = None if branchRates is None else _lib.as_c(branchRates, np.float64)
+        if r is not None and r.shape != h.shape:
+            raise ValueError("branchRates must have one entry per listed node")
+        kap = None if kappa is None else _lib.as_c(
+            np.broadcast_to(np.asarray(kappa, np.float64), (K,)), np.float64)
+        clk = None if clockRate is None else _lib.as_c(
+            np.broadcast_to(np.asarray(clockRate, np.float64), (K,)), np.float64)
+        out = np.empty(K, np.float64)
+        self.ctx.check(_lib.lib().mtt_peel_chains_update_sparse(
+            self._s, _lib.ptr(off), _lib.ptr(node), _lib.ptr(par), _lib.ptr(h), _lib.ptr(r),
+            _lib.ptr(kap), _lib.ptr(clk), _lib.ptr(out)))
+        return out
+
     def accept(self, mask=None) -> None:
         """mask[nChains] (None = all): nonzero keeps the chain's proposal, zero drops it."""
         m = None if mask is None else _flags(mask)

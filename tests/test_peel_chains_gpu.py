@@ -359,3 +359,55 @@ def test_chains_verify_mode_catches_an_unflagged_change(ctx):
     np.testing.assert_allclose(got, tl.calculateLogPBatch(par, h2), rtol=RTOL_FULL)
     ch.close()
     tl.close()
+
+
+def test_chains_sparse_updates(ctx):
+    """The proposal as a list of changed nodes (what a BEAST shim has in hand) gives what the
+    full-array form gives: same moves, same accept / reject sequence, two sets of chains."""
+    n, K, steps = 40, 5, 40
+    N = 2 * n - 1
+    rng = np.random.default_rng(99)
+    par, hgt = _trees(K, n, seed=77)
+    f = np.array([.1, .2, .3, .4])
+    tips = simulate_alignment(par[0], hgt[0], 400, 2.5, f, 0.05, seed=3)
+    tl = TreeLikelihood(data=Alignment(states=tips), siteModel=SiteModel(HKY(2.5, f), 0.05), ctx=ctx)
+    dense, sparse = tl.chains(K), tl.chains(K)
+    empty = np.zeros(0)
+    with pytest.raises(mtt.MttError, match="full update"):      # nothing accepted yet
+        sparse.update_sparse(np.zeros(K + 1, np.int64), empty, empty, empty)
+    a = dense.update(par, hgt)
+    b = sparse.update(par, hgt)
+    assert np.array_equal(a, b)
+    dense.accept()
+    sparse.accept()
+    for step in range(steps):
+        ppar, phgt = par.copy(), hgt.copy()
+        off, node = [0], []
+        for k in range(K):
+            touched = _propose(rng, ppar[k], phgt[k], n)
+            if step % 5 == 0 and touched:
+                touched = touched + touched[:1]                 # a node named twice
+            node += touched
+            off.append(len(node))
+        node = np.array(node, np.int64)
+        chain = np.repeat(np.arange(K), np.diff(off))
+        a = dense.update(ppar, phgt)
+        b = sparse.update_sparse(off, node, ppar[chain, node], phgt[chain, node])
+        assert np.array_equal(a, b)
+        assert dense.last_entries == sparse.last_entries
+        acc = rng.random(K) < 0.5
+        dense.accept(acc)
+        sparse.accept(acc)
+        par[acc], hgt[acc] = ppar[acc], phgt[acc]
+    # a kappa move cannot be said with a list
+    with pytest.raises(mtt.MttError, match="full update"):
+        sparse.update_sparse(np.zeros(K + 1, np.int64), empty, empty, empty, kappa=3.0)
+    # ... and leaves the chains as they were; an out-of-range node is a malformed proposal
+    bad = sparse.update_sparse(np.array([0, 1, 1, 1, 1, 1]), [N + 4], [n], [1.0])
+    assert np.isnan(bad[0]) and np.array_equal(bad[1:], dense.update(par, hgt)[1:])
+    np.testing.assert_allclose(sparse.update(par, hgt), tl.calculateLogPBatch(par, hgt),
+                               rtol=RTOL_FULL)
+    assert sparse.last_entries == 0
+    for x in (dense, sparse):
+        x.close()
+    tl.close()

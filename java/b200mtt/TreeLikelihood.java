@@ -32,7 +32,7 @@ public class TreeLikelihood extends GenericTreeLikelihood {
     private MttNative.Chains chain;
     private Arena arena;
     private MemorySegment parent, height, dirtyNode, dirtyParent, dirtyHeight, off, one, zero, rates, props, freqs, out;
-    private boolean needFull = true;
+    private boolean needFull = true, pushedThisProposal = false;
     private double[] lastRates, lastProps, lastFreqs;
     private double lastPInv = Double.NaN, lastClock = Double.NaN, lastKappa = Double.NaN;
     private int nTips, nCat;
@@ -92,9 +92,9 @@ public class TreeLikelihood extends GenericTreeLikelihood {
                 || !java.util.Arrays.equals(f, lastFreqs) || pInv != lastPInv || clockRate != lastClock) {
             peel.setSiteModel(rates, props, freqs, pInv, clockRate);
             lastRates = r.clone(); lastProps = pr.clone(); lastFreqs = f.clone(); lastPInv = pInv; lastClock = clockRate;
-            needFull = true;
+            needFull = true; pushedThisProposal = true;
         }
-        if (kappa != lastKappa) { peel.setHky(kappa); lastKappa = kappa; needFull = true; }
+        if (kappa != lastKappa) { peel.setHky(kappa); lastKappa = kappa; needFull = true; pushedThisProposal = true; }
         if (needFull) {
             // first evaluation, or a model parameter moved: the whole tree, every node recomputed
             for (Node node : tree.getNodesAsArray()) {
@@ -129,14 +129,21 @@ public class TreeLikelihood extends GenericTreeLikelihood {
     @Override
     public void store() { super.store(); }
 
-    /** proposal rejected: drop it (BeerLikelihoodCore.restore); a rejected model-parameter move
-     *  leaves the library's setters at the rejected value, so the next evaluation is a full one */
+    /** proposal rejected: drop it (BeerLikelihoodCore.restore).  A rejected model-parameter move
+     *  leaves the library's setters at the rejected value: forget what was pushed, so that the
+     *  next evaluation pushes the restored values (and is a full one); a rejected tree move
+     *  costs nothing */
     @Override
-    public void restore() { chain.accept(zero); lastKappa = Double.NaN; lastPInv = Double.NaN; super.restore(); }
+    public void restore() {
+        chain.accept(zero);
+        if (pushedThisProposal) { lastKappa = Double.NaN; lastPInv = Double.NaN; }
+        pushedThisProposal = false;
+        super.restore();
+    }
 
     /** proposal accepted: its partials become the accepted ones */
     @Override
-    protected void accept() { chain.accept(one); super.accept(); }
+    protected void accept() { chain.accept(one); pushedThisProposal = false; super.accept(); }
 
     @Override
     protected boolean requiresRecalculation() {

@@ -534,7 +534,8 @@ def bench_peel(args):
 
 def bench_peel_chains(args):
     """cfg3 shape, MCMC regime: 64 resident chains, one node-height proposal per chain and step
-    (MultiTypeUniform), incremental peeling (mtt_peel_chains_update) + accept / reject, against a
+    (MultiTypeUniform) given as the changed node (mtt_peel_chains_update_sparse), incremental
+    peeling + accept / reject, against a
     full re-evaluation of the same proposals (mtt_peel_logl_batch).  Host-buffer API on both
     sides: the planner's host time is part of the number."""
     import torch
@@ -580,15 +581,16 @@ def bench_peel_chains(args):
         hi = np.where(pp >= 0, hgt[rows, np.maximum(pp, 0)], lo + 1.0)
         ph = hgt.copy()
         ph[rows, v] = lo + (hi - lo) * rng.uniform(0.05, 0.95, K)
-        dirty = np.zeros((K, nN), np.uint8)
-        dirty[rows, v] = 1
-        return ph, dirty
+        # the proposal in sparse form: one changed node per chain, with its parent and height
+        node = v.astype(np.int32)
+        return ph, (node, np.ascontiguousarray(par[rows, v]), np.ascontiguousarray(ph[rows, v]))
 
     ch.update(par, hgt)
     ch.accept()
     L = _lib.lib()
     got = np.empty(K, np.float64)
-    par_p, got_p = _lib.ptr(par), _lib.ptr(got)
+    off = np.arange(K + 1, dtype=np.int64)
+    off_p, got_p = _lib.ptr(off), _lib.ptr(got)
     t_upd = t_full = dev_ms = 0.0
     entries = dev_entries = 0
     err = 0.0
@@ -598,7 +600,7 @@ def bench_peel_chains(args):
     # reading the events back costs host time, so it is not part of pass 1
     with ClockSampler(local) as clk:
         for it in range(args.warmup + 2 * args.steps):
-            ph, dirty = propose()
+            ph, (node, npar, nhgt) = propose()
             timed = args.warmup <= it < args.warmup + args.steps
             if it == args.warmup + args.steps:
                 ch.set_timing(True)
@@ -606,8 +608,8 @@ def bench_peel_chains(args):
             lf0 = ctx.launch_count()
             # the C-ABI calls a Java shim would make, on the caller's buffers
             t0 = time.perf_counter()
-            ctx.check(L.mtt_peel_chains_update(ch._s, par_p, _lib.ptr(ph), None, None, None,
-                                               _lib.ptr(dirty), got_p))
+            ctx.check(L.mtt_peel_chains_update_sparse(ch._s, off_p, _lib.ptr(node), _lib.ptr(npar),
+                                                      _lib.ptr(nhgt), None, None, None, got_p))
             ctx.check(L.mtt_peel_chains_accept(ch._s, _lib.ptr(acc)))
             dt = time.perf_counter() - t0
             acc = acc != 0

@@ -611,6 +611,23 @@ public:
                                           nullptr, logL.data()));
         return logL;
     }
+    // the proposals as lists of changed nodes: chain k names node[off[k] .. off[k+1]) with their
+    // new parent / height per list entry; everything else stays as accepted
+    std::vector<double> updateSparse(const std::vector<int64_t> &off,
+                                     const std::vector<int32_t> &node,
+                                     const std::vector<int32_t> &parent,
+                                     const std::vector<double> &height)
+    {
+        if ((int)off.size() != K_ + 1 || node.size() != (size_t)off.back() ||
+            parent.size() != node.size() || height.size() != node.size())
+            throw std::invalid_argument("PeelChains::updateSparse: off[nChains+1], one entry per "
+                                        "listed node");
+        std::vector<double> logL(K_);
+        ctx_.check(mtt_peel_chains_update_sparse(s_, off.data(), node.data(), parent.data(),
+                                                 height.data(), nullptr, nullptr, nullptr,
+                                                 logL.data()));
+        return logL;
+    }
     // keep[k] != 0: chain k's proposal becomes its accepted state; empty = all
     void accept(const std::vector<uint8_t> &keep = {})
     {

@@ -112,6 +112,13 @@ int main(int argc, char **argv)
         const double wantB = lik.calculateLogP(b);
         chains.accept({1, 0});                         // chain 1 rejects: back to `tree`
         std::vector<double> l2 = chains.update({&a, &tree});
+        // the same move of chain 1 said as a list of one node
+        std::vector<double> l3 = chains.updateSparse({0, 0, 1}, {v}, {b.parent[v]}, {b.height[v]});
+        if (l3[0] != l0[0] || l3[1] != l1[1])
+            return 1;
+        chains.accept({0, 0});
+        if (chains.update({&a, &tree})[1] != l0[1] || chains.lastEntries() != 0)
+            return 1;
         std::printf("RESIDENT %.12f %.12f moved %.12f full %.12f entries %lld then %lld\n", l0[0],
                     l0[1], l1[1], wantB, entries, chains.lastEntries());
         auto close = [](double x, double y) { return std::fabs(x - y) <= 1e-12 * std::fabs(y); };

@@ -49,13 +49,29 @@ __device__ __noinline__ void mm(int d, const double *A, const double *B, double 
         __syncwarp();
         return;
     }
+    // four elements of C per lane and pass, as four independent sums: the rounding sequence of
+    // every element is the sequential one, only the dependent chains overlap
+    const int dd = d * d;
     #pragma unroll 1
-    for (int e = lane; e < d * d; e += 32) {
-        const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
-        double s = 0.0;
-        for (int k = 0; k < d; k++)
-            s = add_rn(s, mul_rn(A[i * d + k], B[k * d + j]));
-        C[e] = s;
+    for (int e0 = lane; e0 < dd; e0 += 128) {
+        int ia[4], jb[4];
+        double s[4];
+        #pragma unroll
+        for (int q = 0; q < 4; q++) {
+            const int e = min(e0 + 32 * q, dd - 1);     // (clamped: computed, not stored)
+            ia[q] = RC_ROW(rc[e]) * d;
+            jb[q] = RC_COL(rc[e]);
+            s[q] = 0.0;
+        }
+        for (int k = 0; k < d; k++) {
+            #pragma unroll
+            for (int q = 0; q < 4; q++)
+                s[q] = add_rn(s[q], mul_rn(A[ia[q] + k], B[k * d + jb[q]]));
+        }
+        #pragma unroll
+        for (int q = 0; q < 4; q++)
+            if (e0 + 32 * q < dd)
+                C[e0 + 32 * q] = s[q];
     }
     __syncwarp();
 }
@@ -326,9 +342,33 @@ __device__ __forceinline__ BranchSample sample_branch(
             int n = 0;
             double curLogRn = (size > 0) ? logTab[ab] : 0.0;         // log R^0[a,b]
             double curLogN = logN[1];                                // log(n) of the next step
-            while (true) {
+            // what the reference does when the table turned steady before the draw was found
+            auto steadyTail = [&]() {                                // :96-102
+                st = MTT_ST_NEEDS_POISSON_TAIL;                      // -> host
+                nVirt = n;                                           // thresh
+                if (TAIL_ON_DEVICE) {
+                    // rejection from Poisson(muL) until >= thresh, from the same window
+                    for (;;) {
+                        int draw = 0;
+                        if (!poisson_window(muL, u, nU, pos, draw)) {
+                            st = MTT_ST_NEED_MORE_UNIFORMS;
+                            break;
+                        }
+                        if (draw >= n) {
+                            nVirt = draw;
+                            st = MTT_ST_OK;
+                            break;
+                        }
+                    }
+                }
+            };
+            // (1) the first terms one by one: most branches are short and stop here
+            constexpr int SEQ_TERMS = 6;
+            bool done = false;
+            while (!done && n < SEQ_TERMS) {
                 if (n >= size && !steady) {
                     st = MTT_ST_NEED_MORE_POWERS;
+                    done = true;
                     break;
                 }
                 const int n1 = n + 1;
@@ -341,6 +381,7 @@ __device__ __forceinline__ BranchSample sample_branch(
                 Plow = add_rn(Plow, exp_ni(add_rn(curLogRn, acc)));        // :86
                 if (Plow > uu) {                                     // :88-89
                     nVirt = n;
+                    done = true;
                     break;
                 }
                 n += 1;
@@ -348,25 +389,47 @@ __device__ __forceinline__ BranchSample sample_branch(
                 curLogRn = nxtLogRn;
                 curLogN = nxtLogN;
                 if (!(steadyN < 0 || n < steadyN)) {                 // :94
-                    st = MTT_ST_NEEDS_POISSON_TAIL;                  // :96-102 -> host
-                    nVirt = n;                                       // thresh
-                    if (TAIL_ON_DEVICE) {
-                        // rejection from Poisson(muL) until >= thresh, from the same window
-                        for (;;) {
-                            int draw = 0;
-                            if (!poisson_window(muL, u, nU, pos, draw)) {
-                                st = MTT_ST_NEED_MORE_UNIFORMS;
-                                break;
-                            }
-                            if (draw >= n) {
-                                nVirt = draw;
-                                st = MTT_ST_OK;
-                                break;
-                            }
-                        }
-                    }
-                    break;
+                    steadyTail();
+                    done = true;
                 }
+            }
+            // (2) a long branch: 32 terms at a time.  Lane j owns term n + j; the running
+            // exponent acc_(n+j) is the reference's chain of rounded additions (cheap, done by
+            // every lane), the exp() of the 32 terms is evaluated side by side, and the partial
+            // sums are then added up and tested in the reference's order.
+            while (!done) {
+                const int nj = n + lane;
+                const int m = nj + 1;                                // index of the log(n) the step after term nj uses
+                const double dj = sub_rn(log_muL, m < U_LOGN ? logN[m] : log_ni((double)m));
+                const double logRj = logTab[(size_t)min(nj, size - 1) * dd + ab];
+                double run = acc, mine = acc;
+#pragma unroll
+                for (int j = 0; j < 32; j++) {
+                    if (lane == j)
+                        mine = run;
+                    run = add_rn(run, __shfl_sync(FULL_MASK, dj, j));
+                }
+                const double term = exp_ni(add_rn(logRj, mine));
+                for (int j = 0; j < 32; j++) {
+                    if (n >= size && !steady) {
+                        st = MTT_ST_NEED_MORE_POWERS;
+                        done = true;
+                        break;
+                    }
+                    Plow = add_rn(Plow, __shfl_sync(FULL_MASK, term, j));   // :86
+                    if (Plow > uu) {                                 // :88-89
+                        nVirt = n;
+                        done = true;
+                        break;
+                    }
+                    n += 1;                                          // :92 (acc: `run`, below)
+                    if (!(steadyN < 0 || n < steadyN)) {             // :94
+                        steadyTail();
+                        done = true;
+                        break;
+                    }
+                }
+                acc = run;
             }
         }
     }
@@ -419,15 +482,32 @@ __device__ __forceinline__ BranchSample sample_branch(
             double prod = 0.0;
             if (lane < d)
                 prod = mul_rn(buf[prev * d + lane], loCol);
-            int c = 0;
-            bool fell = true;
-            for (c = 0; c < d; c++) {
-                u2 = sub_rn(u2, __shfl_sync(FULL_MASK, prod, c));    // :170-171
-                if (u2 < 0.0) {
-                    fell = false;
-                    break;
+            int c = d;
+            if (d > 4) {
+                // many demes: the d products first (independent shuffles), then the chain of
+                // subtractions in the reference's order, stopping at the first negative value
+                double pr[MTT_MAX_DEMES];
+#pragma unroll
+                for (int q = 0; q < MTT_MAX_DEMES; q++)
+                    pr[q] = __shfl_sync(FULL_MASK, prod, q);
+#pragma unroll
+                for (int q = 0; q < MTT_MAX_DEMES; q++) {
+                    if (q < d && c == d) {
+                        u2 = sub_rn(u2, pr[q]);                      // :170-171
+                        if (u2 < 0.0)
+                            c = q;
+                    }
+                }
+            } else {
+                for (int q = 0; q < d; q++) {
+                    u2 = sub_rn(u2, __shfl_sync(FULL_MASK, prod, q));    // :170-171
+                    if (u2 < 0.0) {
+                        c = q;
+                        break;
+                    }
                 }
             }
+            const bool fell = c == d;
             if (fell) {                                              // :179-190
                 st = MTT_ST_FB_FELL_THROUGH;
                 break;

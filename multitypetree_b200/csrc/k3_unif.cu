@@ -24,7 +24,7 @@ namespace {
 
 // ---- updateMatrices (SCMigrationModel.java:150-201), one warp per model ------------------
 __global__ void k3_update_matrices(int nModels, int d, const double *m, int sym, double *Q,
-                                   double *R, double *mu)
+                                   double *R, double *mu, double *logQ)
 {
     const int model = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
@@ -53,6 +53,12 @@ __global__ void k3_update_matrices(int nModels, int d, const double *m, int sym,
         const int i = e / d, j = e - i * d;
         r[e] = add_rn(mul_rn(q[e], rm), (i == j) ? 1.0 : 0.0);   // Q.mul(1.0/mu).add(eye) :183
     }
+    // log Q[i,j], the term a type change i -> j adds to a path probability (:211-221, :249-258):
+    // tabulated once per model with the device log() the kernels would call per change
+    double *lq = logQ + (size_t)model * d * d;
+    #pragma unroll 1
+    for (int e = lane; e < d * d; e += 32)
+        lq[e] = log_ni(q[e]);
     if (lane == 0)
         mu[model] = muV;
 }
@@ -181,7 +187,8 @@ __global__ void k3_pba(long long n, int d, const double *Qall, const int *model,
 }
 
 // ---- getBranchTypeProb (UniformizationRetypeOperator.java:233-275), one warp per branch ----
-__global__ void k3_branch_logp(long long n, int d, const double *Qall, const int *model,
+__global__ void k3_branch_logp(long long n, int d, const double *Qall, const double *logQall,
+                               const int *model,
                                const double *tBottom, const double *tTop,
                                const uint8_t *typeBottom, const uint8_t *typeTop,
                                const long long *chgOff, const double *chgTime,
@@ -197,7 +204,7 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
     uint16_t *rc = rcAll[threadIdx.x >> 5];
     fill_rc(rc, d, threadIdx.x & 31);
     double *buf = sm + (size_t)warp * 8 * dd;
-    const double *Q = Qall + (size_t)model[br] * dd;
+    const double *Q = Qall + (size_t)model[br] * dd, *lQ = logQall + (size_t)model[br] * dd;
     const double t0 = tBottom[br], t1 = tTop[br];
     const int a = typeBottom[br], b = typeTop[br];
     double lp = 0.0, lastTime = t0;
@@ -206,7 +213,7 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
         const double thisTime = chgTime[k];
         const int thisCol = chgType[k];
         lp = add_rn(lp, add_rn(mul_rn(sub_rn(thisTime, lastTime), Q[lastCol * d + lastCol]),
-                               log_ni(Q[lastCol * d + thisCol])));
+                               lQ[lastCol * d + thisCol]));
         lastTime = thisTime;
         lastCol = thisCol;
     }
@@ -228,7 +235,7 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const int
 struct RetypeParams {
     long long nJobs;
     int d, powCap, outCap;
-    const double *Q, *R, *mu, *pow, *logPow, *logN;
+    const double *Q, *R, *mu, *pow, *logPow, *logN, *logQ;
     const int *meta;
     const long long *brOff;
     const int *model;
@@ -283,6 +290,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
         }
         const int mdl = p.model[br];
         const double *Q = p.Q + (size_t)mdl * dd, *R = p.R + (size_t)mdl * dd;
+        const double *lQ = p.logQ + (size_t)mdl * dd;
         const double t0 = p.tBottom[br], t1 = p.tTop[br];
         const int a = p.typeBottom[br], b = p.typeTop[br];
         const size_t w = (size_t)blockIdx.x * U_WARPS + warp;
@@ -314,7 +322,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
                     }
                     nChg++;
                     lp = add_rn(lp, add_rn(mul_rn(Q[prevType * d + prevType], sub_rn(ti, prevTime)),
-                                           log_ni(Q[prevType * d + ty])));
+                                           lQ[prevType * d + ty]));
                     prevType = ty;
                     prevTime = ti;
                 }
@@ -425,8 +433,11 @@ int mtt_unif_set_models(mtt_ctx *ctx, int nModels, int d, const double *m, int s
     MTT_CUDA(ctx, cudaMemcpyAsync(dM, m, nModels * dd * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemsetAsync(meta, 0, nModels * 2 * sizeof(int), s));   // drop cached powers
     const int wpb = 4;
+    double *dLogQ = (double *)mtt_buf(ctx, BUF_U_LOGQ, nModels * dd * 8);
+    if (!dLogQ)
+        return MTT_ERR_CUDA;
     k3_update_matrices<<<(nModels + wpb - 1) / wpb, wpb * 32, 0, s>>>(nModels, d, dM, sym, dQ, dR,
-                                                                      dMu);
+                                                                      dMu, dLogQ);
     MTT_CHECK_LAUNCH(ctx);
     double *logN = (double *)mtt_buf(ctx, BUF_U_LOGN, U_LOGN * 8);
     if (!logN)
@@ -573,7 +584,8 @@ int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t n, const int32_t *model,
     MTT_CUDA(ctx, cudaFuncSetAttribute(k3_branch_logp, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)expm_smem(d)));
     k3_branch_logp<<<(unsigned)((n + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
-        n, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel, dT0, dT1, dA, dB, dOff, dCT, dCTy, dLP,
+        n, d, (const double *)ctx->bufs[BUF_U_Q].p, (const double *)ctx->bufs[BUF_U_LOGQ].p, dModel,
+        dT0, dT1, dA, dB, dOff, dCT, dCTy, dLP,
         dSt);
     MTT_CHECK_LAUNCH(ctx);
     return x.download();
@@ -700,7 +712,8 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
                                            (int)expm_smem(d)));
         k3_branch_logp<<<(unsigned)((old->n + U_WARPS - 1) / U_WARPS), U_WARPS * 32,
                          expm_smem(d), ctx->copyStream>>>(
-            old->n, d, (const double *)ctx->bufs[BUF_U_Q].p, dOModel, dOT0, dOT1, dOA, dOB, dOOff,
+            old->n, d, (const double *)ctx->bufs[BUF_U_Q].p,
+            (const double *)ctx->bufs[BUF_U_LOGQ].p, dOModel, dOT0, dOT1, dOA, dOB, dOOff,
             dOCT2, dOCTy2, dOLP, dOSt);
         MTT_CHECK_LAUNCH(ctx);
         MTT_CUDA(ctx, cudaEventRecord(ctx->events[1], ctx->copyStream));
@@ -744,6 +757,7 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         RetypeParams p;
         p.nJobs = nJobs; p.d = d; p.powCap = ctx->unifPowCap; p.outCap = outCap;
         p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
+        p.logQ = (const double *)ctx->bufs[BUF_U_LOGQ].p;
         p.mu = (const double *)ctx->bufs[BUF_U_MU].p; p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
         p.logPow = (const double *)ctx->bufs[BUF_U_LOGPOW].p;
         p.logN = (const double *)ctx->bufs[BUF_U_LOGN].p;

@@ -41,7 +41,7 @@ struct ParticleParams {
     long long nTrees;
     int nParticles, d, powCap;
     int eCap, tCap, nCap;            // stage capacities (multiples of 8)
-    const double *Q, *R, *mu, *pow, *logPow, *logN;
+    const double *Q, *R, *mu, *pow, *logPow, *logN, *logQ;
     const int *meta;
     const int *model;                // per tree
     const double *N;                 // [nModels][d]
@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
     const int part = (int)(q - tree * p.nParticles);
     const int mdl = p.model[tree];
     const double *Q = p.Q + (size_t)mdl * dd, *R = p.R + (size_t)mdl * dd;
+    const double *lQ = p.logQ + (size_t)mdl * dd;
     const double *tab = p.pow + (size_t)mdl * p.powCap * dd;
     const double *logTab = p.logPow + (size_t)mdl * p.powCap * dd;
     const int size = p.meta[2 * mdl], steady = p.meta[2 * mdl + 1];
@@ -182,7 +183,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
                 if (newType >= d)
                     newType = (type == d - 1) ? d - 2 : d - 1;
                 emit(PK_MIGRATE, type, newType, time);
-                thisLogP = add_rn(thisLogP, log_ni(Q[type * d + newType]));
+                thisLogP = add_rn(thisLogP, lQ[type * d + newType]);
                 type = newType;
             }
             w = sub_rn(w, thisLogP);                                             // :134
@@ -228,7 +229,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
                     prevNode = parent[prevNode];
                 }
                 lp = add_rn(lp, add_rn(mul_rn(Q[prevType * d + prevType], sub_rn(ti, prevTime)),
-                                       log_ni(Q[prevType * d + ty])));
+                                       lQ[prevType * d + ty]));
                 prevType = ty;
                 prevTime = ti;
             }
@@ -473,6 +474,7 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         p.nTrees = nTrees; p.nParticles = nParticles; p.d = d; p.powCap = ctx->unifPowCap;
         p.eCap = eCap; p.tCap = tCap; p.nCap = nCap;
         p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
+        p.logQ = (const double *)ctx->bufs[BUF_U_LOGQ].p;
         p.mu = (const double *)ctx->bufs[BUF_U_MU].p;
         p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
         p.logPow = (const double *)ctx->bufs[BUF_U_LOGPOW].p;

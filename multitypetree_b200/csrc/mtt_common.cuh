@@ -46,7 +46,7 @@ enum BufId {
     BUF_D_MODEL = 0, BUF_D_N, BUF_D_NODEOFF, BUF_D_HEIGHT, BUF_D_PARENT, BUF_D_NODETYPE,
     BUF_D_CHGCOUNT, BUF_D_CHGBASE, BUF_D_CHGTIME, BUF_D_CHGTYPE, BUF_D_LOGP, BUF_D_VALID,
     BUF_D_QUEUE, BUF_D_CHGNODE, BUF_D_TIPH, BUF_D_TIPT, BUF_D_INTH, BUF_D_INTT,
-    BUF_U_Q, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
+    BUF_U_Q, BUF_U_LOGQ, BUF_U_R, BUF_U_MU, BUF_U_POW, BUF_U_LOGPOW, BUF_U_LOGN, BUF_U_META, BUF_U_IN0, BUF_U_IN1, BUF_U_IN2,
     BUF_U_IN3, BUF_U_IN4, BUF_U_IN5, BUF_U_IN6, BUF_U_IN7, BUF_U_IN8, BUF_U_OUT0, BUF_U_OUT1,
     BUF_U_OUT2, BUF_U_OUT3, BUF_U_OUT4, BUF_U_OUT5, BUF_U_OUT6, BUF_U_OUT7, BUF_U_PBA,
     BUF_U_LIN0, BUF_U_LIN1, BUF_U_LIN2, BUF_U_LIN3, BUF_U_LIN4, BUF_U_LIN5, BUF_U_LIN6, BUF_U_LIN7,

@@ -686,7 +686,7 @@ public:
         const size_t C = chains_.size();
         std::vector<double> logHR(C, 0.0);
         std::vector<int> node(C);
-        std::vector<std::vector<int>> br(C);
+        std::vector<BranchList> br(C);
         // ---- node choice (:36-37) and probability of the current typing (:40-44)
         B_.clear();
         std::vector<int64_t> off{0};
@@ -721,7 +721,7 @@ public:
             size_t chain;
             size_t start = 0;
             int window;
-            std::vector<int32_t> forced;
+            int32_t forced[3] = {-1, -1, -1};
             bool failed = false;
         };
         std::vector<Job> pending;
@@ -738,7 +738,6 @@ public:
                 need += 2.0 * (muL + 6.0 * std::sqrt(muL) + 8.0) + 1.0;
             }
             j.window = std::max(window_, ((int)need + 31) / 32 * 32);
-            j.forced.assign(br[c].size(), -1);
             pending.push_back(j);
         }
         std::vector<char> noPath(C, 0);
@@ -856,6 +855,16 @@ public:
     }
 
 private:
+    // the <= 3 branches of a proposal (node, left, right), without a heap allocation per chain
+    struct BranchList {
+        int v[3];
+        int n = 0;
+        void push_back(int x) { v[n++] = x; }
+        size_t size() const { return (size_t)n; }
+        int operator[](size_t i) const { return v[i]; }
+        const int *begin() const { return v; }
+        const int *end() const { return v + n; }
+    };
     struct Branches {
         std::vector<double> t0, t1;
         std::vector<uint8_t> a, b;

@@ -36,6 +36,7 @@ __device__ __forceinline__ void fill_rc(uint16_t *rc, int d, int lane)
 // C = A * B (d x d, row-major, shared memory); C must not alias A or B.  Deliberately NOT
 // inlined: expm calls it ~10 times and the kernels must stay instruction-cache resident
 // (the fully inlined expm was 4400 SASS instructions and stalled on instruction fetch).
+template <bool ILP>
 __device__ __noinline__ void mm(int d, const double *A, const double *B, double *C,
                                 const uint16_t *rc, int lane)
 {
@@ -49,29 +50,41 @@ __device__ __noinline__ void mm(int d, const double *A, const double *B, double 
         __syncwarp();
         return;
     }
-    // four elements of C per lane and pass, as four independent sums: the rounding sequence of
-    // every element is the sequential one, only the dependent chains overlap
     const int dd = d * d;
-    #pragma unroll 1
-    for (int e0 = lane; e0 < dd; e0 += 128) {
-        int ia[4], jb[4];
-        double s[4];
-        #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            const int e = min(e0 + 32 * q, dd - 1);     // (clamped: computed, not stored)
-            ia[q] = RC_ROW(rc[e]) * d;
-            jb[q] = RC_COL(rc[e]);
-            s[q] = 0.0;
-        }
-        for (int k = 0; k < d; k++) {
+    if (ILP) {
+        // four elements of C per lane and pass, as four independent sums: the rounding
+        // sequence of every element is the sequential one, only the dependent chains overlap
+        // (the latency-bound kernels of a few dozen chains; costs registers)
+        #pragma unroll 1
+        for (int e0 = lane; e0 < dd; e0 += 128) {
+            int ia[4], jb[4];
+            double s[4];
+            #pragma unroll
+            for (int q = 0; q < 4; q++) {
+                const int e = min(e0 + 32 * q, dd - 1);     // (clamped: computed, not stored)
+                ia[q] = RC_ROW(rc[e]) * d;
+                jb[q] = RC_COL(rc[e]);
+                s[q] = 0.0;
+            }
+            for (int k = 0; k < d; k++) {
+                #pragma unroll
+                for (int q = 0; q < 4; q++)
+                    s[q] = add_rn(s[q], mul_rn(A[ia[q] + k], B[k * d + jb[q]]));
+            }
             #pragma unroll
             for (int q = 0; q < 4; q++)
-                s[q] = add_rn(s[q], mul_rn(A[ia[q] + k], B[k * d + jb[q]]));
+                if (e0 + 32 * q < dd)
+                    C[e0 + 32 * q] = s[q];
         }
-        #pragma unroll
-        for (int q = 0; q < 4; q++)
-            if (e0 + 32 * q < dd)
-                C[e0 + 32 * q] = s[q];
+    } else {
+        #pragma unroll 1
+        for (int e = lane; e < dd; e += 32) {
+            const int i = RC_ROW(rc[e]), j = RC_COL(rc[e]);
+            double s = 0.0;
+            for (int k = 0; k < d; k++)
+                s = add_rn(s, mul_rn(A[i * d + k], B[k * d + j]));
+            C[e] = s;
+        }
     }
     __syncwarp();
 }
@@ -147,6 +160,7 @@ __device__ __noinline__ void lu_solve(int d, double *D, double *N, const uint16_
 
 // expm(Q * L) with Q in global/shared memory; `buf` = 8 d*d shared-memory matrices of this
 // warp.  Returns a pointer (inside buf) to the result.
+template <bool ILP = false>
 __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, double *buf,
                                               const uint16_t *rc, int lane)
 {
@@ -174,14 +188,14 @@ __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, 
     for (int e = lane; e < dd; e += 32)
         As[e] = mul_rn(As[e], invScale);
     __syncwarp();
-    mm(d, As, As, A2, rc, lane);
-    mm(d, A2, A2, A4, rc, lane);
-    mm(d, A4, A2, A6, rc, lane);
+    mm<ILP>(d, As, As, A2, rc, lane);
+    mm<ILP>(d, A2, A2, A4, rc, lane);
+    mm<ILP>(d, A4, A2, A6, rc, lane);
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
         T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 6);
     __syncwarp();
-    mm(d, T, A6, U, rc, lane);
+    mm<ILP>(d, T, A6, U, rc, lane);
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
         const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
@@ -194,7 +208,7 @@ __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, 
     for (int e = lane; e < dd; e += 32)
         T[e] = pade_poly((RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0, A2[e], A4[e], A6[e], 7);
     __syncwarp();
-    mm(d, T, A6, V, rc, lane);
+    mm<ILP>(d, T, A6, V, rc, lane);
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
         const double eye = (RC_ROW(rc[e]) == RC_COL(rc[e])) ? 1.0 : 0.0;
@@ -203,7 +217,7 @@ __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, 
                       V[e]);
     }
     __syncwarp();
-    mm(d, As, V, W, rc, lane);                                  // AV
+    mm<ILP>(d, As, V, W, rc, lane);                                  // AV
     double *Nn = A2, *D = A4;                               // A2, A4 are dead from here
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32) {
@@ -215,7 +229,7 @@ __device__ __noinline__ const double *expm_QL(int d, const double *Q, double L, 
     lu_solve(d, D, Nn, rc, lane);
     double *F = Nn, *G = T;
     for (int k = 0; k < j; k++) {                           // F = F * F, j times
-        mm(d, F, F, G, rc, lane);
+        mm<ILP>(d, F, F, G, rc, lane);
         double *t = F;
         F = G;
         G = t;
@@ -293,7 +307,10 @@ struct BranchSample {
 // describe the model's R^k table, logTab the elementwise log of it, logN[n] = log(n).
 // TAIL_ON_DEVICE draws the steady-state Poisson tail
 // (:96-102) from the window instead of handing it to the host.
-template <bool TAIL_ON_DEVICE>
+// LONG_BRANCHES adds the paths that cut the LATENCY of a branch with many virtual events (the
+// retype kernel of a few dozen chains waits for its slowest warp); they cost registers, so the
+// throughput-bound particle kernel leaves them out.  Results are identical either way.
+template <bool TAIL_ON_DEVICE, bool LONG_BRANCHES = false>
 __device__ __forceinline__ BranchSample sample_branch(
     int d, const double *Q, const double *R, const double *tab, const double *logTab,
     const double *logN, int size, int steady, double mu,
@@ -312,7 +329,7 @@ __device__ __forceinline__ BranchSample sample_branch(
     if (PbaPre) {
         Pba = *PbaPre;
     } else {
-        const double *E = expm_QL(d, Q, L, buf, rc, lane);
+        const double *E = expm_QL<LONG_BRANCHES>(d, Q, L, buf, rc, lane);
         Pba = E[a * d + b];
     }
     __syncwarp();
@@ -363,7 +380,7 @@ __device__ __forceinline__ BranchSample sample_branch(
                 }
             };
             // (1) the first terms one by one: most branches are short and stop here
-            constexpr int SEQ_TERMS = 6;
+            constexpr int SEQ_TERMS = LONG_BRANCHES ? 6 : 0x7fffffff;
             bool done = false;
             while (!done && n < SEQ_TERMS) {
                 if (n >= size && !steady) {
@@ -397,7 +414,7 @@ __device__ __forceinline__ BranchSample sample_branch(
             // exponent acc_(n+j) is the reference's chain of rounded additions (cheap, done by
             // every lane), the exp() of the 32 terms is evaluated side by side, and the partial
             // sums are then added up and tested in the reference's order.
-            while (!done) {
+            while (LONG_BRANCHES && !done) {
                 const int nj = n + lane;
                 const int m = nj + 1;                                // index of the log(n) the step after term nj uses
                 const double dj = sub_rn(log_muL, m < U_LOGN ? logN[m] : log_ni((double)m));
@@ -483,7 +500,7 @@ __device__ __forceinline__ BranchSample sample_branch(
             if (lane < d)
                 prod = mul_rn(buf[prev * d + lane], loCol);
             int c = d;
-            if (d > 4) {
+            if (LONG_BRANCHES && d > 4) {
                 // many demes: the d products first (independent shuffles), then the chain of
                 // subtractions in the reference's order, stopping at the first negative value
                 double pr[MTT_MAX_DEMES];

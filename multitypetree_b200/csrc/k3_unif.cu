@@ -96,7 +96,7 @@ __global__ void k3_rpow_extend(int nModels, int d, const double *R, double *pow,
     if (target >= powCap)
         target = powCap - 1;
     for (int i = size; i <= target && !steady; i++) {       // :428-448
-        mm(d, sPrev, sR, sNew, rc, lane);
+        mm<false>(d, sPrev, sR, sNew, rc, lane);
         bool anyNaN = false, anyPos = false;
         #pragma unroll 1
         for (int e = lane; e < dd; e += 32) {
@@ -157,7 +157,7 @@ __global__ void k3_expm_batch(long long n, int d, const double *Q, const int *mo
     uint16_t *rc = rcAll[threadIdx.x >> 5];
     fill_rc(rc, d, threadIdx.x & 31);
     double *buf = sm + (size_t)warp * 8 * dd;
-    const double *F = expm_QL(d, Q + (size_t)model[item] * dd, L[item], buf, rc, lane);
+    const double *F = expm_QL<true>(d, Q + (size_t)model[item] * dd, L[item], buf, rc, lane);
     #pragma unroll 1
     for (int e = lane; e < dd; e += 32)
         out[item * dd + e] = F[e];
@@ -181,7 +181,7 @@ __global__ void k3_pba(long long n, int d, const double *Qall, const int *model,
     fill_rc(rc, d, threadIdx.x & 31);
     double *buf = sm + (size_t)warp * 8 * dd;
     const double L = sub_rn(tTop[br], tBottom[br]);
-    const double *E = expm_QL(d, Qall + (size_t)model[br] * dd, L, buf, rc, lane);
+    const double *E = expm_QL<true>(d, Qall + (size_t)model[br] * dd, L, buf, rc, lane);
     if (lane == 0)
         pba[br] = E[typeBottom[br] * d + typeTop[br]];
 }
@@ -218,7 +218,7 @@ __global__ void k3_branch_logp(long long n, int d, const double *Qall, const dou
         lastCol = thisCol;
     }
     lp = add_rn(lp, mul_rn(sub_rn(t1, lastTime), Q[lastCol * d + lastCol]));   // :259
-    const double *E = expm_QL(d, Q, sub_rn(t1, t0), buf, rc, lane);          // :263-264
+    const double *E = expm_QL<true>(d, Q, sub_rn(t1, t0), buf, rc, lane);    // :263-264
     const double Pba = E[a * d + b];
     if (lane == 0) {
         if (Pba > 1.0 || Pba < 0.0) {                                    // :267-270
@@ -294,7 +294,7 @@ __global__ void __launch_bounds__(U_WARPS * 32) k3_retype(const RetypeParams p)
         const double t0 = p.tBottom[br], t1 = p.tTop[br];
         const int a = p.typeBottom[br], b = p.typeTop[br];
         const size_t w = (size_t)blockIdx.x * U_WARPS + warp;
-        const BranchSample bs = sample_branch<false>(
+        const BranchSample bs = sample_branch<false, true>(
             d, Q, R, p.pow + (size_t)mdl * p.powCap * dd, p.logPow + (size_t)mdl * p.powCap * dd,
             p.logN, p.meta[2 * mdl], p.meta[2 * mdl + 1],
             p.mu[mdl], t0, t1, a, b, p.nVirtForced ? p.nVirtForced[br] : -1, u, nU, pos, buf, rc,

@@ -608,6 +608,148 @@ struct OldTyping {
     int32_t *status;
 };
 
+constexpr int RETYPE_REDO = 1;        // (internal) the R^k table was too short
+
+int retype_chunked(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff, const int32_t *model,
+                   const double *tBottom, const double *tTop, const uint8_t *typeBottom,
+                   const uint8_t *typeTop, const int32_t *nVirtForced, const double *uniforms,
+                   const int64_t *uOff, int outCap, int32_t *nChg, double *outChgTime,
+                   uint8_t *outChgType, double *logProb, int32_t *status, int32_t *nVirt,
+                   int64_t *uUsed, int K)
+{
+    constexpr int NC = 8;
+    cudaStream_t s = ctx->stream;
+    const int d = ctx->unifD;
+    const size_t dd = (size_t)d * d;
+    const int64_t nBr = brOff[nJobs], nU = uOff[nJobs];
+    if (!ctx->copyStream)
+        MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+    if (!ctx->copyStream2)
+        MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream2, cudaStreamNonBlocking));
+    while ((int)ctx->events.size() < 2 * NC + 1) {
+        cudaEvent_t ev;
+        MTT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+        ctx->events.push_back(ev);
+    }
+    // the per-branch and per-job inputs are small next to the uniforms: one upload up front
+    int *dModel, *dForced = nullptr;
+    double *dT0, *dT1;
+    uint8_t *dA, *dB;
+    long long *dBrOff, *dUOff;
+    Xfer x(ctx, 0);                     // (never staged: these arrays are megabytes)
+    x.in(model, (size_t)nBr, BUF_U_IN0, &dModel);
+    x.in(tBottom, (size_t)nBr, BUF_U_IN1, &dT0);
+    x.in(tTop, (size_t)nBr, BUF_U_IN2, &dT1);
+    x.in(typeBottom, (size_t)nBr, BUF_U_IN3, &dA);
+    x.in(typeTop, (size_t)nBr, BUF_U_IN4, &dB);
+    x.in((const long long *)brOff, (size_t)nJobs + 1, BUF_U_IN5, &dBrOff);
+    x.in((const long long *)uOff, (size_t)nJobs + 1, BUF_U_IN7, &dUOff);
+    if (nVirtForced)
+        x.in(nVirtForced, (size_t)nBr, BUF_U_IN8, &dForced);
+    int rc = x.prepare();
+    if (rc == MTT_OK)
+        rc = x.upload();
+    if (rc != MTT_OK)
+        return rc;
+    double *dU = (double *)mtt_buf(ctx, BUF_U_IN6, (size_t)nU * 8);
+    int *dNChg = (int *)mtt_buf(ctx, BUF_U_OUT0, (size_t)nBr * 4);
+    double *dOCT = (double *)mtt_buf(ctx, BUF_U_OUT1, (size_t)nBr * outCap * 8);
+    uint8_t *dOCTy = (uint8_t *)mtt_buf(ctx, BUF_U_OUT2, (size_t)nBr * outCap);
+    double *dLP = (double *)mtt_buf(ctx, BUF_U_OUT3, (size_t)nBr * 8);
+    int *dSt = (int *)mtt_buf(ctx, BUF_U_OUT4, (size_t)nBr * 4);
+    int *dNVirt = (int *)mtt_buf(ctx, BUF_U_OUT7, (size_t)nBr * 4);
+    long long *dUsed = (long long *)mtt_buf(ctx, BUF_U_OUT5, (size_t)nJobs * 8);
+    double *dPba = (double *)mtt_buf(ctx, BUF_U_PBA, (size_t)nBr * 8);
+    if (!dU || !dNChg || !dOCT || !dOCTy || !dLP || !dSt || !dNVirt || !dUsed || !dPba)
+        return MTT_ERR_CUDA;
+    if ((rc = ensure_powers(ctx, K)) != MTT_OK)
+        return rc;
+    int tCap = 32;
+    while (tCap < K && tCap < U_TCAP)
+        tCap <<= 1;
+    const size_t smem = (size_t)U_WARPS * (8 * dd + tCap + tCap / 8) * 8;
+    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_retype, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)smem));
+    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_pba, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)expm_smem(d)));
+    const int64_t perChunk = (nJobs + NC - 1) / NC;
+    const unsigned maxBlocks = (unsigned)((perChunk + U_WARPS - 1) / U_WARPS);
+    int scratchCap = 0;
+    double *scrT = nullptr;
+    uint8_t *scrTy = nullptr;
+    if (K > U_TCAP) {
+        scratchCap = K + 1;
+        scrT = (double *)mtt_buf(ctx, BUF_U_OUT6, (size_t)maxBlocks * U_WARPS * scratchCap * 9);
+        if (!scrT)
+            return MTT_ERR_CUDA;
+        scrTy = (uint8_t *)(scrT + (size_t)maxBlocks * U_WARPS * scratchCap);
+    }
+    // everything above runs on the main stream: the copy streams start after it
+    MTT_CUDA(ctx, cudaEventRecord(ctx->events[2 * NC], s));
+    MTT_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->events[2 * NC], 0));
+    MTT_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream2, ctx->events[2 * NC], 0));
+    for (int c = 0; c < NC; c++) {
+        const int64_t j0 = std::min<int64_t>(nJobs, perChunk * c);
+        const int64_t j1 = std::min<int64_t>(nJobs, perChunk * (c + 1));
+        if (j1 <= j0)
+            continue;
+        const int64_t br0 = brOff[j0], br1 = brOff[j1], u0 = uOff[j0], u1 = uOff[j1];
+        // up: this chunk's uniforms
+        if (u1 > u0)
+            MTT_CUDA(ctx, cudaMemcpyAsync(dU + u0, uniforms + u0, (size_t)(u1 - u0) * 8,
+                                          cudaMemcpyHostToDevice, ctx->copyStream));
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[c], ctx->copyStream));
+        MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[c], 0));
+        // kernels: the branches' matrix exponentials, then the jobs
+        if (br1 > br0) {
+            k3_pba<<<(unsigned)((br1 - br0 + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d),
+                     s>>>(br1 - br0, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel + br0,
+                          dT0 + br0, dT1 + br0, dA + br0, dB + br0, dPba + br0);
+            MTT_CHECK_LAUNCH(ctx);
+        }
+        RetypeParams p;
+        p.nJobs = j1 - j0; p.d = d; p.powCap = ctx->unifPowCap; p.outCap = outCap;
+        p.Q = (const double *)ctx->bufs[BUF_U_Q].p; p.R = (const double *)ctx->bufs[BUF_U_R].p;
+        p.logQ = (const double *)ctx->bufs[BUF_U_LOGQ].p;
+        p.mu = (const double *)ctx->bufs[BUF_U_MU].p; p.pow = (const double *)ctx->bufs[BUF_U_POW].p;
+        p.logPow = (const double *)ctx->bufs[BUF_U_LOGPOW].p;
+        p.logN = (const double *)ctx->bufs[BUF_U_LOGN].p;
+        p.meta = (const int *)ctx->bufs[BUF_U_META].p;
+        // (offsets stay absolute: the branch / uniform / output arrays are passed whole)
+        p.brOff = dBrOff + j0; p.model = dModel; p.tBottom = dT0; p.tTop = dT1; p.typeBottom = dA;
+        p.typeTop = dB; p.nVirtForced = dForced; p.uniforms = dU; p.uOff = dUOff + j0;
+        p.nChg = dNChg; p.outChgTime = dOCT; p.outChgType = dOCTy; p.logProb = dLP;
+        p.status = dSt; p.nVirt = dNVirt; p.uUsed = dUsed + j0;
+        p.scratchT = scrT; p.scratchTy = scrTy; p.scratchCap = scratchCap; p.tCap = tCap;
+        p.pba = dPba;
+        k3_retype<<<(unsigned)((j1 - j0 + U_WARPS - 1) / U_WARPS), U_WARPS * 32, smem, s>>>(p);
+        MTT_CHECK_LAUNCH(ctx);
+        MTT_CUDA(ctx, cudaEventRecord(ctx->events[NC + c], s));
+        // down: this chunk's results
+        cudaStream_t dn = ctx->copyStream2;
+        MTT_CUDA(ctx, cudaStreamWaitEvent(dn, ctx->events[NC + c], 0));
+        const size_t nb = (size_t)(br1 - br0);
+        MTT_CUDA(ctx, cudaMemcpyAsync(nChg + br0, dNChg + br0, nb * 4, cudaMemcpyDeviceToHost, dn));
+        if (outCap > 0) {
+            MTT_CUDA(ctx, cudaMemcpyAsync(outChgTime + br0 * outCap, dOCT + br0 * outCap,
+                                          nb * outCap * 8, cudaMemcpyDeviceToHost, dn));
+            MTT_CUDA(ctx, cudaMemcpyAsync(outChgType + br0 * outCap, dOCTy + br0 * outCap,
+                                          nb * outCap, cudaMemcpyDeviceToHost, dn));
+        }
+        MTT_CUDA(ctx, cudaMemcpyAsync(logProb + br0, dLP + br0, nb * 8, cudaMemcpyDeviceToHost, dn));
+        MTT_CUDA(ctx, cudaMemcpyAsync(status + br0, dSt + br0, nb * 4, cudaMemcpyDeviceToHost, dn));
+        MTT_CUDA(ctx, cudaMemcpyAsync(nVirt + br0, dNVirt + br0, nb * 4, cudaMemcpyDeviceToHost, dn));
+        MTT_CUDA(ctx, cudaMemcpyAsync(uUsed + j0, dUsed + j0, (size_t)(j1 - j0) * 8,
+                                      cudaMemcpyDeviceToHost, dn));
+    }
+    MTT_CUDA(ctx, cudaStreamSynchronize(ctx->copyStream2));
+    MTT_CUDA(ctx, cudaStreamSynchronize(s));
+    for (int64_t i = 0; i < nBr; i++)
+        if (status[i] == MTT_ST_NEED_MORE_POWERS)
+            return RETYPE_REDO;
+    return MTT_OK;
+}
+
 int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
                           const int32_t *model, const double *tBottom, const double *tTop,
                           const uint8_t *typeBottom, const uint8_t *typeTop,
@@ -647,6 +789,20 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
     if (!(maxMuL < 1e7))
         return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "mu*L = %g is too large", maxMuL);
     int K = (int)(maxMuL + 10.0 * sqrt(maxMuL) + 32.0);
+
+    // Large batches (the throughput sweeps): the uniforms are most of the input and the change
+    // lists most of the output, so the batch is cut into chunks of jobs whose upload, kernels
+    // and download overlap on three streams.  A table that turns out too short (rare: K is a
+    // generous bound) falls through to the one-piece path below, which extends it and redoes
+    // the batch.
+    if (!old && nJobs >= 16384) {
+        const int rc = retype_chunked(ctx, nJobs, brOff, model, tBottom, tTop, typeBottom, typeTop,
+                                      nVirtForced, uniforms, uOff, outCap, nChg, outChgTime,
+                                      outChgType, logProb, status, nVirt, uUsed, K);
+        if (rc != RETYPE_REDO)
+            return rc;
+        K = 2 * K + 64;
+    }
 
     int *dModel, *dForced = nullptr, *dNChg, *dSt, *dNVirt;
     double *dT0, *dT1, *dU, *dOCT, *dLP;

@@ -36,6 +36,7 @@ struct mtt_ctx {
     std::vector<double> unifMu;         // host copy of mu per model
     // copy stream + events of the chunked host-buffer density entry (mtt_ctx.cu)
     cudaStream_t copyStream = nullptr;
+    cudaStream_t copyStream2 = nullptr;   // device -> host leg of the chunked retype call
     std::vector<cudaEvent_t> events;
     // pinned staging of small calls (Xfer below)
     void *pinIn = nullptr, *pinOut = nullptr;

@@ -206,6 +206,8 @@ int mtt_ctx_destroy(mtt_ctx *ctx)
         cudaEventDestroy(ev);
     if (ctx->copyStream)
         cudaStreamDestroy(ctx->copyStream);
+    if (ctx->copyStream2)
+        cudaStreamDestroy(ctx->copyStream2);
     if (ctx->pinIn)
         cudaFreeHost(ctx->pinIn);
     if (ctx->pinOut)

@@ -322,3 +322,44 @@ def test_migration_model_device_accessors(ctx):
     assert np.array_equal(model.getQ(True), [[-1.5, 1.5], [1.5, -1.5]])
     model.setRateMatrix([4.0, 1.0])
     assert model.getMu(False) == 4.0        # dirty -> matrices rebuilt, cached powers dropped
+
+
+def test_retype_large_batch_chunked_path_equals_one_piece_path(ctx):
+    """Batches of >= 16384 jobs go through the chunked three-stream path (upload, kernels and
+    download of eight chunks overlap): it must return exactly what the one-piece path returns for
+    the same jobs, and what the oracle returns."""
+    d = 6
+    rng = np.random.default_rng(4242)
+    m = _model(d, 5)
+    um = UniformizationModels(m, ctx=ctx)
+    o = orc.UnifModel(m)
+    nJobs, W = 20000, 64
+    brOff, t0, t1, a, b = _random_jobs(rng, nJobs, d, Lscale=1.0)
+    u = rng.random(nJobs * W)
+    uOff = np.arange(nJobs + 1) * W
+    whole = um.retype(brOff, t0, t1, a, b, u, uOff, outCap=32)
+    whole = {k: np.array(v) for k, v in whole.items()}
+    lo = 0
+    for hi in (7000, 14000, nJobs):                     # three one-piece calls
+        bs, be = brOff[lo], brOff[hi]
+        part = um.retype(brOff[lo:hi + 1] - bs, t0[bs:be], t1[bs:be], a[bs:be], b[bs:be],
+                         u[lo * W:hi * W], uOff[lo:hi + 1] - lo * W, outCap=32)
+        for k in ("status", "nVirt", "nChg", "logProb"):
+            assert np.array_equal(np.asarray(part[k]), whole[k][bs:be], equal_nan=True), (k, lo)
+        live = np.arange(32)[None, :] < np.minimum(whole["nChg"][bs:be], 32)[:, None]
+        for k in ("chgTime", "chgType"):                # (entries past nChg are not written)
+            assert np.array_equal(np.asarray(part[k])[live], whole[k][bs:be][live]), (k, lo)
+        assert np.array_equal(np.asarray(part["uUsed"]), whole["uUsed"][lo:hi])
+        lo = hi
+    for j in rng.integers(0, nJobs, 150):               # and against the oracle
+        pos = 0
+        for br in range(brOff[j], brOff[j + 1]):
+            w = o.retype_branch(t0[br], t1[br], int(a[br]), int(b[br]), u[j * W + pos:(j + 1) * W],
+                                cap=32)
+            assert whole["status"][br] == w["status"]
+            if w["status"] != ST_OK:
+                break
+            pos += w["uUsed"]
+            n = w["nChg"]
+            assert whole["nVirt"][br] == w["nVirt"] and whole["nChg"][br] == n
+            assert np.array_equal(whole["chgTime"][br, :n], w["chgTime"])

@@ -56,6 +56,7 @@ struct ParticleParams {
     double *logW;
     int *status;
     long long *uUsed;
+    long long partBase, partEnd;     // particles [partBase, partEnd) of this launch
 };
 
 __host__ __device__ __forceinline__ size_t particle_smem_doubles(int d, int eCap, int tCap,
@@ -71,8 +72,8 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
 {
     extern __shared__ double sm[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const long long q = (long long)blockIdx.x * P_WARPS + warp;      // particle
-    if (q >= p.nTrees * p.nParticles)
+    const long long q = p.partBase + (long long)blockIdx.x * P_WARPS + warp;   // particle
+    if (q >= p.partEnd)
         return;
     const int d = p.d, dd = d * d;
     __shared__ uint16_t rcAll[P_WARPS][MTT_MAX_DEMES * MTT_MAX_DEMES];
@@ -449,8 +450,22 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
                                   cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dOrder, leafOrder, hOrderOff[nTrees] * 4,
                                   cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaMemcpyAsync(dU, uniforms, nU * 8, cudaMemcpyHostToDevice, s));
+    // The uniforms are nearly all of the input.  Large calls send them in chunks of particles on
+    // a second stream, each chunk's particles starting as soon as its uniforms have landed
+    // (first attempt only: a retry with larger stages finds everything on the device).
+    const int nChunks = (nPart >= 4096) ? 8 : 1;
+    if (nChunks == 1)
+        MTT_CUDA(ctx, cudaMemcpyAsync(dU, uniforms, nU * 8, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dUOff, uOff, (nPart + 1) * 8, cudaMemcpyHostToDevice, s));
+    if (nChunks > 1) {
+        if (!ctx->copyStream)
+            MTT_CUDA(ctx, cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking));
+        while ((int)ctx->events.size() < nChunks + 1) {
+            cudaEvent_t ev;
+            MTT_CUDA(ctx, cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->events.push_back(ev);
+        }
+    }
 
     // stage capacities: start from the tree size / the expected number of virtual events and
     // grow on demand
@@ -483,8 +498,34 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         p.model = dModel; p.N = dN; p.nodeOff = dNodeOff; p.height = dHeight; p.parent = dParent;
         p.leafType = dLeafType; p.orderOff = dOrderOff; p.leafOrder = dOrder; p.uniforms = dU;
         p.uOff = dUOff; p.logW = dLogW; p.status = dStatus; p.uUsed = dUsed;
-        k4_particles<<<blocks, P_WARPS * 32, smem, s>>>(p);
-        MTT_CHECK_LAUNCH(ctx);
+        if (attempt == 0 && nChunks > 1) {
+            // (the buffers of the previous call are free: every call ends with a synchronise)
+            MTT_CUDA(ctx, cudaEventRecord(ctx->events[nChunks], s));
+            MTT_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->events[nChunks], 0));
+            const int64_t per = (nPart + nChunks - 1) / nChunks;
+            for (int c = 0; c < nChunks; c++) {
+                const int64_t q0 = std::min<int64_t>(nPart, per * c);
+                const int64_t q1 = std::min<int64_t>(nPart, per * (c + 1));
+                if (q1 <= q0)
+                    continue;
+                const int64_t u0 = uOff[q0], u1 = uOff[q1];
+                if (u1 > u0)
+                    MTT_CUDA(ctx, cudaMemcpyAsync(dU + u0, uniforms + u0, (size_t)(u1 - u0) * 8,
+                                                  cudaMemcpyHostToDevice, ctx->copyStream));
+                MTT_CUDA(ctx, cudaEventRecord(ctx->events[c], ctx->copyStream));
+                MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[c], 0));
+                p.partBase = q0;
+                p.partEnd = q1;
+                k4_particles<<<(unsigned)((q1 - q0 + P_WARPS - 1) / P_WARPS), P_WARPS * 32, smem,
+                               s>>>(p);
+                MTT_CHECK_LAUNCH(ctx);
+            }
+        } else {
+            p.partBase = 0;
+            p.partEnd = nPart;
+            k4_particles<<<blocks, P_WARPS * 32, smem, s>>>(p);
+            MTT_CHECK_LAUNCH(ctx);
+        }
         MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dStatus, nPart * 4, cudaMemcpyDeviceToHost, s));
         MTT_CUDA(ctx, cudaStreamSynchronize(s));
         bool morePow = false, moreEv = false;

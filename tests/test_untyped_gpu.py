@@ -281,3 +281,34 @@ def test_oracle_particle_matches_python_restatement(d, n):
             assert got[1] == want["uUsed"] and got[3] == want["nEvents"]
             assert list(got[2]) == list(want["nodeType"])
             assert got[0] == pytest.approx(want["logW"], rel=1e-12, abs=1e-12)
+
+
+@pytest.mark.gpu
+def test_large_call_chunked_upload_equals_small_calls(ctx):
+    """Calls with >= 4096 particles upload their uniforms in chunks on a second stream and start
+    each chunk's particles as it lands: same log weights and uniform counts as the same
+    particles evaluated tree by tree in small calls, and as the oracle on a sample."""
+    d, n = 3, 12
+    m, N = mtt.synthetic_model(d)
+    T, P, win = 20, 256, 512                       # 5120 particles
+    trees = [mtt.simulate_trees(T, n, d, m, N, seed=77).tree(b) for b in range(T)]
+    orders, u, uOff = _inputs(trees, P, win, 31)
+    um = UniformizationModels(m, ctx=ctx)
+    big = untyped_logp_batch(um, N, trees, P, np.concatenate(orders), u, uOff, ctx=ctx)
+    assert np.all(big["status"] == 0)
+    for b in range(T):                             # one tree per call: 256 particles, one piece
+        lo, hi = b * P, (b + 1) * P
+        small = untyped_logp_batch(um, N, trees[b:b + 1], P, np.concatenate(orders[lo:hi]),
+                                   u[uOff[lo]:uOff[hi]], uOff[lo:hi + 1] - uOff[lo], ctx=ctx)
+        assert np.array_equal(small["logW"][0], big["logW"][b])
+        assert np.array_equal(small["uUsed"][0], big["uUsed"][b])
+        assert small["logP"][0] == big["logP"][b]
+    o = orc.UnifModel(m)
+    rng = np.random.default_rng(3)
+    for q in rng.integers(0, T * P, 40):
+        b, p = divmod(int(q), P)
+        t = trees[b]
+        ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[q],
+                                  u[uOff[q]:uOff[q + 1]])
+        assert ro["status"] == 0 and ro["uUsed"] == big["uUsed"][b, p]
+        assert big["logW"][b, p] == pytest.approx(ro["logW"], rel=1e-9, abs=1e-9)

@@ -721,6 +721,7 @@ public:
             size_t chain;
             size_t start = 0;
             int window;
+            int cap = 32;                // changes returned per branch (grown when exceeded)
             int32_t forced[3] = {-1, -1, -1};
             bool failed = false;
         };
@@ -738,6 +739,10 @@ public:
                 need += 2.0 * (muL + 6.0 * std::sqrt(muL) + 8.0) + 1.0;
             }
             j.window = std::max(window_, ((int)need + 31) / 32 * 32);
+            // a branch has at most (window - 1) / 2 virtual events, hence changes: half the
+            // window is always enough room for the changes returned (and keeps the call's
+            // outputs small enough for the staged, two-copy transfer)
+            j.cap = std::max(32, j.window / 2);
             pending.push_back(j);
         }
         std::vector<char> noPath(C, 0);
@@ -758,7 +763,7 @@ public:
                 us.resize(us.size() + j.window);
                 chains_[j.chain].rng->peekDoubles(j.window, us.data() + us.size() - j.window);
                 uOff.push_back((int64_t)us.size());
-                outCap = std::max(outCap, j.window);
+                outCap = std::max(outCap, j.cap);
             }
             const size_t nBr = B_.t0.size();
             std::vector<int32_t> nChg(nBr), status(nBr), nVirt(nBr);
@@ -799,6 +804,15 @@ public:
                 if (more) {                              // nothing consumed: a longer window
                     resubmits[MTT_ST_NEED_MORE_UNIFORMS]++;
                     j.window *= 4;
+                    j.cap = std::max(j.cap, j.window / 2);
+                    next.push_back(j);
+                    continue;
+                }
+                bool overflow = false;                   // more changes than were returned
+                for (size_t x = lo; x < hi; x++)
+                    overflow |= status[x] == MTT_ST_OK && nChg[x] > outCap;
+                if (overflow) {                          // nothing consumed either: same draws
+                    j.cap = 4 * outCap;
                     next.push_back(j);
                     continue;
                 }

@@ -384,6 +384,77 @@ static int sc_logp_host(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t
 
     cudaStream_t s = ctx->stream;
     const size_t md = (size_t)nModels * d * d * 8, nd = (size_t)nModels * d * 8;
+    {
+        // Small calls -- one tree of a BEAST chain, the few dozen trees of an ensemble step --
+        // are latency: every input goes through one page-locked staging buffer and one copy,
+        // the results come back in another (Xfer), instead of a dozen copies from pageable
+        // memory.
+        const size_t small = md + nd + (size_t)(B + 1) * 16 +
+                             (size_t)nodes * (8 + 1 + (owners ? 0 : 2) + (parent ? 4 : 0)) +
+                             (size_t)changes * (8 + 1 + 2) + (size_t)B * 9;
+        if (small + 16 * 256 <= ((size_t)1 << 20)) {
+            Xfer x(ctx);
+            double *dM, *dN, *dH, *dCT = nullptr, *dLogP;
+            long long *dNodeOff, *dChgBase;
+            uint8_t *dT, *dCTy = nullptr, *dValid = nullptr;
+            uint16_t *dK = nullptr, *dO = nullptr;
+            int32_t *dP = nullptr;
+            x.in(m, md / 8, BUF_D_MODEL, &dM);
+            x.in(N, nd / 8, BUF_D_N, &dN);
+            x.in((const long long *)nodeOff, (size_t)B + 1, BUF_D_NODEOFF, &dNodeOff);
+            x.in((const long long *)chgBase, (size_t)B + 1, BUF_D_CHGBASE, &dChgBase);
+            x.in(height, (size_t)nodes, BUF_D_HEIGHT, &dH);
+            x.in(nodeType, (size_t)nodes, BUF_D_NODETYPE, &dT);
+            if (!owners)
+                x.in(chgCountOrNode, (size_t)nodes, BUF_D_CHGCOUNT, &dK);
+            else if (changes > 0)
+                x.in(chgCountOrNode, (size_t)changes, BUF_D_CHGNODE, &dO);
+            if (changes > 0) {
+                x.in(chgTime, (size_t)changes, BUF_D_CHGTIME, &dCT);
+                x.in(chgType, (size_t)changes, BUF_D_CHGTYPE, &dCTy);
+            }
+            if (parent)
+                x.in(parent, (size_t)nodes, BUF_D_PARENT, &dP);
+            x.out(logP, (size_t)B, BUF_D_LOGP, &dLogP);
+            if (valid && parent)
+                x.out(valid, (size_t)B, BUF_D_VALID, &dValid);
+            int rc = x.prepare();
+            if (rc == MTT_OK && x.staged()) {
+                // (arrays that a tree set without changes never reads still need an address,
+                // and the expanded owner list a place)
+                if (!owners)
+                    dO = (uint16_t *)mtt_buf(ctx, BUF_D_CHGNODE, (size_t)changes * 2);
+                if (!dO)
+                    dO = (uint16_t *)mtt_buf(ctx, BUF_D_CHGNODE, 16);
+                if (!dCT)
+                    dCT = (double *)mtt_buf(ctx, BUF_D_CHGTIME, 16);
+                if (!dCTy)
+                    dCTy = (uint8_t *)mtt_buf(ctx, BUF_D_CHGTYPE, 16);
+                if (!dO || !dCT || !dCTy)
+                    return MTT_ERR_CUDA;
+                if ((rc = x.upload()) != MTT_OK)
+                    return rc;
+                if (!owners)
+                    rc = mtt_k1_expand_counts(ctx, B, (const int64_t *)dNodeOff, dK,
+                                              (const int64_t *)dChgBase, dO);
+                if (rc != MTT_OK)
+                    return rc;
+                rc = mtt_k1_launch(ctx, B, d, nModels > 1 ? B : 1, dM, dN,
+                                   (const int64_t *)dNodeOff, dH, dP, dT, dO,
+                                   (const int64_t *)dChgBase, dCT, dCTy, checkValidity, dLogP,
+                                   dValid, maxEv > 0 ? maxEv : 1);
+                if (rc != MTT_OK)
+                    return rc;
+                if ((rc = x.download()) != MTT_OK)
+                    return rc;
+                if (valid && !parent)
+                    memset(valid, 1, (size_t)B);
+                return MTT_OK;
+            }
+            if (rc != MTT_OK)
+                return rc;
+        }
+    }
     double *dM = (double *)mtt_buf(ctx, BUF_D_MODEL, md);
     double *dN = (double *)mtt_buf(ctx, BUF_D_N, nd);
     int64_t *dNodeOff = (int64_t *)mtt_buf(ctx, BUF_D_NODEOFF, (B + 1) * 8);

@@ -257,6 +257,29 @@ int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles, const i
                            const int64_t *uOff, double *logP, double *logW, int32_t *status,
                            int64_t *uUsed);
 
+/* The typings themselves: every particle of mtt_untyped_logp_batch returned as a typed tree.
+ * Replaces evolution/tree/MultiTypeTreeFromUntypedNewick.java:104-134 (the lineage-by-lineage
+ * colouring of an untyped tree: colourFirstLineage :150-199, colourLineage :202-212,
+ * addTypeChanges :272-357 -- the same sampler as the density's), batched over trees x
+ * particles; inputs as above.  Outputs per particle q = t * nParticles + p:
+ *   nodeType[nodeOff[t] * nParticles + p * n .. + n)  the type of every node (255 = not reached:
+ *       status != MTT_ST_OK);
+ *   nChg[q] type changes, the first min(nChg[q], chgCap) of them in chgTime / chgType /
+ *       chgNode[q * chgCap ..): chgNode = the node BELOW the change (MultiTypeNode.addChange),
+ *       chgType = the type entered going rootward; the changes of one node appear in increasing
+ *       time.  nChg[q] > chgCap: resubmit with more room.
+ *   logW (optional): the particle's importance weight, as in mtt_untyped_logp_batch.
+ * status: MTT_ST_OK, MTT_ST_NEED_MORE_UNIFORMS, or the status of the lineage that has no valid
+ * path (MTT_ST_NO_VALID_PATH / _PBA_RUBBISH / _FB_FELL_THROUGH): the reference starts the whole
+ * colouring over with a new leaf order (:128-131). */
+int mtt_untyped_sample_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles, const int32_t *model,
+                             const double *N, const int64_t *nodeOff, const double *height,
+                             const int32_t *parent, const uint8_t *leafType,
+                             const int32_t *leafOrder, const double *uniforms,
+                             const int64_t *uOff, int chgCap, uint8_t *nodeType, int32_t *nChg,
+                             double *chgTime, uint8_t *chgType, int32_t *chgNode, double *logW,
+                             int32_t *status, int64_t *uUsed);
+
 /* ------------------------------------------------------------------ piece 2: peeling
  * Replaces BEAST 2 core beast.base.evolution.likelihood.TreeLikelihood.calculateLogP +
  * BeerLikelihoodCore as wired by the reference at examples/structuredCoalescent.xml:568-572

@@ -16,6 +16,9 @@ from .operators import (MultiTypeTreeScale, MultiTypeUniform, NodeRetype,  # noq
                         NodeShiftRetype, TypedSubtreeExchange, TypedWilsonBalding,
                         run_proposals)
 from .mcmc import MCMC, Chain, MCMCEnsemble  # noqa: F401
+from .untyped import (MultiTypeTreeFromUntypedNewick, StructuredCoalescentUntypedTree,  # noqa: F401
+                      StructuredCoalescentUntypedTreeDensity, colour_untyped_trees,
+                      untyped_sample_batch)
 
 __all__ = [
     "Context", "MttError", "default_context", "lib", "DeviceTreeBatch", "MultiTypeTree",
@@ -24,4 +27,6 @@ __all__ = [
     "sc_logp_batch", "sc_logp_tips_batch", "set_tips", "tree_validity", "Randomizer", "UniformizationModels", "NodeRetype",
     "NodeShiftRetype", "TypedSubtreeExchange", "TypedWilsonBalding", "MultiTypeTreeScale",
     "MultiTypeUniform", "run_proposals", "MCMC", "Chain", "MCMCEnsemble",
+    "MultiTypeTreeFromUntypedNewick", "StructuredCoalescentUntypedTree",
+    "StructuredCoalescentUntypedTreeDensity", "colour_untyped_trees", "untyped_sample_batch",
 ]

@@ -53,6 +53,8 @@ ABI = {
                                              VP]),
     "mtt_untyped_logp_batch": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP,
                                         VP, VP, VP, VP, VP]),
+    "mtt_untyped_sample_batch": (C.c_int, [VP, C.c_int64, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP,
+                                          VP, C.c_int, VP, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_unif_retype_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP,
                                         C.c_int, VP, VP, VP, VP, VP, VP, VP]),
     "mtt_unif_node_retype_batch": (C.c_int, [VP, C.c_int64, VP, VP, VP, VP, VP, VP, VP, VP, VP, VP,

@@ -57,6 +57,13 @@ struct ParticleParams {
     int *status;
     long long *uUsed;
     long long partBase, partEnd;     // particles [partBase, partEnd) of this launch
+    // typed trees of the particles (k4_particles<true>: mtt_untyped_sample_batch)
+    uint8_t *outNodeType;            // particle (t, p): nodeOff[t] * nParticles + p * n
+    int chgCap;                      // room per particle in the three change arrays
+    int *outNChg;
+    double *outChgTime;
+    uint8_t *outChgType;
+    int *outChgNode;
 };
 
 __host__ __device__ __forceinline__ size_t particle_smem_doubles(int d, int eCap, int tCap,
@@ -68,6 +75,10 @@ __host__ __device__ __forceinline__ size_t particle_smem_doubles(int d, int eCap
            32 * dPad / 2 /* per-lane counts, int */ + 2 * dPad /* N, muOut */;
 }
 
+// TREE: also return the typing itself -- the type of every node and the type changes with the
+// node below each (MultiTypeNode.addChange on that node); a lineage without a valid path ends the
+// particle with that lineage's status (MultiTypeTreeFromUntypedNewick.java:118-133 starts over).
+template <bool TREE>
 __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParams p)
 {
     extern __shared__ double sm[];
@@ -133,6 +144,18 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
         }
         nEv++;
     };
+    int nChg = 0;
+    auto record = [&](int node, int newType, double time) {      // node.addChange(newType, time)
+        if (TREE) {
+            if (lane == 0 && nChg < p.chgCap) {
+                const long long at = q * p.chgCap + nChg;
+                p.outChgTime[at] = time;
+                p.outChgType[at] = (uint8_t)newType;
+                p.outChgNode[at] = node;
+            }
+            nChg++;
+        }
+    };
 
     for (int li = 0; li < nLeaves && st == MTT_ST_OK; li++) {
         const int leaf = order[li];
@@ -141,6 +164,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
             double time = height[leaf];
             int type = nodeType[leaf];
             int next = parent[leaf];
+            int thisNode = leaf;
             emit(PK_SAMPLE, type, 0, time);
             double thisLogP = 0.0;
             for (;;) {
@@ -162,6 +186,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
                     emit(PK_COALESCE, type, 0, hn);
                     thisLogP = add_rn(thisLogP, mul_rn(-aTot, sub_rn(hn, time)));
                     time = hn;
+                    thisNode = next;
                     next = parent[next];
                 }
                 if (next < 0)
@@ -184,6 +209,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
                 if (newType >= d)
                     newType = (type == d - 1) ? d - 2 : d - 1;
                 emit(PK_MIGRATE, type, newType, time);
+                record(thisNode, newType, time);
                 thisLogP = add_rn(thisLogP, lQ[type * d + newType]);
                 type = newType;
             }
@@ -207,6 +233,10 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
             st = bs.st;
             break;
         }
+        if (TREE && bs.st != MTT_ST_OK) {
+            st = bs.st;
+            break;
+        }
         if (bs.st != MTT_ST_OK) {
             // NoValidPath / rubbish / forward-backward failure: the Java returns -Infinity and
             // the weight takes "-= -Infinity" (:136, :311-313, :399-403, :438-441)
@@ -214,7 +244,7 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
             continue;
         }
         double lp = 0.0;
-        int prevType = a, prevNode = leaf;
+        int prevType = a, prevNode = leaf, below = leaf;
         double prevTime = t0;
         for (int i = 0; i < bs.nVirt; i++) {                                     // :452-486
             const int ty = bs.types[i];
@@ -227,8 +257,10 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
                             nodeType[prevNode] = (int8_t)prevType;
                         emit(PK_COALESCE, prevType, 0, height[prevNode]);
                     }
+                    below = prevNode;
                     prevNode = parent[prevNode];
                 }
+                record(below, ty, ti);
                 lp = add_rn(lp, add_rn(mul_rn(Q[prevType * d + prevType], sub_rn(ti, prevTime)),
                                        lQ[prevType * d + ty]));
                 prevType = ty;
@@ -334,6 +366,14 @@ __global__ void __launch_bounds__(P_WARPS * 32) k4_particles(const ParticleParam
         p.status[q] = st;
         p.uUsed[q] = pos;
     }
+    if (TREE) {
+        __syncwarp();
+        uint8_t *o = p.outNodeType + n0 * p.nParticles + (long long)part * n;
+        for (int i = lane; i < n; i += 32)
+            o[i] = (uint8_t)nodeType[i];           // 255 = not reached (status != MTT_ST_OK)
+        if (lane == 0)
+            p.outNChg[q] = nChg;
+    }
 }
 
 // logP = log(sum_p exp(w_p - max) / P) + max  (:193-201); Math.max propagates NaN
@@ -364,13 +404,24 @@ __global__ void k4_combine(long long nTrees, int nParticles, const double *logW,
 
 }  // namespace
 
-extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles,
-                                      const int32_t *model, const double *N,
-                                      const int64_t *nodeOff, const double *height,
-                                      const int32_t *parent, const uint8_t *leafType,
-                                      const int32_t *leafOrder, const double *uniforms,
-                                      const int64_t *uOff, double *logP, double *logW,
-                                      int32_t *status, int64_t *uUsed)
+namespace {
+// Both entries: the density estimate (tr == nullptr) and the typed trees themselves.
+struct TreeOut {
+    int chgCap;
+    uint8_t *nodeType;
+    int32_t *nChg;
+    double *chgTime;
+    uint8_t *chgType;
+    int32_t *chgNode;
+};
+}  // namespace
+
+static int untyped_run(mtt_ctx *ctx, int64_t nTrees, int nParticles, const int32_t *model,
+                       const double *N, const int64_t *nodeOff, const double *height,
+                       const int32_t *parent, const uint8_t *leafType,
+                       const int32_t *leafOrder, const double *uniforms, const int64_t *uOff,
+                       double *logP, double *logW, int32_t *status, int64_t *uUsed,
+                       const TreeOut *tr)
 {
     if (!ctx)
         return MTT_ERR_INVALID_ARG;
@@ -380,8 +431,11 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         return mtt_fail(ctx, MTT_ERR_STATE,
                         "the untyped density uses the unsymmetrised model (sym = 0)");
     if (nTrees < 0 || nParticles < 1 || !N || !nodeOff || !height || !parent || !leafType ||
-        !leafOrder || !uniforms || !uOff || !logP)
+        !leafOrder || !uniforms || !uOff || (!logP && !tr))
         return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_untyped_logp_batch: bad argument");
+    if (tr && (tr->chgCap < 0 || !tr->nodeType || !tr->nChg ||
+               (tr->chgCap > 0 && (!tr->chgTime || !tr->chgType || !tr->chgNode))))
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_untyped_sample_batch: bad argument");
     if (nTrees == 0)
         return MTT_OK;
     MTT_CUDA(ctx, cudaSetDevice(ctx->device));
@@ -437,6 +491,19 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
     int *dStatus = (int *)mtt_buf(ctx, BUF_P_STATUS, nPart * 4);
     long long *dUsed = (long long *)mtt_buf(ctx, BUF_P_USED, nPart * 8);
     double *dLogP = (double *)mtt_buf(ctx, BUF_P_LOGP, nTrees * 8);
+    uint8_t *dOutType = nullptr, *dChgType = nullptr;
+    int *dNChg = nullptr, *dChgNode = nullptr;
+    double *dChgTime = nullptr;
+    const size_t nChgRoom = tr ? (size_t)nPart * tr->chgCap : 0;
+    if (tr) {
+        dOutType = (uint8_t *)mtt_buf(ctx, BUF_P_OUTTYPE, (size_t)nNodes * nParticles);
+        dNChg = (int *)mtt_buf(ctx, BUF_P_NCHG, nPart * 4);
+        dChgTime = (double *)mtt_buf(ctx, BUF_P_CHGTIME, nChgRoom * 8 + 8);
+        dChgType = (uint8_t *)mtt_buf(ctx, BUF_P_CHGTYPE, nChgRoom + 8);
+        dChgNode = (int *)mtt_buf(ctx, BUF_P_CHGNODE, nChgRoom * 4 + 8);
+        if (!dOutType || !dNChg || !dChgTime || !dChgType || !dChgNode)
+            return MTT_ERR_CUDA;
+    }
     if (!dModel || !dN || !dNodeOff || !dHeight || !dParent || !dLeafType || !dOrderOff ||
         !dOrder || !dU || !dUOff || !dLogW || !dStatus || !dUsed || !dLogP)
         return MTT_ERR_CUDA;
@@ -483,8 +550,9 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         if (rc != MTT_OK)
             return rc;
         const size_t smem = (size_t)P_WARPS * particle_smem_doubles(d, eCap, tCap, nCap) * 8;
-        MTT_CUDA(ctx, cudaFuncSetAttribute(k4_particles,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        void (*kernel)(const ParticleParams) = tr ? k4_particles<true> : k4_particles<false>;
+        MTT_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)smem));
         ParticleParams p;
         p.nTrees = nTrees; p.nParticles = nParticles; p.d = d; p.powCap = ctx->unifPowCap;
         p.eCap = eCap; p.tCap = tCap; p.nCap = nCap;
@@ -498,6 +566,8 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
         p.model = dModel; p.N = dN; p.nodeOff = dNodeOff; p.height = dHeight; p.parent = dParent;
         p.leafType = dLeafType; p.orderOff = dOrderOff; p.leafOrder = dOrder; p.uniforms = dU;
         p.uOff = dUOff; p.logW = dLogW; p.status = dStatus; p.uUsed = dUsed;
+        p.outNodeType = dOutType; p.chgCap = tr ? tr->chgCap : 0; p.outNChg = dNChg;
+        p.outChgTime = dChgTime; p.outChgType = dChgType; p.outChgNode = dChgNode;
         if (attempt == 0 && nChunks > 1) {
             // (the buffers of the previous call are free: every call ends with a synchronise)
             MTT_CUDA(ctx, cudaEventRecord(ctx->events[nChunks], s));
@@ -516,14 +586,13 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
                 MTT_CUDA(ctx, cudaStreamWaitEvent(s, ctx->events[c], 0));
                 p.partBase = q0;
                 p.partEnd = q1;
-                k4_particles<<<(unsigned)((q1 - q0 + P_WARPS - 1) / P_WARPS), P_WARPS * 32, smem,
-                               s>>>(p);
+                kernel<<<(unsigned)((q1 - q0 + P_WARPS - 1) / P_WARPS), P_WARPS * 32, smem, s>>>(p);
                 MTT_CHECK_LAUNCH(ctx);
             }
         } else {
             p.partBase = 0;
             p.partEnd = nPart;
-            k4_particles<<<blocks, P_WARPS * 32, smem, s>>>(p);
+            kernel<<<blocks, P_WARPS * 32, smem, s>>>(p);
             MTT_CHECK_LAUNCH(ctx);
         }
         MTT_CUDA(ctx, cudaMemcpyAsync(hSt.data(), dStatus, nPart * 4, cudaMemcpyDeviceToHost, s));
@@ -550,9 +619,24 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
                 tCap <<= 1;
         }
     }
-    k4_combine<<<(unsigned)((nTrees + 3) / 4), 128, 0, s>>>(nTrees, nParticles, dLogW, dLogP);
-    MTT_CHECK_LAUNCH(ctx);
-    MTT_CUDA(ctx, cudaMemcpyAsync(logP, dLogP, nTrees * 8, cudaMemcpyDeviceToHost, s));
+    if (logP) {
+        k4_combine<<<(unsigned)((nTrees + 3) / 4), 128, 0, s>>>(nTrees, nParticles, dLogW, dLogP);
+        MTT_CHECK_LAUNCH(ctx);
+        MTT_CUDA(ctx, cudaMemcpyAsync(logP, dLogP, nTrees * 8, cudaMemcpyDeviceToHost, s));
+    }
+    if (tr) {
+        MTT_CUDA(ctx, cudaMemcpyAsync(tr->nodeType, dOutType, (size_t)nNodes * nParticles,
+                                      cudaMemcpyDeviceToHost, s));
+        MTT_CUDA(ctx, cudaMemcpyAsync(tr->nChg, dNChg, nPart * 4, cudaMemcpyDeviceToHost, s));
+        if (nChgRoom) {
+            MTT_CUDA(ctx, cudaMemcpyAsync(tr->chgTime, dChgTime, nChgRoom * 8,
+                                          cudaMemcpyDeviceToHost, s));
+            MTT_CUDA(ctx, cudaMemcpyAsync(tr->chgType, dChgType, nChgRoom,
+                                          cudaMemcpyDeviceToHost, s));
+            MTT_CUDA(ctx, cudaMemcpyAsync(tr->chgNode, dChgNode, nChgRoom * 4,
+                                          cudaMemcpyDeviceToHost, s));
+        }
+    }
     if (logW)
         MTT_CUDA(ctx, cudaMemcpyAsync(logW, dLogW, nPart * 8, cudaMemcpyDeviceToHost, s));
     if (uUsed)
@@ -561,4 +645,33 @@ extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticl
     if (status)
         memcpy(status, hSt.data(), nPart * 4);
     return MTT_OK;
+}
+
+extern "C" int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles,
+                                      const int32_t *model, const double *N,
+                                      const int64_t *nodeOff, const double *height,
+                                      const int32_t *parent, const uint8_t *leafType,
+                                      const int32_t *leafOrder, const double *uniforms,
+                                      const int64_t *uOff, double *logP, double *logW,
+                                      int32_t *status, int64_t *uUsed)
+{
+    if (ctx && !logP)
+        return mtt_fail(ctx, MTT_ERR_INVALID_ARG, "mtt_untyped_logp_batch: logP is NULL");
+    return untyped_run(ctx, nTrees, nParticles, model, N, nodeOff, height, parent, leafType,
+                       leafOrder, uniforms, uOff, logP, logW, status, uUsed, nullptr);
+}
+
+extern "C" int mtt_untyped_sample_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles,
+                                        const int32_t *model, const double *N,
+                                        const int64_t *nodeOff, const double *height,
+                                        const int32_t *parent, const uint8_t *leafType,
+                                        const int32_t *leafOrder, const double *uniforms,
+                                        const int64_t *uOff, int chgCap, uint8_t *nodeType,
+                                        int32_t *nChg, double *chgTime, uint8_t *chgType,
+                                        int32_t *chgNode, double *logW, int32_t *status,
+                                        int64_t *uUsed)
+{
+    const TreeOut tr = {chgCap, nodeType, nChg, chgTime, chgType, chgNode};
+    return untyped_run(ctx, nTrees, nParticles, model, N, nodeOff, height, parent, leafType,
+                       leafOrder, uniforms, uOff, nullptr, logW, status, uUsed, &tr);
 }

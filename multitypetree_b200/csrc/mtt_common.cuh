@@ -54,7 +54,7 @@ enum BufId {
     BUF_U_LOUT0, BUF_U_LOUT1,
     BUF_P_MODEL, BUF_P_N, BUF_P_NODEOFF, BUF_P_HEIGHT, BUF_P_PARENT, BUF_P_LEAFTYPE,
     BUF_P_ORDEROFF, BUF_P_ORDER, BUF_P_U, BUF_P_UOFF, BUF_P_LOGW, BUF_P_STATUS, BUF_P_USED,
-    BUF_P_LOGP,
+    BUF_P_LOGP, BUF_P_OUTTYPE, BUF_P_NCHG, BUF_P_CHGTIME, BUF_P_CHGTYPE, BUF_P_CHGNODE,
     BUF_C_OPS, BUF_C_OPOFF, BUF_C_ORDER, BUF_C_KAPPA, BUF_C_LOGL,
     BUF_STAGE_IN, BUF_STAGE_OUT,
     BUF_COUNT

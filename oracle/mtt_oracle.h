@@ -158,6 +158,14 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
                          const int32_t *parent, const double *height, const uint8_t *leafType,
                          const int32_t *leafOrder, const double *u, int64_t nU, double *logW,
                          int64_t *uUsed, int32_t *nodeTypeOut, int32_t *nEventsOut);
+/* the same particle returned as a typed tree (evolution/tree/MultiTypeTreeFromUntypedNewick.java
+ * :104-134, :150-357): node types and the changes in the order they are added */
+int orc_untyped_particle_tree(const orc_unif_model *um, const double *N, int nNodes,
+                              const int32_t *parent, const double *height,
+                              const uint8_t *leafType, const int32_t *leafOrder, const double *u,
+                              int64_t nU, double *logW, int64_t *uUsed, int32_t *nodeTypeOut,
+                              int chgCap, int32_t *nChgOut, int32_t *chgNodeOut,
+                              int32_t *chgTypeOut, double *chgTimeOut);
 double orc_untyped_combine(const double *logW, int nParticles);
 
 /* ---------------------------------------------------------------- piece 2: peeling */

@@ -78,6 +78,9 @@ def lib():
         L.orc_untyped_particle.restype = C.c_int
         L.orc_untyped_particle.argtypes = [VP, VP, C.c_int, VP, VP, VP, VP, VP, C.c_int64, VP,
                                            VP, VP, VP]
+        L.orc_untyped_particle_tree.restype = C.c_int
+        L.orc_untyped_particle_tree.argtypes = [VP, VP, C.c_int, VP, VP, VP, VP, VP, C.c_int64,
+                                                VP, VP, VP, C.c_int, VP, VP, VP, VP]
         L.orc_untyped_combine.restype = C.c_double
         L.orc_untyped_combine.argtypes = [VP, C.c_int]
         L.orc_poisson_window.restype = C.c_int
@@ -220,6 +223,34 @@ def untyped_particle(um: "UnifModel", N, parent, height, leafType, leafOrder, u)
                                 _p(leafOrder), _p(u), len(u), C.byref(logW), C.byref(used),
                                 _p(nodeType), C.byref(nEv))
     return dict(status=st, logW=logW.value, uUsed=used.value, nodeType=nodeType, nEvents=nEv.value)
+
+
+def untyped_particle_tree(um: "UnifModel", N, parent, height, leafType, leafOrder, u, chgCap=4096):
+    """The same particle returned as a typed tree (MultiTypeTreeFromUntypedNewick.java:104-134):
+    dict(status, logW, uUsed, nodeType, nChg, chgNode, chgType, chgTime) -- changes in the order
+    they are added."""
+    L = lib()
+    N = _c(N, np.float64)
+    parent = _c(parent, np.int32)
+    height = _c(height, np.float64)
+    leafType = _c(leafType, np.uint8)
+    leafOrder = _c(leafOrder, np.int32)
+    u = _c(u, np.float64)
+    n = len(parent)
+    logW = C.c_double()
+    used = C.c_int64()
+    nChg = C.c_int32()
+    nodeType = np.zeros(n, np.int32)
+    chgNode = np.zeros(chgCap, np.int32)
+    chgType = np.zeros(chgCap, np.int32)
+    chgTime = np.zeros(chgCap, np.float64)
+    st = L.orc_untyped_particle_tree(C.byref(um._s), _p(N), n, _p(parent), _p(height),
+                                     _p(leafType), _p(leafOrder), _p(u), len(u), C.byref(logW),
+                                     C.byref(used), _p(nodeType), chgCap, C.byref(nChg),
+                                     _p(chgNode), _p(chgType), _p(chgTime))
+    k = min(nChg.value, chgCap)
+    return dict(status=st, logW=logW.value, uUsed=used.value, nodeType=nodeType, nChg=nChg.value,
+                chgNode=chgNode[:k], chgType=chgType[:k], chgTime=chgTime[:k])
 
 
 def untyped_combine(logW):

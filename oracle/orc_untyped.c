@@ -96,10 +96,16 @@ static void push(ev_list *L, int kind, int type, int dest, double time)
 /* One particle.  Returns ORC_ST_OK or ORC_ST_NEED_MORE_UNIFORMS.  *logW is the particle's log
  * weight (:145-186 minus the proposal log-probabilities :134-137); may be +-inf / NaN exactly
  * where the Java arithmetic produces them. */
-int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
+/* The typing is also returned when chgNodeOut != NULL: the changes in the order they are
+ * added (node below the change, type entered, time), *nChgOut of them (at most chgCap stored) --
+ * the typed tree MultiTypeTreeFromUntypedNewick.java:104-134 builds with the same colouring; a
+ * lineage without a valid path then ends the particle with that lineage's status (:128-131). */
+static int particle_impl(const orc_unif_model *um, const double *N, int nNodes,
                          const int32_t *parent, const double *height, const uint8_t *leafType,
                          const int32_t *leafOrder, const double *u, int64_t nU, double *logW,
-                         int64_t *uUsed, int32_t *nodeTypeOut, int32_t *nEventsOut)
+                         int64_t *uUsed, int32_t *nodeTypeOut, int32_t *nEventsOut, int chgCap,
+                         int32_t *nChgOut, int32_t *chgNodeOut, int32_t *chgTypeOut,
+                         double *chgTimeOut)
 {
     const int d = um->d;
     const int nLeaves = (nNodes + 1) / 2;
@@ -110,6 +116,7 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
     int64_t pos = 0;
     double w = 0.0;
     int rc = ORC_ST_OK;
+    int nAdded = 0;
     const int cap = 4096;
     double *ct = malloc(sizeof(double) * cap);
     int32_t *cty = malloc(sizeof(int32_t) * cap);
@@ -121,6 +128,7 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
             double time = height[leaf];
             int type = nodeType[leaf];
             int next = parent[leaf];
+            int thisNode = leaf;
             push(&L, UK_SAMPLE, type, 0, height[leaf]);
             double thisLogP = 0.0;
             for (;;) {
@@ -138,6 +146,7 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
                     push(&L, UK_COALESCE, type, 0, height[next]);
                     thisLogP += -aTot * (height[next] - time);
                     time = height[next];
+                    thisNode = next;
                     next = parent[next];
                 }
                 if (next < 0)
@@ -160,6 +169,14 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
                 if (newType >= d)       /* rounding fell through: Java would throw; take the last */
                     newType = (type == d - 1) ? d - 2 : d - 1;
                 push(&L, UK_MIGRATE, type, newType, time);
+                if (chgNodeOut) {                                 /* thisNode.addChange */
+                    if (nAdded < chgCap) {
+                        chgNodeOut[nAdded] = thisNode;
+                        chgTypeOut[nAdded] = newType;
+                        chgTimeOut[nAdded] = time;
+                    }
+                    nAdded++;
+                }
                 thisLogP += log(um->Q[type * d + newType]);
                 type = newType;
             }
@@ -193,13 +210,17 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
                 break;
             }
             pos += used;
+            if (st != ORC_ST_OK && chgNodeOut) {
+                rc = st;
+                break;
+            }
             if (st != ORC_ST_OK) {
                 /* NoValidPath / rubbish / FB failure: colourLineage or addTypeChanges returns
                  * -Infinity (:311-313, :399-403, :438-441) and the weight takes "-= -inf" */
                 w -= -INFINITY;
                 continue;
             }
-            int prevType = a, prevNode = leaf;
+            int prevType = a, prevNode = leaf, below = leaf;
             for (int i = 0; i < nChg && i < cap; i++) {           /* :452-486 */
                 push(&L, UK_MIGRATE, prevType, cty[i], ct[i]);
                 while (height[prevNode] < ct[i]) {
@@ -207,7 +228,16 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
                         nodeType[prevNode] = prevType;
                         push(&L, UK_COALESCE, prevType, 0, height[prevNode]);
                     }
+                    below = prevNode;
                     prevNode = parent[prevNode];
+                }
+                if (chgNodeOut) {                                 /* prevNode.addChange */
+                    if (nAdded < chgCap) {
+                        chgNodeOut[nAdded] = below;
+                        chgTypeOut[nAdded] = cty[i];
+                        chgTimeOut[nAdded] = ct[i];
+                    }
+                    nAdded++;
                 }
                 prevType = cty[i];
             }
@@ -265,8 +295,30 @@ int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
             nodeTypeOut[i] = nodeType[i];
     if (nEventsOut)
         *nEventsOut = L.n;
+    if (nChgOut)
+        *nChgOut = nAdded;
     free(nodeType); free(L.ev); free(ct); free(cty);
     return rc;
+}
+
+int orc_untyped_particle(const orc_unif_model *um, const double *N, int nNodes,
+                         const int32_t *parent, const double *height, const uint8_t *leafType,
+                         const int32_t *leafOrder, const double *u, int64_t nU, double *logW,
+                         int64_t *uUsed, int32_t *nodeTypeOut, int32_t *nEventsOut)
+{
+    return particle_impl(um, N, nNodes, parent, height, leafType, leafOrder, u, nU, logW, uUsed,
+                         nodeTypeOut, nEventsOut, 0, NULL, NULL, NULL, NULL);
+}
+
+int orc_untyped_particle_tree(const orc_unif_model *um, const double *N, int nNodes,
+                              const int32_t *parent, const double *height,
+                              const uint8_t *leafType, const int32_t *leafOrder, const double *u,
+                              int64_t nU, double *logW, int64_t *uUsed, int32_t *nodeTypeOut,
+                              int chgCap, int32_t *nChgOut, int32_t *chgNodeOut,
+                              int32_t *chgTypeOut, double *chgTimeOut)
+{
+    return particle_impl(um, N, nNodes, parent, height, leafType, leafOrder, u, nU, logW, uUsed,
+                         nodeTypeOut, NULL, chgCap, nChgOut, chgNodeOut, chgTypeOut, chgTimeOut);
 }
 
 /* logP = log(sum_p exp(w_p - max) / P) + max   (:193-201) */

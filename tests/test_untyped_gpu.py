@@ -312,3 +312,150 @@ def test_large_call_chunked_upload_equals_small_calls(ctx):
                                   u[uOff[q]:uOff[q + 1]])
         assert ro["status"] == 0 and ro["uUsed"] == big["uUsed"][b, p]
         assert big["logW"][b, p] == pytest.approx(ro["logW"], rel=1e-9, abs=1e-9)
+
+
+# ------------------------------------------------------------------ the typings themselves
+def _check_typed_tree(t, d):
+    """MultiTypeTree.isValid (evolution/tree/MultiTypeTree.java:396-429) in plain Python: every
+    node typed, change times inside the branch and increasing, no change into the type it
+    leaves, the type at the top of every branch = the parent's type."""
+    n = t.getNodeCount()
+    for v in range(n):
+        assert 0 <= t.nodeType[v] < d
+        p = int(t.parent[v])
+        if p < 0:
+            assert t.getChangeCount(v) == 0
+            continue
+        prev_t, prev_ty = t.height[v], int(t.nodeType[v])
+        for k in range(t.getChangeCount(v)):
+            ct, cy = t.getChangeTime(v, k), t.getChangeType(v, k)
+            assert prev_t <= ct <= t.height[p]
+            assert cy != prev_ty and 0 <= cy < d
+            prev_t, prev_ty = ct, cy
+        assert prev_ty == int(t.nodeType[p]), v
+
+
+def test_oracle_typed_tree_is_a_valid_typing_of_the_untyped_tree():
+    from multitypetree_b200.untyped import typed_tree_from_sample
+    for d, n in ((2, 20), (4, 35), (7, 12)):
+        m, N = mtt.synthetic_model(d)
+        t = mtt.simulate_trees(1, n, d, m, N, seed=300 + d).tree(0)
+        o = orc.UnifModel(m)
+        rng = np.random.default_rng(d)
+        for _ in range(10):
+            order = rng.permutation(n).astype(np.int32)
+            u = rng.random(8192)
+            r = orc.untyped_particle_tree(o, N, t.parent, t.height, t.nodeType, order, u)
+            r0 = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, order, u)
+            assert r["status"] == 0 and r["uUsed"] == r0["uUsed"] and r["logW"] == r0["logW"]
+            assert np.array_equal(r["nodeType"], r0["nodeType"])
+            assert np.array_equal(r["nodeType"][:n], t.nodeType[:n])      # leaves keep their types
+            ty = typed_tree_from_sample(t, r["nodeType"], r["chgNode"], r["chgType"], r["chgTime"])
+            _check_typed_tree(ty, d)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("d,n,scale", [(2, 8, 1.0), (2, 100, 1.0), (3, 25, 0.5), (4, 60, 2.0),
+                                       (10, 30, 1.0), (16, 12, 1.0), (2, 10, 30.0)])
+def test_sampled_typings_match_oracle_bit_for_bit(ctx, d, n, scale):
+    """mtt_untyped_sample_batch: node types, change owners, change types and change TIMES of
+    every particle identical to the restatement's for the same leaf order and uniform window;
+    weights as in the density entry; the returned trees are valid and the typed density of each
+    (mtt_sc_logp_batch, the k1 kernel) agrees with the weight's density part."""
+    from multitypetree_b200.untyped import typed_tree_from_sample, untyped_sample_batch
+    m, N = mtt.synthetic_model(d)
+    m = m * scale
+    trees = [mtt.simulate_trees(3, n, d, m, N, seed=190 + d).tree(b) for b in range(3)]
+    P, win = 6, 8192
+    orders, u, uOff = _inputs(trees, P, win, 15 + d)
+    um = UniformizationModels(m, ctx=ctx)
+    r = untyped_sample_batch(um, N, trees, P, np.concatenate(orders), u, uOff, ctx=ctx)
+    rl = untyped_logp_batch(um, N, trees, P, np.concatenate(orders), u, uOff, ctx=ctx)
+    assert np.array_equal(r["logW"], rl["logW"]) and np.array_equal(r["uUsed"], rl["uUsed"])
+    o = orc.UnifModel(m)
+    typed = []
+    for b, t in enumerate(trees):
+        for p in range(P):
+            q = b * P + p
+            ro = orc.untyped_particle_tree(o, N, t.parent, t.height, t.nodeType, orders[q],
+                                           u[uOff[q]:uOff[q + 1]])
+            assert ro["status"] == r["status"][b, p] == 0
+            c = ro["nChg"]
+            assert r["nChg"][b, p] == c
+            assert np.array_equal(r["nodeType"][b][p], ro["nodeType"].astype(np.uint8))
+            assert np.array_equal(r["chgNode"][b, p, :c], ro["chgNode"])
+            assert np.array_equal(r["chgType"][b, p, :c], ro["chgType"].astype(np.uint8))
+            assert np.array_equal(r["chgTime"][b, p, :c], ro["chgTime"])          # bit-exact
+            ty = typed_tree_from_sample(t, r["nodeType"][b][p], r["chgNode"][b, p, :c],
+                                        r["chgType"][b, p, :c], r["chgTime"][b, p, :c])
+            _check_typed_tree(ty, d)
+            typed.append(ty)
+    tb = mtt.TreeBatch.from_trees(typed)
+    lp = mtt.sc_logp_batch(tb, m, N, checkValidity=True, ctx=ctx)
+    want = orc.sc_logp_batch(tb, m, N, variant=orc.FAITHFUL)
+    assert np.all(np.isfinite(lp)) and np.allclose(lp, want, rtol=1e-9, atol=0)
+
+
+@pytest.mark.gpu
+def test_sample_room_and_failures_are_reported(ctx):
+    """nChg beyond chgCap is reported (never written past the room); a colouring without a valid
+    path returns that lineage's status and unreached nodes as 255."""
+    from multitypetree_b200.untyped import untyped_sample_batch
+    m, N = mtt.synthetic_model(2)
+    m = 20.0 * m
+    t = mtt.simulate_trees(1, 10, 2, m, N, seed=4).tree(0)
+    orders, u, uOff = _inputs([t], 3, 8192, 1)
+    um = UniformizationModels(m, ctx=ctx)
+    full = untyped_sample_batch(um, N, [t], 3, np.concatenate(orders), u, uOff, ctx=ctx)
+    small = untyped_sample_batch(um, N, [t], 3, np.concatenate(orders), u, uOff, chgCap=4, ctx=ctx)
+    assert np.array_equal(small["nChg"], full["nChg"]) and full["nChg"].min() > 4
+    assert np.array_equal(small["chgTime"][0, :, :4], full["chgTime"][0, :, :4])
+    m1 = np.array([[0.0, 0.5], [0.0, 0.0]])          # 1 -> 0 impossible backward in time
+    t1 = mtt.MultiTypeTreeFromNewick("((a[&t=0]:1,b[&t=1]:1)[&t=0]:1,c[&t=0]:2)[&t=0]:0;", "t")
+    um1 = UniformizationModels(m1, ctx=ctx)
+    orders, u, uOff = _inputs([t1], 8, 256, 3)
+    r = untyped_sample_batch(um1, np.array([1.0, 1.0]), [t1], 8, np.concatenate(orders), u, uOff,
+                             ctx=ctx)
+    o = orc.UnifModel(m1)
+    for p in range(8):
+        ro = orc.untyped_particle_tree(o, [1.0, 1.0], t1.parent, t1.height, t1.nodeType,
+                                       orders[p], u[uOff[p]:uOff[p + 1]])
+        assert ro["status"] == r["status"][0, p]
+        got = r["nodeType"][0][p].astype(np.int32)
+        got[got == 255] = -1
+        assert np.array_equal(got, ro["nodeType"])
+    assert np.any(r["status"] == 1)
+
+
+@pytest.mark.gpu
+def test_tree_initialisers(ctx):
+    """MultiTypeTreeFromUntypedNewick and StructuredCoalescentUntypedTree through the device:
+    valid typed trees with the Newick's topology, heights and leaf types; the same seed gives
+    the same tree."""
+    ts = mtt.TypeSet("A", "B", "C")
+    model = mtt.SCMigrationModel([0.3, 0.1, 0.2, 0.4, 0.2, 0.1], [5.0, 3.0, 4.0], ts, ctx=ctx)
+    nwk = "(((a:1.0,b:1.0):0.5,c:1.5):1.0,(d:0.7,e:0.2):1.3);"
+    trait = dict(a="A", b="B", c="C", d="A", e="C")
+    t1 = mtt.MultiTypeTreeFromUntypedNewick(nwk, model, trait, randomizer=Randomizer(11), ctx=ctx)
+    t2 = mtt.MultiTypeTreeFromUntypedNewick(nwk, model, trait, randomizer=Randomizer(11), ctx=ctx)
+    assert t1.getFlattenedNewick() == t2.getFlattenedNewick()
+    assert t1.getLeafNodeCount() == 5 and list(t1.taxa) == list("abcde")
+    assert [int(x) for x in t1.nodeType[:5]] == [0, 1, 2, 0, 2]
+    assert t1.height[t1.getRoot()] == pytest.approx(2.5)
+    _check_typed_tree(t1, 3)
+    assert t1.isValid(ctx=ctx)
+    back = mtt.MultiTypeTreeFromNewick(t1.getFlattenedNewick(), "type")
+    assert back.getTotalNumberOfChanges() == t1.getTotalNumberOfChanges()
+    with pytest.raises(ValueError, match="Trait set"):
+        mtt.MultiTypeTreeFromUntypedNewick(nwk, model, None, ctx=ctx)
+    # many trees in one call per round
+    m, N = model.dense()
+    many = [mtt.simulate_trees(16, 20, 3, m, N, seed=77).tree(b) for b in range(16)]
+    for ty in mtt.colour_untyped_trees(model, many, Randomizer(5), ctx=ctx):
+        _check_typed_tree(ty, 3)
+    u = mtt.StructuredCoalescentUntypedTree(model, [0, 1, 2, 0, 1, 2, 0, 1], seed=9, ctx=ctx)
+    assert u.getLeafNodeCount() == 8 and u.getTotalNumberOfChanges() == 0
+    assert np.all(u.height[:8] == 0.0)
+    for v in range(u.getNodeCount() - 1):
+        assert u.height[u.parent[v]] > u.height[v]
+    _check_typed_tree(mtt.colour_untyped_trees(model, [u], Randomizer(3), ctx=ctx)[0], 3)

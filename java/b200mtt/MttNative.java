@@ -39,6 +39,9 @@ public final class MttNative implements AutoCloseable {
     private static final MethodHandle UNTYPED_LOGP = h("mtt_untyped_logp_batch", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
             ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
+    private static final MethodHandle UNTYPED_SAMPLE = h("mtt_untyped_sample_batch", FunctionDescriptor.of(JAVA_INT,
+            ADDRESS, JAVA_LONG, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS,
+            ADDRESS, JAVA_INT, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS, ADDRESS));
     private static final MethodHandle PEEL_CREATE = h("mtt_peel_create", FunctionDescriptor.of(JAVA_INT,
             ADDRESS, JAVA_INT, JAVA_LONG, JAVA_INT, ADDRESS));
     private static final MethodHandle PEEL_DESTROY = h("mtt_peel_destroy", FunctionDescriptor.of(JAVA_INT, ADDRESS));
@@ -157,6 +160,24 @@ public final class MttNative implements AutoCloseable {
         try {
             check((int) UNTYPED_LOGP.invoke(ctx, nTrees, nParticles, model, N, nodeOff, height, parent, leafType,
                     leafOrder, uniforms, uOff, logP, logW, status, uUsed));
+        } catch (RuntimeException e) {
+            throw e;
+        } catch (Throwable t) {
+            throw new RuntimeException(t);
+        }
+    }
+
+    /** mtt_untyped_sample_batch: the particles returned as typings (node types + change lists). */
+    public void untypedSampleBatch(long nTrees, int nParticles, MemorySegment model, MemorySegment N,
+                                   MemorySegment nodeOff, MemorySegment height, MemorySegment parent,
+                                   MemorySegment leafType, MemorySegment leafOrder, MemorySegment uniforms,
+                                   MemorySegment uOff, int chgCap, MemorySegment nodeType, MemorySegment nChg,
+                                   MemorySegment chgTime, MemorySegment chgType, MemorySegment chgNode,
+                                   MemorySegment logW, MemorySegment status, MemorySegment uUsed) {
+        try {
+            check((int) UNTYPED_SAMPLE.invoke(ctx, nTrees, nParticles, model, N, nodeOff, height, parent, leafType,
+                    leafOrder, uniforms, uOff, chgCap, nodeType, nChg, chgTime, chgType, chgNode, logW, status,
+                    uUsed));
         } catch (RuntimeException e) {
             throw e;
         } catch (Throwable t) {

@@ -68,7 +68,8 @@ private:
 // evolution/tree/TypeSet.java: sorted set of type names; getNTypes() = max(size, 2) (:59-61)
 class TypeSet {
 public:
-    TypeSet(std::initializer_list<std::string> names) : names_(names)
+    TypeSet(std::initializer_list<std::string> names) : TypeSet(std::vector<std::string>(names)) {}
+    explicit TypeSet(std::vector<std::string> names) : names_(std::move(names))
     {
         std::sort(names_.begin(), names_.end());
         names_.erase(std::unique(names_.begin(), names_.end()), names_.end());
@@ -925,5 +926,143 @@ public:
 private:
     std::unique_ptr<NodeRetypeEnsemble> ens_;
 };
+
+// ------------------------------------------------------------------------------------------
+// untyped trees -- the particle density and the typings themselves
+
+// Randomizer.shuffled(n) [EXT]: identity, then element i swapped with element i + nextInt(n - i)
+inline std::vector<int32_t> shuffled(Randomizer &rng, int n)
+{
+    std::vector<int32_t> a(n);
+    for (int i = 0; i < n; i++)
+        a[i] = i;
+    for (int i = 0; i < n; i++)
+        std::swap(a[i], a[i + rng.nextInt(n - i)]);
+    return a;
+}
+
+// What both untyped entries read of a tree and of the chain's Randomizer: topology, heights and
+// leaf types; per particle a leaf order and one window of uniforms.
+class UntypedParticles {
+public:
+    UntypedParticles(const SCMigrationModel &migrationModel, const MultiTypeTree &tree,
+                     const Context &ctx)
+        : tree_(tree), ctx_(ctx), d_(migrationModel.getNTypes())
+    {
+        std::vector<double> m;
+        migrationModel.dense(m, N_);
+        ctx_.check(mtt_unif_set_models(ctx_.get(), 1, d_, m.data(), 0));
+        std::vector<double> Q((size_t)d_ * d_), R((size_t)d_ * d_);
+        double mu = 0;
+        ctx_.check(mtt_unif_get_matrices(ctx_.get(), 0, Q.data(), R.data(), &mu));
+        const auto mm = std::minmax_element(tree.height.begin(), tree.height.end());
+        const double muL = mu * (*mm.second - *mm.first);
+        window = 64 + (int64_t)(tree.getLeafNodeCount() * (muL + 6 * std::sqrt(muL + 1) + 4));
+        nodeOff_ = {0, tree.getNodeCount()};
+    }
+    int64_t window;                   // uniforms per particle (a lineage uses 1 + 2 nVirt)
+    void draw(Randomizer &rng, int nParticles)
+    {
+        const int nLeaves = tree_.getLeafNodeCount();
+        order_.clear();
+        u_.resize((size_t)nParticles * window);
+        uOff_.assign(nParticles + 1, 0);
+        for (int p = 0; p < nParticles; p++) {
+            const std::vector<int32_t> perm = shuffled(rng, nLeaves);
+            order_.insert(order_.end(), perm.begin(), perm.end());
+            rng.peekDoubles(window, u_.data() + (size_t)p * window);
+            rng.skipDoubles(window);
+            uOff_[p + 1] = (int64_t)(p + 1) * window;
+        }
+    }
+    const MultiTypeTree &tree_;
+    const Context &ctx_;
+    int d_;
+    std::vector<double> N_, u_;
+    std::vector<int64_t> nodeOff_, uOff_;
+    std::vector<int32_t> order_;
+};
+
+// distributions/StructuredCoalescentUntypedTreeDensity.java: Inputs tree, migrationModel,
+// nParticles; calculateLogP() (:116-207) = one call of mtt_untyped_logp_batch.
+class StructuredCoalescentUntypedTreeDensity {
+public:
+    StructuredCoalescentUntypedTreeDensity(const SCMigrationModel &migrationModel,
+                                           const MultiTypeTree &tree, int nParticles,
+                                           Randomizer &randomizer, const Context &ctx)
+        : in_(migrationModel, tree, ctx), nParticles_(nParticles), rng_(randomizer)
+    {
+    }
+    double calculateLogP()
+    {
+        std::vector<int32_t> status(nParticles_);
+        for (;;) {
+            in_.draw(rng_, nParticles_);
+            const MultiTypeTree &t = in_.tree_;
+            in_.ctx_.check(mtt_untyped_logp_batch(
+                in_.ctx_.get(), 1, nParticles_, nullptr, in_.N_.data(), in_.nodeOff_.data(),
+                t.height.data(), t.parent.data(), t.nodeType.data(), in_.order_.data(),
+                in_.u_.data(), in_.uOff_.data(), &logP, nullptr, status.data(), nullptr));
+            if (std::find(status.begin(), status.end(), (int32_t)MTT_ST_NEED_MORE_UNIFORMS) ==
+                status.end())
+                return logP;
+            in_.window *= 4;
+        }
+    }
+    bool isStochastic() const { return true; }
+    double logP = NAN;
+
+private:
+    UntypedParticles in_;
+    int nParticles_;
+    Randomizer &rng_;
+};
+
+// evolution/tree/MultiTypeTreeFromUntypedNewick.java:104-134: the types of the internal nodes
+// and the type changes of an untyped tree (topology, heights, leaf types) drawn lineage by
+// lineage -- one particle of mtt_untyped_sample_batch per attempt; a colouring without a valid
+// path starts over with a new leaf order (:118-133).
+inline MultiTypeTree colourUntypedTree(const MultiTypeTree &untyped,
+                                       const SCMigrationModel &migrationModel,
+                                       Randomizer &randomizer, const Context &ctx)
+{
+    UntypedParticles in(migrationModel, untyped, ctx);
+    const int n = untyped.getNodeCount();
+    int chgCap = std::max(16, n);
+    for (int attempt = 0; attempt < 1000; attempt++) {
+        in.draw(randomizer, 1);
+        std::vector<uint8_t> nodeType(n), chgType;
+        std::vector<double> chgTime;
+        std::vector<int32_t> chgNode;
+        int32_t nChg = 0, status = 0;
+        do {                                   // the same draw again if the changes need more room
+            chgCap = std::max(chgCap, 2 * nChg);
+            chgType.resize(chgCap);
+            chgTime.resize(chgCap);
+            chgNode.resize(chgCap);
+            ctx.check(mtt_untyped_sample_batch(
+                ctx.get(), 1, 1, nullptr, in.N_.data(), in.nodeOff_.data(), untyped.height.data(),
+                untyped.parent.data(), untyped.nodeType.data(), in.order_.data(), in.u_.data(),
+                in.uOff_.data(), chgCap, nodeType.data(), &nChg, chgTime.data(), chgType.data(),
+                chgNode.data(), nullptr, &status, nullptr));
+        } while (status == MTT_ST_OK && nChg > chgCap);
+        if (status == MTT_ST_NEED_MORE_UNIFORMS) {
+            in.window *= 4;
+            continue;
+        }
+        if (status != MTT_ST_OK)
+            continue;                          // "Colour simulation failed. Retrying." (:129)
+        MultiTypeTree out;
+        out.height = untyped.height;
+        out.parent = untyped.parent;
+        out.nodeType = nodeType;
+        out.changeTimes.assign(n, {});
+        out.changeTypes.assign(n, {});
+        for (int k = 0; k < nChg; k++)
+            out.addChange(chgNode[k], chgType[k], chgTime[k]);
+        return out;
+    }
+    throw Error(MTT_ERR_STATE, "colour simulation failed 1000 times");
+}
 
 }  // namespace mtt

@@ -103,8 +103,7 @@ public class MultiTypeTreeFromUntypedNewick extends MultiTypeTree implements Sta
             for (;;) {
                 MemorySegment order = a.allocate(4L * nLeaves, 16), u = a.allocate(8L * win, 16),
                         uOff = a.allocate(16, 8), nodeType = a.allocate(n, 16), nChg = a.allocate(4, 4),
-                        chgTime = a.allocate(8L * chgCap, 16), chgType = a.allocate(chgCap, 16),
-                        chgNode = a.allocate(4L * chgCap, 16), status = a.allocate(4, 4);
+                        status = a.allocate(4, 4);
                 int[] perm = Randomizer.shuffled(nLeaves);                               // :116
                 for (int i = 0; i < nLeaves; i++)
                     order.setAtIndex(JAVA_INT, i, perm[i]);
@@ -112,20 +111,25 @@ public class MultiTypeTreeFromUntypedNewick extends MultiTypeTree implements Sta
                     u.setAtIndex(JAVA_DOUBLE, i, Randomizer.nextDouble());
                 uOff.setAtIndex(JAVA_LONG, 0, 0);
                 uOff.setAtIndex(JAVA_LONG, 1, win);
-                nativeLib.untypedSampleBatch(1, 1, MemorySegment.NULL, N, nodeOff, height, parent, leafType, order,
-                        u, uOff, chgCap, nodeType, nChg, chgTime, chgType, chgNode, MemorySegment.NULL, status,
-                        MemorySegment.NULL);
-                int st = status.get(JAVA_INT, 0), c = nChg.get(JAVA_INT, 0);
+                MemorySegment chgTime, chgType, chgNode;
+                int st, c = 0;
+                do {                            // the same draw again if the changes need more room
+                    chgCap = Math.max(chgCap, 2 * c);
+                    chgTime = a.allocate(8L * chgCap, 16);
+                    chgType = a.allocate(chgCap, 16);
+                    chgNode = a.allocate(4L * chgCap, 16);
+                    nativeLib.untypedSampleBatch(1, 1, MemorySegment.NULL, N, nodeOff, height, parent, leafType,
+                            order, u, uOff, chgCap, nodeType, nChg, chgTime, chgType, chgNode, MemorySegment.NULL,
+                            status, MemorySegment.NULL);
+                    st = status.get(JAVA_INT, 0);
+                    c = nChg.get(JAVA_INT, 0);
+                } while (st == 0 && c > chgCap);
                 if (st == MttNative.ST_NEED_MORE_UNIFORMS) {
                     win *= 4;
                     continue;
                 }
                 if (st != 0) {
                     Log.info.println("Colour simulation failed. Retrying.");             // :129
-                    continue;
-                }
-                if (c > chgCap) {               // more changes than room: same draw cannot be replayed, go again
-                    chgCap = 2 * c;
                     continue;
                 }
                 for (int i = 0; i < n; i++) {

@@ -135,6 +135,61 @@ int main(int argc, char **argv)
             if (c != cp)
                 m[(size_t)c * d + cp] = (1.0 + 0.1 * ((c * d + cp) % 3)) / (d - 1);
     }
+
+    // ---------------------------------------------------------------- untyped trees (8f rank 1)
+    if (!timing) {
+        std::vector<std::string> names;
+        for (int c = 0; c < d; c++)
+            names.push_back(std::to_string(c));
+        mtt::TypeSet ts(names);
+        mtt::SCMigrationModel model(m, N, ts);
+        const mtt::MultiTypeTree untyped = simulate(1, n, d, m, N, 6000)[0];
+        // the typing: the C++ mirror against the oracle fed the same leaf order and uniforms
+        mtt::Randomizer r1(77), r2(77);
+        const mtt::MultiTypeTree typed = mtt::colourUntypedTree(untyped, model, r1, ctx);
+        std::vector<double> Q((size_t)d * d), Qs((size_t)d * d), R((size_t)d * d), Rs((size_t)d * d);
+        double mu = 0, mus = 0;
+        orc_update_matrices(d, m.data(), Q.data(), Qs.data(), &mu, &mus, R.data(), Rs.data());
+        orc_unif_model om{d, Q.data(), R.data(), mu, orc_rpow_new(d, R.data())};
+        const std::vector<int32_t> order = mtt::shuffled(r2, n);
+        std::vector<double> u(1 << 16);
+        r2.peekDoubles((int64_t)u.size(), u.data());
+        const int cap = 4096;
+        std::vector<int32_t> oType(untyped.getNodeCount()), oNode(cap), oCty(cap);
+        std::vector<double> oTime(cap);
+        int32_t oChg = 0;
+        double oW = 0;
+        int64_t oUsed = 0;
+        const int ost = orc_untyped_particle_tree(&om, N.data(), untyped.getNodeCount(),
+                                                  untyped.parent.data(), untyped.height.data(),
+                                                  untyped.nodeType.data(), order.data(), u.data(),
+                                                  (int64_t)u.size(), &oW, &oUsed, oType.data(), cap,
+                                                  &oChg, oNode.data(), oCty.data(), oTime.data());
+        orc_rpow_free(om.rpow);
+        mtt::MultiTypeTree want = untyped;
+        want.changeTimes.assign(untyped.getNodeCount(), {});
+        want.changeTypes.assign(untyped.getNodeCount(), {});
+        for (int k = 0; k < oChg; k++)
+            want.addChange(oNode[k], oCty[k], oTime[k]);
+        bool same = ost == ORC_ST_OK && typed.changeTimes == want.changeTimes &&
+                    typed.changeTypes == want.changeTypes;
+        for (int i = 0; i < untyped.getNodeCount(); i++)
+            same = same && typed.nodeType[i] == (uint8_t)oType[i];
+        // ... and a valid typed tree for the density of piece 1
+        mtt::StructuredCoalescentTreeDensity dens(model, typed, true, ctx);
+        const double lpTyped = dens.calculateLogP();
+        double st = 0;
+        for (auto &c : typed.changeTimes)
+            for (double x : c)
+                st += x;
+        std::printf("COLOUR %d %d %.12f %.12f\n", same ? 1 : 0, typed.getTotalNumberOfChanges(), st,
+                    lpTyped);
+        if (!same || !std::isfinite(lpTyped))
+            return 1;
+        mtt::Randomizer r3(78);
+        mtt::StructuredCoalescentUntypedTreeDensity ud(model, untyped, 32, r3, ctx);
+        std::printf("UNTYPED %.12f\n", ud.calculateLogP());
+    }
     std::vector<mtt::MultiTypeTree> trees = simulate(C, n, d, m, N, 5000);
     std::vector<std::unique_ptr<mtt::Randomizer>> rngs;
     mtt::NodeRetypeEnsemble ens(ctx, 1, d, m, false, window);

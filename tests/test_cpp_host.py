@@ -105,3 +105,18 @@ def test_cpp_tree_likelihood_and_node_retype_match_python_mirror():
         assert int(g[4]) == sty
         assert abs(float(g[3]) - st) <= 1e-9 * max(1.0, abs(st))
         assert abs(float(g[0]) - sumHR[c]) <= 1e-8 * max(1.0, abs(sumHR[c]))
+    # untyped trees: the C++ colouring (checked against the oracle inside the executable) and the
+    # particle density reproduce the Python mirror from the same seeds
+    from multitypetree_b200.untyped import (StructuredCoalescentUntypedTreeDensity,
+                                            colour_untyped_trees)
+    ut = mtt.simulate_trees(1, n, d, m, N, seed=6000, nThreads=4).tree(0)
+    col = [l for l in r.stdout.splitlines() if l.startswith("COLOUR")][0].split()
+    ty = colour_untyped_trees(model, [ut], Randomizer(77), ctx=ctx)[0]
+    assert int(col[1]) == 1 and int(col[2]) == ty.getTotalNumberOfChanges()
+    assert abs(float(col[3]) - sum(sum(x) for x in ty.changeTimes)) <= 1e-9 * max(1.0, float(col[3]))
+    lp = mtt.StructuredCoalescentTreeDensity(model, ty, checkValidity=True, ctx=ctx).calculateLogP()
+    assert abs(float(col[4]) - lp) <= 1e-9 * abs(lp)
+    und = [l for l in r.stdout.splitlines() if l.startswith("UNTYPED")][0].split()
+    up = StructuredCoalescentUntypedTreeDensity(model, ut, nParticles=32, randomizer=Randomizer(78),
+                                                ctx=ctx).calculateLogP()
+    assert abs(float(und[1]) - up) <= 1e-9 * abs(up)

@@ -837,10 +837,15 @@ def bench_retype(args):
 
 
 def bench_untyped(args):
-    """untyped-tree particle density, trees x particles in one call."""
+    """untyped-tree particle density, trees x particles in one call
+    (--workload untyped_sample: the same particles returned as typed trees)."""
     import multitypetree_b200 as mtt
     from multitypetree_b200.uniformization import UniformizationModels
-    from multitypetree_b200.untyped import untyped_logp_batch
+    from multitypetree_b200.untyped import untyped_logp_batch, untyped_sample_batch
+    as_trees = args.workload == "untyped_sample"
+    if as_trees:
+        def untyped_logp_batch(um, N, trees, P, orders, u, uOff, ctx=None):      # noqa: F811
+            return untyped_sample_batch(um, N, trees, P, orders, u, uOff, chgCap=256, ctx=ctx)
     world, rank, local = dist_setup(args.gpus)
     d, n = 2, (args.tips or 100)
     B = args.batch if args.batch != (1 << 19) else 64
@@ -875,18 +880,34 @@ def bench_untyped(args):
     worst = 0.0
     for q in range(sample):
         t = trees[q // P]
-        ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType, orders[q * n:(q + 1) * n],
-                                  u[uOff[q]:uOff[q + 1]])
+        if as_trees:
+            ro = orc.untyped_particle_tree(o, N, t.parent, t.height, t.nodeType,
+                                           orders[q * n:(q + 1) * n], u[uOff[q]:uOff[q + 1]])
+            b, p_, c = q // P, q % P, ro["nChg"]
+            same = (r["nChg"][b, p_] == c and c <= 256
+                    and np.array_equal(r["nodeType"][b][p_], ro["nodeType"].astype(np.uint8))
+                    and np.array_equal(r["chgNode"][b, p_, :c], ro["chgNode"])
+                    and np.all(np.abs(r["chgTime"][b, p_, :c] - ro["chgTime"])
+                               <= 4 * np.spacing(ro["chgTime"])))
+            if not same:
+                raise SystemExit("typed tree of particle %d differs from the oracle's" % q)
+        else:
+            ro = orc.untyped_particle(o, N, t.parent, t.height, t.nodeType,
+                                      orders[q * n:(q + 1) * n], u[uOff[q]:uOff[q + 1]])
         worst = max(worst, abs(ro["logW"] - r["logW"].ravel()[q]) / max(1.0, abs(ro["logW"])))
     cdt = time.perf_counter() - c0
     print(json.dumps({
-        "metric": "untyped-tree density: particle evaluations/s (end to end, host buffers)",
+        "metric": ("typed trees sampled from untyped ones: typings/s (end to end, host buffers; "
+                   "identical to the oracle on the sample, times to the last place)" if as_trees else
+                   "untyped-tree density: particle evaluations/s (end to end, host buffers)"),
         "value": B * P * world * args.steps / dt, "unit": "particles/s", "n_gpus": world,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
         "data": "synthetic",
-        "config": {"workload": "untyped density: %d trees x %d particles per GPU, %d tips, d=%d"
-                               % (B, P, n, d), "tree_evals_per_s": B * world * args.steps / dt,
+        "config": {"workload": "%s: %d trees x %d particles per GPU, %d tips, d=%d"
+                               % ("typed trees from untyped ones (room for 256 changes each)"
+                                  if as_trees else "untyped density", B, P, n, d),
+                   "tree_evals_per_s": B * world * args.steps / dt,
                    "uniform_window": W, "pinned": len(pinned) == 2},
         "cpu_baseline": {"value": sample / cdt, "unit": "particles/s", "cores": 1, "kind": "port",
                          "sample": "%d particles of the same batch, oracle/orc_untyped.c" % sample},
@@ -900,7 +921,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_chains", "peel_sharded", "retype", "untyped"])
+    ap.add_argument("--workload", default="density", choices=["density", "peel", "peel_chains", "peel_sharded", "retype", "untyped", "untyped_sample"])
     ap.add_argument("--tips", type=int, default=0)
     ap.add_argument("--sites", type=int, default=0)
     ap.add_argument("--batch", type=int, default=1 << 19, help="trees per GPU per step")
@@ -916,7 +937,7 @@ def main():
         return bench_peel_sharded(args)
     if args.workload == "retype":
         return bench_retype(args)
-    if args.workload == "untyped":
+    if args.workload in ("untyped", "untyped_sample"):
         return bench_untyped(args)
     return bench_density(args)
 

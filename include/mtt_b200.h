@@ -267,7 +267,10 @@ int mtt_untyped_logp_batch(mtt_ctx *ctx, int64_t nTrees, int nParticles, const i
  *   nChg[q] type changes, the first min(nChg[q], chgCap) of them in chgTime / chgType /
  *       chgNode[q * chgCap ..): chgNode = the node BELOW the change (MultiTypeNode.addChange),
  *       chgType = the type entered going rootward; the changes of one node appear in increasing
- *       time.  nChg[q] > chgCap: resubmit with more room.
+ *       time.  nChg[q] > chgCap: resubmit with more room.  Times along the conditioned paths
+ *       (u * L + t0) are bit-reproducible against the CPU restatement; the waiting times of the
+ *       first, unconditioned lineage go through log() (Randomizer.nextExponential) and agree to
+ *       the last place.
  *   logW (optional): the particle's importance weight, as in mtt_untyped_logp_batch.
  * status: MTT_ST_OK, MTT_ST_NEED_MORE_UNIFORMS, or the status of the lineage that has no valid
  * path (MTT_ST_NO_VALID_PATH / _PBA_RUBBISH / _FB_FELL_THROUGH): the reference starts the whole

@@ -335,6 +335,14 @@ def _check_typed_tree(t, d):
         assert prev_ty == int(t.nodeType[p]), v
 
 
+def _root_path(t, leaf):
+    path, v = [], int(leaf)
+    while v >= 0:
+        path.append(v)
+        v = int(t.parent[v])
+    return np.array(path)
+
+
 def test_oracle_typed_tree_is_a_valid_typing_of_the_untyped_tree():
     from multitypetree_b200.untyped import typed_tree_from_sample
     for d, n in ((2, 20), (4, 35), (7, 12)):
@@ -358,8 +366,9 @@ def test_oracle_typed_tree_is_a_valid_typing_of_the_untyped_tree():
 @pytest.mark.parametrize("d,n,scale", [(2, 8, 1.0), (2, 100, 1.0), (3, 25, 0.5), (4, 60, 2.0),
                                        (10, 30, 1.0), (16, 12, 1.0), (2, 10, 30.0)])
 def test_sampled_typings_match_oracle_bit_for_bit(ctx, d, n, scale):
-    """mtt_untyped_sample_batch: node types, change owners, change types and change TIMES of
-    every particle identical to the restatement's for the same leaf order and uniform window;
+    """mtt_untyped_sample_batch: node types, change owners, change types and change times of
+    every particle identical to the restatement's for the same leaf order and uniform window
+    (the unconditioned first lineage's times to the last place of log());
     weights as in the density entry; the returned trees are valid and the typed density of each
     (mtt_sc_logp_batch, the k1 kernel) agrees with the weight's density part."""
     from multitypetree_b200.untyped import typed_tree_from_sample, untyped_sample_batch
@@ -385,7 +394,14 @@ def test_sampled_typings_match_oracle_bit_for_bit(ctx, d, n, scale):
             assert np.array_equal(r["nodeType"][b][p], ro["nodeType"].astype(np.uint8))
             assert np.array_equal(r["chgNode"][b, p, :c], ro["chgNode"])
             assert np.array_equal(r["chgType"][b, p, :c], ro["chgType"].astype(np.uint8))
-            assert np.array_equal(r["chgTime"][b, p, :c], ro["chgTime"])          # bit-exact
+            # times: bit-identical along every conditioned path (u * L + t0); the first
+            # lineage's waiting times go through log() (Randomizer.nextExponential), where the
+            # device's log and the host's may differ in the last place
+            first = _root_path(t, orders[q][0])
+            onFirst = np.isin(ro["chgNode"], first)
+            gt = r["chgTime"][b, p, :c]
+            assert np.array_equal(gt[~onFirst], ro["chgTime"][~onFirst])
+            assert np.all(np.abs(gt - ro["chgTime"]) <= 4 * np.spacing(ro["chgTime"]))
             ty = typed_tree_from_sample(t, r["nodeType"][b][p], r["chgNode"][b, p, :c],
                                         r["chgType"][b, p, :c], r["chgTime"][b, p, :c])
             _check_typed_tree(ty, d)

@@ -475,3 +475,45 @@ def test_tree_initialisers(ctx):
     for v in range(u.getNodeCount() - 1):
         assert u.height[u.parent[v]] > u.height[v]
     _check_typed_tree(mtt.colour_untyped_trees(model, [u], Randomizer(3), ctx=ctx)[0], 3)
+
+
+def test_oracle_typed_trees_weighted_root_type_matches_exact_posterior():
+    """The typing that comes back IS the one the weight belongs to: over many particles of a
+    two-leaf tree the importance-weighted frequency of the root's type equals the exact posterior
+    P(root type c | T) ~ expm(G T)[(a, b), (c, c)] / N_c of the killed pair process."""
+    m = np.array([[0, 0.3], [0.2, 0]])
+    N = np.array([5.0, 10.0])
+    d = 2
+    Q = np.array(m, float)
+    for i in range(d):
+        Q[i, i] = -Q[i].sum()
+    G = np.kron(Q, np.eye(d)) + np.kron(np.eye(d), Q)
+    for c in range(d):
+        G[c * d + c, c * d + c] -= 1.0 / N[c]
+    a, b, T = 0, 1, 4.0
+    E = sl.expm(G * T)
+    post = np.array([E[a * d + b, c * d + c] / N[c] for c in range(d)])
+    post /= post.sum()
+    um = orc.UnifModel(m)
+    parent = np.array([2, 2, -1], np.int32)
+    height = np.array([0.0, 0.0, T])
+    rng = np.random.default_rng(11)
+    ws, roots = [], []
+    for _ in range(20000):
+        r = orc.untyped_particle_tree(um, N, parent, height, [a, b, 0], rng.permutation(2),
+                                      rng.random(512))
+        assert r["status"] == 0
+        # the changes lead from each leaf's type to the root's
+        for leaf in (0, 1):
+            ty = [a, b][leaf]
+            for k in np.nonzero(r["chgNode"] == leaf)[0]:
+                assert r["chgType"][k] != ty
+                ty = r["chgType"][k]
+            assert ty == r["nodeType"][2]
+        ws.append(r["logW"])
+        roots.append(r["nodeType"][2])
+    w = np.exp(np.array(ws) - max(ws))
+    roots = np.array(roots)
+    est = np.array([w[roots == c].sum() for c in range(d)]) / w.sum()
+    ess = w.sum() ** 2 / (w ** 2).sum()
+    assert np.all(np.abs(est - post) < 5 * np.sqrt(post * (1 - post) / ess) + 1e-3), (est, post)

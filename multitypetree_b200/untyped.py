@@ -261,18 +261,22 @@ def _untyped_from_flat(flat, leafTypeOf) -> MultiTypeTree:
 
 
 def MultiTypeTreeFromUntypedNewick(value: str, migrationModel, typeTrait, typeLabel: str = "type",
-                                   randomizer: Optional[Randomizer] = None, ctx=None) -> MultiTypeTree:
+                                   randomizer: Optional[Randomizer] = None, ctx=None,
+                                   adjustTipHeights: bool = True) -> MultiTypeTree:
     """evolution/tree/MultiTypeTreeFromUntypedNewick.java: a typed tree from an untyped Newick
     string, the leaf types from ``typeTrait`` (taxon -> type name or index; the reference's
     TraitSet named ``typeLabel``), the rest coloured lineage by lineage with the uniformization
     sampler on the device.  Inputs keep the reference's names (``value``, ``migrationModel``,
-    ``typeLabel``)."""
+    ``typeLabel``, ``adjustTipHeights`` -- default true here, :37-38: BEAST's TreeParser then
+    puts every tip at height 0 when there is no date trait [EXT])."""
     from .tree import _type_index, parse_flat_newick
     if typeTrait is None:
         raise ValueError("Trait set (with name '%s') must be provided." % typeLabel)   # :98-101
     typeSet = getattr(migrationModel, "typeSet", None)
     tree = _untyped_from_flat(parse_flat_newick(value),
                               lambda name: _type_index(typeTrait[name], typeSet))
+    if adjustTipHeights:
+        tree.height[:tree.getLeafNodeCount()] = 0.0
     return colour_untyped_trees(migrationModel, [tree], randomizer or Randomizer(127), ctx=ctx)[0]
 
 

@@ -457,7 +457,11 @@ def test_tree_initialisers(ctx):
     assert t1.getFlattenedNewick() == t2.getFlattenedNewick()
     assert t1.getLeafNodeCount() == 5 and list(t1.taxa) == list("abcde")
     assert [int(x) for x in t1.nodeType[:5]] == [0, 1, 2, 0, 2]
-    assert t1.height[t1.getRoot()] == pytest.approx(2.5)
+    assert t1.height[t1.getRoot()] == pytest.approx(2.5) and np.all(t1.height[:5] == 0.0)
+    t3 = mtt.MultiTypeTreeFromUntypedNewick(nwk, model, trait, randomizer=Randomizer(11), ctx=ctx,
+                                            adjustTipHeights=False)
+    assert t3.height[:5] == pytest.approx([0.0, 0.0, 0.0, 0.5, 1.0])
+    _check_typed_tree(t3, 3)
     _check_typed_tree(t1, 3)
     assert t1.isValid(ctx=ctx)
     back = mtt.MultiTypeTreeFromNewick(t1.getFlattenedNewick(), "type")

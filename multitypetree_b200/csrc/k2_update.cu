@@ -774,6 +774,7 @@ static int chains_launch(mtt_peel_chains *s, const std::vector<double> &kap,
     x.in(order.data(), order.size(), BUF_C_ORDER, &dOrder);
     x.in(kap.data(), kap.size(), BUF_C_KAPPA, &dKappa);
     x.out(got.data(), got.size(), BUF_C_LOGL, &dLogL);
+    x.direct_out();                         // written once, by the last tile of each chain
     if ((rc = x.prepare()) != MTT_OK || (rc = x.upload()) != MTT_OK)
         return rc;
     if (s->timing)

@@ -576,6 +576,7 @@ int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t n, const int32_t *model,
     x.in(chgType, (size_t)nChg, BUF_U_IN7, &dCTy);
     x.out(logProb, (size_t)n, BUF_U_OUT0, &dLP);
     x.out(status, (size_t)n, BUF_U_OUT1, &dSt);
+    x.direct_out();
     int rc = x.prepare();
     if (rc == MTT_OK)
         rc = x.upload();

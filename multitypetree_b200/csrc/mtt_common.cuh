@@ -85,6 +85,10 @@ public:
         outs_.push_back(Item{(void *)dst, count * sizeof(T), bufId, (void **)dptr, 0});
     }
     bool staged() const { return staged_; }
+    // Staged outputs of at most this many bytes are written by the kernels straight into the
+    // page-locked buffer (device-visible under unified addressing): no copy back, only the
+    // synchronise.  For outputs that are written once and not read on the device.
+    void direct_out(size_t limit = 4096) { directLimit_ = limit; }
     int prepare();      // device (and staging) memory, device addresses
     int upload();       // inputs -> device, asynchronous on the ctx stream
     int download();     // outputs -> host, synchronises the stream
@@ -108,7 +112,8 @@ private:
     };
     mtt_ctx *ctx_;
     size_t limit_;
-    bool staged_ = false;
+    bool staged_ = false, direct_ = false;
+    size_t directLimit_ = 0;
     size_t inBytes_ = 0, outBytes_ = 0;
     std::vector<Item> ins_, outs_;
 };

@@ -88,8 +88,9 @@ int Xfer::prepare()
             return rc;
         for (Item &i : ins_)
             *i.dptr = dIn + i.off;
+        direct_ = out > 0 && out <= directLimit_;
         for (Item &o : outs_)
-            *o.dptr = dOut + o.off;
+            *o.dptr = (direct_ ? (char *)ctx_->pinOut : dOut) + o.off;
         return MTT_OK;
     }
     for (Item &i : ins_)
@@ -124,7 +125,7 @@ int Xfer::download()
 {
     cudaStream_t s = ctx_->stream;
     if (staged_) {
-        if (outBytes_)
+        if (outBytes_ && !direct_)
             MTT_CUDA(ctx_, cudaMemcpyAsync(ctx_->pinOut, ctx_->bufs[BUF_STAGE_OUT].p, outBytes_,
                                            cudaMemcpyDeviceToHost, s));
         MTT_CUDA(ctx_, cudaStreamSynchronize(s));
@@ -418,6 +419,7 @@ static int sc_logp_host(mtt_ctx *ctx, const char *who, int64_t B, int d, int64_t
             x.out(logP, (size_t)B, BUF_D_LOGP, &dLogP);
             if (valid && parent)
                 x.out(valid, (size_t)B, BUF_D_VALID, &dValid);
+            x.direct_out();                 // logP / valid: written once per tree
             int rc = x.prepare();
             if (rc == MTT_OK && x.staged()) {
                 // (arrays that a tree set without changes never reads still need an address,

@@ -1695,10 +1695,9 @@ int launch_warp(mtt_ctx *ctx, const K1Params &p)
     constexpr int W = warps_per_cta(EMAX);
     size_t smem = sizeof(ModelTab) * (PT ? W : 1) + sizeof(WarpSmem<NW, HP, EMAX>) * W;
     auto kern = k1_density_warp<NW, HP, PT, EMAX>;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, kern, smem));
     int perSM = 1;
-    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, W * 32, smem));
+    MTT_CUDA(ctx, mtt_fn_occupancy(ctx, kern, W * 32, smem, &perSM));
     if (perSM < 1)
         perSM = 1;
     long long want = (p.B + W - 1) / W;
@@ -1730,10 +1729,9 @@ int launch_cta_t(mtt_ctx *ctx, const K1Params &p, int Scap, int useQueue, long l
     int tmInSmem = fixed + (size_t)Scap * 18 <= 200 * 1024;
     size_t smem = fixed + (size_t)Scap * (tmInSmem ? 18 : 10);
     auto kern = k1_density_cta<(NW == 0) ? 1 : NW, THREADS>;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, kern, smem));
     int perSM = 1;
-    MTT_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, THREADS, smem));
+    MTT_CUDA(ctx, mtt_fn_occupancy(ctx, kern, THREADS, smem, &perSM));
     if (perSM < 1)
         perSM = 1;
     long long grid = (long long)ctx->numSMs * perSM;

@@ -640,8 +640,7 @@ int launch_peel_t(mtt_peel *h, long long B, int nSlots, int smemSlots, double *p
     smemSlots = std::min(smemSlots, nSlots);
     const size_t smem = 2 * Cfg::STAGE_BYTES + 16 + (size_t)smemSlots * SLOT_BYTES;
     auto kern = k2_peel<C, TPT, PPT, XL>;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, kern, smem));
     // global scratch for the deeper slots, at most ~1 GB: larger batches run in sub-batches
     const size_t coldPerTree = (size_t)nTiles * (size_t)(nSlots - smemSlots) * SLOT_BYTES;
     long long sub = B;
@@ -710,8 +709,7 @@ int peel_chunk(mtt_peel *h, long long B, const int *dParent, const double *dHeig
     if (prepSmem > 227 * 1024)
         return mtt_fail(ctx, MTT_ERR_TOO_LARGE, "peeling: %d tips exceed the traversal planner's "
                         "shared memory (limit ~7700 tips)", n);
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k2_prepare, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)prepSmem));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k2_prepare, prepSmem));
     if (!h->dMaxSlots) {
         MTT_CUDA(ctx, cudaMalloc((void **)&h->dMaxSlots, 256));
         MTT_CUDA(ctx, cudaMallocHost((void **)&h->hMaxSlots, sizeof(int)));

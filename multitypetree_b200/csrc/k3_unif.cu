@@ -531,8 +531,7 @@ int mtt_unif_expm_batch(mtt_ctx *ctx, int64_t n, const int32_t *model, const dou
         return MTT_ERR_CUDA;
     MTT_CUDA(ctx, cudaMemcpyAsync(dModel, model, n * 4, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dL, L, n * 8, cudaMemcpyHostToDevice, s));
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_expm_batch, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)expm_smem(d)));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_expm_batch, expm_smem(d)));
     k3_expm_batch<<<(unsigned)((n + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
         n, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel, dL, dOut);
     MTT_CHECK_LAUNCH(ctx);
@@ -582,8 +581,7 @@ int mtt_unif_branch_logp_batch(mtt_ctx *ctx, int64_t n, const int32_t *model,
         rc = x.upload();
     if (rc != MTT_OK)
         return rc;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_branch_logp, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)expm_smem(d)));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_branch_logp, expm_smem(d)));
     k3_branch_logp<<<(unsigned)((n + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
         n, d, (const double *)ctx->bufs[BUF_U_Q].p, (const double *)ctx->bufs[BUF_U_LOGQ].p, dModel,
         dT0, dT1, dA, dB, dOff, dCT, dCTy, dLP,
@@ -669,10 +667,8 @@ int retype_chunked(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff, const int3
     while (tCap < K && tCap < U_TCAP)
         tCap <<= 1;
     const size_t smem = (size_t)U_WARPS * (8 * dd + tCap + tCap / 8) * 8;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_retype, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)smem));
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_pba, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)expm_smem(d)));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_retype, smem));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_pba, expm_smem(d)));
     const int64_t perChunk = (nJobs + NC - 1) / NC;
     const unsigned maxBlocks = (unsigned)((perChunk + U_WARPS - 1) / U_WARPS);
     int scratchCap = 0;
@@ -864,9 +860,7 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         }
         MTT_CUDA(ctx, cudaEventRecord(ctx->events[0], s));
         MTT_CUDA(ctx, cudaStreamWaitEvent(ctx->copyStream, ctx->events[0], 0));
-        MTT_CUDA(ctx, cudaFuncSetAttribute(k3_branch_logp,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)expm_smem(d)));
+        MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_branch_logp, expm_smem(d)));
         k3_branch_logp<<<(unsigned)((old->n + U_WARPS - 1) / U_WARPS), U_WARPS * 32,
                          expm_smem(d), ctx->copyStream>>>(
             old->n, d, (const double *)ctx->bufs[BUF_U_Q].p,
@@ -881,8 +875,7 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
     double *dPba = (double *)mtt_buf(ctx, BUF_U_PBA, (size_t)nBr * 8);
     if (!dPba)
         return MTT_ERR_CUDA;
-    MTT_CUDA(ctx, cudaFuncSetAttribute(k3_pba, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)expm_smem(d)));
+    MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_pba, expm_smem(d)));
     k3_pba<<<(unsigned)((nBr + U_WARPS - 1) / U_WARPS), U_WARPS * 32, expm_smem(d), s>>>(
         nBr, d, (const double *)ctx->bufs[BUF_U_Q].p, dModel, dT0, dT1, dA, dB, dPba);
     MTT_CHECK_LAUNCH(ctx);
@@ -899,8 +892,7 @@ int retype_impl(mtt_ctx *ctx, int64_t nJobs, const int64_t *brOff,
         while (tCap < K && tCap < U_TCAP)
             tCap <<= 1;
         const size_t smem = (size_t)U_WARPS * (8 * dd + tCap + tCap / 8) * 8;
-        MTT_CUDA(ctx, cudaFuncSetAttribute(k3_retype, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
+        MTT_CUDA(ctx, mtt_fn_smem(ctx, k3_retype, smem));
         int scratchCap = 0;
         double *scrT = nullptr;
         uint8_t *scrTy = nullptr;

@@ -551,8 +551,7 @@ static int untyped_run(mtt_ctx *ctx, int64_t nTrees, int nParticles, const int32
             return rc;
         const size_t smem = (size_t)P_WARPS * particle_smem_doubles(d, eCap, tCap, nCap) * 8;
         void (*kernel)(const ParticleParams) = tr ? k4_particles<true> : k4_particles<false>;
-        MTT_CUDA(ctx, cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                           (int)smem));
+        MTT_CUDA(ctx, mtt_fn_smem(ctx, kernel, smem));
         ParticleParams p;
         p.nTrees = nTrees; p.nParticles = nParticles; p.d = d; p.powCap = ctx->unifPowCap;
         p.eCap = eCap; p.tCap = tCap; p.nCap = nCap;

@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <map>
 #include <string>
 #include <vector>
 
@@ -41,6 +42,13 @@ struct mtt_ctx {
     // pinned staging of small calls (Xfer below)
     void *pinIn = nullptr, *pinOut = nullptr;
     size_t pinInCap = 0, pinOutCap = 0;
+    // per kernel: the dynamic shared-memory limit already granted and the last occupancy answer
+    // (mtt_fn_smem / mtt_fn_occupancy: no runtime query on the latency path of small calls)
+    struct FnState {
+        size_t smemSet = 0, occSmem = (size_t)-1;
+        int occThreads = -1, perSM = 0;
+    };
+    std::map<const void *, FnState> fns;
 };
 
 enum BufId {
@@ -125,6 +133,38 @@ private:
             return mtt_fail((ctx), MTT_ERR_CUDA, "%s failed: %s (%s:%d)", #expr,         \
                             cudaGetErrorString(_e), __FILE__, __LINE__);                 \
     } while (0)
+
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per kernel and size (the limit only grows)
+template <typename F>
+inline cudaError_t mtt_fn_smem(mtt_ctx *ctx, F kernel, size_t smem)
+{
+    mtt_ctx::FnState &f = ctx->fns[(const void *)kernel];
+    if (smem <= f.smemSet)
+        return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute((const void *)kernel,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess)
+        f.smemSet = smem;
+    return e;
+}
+// resident CTAs per SM, asked once per (kernel, threads, shared memory)
+template <typename F>
+inline cudaError_t mtt_fn_occupancy(mtt_ctx *ctx, F kernel, int threads, size_t smem, int *perSM)
+{
+    mtt_ctx::FnState &f = ctx->fns[(const void *)kernel];
+    if (f.occThreads != threads || f.occSmem != smem) {
+        int n = 0;
+        cudaError_t e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, (const void *)kernel,
+                                                                      threads, smem);
+        if (e != cudaSuccess)
+            return e;
+        f.occThreads = threads;
+        f.occSmem = smem;
+        f.perSM = n;
+    }
+    *perSM = f.perSM;
+    return cudaSuccess;
+}
 
 #define MTT_CHECK_LAUNCH(ctx)                                                            \
     do {                                                                                 \

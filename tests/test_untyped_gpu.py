@@ -521,3 +521,33 @@ def test_oracle_typed_trees_weighted_root_type_matches_exact_posterior():
     est = np.array([w[roots == c].sum() for c in range(d)]) / w.sum()
     ess = w.sum() ** 2 / (w ** 2).sum()
     assert np.all(np.abs(est - post) < 5 * np.sqrt(post * (1 - post) / ess) + 1e-3), (est, post)
+
+
+@pytest.mark.gpu
+def test_sampled_typings_of_trees_of_different_sizes(ctx):
+    """Ragged batch: trees of 8, 20 and 13 tips in one call, three particles each."""
+    from multitypetree_b200.untyped import typed_tree_from_sample, untyped_sample_batch
+    d = 3
+    m, N = mtt.synthetic_model(d)
+    trees = [mtt.simulate_trees(1, n, d, m, N, seed=500 + n).tree(0) for n in (8, 20, 13)]
+    P, win = 3, 4096
+    orders, u, uOff = _inputs(trees, P, win, 21)
+    um = UniformizationModels(m, ctx=ctx)
+    r = untyped_sample_batch(um, N, trees, P, np.concatenate(orders), u, uOff, ctx=ctx)
+    o = orc.UnifModel(m)
+    for b, t in enumerate(trees):
+        assert r["nodeType"][b].shape == (P, t.getNodeCount())
+        for p in range(P):
+            q = b * P + p
+            ro = orc.untyped_particle_tree(o, N, t.parent, t.height, t.nodeType, orders[q],
+                                           u[uOff[q]:uOff[q + 1]])
+            c = ro["nChg"]
+            assert ro["status"] == r["status"][b, p] == 0 and r["nChg"][b, p] == c
+            assert np.array_equal(r["nodeType"][b][p], ro["nodeType"].astype(np.uint8))
+            assert np.array_equal(r["chgNode"][b, p, :c], ro["chgNode"])
+            assert np.array_equal(r["chgType"][b, p, :c], ro["chgType"].astype(np.uint8))
+            assert np.all(np.abs(r["chgTime"][b, p, :c] - ro["chgTime"])
+                          <= 4 * np.spacing(ro["chgTime"]))
+            _check_typed_tree(typed_tree_from_sample(t, r["nodeType"][b][p], r["chgNode"][b, p, :c],
+                                                     r["chgType"][b, p, :c],
+                                                     r["chgTime"][b, p, :c]), d)

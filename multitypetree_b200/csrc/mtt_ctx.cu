@@ -679,10 +679,51 @@ extern "C" int mtt_sc_logp_tips_batch(mtt_ctx *ctx, int64_t B, int d, int64_t nM
         return MTT_ERR_CUDA;
     const double *dTipH = (const double *)ctx->bufs[BUF_D_TIPH].p;
     const uint8_t *dTipT = (const uint8_t *)ctx->bufs[BUF_D_TIPT].p;
+    const size_t bytes = (size_t)B * nI * 9 + (size_t)nodes * (parent ? 4 : 0) + (size_t)changes * 11;
+    if (md + nd + (size_t)(B + 1) * 8 + bytes + (size_t)B * 9 + 12 * 256 <= ((size_t)1 << 20)) {
+        // Small calls -- calculateLogP() of one chain, an ensemble step -- are latency: all
+        // inputs through one page-locked staging buffer and one copy, the results written by
+        // the kernel straight into page-locked memory (Xfer), as in mtt_sc_logp_owner_batch.
+        Xfer x(ctx);
+        x.in(m, md / 8, BUF_D_MODEL, &dM);
+        x.in(N, nd / 8, BUF_D_N, &dN);
+        x.in(chgBase, (size_t)B + 1, BUF_D_CHGBASE, &dChgBase);
+        x.in(intHeight, (size_t)B * nI, BUF_D_INTH, &dIH);
+        x.in(intType, (size_t)B * nI, BUF_D_INTT, &dIT);
+        if (changes > 0) {
+            x.in(chgTime, (size_t)changes, BUF_D_CHGTIME, &dCT);
+            x.in(chgType, (size_t)changes, BUF_D_CHGTYPE, &dCTy);
+            x.in(chgNode, (size_t)changes, BUF_D_CHGNODE, &dO);
+        }
+        if (parent)
+            x.in(parent, (size_t)nodes, BUF_D_PARENT, &dP);
+        x.out(logP, (size_t)B, BUF_D_LOGP, &dLogP);
+        if (dValid)
+            x.out(valid, (size_t)B, BUF_D_VALID, &dValid);
+        x.direct_out();
+        int rc = x.prepare();
+        if (rc == MTT_OK)
+            rc = x.upload();
+        if (rc != MTT_OK)
+            return rc;
+        const long long total = (long long)B * nN;
+        const unsigned grid = (unsigned)std::min<long long>((total + 255) / 256, 148 * 32);
+        k1_expand_tips<<<grid, 256, 0, s>>>(B, nL, dTipH, dTipT, dIH, dIT, 0, dH, dT,
+                                            (long long *)dNodeOff);
+        MTT_CHECK_LAUNCH(ctx);
+        rc = mtt_k1_launch(ctx, B, d, nModels > 1 ? B : 1, dM, dN, dNodeOff, dH, dP, dT, dO,
+                           dChgBase, dCT, dCTy, checkValidity, dLogP, dValid, maxEv);
+        if (rc != MTT_OK)
+            return rc;
+        if ((rc = x.download()) != MTT_OK)
+            return rc;
+        if (valid && !parent)
+            memset(valid, 1, (size_t)B);
+        return MTT_OK;
+    }
     MTT_CUDA(ctx, cudaMemcpyAsync(dM, m, md, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dN, N, nd, cudaMemcpyHostToDevice, s));
     MTT_CUDA(ctx, cudaMemcpyAsync(dChgBase, chgBase, (B + 1) * 8, cudaMemcpyHostToDevice, s));
-    const size_t bytes = (size_t)B * nI * 9 + (size_t)nodes * (parent ? 4 : 0) + (size_t)changes * 11;
     const int nChunks = (bytes > ((size_t)32 << 20) && B >= 1024) ? 8 : 1;
     cudaStream_t cs = s;
     if (nChunks > 1) {

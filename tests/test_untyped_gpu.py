@@ -551,3 +551,76 @@ def test_sampled_typings_of_trees_of_different_sizes(ctx):
             _check_typed_tree(typed_tree_from_sample(t, r["nodeType"][b][p], r["chgNode"][b, p, :c],
                                                      r["chgType"][b, p, :c],
                                                      r["chgTime"][b, p, :c]), d)
+
+
+def test_initialiser_host_logic_with_the_oracle_standing_in_for_the_device(monkeypatch):
+    """MultiTypeTreeFromUntypedNewick's host side on CPU: Newick and trait handling,
+    adjustTipHeights, the retry after a colouring without a valid path -- with the device call
+    replaced (in this test only) by the oracle's particle."""
+    import multitypetree_b200.untyped as un
+
+    m = np.array([[0.0, 0.4, 0.1], [0.3, 0.0, 0.2], [0.2, 0.5, 0.0]])
+    N = np.array([5.0, 3.0, 4.0])
+    calls = []
+
+    class _Dev:
+        ctx = None
+
+        def matrices(self, k):
+            o = orc.UnifModel(m)
+            return o.Q, o.R, o.mu
+
+    class _Model:
+        typeSet = mtt.TypeSet("A", "B", "C")
+
+        def _ensure_device(self, sym):
+            return _Dev()
+
+        def dense(self):
+            return m, N
+
+    def fake_sample(um, N_, trees, P, order, u, uOff, chgCap=None, model=None, ctx=None):
+        o = orc.UnifModel(m)
+        B = len(trees)
+        out = dict(nodeType=[], nChg=np.zeros((B, 1), np.int32), status=np.zeros((B, 1), np.int32),
+                   chgNode=np.zeros((B, 1, 512), np.int32), chgType=np.zeros((B, 1, 512), np.uint8),
+                   chgTime=np.zeros((B, 1, 512)))
+        pos = 0
+        for b, t in enumerate(trees):
+            n = t.getLeafNodeCount()
+            r = orc.untyped_particle_tree(o, N_, t.parent, t.height, t.nodeType,
+                                          order[pos:pos + n], u[uOff[b]:uOff[b + 1]])
+            pos += n
+            st = r["status"]
+            if len(calls) == 0 and b == 0:
+                st = 1                      # first attempt: pretend there was no valid path
+            out["status"][b, 0] = st
+            out["nChg"][b, 0] = r["nChg"]
+            out["nodeType"].append(r["nodeType"].astype(np.uint8)[None, :])
+            c = r["nChg"]
+            out["chgNode"][b, 0, :c] = r["chgNode"]
+            out["chgType"][b, 0, :c] = r["chgType"]
+            out["chgTime"][b, 0, :c] = r["chgTime"]
+        calls.append(B)
+        return out
+
+    monkeypatch.setattr(un, "untyped_sample_batch", fake_sample)
+    nwk = "(((a:1.0,b:1.0):0.5,(c:1.5)x:0.0):1.0,(d:0.7,e:0.2):1.3);"      # one single-child node
+    trait = dict(a="A", b="B", c="C", d="A", e="C")
+    t = un.MultiTypeTreeFromUntypedNewick(nwk, _Model(), trait, randomizer=Randomizer(3))
+    assert calls == [1, 1]                                   # retried once
+    assert t.getNodeCount() == 9 and list(t.taxa) == list("abcde")
+    assert [int(x) for x in t.nodeType[:5]] == [0, 1, 2, 0, 2]
+    assert np.all(t.height[:5] == 0.0) and t.height[8] == pytest.approx(2.5)
+    _check_typed_tree(t, 3)
+    t2 = un.MultiTypeTreeFromUntypedNewick(nwk, _Model(), trait, randomizer=Randomizer(3),
+                                           adjustTipHeights=False)
+    assert t2.height[:5] == pytest.approx([0.0, 0.0, 0.0, 0.5, 1.0])
+    _check_typed_tree(t2, 3)
+    back = mtt.MultiTypeTreeFromNewick(t2.getFlattenedNewick(), "type")
+    assert back.getTotalNumberOfChanges() == t2.getTotalNumberOfChanges()
+    assert np.allclose(np.sort(back.height), np.sort(t2.height), atol=1e-12)
+    with pytest.raises(ValueError, match="Trait set"):
+        un.MultiTypeTreeFromUntypedNewick(nwk, _Model(), None)
+    with pytest.raises(KeyError):
+        un.MultiTypeTreeFromUntypedNewick(nwk, _Model(), dict(a="A"))

@@ -1,5 +1,6 @@
 """Probe: typed trees of the untyped bench batch against the oracle, field by field."""
 import sys
+sys.path.insert(0, ".")
 import numpy as np
 import multitypetree_b200 as mtt
 from multitypetree_b200.uniformization import UniformizationModels
